@@ -1,0 +1,753 @@
+// oracle/oracle.hpp — CPU restatement of cpp.audio's rt.resynth analysis + sine-bank synthesis hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under cpp.audio_b200/ (the product) includes, links or runs this file.
+// It is used by tests/, by __graft_entry__.smoke() and by the cpu_baseline / --impl reference legs of bench.py.
+//
+// PARITY STATUS: the synthesis half restates in-tree reference code and is pinned by it; the FFT / window /
+// peak-interpolation arithmetic lives in the un-vendored sibling repo cpp.algorithms (include/public.h:13) and is
+// therefore "PARITY UNPINNED" — see oracle/SPEC.md (decisions S1..S9).
+//
+// All citations are path:line under /root/reference/.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <optional>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+namespace orc {
+
+constexpr double kPi = 3.141592653589793238462643383279502884;
+
+// ------------------------------------------------------------------------------------------------------------
+// FFT (the reference delegates to fft::Fastest in cpp.algorithms; call sites
+// source/rt.resynth.lib.periodicfft.cpp:214-234, :304-311; source/main.test_fft.cpp:78).
+// Forward transform, unscaled: X[k] = sum_n x[n] exp(-2 pi i k n / N).
+// ------------------------------------------------------------------------------------------------------------
+
+inline bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+template <class T>
+class ComplexFft {
+public:
+  explicit ComplexFft(int n) : n_(n) {
+    if (!is_pow2(n)) throw std::invalid_argument("fft size must be a power of two");
+    tw_.resize(std::max(1, n / 2));
+    for (int k = 0; k < n / 2; ++k) {
+      long double a = -2.0L * static_cast<long double>(kPi) * k / n;
+      tw_[k] = {static_cast<T>(std::cos(a)), static_cast<T>(std::sin(a))};
+    }
+    rev_.resize(n);
+    int bits = 0;
+    while ((1 << bits) < n) ++bits;
+    for (int i = 0; i < n; ++i) {
+      uint32_t r = 0;
+      for (int b = 0; b < bits; ++b)
+        if (i & (1 << b)) r |= 1u << (bits - 1 - b);
+      rev_[i] = r;
+    }
+  }
+  int size() const { return n_; }
+
+  // in-place, iterative radix-2 decimation in time
+  void forward(std::complex<T>* a) const {
+    for (int i = 0; i < n_; ++i) {
+      int j = static_cast<int>(rev_[i]);
+      if (i < j) std::swap(a[i], a[j]);
+    }
+    for (int len = 2; len <= n_; len <<= 1) {
+      int half = len >> 1;
+      int step = n_ / len;
+      for (int i = 0; i < n_; i += len) {
+        for (int j = 0; j < half; ++j) {
+          std::complex<T> w = tw_[j * step];
+          T xr = a[i + j + half].real(), xi = a[i + j + half].imag();
+          T tr = xr * w.real() - xi * w.imag();
+          T ti = xr * w.imag() + xi * w.real();
+          T ur = a[i + j].real(), ui = a[i + j].imag();
+          a[i + j] = {ur + tr, ui + ti};
+          a[i + j + half] = {ur - tr, ui - ti};
+        }
+      }
+    }
+  }
+
+private:
+  int n_;
+  std::vector<std::complex<T>> tw_;
+  std::vector<uint32_t> rev_;
+};
+
+// N real samples -> N/2+1 complex bins, through one N/2-point complex FFT and the usual untangling step.
+template <class T>
+class RealFft {
+public:
+  explicit RealFft(int n) : n_(n), half_(std::max(1, n / 2)), work_(std::max(1, n / 2)) {
+    if (!is_pow2(n) || n < 2) throw std::invalid_argument("real fft size must be a power of two >= 2");
+    tw_.resize(n / 2 + 1);
+    for (int k = 0; k <= n / 2; ++k) {
+      long double a = -2.0L * static_cast<long double>(kPi) * k / n;
+      tw_[k] = {static_cast<T>(std::cos(a)), static_cast<T>(std::sin(a))};
+    }
+  }
+  int size() const { return n_; }
+  int bins() const { return n_ / 2 + 1; }
+
+  void forward(const T* x, std::complex<T>* X) {
+    int h = n_ / 2;
+    for (int i = 0; i < h; ++i) work_[i] = {x[2 * i], x[2 * i + 1]};
+    half_.forward(work_.data());
+    for (int k = 0; k <= h; ++k) {
+      std::complex<T> zk = work_[k % h];
+      std::complex<T> zm = std::conj(work_[(h - k) % h]);
+      std::complex<T> even = (zk + zm) * static_cast<T>(0.5);
+      std::complex<T> odd = (zk - zm) * std::complex<T>(0, static_cast<T>(-0.5));
+      X[k] = even + tw_[k] * odd;
+    }
+  }
+
+private:
+  int n_;
+  ComplexFft<T> half_;
+  std::vector<std::complex<T>> work_;
+  std::vector<std::complex<T>> tw_;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Windows and spectrum (SPEC S1..S5; call sites source/rt.resynth.lib.periodicfft.cpp:273-311)
+// ------------------------------------------------------------------------------------------------------------
+
+enum class Window : int { Rectangular = 0, Gaussian = 1 };
+
+inline int fft_length_for(int n_samples, int zero_padding_factor) {  // S1
+  int64_t want = static_cast<int64_t>(n_samples) * zero_padding_factor;
+  int n = 1;
+  while (n < want) n <<= 1;
+  return n;
+}
+
+// S2 + S3: half window (index = distance from the centre), normalised so that the full symmetric window has mean 1.
+template <class T>
+std::vector<T> make_half_window(Window type, double sigma_factor, int half_size) {
+  std::vector<T> hw(half_size);
+  long double sum = 0;
+  for (int j = 0; j < half_size; ++j) {
+    long double v = 1;
+    if (type == Window::Gaussian) {
+      long double u = static_cast<long double>(sigma_factor) * (j + 0.5L) / half_size;
+      v = std::exp(-0.5L * u * u);
+    }
+    hw[j] = static_cast<T>(v);
+    sum += v;
+  }
+  long double scale = half_size / sum;  // mean over the full window == mean over the half window
+  for (auto& v : hw) v = static_cast<T>(v * scale);
+  return hw;
+}
+
+template <class T>
+inline T window_at(const std::vector<T>& hw, int n) {  // full window of length 2*hw.size()
+  int H = static_cast<int>(hw.size());
+  return n < H ? hw[H - 1 - n] : hw[n - H];
+}
+
+// Restates SqMagFftOperation<window,T> (source/rt.resynth.lib.periodicfft.cpp:251-325):
+// init_data(W) builds the normalised half window; operator() = findFrequenciesSqMag (window, zero pad, real FFT, |X|^2).
+template <class T>
+class SqMagOp {
+public:
+  using FPT = T;
+  SqMagOp(Window type, double sigma_factor) : type_(type), sigma_(sigma_factor) {}
+
+  bool init_data(int window_size) {
+    if (window_size % 2) throw std::invalid_argument("window size must be even");  // Assert at :274
+    int n = fft_length_for(window_size, 1);
+    if (!fft_ || fft_->size() != n) {
+      fft_.emplace(n);
+      signal_.assign(n, T(0));
+      bins_.assign(n / 2 + 1, {});
+      sqmag_.assign(n / 2 + 1, T(0));
+    }
+    if (static_cast<int>(half_window_.size()) != window_size / 2) {
+      half_window_ = make_half_window<T>(type_, sigma_, window_size / 2);
+      return true;  // :296 — caller zeroes its samples
+    }
+    return false;
+  }
+
+  template <class It>
+  void operator()(It begin, It end) {
+    int w = static_cast<int>(end - begin);
+    int n = fft_->size();
+    for (int i = 0; i < w; ++i) signal_[i] = static_cast<T>(begin[i]) * window_at(half_window_, i);
+    for (int i = w; i < n; ++i) signal_[i] = T(0);
+    fft_->forward(signal_.data(), bins_.data());
+    T scale = T(1) / static_cast<T>(w);  // S4
+    for (int k = 0; k <= n / 2; ++k) {   // S5
+      T re = bins_[k].real() * scale, im = bins_[k].imag() * scale;
+      sqmag_[k] = re * re + im * im;
+    }
+  }
+
+  const std::vector<T>& get_results() const { return sqmag_; }
+  int fft_length() const { return fft_ ? fft_->size() : 0; }
+
+private:
+  Window type_;
+  double sigma_;
+  std::optional<RealFft<T>> fft_;
+  std::vector<T> half_window_, signal_, sqmag_;
+  std::vector<std::complex<T>> bins_;
+};
+
+// Restates PeriodicFFT<Op> (source/rt.resynth.lib.periodicfft.cpp:13-181): sample-at-a-time feed into a window
+// buffer, operator fired when the buffer is full, then the overlap is shifted left by the stride.
+template <class Op>
+class PeriodicFft {
+public:
+  using FPT = typename Op::FPT;
+  using OnResult = std::function<void(int, const std::vector<FPT>&)>;
+
+  template <class... Args>
+  explicit PeriodicFft(Args&&... args) : op_(std::forward<Args>(args)...) {}
+
+  void set_lambdas(std::function<int()> get_window_size, std::function<int()> get_stride, OnResult on_result) {
+    get_window_size_ = std::move(get_window_size);
+    get_stride_ = std::move(get_stride);
+    on_result_ = std::move(on_result);
+    ignore_ = 0;
+    init_data();
+    reset_samples();
+  }
+
+  void feed(float sample) {  // :55-67
+    if (ignore_ > 0) {
+      --ignore_;
+      return;
+    }
+    samples_[end_] = sample;
+    ++end_;
+    if (end_ == window_) {
+      end_ = 0;
+      on_full_buffer();
+    }
+  }
+
+  void reset_samples() { samples_.assign(window_, FPT(0)); }
+  Op& op() { return op_; }
+
+private:
+  bool init_data() {  // :122-134
+    bool changed = false;
+    int w = get_window_size_();
+    if (w != window_) {
+      window_ = w;
+      changed = true;
+    }
+    return op_.init_data(window_) || changed;
+  }
+
+  void on_full_buffer() {  // :136-180
+    int stride = get_stride_();
+    op_(samples_.begin(), samples_.begin() + window_);
+    on_result_(stride, op_.get_results());
+    if (init_data()) reset_samples();
+    int overlap = window_ - stride;
+    if (overlap >= 0) {
+      for (; end_ < overlap; ++end_) samples_[end_] = samples_[end_ + stride];
+      ignore_ = 0;
+    } else {
+      ignore_ = -overlap;
+    }
+  }
+
+  Op op_;
+  std::vector<FPT> samples_;
+  int window_ = 0, end_ = 0, ignore_ = 0;
+  std::function<int()> get_window_size_, get_stride_;
+  OnResult on_result_;
+};
+
+inline int64_t num_frames(int64_t n_samples, int window, int hop) {
+  if (n_samples < window) return 0;
+  if (hop >= window) return 1 + (n_samples - window) / hop;  // ignore_frames path, same count
+  return 1 + (n_samples - window) / hop;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Peak extraction (SPEC S6; call site source/rt.resynth.lib.cpp:1592-1595)
+// ------------------------------------------------------------------------------------------------------------
+
+template <class T>
+struct FreqMag {
+  T freq;
+  T mag_db;
+  int bin;
+};
+
+template <class T>
+inline T sqmag_to_db(T s) {
+  T floor_v = std::is_same<T, float>::value ? T(1e-37) : T(1e-300);
+  return T(10) * std::log10(std::max(s, floor_v));
+}
+template <class T>
+inline T db_to_mag(T db) { return std::pow(T(10), db / T(20)); }
+
+template <class T>
+void extract_local_max_freqs_mags(T sample_rate, const T* sqmag, int fft_length, T min_db,
+                                  std::vector<FreqMag<T>>& out) {
+  out.clear();
+  int half = fft_length / 2;
+  T bin_to_hz = sample_rate / static_cast<T>(fft_length);
+  for (int k = 1; k <= half - 1; ++k) {
+    T c = sqmag[k];
+    if (!(c > sqmag[k - 1] && c > sqmag[k + 1])) continue;
+    T beta = sqmag_to_db(c);
+    if (!(beta >= min_db)) continue;
+    T alpha = sqmag_to_db(sqmag[k - 1]);
+    T gamma = sqmag_to_db(sqmag[k + 1]);
+    T denom = alpha - T(2) * beta + gamma;
+    T p = denom != T(0) ? T(0.5) * (alpha - gamma) / denom : T(0);
+    out.push_back({(static_cast<T>(k) + p) * bin_to_hz, beta - T(0.25) * (alpha - gamma) * p, k});
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Interpolation (SPEC S7; call sites include/audioelement.h:733-737,994-998,2774)
+// ------------------------------------------------------------------------------------------------------------
+
+enum Itp : int {
+  LINEAR = 0,
+  EASE_IN_QUAD = 1, EASE_OUT_QUAD = 2, EASE_INOUT_QUAD = 3,
+  EASE_IN_CUBIC = 4, EASE_OUT_CUBIC = 5, EASE_INOUT_CUBIC = 6,
+  EASE_IN_QUART = 7, EASE_OUT_QUART = 8, EASE_INOUT_QUART = 9,
+  EASE_IN_QUINT = 10, EASE_OUT_QUINT = 11, EASE_INOUT_QUINT = 12,
+};
+
+template <class T>
+T interpolate(int type, T t, T b, T c, T d) {
+  T u = t / d;
+  auto in_pow = [](T x, int p) { T r = 1; for (int i = 0; i < p; ++i) r *= x; return r; };
+  if (type == LINEAR) return b + c * u;
+  int fam = (type - 1) / 3;      // 0 quad .. 3 quint
+  int mode = (type - 1) % 3;     // 0 in, 1 out, 2 inout
+  int p = fam + 2;
+  T e;
+  if (mode == 0) e = in_pow(u, p);
+  else if (mode == 1) e = T(1) - in_pow(T(1) - u, p);
+  else {
+    if (u < T(0.5)) e = T(0.5) * in_pow(T(2) * u, p);
+    else e = T(1) - T(0.5) * in_pow(T(2) - T(2) * u, p);
+  }
+  return b + c * e;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Oscillator (include/audioelement.h:2366-2452) and aliasing gain (:466-483)
+// ------------------------------------------------------------------------------------------------------------
+
+template <class T>
+T freq_aliasing_multiplicator(T angle_increment) {
+  if (angle_increment == T(0)) return T(1);
+  T half_spp = T(1) / angle_increment;
+  if (half_spp < T(1)) return T(0);
+  if (half_spp > T(4)) return T(1);
+  return (half_spp - T(1)) * (T(1) / T(3));
+}
+
+template <class T>
+T freq_to_angle_increment(T freq, int sample_rate) { return 2 * freq / sample_rate; }  // include/sound.functions.h:58-62
+
+template <class T>
+T angle_increment_to_period_in_continuous_samples(T i) {  // include/sound.functions.h:70-76
+  if (i == T(0)) return T(1);
+  return T(2) / std::abs(i);
+}
+
+template <class T>
+class SineOsc {
+public:
+  void set_start_angle(T a) { cre_ = std::cos(static_cast<T>(kPi) * a); cim_ = std::sin(static_cast<T>(kPi) * a); }  // :2401
+  void set_angle_increments(T f) {                                                                                  // :2404
+    if (ai_ && *ai_ == f) return;
+    ai_ = f;
+    mre_ = std::cos(static_cast<T>(kPi) * f);
+    mim_ = std::sin(static_cast<T>(kPi) * f);
+    alias_ = freq_aliasing_multiplicator(f);
+  }
+  void synchronize_angles(const SineOsc& o) { cre_ = o.cre_; cim_ = o.cim_; }
+  void step() {                                                                                                     // :2413, :2443
+    T r = cre_ * mre_ - cim_ * mim_;
+    T i = cre_ * mim_ + cim_ * mre_;
+    T k = T(0.5) * (T(3) - (r * r + i * i));
+    cre_ = r * k;
+    cim_ = i * k;
+  }
+  T imag() const { return alias_ * cim_; }
+  T real() const { return alias_ * cre_; }
+  T angle_increments() const { return ai_ ? *ai_ : T(0); }
+
+private:
+  T cre_ = 1, cim_ = 0, mre_ = 1, mim_ = 0, alias_ = 1;
+  std::optional<T> ai_;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// AHDSR envelope (include/audioelement.h:314-335, :666-842, :855-1099), WaitForKeyRelease / AllowZeroAttack::No
+// ------------------------------------------------------------------------------------------------------------
+
+struct Ahdsr {
+  int32_t attack; int32_t attack_itp;
+  int32_t hold;
+  int32_t decay; int32_t decay_itp;
+  int32_t release; int32_t release_itp;
+  float sustain;
+};
+
+enum class EnvState : uint8_t { SoonKeyPressed, KeyPressed, KeyReleased, Done1, Done2 };
+constexpr int kFramesPerBuffer = 16;  // include/audioelement.h:3
+
+template <class T>
+class Envelope {
+public:
+  void set_ahdsr(const Ahdsr& s, int sample_rate) {  // :923-952
+    int32_t min_dt = sample_rate / 1000;            // :863-872
+    bool has_decay = s.sustain < 0.999999;
+    s_minus_one_ = has_decay ? std::min(std::max(s.sustain, 0.f), 1.f) - 1.f : 0.f;
+    A_ = std::max(s.attack, min_dt);
+    H_ = std::max(s.hold, 0);
+    D_ = has_decay ? std::max(s.decay, min_dt) : 0;
+    R_ = std::max(s.release, min_dt);
+    attack_itp_ = s.attack_itp; decay_itp_ = s.decay_itp; release_itp_ = s.release_itp;
+  }
+  void set_min_change_duration_samples(int n) { next_min_change_ = n; }  // :857-861
+  void forget_past_signals() { counter_ = 0; min_change_ = next_min_change_; }  // :694-700
+  bool try_acquire() { if (state_ != EnvState::Done2) return false; state_ = EnvState::SoonKeyPressed; return true; }
+
+  void on_key_pressed(int32_t delay) {  // :762-767
+    state_ = EnvState::KeyPressed;
+    counter_ = -delay;
+    release_delay_ = -1;
+    value_ = 0;
+  }
+  void on_key_released(int32_t delay) {  // :769-781
+    if (state_ != EnvState::KeyPressed) return;
+    if (counter_ + delay <= 0) state_ = EnvState::Done1;
+    else release_delay_ = delay;
+  }
+
+  void step() {  // :702-756
+    if (release_delay_ >= 0) {
+      if (release_delay_ == 0) start_released();
+      --release_delay_;
+    }
+    ++counter_;
+    switch (state_) {
+      case EnvState::KeyPressed:
+        if (counter_ < 1) return;
+        if (counter_ == 1) { ahd_ = 0; on_ahd_change(); }
+        value_ = step_pressed();
+        break;
+      case EnvState::KeyReleased:
+        value_ = interpolate<T>(release_itp_, static_cast<T>(counter_), top_, -top_, static_cast<T>(release_time()));
+        if (counter_ >= release_time()) { state_ = EnvState::Done1; counter_ = 0; value_ = 0; }
+        break;
+      case EnvState::Done1:
+        if (counter_ > kFramesPerBuffer) { state_ = EnvState::Done2; counter_ = 0; }
+        value_ = 0;
+        break;
+      case EnvState::Done2:
+      case EnvState::SoonKeyPressed:
+        value_ = 0;
+        break;
+    }
+  }
+
+  T value() const { return value_; }
+  EnvState state() const { return state_; }
+  bool rt_active() const { return state_ != EnvState::SoonKeyPressed && state_ != EnvState::Done2; }
+  bool finished() const { return state_ == EnvState::Done2; }
+
+private:
+  // ahd_: 0 attacking, 1 holding, 2 decaying, 3 none (sustain)
+  int32_t max_counter() const {  // :1066-1084
+    switch (ahd_) {
+      case 0: return std::max(min_change_, A_);
+      case 1: return H_;
+      default: return D_ == 0 ? 0 : std::max(min_change_, D_);
+    }
+  }
+  void on_ahd_change() {  // :1040-1053
+    ahd_counter_ = 0;
+    min_change_ = next_min_change_;
+    if (ahd_ == 3) return;
+    if (max_counter() == 0) step_ahd();
+  }
+  void step_ahd() {  // :1055-1064
+    if (ahd_counter_ < max_counter()) return;
+    ++ahd_;
+    on_ahd_change();
+  }
+  T step_pressed() {  // :960-1000
+    if (ahd_ != 3) { step_ahd(); ++ahd_counter_; }
+    if (ahd_ == 3) return T(1) + static_cast<T>(s_minus_one_);
+    T from, delta; int itp;
+    if (ahd_ == 0) { from = 0; delta = 1; itp = attack_itp_; }
+    else if (ahd_ == 1) { from = 1; delta = 0; itp = LINEAR; }
+    else { from = 1; delta = static_cast<T>(s_minus_one_); itp = decay_itp_; }
+    return interpolate<T>(itp, static_cast<T>(ahd_counter_), from, delta, static_cast<T>(max_counter()));
+  }
+  int32_t release_time() const { return std::max(min_change_, R_); }  // :1002-1004
+  void start_released() {  // :836-841
+    min_change_ = next_min_change_;
+    state_ = EnvState::KeyReleased;
+    top_ = value_;
+    counter_ = 0;
+  }
+
+  T value_ = 0, top_ = 0;
+  EnvState state_ = EnvState::Done2;
+  int32_t counter_ = 0, release_delay_ = -1;
+  int32_t min_change_ = 0, next_min_change_ = 0;
+  int32_t ahd_counter_ = 0, A_ = 100000, H_ = 0, D_ = 100000, R_ = 100000;
+  float s_minus_one_ = -0.5f;
+  int ahd_ = 3;
+  int attack_itp_ = LINEAR, decay_itp_ = LINEAR, release_itp_ = LINEAR;
+};
+
+// Enveloped<SineOscillatorAlgo, AHDSREnvelope> (include/audioelement.h:182-291)
+template <class T>
+class EnvelopedOsc {
+public:
+  void forget_past_signals() { env.forget_past_signals(); }
+  void set_angle_increments(T a) {  // :218-225
+    T period = angle_increment_to_period_in_continuous_samples(a);
+    env.set_min_change_duration_samples(static_cast<int>(0.5f + T(2.5) * period));
+    osc.set_angle_increments(a);
+  }
+  void step() { env.step(); osc.step(); }      // :197-200
+  T imag() const { return osc.imag() * env.value(); }  // :231
+  Envelope<T> env;
+  SineOsc<T> osc;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Harmonic bank = MultiEnveloped (include/audioelement.h:486-657) inside VolumeAdjusted (:1111-1265)
+// ------------------------------------------------------------------------------------------------------------
+
+struct HarmonicProps { float phase; float volume; };  // harmonicProperties_t (ext.; built at source/main.tune.cpp:1998-2001)
+
+// SPEC S8 one-pole low pass standing in for Filter<T,1,LOW_PASS,1>
+template <class T>
+struct OnePole {
+  T a = 1, y = 0;
+  void init_with_angle_increment(T inc) { a = T(1) - std::exp(-static_cast<T>(kPi) * inc); }
+  void set_initial_value(T v) { y = v; }
+  T feed(T x) { y += a * (x - y); return y; }
+};
+
+template <class T>
+class BankVoice {
+public:
+  void set_harmonics(const HarmonicProps* props, int n) {  // :507-521 (trailing inaudible harmonics dropped, :401-415)
+    int last = -1;
+    for (int i = n - 1; i >= 0; --i)
+      if (std::abs(props[i].volume) > 0.000001f) { last = i; break; }
+    harmonics_.assign(last + 1, {});
+    props_.assign(props, props + last + 1);
+  }
+  void set_ahdsr(const Ahdsr& s, int sr) { for (auto& h : harmonics_) h.env.set_ahdsr(s, sr); }
+  void forget_past_signals() { for (auto& h : harmonics_) h.forget_past_signals(); volume_.reset(); target_.reset(); }
+  void set_volume_target(T v) { target_ = v; }
+  void set_angle_increments(T a) {  // :614-619
+    for (size_t i = 0; i < harmonics_.size(); ++i) harmonics_[i].set_angle_increments(static_cast<T>(i + 1) * a);
+  }
+  void set_start_angle(T a) {  // :590-594
+    for (size_t i = 0; i < harmonics_.size(); ++i)
+      harmonics_[i].osc.set_start_angle(props_[i].phase + static_cast<T>(i + 1) * a);
+  }
+  void on_key_pressed(int32_t delay) { for (auto& h : harmonics_) h.env.on_key_pressed(delay); state_ = EnvState::KeyPressed; }
+  void on_key_released(int32_t delay) { for (auto& h : harmonics_) h.env.on_key_released(delay); }
+  bool try_acquire() { if (state_ != EnvState::Done2) return false; state_ = EnvState::SoonKeyPressed; return true; }
+  bool rt_active() const { return state_ != EnvState::SoonKeyPressed && state_ != EnvState::Done2; }
+
+  void step() {  // VolumeAdjusted::step :1195-1216 around MultiEnveloped::step :529-545
+    imag_ = 0;
+    bool go_on = false;
+    for (size_t i = 0; i < harmonics_.size(); ++i) {
+      auto& h = harmonics_[i];
+      h.step();
+      if (!h.env.finished()) go_on = true;
+      imag_ += h.imag() * props_[i].volume;
+    }
+    if (!go_on) state_ = EnvState::Done2;
+    T inc = std::min(max_filter_increment, harmonics_.empty() ? T(0) : std::abs(harmonics_[0].osc.angle_increments()));
+    if (!volume_) {
+      filter_inc_ = inc;
+      filter_.init_with_angle_increment(inc);
+      filter_.set_initial_value(*target_);
+    } else if (*volume_ != *target_ && filter_inc_ != inc) {
+      filter_inc_ = inc;
+      filter_.init_with_angle_increment(inc);
+    }
+    volume_ = filter_.feed(*target_);
+  }
+  T imag() const { return *volume_ * imag_; }  // :1126-1129
+
+  T max_filter_increment = std::numeric_limits<T>::max();
+
+private:
+  std::vector<EnvelopedOsc<T>> harmonics_;
+  std::vector<HarmonicProps> props_;
+  EnvState state_ = EnvState::Done2;
+  T imag_ = 0;
+  std::optional<T> volume_, target_;
+  T filter_inc_ = 0;
+  OnePole<T> filter_;
+};
+
+// stereo pan law (include/stereo.h:18-27)
+inline void stereo_gains(double pan, double& left, double& right) {
+  pan = std::max(-1., std::min(1., pan));
+  double angle = 0.25 * kPi * (pan + 1.);
+  left = std::cos(angle);
+  right = std::sin(angle);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Frequency glide (InterpolatedFreq, include/audioelement.h:2706-2817) + FreqCtrl_ (:3056-3155)
+// and the rt.resynth element StereoPanned<VolumeAdjusted<Enveloped<FreqCtrl_<Sine,InterpolatedFreq>,AHDSR>>>
+// (source/rt.resynth.lib.cpp:5-18)
+// ------------------------------------------------------------------------------------------------------------
+
+template <class T>
+class InterpolatedFreq {
+public:
+  void forget_past_signals() { f_result_.reset(); }
+  void setup(T duration, int itp) {  // :2739-2750
+    duration_ = duration; itp_ = itp; cur_ = 0;
+    if (f_result_) { from_ = *f_result_; C_ = prop_const(); }
+  }
+  void set_angle_increments(T inc) {  // :2752-2762
+    cur_ = 0; to_ = inc;
+    from_ = f_result_ ? *f_result_ : inc;
+    C_ = prop_const();
+  }
+  T step() {  // :2764-2788
+    if (f_result_ && *f_result_ == to_) return to_;
+    if (cur_ + T(.5f) > duration_) cur_ = duration_;
+    f_result_ = interpolate<T>(itp_, cur_, from_, to_ - from_, duration_);
+    if (cur_ < duration_) {
+      T f = from_ + (to_ - from_) * (cur_ + T(.5f)) / duration_;
+      cur_ += C_ * f;
+    }
+    return *f_result_;
+  }
+  T from() const { return from_; }
+
+private:
+  T prop_const() const { return (to_ == from_) ? T(1) : -std::log(from_ / to_) / (to_ - from_); }  // :2804-2816
+  T from_ = 0, to_ = 0, cur_ = 0, duration_ = 0, C_ = 1;
+  int itp_ = LINEAR;
+  std::optional<T> f_result_;
+};
+
+template <class T>
+class ResynthVoice {
+public:
+  // ResynthElementInitializer (source/rt.resynth.lib.cpp:96-118)
+  void initialize(const Ahdsr& a, int sample_rate, int stride, double pan) {
+    env_.set_ahdsr(a, sample_rate);
+    max_filter_increment_ = T(2) / static_cast<T>(stride);
+    ctrl_.setup(static_cast<T>(stride), LINEAR);
+    stereo_gains(pan, gl_, gr_);
+  }
+  void reinitialize(const Ahdsr& a, int sample_rate, int stride) {  // InitializationType::ExistingNote
+    env_.set_ahdsr(a, sample_rate);
+    max_filter_increment_ = T(2) / static_cast<T>(stride);
+    ctrl_.setup(static_cast<T>(stride), LINEAR);
+  }
+  void forget_past_signals() { env_.forget_past_signals(); ctrl_.forget_past_signals(); volume_.reset(); target_.reset(); }
+  void set_volume_target(T v) { target_ = v; }
+  void set_angle_increments(T a) {  // Enveloped :218-225 -> FreqCtrl_ :3103-3108
+    T period = angle_increment_to_period_in_continuous_samples(a);
+    env_.set_min_change_duration_samples(static_cast<int>(0.5f + T(2.5) * period));
+    ctrl_.set_angle_increments(a);
+  }
+  void set_start_angle(T a) { osc_.set_start_angle(a); }
+  void on_key_pressed(int32_t d) { env_.on_key_pressed(d); }
+  void on_key_released(int32_t d) { env_.on_key_released(d); }
+  bool try_acquire() { return env_.try_acquire(); }
+  bool rt_active() const { return env_.rt_active(); }
+  T angle_increments() const {  // FreqCtrl_::angleIncrements :3117-3124
+    T ai = osc_.angle_increments();
+    return ai != T(0) ? ai : ctrl_.from();
+  }
+  void step() {  // StereoPanned -> VolumeAdjusted::step -> Enveloped::step -> FreqCtrl_::step
+    env_.step();
+    osc_.set_angle_increments(ctrl_.step());
+    osc_.step();
+    T inc = std::min(max_filter_increment_, std::abs(angle_increments()));
+    if (!volume_) {
+      filter_inc_ = inc;
+      filter_.init_with_angle_increment(inc);
+      filter_.set_initial_value(*target_);
+    } else if (*volume_ != *target_ && filter_inc_ != inc) {
+      filter_inc_ = inc;
+      filter_.init_with_angle_increment(inc);
+    }
+    volume_ = filter_.feed(*target_);
+  }
+  T imag(int ch) const { return (ch == 0 ? gl_ : gr_) * (*volume_ * (osc_.imag() * env_.value())); }
+  T imag_mono() const { return *volume_ * (osc_.imag() * env_.value()); }
+
+private:
+  Envelope<T> env_;
+  SineOsc<T> osc_;
+  InterpolatedFreq<T> ctrl_;
+  std::optional<T> volume_, target_;
+  T filter_inc_ = 0, max_filter_increment_ = std::numeric_limits<T>::max();
+  OnePole<T> filter_;
+  double gl_ = 1, gr_ = 1;
+};
+
+// ImplCRTP::compute (include/gen.crtp.h:350-378): voice-major accumulation of n_frames <= 16 frames into an interleaved,
+// pre-zeroed double buffer (caller: SimpleAudioOutContext::step, include/simple_audio_context.h:69-112).
+template <class Voice>
+bool pool_compute_mono(std::vector<Voice>& voices, double* buffer, int n_frames, int n_out) {
+  bool silence = true;
+  for (auto& v : voices) {
+    if (!v.rt_active()) continue;
+    silence = false;
+    for (int i = 0; i < n_frames; ++i) {
+      v.step();
+      if (!v.rt_active()) break;
+      for (int j = 0; j < n_out; ++j) buffer[n_out * i + j] += v.imag();
+    }
+  }
+  return !silence;
+}
+
+template <class Voice>
+bool pool_compute_stereo(std::vector<Voice>& voices, double* buffer, int n_frames) {
+  bool silence = true;
+  for (auto& v : voices) {
+    if (!v.rt_active()) continue;
+    silence = false;
+    for (int i = 0; i < n_frames; ++i) {
+      v.step();
+      if (!v.rt_active()) break;
+      buffer[2 * i + 0] += v.imag(0);
+      buffer[2 * i + 1] += v.imag(1);
+    }
+  }
+  return !silence;
+}
+
+}  // namespace orc

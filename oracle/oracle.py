@@ -1,0 +1,172 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs. The product package (cpp.audio_b200/) never imports this module.
+Parity status: analysis arithmetic "parity unpinned" (oracle/SPEC.md), synthesis pinned by in-tree reference code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src_newer = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("oracle.hpp", "oracle_capi.cpp", "Makefile")
+    )
+    if force or src_newer:
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class Ahdsr(C.Structure):
+    """Mirror of audioelement::AHDSR (include/audioelement.h:314-335); itp values per oracle/SPEC.md S7."""
+
+    _fields_ = [
+        ("attack", C.c_int32), ("attack_itp", C.c_int32),
+        ("hold", C.c_int32),
+        ("decay", C.c_int32), ("decay_itp", C.c_int32),
+        ("release", C.c_int32), ("release_itp", C.c_int32),
+        ("sustain", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        p = C.c_void_p
+        L.orc_hardware_threads.restype = C.c_int
+        L.orc_rfft_f64.argtypes = [p, C.c_int, C.c_int64, p, C.c_int]
+        L.orc_rfft_f32.argtypes = [p, C.c_int, C.c_int64, p, C.c_int]
+        L.orc_num_frames.argtypes = [C.c_int64, C.c_int, C.c_int]
+        L.orc_num_frames.restype = C.c_int64
+        L.orc_fft_length_for.argtypes = [C.c_int, C.c_int]
+        L.orc_fft_length_for.restype = C.c_int
+        L.orc_window_f64.argtypes = [C.c_int, C.c_double, C.c_int, p]
+        L.orc_stft_analyze.argtypes = [p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       C.c_int, C.c_double, C.c_int, p, p, p, p, p, C.c_int]
+        L.orc_stft_analyze.restype = C.c_int64
+        L.orc_oscbank_render.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int, p, p, p, p, p, p, p, p, C.c_int64,
+                                         p, C.c_int, p, C.c_int]
+        L.orc_envelope_trace.argtypes = [p, C.c_int, C.c_double, C.c_int32, C.c_int64, C.c_int64, p, p]
+        L.orc_freq_aliasing_multiplicator.argtypes = [C.c_double]
+        L.orc_freq_aliasing_multiplicator.restype = C.c_double
+        L.orc_sine_trace.argtypes = [C.c_double, C.c_double, C.c_int64, p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def hardware_threads() -> int:
+    return int(lib().orc_hardware_threads())
+
+
+def rfft(x: np.ndarray, dtype=np.float64, threads: int = 1) -> np.ndarray:
+    """Forward real FFT of each row, unscaled. Returns complex array [batch, n/2+1]."""
+    x = np.ascontiguousarray(x, dtype=dtype)
+    batch, n = x.shape
+    out = np.empty((batch, n // 2 + 1, 2), dtype=dtype)
+    fn = lib().orc_rfft_f64 if dtype == np.float64 else lib().orc_rfft_f32
+    fn(_ptr(x), n, batch, _ptr(out), threads)
+    return out[..., 0] + 1j * out[..., 1]
+
+
+def num_frames(n_samples: int, window: int, hop: int) -> int:
+    return int(lib().orc_num_frames(n_samples, window, hop))
+
+
+def window(window_type: int, sigma_factor: float, size: int) -> np.ndarray:
+    out = np.empty(size, dtype=np.float64)
+    lib().orc_window_f64(window_type, float(sigma_factor), size, _ptr(out))
+    return out
+
+
+def stft_analyze(x: np.ndarray, window: int, hop: int, window_type: int = 1, sigma_factor: float = 4.0,
+                 sample_rate: int = 48000, min_db: float = -80.0, max_peaks: int = 200, want_sqmag: bool = True,
+                 want_peaks: bool = True, threads: int = 1):
+    """x: float32 [streams, samples] (or 1-D). Returns dict(frames, sqmag, peak_bin, peak_freq, peak_db, peak_count)."""
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+    streams, n = x.shape
+    frames = num_frames(n, window, hop)
+    n_fft = int(lib().orc_fft_length_for(window, 1))
+    bins = n_fft // 2 + 1
+    sqmag = np.zeros((streams, frames, bins), dtype=np.float64) if want_sqmag else None
+    pb = np.full((streams, frames, max_peaks), -1, dtype=np.int32) if want_peaks else None
+    pf = np.zeros((streams, frames, max_peaks), dtype=np.float64) if want_peaks else None
+    pd = np.zeros((streams, frames, max_peaks), dtype=np.float64) if want_peaks else None
+    pc = np.zeros((streams, frames), dtype=np.int32) if want_peaks else None
+    got = lib().orc_stft_analyze(_ptr(x), n, streams, n, window, hop, window_type, float(sigma_factor), sample_rate,
+                                 float(min_db), max_peaks, _ptr(sqmag), _ptr(pb), _ptr(pf), _ptr(pd), _ptr(pc), threads)
+    assert got == frames
+    return dict(frames=frames, n_fft=n_fft, sqmag=sqmag, peak_bin=pb, peak_freq=pf, peak_db=pd, peak_count=pc)
+
+
+def make_ahdsr(attack=0, hold=0, decay=0, release=0, sustain=1.0, attack_itp=0, decay_itp=0, release_itp=0) -> Ahdsr:
+    return Ahdsr(attack, attack_itp, hold, decay, decay_itp, release, release_itp, sustain)
+
+
+def oscbank_render(f0_hz, volume, partial_volume, partial_phase, n_samples: int, sample_rate: int = 48000, env=None,
+                   start_angle=None, key_delay=None, release_at=None, pan=None, mix: int = 0, threads: int = 1):
+    """Render harmonic-bank voices. partial_volume/phase: [voices, partials]. env: Ahdsr or list of Ahdsr per voice."""
+    f0 = np.ascontiguousarray(f0_hz, dtype=np.float32)
+    nv = f0.shape[0]
+    vol = np.ascontiguousarray(volume, dtype=np.float32)
+    pv = np.ascontiguousarray(partial_volume, dtype=np.float32)
+    pp = np.ascontiguousarray(partial_phase, dtype=np.float32)
+    npart = pv.shape[1]
+    if env is None:
+        env = make_ahdsr()
+    if isinstance(env, Ahdsr):
+        envs = (Ahdsr * 1)(env)
+        n_env = 1
+    else:
+        envs = (Ahdsr * len(env))(*env)
+        n_env = len(env)
+        assert n_env == nv
+    sa = None if start_angle is None else np.ascontiguousarray(start_angle, dtype=np.float32)
+    kd = None if key_delay is None else np.ascontiguousarray(key_delay, dtype=np.int32)
+    ra = None if release_at is None else np.ascontiguousarray(release_at, dtype=np.int64)
+    pn = None if pan is None else np.ascontiguousarray(pan, dtype=np.float32)
+    if mix == 0:
+        out = np.zeros((nv, n_samples), dtype=np.float64)
+    elif mix == 1:
+        out = np.zeros((n_samples, 2), dtype=np.float64)
+    else:
+        out = np.zeros((n_samples,), dtype=np.float64)
+    lib().orc_oscbank_render(nv, npart, n_samples, sample_rate, _ptr(f0), _ptr(vol), _ptr(sa), _ptr(kd), _ptr(ra),
+                             _ptr(pv), _ptr(pp), C.cast(envs, C.c_void_p), n_env, _ptr(pn), mix, _ptr(out), threads)
+    return out
+
+
+def envelope_trace(env: Ahdsr, n_steps: int, angle_increment: float, sample_rate: int = 48000, key_delay: int = 0,
+                   release_at: int = -1):
+    vals = np.zeros(n_steps, dtype=np.float64)
+    states = np.zeros(n_steps, dtype=np.int32)
+    lib().orc_envelope_trace(C.byref(env), sample_rate, float(angle_increment), key_delay, release_at, n_steps,
+                             _ptr(vals), _ptr(states))
+    return vals, states
+
+
+def freq_aliasing_multiplicator(ai: float) -> float:
+    return float(lib().orc_freq_aliasing_multiplicator(float(ai)))
+
+
+def sine_trace(start_angle: float, angle_increment: float, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.float64)
+    lib().orc_sine_trace(float(start_angle), float(angle_increment), n, _ptr(out))
+    return out
