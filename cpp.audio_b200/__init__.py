@@ -1,0 +1,23 @@
+"""cpp.audio_b200 — B200-native rt.resynth hot path (periodic-FFT analysis + sine-bank resynthesis).
+
+The directory name contains a dot, so it is loaded by path: `import __graft_entry__; pkg = __graft_entry__.load_package()`
+(module name `cpp_audio_b200`). The product is the C-ABI shared library `libcpp_audio_b200.so` built from `csrc/`; this
+Python layer only binds it with ctypes for tests and benchmarks, and uses torch for device memory, streams and
+torch.distributed. There is no CPU fallback: importing works without a GPU (so symbols can be checked), every compute
+call raises when the library or a B200 is missing.
+"""
+from ._capi import (  # noqa: F401
+    Ahdsr,
+    CaError,
+    Context,
+    OscBankDesc,
+    StftParams,
+    fft_length_for,
+    lib,
+    lib_path,
+    stft_num_frames,
+    version,
+    DECLARED_SYMBOLS,
+)
+from .analysis import SqMagAnalyzer, analyze_streams, rfft_batched  # noqa: F401
+from .synth import SineBank, render_bank  # noqa: F401

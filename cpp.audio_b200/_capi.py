@@ -1,0 +1,136 @@
+"""ctypes binding of include/cpp_audio_b200.h (one Python name per C entry point, same argument order)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libcpp_audio_b200.so")
+
+DECLARED_SYMBOLS = [
+    "ca_version", "ca_init", "ca_destroy", "ca_last_error", "ca_sm_count", "ca_kernel_launches", "ca_host_alloc",
+    "ca_host_free", "ca_rfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
+    "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
+    "ca_measure_fp32_peak",
+]
+
+
+class CaError(RuntimeError):
+    pass
+
+
+class StftParams(C.Structure):
+    _fields_ = [("window", C.c_int32), ("hop", C.c_int32), ("window_type", C.c_int32), ("sigma_factor", C.c_float),
+                ("sample_rate", C.c_int32), ("min_db", C.c_float), ("max_peaks", C.c_int32)]
+
+
+class Ahdsr(C.Structure):
+    _fields_ = [("attack", C.c_int32), ("attack_itp", C.c_int32), ("hold", C.c_int32), ("decay", C.c_int32),
+                ("decay_itp", C.c_int32), ("release", C.c_int32), ("release_itp", C.c_int32), ("sustain", C.c_float)]
+
+
+class OscBankDesc(C.Structure):
+    _fields_ = [("n_voices", C.c_int64), ("n_partials", C.c_int32), ("n_samples", C.c_int64), ("sample_rate", C.c_int32),
+                ("f0_hz", C.c_void_p), ("volume", C.c_void_p), ("start_angle", C.c_void_p), ("key_delay", C.c_void_p),
+                ("release_at", C.c_void_p), ("partial_volume", C.c_void_p), ("partial_phase", C.c_void_p),
+                ("env", C.c_void_p), ("n_env", C.c_int64), ("pan", C.c_void_p), ("mix", C.c_int32)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _LIB
+
+
+def lib():
+    """Load the shared library. Raises (loudly) if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise CaError(f"{_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    L = C.CDLL(_LIB)
+    p, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.ca_version.restype = C.c_char_p
+    L.ca_init.argtypes = [i32, C.POINTER(p)]
+    L.ca_destroy.argtypes = [p]
+    L.ca_destroy.restype = None
+    L.ca_last_error.argtypes = [p]
+    L.ca_last_error.restype = C.c_char_p
+    L.ca_sm_count.argtypes = [p]
+    L.ca_kernel_launches.argtypes = [p]
+    L.ca_kernel_launches.restype = i64
+    L.ca_host_alloc.argtypes = [C.c_size_t]
+    L.ca_host_alloc.restype = p
+    L.ca_host_free.argtypes = [p]
+    L.ca_host_free.restype = None
+    L.ca_rfft_batched.argtypes = [p, p, i32, i64, p, p]
+    L.ca_rfft_batched_host.argtypes = [p, p, i32, i64, p]
+    L.ca_fft_length_for.argtypes = [i32, i32]
+    L.ca_stft_num_frames.argtypes = [i64, i32, i32]
+    L.ca_stft_num_frames.restype = i64
+    L.ca_stft_plan.argtypes = [p, C.POINTER(StftParams)]
+    L.ca_stft_analyze.argtypes = [p, p, i64, i64, i64, p, i64, p, p, p, p, p]
+    L.ca_stft_analyze_host.argtypes = [p, p, i64, i64, i64, p, i64, p, p, p, p]
+    L.ca_oscbank_plan.argtypes = [p, i64, C.c_int32]
+    L.ca_oscbank_render.argtypes = [p, C.POINTER(OscBankDesc), p, p]
+    L.ca_oscbank_render_host.argtypes = [p, C.POINTER(OscBankDesc), p]
+    L.ca_measure_fp32_peak.argtypes = [p, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def version() -> str:
+    return lib().ca_version().decode()
+
+
+def fft_length_for(n: int, zpf: int = 1) -> int:
+    return int(lib().ca_fft_length_for(n, zpf))
+
+
+def stft_num_frames(n_samples: int, window: int, hop: int) -> int:
+    return int(lib().ca_stft_num_frames(n_samples, window, hop))
+
+
+class Context:
+    """One per GPU (ca_ctx). Not thread-safe, like the reference operators."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().ca_init(device, C.byref(self._h))
+        if rc != 0:
+            raise CaError(f"ca_init(device={device}) failed with {rc}: a B200 (sm_100) is required, there is no CPU fallback")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().ca_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise CaError(f"{what} failed ({rc}): {lib().ca_last_error(self._h).decode()}")
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib().ca_sm_count(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().ca_kernel_launches(self._h))
+
+    def measure_fp32_peak(self) -> float:
+        v = C.c_double()
+        self.check(lib().ca_measure_fp32_peak(self._h, C.byref(v)), "ca_measure_fp32_peak")
+        return v.value

@@ -1,0 +1,232 @@
+// capi.cu — the extern "C" layer declared in include/cpp_audio_b200.h: context, argument checks, host-buffer wrappers.
+#include <math.h>
+
+#include <new>
+
+#include "ctx.hpp"
+
+using namespace ca;
+
+extern "C" {
+
+const char* ca_version(void) { return "cpp.audio_b200 0.1 (sm_100a)"; }
+
+int ca_init(int device, ca_ctx** out) {
+  if (!out) return CA_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return CA_ERR_CUDA;
+  ca_ctx* ctx = new (std::nothrow) ca_ctx();
+  if (!ctx) return CA_ERR_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop{};
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return CA_ERR_CUDA;
+  }
+  if (prop.major != 10) {  // the kernels are built for sm_100a only; there is no fallback
+    delete ctx;
+    return CA_ERR_UNSUPPORTED;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return CA_ERR_CUDA;
+  }
+  *out = ctx;
+  return CA_OK;
+}
+
+void ca_destroy(ca_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  stft_release(ctx);
+  rfft_release(ctx);
+  oscbank_release(ctx);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char* ca_last_error(const ca_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+int ca_sm_count(const ca_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t ca_kernel_launches(const ca_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* ca_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void ca_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int ca_fft_length_for(int n_samples, int zero_padding_factor) {
+  long long want = static_cast<long long>(n_samples) * zero_padding_factor;
+  int n = 1;
+  while (n < want) n <<= 1;
+  return n;
+}
+
+int64_t ca_stft_num_frames(int64_t n_samples, int window, int hop) {
+  if (window <= 0 || hop <= 0 || n_samples < window) return 0;
+  return 1 + (n_samples - window) / hop;
+}
+
+int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, ca_stream stream) {
+  if (!ctx) return CA_ERR_INVALID;
+  return rfft_batched(ctx, d_in, n_fft, batch, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out) {
+  if (!ctx) return CA_ERR_INVALID;
+  if (!h_in || !h_out || batch < 0 || n_fft < 2) return fail(ctx, CA_ERR_INVALID, "ca_rfft_batched_host: bad argument");
+  const size_t in_bytes = sizeof(float) * static_cast<size_t>(batch) * n_fft;
+  const size_t out_bytes = sizeof(float) * 2 * static_cast<size_t>(batch) * (n_fft / 2 + 1);
+  int rc = ensure_scratch(ctx, 0, in_bytes);
+  if (rc) return rc;
+  rc = ensure_scratch(ctx, 1, out_bytes);
+  if (rc) return rc;
+  cudaStream_t s = ctx->own_stream;
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[0], h_in, in_bytes, cudaMemcpyHostToDevice, s));
+  rc = rfft_batched(ctx, static_cast<const float*>(ctx->d_scratch[0]), n_fft, batch, static_cast<float*>(ctx->d_scratch[1]), s);
+  if (rc) return rc;
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[1], out_bytes, cudaMemcpyDeviceToHost, s));
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  return CA_OK;
+}
+
+int ca_stft_plan(ca_ctx* ctx, const ca_stft_params* params) {
+  if (!ctx) return CA_ERR_INVALID;
+  return stft_plan(ctx, params);
+}
+
+int ca_stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                    float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
+                    int32_t* d_peak_count, ca_stream stream) {
+  if (!ctx) return CA_ERR_INVALID;
+  return stft_analyze(ctx, d_x, n_samples, n_streams, stream_stride, d_sqmag, sqmag_row_stride, d_peak_bin, d_peak_freq,
+                      d_peak_db, d_peak_count, static_cast<cudaStream_t>(stream));
+}
+
+int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                         float* h_sqmag, int64_t sqmag_row_stride, int32_t* h_peak_bin, float* h_peak_freq,
+                         float* h_peak_db, int32_t* h_peak_count) {
+  if (!ctx) return CA_ERR_INVALID;
+  if (!ctx->stft_planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze_host: call ca_stft_plan first");
+  if (!h_x || n_streams < 0 || n_samples < 0 || stream_stride < n_samples)
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze_host: bad input shape");
+  const bool any_peak = h_peak_bin || h_peak_freq || h_peak_db || h_peak_count;
+  if (any_peak && !(h_peak_bin && h_peak_freq && h_peak_db && h_peak_count))
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze_host: peak outputs must be all null or all non-null");
+  const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
+  const size_t rows = static_cast<size_t>(frames) * n_streams;
+  if (rows == 0) return CA_OK;
+  const size_t x_bytes = sizeof(float) * static_cast<size_t>(n_streams) * stream_stride;
+  const size_t sq_bytes = h_sqmag ? sizeof(float) * rows * sqmag_row_stride : 0;
+  const size_t pk_bytes = any_peak ? 4 * rows * ctx->stft.max_peaks : 0;
+  const size_t cnt_bytes = any_peak ? 4 * rows : 0;
+  int rc = ensure_scratch(ctx, 0, x_bytes);
+  if (!rc && sq_bytes) rc = ensure_scratch(ctx, 1, sq_bytes);
+  if (!rc && any_peak) rc = ensure_scratch(ctx, 2, pk_bytes ? pk_bytes : 4);
+  if (!rc && any_peak) rc = ensure_scratch(ctx, 3, pk_bytes ? pk_bytes : 4);
+  if (!rc && any_peak) rc = ensure_scratch(ctx, 4, pk_bytes ? pk_bytes : 4);
+  if (!rc && any_peak) rc = ensure_scratch(ctx, 5, cnt_bytes);
+  if (rc) return rc;
+  cudaStream_t s = ctx->own_stream;
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[0], h_x, x_bytes, cudaMemcpyHostToDevice, s));
+  rc = stft_analyze(ctx, static_cast<const float*>(ctx->d_scratch[0]), n_samples, n_streams, stream_stride,
+                    h_sqmag ? static_cast<float*>(ctx->d_scratch[1]) : nullptr, sqmag_row_stride,
+                    any_peak ? static_cast<int32_t*>(ctx->d_scratch[2]) : nullptr,
+                    any_peak ? static_cast<float*>(ctx->d_scratch[3]) : nullptr,
+                    any_peak ? static_cast<float*>(ctx->d_scratch[4]) : nullptr,
+                    any_peak ? static_cast<int32_t*>(ctx->d_scratch[5]) : nullptr, s);
+  if (rc) return rc;
+  if (h_sqmag) CA_CUDA_OK(ctx, cudaMemcpyAsync(h_sqmag, ctx->d_scratch[1], sq_bytes, cudaMemcpyDeviceToHost, s));
+  if (any_peak) {
+    if (pk_bytes) {
+      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_bin, ctx->d_scratch[2], pk_bytes, cudaMemcpyDeviceToHost, s));
+      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_freq, ctx->d_scratch[3], pk_bytes, cudaMemcpyDeviceToHost, s));
+      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_db, ctx->d_scratch[4], pk_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_count, ctx->d_scratch[5], cnt_bytes, cudaMemcpyDeviceToHost, s));
+  }
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  return CA_OK;
+}
+
+int ca_oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials) {
+  if (!ctx) return CA_ERR_INVALID;
+  return oscbank_plan(ctx, max_voices, max_partials);
+}
+
+int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca_stream stream) {
+  if (!ctx) return CA_ERR_INVALID;
+  return oscbank_render(ctx, desc, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_out) {
+  if (!ctx) return CA_ERR_INVALID;
+  if (!desc || !h_out) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: null argument");
+  const ca_oscbank_desc& h = *desc;
+  if (h.n_voices < 0 || h.n_partials < 1 || h.n_samples < 0 || !h.f0_hz || !h.volume || !h.partial_volume ||
+      !h.partial_phase || !h.env || (h.n_env != 1 && h.n_env != h.n_voices))
+    return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: bad descriptor");
+  if (h.n_voices == 0 || h.n_samples == 0) return CA_OK;
+  const size_t nv = static_cast<size_t>(h.n_voices), np = static_cast<size_t>(h.n_partials);
+  // one parameter block: f0 | volume | start_angle | pan | key_delay | release_at | pvol | pphase | env
+  size_t off = 0;
+  auto take = [&off](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 15) / 16 * 16;
+    return o;
+  };
+  const size_t o_f0 = take(4 * nv), o_vol = take(4 * nv), o_sa = take(4 * nv), o_pan = take(4 * nv), o_kd = take(4 * nv),
+               o_ra = take(8 * nv), o_pv = take(4 * nv * np), o_pp = take(4 * nv * np),
+               o_env = take(sizeof(ca_ahdsr) * static_cast<size_t>(h.n_env));
+  const size_t n_out = h.mix == CA_MIX_NONE ? nv * h.n_samples : static_cast<size_t>(h.n_samples) * (h.mix == CA_MIX_STEREO ? 2 : 1);
+  int rc = ensure_scratch(ctx, 6, off);
+  if (!rc) rc = ensure_scratch(ctx, 7, sizeof(float) * n_out);
+  if (rc) return rc;
+  cudaStream_t s = ctx->own_stream;
+  char* base = static_cast<char*>(ctx->d_scratch[6]);
+  auto up = [&](size_t o, const void* src, size_t bytes) -> cudaError_t {
+    return src ? cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+  };
+  CA_CUDA_OK(ctx, up(o_f0, h.f0_hz, 4 * nv));
+  CA_CUDA_OK(ctx, up(o_vol, h.volume, 4 * nv));
+  CA_CUDA_OK(ctx, up(o_sa, h.start_angle, 4 * nv));
+  CA_CUDA_OK(ctx, up(o_pan, h.pan, 4 * nv));
+  CA_CUDA_OK(ctx, up(o_kd, h.key_delay, 4 * nv));
+  CA_CUDA_OK(ctx, up(o_ra, h.release_at, 8 * nv));
+  CA_CUDA_OK(ctx, up(o_pv, h.partial_volume, 4 * nv * np));
+  CA_CUDA_OK(ctx, up(o_pp, h.partial_phase, 4 * nv * np));
+  CA_CUDA_OK(ctx, up(o_env, h.env, sizeof(ca_ahdsr) * static_cast<size_t>(h.n_env)));
+  ca_oscbank_desc d = h;
+  d.f0_hz = reinterpret_cast<const float*>(base + o_f0);
+  d.volume = reinterpret_cast<const float*>(base + o_vol);
+  d.start_angle = h.start_angle ? reinterpret_cast<const float*>(base + o_sa) : nullptr;
+  d.pan = h.pan ? reinterpret_cast<const float*>(base + o_pan) : nullptr;
+  d.key_delay = h.key_delay ? reinterpret_cast<const int32_t*>(base + o_kd) : nullptr;
+  d.release_at = h.release_at ? reinterpret_cast<const int64_t*>(base + o_ra) : nullptr;
+  d.partial_volume = reinterpret_cast<const float*>(base + o_pv);
+  d.partial_phase = reinterpret_cast<const float*>(base + o_pp);
+  d.env = reinterpret_cast<const ca_ahdsr*>(base + o_env);
+  if (h.n_voices > ctx->osc_max_voices || h.n_partials > ctx->osc_max_partials) {
+    rc = oscbank_plan(ctx, h.n_voices, h.n_partials);
+    if (rc) return rc;
+  }
+  rc = oscbank_render(ctx, &d, static_cast<float*>(ctx->d_scratch[7]), s);
+  if (rc) return rc;
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], sizeof(float) * n_out, cudaMemcpyDeviceToHost, s));
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  return CA_OK;
+}
+
+int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops) {
+  if (!ctx) return CA_ERR_INVALID;
+  return measure_fp32_peak(ctx, tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// ctx.hpp — the per-GPU context behind the C ABI (include/cpp_audio_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/cpp_audio_b200.h"
+
+struct ca_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int64_t launches = 0;
+  std::string last_error;
+  cudaStream_t own_stream = nullptr;  // used by the *_host entry points
+
+  // analysis plan
+  bool stft_planned = false;
+  ca_stft_params stft{};
+  int n_fft = 0;
+  float* d_window = nullptr;  // [n_fft] window, zero padded, pre-scaled (see stft.cu)
+  float thr_sq = 0.f;
+
+  // generic FFT scratch (twiddle tables, four-step buffers)
+  float2* d_fft_tw = nullptr;
+  int fft_tw_n = 0;
+  float2* d_fft_work = nullptr;
+  size_t fft_work_bytes = 0;
+
+  // synthesis plan
+  int64_t osc_max_voices = 0;
+  int32_t osc_max_partials = 0;
+  void* d_osc_partials = nullptr;  // PartialParams[max_voices][padded partials]
+  void* d_osc_voices = nullptr;    // VoiceParams[max_voices]
+
+  // scratch for the *_host entry points
+  void* d_scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace ca {
+
+inline int fail(ca_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+#define CA_CUDA_OK(ctx, expr)                                                                          \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return ca::fail((ctx), CA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+inline int ensure_scratch(ca_ctx* ctx, int slot, size_t bytes) {
+  if (ctx->scratch_bytes[slot] >= bytes) return CA_OK;
+  if (ctx->d_scratch[slot]) cudaFree(ctx->d_scratch[slot]);
+  ctx->d_scratch[slot] = nullptr;
+  ctx->scratch_bytes[slot] = 0;
+  CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_scratch[slot], bytes));
+  ctx->scratch_bytes[slot] = bytes;
+  return CA_OK;
+}
+
+// entry points implemented per kernel family
+int stft_plan(ca_ctx* ctx, const ca_stft_params* p);
+int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                 float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
+                 int32_t* d_peak_count, cudaStream_t stream);
+int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream);
+int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
+int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream);
+int measure_fp32_peak(ca_ctx* ctx, double* tflops);
+void stft_release(ca_ctx* ctx);
+void rfft_release(ca_ctx* ctx);
+void oscbank_release(ca_ctx* ctx);
+
+}  // namespace ca

@@ -1,0 +1,388 @@
+// stft.cu — K2: fused periodic-FFT analysis for 4096-point frames.
+//
+// One warp owns one frame from load to peak list; the only synchronisation is __syncwarp().
+//   load x[f*hop + n]*w[n]  (float2 per lane, coalesced; window table pre-scaled by 1/(2W))
+//   -> pack as 2048 complex z[n] = (x[2n], x[2n+1])
+//   -> lane n2 runs a 64-point in-register FFT over n1 (z[32*n1+n2])                      [stage 1]
+//   -> twiddle W_2048^(n2*k1), transpose through shared memory (64 x 33 float2 per warp)
+//   -> lane t runs two 32-point in-register FFTs, columns k1 = t and 64-t (lane 0: 32)   [stage 2]
+//      so that Z[k] and Z[2048-k] sit in the same lane and the real-FFT untangling needs no exchange;
+//      column k1 = 0 (bins 64*j) is a 32-point FFT across the lanes done with shuffles
+//   -> |X[k]|^2 written straight from registers to HBM (coalesced 128 B rows) and to the warp's shared buffer
+//   -> each lane scans 64 contiguous bins for strict local maxima above the threshold, a warp prefix sum orders
+//      them, parabolic interpolation on log-magnitudes gives (freq, dB).
+//
+// Restates PeriodicFFT<SqMagFftOperation<Window,T>> + extractLocalMaxFreqsMags for whole streams
+// (source/rt.resynth.lib.periodicfft.cpp:13-181,251-325; call site source/rt.resynth.lib.cpp:1592-1595);
+// the unpinned arithmetic follows oracle/SPEC.md S1-S6.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "ctx.hpp"
+
+namespace ca {
+
+namespace {
+
+constexpr int kN = 4096;         // real FFT length
+constexpr int kM = 2048;         // complex FFT length
+constexpr int kBins = kM + 1;
+constexpr int kExchStride = 33;  // float2 per row of the 64 x 32 transpose buffer (conflict-free both ways)
+constexpr int kExchFloat2 = 64 * kExchStride;
+constexpr int kTabRows = 21;
+
+struct StftArgs {
+  const float* x;
+  int64_t n_samples;
+  int64_t stream_stride;
+  int64_t frames_per_stream;
+  int64_t total_frames;
+  int32_t hop;
+  int32_t window;       // samples actually read per frame (<= 4096); the rest is zero padding
+  const float* win;     // [4096] window * 1/(2W), zero beyond `window`
+  float* sqmag;         // nullable
+  int64_t sqmag_row_stride;
+  int32_t* peak_bin;    // nullable
+  float* peak_freq;
+  float* peak_db;
+  int32_t* peak_count;
+  int32_t max_peaks;
+  float thr_sq;
+  float bin_to_hz;
+};
+
+__device__ __forceinline__ float2 cis_neg(float turns_times_two) {  // exp(-i*pi*arg)
+  float s, c;
+  sincospif(turns_times_two, &s, &c);
+  return make_float2(c, -s);
+}
+
+// sqmag of the pair (k, M-k) from Z[k] and Z[M-k]; wp = -i*W_N^k
+__device__ __forceinline__ void untangle(float2 zk, float2 zm, float2 wp, float& sq_k, float& sq_m) {
+  const float ex = zk.x + zm.x, ey = zk.y - zm.y;  // Z[k] + conj(Z[M-k])
+  const float dx = zk.x - zm.x, dy = zk.y + zm.y;  // Z[k] - conj(Z[M-k])
+  const float tx = fmaf(-dy, wp.y, dx * wp.x), ty = fmaf(dx, wp.y, dy * wp.x);
+  const float px = ex + tx, py = ey + ty, qx = ex - tx, qy = ey - ty;
+  sq_k = fmaf(px, px, py * py);
+  sq_m = fmaf(qx, qx, qy * qy);
+}
+
+template <int K2>
+__device__ __forceinline__ void post_pair(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float (&sA)[32],
+                                          float (&sB)[32]) {
+  constexpr float2 w64 = {Tw<64, K2>::re, Tw<64, K2>::im};
+  float2 wp;
+  if constexpr (K2 == 0) wp = wpbase;
+  else wp = cmul(wpbase, w64);
+  untangle(A[bitrev(K2, 5)], B[bitrev(31 - K2, 5)], wp, sA[K2], sB[31 - K2]);
+}
+template <int... K2>
+__device__ __forceinline__ void post_all(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float (&sA)[32],
+                                         float (&sB)[32], std::integer_sequence<int, K2...>) {
+  (post_pair<K2>(A, B, wpbase, sA, sB), ...);
+}
+
+// stage-1 twiddle + transposed store for output slot J (k1 = bitrev6(J))
+template <int J>
+__device__ __forceinline__ void tw_store(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8], float2* exch,
+                                         int lane) {
+  constexpr int k1 = bitrev(J, 6);
+  constexpr int a = k1 >> 3, b = k1 & 7;
+  float2 y = v[J];
+  if constexpr (a != 0 && b != 0) y = cmul(y, cmul(wa[a], wb[b]));
+  else if constexpr (a != 0) y = cmul(y, wa[a]);
+  else if constexpr (b != 0) y = cmul(y, wb[b]);
+  exch[k1 * kExchStride + lane] = y;
+}
+template <int... J>
+__device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8],
+                                             float2* exch, int lane, std::integer_sequence<int, J...>) {
+  (tw_store<J>(v, wa, wb, exch, lane), ...);
+}
+
+__device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
+
+template <int WARPS, bool kVec2>
+__global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_constant__ StftArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
+  float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < kTabRows * 32; i += WARPS * 32) {
+    const int r = i >> 5, l = i & 31;
+    float2 w;
+    if (r < 7) {
+      w = cis_neg(2.f * static_cast<float>(l * (r + 1)) / kM);  // W_2048^(l*b), b = r+1
+    } else if (r < 14) {
+      w = cis_neg(2.f * static_cast<float>(l * 8 * (r - 6)) / kM);  // W_2048^(l*8a), a = r-6
+    } else if (r < 19) {
+      const int d = 16 >> (r - 14);
+      w = cis_neg(static_cast<float>(l % d) / d);  // exp(-2 pi i (l%d)/(2d))
+    } else if (r == 19) {
+      const int k = 64 * static_cast<int>(__brev(static_cast<unsigned>(l)) >> 27);  // k = 64*brev5(l)
+      float s, c;
+      sincospif(2.f * static_cast<float>(k) / kN, &s, &c);
+      w = make_float2(-s, -c);  // -i * W_4096^k
+    } else {
+      const int col = l ? l : 32;
+      float s, c;
+      sincospif(2.f * static_cast<float>(col) / kN, &s, &c);
+      w = make_float2(-s, -c);
+    }
+    tab[i] = w;
+  }
+  __syncthreads();
+
+  float2* exch = exch_all + warp * kExchFloat2;
+  float* sq = reinterpret_cast<float*>(exch);
+  const int colA = lane ? lane : 32;
+  const int colB = lane ? 64 - lane : 32;
+  const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
+
+  for (int64_t f = static_cast<int64_t>(blockIdx.x) * WARPS + warp; f < p.total_frames;
+       f += static_cast<int64_t>(gridDim.x) * WARPS) {
+    const int64_t stream = f / p.frames_per_stream;
+    const int64_t fr = f - stream * p.frames_per_stream;
+    const float* xs = p.x + stream * p.stream_stride + fr * p.hop;
+
+    // ---- load + window: lane n2 takes z[32*n1 + n2] = (x[64*n1+2*n2], x[64*n1+2*n2+1]) ----
+    float2 v[64];
+#pragma unroll
+    for (int n1 = 0; n1 < 64; ++n1) {
+      const int idx = 64 * n1 + 2 * lane;
+      float2 s;
+      if (kVec2) {
+        s = (idx < p.window) ? ldg2(xs + idx) : make_float2(0.f, 0.f);
+      } else {
+        s.x = (idx < p.window) ? __ldg(xs + idx) : 0.f;
+        s.y = (idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f;
+      }
+      const float2 w = ldg2(p.win + idx);
+      v[n1] = make_float2(s.x * w.x, s.y * w.y);
+    }
+
+    // ---- stage 1: 64-point FFT over n1 ----
+    Dif<64, 64, 0>::run(v);
+    const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
+
+    {
+      float2 wa[8], wb[8];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        wb[i] = tab[(i - 1) * 32 + lane];
+        wa[i] = tab[(6 + i) * 32 + lane];
+      }
+      wa[0] = wb[0] = make_float2(1.f, 0.f);
+      tw_store_all(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
+    }
+    __syncwarp();
+
+    // ---- stage 2: two 32-point FFTs over n2 (columns colA, colB) ----
+    float2 A[32], B[32];
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      A[n2] = exch[colA * kExchStride + n2];
+      B[n2] = exch[colB * kExchStride + n2];
+    }
+    __syncwarp();  // exch is reused as the sqmag buffer below
+    Dif<32, 32, 0>::run(A);
+    Dif<32, 32, 0>::run(B);
+
+    // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
+    float2 u = c0;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const int d = 16 >> s;
+      const float ox = __shfl_xor_sync(0xffffffffu, u.x, d);
+      const float oy = __shfl_xor_sync(0xffffffffu, u.y, d);
+      if (lane & d) {
+        const float2 w = tab[(14 + s) * 32 + lane];
+        u = cmul(make_float2(ox - u.x, oy - u.y), w);
+      } else {
+        u = make_float2(u.x + ox, u.y + oy);
+      }
+    }
+    float sq0, sqM;
+    {
+      const int pk2 = (32 - k2c) & 31;
+      const int plane = static_cast<int>(__brev(static_cast<unsigned>(pk2)) >> 27);
+      const float mx = __shfl_sync(0xffffffffu, u.x, plane);
+      const float my = __shfl_sync(0xffffffffu, u.y, plane);
+      untangle(u, make_float2(mx, my), tab[19 * 32 + lane], sq0, sqM);
+    }
+
+    // ---- untangle the real FFT: bins k = colA + 64*k2 and 2048 - k ----
+    float sA[32], sB[32];
+    post_all(A, B, tab[20 * 32 + lane], sA, sB, std::make_integer_sequence<int, 32>{});
+
+    // ---- write |X|^2: HBM row (coalesced across lanes) and the warp's shared buffer (padded, conflict-free) ----
+    if (p.sqmag) {
+      float* row = p.sqmag + f * p.sqmag_row_stride;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        row[colA + 64 * k2] = sA[k2];
+        row[colB + 64 * k2] = sB[k2];
+      }
+      row[64 * k2c] = sq0;
+      if (lane == 0) row[kM] = sqM;
+    }
+    if (p.peak_count) {
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        sq[65 * k2 + colA] = sA[k2];
+        sq[65 * k2 + colB] = sB[k2];
+      }
+      sq[65 * k2c] = sq0;
+      if (lane == 0) sq[phys(kM)] = sqM;
+      __syncwarp();
+
+      // ---- peak scan: lane owns bins [64*lane, 64*lane+64) ----
+      const int base = 65 * lane;
+      uint64_t mask = 0;
+      float l = lane ? sq[base - 2] : 0.f;
+      float c = sq[base];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float r = sq[j == 63 ? base + 65 : base + j + 1];
+        const bool is_peak = (c > l) && (c > r) && (c >= p.thr_sq) && (j > 0 || lane > 0);
+        mask |= static_cast<uint64_t>(is_peak) << j;
+        l = c;
+        c = r;
+      }
+      const int cnt = __popcll(mask);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int slot = incl - cnt;
+      if (lane == 0) p.peak_count[f] = total;
+      const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
+      while (mask && slot < p.max_peaks) {
+        const int j = __ffsll(static_cast<long long>(mask)) - 1;
+        mask &= mask - 1;
+        const int k = 64 * lane + j;
+        const float fl = 1e-37f;
+        const float sa = fmaxf(sq[phys(k - 1)], fl), sb = fmaxf(sq[phys(k)], fl), sc = fmaxf(sq[phys(k + 1)], fl);
+        // dB differences from ratios (well conditioned): alpha-gamma and alpha-2beta+gamma, in log2 units
+        const float ra = sa / sb, rc = sc / sb;
+        const float num = log2f(sa / sc);
+        const float den = log2f(ra * rc);
+        const float pp = den != 0.f ? 0.5f * num / den : 0.f;
+        constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
+        const float beta = kDbPerLog2 * log2f(sb);
+        p.peak_bin[out_base + slot] = k;
+        p.peak_freq[out_base + slot] = (static_cast<float>(k) + pp) * p.bin_to_hz;
+        p.peak_db[out_base + slot] = beta - 0.25f * (kDbPerLog2 * num) * pp;
+        ++slot;
+      }
+      __syncwarp();  // the next frame overwrites the buffer
+    }
+  }
+}
+
+}  // namespace
+
+int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
+  if (!p || p->window < 2 || (p->window & 1) || p->hop < 1 || p->max_peaks < 0 || p->sample_rate <= 0)
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_plan: window must be even and >= 2, hop >= 1");
+  if (p->window_type != CA_WINDOW_RECTANGULAR && p->window_type != CA_WINDOW_GAUSSIAN)
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_plan: unknown window type");
+  const int n_fft = ca_fft_length_for(p->window, 1);
+  if (n_fft != kN)
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_plan: only windows with fft length 4096 (2048 < window <= 4096) are built");
+  // half window, normalised to mean 1 (oracle/SPEC.md S2,S3), then scaled by 1/W (S4) and by the 1/2 of the real-FFT
+  // untangling so that the kernel's |E+T|^2 is |X|^2 directly.
+  const int W = p->window, H = W / 2;
+  std::vector<double> hw(H);
+  long double sum = 0;
+  for (int j = 0; j < H; ++j) {
+    long double v = 1;
+    if (p->window_type == CA_WINDOW_GAUSSIAN) {
+      long double u = static_cast<long double>(p->sigma_factor) * (j + 0.5L) / H;
+      v = expl(-0.5L * u * u);
+    }
+    hw[j] = static_cast<double>(v);
+    sum += v;
+  }
+  const double norm = static_cast<double>(H / sum) * 0.5 / W;
+  std::vector<float> full(n_fft, 0.f);
+  for (int n = 0; n < W; ++n) full[n] = static_cast<float>((n < H ? hw[H - 1 - n] : hw[n - H]) * norm);
+  if (!ctx->d_window || ctx->n_fft != n_fft) {
+    if (ctx->d_window) cudaFree(ctx->d_window);
+    ctx->d_window = nullptr;
+    CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_window, sizeof(float) * n_fft));
+  }
+  CA_CUDA_OK(ctx, cudaMemcpy(ctx->d_window, full.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+  ctx->n_fft = n_fft;
+  ctx->stft = *p;
+  ctx->thr_sq = isinf(p->min_db) && p->min_db < 0 ? 0.f : static_cast<float>(pow(10.0, p->min_db / 10.0));
+  ctx->stft_planned = true;
+  return CA_OK;
+}
+
+void stft_release(ca_ctx* ctx) {
+  if (ctx->d_window) cudaFree(ctx->d_window);
+  ctx->d_window = nullptr;
+  ctx->stft_planned = false;
+}
+
+int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                 float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
+                 int32_t* d_peak_count, cudaStream_t stream) {
+  if (!ctx->stft_planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze: call ca_stft_plan first");
+  if (!d_x || n_streams < 0 || n_samples < 0 || stream_stride < n_samples)
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: bad input shape");
+  const bool any_peak = d_peak_bin || d_peak_freq || d_peak_db || d_peak_count;
+  if (any_peak && !(d_peak_bin && d_peak_freq && d_peak_db && d_peak_count))
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: peak outputs must be all null or all non-null");
+  if (d_sqmag && sqmag_row_stride < kBins) return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: sqmag_row_stride < n_fft/2+1");
+  const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
+  const int64_t total = frames * n_streams;
+  if (total == 0) return CA_OK;
+
+  StftArgs a{};
+  a.x = d_x;
+  a.n_samples = n_samples;
+  a.stream_stride = stream_stride;
+  a.frames_per_stream = frames;
+  a.total_frames = total;
+  a.hop = ctx->stft.hop;
+  a.window = ctx->stft.window;
+  a.win = ctx->d_window;
+  a.sqmag = d_sqmag;
+  a.sqmag_row_stride = sqmag_row_stride;
+  a.peak_bin = d_peak_bin;
+  a.peak_freq = d_peak_freq;
+  a.peak_db = d_peak_db;
+  a.peak_count = d_peak_count;
+  a.max_peaks = ctx->stft.max_peaks;
+  a.thr_sq = ctx->thr_sq;
+  a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / kN);
+
+  constexpr int WARPS = 4;
+  const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
+  const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
+                    (ctx->stft.window % 2 == 0);
+  auto kern = vec2 ? stft4096_kernel<WARPS, true> : stft4096_kernel<WARPS, false>;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = static_cast<int64_t>(ctx->sm_count) * per_sm;
+  const int64_t need = (total + WARPS - 1) / WARPS;
+  if (grid > need) grid = need;
+  kern<<<static_cast<unsigned>(grid), WARPS * 32, smem, stream>>>(a);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
+}  // namespace ca

@@ -1,0 +1,143 @@
+/* cpp_audio_b200.h — C ABI of the B200-native rt.resynth hot path (periodic-FFT analysis + sine-bank resynthesis).
+ *
+ * The reference (OlivierSohn/cpp.audio) has no FFI: its seams are C++ concepts. Each entry point below names the
+ * reference interface it stands in for (path:line under the reference tree). C++ adapters that present those
+ * concepts on top of this ABI live in cpp.audio_b200/host/.
+ *
+ * Conventions
+ *   - return 0 (CA_OK) or a negative ca_status; no exceptions cross the ABI; ca_last_error(ctx) gives the text.
+ *   - pointers named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers (pinned recommended).
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *   - no allocation happens in the device entry points after the matching ca_*_plan call (mirrors the reference's
+ *     "no dynamic allocation after setLambdas" rule, source/rt.resynth.lib.periodicfft.cpp:32).
+ *   - one ctx per GPU; a ctx is not thread-safe (the reference drives each operator from a single thread).
+ *   - there is NO CPU fallback: every entry point fails with CA_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CPP_AUDIO_B200_H
+#define CPP_AUDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ca_ctx ca_ctx;
+typedef void* ca_stream;
+
+enum ca_status {
+  CA_OK = 0,
+  CA_ERR_INVALID = -1,     /* bad argument */
+  CA_ERR_CUDA = -2,        /* CUDA runtime error (text in ca_last_error) */
+  CA_ERR_UNSUPPORTED = -3, /* shape outside what the kernels cover */
+  CA_ERR_NOT_PLANNED = -4, /* ca_*_plan was not called or is too small */
+  CA_ERR_NOMEM = -5
+};
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+const char* ca_version(void);
+int ca_init(int device, ca_ctx** ctx);
+void ca_destroy(ca_ctx* ctx);
+const char* ca_last_error(const ca_ctx* ctx);
+int ca_sm_count(const ca_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t ca_kernel_launches(const ca_ctx* ctx);
+/* pinned host memory for the *_host entry points */
+void* ca_host_alloc(size_t bytes);
+void ca_host_free(void* p);
+
+/* ---- K1: batched forward real FFT ------------------------------------------------------------------------------
+ * Stands in for fft::Algo_<Tag,T>::forward as used by FftOperation<T>::operator()
+ * (source/rt.resynth.lib.periodicfft.cpp:210-235) and forward_fft (source/main.test_fft.cpp:78).
+ * Unscaled: X[k] = sum_n x[n] exp(-2 pi i k n / n_fft). d_in [batch][n_fft] float, d_out [batch][n_fft/2+1] (re,im).
+ * n_fft: power of two, 2^10 .. 2^20. */
+int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, ca_stream stream);
+int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out);
+
+/* ---- K2: periodic-FFT analysis ----------------------------------------------------------------------------------
+ * Stands in for PeriodicFFT<SqMagFftOperation<Window,T>> (source/rt.resynth.lib.periodicfft.cpp:13-181, :251-325)
+ * followed by extractLocalMaxFreqsMags (call site source/rt.resynth.lib.cpp:1592-1595), for whole streams at once:
+ * frame f of a stream covers samples [f*hop, f*hop+window); frames = floor((n-window)/hop)+1. */
+enum ca_window { CA_WINDOW_RECTANGULAR = 0, CA_WINDOW_GAUSSIAN = 1 };
+
+typedef struct ca_stft_params {
+  int32_t window;       /* even (Assert at periodicfft.cpp:274) */
+  int32_t hop;          /* window_center_stride in frames, >= 1 */
+  int32_t window_type;  /* ca_window */
+  float sigma_factor;   /* Gaussian truncation, reference uses 4 (periodicfft.cpp:288) */
+  int32_t sample_rate;
+  float min_db;         /* peaks below this level are not reported; -INFINITY = none (reference behaviour) */
+  int32_t max_peaks;    /* capacity per frame; reference reserves 200 (rt.resynth.lib.cpp:1102) */
+} ca_stft_params;
+
+int ca_fft_length_for(int n_samples, int zero_padding_factor);
+int64_t ca_stft_num_frames(int64_t n_samples, int window, int hop);
+/* builds the window table on the device; the only allocating call of the analysis path */
+int ca_stft_plan(ca_ctx* ctx, const ca_stft_params* params);
+/* d_x [n_streams][stream_stride] (n_samples used per stream).
+ * d_sqmag (nullable) [n_streams*frames][sqmag_row_stride], row holds n_fft/2+1 values (sqmag_row_stride >= that).
+ * peaks (all nullable together): d_peak_bin/freq/db [n_streams*frames][max_peaks] ascending in frequency,
+ * d_peak_count [n_streams*frames] = number of peaks found (may exceed max_peaks; only the first max_peaks stored). */
+int ca_stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                    float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq,
+                    float* d_peak_db, int32_t* d_peak_count, ca_stream stream);
+/* same with host buffers: H2D of x, kernel, D2H of every non-null output, stream sync. Uses ctx scratch (grown on
+ * demand, reused across calls). */
+int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                         float* h_sqmag, int64_t sqmag_row_stride, int32_t* h_peak_bin, float* h_peak_freq,
+                         float* h_peak_db, int32_t* h_peak_count);
+
+/* ---- K3: sine oscillator bank ----------------------------------------------------------------------------------
+ * Stands in for ImplCRTP::compute (include/gen.crtp.h:350-378) over elements
+ * VolumeAdjusted<MultiEnveloped<SineOscillatorAlgo,AHDSREnvelope>> (include/audioelement.h:486-657, :1111-1265,
+ * :2366-2452), for whole notes at once instead of 16-frame blocks. */
+enum ca_itp { CA_ITP_LINEAR = 0 }; /* itp::LINEAR; the only easing the rt.resynth path uses (rt.resynth.lib.cpp:75-81) */
+
+typedef struct ca_ahdsr { /* audioelement::AHDSR, include/audioelement.h:314-335 (durations in samples) */
+  int32_t attack;
+  int32_t attack_itp;
+  int32_t hold;
+  int32_t decay;
+  int32_t decay_itp;
+  int32_t release;
+  int32_t release_itp;
+  float sustain;
+} ca_ahdsr;
+
+enum ca_mix { CA_MIX_NONE = 0, CA_MIX_STEREO = 1, CA_MIX_MONO = 2 };
+
+typedef struct ca_oscbank_desc {
+  int64_t n_voices;
+  int32_t n_partials;
+  int64_t n_samples;
+  int32_t sample_rate;
+  const float* f0_hz;          /* [voices] note frequency (Event::noteOn.frequency) */
+  const float* volume;         /* [voices] volume target = baseVolume*velocity (gen.crtp.h:425) */
+  const float* start_angle;    /* [voices] nullable; voice start angle in units of pi rad (setStartAngle) */
+  const int32_t* key_delay;    /* [voices] nullable; onKeyPressed(delay) */
+  const int64_t* release_at;   /* [voices] nullable; onKeyReleased(0) is applied before the step of this sample; <0 never */
+  const float* partial_volume; /* [voices][partials] harmonicProperties_t::volume */
+  const float* partial_phase;  /* [voices][partials] harmonicProperties_t::phase (units of pi rad) */
+  const ca_ahdsr* env;         /* [n_env] */
+  int64_t n_env;               /* 1 (shared) or n_voices */
+  const float* pan;            /* [voices] nullable, used by CA_MIX_STEREO (include/stereo.h:18-27) */
+  int32_t mix;                 /* ca_mix */
+} ca_oscbank_desc;
+
+/* sizes scratch for up to max_voices x max_partials; the only allocating call of the synthesis path */
+int ca_oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
+/* every pointer inside desc is a DEVICE pointer. d_out: CA_MIX_NONE [voices][samples]; CA_MIX_STEREO interleaved
+ * [samples][2]; CA_MIX_MONO [samples]. Mixed outputs are overwritten (zeroed first), not accumulated. */
+int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca_stream stream);
+/* every pointer inside desc is a HOST pointer; H2D of the note parameters, kernels, D2H of h_out, stream sync */
+int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_out);
+
+/* measured FP32 FMA throughput of this GPU in TFLOP/s (dependent-free FFMA chains, `ms` of work); used as the
+ * denominator of the synthesis roofline */
+int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPP_AUDIO_B200_H */

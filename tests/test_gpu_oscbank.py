@@ -1,0 +1,157 @@
+"""GPU parity of the oscillator bank (K3) against the CPU oracle (line-by-line restatement of the reference elements)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def T(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_render(pkg, ctx, b, n_samples, env, sr=48000, **kw):
+    tk = {k: T(v) for k, v in kw.items() if k in ("start_angle", "key_delay", "release_at", "pan")}
+    mix = kw.get("mix", 0)
+    out = pkg.render_bank(ctx, n_samples, T(b["f0_hz"]), T(b["volume"]), T(b["partial_volume"]), T(b["partial_phase"]), env,
+                          sample_rate=sr, mix=mix, **tk)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def default_env(pkg):
+    return pkg.Ahdsr(0, 0, 0, 0, 0, 0, 0, 1.0)  # rt.resynth defaults, source/rt.resynth.lib.cpp:957-961
+
+
+def orc_env(orc, e):
+    return orc.make_ahdsr(e.attack, e.hold, e.decay, e.release, e.sustain)
+
+
+def test_small_bank_default_envelope(pkg, orc, ctx, wl):
+    b = wl.c3_bank(8, 64)
+    n = 20000
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    err = np.abs(out - ref).max()
+    assert err < TOL * 0.1, err  # volume is 0.1: hold the bar on the normalised signal
+
+
+def test_single_partial_closed_form(pkg, ctx):
+    # one voice, one partial, attack 48 samples at 1 kHz: y[n] = 0.1*env*sin(pi*(a0+(n+1)ai)), ai = float32(2f/sr)
+    f0 = np.array([1000.0], np.float32)
+    b = dict(f0_hz=f0, volume=np.array([0.1], np.float32), partial_volume=np.ones((1, 1), np.float32),
+             partial_phase=np.array([[0.25]], np.float32))
+    n = 100000
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))[0]
+    ai = float(np.float32(2) * f0[0] / np.float32(48000))
+    k = np.arange(n)
+    env = np.minimum(1.0, (k + 1) / 120.0)  # min change = int(0.5 + 2.5 * 48) = 120 samples > 48
+    ref = 0.1 * env * np.sin(np.pi * (0.25 + (k + 1) * ai))
+    assert np.abs(out - ref).max() < TOL * 0.1
+
+
+def test_aliasing_fade_and_nyquist(pkg, orc, ctx):
+    # partials between sr/8 and sr/2 are attenuated, above sr/2 silent (include/audioelement.h:466-483)
+    b = dict(f0_hz=np.array([3000.0, 7000.0], np.float32), volume=np.array([0.1, 0.1], np.float32),
+             partial_volume=np.ones((2, 8), np.float32) / 8, partial_phase=np.zeros((2, 8), np.float32))
+    n = 6000
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    assert np.abs(out - ref).max() < TOL * 0.1
+
+
+def test_full_ahdsr_with_release(pkg, orc, ctx, wl):
+    b = wl.c3_bank(6, 16)
+    n = 30000
+    e = pkg.Ahdsr(300, 0, 200, 500, 0, 2000, 0, 0.6)
+    rel = np.array([9000, 100, 15000, -1, 29990, 400], np.int64)
+    kd = np.array([0, 50, 1000, 0, 7, 500], np.int32)
+    sa = np.array([0.0, 0.3, -0.7, 0.9, 0.1, 0.0], np.float32)
+    out = gpu_render(pkg, ctx, b, n, e, release_at=rel, key_delay=kd, start_angle=sa)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
+                             release_at=rel, key_delay=kd, start_angle=sa)
+    assert np.abs(out - ref).max() < TOL * 0.1
+    # voice 5 is released before its key delay elapsed: the note is skipped (audioelement.h:774-777)
+    assert np.abs(out[5]).max() == 0.0
+
+
+def test_per_voice_envelopes_and_odd_sizes(pkg, orc, ctx, wl):
+    b = wl.c3_bank(5, 7)
+    n = 5001
+    envs = [pkg.Ahdsr(10 * (i + 1), 0, 5 * i, 100 * i, 0, 50, 0, 1.0 - 0.1 * i) for i in range(5)]
+    out = gpu_render(pkg, ctx, b, n, envs)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n,
+                             env=[orc_env(orc, e) for e in envs])
+    assert np.abs(out - ref).max() < TOL * 0.1
+
+
+def test_inaudible_trailing_harmonics_dropped(pkg, orc, ctx):
+    pv = np.array([[0.5, 0.0, 0.25, 1e-7, 0.0, 5e-7]], np.float32)
+    b = dict(f0_hz=np.array([440.0], np.float32), volume=np.array([0.1], np.float32), partial_volume=pv,
+             partial_phase=np.zeros((1, 6), np.float32))
+    out = gpu_render(pkg, ctx, b, 4000, default_env(pkg))
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], pv, b["partial_phase"], 4000)
+    assert np.abs(out - ref).max() < 1e-7
+
+
+@pytest.mark.parametrize("mix", [1, 2])
+def test_mix_modes(pkg, orc, ctx, wl, mix):
+    b = wl.c3_bank(40, 32)
+    n = 9000
+    pan = np.linspace(-1, 1, 40).astype(np.float32)
+    rel = np.full(40, 6000, np.int64)
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg), pan=pan, release_at=rel, mix=mix)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, pan=pan, release_at=rel,
+                             mix=mix)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() < TOL * 0.1 * 10  # 40 voices of volume 0.1 on one bus
+
+
+def test_long_note_phase_stays_exact(pkg, ctx):
+    """10 s note (BASELINE config 3 length): fp32 must not drift — compare the last second with the closed form."""
+    f0 = np.array([97.3, 3520.1], np.float32)
+    b = dict(f0_hz=f0, volume=np.array([0.1, 0.1], np.float32), partial_volume=np.ones((2, 1), np.float32),
+             partial_phase=np.array([[0.1], [-0.4]], np.float32))
+    n = 480000
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))
+    k = np.arange(n - 48000, n)
+    for v in range(2):
+        ai = float(np.float32(2) * f0[v] / np.float32(48000))
+        ref = 0.1 * np.sin(np.pi * (float(b["partial_phase"][v, 0]) + (k + 1) * ai))
+        assert np.abs(out[v, -48000:] - ref).max() < TOL * 0.1
+
+
+def test_c3_full_size_properties(pkg, orc, ctx, wl):
+    """BASELINE config 3 at full size (1024 x 64 x 480000): spot-check voices against the oracle, energy for the rest."""
+    b = wl.c3_bank()
+    n = 480000
+    out = pkg.render_bank(ctx, n, T(b["f0_hz"]), T(b["volume"]), T(b["partial_volume"]), T(b["partial_phase"]),
+                          default_env(pkg))
+    torch.cuda.synchronize()
+    sel = [0, 511, 1023]
+    ref = orc.oscbank_render(b["f0_hz"][sel], b["volume"][sel], b["partial_volume"][sel], b["partial_phase"][sel], n)
+    got = out[sel].cpu().numpy()
+    assert np.abs(got - ref).max() < TOL * 0.1
+    # every voice: steady-state RMS = 0.1 * sqrt(sum (vol_p g_p)^2 / 2)
+    rms = out[:, 48000:].square().mean(dim=1).sqrt().cpu().numpy()
+    ai = (np.float32(2) * b["f0_hz"] / np.float32(48000)).astype(np.float64)[:, None] * np.arange(1, 65)[None, :]
+    g = np.clip((1.0 / ai - 1.0) / 3.0, 0.0, 1.0)
+    expect = 0.1 * np.sqrt(((b["partial_volume"] * g) ** 2).sum(axis=1) / 2)
+    assert np.abs(rms - expect).max() < 2e-4
+
+
+def test_host_entry_point(pkg, orc, ctx, wl):
+    import ctypes as C
+    b = wl.c3_bank(3, 16)
+    n = 7000
+    env = (pkg.Ahdsr * 1)(default_env(pkg))
+    out = np.empty((3, n), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p).value
+    d = pkg.OscBankDesc(3, 16, n, 48000, vp(b["f0_hz"]), vp(b["volume"]), None, None, None, vp(b["partial_volume"]),
+                        vp(b["partial_phase"]), C.cast(env, C.c_void_p).value, 1, None, 0)
+    rc = pkg.lib().ca_oscbank_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    assert np.abs(out - ref).max() < TOL * 0.1

@@ -1,0 +1,56 @@
+"""GPU parity of the batched real FFT (K1) against the CPU oracle (and numpy as an independent anchor)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_rfft(pkg, ctx, x):
+    out = pkg.rfft_batched(ctx, torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_c1_1024_batch_4096(pkg, orc, ctx, wl):
+    x = wl.c1_frames()
+    X = gpu_rfft(pkg, ctx, x)
+    ref = orc.rfft(x.astype(np.float64))
+    # normalised: divide by N/2 so a full-scale sine has magnitude 1
+    err = np.abs(X - ref).max() / (x.shape[1] / 2)
+    assert err < 1e-5, err
+    assert np.abs(ref - np.fft.rfft(x.astype(np.float64), axis=1)).max() < 1e-9
+
+
+@pytest.mark.parametrize("p", [10, 11, 12, 13, 14, 15])
+def test_sizes_in_shared_memory(pkg, orc, ctx, p):
+    n = 1 << p
+    rng = np.random.default_rng(5000 + p)
+    x = rng.uniform(-1, 1, (37, n)).astype(np.float32)
+    X = gpu_rfft(pkg, ctx, x)
+    ref = orc.rfft(x.astype(np.float64))
+    err = np.abs(X - ref).max() / np.sqrt(n)  # white noise: bins scale like sqrt(N)
+    assert err < 1e-5, (p, err)
+
+
+def test_linearity_and_impulse(pkg, ctx):
+    n = 4096
+    x = np.zeros((3, n), np.float32)
+    x[0, 0] = 1.0      # impulse -> flat spectrum of ones
+    x[1, 1] = 1.0      # delayed impulse -> exp(-2 pi i k / n)
+    x[2, :] = 1.0      # DC
+    X = gpu_rfft(pkg, ctx, x)
+    k = np.arange(n // 2 + 1)
+    assert np.abs(X[0] - 1).max() < 1e-6
+    assert np.abs(X[1] - np.exp(-2j * np.pi * k / n)).max() < 1e-6
+    assert abs(X[2, 0] - n) < 1e-2 and np.abs(X[2, 1:]).max() < 1e-3
+
+
+def test_batch_edge_cases(pkg, ctx):
+    x = np.random.default_rng(0).uniform(-1, 1, (1, 1024)).astype(np.float32)
+    X = gpu_rfft(pkg, ctx, x)
+    assert np.abs(X - np.fft.rfft(x.astype(np.float64), axis=1)).max() < 1e-3
+    with pytest.raises(pkg.CaError):
+        pkg.rfft_batched(ctx, torch.zeros((2, 512), device="cuda"))
+    with pytest.raises(pkg.CaError):
+        pkg.rfft_batched(ctx, torch.zeros((2, 3000), device="cuda"))
