@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native rt.resynth hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on the host cores
+
+Headline metric (BASELINE.json): STFT frames/s at 4096 points. A step = one pass of the fused analysis kernel
+(window -> real FFT -> |X|^2 -> peak extraction) over a batch of `streams_per_gpu` independent 60 s / 48 kHz streams
+(BASELINE config 2 per stream, the 32-streams-per-GPU sharding of config 4), inputs resident in HBM. `e2e` is the same
+metric through the host-buffer C-ABI entry point (pinned host input, peak lists copied back). `extra.synthesis` carries
+the second half of the metric (oscillator-bank samples/s, BASELINE config 3). One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+SR, WINDOW, HOP, NFFT = 48000, 4096, 256, 4096
+SECONDS = 60.0
+MAX_PEAKS = 32
+MIN_DB = -80.0
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_analysis_rate(orc, wl, threads: int, streams: int, seconds: float):
+    """frames/s of the CPU oracle (the reference's structure: per-sample feed, double precision, one FFT per hop) over
+    `streams` independent streams of `seconds` each, `threads` host threads."""
+    x = wl.tiled_streams(min(streams, 8), seconds)
+    reps = (streams + x.shape[0] - 1) // x.shape[0]
+    x = np.ascontiguousarray(np.tile(x, (reps, 1))[:streams])
+    t0 = time.perf_counter()
+    r = orc.stft_analyze(x, WINDOW, HOP, sample_rate=SR, min_db=MIN_DB, max_peaks=MAX_PEAKS, want_sqmag=False, threads=threads)
+    dt = time.perf_counter() - t0
+    return streams * r["frames"] / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    orc = graft.load_oracle()
+    graft.load_package()
+    import cpp_audio_b200.workloads as wl
+    cores = orc.hardware_threads()
+    streams = max(1, cores)
+    seconds = 20.0
+    for _ in range(args.warmup):
+        cpu_analysis_rate(orc, wl, cores, streams, 2.0)
+    t_total, frames_total = 0.0, 0
+    for _ in range(args.steps):
+        rate, dt = cpu_analysis_rate(orc, wl, cores, streams, seconds)
+        t_total += dt
+        frames_total += rate * dt
+    value = frames_total / t_total
+    sample = f"{streams} streams x {seconds:.0f} s per step ({int(frames_total / args.steps)} frames), {cores} threads"
+    line = {
+        "impl": "reference", "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: rt.resynth periodic-FFT analysis, 48 kHz harmonic tone, window 4096, hop 256, Gaussian "
+                               "window, peak extraction (CPU oracle port of the reference, bounded sample)",
+                   "window": WINDOW, "hop": HOP, "n_fft": NFFT, "max_peaks": MAX_PEAKS, "min_db": MIN_DB},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = graft.load_package()
+    import cpp_audio_b200.workloads as wl
+    ctx = pkg.Context(local_rank)
+    S = args.streams_per_gpu
+    n_samples = int(round(SECONDS * SR))
+
+    # ---- inputs: S streams per rank (weak scaling), resident in HBM before the timed region ----
+    x_host_np = wl.tiled_streams(S, SECONDS)
+    x_pinned = torch.from_numpy(x_host_np).pin_memory()
+    x = x_pinned.to(dev)
+    an = pkg.SqMagAnalyzer(ctx, WINDOW, HOP, sample_rate=SR, min_db=MIN_DB, max_peaks=MAX_PEAKS)
+    frames = an.num_frames(n_samples)
+    rows = S * frames
+    out = an.allocate(S, n_samples, dev)
+
+    def step():
+        an(x, out)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    launches0 = ctx.kernel_launches
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    launches_warm = ctx.kernel_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    t_end.record()
+    sync_all()
+    clocks = sampler.stop()
+    launches_timed = ctx.kernel_launches - launches_warm
+    total_ms = t_start.elapsed_time(t_end)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * rows * args.steps / (total_ms * 1e-3)
+
+    # ---- sanity on the timed outputs (cheap, outside the timed region): 16 partials per frame ----
+    cnt = out["peak_count"]
+    assert int(cnt.min()) == 16 and int(cnt.max()) == 16, "unexpected peak counts: the timed kernel did not do the work"
+
+    # ---- end to end through the host-buffer C ABI: pinned x -> H2D -> kernel -> D2H peak lists ----
+    P = MAX_PEAKS
+    h_bin = torch.empty((rows, P), dtype=torch.int32).pin_memory()
+    h_freq = torch.empty((rows, P), dtype=torch.float32).pin_memory()
+    h_db = torch.empty((rows, P), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((rows,), dtype=torch.int32).pin_memory()
+    L = pkg.lib()
+
+    def e2e_step():
+        ctx.check(L.ca_stft_analyze_host(ctx.handle, x_pinned.data_ptr(), n_samples, S, n_samples, None, 0, h_bin.data_ptr(),
+                                         h_freq.data_ptr(), h_db.data_ptr(), h_cnt.data_ptr()), "ca_stft_analyze_host")
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * rows * e2e_steps / e2e_s
+    assert int(h_cnt.min()) == 16 and int(h_cnt.max()) == 16
+    h2d = x_pinned.numel() * 4
+    d2h = (h_bin.numel() + h_freq.numel() + h_db.numel() + h_cnt.numel()) * 4
+
+    # ---- final gather of the peak lists over NVLink (reported separately) ----
+    gather_ms = None
+    if world > 1:
+        payload = torch.cat([out["peak_freq"][:, :16].reshape(-1), out["peak_db"][:, :16].reshape(-1)])
+        bufs = [torch.empty_like(payload) for _ in range(world)]
+        dist.all_gather(bufs, payload)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather(bufs, payload)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gather_ms = g0.elapsed_time(g1)
+
+    # ---- synthesis half of the metric: BASELINE config 3 (1024 voices x 64 partials x 10 s) per rank ----
+    extra = {}
+    if not args.skip_synth:
+        b = wl.c3_bank(args.voices, 64)
+        tt = {k: torch.from_numpy(v).to(dev) for k, v in b.items()}
+        ns = int(round(args.synth_seconds * SR))
+        bank = pkg.SineBank(ctx, args.voices, 64, SR)
+        env = pkg.Ahdsr(0, 0, 0, 0, 0, 0, 0, 1.0)
+        sout = torch.empty((args.voices, ns), dtype=torch.float32, device=dev)
+
+        def synth_step():
+            bank.render(ns, tt["f0_hz"], tt["volume"], tt["partial_volume"], tt["partial_phase"], env, out=sout)
+
+        for _ in range(3):
+            synth_step()
+        sync_all()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        s0.record()
+        for _ in range(reps):
+            synth_step()
+        s1.record()
+        sync_all()
+        sms = s0.elapsed_time(s1) / reps
+        if world > 1:
+            t = torch.tensor([sms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms = float(t.item())
+        voice_samples = world * args.voices * ns / (sms * 1e-3)
+        fp32_peak = ctx.measure_fp32_peak()
+        part = voice_samples * 64
+        extra["synthesis"] = {
+            "workload": f"C3: {args.voices} voices x 64 partials x {args.synth_seconds:g} s @48 kHz per GPU, per-voice float32 output",
+            "voice_samples_per_s": voice_samples, "partial_samples_per_s": part, "ms_per_render": sms,
+            "fp32_peak_tflops_measured": fp32_peak,
+            "fp32_frac_official_8flop": part * 8 / world / 1e12 / fp32_peak,
+            "fp32_frac_executed_4flop": part * 4 / world / 1e12 / fp32_peak,
+            "note": "official count = 8 FLOP per partial-sample (rotate 6 + MAC 2, SURVEY §8d); the kernel executes 3 FP32 "
+                    "instructions (4 FLOP) per partial-sample via the Reinsch recurrence, so the official fraction can exceed 1",
+            "hbm_write_gbs": voice_samples * 4 / world / 1e9,
+        }
+        del sout
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        orc = graft.load_oracle()
+        cores = orc.hardware_threads()
+        rate_1t, dt1 = cpu_analysis_rate(orc, wl, 1, 1, 30.0)
+        rate_mt, dtm = cpu_analysis_rate(orc, wl, cores, cores, 30.0)
+        cpu = {"value": rate_mt, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{cores} streams x 30 s of config 2 on {cores} threads ({dtm:.1f} s); single thread: {rate_1t:.0f} frames/s "
+                         f"on 1 stream x 30 s ({dt1:.1f} s)",
+               "value_1_thread": rate_1t}
+
+    peak, peak_src = measured_peaks()
+    per_frame = 4 * HOP + 4 * (NFFT // 2 + 1) + 4 + 12 * 16
+    achieved = rows * per_frame / (kernel_ms * 1e-3) / 1e9
+    noreuse = rows * (4 * WINDOW + 4 * (NFFT // 2 + 1)) / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: rt.resynth periodic-FFT analysis, 60 s mono 48 kHz harmonic tone per stream, window 4096, hop "
+                               "256, Gaussian window (sigma factor 4), |X|^2 spectrum written + peak extraction",
+                   "streams_per_gpu": S, "frames_per_step_per_gpu": rows, "window": WINDOW, "hop": HOP, "n_fft": NFFT,
+                   "max_peaks": MAX_PEAKS, "min_db": MIN_DB, "parallelism": f"{world} x independent streams, no data-path collective",
+                   "l2": "inputs+outputs per step (0.37 GB + 2.9 GB) exceed the 126 MB L2; no flush needed"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("stft4096_kernel"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_frame": per_frame, "kernel": "stft4096_kernel", "kernel_ms": kernel_ms,
+                     "achieved_no_reuse_convention_gbs": noreuse, "frac_no_reuse_convention": noreuse / peak},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "outputs": "peak lists (bin, freq, dB, count); the spectrum stays on the device"},
+        "gpu_launches": launches_timed, "clocks": clocks, "extra": dict(extra, final_gather_ms=gather_ms),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams-per-gpu", type=int, default=32)
+    ap.add_argument("--voices", type=int, default=1024)
+    ap.add_argument("--synth-seconds", type=float, default=10.0)
+    ap.add_argument("--skip-synth", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

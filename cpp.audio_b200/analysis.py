@@ -90,8 +90,9 @@ class SqMagAnalyzer:
             out = self.allocate(n_streams, n_samples, x.device, want_sqmag, want_peaks)
         sq = out.get("sqmag")
         pk = out.get("peak_count")
+        stream_stride = x.stride(0) if n_streams > 1 else n_samples  # a size-1 dimension may carry any stride
         self.ctx.check(lib().ca_stft_analyze(
-            self.ctx.handle, x.data_ptr(), n_samples, n_streams, x.stride(0),
+            self.ctx.handle, x.data_ptr(), n_samples, n_streams, stream_stride,
             sq.data_ptr() if sq is not None else None, sq.stride(0) if sq is not None else 0,
             out["peak_bin"].data_ptr() if pk is not None else None,
             out["peak_freq"].data_ptr() if pk is not None else None,

@@ -39,6 +39,7 @@ struct StftArgs {
   int64_t stream_stride;
   int64_t frames_per_stream;
   int64_t total_frames;
+  int32_t n_streams;
   int32_t hop;
   int32_t window;       // samples actually read per frame (<= 4096); the rest is zero padding
   const float* win;     // [4096] window * 1/(2W), zero beyond `window`
@@ -49,7 +50,7 @@ struct StftArgs {
   float* peak_db;
   int32_t* peak_count;
   int32_t max_peaks;
-  float thr_sq;
+  float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
   float bin_to_hz;
 };
 
@@ -69,19 +70,30 @@ __device__ __forceinline__ void untangle(float2 zk, float2 zm, float2 wp, float&
   sq_m = fmaf(qx, qx, qy * qy);
 }
 
+// untangle bins k = colA + 64*K2 and 2048-k = colB + 64*(31-K2) and store them at once (HBM row and/or the warp's padded
+// shared buffer), so that the stores are spread over the arithmetic instead of queueing up behind it
 template <int K2>
-__device__ __forceinline__ void post_pair(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float (&sA)[32],
-                                          float (&sB)[32]) {
+__device__ __forceinline__ void post_pair(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float* __restrict__ rowA,
+                                          float* __restrict__ rowB, float* __restrict__ sqA, float* __restrict__ sqB) {
   constexpr float2 w64 = {Tw<64, K2>::re, Tw<64, K2>::im};
   float2 wp;
   if constexpr (K2 == 0) wp = wpbase;
   else wp = cmul(wpbase, w64);
-  untangle(A[bitrev(K2, 5)], B[bitrev(31 - K2, 5)], wp, sA[K2], sB[31 - K2]);
+  float sk, sm;
+  untangle(A[bitrev(K2, 5)], B[bitrev(31 - K2, 5)], wp, sk, sm);
+  if (rowA) {
+    rowA[64 * K2] = sk;
+    rowB[64 * (31 - K2)] = sm;
+  }
+  if (sqA) {
+    sqA[65 * K2] = sk;
+    sqB[65 * (31 - K2)] = sm;
+  }
 }
 template <int... K2>
-__device__ __forceinline__ void post_all(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float (&sA)[32],
-                                         float (&sB)[32], std::integer_sequence<int, K2...>) {
-  (post_pair<K2>(A, B, wpbase, sA, sB), ...);
+__device__ __forceinline__ void post_all(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float* rowA, float* rowB,
+                                         float* sqA, float* sqB, std::integer_sequence<int, K2...>) {
+  (post_pair<K2>(A, B, wpbase, rowA, rowB, sqA, sqB), ...);
 }
 
 // stage-1 twiddle + transposed store for output slot J (k1 = bitrev6(J))
@@ -104,8 +116,9 @@ __device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2
 
 __device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
 
-template <int WARPS, bool kVec2>
-__global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_constant__ StftArgs p) {
+// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal
+template <int WARPS, bool kVec2, bool kFull>
+__global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_constant__ StftArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
   float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
@@ -144,11 +157,19 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_co
   const int colB = lane ? 64 - lane : 32;
   const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
 
-  for (int64_t f = static_cast<int64_t>(blockIdx.x) * WARPS + warp; f < p.total_frames;
-       f += static_cast<int64_t>(gridDim.x) * WARPS) {
-    const int64_t stream = f / p.frames_per_stream;
-    const int64_t fr = f - stream * p.frames_per_stream;
-    const float* xs = p.x + stream * p.stream_stride + fr * p.hop;
+  // (stream, frame) advance incrementally: no 64-bit division in the loop. frames_per_stream and n_streams fit in int32.
+  const int fps = static_cast<int>(p.frames_per_stream);
+  int fr = blockIdx.x * WARPS + warp;
+  int stream = fr / fps;
+  fr -= stream * fps;
+  for (;; fr += gridDim.x * WARPS) {
+    while (fr >= fps) {
+      fr -= fps;
+      ++stream;
+    }
+    if (stream >= p.n_streams) break;
+    const int64_t f = static_cast<int64_t>(stream) * fps + fr;
+    const float* xs = p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
 
     // ---- load + window: lane n2 takes z[32*n1 + n2] = (x[64*n1+2*n2], x[64*n1+2*n2+1]) ----
     float2 v[64];
@@ -156,11 +177,13 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_co
     for (int n1 = 0; n1 < 64; ++n1) {
       const int idx = 64 * n1 + 2 * lane;
       float2 s;
-      if (kVec2) {
+      if (kVec2 && kFull) {
+        s = ldg2(xs + idx);
+      } else if (kVec2) {
         s = (idx < p.window) ? ldg2(xs + idx) : make_float2(0.f, 0.f);
       } else {
-        s.x = (idx < p.window) ? __ldg(xs + idx) : 0.f;
-        s.y = (idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f;
+        s.x = (kFull || idx < p.window) ? __ldg(xs + idx) : 0.f;
+        s.y = (kFull || idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f;
       }
       const float2 w = ldg2(p.win + idx);
       v[n1] = make_float2(s.x * w.x, s.y * w.y);
@@ -216,44 +239,37 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_co
       untangle(u, make_float2(mx, my), tab[19 * 32 + lane], sq0, sqM);
     }
 
-    // ---- untangle the real FFT: bins k = colA + 64*k2 and 2048 - k ----
-    float sA[32], sB[32];
-    post_all(A, B, tab[20 * 32 + lane], sA, sB, std::make_integer_sequence<int, 32>{});
-
-    // ---- write |X|^2: HBM row (coalesced across lanes) and the warp's shared buffer (padded, conflict-free) ----
-    if (p.sqmag) {
-      float* row = p.sqmag + f * p.sqmag_row_stride;
-#pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        row[colA + 64 * k2] = sA[k2];
-        row[colB + 64 * k2] = sB[k2];
-      }
+    // ---- untangle the real FFT (bins k = colA + 64*k2 and 2048 - k) and write |X|^2: HBM row (coalesced across lanes)
+    //      and the warp's shared buffer (padded, conflict-free) ----
+    float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
+    float* sqw = p.peak_count ? sq : nullptr;
+    post_all(A, B, tab[20 * 32 + lane], row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
+             sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
+    if (row) {
       row[64 * k2c] = sq0;
       if (lane == 0) row[kM] = sqM;
     }
     if (p.peak_count) {
-#pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) {
-        sq[65 * k2 + colA] = sA[k2];
-        sq[65 * k2 + colB] = sB[k2];
-      }
       sq[65 * k2c] = sq0;
       if (lane == 0) sq[phys(kM)] = sqM;
       __syncwarp();
 
       // ---- peak scan: lane owns bins [64*lane, 64*lane+64) ----
+      // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
       const int base = 65 * lane;
-      uint64_t mask = 0;
-      float l = lane ? sq[base - 2] : 0.f;
+      uint32_t mlo = 0, mhi = 0;
+      float l = lane ? sq[base - 2] : __int_as_float(0x7f800000);  // bin 0 is never a peak
       float c = sq[base];
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const float r = sq[j == 63 ? base + 65 : base + j + 1];
-        const bool is_peak = (c > l) && (c > r) && (c >= p.thr_sq) && (j > 0 || lane > 0);
-        mask |= static_cast<uint64_t>(is_peak) << j;
+        const bool is_peak = c > fmaxf(fmaxf(l, r), p.thr_below);
+        if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
+        else mhi |= is_peak ? (1u << (j - 32)) : 0u;
         l = c;
         c = r;
       }
+      uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
       const int cnt = __popcll(mask);
       int incl = cnt;
 #pragma unroll
@@ -271,13 +287,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) stft4096_kernel(const __grid_co
         const int k = 64 * lane + j;
         const float fl = 1e-37f;
         const float sa = fmaxf(sq[phys(k - 1)], fl), sb = fmaxf(sq[phys(k)], fl), sc = fmaxf(sq[phys(k + 1)], fl);
-        // dB differences from ratios (well conditioned): alpha-gamma and alpha-2beta+gamma, in log2 units
-        const float ra = sa / sb, rc = sc / sb;
-        const float num = log2f(sa / sc);
-        const float den = log2f(ra * rc);
-        const float pp = den != 0.f ? 0.5f * num / den : 0.f;
+        // dB differences in log2 units, from ratios to the centre bin (well conditioned); MUFU.LG2 / MUFU.RCP precision
+        const float inv_b = __frcp_rn(sb);
+        const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);  // (alpha-beta), (gamma-beta) / (10 log10 2)
+        const float num = la - lc;
+        const float den = la + lc;
+        const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
         constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
-        const float beta = kDbPerLog2 * log2f(sb);
+        const float beta = kDbPerLog2 * __log2f(sb);
         p.peak_bin[out_base + slot] = k;
         p.peak_freq[out_base + slot] = (static_cast<float>(k) + pp) * p.bin_to_hz;
         p.peak_db[out_base + slot] = beta - 0.25f * (kDbPerLog2 * num) * pp;
@@ -347,6 +364,8 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
   const int64_t total = frames * n_streams;
   if (total == 0) return CA_OK;
+  if (frames >= (1ll << 31) - (1 << 20) || n_streams >= (1ll << 31))
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_analyze: more than 2^31 frames per stream or streams per call");
 
   StftArgs a{};
   a.x = d_x;
@@ -354,6 +373,7 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.stream_stride = stream_stride;
   a.frames_per_stream = frames;
   a.total_frames = total;
+  a.n_streams = static_cast<int32_t>(n_streams);
   a.hop = ctx->stft.hop;
   a.window = ctx->stft.window;
   a.win = ctx->d_window;
@@ -364,14 +384,16 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.peak_db = d_peak_db;
   a.peak_count = d_peak_count;
   a.max_peaks = ctx->stft.max_peaks;
-  a.thr_sq = ctx->thr_sq;
+  a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
   a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / kN);
 
   constexpr int WARPS = 4;
   const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
   const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
                     (ctx->stft.window % 2 == 0);
-  auto kern = vec2 ? stft4096_kernel<WARPS, true> : stft4096_kernel<WARPS, false>;
+  const bool full = ctx->stft.window == kN;
+  auto kern = vec2 ? (full ? stft4096_kernel<WARPS, true, true> : stft4096_kernel<WARPS, true, false>)
+                   : (full ? stft4096_kernel<WARPS, false, true> : stft4096_kernel<WARPS, false, false>);
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));

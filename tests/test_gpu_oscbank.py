@@ -88,12 +88,19 @@ def test_per_voice_envelopes_and_odd_sizes(pkg, orc, ctx, wl):
 
 
 def test_inaudible_trailing_harmonics_dropped(pkg, orc, ctx):
-    pv = np.array([[0.5, 0.0, 0.25, 1e-7, 0.0, 5e-7]], np.float32)
-    b = dict(f0_hz=np.array([440.0], np.float32), volume=np.array([0.1], np.float32), partial_volume=pv,
-             partial_phase=np.zeros((1, 6), np.float32))
-    out = gpu_render(pkg, ctx, b, 4000, default_env(pkg))
-    ref = orc.oscbank_render(b["f0_hz"], b["volume"], pv, b["partial_phase"], 4000)
-    assert np.abs(out - ref).max() < 1e-7
+    # trailing harmonics with |volume| <= 1e-6 are dropped (audioelement.h:401-415,512); inaudible ones in the middle are kept
+    def bank(pv):
+        pv = np.array([pv], np.float32)
+        return dict(f0_hz=np.array([440.0], np.float32), volume=np.array([1.0], np.float32), partial_volume=pv,
+                    partial_phase=np.zeros((1, pv.shape[1]), np.float32))
+    a = gpu_render(pkg, ctx, bank([0.5, 9e-7, 0.25, 9e-7, 0.0, 5e-7]), 4000, default_env(pkg))
+    b = gpu_render(pkg, ctx, bank([0.5, 9e-7, 0.25, 0.0, 0.0, 0.0]), 4000, default_env(pkg))
+    c = gpu_render(pkg, ctx, bank([0.5, 0.0, 0.25, 0.0, 0.0, 0.0]), 4000, default_env(pkg))
+    assert np.array_equal(a, b)          # the trailing ones contribute nothing at all
+    assert np.abs(b - c).max() > 5e-7    # the one in the middle is played
+    bb = bank([0.5, 9e-7, 0.25, 9e-7, 0.0, 5e-7])
+    ref = orc.oscbank_render(bb["f0_hz"], bb["volume"], bb["partial_volume"], bb["partial_phase"], 4000)
+    assert np.abs(a - ref).max() < 3e-6  # full-scale voice (volume 1): fp32 recurrence error over a 64-step chunk
 
 
 @pytest.mark.parametrize("mix", [1, 2])
