@@ -16,6 +16,7 @@
 // (source/rt.resynth.lib.periodicfft.cpp:13-181,251-325; call site source/rt.resynth.lib.cpp:1592-1595);
 // the unpinned arithmetic follows oracle/SPEC.md S1-S6.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -116,9 +117,12 @@ __device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2
 
 __device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
 
-// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal
-template <int WARPS, bool kVec2, bool kFull>
-__global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_constant__ StftArgs p) {
+// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal.
+// kSync: the warps of the CTA walk the frame code in step (one __syncthreads per phase). The frame body is ~70 KB of
+// straight-line SASS; unsynchronised warps each stream it from L2 on their own and instruction fetch becomes the limiter
+// (ncu: stall_no_inst 26 % of samples, profiles/), in step they share the fetches.
+template <int WARPS, int MINB, bool kSync, bool kVec2, bool kFull>
+__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid_constant__ StftArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
   float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
@@ -157,18 +161,23 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
   const int colB = lane ? 64 - lane : 32;
   const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
 
-  // (stream, frame) advance incrementally: no 64-bit division in the loop. frames_per_stream and n_streams fit in int32.
+  // CTA-uniform rounds: round r covers frames base .. base+WARPS-1, one per warp (the tail warps of the last round idle)
   const int fps = static_cast<int>(p.frames_per_stream);
-  int fr = blockIdx.x * WARPS + warp;
-  int stream = fr / fps;
-  fr -= stream * fps;
-  for (;; fr += gridDim.x * WARPS) {
-    while (fr >= fps) {
-      fr -= fps;
-      ++stream;
+  for (int64_t fbase = static_cast<int64_t>(blockIdx.x) * WARPS; fbase < p.total_frames;
+       fbase += static_cast<int64_t>(gridDim.x) * WARPS) {
+    const int64_t f = fbase + warp;
+    const bool active = f < p.total_frames;
+    if (kSync) __syncthreads();
+    if (!kSync && !active) break;
+    int stream, fr;
+    if (p.total_frames < (1ll << 31)) {
+      const unsigned uf = static_cast<unsigned>(active ? f : 0);
+      stream = static_cast<int>(uf / static_cast<unsigned>(fps));
+      fr = static_cast<int>(uf - static_cast<unsigned>(stream) * static_cast<unsigned>(fps));
+    } else {
+      stream = static_cast<int>((active ? f : 0) / fps);
+      fr = static_cast<int>((active ? f : 0) - static_cast<int64_t>(stream) * fps);
     }
-    if (stream >= p.n_streams) break;
-    const int64_t f = static_cast<int64_t>(stream) * fps + fr;
     const float* xs = p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
 
     // ---- load + window: lane n2 takes z[32*n1 + n2] = (x[64*n1+2*n2], x[64*n1+2*n2+1]) ----
@@ -190,9 +199,11 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
     }
 
     // ---- stage 1: 64-point FFT over n1 ----
+    if (kSync) __syncthreads();
     Dif<64, 64, 0>::run(v);
     const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
 
+    if (kSync) __syncthreads();
     {
       float2 wa[8], wb[8];
 #pragma unroll
@@ -213,7 +224,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
       B[n2] = exch[colB * kExchStride + n2];
     }
     __syncwarp();  // exch is reused as the sqmag buffer below
+    if (kSync) __syncthreads();
     Dif<32, 32, 0>::run(A);
+    if (kSync) __syncthreads();
     Dif<32, 32, 0>::run(B);
 
     // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
@@ -241,7 +254,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
 
     // ---- untangle the real FFT (bins k = colA + 64*k2 and 2048 - k) and write |X|^2: HBM row (coalesced across lanes)
     //      and the warp's shared buffer (padded, conflict-free) ----
-    float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
+    if (kSync) __syncthreads();
+    float* row = (p.sqmag && active) ? p.sqmag + f * p.sqmag_row_stride : nullptr;
     float* sqw = p.peak_count ? sq : nullptr;
     post_all(A, B, tab[20 * 32 + lane], row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
              sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
@@ -249,6 +263,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
       row[64 * k2c] = sq0;
       if (lane == 0) row[kM] = sqM;
     }
+    if (kSync) __syncthreads();
     if (p.peak_count) {
       sq[65 * k2c] = sq0;
       if (lane == 0) sq[phys(kM)] = sqM;
@@ -279,8 +294,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft4096_kernel(const __grid_co
       }
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int slot = incl - cnt;
-      if (lane == 0) p.peak_count[f] = total;
+      if (lane == 0 && active) p.peak_count[f] = total;
       const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
+      if (!active) mask = 0;
       while (mask && slot < p.max_peaks) {
         const int j = __ffsll(static_cast<long long>(mask)) - 1;
         mask &= mask - 1;
@@ -387,13 +403,32 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
   a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / kN);
 
-  constexpr int WARPS = 4;
-  const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
+  // tuning knobs (defaults are the measured best): CA_STFT_VARIANT = 0..4
+  static const int variant = [] {
+    const char* e = getenv("CA_STFT_VARIANT");
+    return e ? atoi(e) : 4;
+  }();
   const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
                     (ctx->stft.window % 2 == 0);
   const bool full = ctx->stft.window == kN;
-  auto kern = vec2 ? (full ? stft4096_kernel<WARPS, true, true> : stft4096_kernel<WARPS, true, false>)
-                   : (full ? stft4096_kernel<WARPS, false, true> : stft4096_kernel<WARPS, false, false>);
+  void (*kern)(StftArgs) = nullptr;
+  int WARPS = 4;
+#define CA_PICK(W, MB, SY)                                                                                       \
+  do {                                                                                                           \
+    WARPS = W;                                                                                                   \
+    kern = vec2 ? (full ? stft4096_kernel<W, MB, SY, true, true> : stft4096_kernel<W, MB, SY, true, false>)     \
+                : (full ? stft4096_kernel<W, MB, SY, false, true> : stft4096_kernel<W, MB, SY, false, false>);  \
+  } while (0)
+  switch (variant) {  // measured on B200, 32 x 60 s streams (profiles/sweep_stft_variants.sh): 0: 135.9, 1: 127.2, 2: 126.5,
+                      // 3: 139.5, 4: 144.9 Mframes/s
+    case 0: CA_PICK(4, 3, false); break;
+    case 1: CA_PICK(8, 1, true); break;
+    case 2: CA_PICK(8, 1, false); break;
+    case 3: CA_PICK(12, 1, true); break;
+    default: CA_PICK(4, 3, true); break;
+  }
+#undef CA_PICK
+  const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
