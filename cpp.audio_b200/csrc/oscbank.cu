@@ -175,6 +175,7 @@ struct OscArgs {
   int32_t mix;
   int32_t voices_per_group;
   int64_t n_chunks;
+  int64_t first_sample;  // global index of output sample 0 (phases and envelopes are closed-form in the global index)
   float* out;
 };
 
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
   float2* E = reinterpret_cast<float2*>(sp + a.ppad);                             // [ppad][32] lane offsets
   float4* sgn4 = reinterpret_cast<float4*>(E + a.ppad * 32);                      // [ppad/4]
   float2* base_all = reinterpret_cast<float2*>(sgn4 + a.ppad / 4);                // [WARPS][kNP]
-  float* outbuf_all = reinterpret_cast<float*>(base_all + WARPS * kNP);           // [WARPS][kChunk]
+  int* kend_all = reinterpret_cast<int*>(base_all + WARPS * kNP);                 // [WARPS][kNP]
+  float* cval_all = reinterpret_cast<float*>(kend_all + WARPS * kNP);             // [WARPS][kNP]
+  float* outbuf_all = cval_all + WARPS * kNP;                                     // [WARPS][kChunk]
   float* bus_all = outbuf_all + WARPS * kChunk;                                   // [WARPS][kChunk*2] (mix only)
   __shared__ VoiceParams s_vp;
   __shared__ int s_max_press, s_max_release;
@@ -224,12 +227,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float2* base = base_all + warp * kNP;
+  int* kend = kend_all + warp * kNP;
+  float* cval = cval_all + warp * kNP;
   float* outbuf = outbuf_all + warp * kChunk;
   float* bus = bus_all + warp * (kChunk * 2);
 
   const int64_t chunk = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
   const bool has_chunk = chunk < a.n_chunks;
-  const int64_t n0 = chunk * kChunk;
+  const int64_t l0 = chunk * kChunk;         // local (output) index of the chunk
+  const int64_t n0 = a.first_sample + l0;    // global sample index of the chunk
+  const int64_t n_end = a.first_sample + a.n_samples;
   const int n_out = a.mix == CA_MIX_STEREO ? 2 : 1;
 
   if (a.mix != CA_MIX_NONE)
@@ -266,14 +273,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
     const VoiceParams vp = s_vp;
     if (!has_chunk) continue;
 
-    const int64_t n1 = min(n0 + kChunk, a.n_samples);
+    const int64_t n1 = min(n0 + kChunk, n_end);
     const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
     const bool released = vp.release_at >= 0;
     const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
     bool silent = (n1 - vp.key_delay < 1);  // chunk entirely before the attack starts
     if (released) {
-      const int64_t silent_from = dead_note ? vp.release_at : vp.release_at + s_max_release - 1;
-      if (n0 >= silent_from && (dead_note ? n1 - vp.key_delay < 1 || n0 >= vp.release_at : true)) silent = true;
+      if (dead_note) silent = true;  // released before the key delay elapsed: the note is skipped (:774-777)
+      else if (n0 >= vp.release_at + s_max_release - 1) silent = true;  // every partial has finished its release
     }
     const bool steady = !silent && (n0 + 1 > press_end) && (!released || n1 <= vp.release_at);
 
@@ -345,18 +352,25 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
         }
       }
     } else {
-      // ================= general path: complex rotation + per-sample envelope =================
+      // ================= general path: complex rotation + envelope =================
+      // The envelope of a partial is piecewise linear and becomes constant (sustain level, or 0 after the release) at a
+      // sample T_p; only the steps of the chunk before T_p evaluate it per sample, the others use the constant.
       for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
         {
           const PartialParams& q = sp[p0 + lane];
           const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
           base[lane] = make_float2(q.amp * z.x, q.amp * z.y);
+          const bool rel_seen = released && vp.release_at < n1;
+          const int64_t T = rel_seen ? vp.release_at + q.release - 1
+                                     : static_cast<int64_t>(vp.key_delay) + q.attack + vp.hold + q.decay;
+          const int64_t ke = (T - n0 + 31) >> 5;
+          kend[lane] = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kR), ke)));
+          cval[lane] = rel_seen ? 0.f : vp.sustain;
         }
         __syncwarp();
         float2 z[kNP];
 #pragma unroll
         for (int p = 0; p < kNP; ++p) z[p] = cmul(base[p], E[(p0 + p) * 32 + lane]);
-        __syncwarp();
 #pragma unroll 1
         for (int k = 0; k < kR; ++k) {
           const int64_t n = n0 + 32 * k + lane;
@@ -364,23 +378,26 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
 #pragma unroll
           for (int p = 0; p < kNP; ++p) {
             const PartialParams& q = sp[p0 + p];
-            if (q.amp != 0.f) acc = fmaf(z[p].y, env_value(n, q, vp), acc);
+            float e = cval[p];
+            if (k < kend[p]) e = env_value(n, q, vp);
+            acc = fmaf(z[p].y, e, acc);
             z[p] = cmul(z[p], make_float2(q.rot_re, q.rot_im));
           }
           if (p0 == 0) outbuf[32 * k + lane] = acc;
           else outbuf[32 * k + lane] += acc;
         }
+        __syncwarp();
       }
     }
     __syncwarp();
 
     // ---- emit ----
     if (a.mix == CA_MIX_NONE) {
-      float* o = a.out + v * a.n_samples + n0;
+      float* o = a.out + v * a.n_samples + l0;
 #pragma unroll 4
       for (int k = 0; k < kR; ++k) {
         const int i = 32 * k + lane;
-        if (n0 + i < a.n_samples) o[i] = outbuf[i];
+        if (l0 + i < a.n_samples) o[i] = outbuf[i];
       }
     } else if (!silent) {
       if (a.mix == CA_MIX_STEREO) {
@@ -404,8 +421,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
   }
 
   if (a.mix != CA_MIX_NONE && has_chunk) {
-    float* o = a.out + n0 * n_out;
-    const int64_t lim = (min(n0 + kChunk, a.n_samples) - n0) * n_out;
+    float* o = a.out + l0 * n_out;
+    const int64_t lim = (min(l0 + kChunk, a.n_samples) - l0) * n_out;
     for (int i = lane; i < lim; i += 32) atomicAdd(o + i, bus[i]);
   }
 }
@@ -451,7 +468,7 @@ void oscbank_release(ca_ctx* ctx) {
 int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream) {
   if (!desc || !d_out) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render: null argument");
   const ca_oscbank_desc& d = *desc;
-  if (d.n_voices < 0 || d.n_partials < 1 || d.n_samples < 0 || d.sample_rate <= 0 || !d.f0_hz || !d.volume ||
+  if (d.n_voices < 0 || d.n_partials < 1 || d.n_samples < 0 || d.first_sample < 0 || d.sample_rate <= 0 || !d.f0_hz || !d.volume ||
       !d.partial_volume || !d.partial_phase || !d.env || (d.n_env != 1 && d.n_env != d.n_voices))
     return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render: bad descriptor");
   if (d.mix != CA_MIX_NONE && d.mix != CA_MIX_STEREO && d.mix != CA_MIX_MONO)
@@ -475,13 +492,14 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
   a.ppad = ppad;
   a.mix = d.mix;
   a.n_chunks = (d.n_samples + kChunk - 1) / kChunk;
+  a.first_sample = d.first_sample;
   a.out = d_out;
 
   const size_t common = sizeof(PartialParams) * ppad + sizeof(float2) * ppad * 32 + sizeof(float) * ppad;
   if (d.mix == CA_MIX_NONE) {
     constexpr int WARPS = 8;
     a.voices_per_group = 1;
-    const size_t smem = common + WARPS * (sizeof(float2) * kNP + sizeof(float) * kChunk);
+    const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk);
     CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     dim3 grid(static_cast<unsigned>((a.n_chunks + WARPS - 1) / WARPS), static_cast<unsigned>(d.n_voices));
@@ -491,7 +509,7 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
     constexpr int WARPS = 4;
     const int n_out = d.mix == CA_MIX_STEREO ? 2 : 1;
     CA_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(float) * d.n_samples * n_out, stream));
-    const size_t smem = common + WARPS * (sizeof(float2) * kNP + sizeof(float) * kChunk * 3);
+    const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk * 3);
     CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     const int64_t tiles = (a.n_chunks + WARPS - 1) / WARPS;

@@ -30,7 +30,7 @@ class SineBank:
 
     def render(self, n_samples: int, f0_hz: torch.Tensor, volume: torch.Tensor, partial_volume: torch.Tensor,
                partial_phase: torch.Tensor, env, start_angle=None, key_delay=None, release_at=None, pan=None,
-               mix: int = MIX_NONE, out: torch.Tensor | None = None) -> torch.Tensor:
+               mix: int = MIX_NONE, out: torch.Tensor | None = None, first_sample: int = 0) -> torch.Tensor:
         """All tensors on the same CUDA device. env: one Ahdsr or a list of Ahdsr (one per voice)."""
         dev = f0_hz.device
         nv, npart = partial_volume.shape
@@ -52,7 +52,7 @@ class SineBank:
             out = torch.empty(shape, dtype=torch.float32, device=dev)
         d = OscBankDesc(nv, npart, n_samples, self.sample_rate, f0_hz.data_ptr(), volume.data_ptr(), _opt_ptr(start_angle),
                         _opt_ptr(key_delay), _opt_ptr(release_at), partial_volume.data_ptr(), partial_phase.data_ptr(),
-                        env_dev.data_ptr(), len(envs), _opt_ptr(pan), mix)
+                        env_dev.data_ptr(), len(envs), _opt_ptr(pan), mix, first_sample)
         self.ctx.check(lib().ca_oscbank_render(self.ctx.handle, C.byref(d), out.data_ptr(),
                                                torch.cuda.current_stream(dev).cuda_stream), "ca_oscbank_render")
         self._keep = (env_dev,)  # the render is asynchronous: keep the parameter block alive

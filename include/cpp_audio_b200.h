@@ -123,6 +123,8 @@ typedef struct ca_oscbank_desc {
   int64_t n_env;               /* 1 (shared) or n_voices */
   const float* pan;            /* [voices] nullable, used by CA_MIX_STEREO (include/stereo.h:18-27) */
   int32_t mix;                 /* ca_mix */
+  int64_t first_sample;        /* render samples [first_sample, first_sample+n_samples) of the notes' timeline (block-wise or
+                                  time-sharded rendering; phases and envelopes are closed-form in the sample index) */
 } ca_oscbank_desc;
 
 /* sizes scratch for up to max_voices x max_partials; the only allocating call of the synthesis path */

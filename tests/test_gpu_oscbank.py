@@ -16,7 +16,7 @@ def gpu_render(pkg, ctx, b, n_samples, env, sr=48000, **kw):
     tk = {k: T(v) for k, v in kw.items() if k in ("start_angle", "key_delay", "release_at", "pan")}
     mix = kw.get("mix", 0)
     out = pkg.render_bank(ctx, n_samples, T(b["f0_hz"]), T(b["volume"]), T(b["partial_volume"]), T(b["partial_phase"]), env,
-                          sample_rate=sr, mix=mix, **tk)
+                          sample_rate=sr, mix=mix, first_sample=kw.get("first_sample", 0), **tk)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -116,6 +116,21 @@ def test_mix_modes(pkg, orc, ctx, wl, mix):
     assert np.abs(out - ref).max() < TOL * 0.1 * 10  # 40 voices of volume 0.1 on one bus
 
 
+def test_block_wise_rendering_equals_one_shot(pkg, orc, ctx, wl):
+    # first_sample: rendering [a, b) of the timeline gives the same samples as the slice of a full render
+    b = wl.c3_bank(4, 16)
+    e = pkg.Ahdsr(300, 0, 100, 500, 0, 900, 0, 0.5)
+    rel = np.array([5000, -1, 2500, 7000], np.int64)
+    kd = np.array([0, 3000, 10, 0], np.int32)
+    full = gpu_render(pkg, ctx, b, 9000, e, release_at=rel, key_delay=kd)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], 9000, env=orc_env(orc, e),
+                             release_at=rel, key_delay=kd)
+    assert np.abs(full - ref).max() < TOL * 0.1
+    for a0, n in ((0, 1000), (1000, 2077), (3077, 5923)):
+        part = gpu_render(pkg, ctx, b, n, e, release_at=rel, key_delay=kd, first_sample=a0)
+        assert np.abs(part - ref[:, a0:a0 + n]).max() < TOL * 0.1
+
+
 def test_long_note_phase_stays_exact(pkg, ctx):
     """10 s note (BASELINE config 3 length): fp32 must not drift — compare the last second with the closed form."""
     f0 = np.array([97.3, 3520.1], np.float32)
@@ -157,7 +172,7 @@ def test_host_entry_point(pkg, orc, ctx, wl):
     out = np.empty((3, n), np.float32)
     vp = lambda a: a.ctypes.data_as(C.c_void_p).value
     d = pkg.OscBankDesc(3, 16, n, 48000, vp(b["f0_hz"]), vp(b["volume"]), None, None, None, vp(b["partial_volume"]),
-                        vp(b["partial_phase"]), C.cast(env, C.c_void_p).value, 1, None, 0)
+                        vp(b["partial_phase"]), C.cast(env, C.c_void_p).value, 1, None, 0, 0)
     rc = pkg.lib().ca_oscbank_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
