@@ -33,6 +33,34 @@ def test_sizes_in_shared_memory(pkg, orc, ctx, p):
     assert err < 1e-5, (p, err)
 
 
+@pytest.mark.parametrize("p,batch", [(16, 5), (17, 3), (18, 3), (19, 2), (20, 2)])
+def test_sizes_four_step(pkg, orc, ctx, p, batch):
+    n = 1 << p
+    rng = np.random.default_rng(5000 + p)
+    x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+    X = gpu_rfft(pkg, ctx, x)
+    ref = orc.rfft(x.astype(np.float64))
+    err = np.abs(X - ref).max() / np.sqrt(n)
+    assert err < 1e-5, (p, err)
+    # a pure tone lands in one bin with magnitude N/2 (normalised error)
+    t = np.arange(n)
+    tone = np.sin(2 * np.pi * 12345 * t / n).astype(np.float32)[None, :]
+    T = gpu_rfft(pkg, ctx, tone)[0]
+    assert abs(abs(T[12345]) / (n / 2) - 1) < 1e-5
+    T[12345] = 0
+    assert np.abs(T).max() / (n / 2) < 1e-5
+
+
+def test_many_frames_four_step_grouping(pkg, ctx):
+    # more frames than one work-buffer group (256 MiB / (8*M) frames): exercises the group loop
+    n = 1 << 16
+    batch = 1100
+    x = torch.randn((batch, n), device="cuda")
+    X = pkg.rfft_batched(ctx, x)
+    ref = torch.fft.rfft(x[[0, 1023, 1024, 1099]].double(), dim=1)   # torch/cuFFT only as an independent cross-check
+    assert (X[[0, 1023, 1024, 1099]] - ref).abs().max().item() / np.sqrt(n) < 1e-5
+
+
 def test_linearity_and_impulse(pkg, ctx):
     n = 4096
     x = np.zeros((3, n), np.float32)
