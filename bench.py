@@ -103,14 +103,14 @@ class ClockSampler:
 
 
 def cpu_analysis_rate(orc, wl, threads: int, streams: int, seconds: float):
-    """frames/s of the CPU oracle (the reference's structure: per-sample feed, double precision, one FFT per hop) over
-    `streams` independent streams of `seconds` each, `threads` host threads."""
-    x = wl.tiled_streams(min(streams, 8), seconds)
-    reps = (streams + x.shape[0] - 1) // x.shape[0]
-    x = np.ascontiguousarray(np.tile(x, (reps, 1))[:streams])
+    """frames/s of the CPU oracle (the reference's structure: per-sample feed, double precision, one FFT per hop, peak
+    extraction per frame) over `streams` independent streams of `seconds` each on `threads` host threads."""
+    x = wl.harmonic_tone(int(round(seconds * SR)))
     t0 = time.perf_counter()
-    r = orc.stft_analyze(x, WINDOW, HOP, sample_rate=SR, min_db=MIN_DB, max_peaks=MAX_PEAKS, want_sqmag=False, threads=threads)
+    r = orc.stft_analyze(x, WINDOW, HOP, sample_rate=SR, min_db=MIN_DB, max_peaks=MAX_PEAKS, want_sqmag=False, threads=threads,
+                         repeat=streams, count_only=True)
     dt = time.perf_counter() - t0
+    assert int(r["peak_count"].min()) == 16 and int(r["peak_count"].max()) == 16
     return streams * r["frames"] / dt, dt
 
 
@@ -122,10 +122,10 @@ def run_reference(args):
     graft.load_package()
     import cpp_audio_b200.workloads as wl
     cores = orc.hardware_threads()
-    streams = max(1, cores)
-    seconds = 20.0
-    for _ in range(args.warmup):
-        cpu_analysis_rate(orc, wl, cores, streams, 2.0)
+    streams = max(1, cores) * 4      # ~1.5 s of work per thread per step
+    seconds = 60.0
+    for _ in range(min(args.warmup, 2)):
+        cpu_analysis_rate(orc, wl, cores, cores, 10.0)
     t_total, frames_total = 0.0, 0
     for _ in range(args.steps):
         rate, dt = cpu_analysis_rate(orc, wl, cores, streams, seconds)
@@ -311,11 +311,12 @@ def run_ours(args):
     if world == 1 and not args.skip_cpu:
         orc = graft.load_oracle()
         cores = orc.hardware_threads()
-        rate_1t, dt1 = cpu_analysis_rate(orc, wl, 1, 1, 30.0)
-        rate_mt, dtm = cpu_analysis_rate(orc, wl, cores, cores, 30.0)
+        rate_1t, dt1 = cpu_analysis_rate(orc, wl, 1, 8, 60.0)
+        n_mt = cores * 24
+        rate_mt, dtm = cpu_analysis_rate(orc, wl, cores, n_mt, 60.0)
         cpu = {"value": rate_mt, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} streams x 30 s of config 2 on {cores} threads ({dtm:.1f} s); single thread: {rate_1t:.0f} frames/s "
-                         f"on 1 stream x 30 s ({dt1:.1f} s)",
+               "sample": f"{n_mt} streams x 60 s of config 2 on {cores} threads ({dtm:.1f} s wall); single thread: "
+                         f"{rate_1t:.0f} frames/s on 8 streams x 60 s ({dt1:.1f} s)",
                "value_1_thread": rate_1t}
 
     peak, peak_src = measured_peaks()

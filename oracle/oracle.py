@@ -98,19 +98,26 @@ def window(window_type: int, sigma_factor: float, size: int) -> np.ndarray:
 
 def stft_analyze(x: np.ndarray, window: int, hop: int, window_type: int = 1, sigma_factor: float = 4.0,
                  sample_rate: int = 48000, min_db: float = -80.0, max_peaks: int = 200, want_sqmag: bool = True,
-                 want_peaks: bool = True, threads: int = 1):
-    """x: float32 [streams, samples] (or 1-D). Returns dict(frames, sqmag, peak_bin, peak_freq, peak_db, peak_count)."""
+                 want_peaks: bool = True, threads: int = 1, repeat: int = 0, count_only: bool = False):
+    """x: float32 [streams, samples] (or 1-D). Returns dict(frames, sqmag, peak_bin, peak_freq, peak_db, peak_count).
+    repeat > 0: analyse the single stream x `repeat` times as independent streams (timing runs; stride 0, no copies);
+    count_only: run the peak extraction but keep only the per-frame counts."""
     x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
     streams, n = x.shape
+    stride = n
+    if repeat > 0:
+        assert streams == 1
+        streams, stride = repeat, 0
     frames = num_frames(n, window, hop)
     n_fft = int(lib().orc_fft_length_for(window, 1))
     bins = n_fft // 2 + 1
     sqmag = np.zeros((streams, frames, bins), dtype=np.float64) if want_sqmag else None
-    pb = np.full((streams, frames, max_peaks), -1, dtype=np.int32) if want_peaks else None
-    pf = np.zeros((streams, frames, max_peaks), dtype=np.float64) if want_peaks else None
-    pd = np.zeros((streams, frames, max_peaks), dtype=np.float64) if want_peaks else None
+    full = want_peaks and not count_only
+    pb = np.full((streams, frames, max_peaks), -1, dtype=np.int32) if full else None
+    pf = np.zeros((streams, frames, max_peaks), dtype=np.float64) if full else None
+    pd = np.zeros((streams, frames, max_peaks), dtype=np.float64) if full else None
     pc = np.zeros((streams, frames), dtype=np.int32) if want_peaks else None
-    got = lib().orc_stft_analyze(_ptr(x), n, streams, n, window, hop, window_type, float(sigma_factor), sample_rate,
+    got = lib().orc_stft_analyze(_ptr(x), n, streams, stride, window, hop, window_type, float(sigma_factor), sample_rate,
                                  float(min_db), max_peaks, _ptr(sqmag), _ptr(pb), _ptr(pf), _ptr(pd), _ptr(pc), threads)
     assert got == frames
     return dict(frames=frames, n_fft=n_fft, sqmag=sqmag, peak_bin=pb, peak_freq=pf, peak_db=pd, peak_count=pc)
