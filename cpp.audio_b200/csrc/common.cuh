@@ -114,6 +114,46 @@ struct Dif {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// In-register radix-2 decimation-in-time FFT: on entry v[OFF + i] holds the input of index bitrev(i), on return
+// v[OFF + k] holds output k (natural order). A general butterfly is 6 FFMA whose twiddles are immediates
+// (a + w*b in 4, a - w*b = 2a - (a + w*b) in 2): fewer instructions than the 8 of the DIF form and only two register
+// sources per instruction, which matters on B200 where FFMA with three distinct registers issues at half rate
+// (profiles/microbench/fp32_ports_b200.txt).
+// ---------------------------------------------------------------------------------------------------------------
+template <int SIZE, int N, int OFF>
+struct Dit {
+  template <int J>
+  static __device__ __forceinline__ void butterfly(float2 (&v)[SIZE]) {
+    const float2 a = v[OFF + J];
+    const float2 b = v[OFF + J + N / 2];
+    if constexpr (J == 0) {
+      v[OFF + J] = make_float2(a.x + b.x, a.y + b.y);
+      v[OFF + J + N / 2] = make_float2(a.x - b.x, a.y - b.y);
+    } else if constexpr (4 * J == N) {  // w = -i: w*b = (b.y, -b.x)
+      v[OFF + J] = make_float2(a.x + b.y, a.y - b.x);
+      v[OFF + J + N / 2] = make_float2(a.x - b.y, a.y + b.x);
+    } else {
+      constexpr float wr = Tw<N, J>::re, wi = Tw<N, J>::im;
+      const float ox = fmaf(wr, b.x, fmaf(-wi, b.y, a.x));
+      const float oy = fmaf(wr, b.y, fmaf(wi, b.x, a.y));
+      v[OFF + J] = make_float2(ox, oy);
+      v[OFF + J + N / 2] = make_float2(fmaf(2.f, a.x, -ox), fmaf(2.f, a.y, -oy));
+    }
+  }
+  template <int... J>
+  static __device__ __forceinline__ void stage(float2 (&v)[SIZE], std::integer_sequence<int, J...>) {
+    (butterfly<J>(v), ...);
+  }
+  static __device__ __forceinline__ void run(float2 (&v)[SIZE]) {
+    if constexpr (N > 1) {
+      Dit<SIZE, N / 2, OFF>::run(v);
+      Dit<SIZE, N / 2, OFF + N / 2>::run(v);
+      stage(v, std::make_integer_sequence<int, N / 2>{});
+    }
+  }
+};
+
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
 }  // namespace ca

@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -61,7 +62,8 @@ __device__ __forceinline__ float2 cis_neg(float turns_times_two) {  // exp(-i*pi
   return make_float2(c, -s);
 }
 
-// sqmag of the pair (k, M-k) from Z[k] and Z[M-k]; wp = -i*W_N^k
+// sqmag of the pair (k, M-k) from Z[k] and Z[M-k]; wp = -i*W_N^k. (The shorter form |X|^2 = S +- C with
+// S = |E|^2+|D|^2, C = 2 Re(E conj(wp D)) cancels catastrophically on bins far below their mirror bin: not used.)
 __device__ __forceinline__ void untangle(float2 zk, float2 zm, float2 wp, float& sq_k, float& sq_m) {
   const float ex = zk.x + zm.x, ey = zk.y - zm.y;  // Z[k] + conj(Z[M-k])
   const float dx = zk.x - zm.x, dy = zk.y + zm.y;  // Z[k] - conj(Z[M-k])
@@ -81,7 +83,7 @@ __device__ __forceinline__ void post_pair(const float2 (&A)[32], const float2 (&
   if constexpr (K2 == 0) wp = wpbase;
   else wp = cmul(wpbase, w64);
   float sk, sm;
-  untangle(A[bitrev(K2, 5)], B[bitrev(31 - K2, 5)], wp, sk, sm);
+  untangle(A[K2], B[31 - K2], wp, sk, sm);
   if (rowA) {
     rowA[64 * K2] = sk;
     rowB[64 * (31 - K2)] = sm;
@@ -97,11 +99,11 @@ __device__ __forceinline__ void post_all(const float2 (&A)[32], const float2 (&B
   (post_pair<K2>(A, B, wpbase, rowA, rowB, sqA, sqB), ...);
 }
 
-// stage-1 twiddle + transposed store for output slot J (k1 = bitrev6(J))
+// stage-1 twiddle + transposed store for output k1 = J
 template <int J>
 __device__ __forceinline__ void tw_store(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8], float2* exch,
                                          int lane) {
-  constexpr int k1 = bitrev(J, 6);
+  constexpr int k1 = J;
   constexpr int a = k1 >> 3, b = k1 & 7;
   float2 y = v[J];
   if constexpr (a != 0 && b != 0) y = cmul(y, cmul(wa[a], wb[b]));
@@ -109,6 +111,26 @@ __device__ __forceinline__ void tw_store(const float2 (&v)[64], const float2 (&w
   else if constexpr (b != 0) y = cmul(y, wb[b]);
   exch[k1 * kExchStride + lane] = y;
 }
+// split variant: twiddle in place, then the real and imaginary planes cross the transpose buffer one after the other
+// (half the shared memory per warp: 64 x 33 floats)
+template <int J>
+__device__ __forceinline__ void tw_inplace(float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8]) {
+  constexpr int k1 = J;
+  constexpr int a = k1 >> 3, b = k1 & 7;
+  if constexpr (a != 0 && b != 0) v[J] = cmul(v[J], cmul(wa[a], wb[b]));
+  else if constexpr (a != 0) v[J] = cmul(v[J], wa[a]);
+  else if constexpr (b != 0) v[J] = cmul(v[J], wb[b]);
+}
+template <int... J>
+__device__ __forceinline__ void tw_inplace_all(float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8],
+                                               std::integer_sequence<int, J...>) {
+  (tw_inplace<J>(v, wa, wb), ...);
+}
+template <bool kImag, int... J>
+__device__ __forceinline__ void plane_store_all(const float2 (&v)[64], float* xb, int lane, std::integer_sequence<int, J...>) {
+  ((xb[J * kExchStride + lane] = kImag ? v[J].y : v[J].x), ...);
+}
+
 template <int... J>
 __device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8],
                                              float2* exch, int lane, std::integer_sequence<int, J...>) {
@@ -117,19 +139,167 @@ __device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2
 
 __device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
 
-// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal.
-// kSync: the warps of the CTA walk the frame code in step (one __syncthreads per phase). The frame body is ~70 KB of
-// straight-line SASS; unsynchronised warps each stream it from L2 on their own and instruction fetch becomes the limiter
-// (ncu: stall_no_inst 26 % of samples, profiles/), in step they share the fetches.
-template <int WARPS, int MINB, bool kSync, bool kVec2, bool kFull>
-__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid_constant__ StftArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
-  float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
+// Everything after the load: stage-1 FFT, transpose, stage-2 FFTs, untangling, stores, peak extraction (see file header).
+template <bool kSync, bool kSplit>
+__device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, const float2* __restrict__ tab,
+                                           float2* __restrict__ exch, const int lane, const int64_t f, const bool active) {
+  float* sq = reinterpret_cast<float*>(exch);
+  const int colA = lane ? lane : 32;
+  const int colB = lane ? 64 - lane : 32;
+  const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
+  // ---- stage 1: 64-point FFT over n1 ----
+  if (kSync) __syncthreads();
+  Dit<64, 64, 0>::run(v);  // natural order out: v[k1]
+  const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
 
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  if (kSync) __syncthreads();
+  float2 A[32], B[32];
+  {
+    float2 wa[8], wb[8];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      wb[i] = tab[(i - 1) * 32 + lane];
+      wa[i] = tab[(6 + i) * 32 + lane];
+    }
+    wa[0] = wb[0] = make_float2(1.f, 0.f);
+    if constexpr (!kSplit) {
+      tw_store_all(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
+    } else {
+      tw_inplace_all(v, wa, wb, std::make_integer_sequence<int, 64>{});
+    }
+  }
+  // ---- stage 2 inputs: columns colA, colB of the transposed data ----
+  if constexpr (!kSplit) {
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      A[bitrev(n2, 5)] = exch[colA * kExchStride + n2];
+      B[bitrev(n2, 5)] = exch[colB * kExchStride + n2];
+    }
+  } else {
+    float* xb = reinterpret_cast<float*>(exch);
+    plane_store_all<false>(v, xb, lane, std::make_integer_sequence<int, 64>{});
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      A[bitrev(n2, 5)].x = xb[colA * kExchStride + n2];
+      B[bitrev(n2, 5)].x = xb[colB * kExchStride + n2];
+    }
+    __syncwarp();
+    plane_store_all<true>(v, xb, lane, std::make_integer_sequence<int, 64>{});
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      A[bitrev(n2, 5)].y = xb[colA * kExchStride + n2];
+      B[bitrev(n2, 5)].y = xb[colB * kExchStride + n2];
+    }
+  }
+  __syncwarp();  // exch is reused as the sqmag buffer below
+  if (kSync) __syncthreads();
+  Dit<32, 32, 0>::run(A);
+  if (kSync) __syncthreads();
+  Dit<32, 32, 0>::run(B);
 
+  // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
+  float2 u = c0;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int d = 16 >> s;
+    const float ox = __shfl_xor_sync(0xffffffffu, u.x, d);
+    const float oy = __shfl_xor_sync(0xffffffffu, u.y, d);
+    if (lane & d) {
+      const float2 w = tab[(14 + s) * 32 + lane];
+      u = cmul(make_float2(ox - u.x, oy - u.y), w);
+    } else {
+      u = make_float2(u.x + ox, u.y + oy);
+    }
+  }
+  float sq0, sqM;
+  {
+    const int pk2 = (32 - k2c) & 31;
+    const int plane = static_cast<int>(__brev(static_cast<unsigned>(pk2)) >> 27);
+    const float mx = __shfl_sync(0xffffffffu, u.x, plane);
+    const float my = __shfl_sync(0xffffffffu, u.y, plane);
+    untangle(u, make_float2(mx, my), tab[19 * 32 + lane], sq0, sqM);
+  }
+
+  // ---- untangle the real FFT (bins k = colA + 64*k2 and 2048 - k) and write |X|^2: HBM row (coalesced across lanes)
+  //      and the warp's shared buffer (padded, conflict-free) ----
+  if (kSync) __syncthreads();
+  float* row = (p.sqmag && active) ? p.sqmag + f * p.sqmag_row_stride : nullptr;
+  float* sqw = p.peak_count ? sq : nullptr;
+  post_all(A, B, tab[20 * 32 + lane], row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
+           sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
+  if (row) {
+    row[64 * k2c] = sq0;
+    if (lane == 0) row[kM] = sqM;
+  }
+  if (kSync) __syncthreads();
+  if (p.peak_count) {
+    sq[65 * k2c] = sq0;
+    if (lane == 0) sq[phys(kM)] = sqM;
+    __syncwarp();
+
+    // ---- peak scan: lane owns bins [64*lane, 64*lane+64) ----
+    // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
+    const int base = 65 * lane;
+    uint32_t mlo = 0, mhi = 0;
+    float l = lane ? sq[base - 2] : __int_as_float(0x7f800000);  // bin 0 is never a peak
+    float c = sq[base];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const float r = sq[j == 63 ? base + 65 : base + j + 1];
+      const bool is_peak = c > fmaxf(fmaxf(l, r), p.thr_below);
+      if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
+      else mhi |= is_peak ? (1u << (j - 32)) : 0u;
+      l = c;
+      c = r;
+    }
+    uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
+    const int cnt = __popcll(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int slot = incl - cnt;
+    if (lane == 0 && active) p.peak_count[f] = total;
+    // each lane lists the bins of its peaks (ascending), then the peaks are spread over the lanes: the interpolation
+    // runs once per 32 peaks instead of once per peak of the busiest lane, and the stores are coalesced
+    // (the list lives behind the sqmag buffer, or, in the split variant whose buffer is half as large, in the output itself)
+    const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
+    int* klist = kSplit ? p.peak_bin + out_base : reinterpret_cast<int*>(sq + 2112);
+    const int n_store = active ? min(total, p.max_peaks) : 0;
+    while (mask && slot < n_store) {
+      const int j = __ffsll(static_cast<long long>(mask)) - 1;
+      mask &= mask - 1;
+      klist[slot++] = 64 * lane + j;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < n_store; idx += 32) {
+      const int k = kSplit ? *reinterpret_cast<volatile int*>(klist + idx) : klist[idx];
+      const float fl = 1e-37f;
+      const float sa = fmaxf(sq[phys(k - 1)], fl), sb = fmaxf(sq[phys(k)], fl), sc = fmaxf(sq[phys(k + 1)], fl);
+      // dB differences in log2 units, from ratios to the centre bin (well conditioned); MUFU.LG2 / MUFU.RCP precision
+      const float inv_b = __frcp_rn(sb);
+      const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);  // (alpha-beta), (gamma-beta) / (10 log10 2)
+      const float num = la - lc;
+      const float den = la + lc;
+      const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
+      constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
+      const float beta = kDbPerLog2 * __log2f(sb);
+      if (!kSplit) p.peak_bin[out_base + idx] = k;
+      p.peak_freq[out_base + idx] = (static_cast<float>(k) + pp) * p.bin_to_hz;
+      p.peak_db[out_base + idx] = beta - 0.25f * (kDbPerLog2 * num) * pp;
+    }
+    __syncwarp();  // the next frame overwrites the buffer
+  }
+}
+
+template <int WARPS>
+__device__ __forceinline__ void build_tables(float2* tab) {
   for (int i = threadIdx.x; i < kTabRows * 32; i += WARPS * 32) {
     const int r = i >> 5, l = i & 31;
     float2 w;
@@ -153,13 +323,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid
     }
     tab[i] = w;
   }
+}
+
+// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal.
+// kSync: the warps of the CTA walk the frame code in step (one __syncthreads per phase). The frame body is ~70 KB of
+// straight-line SASS; unsynchronised warps each stream it from L2 on their own and instruction fetch becomes the limiter
+// (ncu: stall_no_inst 26 % of samples, profiles/), in step they share the fetches.
+template <int WARPS, int MINB, bool kSync, bool kVec2, bool kFull>
+__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid_constant__ StftArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
+  float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  build_tables<WARPS>(tab);
   __syncthreads();
 
   float2* exch = exch_all + warp * kExchFloat2;
-  float* sq = reinterpret_cast<float*>(exch);
-  const int colA = lane ? lane : 32;
-  const int colB = lane ? 64 - lane : 32;
-  const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
 
   // CTA-uniform rounds: round r covers frames base .. base+WARPS-1, one per warp (the tail warps of the last round idle)
   const int fps = static_cast<int>(p.frames_per_stream);
@@ -195,129 +377,129 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid
         s.y = (kFull || idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f;
       }
       const float2 w = ldg2(p.win + idx);
-      v[n1] = make_float2(s.x * w.x, s.y * w.y);
+      v[bitrev(n1, 6)] = make_float2(s.x * w.x, s.y * w.y);  // DIT: bit-reversed register order in
     }
 
-    // ---- stage 1: 64-point FFT over n1 ----
-    if (kSync) __syncthreads();
-    Dif<64, 64, 0>::run(v);
-    const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
+    frame_body<kSync, false>(v, p, tab, exch, lane, f, active);
+  }
+}
 
-    if (kSync) __syncthreads();
-    {
-      float2 wa[8], wb[8];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        wb[i] = tab[(i - 1) * 32 + lane];
-        wa[i] = tab[(6 + i) * 32 + lane];
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ring variant (window == 4096, hop % 4 == 0, hop <= 1024, 16-byte aligned streams): the CTA walks a CONTIGUOUS range of
+// frames of one stream, WARPS frames per round, and keeps the samples it needs in an 8192-float shared-memory ring that is
+// fed by 1-D bulk async copies (cp.async.bulk + mbarrier, SASS UBLKCP): the 4*hop new samples of the next round are in
+// flight during the whole arithmetic of the current round, so the load phase reads shared memory instead of waiting on
+// L2/HBM. Frames overlap by (window-hop)/window, so each sample crosses L2->SM once per CTA instead of 16 times.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRing = 8192;  // floats; >= 4096 + 3*hop + 4*hop for hop <= 585, and window + 3*hop <= 8192 for hop <= 1024
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// copy samples [s0, s1) of a stream into the ring (position = sample index mod kRing); s0, s1 multiples of 4
+__device__ __forceinline__ uint32_t ring_fill(float* ring, const float* stream_base, int64_t s0, int64_t s1, uint64_t* bar) {
+  if (s1 <= s0) return 0;
+  const uint32_t bytes = static_cast<uint32_t>(s1 - s0) * 4u;
+  mbar_expect_tx(bar, bytes);
+  int64_t s = s0;
+  while (s < s1) {
+    const int pos = static_cast<int>(s & (kRing - 1));
+    const int64_t n = min(s1 - s, static_cast<int64_t>(kRing - pos));
+    bulk_g2s(ring + pos, stream_base + s, static_cast<uint32_t>(n) * 4u, bar);
+    s += n;
+  }
+  return bytes;
+}
+
+struct RingPlan {
+  int32_t units_per_stream;
+  int32_t frames_per_unit;  // multiple of WARPS
+  int32_t total_units;
+};
+
+template <int WARPS, int MINB, bool kSplit>
+__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_ring_kernel(const __grid_constant__ StftArgs p,
+                                                                        const __grid_constant__ RingPlan rp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);                    // [kRing]
+  float2* tab = reinterpret_cast<float2*>(ring + kRing);               // [kTabRows][32]
+  float2* exch_all = tab + kTabRows * 32;                              // [WARPS][kExchFloat2 (half of it when kSplit)]
+  __shared__ __align__(8) uint64_t bar;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  build_tables<WARPS>(tab);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  float2* exch = exch_all + warp * (kSplit ? kExchFloat2 / 2 : kExchFloat2);
+  const int fps = static_cast<int>(p.frames_per_stream);
+  uint32_t parity = 0;
+
+  for (int u = blockIdx.x; u < rp.total_units; u += gridDim.x) {
+    const int stream = u / rp.units_per_stream;
+    const int fa = (u - stream * rp.units_per_stream) * rp.frames_per_unit;
+    const int fb = min(fps, fa + rp.frames_per_unit);
+    const float* xs = p.x + static_cast<int64_t>(stream) * p.stream_stride;
+    // all warps are past the load phase of the previous unit (barrier after its last load): the ring can be refilled
+    bool pending = false;
+    if (threadIdx.x == 0) {
+      const int last = min(fa + WARPS - 1, fb - 1);
+      ring_fill(ring, xs, static_cast<int64_t>(fa) * p.hop, static_cast<int64_t>(last) * p.hop + kN, &bar);
+    }
+    pending = true;
+    for (int f0 = fa; f0 < fb; f0 += WARPS) {
+      const int fr = f0 + warp;
+      const bool active = fr < fb;
+      const int64_t f = static_cast<int64_t>(stream) * fps + (active ? fr : fa);
+      if (pending) {
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
       }
-      wa[0] = wb[0] = make_float2(1.f, 0.f);
-      tw_store_all(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
-    }
-    __syncwarp();
-
-    // ---- stage 2: two 32-point FFTs over n2 (columns colA, colB) ----
-    float2 A[32], B[32];
+      // ---- load + window from the ring ----
+      float2 v[64];
+      const int pos0 = static_cast<int>((static_cast<int64_t>(active ? fr : fa) * p.hop) & (kRing - 1));
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) {
-      A[n2] = exch[colA * kExchStride + n2];
-      B[n2] = exch[colB * kExchStride + n2];
-    }
-    __syncwarp();  // exch is reused as the sqmag buffer below
-    if (kSync) __syncthreads();
-    Dif<32, 32, 0>::run(A);
-    if (kSync) __syncthreads();
-    Dif<32, 32, 0>::run(B);
-
-    // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
-    float2 u = c0;
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const int d = 16 >> s;
-      const float ox = __shfl_xor_sync(0xffffffffu, u.x, d);
-      const float oy = __shfl_xor_sync(0xffffffffu, u.y, d);
-      if (lane & d) {
-        const float2 w = tab[(14 + s) * 32 + lane];
-        u = cmul(make_float2(ox - u.x, oy - u.y), w);
-      } else {
-        u = make_float2(u.x + ox, u.y + oy);
+      for (int n1 = 0; n1 < 64; ++n1) {
+        const int idx = 64 * n1 + 2 * lane;
+        const float2 sm = *reinterpret_cast<const float2*>(ring + ((pos0 + idx) & (kRing - 1)));
+        const float2 w = ldg2(p.win + idx);
+        v[bitrev(n1, 6)] = make_float2(sm.x * w.x, sm.y * w.y);
       }
-    }
-    float sq0, sqM;
-    {
-      const int pk2 = (32 - k2c) & 31;
-      const int plane = static_cast<int>(__brev(static_cast<unsigned>(pk2)) >> 27);
-      const float mx = __shfl_sync(0xffffffffu, u.x, plane);
-      const float my = __shfl_sync(0xffffffffu, u.y, plane);
-      untangle(u, make_float2(mx, my), tab[19 * 32 + lane], sq0, sqM);
-    }
-
-    // ---- untangle the real FFT (bins k = colA + 64*k2 and 2048 - k) and write |X|^2: HBM row (coalesced across lanes)
-    //      and the warp's shared buffer (padded, conflict-free) ----
-    if (kSync) __syncthreads();
-    float* row = (p.sqmag && active) ? p.sqmag + f * p.sqmag_row_stride : nullptr;
-    float* sqw = p.peak_count ? sq : nullptr;
-    post_all(A, B, tab[20 * 32 + lane], row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
-             sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
-    if (row) {
-      row[64 * k2c] = sq0;
-      if (lane == 0) row[kM] = sqM;
-    }
-    if (kSync) __syncthreads();
-    if (p.peak_count) {
-      sq[65 * k2c] = sq0;
-      if (lane == 0) sq[phys(kM)] = sqM;
-      __syncwarp();
-
-      // ---- peak scan: lane owns bins [64*lane, 64*lane+64) ----
-      // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
-      const int base = 65 * lane;
-      uint32_t mlo = 0, mhi = 0;
-      float l = lane ? sq[base - 2] : __int_as_float(0x7f800000);  // bin 0 is never a peak
-      float c = sq[base];
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float r = sq[j == 63 ? base + 65 : base + j + 1];
-        const bool is_peak = c > fmaxf(fmaxf(l, r), p.thr_below);
-        if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
-        else mhi |= is_peak ? (1u << (j - 32)) : 0u;
-        l = c;
-        c = r;
+      __syncthreads();  // every warp has its samples in registers: the ring may take the next round's data
+      {
+        const int next_last = min(f0 + 2 * WARPS - 1, fb - 1);
+        const int this_last = min(f0 + WARPS - 1, fb - 1);
+        pending = next_last > this_last;  // CTA-uniform
+        if (pending && threadIdx.x == 0)
+          ring_fill(ring, xs, static_cast<int64_t>(this_last) * p.hop + kN, static_cast<int64_t>(next_last) * p.hop + kN, &bar);
       }
-      uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
-      const int cnt = __popcll(mask);
-      int incl = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int slot = incl - cnt;
-      if (lane == 0 && active) p.peak_count[f] = total;
-      const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
-      if (!active) mask = 0;
-      while (mask && slot < p.max_peaks) {
-        const int j = __ffsll(static_cast<long long>(mask)) - 1;
-        mask &= mask - 1;
-        const int k = 64 * lane + j;
-        const float fl = 1e-37f;
-        const float sa = fmaxf(sq[phys(k - 1)], fl), sb = fmaxf(sq[phys(k)], fl), sc = fmaxf(sq[phys(k + 1)], fl);
-        // dB differences in log2 units, from ratios to the centre bin (well conditioned); MUFU.LG2 / MUFU.RCP precision
-        const float inv_b = __frcp_rn(sb);
-        const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);  // (alpha-beta), (gamma-beta) / (10 log10 2)
-        const float num = la - lc;
-        const float den = la + lc;
-        const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
-        constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
-        const float beta = kDbPerLog2 * __log2f(sb);
-        p.peak_bin[out_base + slot] = k;
-        p.peak_freq[out_base + slot] = (static_cast<float>(k) + pp) * p.bin_to_hz;
-        p.peak_db[out_base + slot] = beta - 0.25f * (kDbPerLog2 * num) * pp;
-        ++slot;
-      }
-      __syncwarp();  // the next frame overwrites the buffer
+      frame_body<true, kSplit>(v, p, tab, exch, lane, f, active);
     }
+    __syncthreads();
   }
 }
 
@@ -419,8 +601,10 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
     kern = vec2 ? (full ? stft4096_kernel<W, MB, SY, true, true> : stft4096_kernel<W, MB, SY, true, false>)     \
                 : (full ? stft4096_kernel<W, MB, SY, false, true> : stft4096_kernel<W, MB, SY, false, false>);  \
   } while (0)
-  switch (variant) {  // measured on B200, 32 x 60 s streams (profiles/sweep_stft_variants.sh): 0: 135.9, 1: 127.2, 2: 126.5,
-                      // 3: 139.5, 4: 144.9 Mframes/s
+  // measured on B200, 32 x 60 s streams, Mframes/s (profiles/README.md): 0 (4 warps x 3 CTAs, free running) 144;
+  // 1 (8x1, in step) 127; 2 (8x1, free) 127; 3 (12x1, in step) 140; 4 (4x3, in step) 153 <- default;
+  // 5 (4x3, in step, bulk-copy ring + split transpose) 147; 6 (4x2, in step, bulk-copy ring) 150
+  switch (variant) {
     case 0: CA_PICK(4, 3, false); break;
     case 1: CA_PICK(8, 1, true); break;
     case 2: CA_PICK(8, 1, false); break;
@@ -428,11 +612,44 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
     default: CA_PICK(4, 3, true); break;
   }
 #undef CA_PICK
+  const bool ring_ok = full && ctx->stft.hop % 4 == 0 && ctx->stft.hop <= 1024 && stream_stride % 4 == 0 &&
+                       reinterpret_cast<uintptr_t>(d_x) % 16 == 0 && frames < (1ll << 30) && variant >= 5;
+  if (ring_ok) {
+    constexpr int RW = 4;
+    const bool split = variant != 6;
+    auto rk = split ? stft4096_ring_kernel<RW, 3, true> : stft4096_ring_kernel<RW, 2, false>;
+    const size_t rsmem = sizeof(float) * kRing + sizeof(float2) * (kTabRows * 32 + RW * (split ? kExchFloat2 / 2 : kExchFloat2));
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
+    int rper_sm = 0;
+    CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper_sm, rk, RW * 32, rsmem));
+    if (rper_sm < 1) rper_sm = 1;
+    const int64_t rgrid_full = static_cast<int64_t>(ctx->sm_count) * rper_sm;
+    // units: contiguous frame ranges inside a stream, about 4 per CTA for balance
+    RingPlan rp{};
+    int64_t ups = (4 * rgrid_full + n_streams - 1) / n_streams;
+    if (ups < 1) ups = 1;
+    int64_t fpu = (frames + ups - 1) / ups;
+    fpu = (fpu + RW - 1) / RW * RW;
+    if (fpu < 8 * RW) fpu = 8 * RW;  // amortise the unit prologue (a full window) over at least 8 rounds
+    ups = (frames + fpu - 1) / fpu;
+    rp.units_per_stream = static_cast<int32_t>(ups);
+    rp.frames_per_unit = static_cast<int32_t>(fpu);
+    const int64_t units = ups * n_streams;
+    if (units < (1ll << 31)) {
+      rp.total_units = static_cast<int32_t>(units);
+      const int64_t rgrid = std::min<int64_t>(rgrid_full, units);
+      rk<<<static_cast<unsigned>(rgrid), RW * 32, rsmem, stream>>>(a, rp);
+      CA_CUDA_OK(ctx, cudaGetLastError());
+      ctx->launches += 1;
+      return CA_OK;
+    }
+  }
   const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
+  if (const char* e = getenv("CA_STFT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning experiments
   int64_t grid = static_cast<int64_t>(ctx->sm_count) * per_sm;
   const int64_t need = (total + WARPS - 1) / WARPS;
   if (grid > need) grid = need;
