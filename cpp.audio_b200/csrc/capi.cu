@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" layer declared in include/cpp_audio_b200.h: context, argument checks, host-buffer wrappers.
 #include <math.h>
 
+#include <algorithm>
 #include <new>
 
 #include "ctx.hpp"
@@ -29,7 +30,8 @@ int ca_init(int device, ca_ctx** out) {
     return CA_ERR_UNSUPPORTED;
   }
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream2, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return CA_ERR_CUDA;
   }
@@ -46,6 +48,7 @@ void ca_destroy(ca_ctx* ctx) {
   for (int i = 0; i < 8; ++i)
     if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
   delete ctx;
 }
 
@@ -134,25 +137,64 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
   if (!rc && any_peak) rc = ensure_scratch(ctx, 4, pk_bytes ? pk_bytes : 4);
   if (!rc && any_peak) rc = ensure_scratch(ctx, 5, cnt_bytes);
   if (rc) return rc;
-  cudaStream_t s = ctx->own_stream;
-  CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[0], h_x, x_bytes, cudaMemcpyHostToDevice, s));
-  rc = stft_analyze(ctx, static_cast<const float*>(ctx->d_scratch[0]), n_samples, n_streams, stream_stride,
-                    h_sqmag ? static_cast<float*>(ctx->d_scratch[1]) : nullptr, sqmag_row_stride,
-                    any_peak ? static_cast<int32_t*>(ctx->d_scratch[2]) : nullptr,
-                    any_peak ? static_cast<float*>(ctx->d_scratch[3]) : nullptr,
-                    any_peak ? static_cast<float*>(ctx->d_scratch[4]) : nullptr,
-                    any_peak ? static_cast<int32_t*>(ctx->d_scratch[5]) : nullptr, s);
-  if (rc) return rc;
-  if (h_sqmag) CA_CUDA_OK(ctx, cudaMemcpyAsync(h_sqmag, ctx->d_scratch[1], sq_bytes, cudaMemcpyDeviceToHost, s));
-  if (any_peak) {
-    if (pk_bytes) {
-      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_bin, ctx->d_scratch[2], pk_bytes, cudaMemcpyDeviceToHost, s));
-      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_freq, ctx->d_scratch[3], pk_bytes, cudaMemcpyDeviceToHost, s));
-      CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_db, ctx->d_scratch[4], pk_bytes, cudaMemcpyDeviceToHost, s));
+  // Copy/compute pipeline over two streams: the work is cut into chunks (groups of whole streams, or frame ranges of a
+  // stream with their window-hop halo); chunk c+1's H2D overlaps chunk c's kernel and D2H (separate copy engines).
+  const int W = ctx->stft.window, hop = ctx->stft.hop, P = ctx->stft.max_peaks;
+  float* d_x = static_cast<float*>(ctx->d_scratch[0]);
+  float* d_sq = h_sqmag ? static_cast<float*>(ctx->d_scratch[1]) : nullptr;
+  int32_t* d_pb = any_peak ? static_cast<int32_t*>(ctx->d_scratch[2]) : nullptr;
+  float* d_pf = any_peak ? static_cast<float*>(ctx->d_scratch[3]) : nullptr;
+  float* d_pd = any_peak ? static_cast<float*>(ctx->d_scratch[4]) : nullptr;
+  int32_t* d_pc = any_peak ? static_cast<int32_t*>(ctx->d_scratch[5]) : nullptr;
+  cudaStream_t lanes[2] = {ctx->own_stream, ctx->own_stream2};
+  const int64_t target_chunks = 8;
+  int64_t streams_per_chunk = n_streams >= target_chunks ? (n_streams + target_chunks - 1) / target_chunks : 1;
+  int64_t ranges_per_stream = n_streams >= target_chunks ? 1 : (target_chunks + n_streams - 1) / n_streams;
+  if (ranges_per_stream > frames) ranges_per_stream = frames;
+  // 16-byte aligned spans keep the vector / bulk-copy kernels eligible
+  const bool can_split_frames = (hop % 4 == 0) && (stream_stride % 4 == 0);
+  if (!can_split_frames) ranges_per_stream = 1;
+  int lane_i = 0;
+  for (int64_t s0 = 0; s0 < n_streams; s0 += streams_per_chunk) {
+    const int64_t ns = std::min(streams_per_chunk, n_streams - s0);
+    for (int64_t r = 0; r < ranges_per_stream; ++r) {
+      const int64_t f0 = frames * r / ranges_per_stream, f1 = frames * (r + 1) / ranges_per_stream;
+      if (f1 <= f0) continue;
+      cudaStream_t s = lanes[lane_i++ & 1];
+      const int64_t a0 = f0 * hop, a1 = (f1 - 1) * hop + W;  // sample span of the frame range
+      const int64_t row0 = s0 * frames + f0;
+      int rcc;
+      if (ranges_per_stream == 1) {  // whole streams: one contiguous copy
+        const size_t off = static_cast<size_t>(s0) * stream_stride;
+        const size_t n = static_cast<size_t>(ns - 1) * stream_stride + n_samples;
+        CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x + off, h_x + off, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        rcc = stft_analyze(ctx, d_x + off, n_samples, ns, stream_stride, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
+                           d_pb ? d_pb + row0 * P : nullptr, d_pf ? d_pf + row0 * P : nullptr, d_pd ? d_pd + row0 * P : nullptr,
+                           d_pc ? d_pc + row0 : nullptr, s);
+      } else {  // ns == 1: a frame range of stream s0
+        const size_t off = static_cast<size_t>(s0) * stream_stride + a0;
+        CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x + off, h_x + off, sizeof(float) * (a1 - a0), cudaMemcpyHostToDevice, s));
+        rcc = stft_analyze(ctx, d_x + off, a1 - a0, 1, a1 - a0, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
+                           d_pb ? d_pb + row0 * P : nullptr, d_pf ? d_pf + row0 * P : nullptr, d_pd ? d_pd + row0 * P : nullptr,
+                           d_pc ? d_pc + row0 : nullptr, s);
+      }
+      if (rcc) return rcc;
+      const int64_t nrows = ns * (ranges_per_stream == 1 ? frames : f1 - f0);
+      if (h_sqmag)
+        CA_CUDA_OK(ctx, cudaMemcpyAsync(h_sqmag + row0 * sqmag_row_stride, d_sq + row0 * sqmag_row_stride,
+                                        sizeof(float) * nrows * sqmag_row_stride, cudaMemcpyDeviceToHost, s));
+      if (any_peak) {
+        if (P > 0) {
+          CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_bin + row0 * P, d_pb + row0 * P, 4 * nrows * P, cudaMemcpyDeviceToHost, s));
+          CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_freq + row0 * P, d_pf + row0 * P, 4 * nrows * P, cudaMemcpyDeviceToHost, s));
+          CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_db + row0 * P, d_pd + row0 * P, 4 * nrows * P, cudaMemcpyDeviceToHost, s));
+        }
+        CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_count + row0, d_pc + row0, 4 * nrows, cudaMemcpyDeviceToHost, s));
+      }
     }
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(h_peak_count, ctx->d_scratch[5], cnt_bytes, cudaMemcpyDeviceToHost, s));
   }
-  CA_CUDA_OK(ctx, cudaStreamSynchronize(s));
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(lanes[0]));
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(lanes[1]));
   return CA_OK;
 }
 

@@ -13,7 +13,8 @@ struct ca_ctx {
   int sm_count = 0;
   int64_t launches = 0;
   std::string last_error;
-  cudaStream_t own_stream = nullptr;  // used by the *_host entry points
+  cudaStream_t own_stream = nullptr;   // used by the *_host entry points
+  cudaStream_t own_stream2 = nullptr;  // second lane of the copy/compute pipeline of ca_stft_analyze_host
 
   // analysis plan
   bool stft_planned = false;

@@ -140,7 +140,7 @@ __device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2
 __device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
 
 // Everything after the load: stage-1 FFT, transpose, stage-2 FFTs, untangling, stores, peak extraction (see file header).
-template <bool kSync, bool kSplit>
+template <int kSync, bool kSplit>
 __device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, const float2* __restrict__ tab,
                                            float2* __restrict__ exch, const int lane, const int64_t f, const bool active) {
   float* sq = reinterpret_cast<float*>(exch);
@@ -148,8 +148,16 @@ __device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, c
   const int colB = lane ? 64 - lane : 32;
   const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
   // ---- stage 1: 64-point FFT over n1 ----
-  if (kSync) __syncthreads();
-  Dit<64, 64, 0>::run(v);  // natural order out: v[k1]
+  if (kSync == 1 || kSync == 3) __syncthreads();
+  if constexpr (kSync == 3) {  // finer lock step: the 64-point FFT in three pieces
+    Dit<64, 32, 0>::run(v);
+    __syncthreads();
+    Dit<64, 32, 32>::run(v);
+    __syncthreads();
+    Dit<64, 64, 0>::stage(v, std::make_integer_sequence<int, 32>{});
+  } else {
+    Dit<64, 64, 0>::run(v);  // natural order out: v[k1]
+  }
   const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
 
   if (kSync) __syncthreads();
@@ -197,7 +205,7 @@ __device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, c
   __syncwarp();  // exch is reused as the sqmag buffer below
   if (kSync) __syncthreads();
   Dit<32, 32, 0>::run(A);
-  if (kSync) __syncthreads();
+  if (kSync == 1 || kSync == 3) __syncthreads();
   Dit<32, 32, 0>::run(B);
 
   // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
@@ -234,7 +242,7 @@ __device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, c
     row[64 * k2c] = sq0;
     if (lane == 0) row[kM] = sqM;
   }
-  if (kSync) __syncthreads();
+  if (kSync == 1 || kSync == 3) __syncthreads();
   if (p.peak_count) {
     sq[65 * k2c] = sq0;
     if (lane == 0) sq[phys(kM)] = sqM;
@@ -329,7 +337,7 @@ __device__ __forceinline__ void build_tables(float2* tab) {
 // kSync: the warps of the CTA walk the frame code in step (one __syncthreads per phase). The frame body is ~70 KB of
 // straight-line SASS; unsynchronised warps each stream it from L2 on their own and instruction fetch becomes the limiter
 // (ncu: stall_no_inst 26 % of samples, profiles/), in step they share the fetches.
-template <int WARPS, int MINB, bool kSync, bool kVec2, bool kFull>
+template <int WARPS, int MINB, int kSync, bool kVec2, bool kFull>
 __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid_constant__ StftArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_ring_kernel(const _
         if (pending && threadIdx.x == 0)
           ring_fill(ring, xs, static_cast<int64_t>(this_last) * p.hop + kN, static_cast<int64_t>(next_last) * p.hop + kN, &bar);
       }
-      frame_body<true, kSplit>(v, p, tab, exch, lane, f, active);
+      frame_body<1, kSplit>(v, p, tab, exch, lane, f, active);
     }
     __syncthreads();
   }
@@ -605,11 +613,12 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   // 1 (8x1, in step) 127; 2 (8x1, free) 127; 3 (12x1, in step) 140; 4 (4x3, in step) 153 <- default;
   // 5 (4x3, in step, bulk-copy ring + split transpose) 147; 6 (4x2, in step, bulk-copy ring) 150
   switch (variant) {
-    case 0: CA_PICK(4, 3, false); break;
-    case 1: CA_PICK(8, 1, true); break;
-    case 2: CA_PICK(8, 1, false); break;
-    case 3: CA_PICK(12, 1, true); break;
-    default: CA_PICK(4, 3, true); break;
+    case 0: CA_PICK(4, 3, 0); break;
+    case 1: CA_PICK(8, 1, 1); break;
+    case 3: CA_PICK(12, 1, 1); break;
+    case 7: CA_PICK(4, 3, 2); break;
+    case 8: CA_PICK(4, 3, 3); break;
+    default: CA_PICK(4, 3, 1); break;
   }
 #undef CA_PICK
   const bool ring_ok = full && ctx->stft.hop % 4 == 0 && ctx->stft.hop <= 1024 && stream_stride % 4 == 0 &&

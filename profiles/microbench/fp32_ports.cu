@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(256) k(const float* __restrict__ in, float* ou
 }
 
 template <int MODE>
-void run(const char* name, const float* d_in, float* d_out, int sms, float clk_ghz, int per_iter) {
+void run(const char* name, const float* d_in, float* d_out, int sms, float clk_ghz, int per_iter, int warps_per_sm = 64) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int blocks = sms * 8, threads = 256;
+  const int threads = warps_per_sm >= 8 ? 256 : 32 * warps_per_sm;
+  const int blocks = sms * (warps_per_sm * 32 / threads);
   k<MODE><<<blocks, threads>>>(d_in, d_out, 16);
   cudaEventRecord(e0);
   k<MODE><<<blocks, threads>>>(d_in, d_out, ITERS);
@@ -49,7 +50,7 @@ void run(const char* name, const float* d_in, float* d_out, int sms, float clk_g
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   const double winst = double(blocks) * (threads / 32) * ITERS * NACC * per_iter;
-  printf("%-52s %8.3f ms  %6.3f warp-instr/clk/SM (at %.3f GHz)\n", name, ms, winst / (ms * 1e-3) / (clk_ghz * 1e9) / sms, clk_ghz);
+  printf("%-52s %2d warps/SM %8.3f ms  %6.3f warp-instr/clk/SM (at %.3f GHz)\n", name, warps_per_sm, ms, winst / (ms * 1e-3) / (clk_ghz * 1e9) / sms, clk_ghz);
 }
 
 int main() {
@@ -73,5 +74,11 @@ int main() {
   run<2>("FFMA  a=fma(a,m,c)    (m,c shared: reuse cache)", d_in, d_out, p.multiProcessorCount, ghz, 1);
   run<4>("FFMA  a=fma(a,imm,imm)", d_in, d_out, p.multiProcessorCount, ghz, 1);
   run<6>("pair  d=fma(-k,y,d); y=y+d (oscillator step)", d_in, d_out, p.multiProcessorCount, ghz, 2);
+  // occupancy sensitivity: the production kernels run 8-16 warps/SM with long independent chains
+  for (int w : {4, 8, 12, 16, 32}) {
+    run<0>("FADD  a=a+b  (16 independent chains per thread)", d_in, d_out, p.multiProcessorCount, ghz, 1, w);
+    run<4>("FFMA  imm    (16 independent chains per thread)", d_in, d_out, p.multiProcessorCount, ghz, 1, w);
+    run<6>("pair  oscillator step (16 chains)", d_in, d_out, p.multiProcessorCount, ghz, 2, w);
+  }
   return 0;
 }
