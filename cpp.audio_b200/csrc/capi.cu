@@ -266,6 +266,12 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
   return CA_OK;
 }
 
+int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
+                              int64_t n_streams, float* h_out, int64_t* h_stats) {
+  if (!ctx) return CA_ERR_INVALID;
+  return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
+}
+
 int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops) {
   if (!ctx) return CA_ERR_INVALID;
   return measure_fp32_peak(ctx, tflops);

@@ -22,6 +22,7 @@ struct ca_ctx {
   int n_fft = 0;
   float* d_window = nullptr;  // [n_fft] window, zero padded, pre-scaled (see stft.cu)
   float thr_sq = 0.f;
+  bool stft_freq_as_offset = false;  // internal switch used by the round trip (see stft.cu)
 
   // generic FFT scratch (twiddle tables, four-step buffers)
   float2* d_fft_tw = nullptr;
@@ -73,6 +74,8 @@ int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float
 int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
 int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream);
 int measure_fp32_peak(ca_ctx* ctx, double* tflops);
+int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
+                   float* h_out, int64_t* h_stats);
 void stft_release(ca_ctx* ctx);
 void rfft_release(ca_ctx* ctx);
 void oscbank_release(ca_ctx* ctx);

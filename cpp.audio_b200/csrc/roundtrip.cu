@@ -1,0 +1,546 @@
+// roundtrip.cu — analysis -> pitch pipeline -> resynthesis of whole streams (BASELINE config 4).
+//
+// Reference: the offline RtResynth loop (source/rt.resynth.lib.cpp:1185-1235). Per analysis frame, RtResynth::step
+// (:1670-1759) runs the pitch pipeline of source/rt.resynth.lib.algo.cpp on the peak list and synthesize_sounds (:264-382)
+// posts NoteOn / NoteChange / NoteOff to a pool of ResynthElement voices (:5-18); the voices are stepped one sample at a
+// time (oscillator with a per-sample frequency glide, include/audioelement.h:2706-2817; volume low-pass :1195-1216;
+// AHDSR envelope :666-1099; stereo pan include/stereo.h:18-27).
+//
+// Here:
+//   1. K2 (stft.cu) extracts the peaks of every frame of every stream on the GPU.
+//   2. Host threads (one stream each) run the frame-sequential pitch pipeline and note bookkeeping — control-rate code,
+//      O(peaks) per frame — and emit, per frame interval ("tile" = hop samples) and per sounding note, a SEGMENT: the
+//      closed-form description of that note over the tile. Every per-sample recurrence of the reference voice has a
+//      closed form in the step index (the glide's time warp cur' = alpha*cur + beta is affine, the low-pass and the envelope
+//      are first order / piecewise linear), so a segment is restartable at tile boundaries and tiles are independent.
+//   3. tracks_kernel renders the tiles: one warp per tile, lanes = consecutive samples, phases and glide sums in FP64
+//      (the reference runs in double and phase errors accumulate over the whole stream), the rest in FP32.
+//
+// Unpinned pieces (oracle/SPEC.md): S8 one-pole volume filter, S9 loudness ordering = raw volume, S10 start phase / pan
+// from a hash of the note id instead of the external mersenne<> generator.
+#include <math.h>
+
+#include <algorithm>
+#include <climits>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "ctx.hpp"
+
+namespace ca {
+
+namespace {
+
+struct __align__(8) Segment {
+  double phase_start;  // oscillator angle (units of pi rad, [0,2)) before the first step of the tile
+  double from, to;     // glide end points (angle increments)
+  double K, L;         // f_i = from + K*(exp(i*L) - 1) for glide steps i < m, f_i = to afterwards
+  double c1;           // K / lambda:  P_i = sum_{l<=i} f_l = (i+1)*(from-K) + c1*(exp((i+1)*L) - 1)
+  double P_before;     // P_{i0-1} (0 when i0 == 0)
+  double P_m1;         // P_{m-1}
+  int32_t i0;          // glide step index of the tile's first sample
+  int32_t m;           // first clamped glide step; 0 = steady at `to`
+  float vol_x, vol_dy; // volume = x + dy*exp(-pi*Mv)
+  float cap;           // max filter increment (2/stride)
+  int32_t regime;      // 0: Mv = cap*(j+1); 1: Mv = P-sum since tile start; 2: f-limited until istar then cap; 3: cap then f
+  int32_t istar;       // tile-relative index where a mixed regime switches
+  float m_star;        // Mv accumulated over [0, istar)
+  int32_t c0;          // envelope step counter at the tile's first sample
+  int32_t attack, hold, decay, release;
+  float sustain;
+  int32_t rel_base;    // tile-relative index of the first release step (may be negative); INT_MAX = not released
+  float top;           // envelope value when the release started
+  float gl, gr;
+};
+
+struct TileArgs {
+  const Segment* segs;
+  const int64_t* tile_seg_begin;  // [tiles+1] CSR into segs
+  const int64_t* tile_sample0;    // [tiles] first output sample (absolute index into out / 2)
+  const int32_t* tile_len;        // [tiles]
+  int64_t n_tiles;
+  float* out;                     // interleaved stereo
+};
+
+__device__ __forceinline__ float alias_gain(float ai) {  // freqAliasingMultiplicator, include/audioelement.h:466-483
+  if (ai == 0.f) return 1.f;
+  const float h = 1.f / ai;
+  if (h < 1.f) return 0.f;
+  if (h > 4.f) return 1.f;
+  return (h - 1.f) * (1.f / 3.f);
+}
+
+constexpr int kMaxTile = 1024;  // samples per tile (hop); 32 steps of 32 lanes
+
+__global__ void __launch_bounds__(128) tracks_kernel(const __grid_constant__ TileArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (tile >= a.n_tiles) return;
+  const int len = a.tile_len[tile];
+  const int64_t s_begin = a.tile_seg_begin[tile], s_end = a.tile_seg_begin[tile + 1];
+  float2* out = reinterpret_cast<float2*>(a.out) + a.tile_sample0[tile];
+  for (int j0 = 0; j0 < len; j0 += 32) {
+    const int j = j0 + lane;  // tile-relative sample index
+    float accl = 0.f, accr = 0.f;
+    for (int64_t si = s_begin; si < s_end; ++si) {
+      const Segment& g = a.segs[si];
+      // ---- frequency glide and phase (FP64) ----
+      const int i = g.i0 + j;  // glide step index
+      double f, P;             // emitted increment at this step, sum of increments over glide steps 0..i
+      if (i < g.m) {
+        // expm1, not exp()-1: when `to` is within 1e-10 of `from`, c1 = K/lambda is ~1e14 and the rounding of exp()-1
+        // (1e-16) would reach the phase
+        P = static_cast<double>(i + 1) * (g.from - g.K) + g.c1 * expm1(g.L * static_cast<double>(i + 1));
+        f = g.from + g.K * expm1(g.L * static_cast<double>(i));
+      } else {
+        P = g.P_m1 + static_cast<double>(i - g.m + 1) * g.to;
+        f = g.to;
+      }
+      const double adv = P - g.P_before;  // phase advance since the tile start, this step included
+      double ph = g.phase_start + adv;
+      ph -= 2.0 * floor(0.5 * ph);
+      const float s = sinpif(static_cast<float>(ph));
+      const float ff = static_cast<float>(f);
+      // ---- volume low-pass (SPEC S8): y = x + dy * exp(-pi * sum of min(cap, f)) ----
+      float mv;
+      if (g.regime == 0) mv = g.cap * static_cast<float>(j + 1);
+      else if (g.regime == 1) mv = static_cast<float>(adv);
+      else if (g.regime == 2) {  // f-limited first, cap from istar on
+        if (j < g.istar) mv = static_cast<float>(adv);
+        else mv = g.m_star + g.cap * static_cast<float>(j - g.istar + 1);
+      } else {  // cap first, f-limited from istar on: m_star holds cap*istar - (advance before istar)
+        if (j < g.istar) mv = g.cap * static_cast<float>(j + 1);
+        else mv = g.m_star + static_cast<float>(adv);
+      }
+      const float vol = g.vol_x + g.vol_dy * __expf(-3.14159265358979f * mv);
+      // ---- envelope (include/audioelement.h:960-1000, :733-742) ----
+      float env;
+      if (j >= g.rel_base) {
+        const int jr = j - g.rel_base + 1;
+        env = jr >= g.release ? 0.f : g.top - g.top * (static_cast<float>(jr) / static_cast<float>(g.release));
+      } else {
+        int c = g.c0 + j;
+        if (c < 1) env = 0.f;
+        else if (c <= g.attack) env = static_cast<float>(c) / static_cast<float>(g.attack);
+        else if ((c -= g.attack) <= g.hold) env = 1.f;
+        else if ((c -= g.hold) <= g.decay) env = 1.f + (g.sustain - 1.f) * (static_cast<float>(c) / static_cast<float>(g.decay));
+        else env = g.sustain;
+      }
+      const float y = vol * (alias_gain(ff) * s * env);
+      accl = fmaf(g.gl, y, accl);
+      accr = fmaf(g.gr, y, accr);
+    }
+    if (j < len) out[j] = make_float2(accl, accr);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side: pitch pipeline + note bookkeeping of one stream -> segments
+// ---------------------------------------------------------------------------------------------------------------
+
+inline float hash_unit(uint64_t id, uint64_t salt) {  // SPEC S10
+  uint64_t z = id * 0x9E3779B97F4A7C15ull + salt * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+}
+
+struct Glide {  // InterpolatedFreq in closed form
+  double from = 0, to = 0, K = 0, L = 0, c1 = 0, P_m1 = 0;
+  int32_t m = 0;   // first clamped step
+  int64_t i = 0;   // next glide step index
+  void start(double from_, double to_, double dur) {
+    from = from_;
+    to = to_;
+    i = 0;
+    if (to == from) {  // C = 1: the first step emits `to`, after which the steady-state shortcut holds (:2765-2767)
+      m = 0;
+      K = L = c1 = P_m1 = 0;
+      return;
+    }
+    const double delta = to - from;
+    const double C = -log(from / to) / delta;            // :2815
+    const double lambda = C * delta / dur;               // cur' = (1+lambda)*cur + beta
+    const double beta = C * (from + 0.5 * delta / dur);  // :2783-2784
+    K = delta * beta / (dur * lambda);
+    L = log1p(lambda);
+    c1 = K / lambda;
+    // first step whose cur + .5 exceeds dur (:2768-2770): cur_i = beta*(alpha^i - 1)/lambda
+    const double x = log1p(lambda * (dur - 0.5) / beta) / L;
+    double mf = floor(x) + 1.0;
+    if (mf < 1.0) mf = 1.0;
+    if (mf > 1e9) mf = 1e9;
+    m = static_cast<int32_t>(mf);
+    P_m1 = P(m - 1);
+  }
+  double f_at(int64_t k) const { return k < m ? from + K * expm1(L * static_cast<double>(k)) : to; }
+  double P(int64_t k) const {  // sum of f over steps 0..k
+    if (k < 0) return 0.0;
+    if (k < m) return static_cast<double>(k + 1) * (from - K) + c1 * expm1(L * static_cast<double>(k + 1));
+    return P_m1 + static_cast<double>(k - m + 1) * to;
+  }
+};
+
+struct Note {
+  int64_t id = 0;
+  double pitch = 0;      // current midi pitch (tracking key)
+  Glide glide;
+  double phase = 0;      // units of pi rad, [0,2)
+  double f_last = 0;     // last emitted increment
+  double vol_x = 0, vol_y = 0;
+  int64_t n_on = 0;
+  int32_t attack = 0, hold = 0, decay = -1, release = 0;
+  int32_t next_min_change = 0;
+  int64_t n_off = -1;    // sample of the first release step
+  double top = 0;
+  float gl = 1, gr = 1;
+  bool tracked = true;   // still in played_pitches
+};
+
+struct StreamResult {
+  std::vector<Segment> segs;
+  std::vector<int64_t> tile_seg_begin;  // per tile
+  int64_t notes_started = 0, notes_dropped = 0;
+};
+
+inline int32_t min_change_for(double ai) {  // Enveloped::setAngleIncrements, include/audioelement.h:218-225
+  const double period = ai == 0.0 ? 1.0 : 2.0 / fabs(ai);
+  return static_cast<int32_t>(0.5f + 2.5 * period);
+}
+
+double env_pressed_value(const Note& n, int64_t c, float sustain) {
+  if (c < 1) return 0.0;
+  if (c <= n.attack) return static_cast<double>(c) / n.attack;
+  c -= n.attack;
+  if (c <= n.hold) return 1.0;
+  c -= n.hold;
+  const int32_t d = n.decay < 0 ? 0 : n.decay;
+  if (c <= d) return 1.0 + (static_cast<double>(sustain) - 1.0) * static_cast<double>(c) / d;
+  return sustain;
+}
+
+void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, const int32_t* peak_bin,
+                const float* peak_off, const float* peak_db, const int32_t* peak_count, StreamResult& res) {
+  const int W = prm.stft.window, hop = prm.stft.hop, sr = prm.stft.sample_rate, P = prm.stft.max_peaks;
+  const int n_fft = ca_fft_length_for(W, 1);
+  const double bin_hz = static_cast<double>(sr) / n_fft;
+  // AHDSREnvelopeBase::setAHDSR (include/audioelement.h:923-952)
+  const int32_t min_dt = sr / 1000;
+  const bool has_decay = prm.env.sustain < 0.999999;
+  const float sustain = has_decay ? std::min(std::max(prm.env.sustain, 0.f), 1.f) : 1.f;
+  const int32_t A = std::max(prm.env.attack, min_dt), H = std::max(prm.env.hold, 0);
+  const int32_t D = has_decay ? std::max(prm.env.decay, min_dt) : 0, R = std::max(prm.env.release, min_dt);
+  const double cap = 2.0 / hop;  // setMaxFilterIncrement(2/stride), source/rt.resynth.lib.cpp:106
+
+  std::vector<Note> notes;       // sounding notes (tracked or releasing)
+  std::vector<int> played;       // indices into notes of tracked notes, sorted by pitch
+  struct PV { double pitch, vol; };
+  std::vector<PV> pv, reduced, tuned;
+  std::vector<int> change, order, next_played;
+  std::vector<char> keep;
+
+  res.tile_seg_begin.assign(frames + 1, 0);
+  for (int64_t k = 0; k < frames; ++k) {
+    const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;  // events of frame k act from this sample on
+    const int len = static_cast<int>(std::min<int64_t>(hop, n_samples - n_k));
+    // ---------------- pitch pipeline (source/rt.resynth.lib.algo.cpp) ----------------
+    pv.clear();
+    const int cnt = std::min(peak_count[k], P);
+    for (int i = 0; i < cnt; ++i) {
+      const double freq = (static_cast<double>(peak_bin[k * P + i]) + static_cast<double>(peak_off[k * P + i])) * bin_hz;
+      if (freq > 0) pv.push_back({69. + 12. * log2(freq / 440.f), pow(10.0, static_cast<double>(peak_db[k * P + i]) / 20.0)});
+    }
+    reduced.clear();
+    {
+      bool open = false;
+      double mn = 0, mx = 0, sv = 0, spv = 0;
+      auto close = [&] {
+        if (open && !(sv < prm.min_volume)) reduced.push_back({spv / sv, sv});
+        open = false;
+      };
+      for (auto& q : pv) {
+        if (open && std::max({mn, mx, q.pitch}) - std::min({mn, mx, q.pitch}) > prm.nearby_distance_tones) close();
+        if (!open) {
+          open = true;
+          mn = mx = q.pitch;
+          sv = spv = 0;
+        } else {
+          mn = std::min(mn, q.pitch);
+          mx = std::max(mx, q.pitch);
+        }
+        sv += q.vol;
+        spv += q.pitch * q.vol;
+      }
+      close();
+    }
+    tuned.clear();
+    for (auto& q : reduced) {
+      if (!tuned.empty() && fabs(tuned.back().pitch - q.pitch) < 0.0001f) tuned.back().vol += q.vol;
+      else tuned.push_back(q);
+    }
+    change.assign(tuned.size(), -1);
+    keep.assign(played.size(), 0);
+    {
+      size_t it = 0;
+      for (size_t i = 0; i < tuned.size(); ++i) {
+        for (; it < played.size(); ++it) {
+          const double pp = notes[played[it]].pitch;
+          if (pp < tuned[i].pitch - prm.max_track_pitches) continue;
+          if (pp <= tuned[i].pitch + prm.max_track_pitches) {
+            change[i] = static_cast<int>(it);
+            keep[it] = 1;
+            ++it;
+          }
+          break;
+        }
+      }
+    }
+    order.resize(tuned.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int x, int y) { return static_cast<float>(tuned[x].vol) > static_cast<float>(tuned[y].vol); });
+    // ---------------- events (synthesize_sounds, source/rt.resynth.lib.cpp:264-382) ----------------
+    for (size_t i = 0; i < played.size(); ++i)
+      if (!keep[i]) {  // NoteOff -> onKeyReleased(0), include/audioelement.h:769-781, :836-841
+        Note& n = notes[played[i]];
+        n.tracked = false;
+        n.n_off = n_k;
+        n.top = env_pressed_value(n, n_k - n.n_on, sustain);
+        n.release = std::max(n.next_min_change, R);
+      }
+    next_played.clear();
+    for (size_t i = 0; i < played.size(); ++i)
+      if (keep[i]) next_played.push_back(played[i]);
+    for (int idx : order) {
+      const float new_freq = static_cast<float>(440.f * pow(pow(2., 1. / 12.), tuned[idx].pitch - 69.));
+      const float volume = static_cast<float>(prm.gain * tuned[idx].vol / 0.1f);
+      const double ai = static_cast<double>(2 * new_freq / sr);  // freq_to_angle_increment in float
+      if (change[idx] >= 0) {                                      // NoteChange, include/gen.crtp.h:595-618
+        Note& n = notes[played[change[idx]]];
+        n.pitch = tuned[idx].pitch;
+        n.vol_x = static_cast<double>(0.1f * volume);
+        n.next_min_change = min_change_for(ai);
+        n.glide.start(n.f_last, ai, hop);                          // InterpolatedFreq::setAngleIncrements, :2752-2762
+      } else {
+        if (volume <= 0) continue;
+        int sounding = 0;
+        for (auto& n : notes) sounding += 1;  // every entry of `notes` still holds a channel
+        if (sounding >= prm.max_channels) {
+          ++res.notes_dropped;
+          ++res.notes_started;
+          continue;
+        }
+        ++res.notes_started;
+        Note n;
+        n.id = res.notes_started;
+        n.pitch = tuned[idx].pitch;
+        n.vol_x = n.vol_y = static_cast<double>(0.1f * volume);
+        n.n_on = n_k;
+        n.next_min_change = min_change_for(ai);
+        n.attack = std::max(n.next_min_change, A);
+        n.hold = H;
+        n.decay = -1;
+        n.glide.start(ai, ai, hop);
+        n.f_last = ai;
+        double a0 = static_cast<double>(hash_unit(static_cast<uint64_t>(n.id), 2));
+        a0 -= 2.0 * floor(0.5 * a0);
+        n.phase = a0;
+        double pan = static_cast<double>(prm.stereo_spread * hash_unit(static_cast<uint64_t>(n.id), 1));
+        pan = std::min(1.0, std::max(-1.0, pan));
+        n.gl = static_cast<float>(cos(0.25 * 3.14159265358979323846 * (pan + 1.0)));
+        n.gr = static_cast<float>(sin(0.25 * 3.14159265358979323846 * (pan + 1.0)));
+        notes.push_back(n);
+        next_played.push_back(static_cast<int>(notes.size()) - 1);
+      }
+    }
+    std::stable_sort(next_played.begin(), next_played.end(), [&](int x, int y) { return notes[x].pitch < notes[y].pitch; });
+    played.swap(next_played);
+
+    // ---------------- one segment per sounding note for this tile, then advance the note states ----------------
+    res.tile_seg_begin[k] = static_cast<int64_t>(res.segs.size());
+    if (len > 0) {
+      for (auto& n : notes) {
+        Segment g{};
+        const int64_t i0 = n.glide.i;
+        g.phase_start = n.phase;
+        g.from = n.glide.from;
+        g.to = n.glide.to;
+        g.K = n.glide.K;
+        g.L = n.glide.L;
+        g.c1 = n.glide.c1;
+        g.P_m1 = n.glide.P_m1;
+        g.m = n.glide.m;
+        g.i0 = static_cast<int32_t>(std::min<int64_t>(i0, INT_MAX / 2));
+        g.P_before = n.glide.P(i0 - 1);
+        if (i0 >= n.glide.m) {  // steady for the whole tile: re-base so that the step index stays small
+          g.i0 = 0;
+          g.m = 0;
+          g.P_m1 = 0;  // P(-1)
+          g.P_before = 0;
+        }
+        // volume regime over the tile
+        const double fa = n.glide.f_at(i0), fb = n.glide.f_at(i0 + len - 1);
+        g.cap = static_cast<float>(cap);
+        g.vol_x = static_cast<float>(n.vol_x);
+        g.vol_dy = static_cast<float>(n.vol_y - n.vol_x);
+        double mv_end;
+        const double adv_end = n.glide.P(i0 + len - 1) - n.glide.P(i0 - 1);
+        if (std::min(fa, fb) >= cap) {
+          g.regime = 0;
+          mv_end = cap * len;
+        } else if (std::max(fa, fb) < cap) {
+          g.regime = 1;
+          mv_end = adv_end;
+        } else {  // the glide crosses the cap inside the tile: find the switch by walking the (at most hop) steps
+          int istar = 0;
+          const bool f_first = fa < cap;
+          while (istar < len && ((n.glide.f_at(i0 + istar) < cap) == f_first)) ++istar;
+          g.istar = istar;
+          const double adv_star = n.glide.P(i0 + istar - 1) - n.glide.P(i0 - 1);
+          if (f_first) {
+            g.regime = 2;
+            g.m_star = static_cast<float>(adv_star);
+            mv_end = adv_star + cap * (len - istar);
+          } else {
+            g.regime = 3;
+            g.m_star = static_cast<float>(cap * istar - adv_star);
+            mv_end = cap * istar + (adv_end - adv_star);
+          }
+        }
+        // envelope
+        g.c0 = static_cast<int32_t>(n_k - n.n_on + 1);
+        if (n.decay < 0 && (n_k + len - n.n_on) > static_cast<int64_t>(n.attack) + n.hold)  // decay latched when entered
+          n.decay = D == 0 ? 0 : std::max(n.next_min_change, D);
+        g.attack = n.attack;
+        g.hold = n.hold;
+        g.decay = n.decay < 0 ? 0 : n.decay;
+        g.sustain = sustain;
+        g.release = n.release > 0 ? n.release : 1;
+        g.rel_base = n.n_off < 0 ? INT_MAX : static_cast<int32_t>(std::max<int64_t>(n.n_off - n_k, -(1ll << 30)));
+        g.top = static_cast<float>(n.top);
+        g.gl = n.gl;
+        g.gr = n.gr;
+        res.segs.push_back(g);
+        // advance
+        n.phase += adv_end;
+        n.phase -= 2.0 * floor(0.5 * n.phase);
+        n.f_last = fb;
+        n.glide.i = i0 + len;
+        n.vol_y = n.vol_x + (n.vol_y - n.vol_x) * exp(-3.14159265358979323846 * mv_end);
+      }
+      // a released note leaves the pool once its envelope reached Done2: release steps + 16 more (:738-749)
+      const int64_t n_next = n_k + len;
+      size_t w = 0;
+      std::vector<int> remap(notes.size(), -1);
+      for (size_t i = 0; i < notes.size(); ++i) {
+        const Note& n = notes[i];
+        const bool done = n.n_off >= 0 && n_next >= n.n_off + n.release + 17;
+        if (!done) {
+          remap[i] = static_cast<int>(w);
+          if (w != i) notes[w] = notes[i];
+          ++w;
+        }
+      }
+      notes.resize(w);
+      for (auto& pi : played) pi = remap[pi];
+    }
+  }
+  res.tile_seg_begin[frames] = static_cast<int64_t>(res.segs.size());
+}
+
+}  // namespace
+
+int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
+                   float* h_out, int64_t* h_stats) {
+  if (!params || !h_x || !h_out || n_samples < 0 || n_streams < 0)
+    return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: null argument or negative size");
+  ca_roundtrip_params prm = *params;
+  if (prm.stft.hop > kMaxTile) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: hop > 1024");
+  if (prm.max_channels <= 0) prm.max_channels = 254;
+  if (prm.stft.max_peaks <= 0) prm.stft.max_peaks = 200;
+  int rc = stft_plan(ctx, &prm.stft);
+  if (rc) return rc;
+  const int W = prm.stft.window, hop = prm.stft.hop, P = prm.stft.max_peaks;
+  const int64_t frames = ca_stft_num_frames(n_samples, W, hop);
+  const size_t total = static_cast<size_t>(n_streams) * n_samples;
+  if (total == 0) return CA_OK;
+  const size_t rows = static_cast<size_t>(frames) * n_streams;
+
+  // ---- 1. peaks on the GPU (sub-bin offsets instead of Hz so that the host forms k+p in double) ----
+  std::vector<int32_t> pbin(rows * P), pcnt(rows);
+  std::vector<float> poff(rows * P), pdb(rows * P);
+  if (rows) {
+    ctx->stft_freq_as_offset = true;
+    rc = ca_stft_analyze_host(ctx, h_x, n_samples, n_streams, n_samples, nullptr, 0, pbin.data(), poff.data(), pdb.data(), pcnt.data());
+    ctx->stft_freq_as_offset = false;
+    if (rc) return rc;
+  }
+
+  // ---- 2. pitch pipeline on host threads, one stream at a time per thread ----
+  std::vector<StreamResult> results(n_streams);
+  {
+    int nt = prm.host_threads > 0 ? prm.host_threads : static_cast<int>(std::thread::hardware_concurrency());
+    nt = std::max(1, std::min<int>(nt, static_cast<int>(n_streams)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t)
+      pool.emplace_back([&, t] {
+        for (int64_t s = t; s < n_streams; s += nt)
+          run_stream(prm, n_samples, frames, pbin.data() + s * frames * P, poff.data() + s * frames * P, pdb.data() + s * frames * P,
+                     pcnt.data() + s * frames, results[s]);
+      });
+    for (auto& th : pool) th.join();
+  }
+
+  // ---- 3. flatten and render ----
+  size_t n_segs = 0;
+  for (auto& r : results) n_segs += r.segs.size();
+  const int64_t n_tiles = frames * n_streams;
+  std::vector<int64_t> tile_begin(n_tiles + 1), tile_s0(std::max<int64_t>(n_tiles, 1));
+  std::vector<int32_t> tile_len(std::max<int64_t>(n_tiles, 1));
+  std::vector<Segment> segs;
+  segs.reserve(n_segs);
+  for (int64_t s = 0; s < n_streams; ++s) {
+    const int64_t base = static_cast<int64_t>(segs.size());
+    for (int64_t k = 0; k < frames; ++k) {
+      const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;
+      tile_begin[s * frames + k] = base + results[s].tile_seg_begin[k];
+      tile_s0[s * frames + k] = s * n_samples + n_k;
+      tile_len[s * frames + k] = static_cast<int32_t>(std::max<int64_t>(0, std::min<int64_t>(hop, n_samples - n_k)));
+    }
+    segs.insert(segs.end(), results[s].segs.begin(), results[s].segs.end());
+    if (h_stats) {
+      h_stats[2 * s] = results[s].notes_started;
+      h_stats[2 * s + 1] = results[s].notes_dropped;
+    }
+  }
+  tile_begin[n_tiles] = static_cast<int64_t>(segs.size());
+
+  const size_t out_bytes = sizeof(float) * 2 * total;
+  rc = ensure_scratch(ctx, 7, out_bytes);
+  if (!rc) rc = ensure_scratch(ctx, 6, std::max<size_t>(16, sizeof(Segment) * segs.size()));
+  if (!rc) rc = ensure_scratch(ctx, 1, sizeof(int64_t) * (n_tiles + 1));
+  if (!rc) rc = ensure_scratch(ctx, 2, std::max<size_t>(16, sizeof(int64_t) * n_tiles));
+  if (!rc) rc = ensure_scratch(ctx, 3, std::max<size_t>(16, sizeof(int32_t) * n_tiles));
+  if (rc) return rc;
+  cudaStream_t st = ctx->own_stream;
+  CA_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scratch[7], 0, out_bytes, st));  // samples before the first frame are silent
+  if (n_tiles > 0 && !segs.empty()) {
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[6], segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[1], tile_begin.data(), sizeof(int64_t) * (n_tiles + 1), cudaMemcpyHostToDevice, st));
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[2], tile_s0.data(), sizeof(int64_t) * n_tiles, cudaMemcpyHostToDevice, st));
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[3], tile_len.data(), sizeof(int32_t) * n_tiles, cudaMemcpyHostToDevice, st));
+    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), static_cast<const int64_t*>(ctx->d_scratch[1]),
+                static_cast<const int64_t*>(ctx->d_scratch[2]), static_cast<const int32_t*>(ctx->d_scratch[3]), n_tiles,
+                static_cast<float*>(ctx->d_scratch[7])};
+    tracks_kernel<<<static_cast<unsigned>((n_tiles + 3) / 4), 128, 0, st>>>(ta);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+  }
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], out_bytes, cudaMemcpyDeviceToHost, st));
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return CA_OK;
+}
+
+}  // namespace ca

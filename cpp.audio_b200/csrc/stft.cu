@@ -54,6 +54,7 @@ struct StftArgs {
   int32_t max_peaks;
   float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
   float bin_to_hz;
+  int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
 };
 
 __device__ __forceinline__ float2 cis_neg(float turns_times_two) {  // exp(-i*pi*arg)
@@ -299,7 +300,7 @@ __device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, c
       constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
       const float beta = kDbPerLog2 * __log2f(sb);
       if (!kSplit) p.peak_bin[out_base + idx] = k;
-      p.peak_freq[out_base + idx] = (static_cast<float>(k) + pp) * p.bin_to_hz;
+      p.peak_freq[out_base + idx] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
       p.peak_db[out_base + idx] = beta - 0.25f * (kDbPerLog2 * num) * pp;
     }
     __syncwarp();  // the next frame overwrites the buffer
@@ -592,6 +593,7 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.max_peaks = ctx->stft.max_peaks;
   a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
   a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / kN);
+  a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
 
   // tuning knobs (defaults are the measured best): CA_STFT_VARIANT = 0..4
   static const int variant = [] {

@@ -135,6 +135,30 @@ int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca
 /* every pointer inside desc is a HOST pointer; H2D of the note parameters, kernels, D2H of h_out, stream sync */
 int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_out);
 
+/* ---- analysis -> pitch pipeline -> resynthesis round trip (BASELINE config 4) -----------------------------------
+ * Stands in for the offline RtResynth loop (source/rt.resynth.lib.cpp:1185-1235): per stream, every analysis frame's
+ * peak list goes through RtResynth::step (:1670-1759; source/rt.resynth.lib.algo.cpp:10-440: frequencies_to_pitches,
+ * aggregate_pitches, reduce_pitches, track_pitches, order by loudness) and synthesize_sounds (:264-382) turns the result
+ * into NoteOn / NoteChange / NoteOff on a pool of ResynthElement voices (:5-18: StereoPanned<VolumeAdjusted<Enveloped<
+ * FreqCtrl_<SineOscillatorAlgo, InterpolatedFreq>, AHDSREnvelope>>>) whose output is the resynthesised audio.
+ * Analysis and voice rendering run on the GPU; the per-stream, frame-sequential pitch tracking runs on host threads
+ * (it is control-rate code in the reference too). Events of frame k act from sample window-1 + k*hop on. */
+typedef struct ca_roundtrip_params {
+  ca_stft_params stft;          /* window / hop / sample rate / min_db; max_peaks = peak capacity per frame */
+  float nearby_distance_tones;  /* 0.4   rt.resynth.lib.cpp:948 */
+  float min_volume;             /* 1e-4  :947 */
+  float max_track_pitches;      /* 1.0   :949 */
+  float gain;                   /* analysis_volume, :995 */
+  float stereo_spread;          /* :955 */
+  ca_ahdsr env;                 /* :957-961 (all zero, sustain 1 by default) */
+  int32_t max_channels;         /* 254 = 2*127, :201-210 */
+  int32_t host_threads;         /* 0 = all */
+} ca_roundtrip_params;
+/* h_x [n_streams][n_samples] -> h_out [n_streams][n_samples][2] float32 (stereo). h_stats nullable [n_streams][2]:
+ * notes started, notes dropped (pool full). */
+int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
+                              int64_t n_streams, float* h_out, int64_t* h_stats);
+
 /* measured FP32 FMA throughput of this GPU in TFLOP/s (dependent-free FFMA chains, `ms` of work); used as the
  * denominator of the synthesis roofline */
 int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops);

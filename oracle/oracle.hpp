@@ -750,4 +750,194 @@ bool pool_compute_stereo(std::vector<Voice>& voices, double* buffer, int n_frame
   return !silence;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pitch pipeline (source/rt.resynth.lib.algo.cpp:10-440) and the analysis -> resynthesis round trip of one stream as
+// the offline constructor runs it (source/rt.resynth.lib.cpp:1185-1235, :1572-1759, :264-382): one sample at a time,
+// a frame fires when the window is full, its events are applied before the output sample of the same index.
+// ------------------------------------------------------------------------------------------------------------
+
+inline double frequency_to_midi_pitch(double freq) { return 69. + 12. * std::log2(freq / 440.f); }           // include/midi.h:226-231
+inline double midi_pitch_to_freq(double pitch) { return 440.f * std::pow(std::pow(2., 1. / 12.), pitch - 69.); }  // :258-264
+
+struct PitchVolume {
+  double midipitch;
+  double volume;
+};
+
+// SPEC S10: the reference draws start phases and pans from mersenne<> (external); the oracle and the product use this hash.
+inline float hash_unit(uint64_t id, uint64_t salt) {
+  uint64_t z = id * 0x9E3779B97F4A7C15ull + salt * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+}
+
+struct RoundTripParams {
+  int sample_rate = 48000;
+  int window = 4096;
+  int hop = 256;
+  double sigma_factor = 4.0;
+  double min_db = -80.0;                // SPEC S6 threshold on the peak list
+  double nearby_distance_tones = 0.4;   // rt.resynth.lib.cpp:948
+  double min_volume = 0.0001;           // :947
+  double max_track_pitches = 1.0;       // :949
+  float gain = 1.f;                     // analysis_volume (:995 defaults to 0, i.e. muted; 1 = unity)
+  float stereo_spread = 1.f;            // :955
+  Ahdsr env{0, LINEAR, 0, 0, LINEAR, 0, LINEAR, 1.f};  // :957-961
+  int max_channels = 254;               // 2 * 127 voices, :201-210, gen.crtp.h:225
+};
+
+template <class T>
+class RoundTrip {
+public:
+  explicit RoundTrip(const RoundTripParams& p)
+      : prm_(p), pfft_(Window::Gaussian, p.sigma_factor), channels_(p.max_channels), note_of_(p.max_channels, -1) {
+    pfft_.set_lambdas([this] { return prm_.window; }, [this] { return prm_.hop; },
+                      [this](int stride, const std::vector<double>& sq) { on_frame(stride, sq); });
+  }
+
+  // out: interleaved stereo [n][2]
+  void run(const float* x, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) {
+      pfft_.feed(x[i]);
+      double buf[2] = {0, 0};
+      pool_compute_stereo(channels_, buf, 1);
+      out[2 * i] = buf[0];
+      out[2 * i + 1] = buf[1];
+    }
+  }
+  int64_t dropped_notes() const { return dropped_; }
+  int64_t notes_started() const { return next_noteid_; }
+
+private:
+  struct PlayedNote {
+    int64_t noteid;
+    double midi_pitch;
+  };
+
+  void on_frame(int stride, const std::vector<double>& sq) {
+    extract_local_max_freqs_mags<double>(prm_.sample_rate, sq.data(), pfft_.op().fft_length(), prm_.min_db, freqmags_);
+    // frequencies_to_pitches (:10-29)
+    pv_.clear();
+    for (auto& f : freqmags_)
+      if (f.freq > 0) pv_.push_back({frequency_to_midi_pitch(f.freq), db_to_mag(f.mag_db)});
+    // aggregate_pitches (:124-161) + reduce_pitches (:166-184, PonderateByVolume / SumVolumes, rt.resynth.lib.cpp:400-403)
+    reduced_.clear();
+    bool open = false;
+    double mn = 0, mx = 0, sum_v = 0, sum_pv = 0;
+    auto close = [&] {
+      if (open && !(sum_v < prm_.min_volume)) reduced_.push_back({sum_pv / sum_v, sum_v});
+      open = false;
+    };
+    for (auto& q : pv_) {
+      if (open && std::max({mn, mx, q.midipitch}) - std::min({mn, mx, q.midipitch}) > prm_.nearby_distance_tones) close();
+      if (!open) {
+        open = true;
+        mn = mx = q.midipitch;
+        sum_v = 0;
+        sum_pv = 0;
+      } else {
+        mn = std::min(mn, q.midipitch);
+        mx = std::max(mx, q.midipitch);
+      }
+      sum_v += q.volume;
+      sum_pv += q.midipitch * q.volume;
+    }
+    close();
+    // autotune_pitches with the identity transform (:192-229): merges pitches closer than pitch_epsilon
+    tuned_.clear();
+    for (auto& q : reduced_) {
+      if (!tuned_.empty() && std::abs(tuned_.back().midipitch - q.midipitch) < 0.0001f) tuned_.back().volume += q.volume;
+      else tuned_.push_back(q);
+    }
+    // track_pitches (:256-305)
+    std::vector<int> change(tuned_.size(), -1);
+    std::vector<char> keep(played_.size(), 0);
+    {
+      size_t it = 0;
+      for (size_t i = 0; i < tuned_.size(); ++i) {
+        for (; it < played_.size(); ++it) {
+          if (played_[it].midi_pitch < tuned_[i].midipitch - prm_.max_track_pitches) continue;
+          if (played_[it].midi_pitch <= tuned_[i].midipitch + prm_.max_track_pitches) {
+            change[i] = static_cast<int>(it);
+            keep[it] = 1;
+            ++it;
+          }
+          break;
+        }
+      }
+    }
+    // order_pitches_by_perceived_loudness (:377-411), SPEC S9: raw volume
+    std::vector<int> order(tuned_.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return static_cast<float>(tuned_[a].volume) > static_cast<float>(tuned_[b].volume);
+    });
+    // synthesize_sounds (rt.resynth.lib.cpp:264-382)
+    for (size_t i = 0; i < played_.size(); ++i)
+      if (!keep[i]) note_off(played_[i].noteid);
+    size_t n_before = played_.size();
+    for (int idx : order) {
+      float new_freq = static_cast<float>(midi_pitch_to_freq(tuned_[idx].midipitch));
+      float volume = static_cast<float>(prm_.gain * tuned_[idx].volume / 0.1f);
+      if (change[idx] >= 0) {
+        note_change(played_[change[idx]].noteid, volume, new_freq);
+        played_[change[idx]].midi_pitch = tuned_[idx].midipitch;
+      } else {
+        if (volume <= 0) continue;
+        ++next_noteid_;
+        if (note_on(next_noteid_, new_freq, volume, stride)) played_.push_back({next_noteid_, tuned_[idx].midipitch});
+        else ++dropped_;
+      }
+    }
+    // remove_dead_notes (:415-432) + sort_by_current_pitch (:434-440)
+    std::vector<PlayedNote> alive;
+    for (size_t i = 0; i < played_.size(); ++i)
+      if (i >= n_before || keep[i]) alive.push_back(played_[i]);
+    std::stable_sort(alive.begin(), alive.end(), [](const PlayedNote& a, const PlayedNote& b) { return a.midi_pitch < b.midi_pitch; });
+    played_.swap(alive);
+  }
+
+  // ImplCRTP::onEvent (include/gen.crtp.h:382-622) with ResynthElementInitializer (rt.resynth.lib.cpp:96-118)
+  bool note_on(int64_t id, float freq, float velocity, int stride) {
+    for (size_t c = 0; c < channels_.size(); ++c) {
+      if (!channels_[c].try_acquire()) continue;
+      auto& e = channels_[c];
+      note_of_[c] = id;
+      e.forget_past_signals();
+      e.set_volume_target(static_cast<T>(0.1f * velocity));
+      e.initialize(prm_.env, prm_.sample_rate, stride, prm_.stereo_spread * hash_unit(static_cast<uint64_t>(id), 1));
+      e.set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, prm_.sample_rate)));
+      e.set_start_angle(static_cast<T>(hash_unit(static_cast<uint64_t>(id), 2)));
+      e.on_key_pressed(0);
+      return true;
+    }
+    return false;
+  }
+  void note_change(int64_t id, float velocity, float freq) {
+    for (size_t c = 0; c < channels_.size(); ++c)
+      if (note_of_[c] == id) {
+        channels_[c].set_volume_target(static_cast<T>(0.1f * velocity));
+        channels_[c].set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, prm_.sample_rate)));
+      }
+  }
+  void note_off(int64_t id) {
+    for (size_t c = 0; c < channels_.size(); ++c)
+      if (note_of_[c] == id) {
+        channels_[c].on_key_released(0);
+        return;
+      }
+  }
+
+  RoundTripParams prm_;
+  PeriodicFft<SqMagOp<double>> pfft_;
+  std::vector<ResynthVoice<T>> channels_;
+  std::vector<int64_t> note_of_;
+  std::vector<FreqMag<double>> freqmags_;
+  std::vector<PitchVolume> pv_, reduced_, tuned_;
+  std::vector<PlayedNote> played_;
+  int64_t next_noteid_ = 0, dropped_ = 0;
+};
+
 }  // namespace orc

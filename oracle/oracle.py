@@ -64,6 +64,8 @@ def lib():
         L.orc_freq_aliasing_multiplicator.argtypes = [C.c_double]
         L.orc_freq_aliasing_multiplicator.restype = C.c_double
         L.orc_sine_trace.argtypes = [C.c_double, C.c_double, C.c_int64, p]
+        L.orc_roundtrip.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p, p,
+                                    C.c_int]
         _lib = L
     return _lib
 
@@ -177,3 +179,17 @@ def sine_trace(start_angle: float, angle_increment: float, n: int) -> np.ndarray
     out = np.zeros(n, dtype=np.float64)
     lib().orc_sine_trace(float(start_angle), float(angle_increment), n, _ptr(out))
     return out
+
+
+def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: int = 48000, min_db: float = -80.0,
+              gain: float = 1.0, stereo_spread: float = 1.0, env: Ahdsr | None = None, threads: int = 1):
+    """Analysis -> pitch pipeline -> resynthesis of each row of x (offline loop of the reference). Returns
+    (audio float64 [streams, samples, 2], stats int64 [streams, 2] = notes started, notes dropped)."""
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+    streams, n = x.shape
+    out = np.zeros((streams, n, 2), dtype=np.float64)
+    stats = np.zeros((streams, 2), dtype=np.int64)
+    e = env if env is not None else make_ahdsr()
+    lib().orc_roundtrip(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
+                        C.byref(e), _ptr(out), _ptr(stats), threads)
+    return out, stats

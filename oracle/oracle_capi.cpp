@@ -228,4 +228,26 @@ void orc_sine_trace(double start_angle, double angle_increment, int64_t n, doubl
   }
 }
 
+// Analysis -> pitch pipeline -> resynthesis of n_streams independent streams (BASELINE config 4), each through the offline
+// loop of the reference. out: [streams][samples][2] double. stats (nullable): [streams][2] = notes started, notes dropped.
+void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
+                   float gain, float stereo_spread, const Ahdsr* env, double* out, int64_t* stats, int threads) {
+  parallel_for(n_streams, threads, [&](int64_t s) {
+    RoundTripParams p;
+    p.sample_rate = sample_rate;
+    p.window = window;
+    p.hop = hop;
+    p.min_db = min_db;
+    p.gain = gain;
+    p.stereo_spread = stereo_spread;
+    if (env) p.env = *env;
+    RoundTrip<double> rt(p);
+    rt.run(x + s * n_samples, n_samples, out + s * n_samples * 2);
+    if (stats) {
+      stats[2 * s] = rt.notes_started();
+      stats[2 * s + 1] = rt.dropped_notes();
+    }
+  });
+}
+
 }  // extern "C"
