@@ -22,6 +22,8 @@ struct ca_ctx {
   int n_fft = 0;
   float* d_window = nullptr;  // [n_fft] window, zero padded, pre-scaled (see stft.cu)
   float thr_sq = 0.f;
+  void* d_stft_work = nullptr;  // generic (non-4096) path: windowed frames + complex bins of one group of frames
+  size_t stft_work_bytes = 0;
   bool stft_freq_as_offset = false;  // internal switch used by the round trip (see stft.cu)
 
   // generic FFT scratch (twiddle tables, four-step buffers)

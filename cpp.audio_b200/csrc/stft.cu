@@ -512,6 +512,92 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_ring_kernel(const _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generic path for FFT lengths other than 4096 (1024 .. 32768; the reference default window of 0.1814 s is 8192 points
+// at 44.1 kHz): frames are windowed into a work buffer, transformed by K1 (rfft.cu) and a third kernel forms |X|^2 and
+// extracts the peaks. Three passes over HBM instead of one — correct for every size, tuned for none.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) window_frames_kernel(const float* __restrict__ x, const float* __restrict__ win,
+                                                            float* __restrict__ out, int64_t stream_stride, int frames_per_stream,
+                                                            int hop, int window, int n_fft, int64_t f_begin, int64_t n_frames) {
+  // grid.x: frames of this group, threads stride over the frame
+  const int64_t f = f_begin + blockIdx.x;
+  if (blockIdx.x >= n_frames) return;
+  const int64_t stream = f / frames_per_stream;
+  const int64_t fr = f - stream * frames_per_stream;
+  const float* xs = x + stream * stream_stride + fr * hop;
+  float* o = out + static_cast<int64_t>(blockIdx.x) * n_fft;
+  for (int n = threadIdx.x; n < n_fft; n += 256) o[n] = n < window ? __ldg(xs + n) * __ldg(win + n) : 0.f;
+}
+
+// one warp per frame: |X|^2 (scale folded into the window), HBM row, peaks as in the fused kernel
+__global__ void __launch_bounds__(128) sqmag_peaks_kernel(const float2* __restrict__ bins, int n_fft, int64_t f_begin,
+                                                          int64_t n_frames, const __grid_constant__ StftArgs p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t local = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (local >= n_frames) return;
+  const int64_t f = f_begin + local;
+  const int half = n_fft / 2;
+  const float2* X = bins + local * (half + 1);
+  float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
+  if (row)
+    for (int k = lane; k <= half; k += 32) {
+      const float2 z = X[k];
+      row[k] = fmaf(z.x, z.x, z.y * z.y);
+    }
+  if (!p.peak_count) return;
+  auto sq = [&](int k) {
+    const float2 z = X[k];
+    return fmaf(z.x, z.x, z.y * z.y);
+  };
+  // lane owns bins [lane*B, lane*B + B), B = half/32; bins 1 .. half-1 are candidates
+  const int B = half / 32;
+  const int k0 = lane * B;
+  int cnt = 0;
+  {
+    float l = k0 > 0 ? sq(k0 - 1) : __int_as_float(0x7f800000);
+    float c = sq(k0);
+    for (int j = 0; j < B; ++j) {
+      const float r = sq(k0 + j + 1);
+      cnt += (c > fmaxf(fmaxf(l, r), p.thr_below)) ? 1 : 0;
+      l = c;
+      c = r;
+    }
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int slot = incl - cnt;
+  if (lane == 0) p.peak_count[f] = total;
+  const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
+  float l = k0 > 0 ? sq(k0 - 1) : __int_as_float(0x7f800000);
+  float c = sq(k0);
+  for (int j = 0; j < B && slot < p.max_peaks; ++j) {
+    const float r = sq(k0 + j + 1);
+    if (c > fmaxf(fmaxf(l, r), p.thr_below)) {
+      const int k = k0 + j;
+      const float fl = 1e-37f;
+      const float sa = fmaxf(l, fl), sb = fmaxf(c, fl), sc = fmaxf(r, fl);
+      const float inv_b = __frcp_rn(sb);
+      const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);
+      const float num = la - lc, den = la + lc;
+      const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
+      constexpr float kDbPerLog2 = 3.01029995663981195f;
+      p.peak_bin[out_base + slot] = k;
+      p.peak_freq[out_base + slot] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
+      p.peak_db[out_base + slot] = kDbPerLog2 * __log2f(sb) - 0.25f * (kDbPerLog2 * num) * pp;
+      ++slot;
+    }
+    l = c;
+    c = r;
+  }
+}
+
 }  // namespace
 
 int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
@@ -520,8 +606,8 @@ int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
   if (p->window_type != CA_WINDOW_RECTANGULAR && p->window_type != CA_WINDOW_GAUSSIAN)
     return fail(ctx, CA_ERR_INVALID, "ca_stft_plan: unknown window type");
   const int n_fft = ca_fft_length_for(p->window, 1);
-  if (n_fft != kN)
-    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_plan: only windows with fft length 4096 (2048 < window <= 4096) are built");
+  if (n_fft < 1024 || n_fft > 32768)
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_plan: fft length must be within 1024 .. 32768 (512 < window <= 32768)");
   // half window, normalised to mean 1 (oracle/SPEC.md S2,S3), then scaled by 1/W (S4) and by the 1/2 of the real-FFT
   // untangling so that the kernel's |E+T|^2 is |X|^2 directly.
   const int W = p->window, H = W / 2;
@@ -536,7 +622,7 @@ int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
     hw[j] = static_cast<double>(v);
     sum += v;
   }
-  const double norm = static_cast<double>(H / sum) * 0.5 / W;
+  const double norm = static_cast<double>(H / sum) * (n_fft == kN ? 0.5 : 1.0) / W;
   std::vector<float> full(n_fft, 0.f);
   for (int n = 0; n < W; ++n) full[n] = static_cast<float>((n < H ? hw[H - 1 - n] : hw[n - H]) * norm);
   if (!ctx->d_window || ctx->n_fft != n_fft) {
@@ -553,6 +639,9 @@ int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
 }
 
 void stft_release(ca_ctx* ctx) {
+  if (ctx->d_stft_work) cudaFree(ctx->d_stft_work);
+  ctx->d_stft_work = nullptr;
+  ctx->stft_work_bytes = 0;
   if (ctx->d_window) cudaFree(ctx->d_window);
   ctx->d_window = nullptr;
   ctx->stft_planned = false;
@@ -567,7 +656,8 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   const bool any_peak = d_peak_bin || d_peak_freq || d_peak_db || d_peak_count;
   if (any_peak && !(d_peak_bin && d_peak_freq && d_peak_db && d_peak_count))
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: peak outputs must be all null or all non-null");
-  if (d_sqmag && sqmag_row_stride < kBins) return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: sqmag_row_stride < n_fft/2+1");
+  if (d_sqmag && sqmag_row_stride < ctx->n_fft / 2 + 1)
+    return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: sqmag_row_stride < n_fft/2+1");
   const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
   const int64_t total = frames * n_streams;
   if (total == 0) return CA_OK;
@@ -592,7 +682,38 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.peak_count = d_peak_count;
   a.max_peaks = ctx->stft.max_peaks;
   a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
-  a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / kN);
+  a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / ctx->n_fft);
+  if (ctx->n_fft != kN) {
+    // generic three-pass path, frames processed in groups that bound the work buffers to ~256 MiB each
+    const int n_fft = ctx->n_fft, half = n_fft / 2;
+    if (frames >= (1ll << 31)) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_analyze: too many frames per stream");
+    const int64_t group = std::max<int64_t>(1, std::min<int64_t>(total, (256ll << 20) / (sizeof(float) * n_fft)));
+    const size_t need = sizeof(float) * n_fft * group + sizeof(float2) * (half + 1) * group;
+    if (ctx->stft_work_bytes < need) {
+      if (ctx->d_stft_work) cudaFree(ctx->d_stft_work);
+      ctx->d_stft_work = nullptr;
+      ctx->stft_work_bytes = 0;
+      CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_stft_work, need));
+      ctx->stft_work_bytes = need;
+    }
+    float* wbuf = static_cast<float*>(ctx->d_stft_work);
+    float* bbuf = wbuf + static_cast<size_t>(n_fft) * group;
+    a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
+    a.max_peaks = ctx->stft.max_peaks;
+    a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
+    for (int64_t f0 = 0; f0 < total; f0 += group) {
+      const int64_t nf = std::min(group, total - f0);
+      window_frames_kernel<<<static_cast<unsigned>(nf), 256, 0, stream>>>(d_x, ctx->d_window, wbuf, stream_stride, static_cast<int>(frames),
+                                                                         ctx->stft.hop, ctx->stft.window, n_fft, f0, nf);
+      CA_CUDA_OK(ctx, cudaGetLastError());
+      int rc = rfft_batched(ctx, wbuf, n_fft, nf, bbuf, stream);
+      if (rc) return rc;
+      sqmag_peaks_kernel<<<static_cast<unsigned>((nf + 3) / 4), 128, 0, stream>>>(reinterpret_cast<const float2*>(bbuf), n_fft, f0, nf, a);
+      CA_CUDA_OK(ctx, cudaGetLastError());
+      ctx->launches += 2;
+    }
+    return CA_OK;
+  }
   a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
 
   // tuning knobs (defaults are the measured best): CA_STFT_VARIANT = 0..4

@@ -121,9 +121,23 @@ def test_peak_capacity_overflow(pkg, orc, ctx):
 
 def test_unsupported_fft_length_fails_loudly(pkg, ctx):
     with pytest.raises(pkg.CaError):
-        pkg.SqMagAnalyzer(ctx, 1024, 256)
+        pkg.SqMagAnalyzer(ctx, 512, 256)       # fft length 512 < 1024
     with pytest.raises(pkg.CaError):
-        pkg.SqMagAnalyzer(ctx, 4095, 256)  # odd window (Assert at periodicfft.cpp:274)
+        pkg.SqMagAnalyzer(ctx, 40000, 256)     # fft length 65536 > 32768
+    with pytest.raises(pkg.CaError):
+        pkg.SqMagAnalyzer(ctx, 4095, 256)      # odd window (Assert at periodicfft.cpp:274)
+
+
+@pytest.mark.parametrize("window,hop,sr", [(1024, 256, 48000), (2000, 300, 48000), (8000, 3969, 44100), (16384, 1024, 48000),
+                                           (30000, 5000, 48000)])
+def test_other_fft_lengths_generic_path(pkg, orc, ctx, wl, window, hop, sr):
+    """Windows whose FFT length is not 4096 take the three-pass path (window 8000 / stride 3969 at 44.1 kHz are the
+    reference defaults: 0.1814 s and 0.09 s, source/rt.resynth.lib.cpp:945-946)."""
+    x = wl.c4_streams(2, 1.5)
+    res = run_gpu(pkg, ctx, x, window, hop, sample_rate=sr)
+    ref = orc.stft_analyze(x, window, hop, sample_rate=sr)
+    compare(res, ref)
+    assert ref["peak_count"].min() >= 1
 
 
 def test_peaks_only_and_sqmag_only(pkg, orc, ctx, wl):
