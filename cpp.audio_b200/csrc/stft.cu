@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "ctx.hpp"
+#include "packed.cuh"
 
 namespace ca {
 
@@ -33,7 +34,6 @@ constexpr int kM = 2048;         // complex FFT length
 constexpr int kBins = kM + 1;
 constexpr int kExchStride = 33;  // float2 per row of the 64 x 32 transpose buffer (conflict-free both ways)
 constexpr int kExchFloat2 = 64 * kExchStride;
-constexpr int kTabRows = 21;
 
 struct StftArgs {
   const float* x;
@@ -74,444 +74,363 @@ __device__ __forceinline__ void untangle(float2 zk, float2 zm, float2 wp, float&
   sq_m = fmaf(qx, qx, qy * qy);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K2: stft4096p_kernel. One warp owns one frame; 2048 complex points = 64 (registers of a lane) x 32 (lanes), all complex
+// arithmetic on FFMA2 / FADD2 / FMUL2 (packed.cuh): a complex value is one register pair, a constant-twiddle butterfly is
+// 3 instructions. The inter-stage twiddle W_2048^(lane*k1), k1 = 8a+b, is applied as two table twiddles (wb[b], then
+// wa[a]: 112 two-instruction multiplies, no products to form); the untangling twiddle -i W_4096^k = wpbase(lane)*W_64^k2
+// is an immediate multiply followed by a per-lane one. The frame loop is software-pipelined by hand: the samples of the
+// warp's NEXT frame are requested right after the spectrum of the current one is stored (the 128 data registers are
+// free then) and land while the peak list is extracted, so the FFT never waits on L2/HBM. The window lives in shared
+// memory. Frame body ~2.3 K instructions (the scalar predecessor: 4.5 K, 70 KB — it thrashed the 32 KB instruction cache).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTab4Rows = 20;  // float4 (wr, s, -wi, wi): rows 0..6 wb[1..7], 7..13 wa[1..7], 14 wpbase, 15..19 column-0 FFT
+constexpr int kSqBlock = 68;   // floats per 64-bin block of the warp's |X|^2 buffer (16-byte aligned, conflict-free)
+constexpr int kSqFloats = 32 * kSqBlock;  // 2176: bins 0..2047 in 32 padded blocks; the 4 padding floats of each block hold
+                                          // the peak-bin list (127 entries) and, in the very last one, bin 2048
+constexpr int kKlistCap = 127;
+constexpr int kStageOff = kSqFloats / 2;  // in c2 units: the upper 8 KB of the warp's buffer stage the next frame's even half
+static_assert(kSqFloats * 4 + 32 * 32 * 8 == kExchFloat2 * 8, "spectrum + staged half frame must fill the exchange buffer");
+
+__device__ __forceinline__ int physp(int k) { return k == kM ? kSqFloats - 1 : k + 4 * (k >> 6); }
+__device__ __forceinline__ int klist_slot(int s) { return kSqBlock * (s >> 2) + 64 + (s & 3); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
+// asynchronous global -> shared copy that bypasses the register file (LDGSTS); n_src = 0 writes zeros without reading
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int n_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, int n_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int WARPS>
+__device__ __forceinline__ void build_tables_p(float4* tab4, float2* tab2, float2* win_s, const float* __restrict__ win) {
+  for (int i = threadIdx.x; i < kTab4Rows * 32; i += WARPS * 32) {
+    const int r = i >> 5, l = i & 31;
+    float2 w;
+    float sgn = 0.f;
+    if (r < 7) {
+      w = cis_neg(2.f * static_cast<float>(l * (r + 1)) / kM);  // W_2048^(l*b), b = r+1
+    } else if (r < 14) {
+      w = cis_neg(2.f * static_cast<float>(l * 8 * (r - 6)) / kM);  // W_2048^(l*8a), a = r-6
+    } else if (r == 14) {
+      const int col = l ? l : 32;
+      float s, c;
+      sincospif(2.f * static_cast<float>(col) / kN, &s, &c);
+      w = make_float2(-s, -c);  // -i * W_4096^col
+    } else {
+      // column-0 FFT across lanes, DIF stage s = r-15, distance d = 16 >> s: lanes with bit d take (other - own) * w,
+      // the others (own + other) * 1; branch-free as (other + sgn*own) * w'
+      const int d = 16 >> (r - 15);
+      if (l & d) {
+        w = cis_neg(static_cast<float>(l % d) / d);  // exp(-2 pi i (l%d)/(2d))
+        sgn = -1.f;
+      } else {
+        w = make_float2(1.f, 0.f);
+        sgn = 1.f;
+      }
+    }
+    tab4[i] = make_float4(w.x, sgn, -w.y, w.y);
+  }
+  for (int l = threadIdx.x; l < 32; l += WARPS * 32) {
+    const int k = 64 * static_cast<int>(__brev(static_cast<unsigned>(l)) >> 27);  // k = 64*brev5(l)
+    float s, c;
+    sincospif(2.f * static_cast<float>(k) / kN, &s, &c);
+    tab2[l] = make_float2(-s, -c);  // -i * W_4096^k
+  }
+  for (int i = threadIdx.x; i < kM; i += WARPS * 32) win_s[i] = __ldg(reinterpret_cast<const float2*>(win) + i);
+}
+
+template <int J>
+__device__ __forceinline__ void tw_store_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane) {
+  constexpr int a = J >> 3, b = J & 7;
+  c2 y = v[J];
+  if constexpr (b != 0) y = cmul_tw(y, wb[b]);
+  if constexpr (a != 0) y = cmul_tw(y, wa[a]);
+  if constexpr (J != 0) exch[J * kExchStride + lane] = y;  // column 0 goes through the shuffle FFT
+}
+template <int... J>
+__device__ __forceinline__ void tw_store_all_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane,
+                                               std::integer_sequence<int, J...>) {
+  (tw_store_p<J>(v, wa, wb, exch, lane), ...);
+}
+
 // untangle bins k = colA + 64*K2 and 2048-k = colB + 64*(31-K2) and store them at once (HBM row and/or the warp's padded
-// shared buffer), so that the stores are spread over the arithmetic instead of queueing up behind it
+// shared buffer), so that the stores are spread over the arithmetic instead of queueing up behind it.
+// (The shorter form |X|^2 = S +- C, S = |E|^2+|D|^2, cancels catastrophically on bins far below their mirror bin.)
 template <int K2>
-__device__ __forceinline__ void post_pair(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float* __restrict__ rowA,
-                                          float* __restrict__ rowB, float* __restrict__ sqA, float* __restrict__ sqB) {
-  constexpr float2 w64 = {Tw<64, K2>::re, Tw<64, K2>::im};
-  float2 wp;
-  if constexpr (K2 == 0) wp = wpbase;
-  else wp = cmul(wpbase, w64);
-  float sk, sm;
-  untangle(A[K2], B[31 - K2], wp, sk, sm);
+__device__ __forceinline__ void post_pair_p(const c2 (&A)[32], const c2 (&B)[32], const TwP& wpb, float* __restrict__ rowA,
+                                            float* __restrict__ rowB, float* __restrict__ sqA, float* __restrict__ sqB) {
+  const c2 zk = A[K2], zm = B[31 - K2];
+  const c2 E = add2(zk, cconj(zm));  // Z[k] + conj(Z[M-k])
+  c2 D = csub(zk, cconj(zm));        // Z[k] - conj(Z[M-k])
+  if constexpr (K2 != 0) D = cmul_imm<Tw<64, K2>>(D);
+  const c2 T = cmul_tw(D, wpb);
+  const float2 P = upk(add2(E, T)), Q = upk(csub(E, T));
+  const float sk = fmaf(P.x, P.x, P.y * P.y);
+  const float sm = fmaf(Q.x, Q.x, Q.y * Q.y);
   if (rowA) {
     rowA[64 * K2] = sk;
     rowB[64 * (31 - K2)] = sm;
   }
   if (sqA) {
-    sqA[65 * K2] = sk;
-    sqB[65 * (31 - K2)] = sm;
+    sqA[kSqBlock * K2] = sk;
+    sqB[kSqBlock * (31 - K2)] = sm;
   }
 }
 template <int... K2>
-__device__ __forceinline__ void post_all(const float2 (&A)[32], const float2 (&B)[32], float2 wpbase, float* rowA, float* rowB,
-                                         float* sqA, float* sqB, std::integer_sequence<int, K2...>) {
-  (post_pair<K2>(A, B, wpbase, rowA, rowB, sqA, sqB), ...);
+__device__ __forceinline__ void post_all_p(const c2 (&A)[32], const c2 (&B)[32], const TwP& wpb, float* rowA, float* rowB,
+                                           float* sqA, float* sqB, std::integer_sequence<int, K2...>) {
+  (post_pair_p<K2>(A, B, wpb, rowA, rowB, sqA, sqB), ...);
 }
 
-// stage-1 twiddle + transposed store for output k1 = J
-template <int J>
-__device__ __forceinline__ void tw_store(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8], float2* exch,
-                                         int lane) {
-  constexpr int k1 = J;
-  constexpr int a = k1 >> 3, b = k1 & 7;
-  float2 y = v[J];
-  if constexpr (a != 0 && b != 0) y = cmul(y, cmul(wa[a], wb[b]));
-  else if constexpr (a != 0) y = cmul(y, wa[a]);
-  else if constexpr (b != 0) y = cmul(y, wb[b]);
-  exch[k1 * kExchStride + lane] = y;
-}
-// split variant: twiddle in place, then the real and imaginary planes cross the transpose buffer one after the other
-// (half the shared memory per warp: 64 x 33 floats)
-template <int J>
-__device__ __forceinline__ void tw_inplace(float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8]) {
-  constexpr int k1 = J;
-  constexpr int a = k1 >> 3, b = k1 & 7;
-  if constexpr (a != 0 && b != 0) v[J] = cmul(v[J], cmul(wa[a], wb[b]));
-  else if constexpr (a != 0) v[J] = cmul(v[J], wa[a]);
-  else if constexpr (b != 0) v[J] = cmul(v[J], wb[b]);
-}
-template <int... J>
-__device__ __forceinline__ void tw_inplace_all(float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8],
-                                               std::integer_sequence<int, J...>) {
-  (tw_inplace<J>(v, wa, wb), ...);
-}
-template <bool kImag, int... J>
-__device__ __forceinline__ void plane_store_all(const float2 (&v)[64], float* xb, int lane, std::integer_sequence<int, J...>) {
-  ((xb[J * kExchStride + lane] = kImag ? v[J].y : v[J].x), ...);
-}
-
-template <int... J>
-__device__ __forceinline__ void tw_store_all(const float2 (&v)[64], const float2 (&wa)[8], const float2 (&wb)[8],
-                                             float2* exch, int lane, std::integer_sequence<int, J...>) {
-  (tw_store<J>(v, wa, wb, exch, lane), ...);
-}
-
-__device__ __forceinline__ int phys(int k) { return k + (k >> 6); }  // padded index of bin k in the warp's sqmag buffer
-
-// Everything after the load: stage-1 FFT, transpose, stage-2 FFTs, untangling, stores, peak extraction (see file header).
-template <int kSync, bool kSplit>
-__device__ __forceinline__ void frame_body(float2 (&v)[64], const StftArgs& p, const float2* __restrict__ tab,
-                                           float2* __restrict__ exch, const int lane, const int64_t f, const bool active) {
+// windowed spectrum of the frame held (bit-reversed over n1, already windowed) in v[]: stage-1 FFT, transpose, stage-2
+// FFTs, untangling, |X|^2 to HBM and to the warp's shared buffer
+__device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p, const float4* __restrict__ tab4,
+                                                 const float2* __restrict__ tab2, c2* __restrict__ exch, const int lane,
+                                                 const int64_t f) {
   float* sq = reinterpret_cast<float*>(exch);
   const int colA = lane ? lane : 32;
   const int colB = lane ? 64 - lane : 32;
   const int k2c = static_cast<int>(__brev(static_cast<unsigned>(lane)) >> 27);  // brev5(lane)
-  // ---- stage 1: 64-point FFT over n1 ----
-  if (kSync == 1 || kSync == 3) __syncthreads();
-  if constexpr (kSync == 3) {  // finer lock step: the 64-point FFT in three pieces
-    Dit<64, 32, 0>::run(v);
-    __syncthreads();
-    Dit<64, 32, 32>::run(v);
-    __syncthreads();
-    Dit<64, 64, 0>::stage(v, std::make_integer_sequence<int, 32>{});
-  } else {
-    Dit<64, 64, 0>::run(v);  // natural order out: v[k1]
-  }
-  const float2 c0 = v[0];  // column k1 = 0 (no twiddle), one value per lane
-
-  if (kSync) __syncthreads();
-  float2 A[32], B[32];
+  // ---- stage 1: last stage of the 64-point FFT over n1 (the two 32-point halves are done by the caller) ----
+  DitP<64, 64, 0>::stage(v, std::make_integer_sequence<int, 32>{});
+  c2 u = v[0];  // column k1 = 0 (no twiddle), one value per lane
   {
-    float2 wa[8], wb[8];
+    TwP wa[8], wb[8];
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
-      wb[i] = tab[(i - 1) * 32 + lane];
-      wa[i] = tab[(6 + i) * 32 + lane];
+      wb[i] = make_twp(tab4[(i - 1) * 32 + lane]);
+      wa[i] = make_twp(tab4[(6 + i) * 32 + lane]);
     }
-    wa[0] = wb[0] = make_float2(1.f, 0.f);
-    if constexpr (!kSplit) {
-      tw_store_all(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
-    } else {
-      tw_inplace_all(v, wa, wb, std::make_integer_sequence<int, 64>{});
-    }
+    wa[0] = wb[0] = TwP{1.f, pk(0.f, 0.f)};
+    tw_store_all_p(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
   }
-  // ---- stage 2 inputs: columns colA, colB of the transposed data ----
-  if constexpr (!kSplit) {
-    __syncwarp();
+  // ---- stage 2: columns colA, colB of the transposed data ----
+  c2 A[32], B[32];
+  __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) {
-      A[bitrev(n2, 5)] = exch[colA * kExchStride + n2];
-      B[bitrev(n2, 5)] = exch[colB * kExchStride + n2];
-    }
-  } else {
-    float* xb = reinterpret_cast<float*>(exch);
-    plane_store_all<false>(v, xb, lane, std::make_integer_sequence<int, 64>{});
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) {
-      A[bitrev(n2, 5)].x = xb[colA * kExchStride + n2];
-      B[bitrev(n2, 5)].x = xb[colB * kExchStride + n2];
-    }
-    __syncwarp();
-    plane_store_all<true>(v, xb, lane, std::make_integer_sequence<int, 64>{});
-    __syncwarp();
-#pragma unroll
-    for (int n2 = 0; n2 < 32; ++n2) {
-      A[bitrev(n2, 5)].y = xb[colA * kExchStride + n2];
-      B[bitrev(n2, 5)].y = xb[colB * kExchStride + n2];
-    }
+  for (int n2 = 0; n2 < 32; ++n2) {
+    A[bitrev(n2, 5)] = exch[colA * kExchStride + n2];
+    B[bitrev(n2, 5)] = exch[colB * kExchStride + n2];
   }
   __syncwarp();  // exch is reused as the sqmag buffer below
-  if (kSync) __syncthreads();
-  Dit<32, 32, 0>::run(A);
-  if (kSync == 1 || kSync == 3) __syncthreads();
-  Dit<32, 32, 0>::run(B);
+  DitP<32, 32, 0>::run(A);
+  DitP<32, 32, 0>::run(B);
 
-  // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)) ----
-  float2 u = c0;
+  // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)), branch-free ----
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const int d = 16 >> s;
-    const float ox = __shfl_xor_sync(0xffffffffu, u.x, d);
-    const float oy = __shfl_xor_sync(0xffffffffu, u.y, d);
-    if (lane & d) {
-      const float2 w = tab[(14 + s) * 32 + lane];
-      u = cmul(make_float2(ox - u.x, oy - u.y), w);
-    } else {
-      u = make_float2(u.x + ox, u.y + oy);
-    }
+    const float2 uu = upk(u);
+    const c2 o = pk(__shfl_xor_sync(0xffffffffu, uu.x, d), __shfl_xor_sync(0xffffffffu, uu.y, d));
+    const float4 t = tab4[(15 + s) * 32 + lane];
+    u = cmul_tw(fma2(bc(t.y), u, o), make_twp(t));
   }
   float sq0, sqM;
   {
     const int pk2 = (32 - k2c) & 31;
     const int plane = static_cast<int>(__brev(static_cast<unsigned>(pk2)) >> 27);
-    const float mx = __shfl_sync(0xffffffffu, u.x, plane);
-    const float my = __shfl_sync(0xffffffffu, u.y, plane);
-    untangle(u, make_float2(mx, my), tab[19 * 32 + lane], sq0, sqM);
+    const float2 uu = upk(u);
+    const float mx = __shfl_sync(0xffffffffu, uu.x, plane);
+    const float my = __shfl_sync(0xffffffffu, uu.y, plane);
+    untangle(uu, make_float2(mx, my), tab2[lane], sq0, sqM);
   }
 
-  // ---- untangle the real FFT (bins k = colA + 64*k2 and 2048 - k) and write |X|^2: HBM row (coalesced across lanes)
-  //      and the warp's shared buffer (padded, conflict-free) ----
-  if (kSync) __syncthreads();
-  float* row = (p.sqmag && active) ? p.sqmag + f * p.sqmag_row_stride : nullptr;
+  // ---- untangle (bins k = colA + 64*k2 and 2048 - k), |X|^2 to the HBM row and to the warp's shared buffer ----
+  float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
   float* sqw = p.peak_count ? sq : nullptr;
-  post_all(A, B, tab[20 * 32 + lane], row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
-           sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
+  const TwP wpb = make_twp(tab4[14 * 32 + lane]);
+  post_all_p(A, B, wpb, row ? row + colA : nullptr, row ? row + colB : nullptr, sqw ? sqw + colA : nullptr,
+             sqw ? sqw + colB : nullptr, std::make_integer_sequence<int, 32>{});
   if (row) {
     row[64 * k2c] = sq0;
     if (lane == 0) row[kM] = sqM;
   }
-  if (kSync == 1 || kSync == 3) __syncthreads();
-  if (p.peak_count) {
-    sq[65 * k2c] = sq0;
-    if (lane == 0) sq[phys(kM)] = sqM;
-    __syncwarp();
+  if (sqw) {
+    sq[kSqBlock * k2c] = sq0;
+    if (lane == 0) sq[kSqFloats - 1] = sqM;
+  }
+}
 
-    // ---- peak scan: lane owns bins [64*lane, 64*lane+64) ----
-    // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
-    const int base = 65 * lane;
-    uint32_t mlo = 0, mhi = 0;
-    float l = lane ? sq[base - 2] : __int_as_float(0x7f800000);  // bin 0 is never a peak
-    float c = sq[base];
+// peak list of the frame whose |X|^2 sits in the warp's shared buffer: lane owns bins [64*lane, 64*lane+64)
+__device__ __forceinline__ void frame_peaks_p(const StftArgs& p, float* __restrict__ sq, const int lane, const int64_t f) {
+  __syncwarp();
+  // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
+  const int base = kSqBlock * lane;
+  uint64_t mask = 0;
+  float l = lane ? sq[base - 5] : __int_as_float(0x7f800000);  // bin 0 is never a peak
+  float c = sq[base];
+#pragma unroll 1
+  for (int ch = 0; ch < 8; ++ch) {
+    const float4 q0 = *reinterpret_cast<const float4*>(sq + base + 8 * ch);
+    const float4 q1 = *reinterpret_cast<const float4*>(sq + base + 8 * ch + 4);
+    const float nxt = sq[base + 8 * ch + 8 + (ch == 7 ? (lane == 31 ? 3 : 4) : 0)];  // first bin of the next block (2048: last pad)
+    const float w[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, nxt};
+    uint32_t m8 = 0;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-      const float r = sq[j == 63 ? base + 65 : base + j + 1];
-      const bool is_peak = c > fmaxf(fmaxf(l, r), p.thr_below);
-      if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
-      else mhi |= is_peak ? (1u << (j - 32)) : 0u;
+    for (int j = 0; j < 8; ++j) {
+      const float r = w[j + 1];
+      if (c > fmaxf(fmaxf(l, r), p.thr_below)) m8 |= 1u << j;
       l = c;
       c = r;
     }
-    uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
-    const int cnt = __popcll(mask);
-    int incl = cnt;
+    mask |= static_cast<uint64_t>(m8) << (8 * ch);
+  }
+  const int cnt = __popcll(mask);
+  int incl = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int slot = incl - cnt;
-    if (lane == 0 && active) p.peak_count[f] = total;
-    // each lane lists the bins of its peaks (ascending), then the peaks are spread over the lanes: the interpolation
-    // runs once per 32 peaks instead of once per peak of the busiest lane, and the stores are coalesced
-    // (the list lives behind the sqmag buffer, or, in the split variant whose buffer is half as large, in the output itself)
-    const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
-    int* klist = kSplit ? p.peak_bin + out_base : reinterpret_cast<int*>(sq + 2112);
-    const int n_store = active ? min(total, p.max_peaks) : 0;
-    while (mask && slot < n_store) {
-      const int j = __ffsll(static_cast<long long>(mask)) - 1;
-      mask &= mask - 1;
-      klist[slot++] = 64 * lane + j;
-    }
-    __syncwarp();
-    for (int idx = lane; idx < n_store; idx += 32) {
-      const int k = kSplit ? *reinterpret_cast<volatile int*>(klist + idx) : klist[idx];
-      const float fl = 1e-37f;
-      const float sa = fmaxf(sq[phys(k - 1)], fl), sb = fmaxf(sq[phys(k)], fl), sc = fmaxf(sq[phys(k + 1)], fl);
-      // dB differences in log2 units, from ratios to the centre bin (well conditioned); MUFU.LG2 / MUFU.RCP precision
-      const float inv_b = __frcp_rn(sb);
-      const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);  // (alpha-beta), (gamma-beta) / (10 log10 2)
-      const float num = la - lc;
-      const float den = la + lc;
-      const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
-      constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
-      const float beta = kDbPerLog2 * __log2f(sb);
-      if (!kSplit) p.peak_bin[out_base + idx] = k;
-      p.peak_freq[out_base + idx] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
-      p.peak_db[out_base + idx] = beta - 0.25f * (kDbPerLog2 * num) * pp;
-    }
-    __syncwarp();  // the next frame overwrites the buffer
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
   }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int slot = incl - cnt;
+  if (lane == 0) p.peak_count[f] = total;
+  // each lane lists the bins of its peaks (ascending), then the peaks are spread over the lanes: the interpolation
+  // runs once per 32 peaks instead of once per peak of the busiest lane, and the stores are coalesced
+  // (the list lives in the padding floats of the spectrum buffer; longer lists go through the output array itself)
+  const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
+  int* sqi = reinterpret_cast<int*>(sq);
+  const bool list_in_smem = p.max_peaks <= kKlistCap;
+  const int n_store = min(total, p.max_peaks);
+  while (mask && slot < n_store) {
+    const int j = __ffsll(static_cast<long long>(mask)) - 1;
+    mask &= mask - 1;
+    if (list_in_smem) sqi[klist_slot(slot)] = 64 * lane + j;
+    else p.peak_bin[out_base + slot] = 64 * lane + j;
+    ++slot;
+  }
+  __syncwarp();
+  for (int idx = lane; idx < n_store; idx += 32) {
+    const int k = list_in_smem ? sqi[klist_slot(idx)] : *reinterpret_cast<volatile int*>(p.peak_bin + out_base + idx);
+    const float fl = 1e-37f;
+    const float sa = fmaxf(sq[physp(k - 1)], fl), sb = fmaxf(sq[physp(k)], fl), sc = fmaxf(sq[physp(k + 1)], fl);
+    // dB differences in log2 units, from ratios to the centre bin (well conditioned); MUFU.LG2 / MUFU.RCP precision
+    const float inv_b = __frcp_rn(sb);
+    const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);  // (alpha-beta), (gamma-beta) / (10 log10 2)
+    const float num = la - lc;
+    const float den = la + lc;
+    const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
+    constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
+    const float beta = kDbPerLog2 * __log2f(sb);
+    if (list_in_smem) p.peak_bin[out_base + idx] = k;
+    p.peak_freq[out_base + idx] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
+    p.peak_db[out_base + idx] = beta - 0.25f * (kDbPerLog2 * num) * pp;
+  }
+  __syncwarp();  // the next frame overwrites the buffer
 }
 
-template <int WARPS>
-__device__ __forceinline__ void build_tables(float2* tab) {
-  for (int i = threadIdx.x; i < kTabRows * 32; i += WARPS * 32) {
-    const int r = i >> 5, l = i & 31;
-    float2 w;
-    if (r < 7) {
-      w = cis_neg(2.f * static_cast<float>(l * (r + 1)) / kM);  // W_2048^(l*b), b = r+1
-    } else if (r < 14) {
-      w = cis_neg(2.f * static_cast<float>(l * 8 * (r - 6)) / kM);  // W_2048^(l*8a), a = r-6
-    } else if (r < 19) {
-      const int d = 16 >> (r - 14);
-      w = cis_neg(static_cast<float>(l % d) / d);  // exp(-2 pi i (l%d)/(2d))
-    } else if (r == 19) {
-      const int k = 64 * static_cast<int>(__brev(static_cast<unsigned>(l)) >> 27);  // k = 64*brev5(l)
-      float s, c;
-      sincospif(2.f * static_cast<float>(k) / kN, &s, &c);
-      w = make_float2(-s, -c);  // -i * W_4096^k
+// raw samples of frame f into v[] (bit-reversed over n1): lane n2 takes z[32*n1 + n2] = (x[64*n1+2*n2], x[64*n1+2*n2+1]).
+// PAR selects the half with n1 = PAR (mod 2), i.e. registers v[32*PAR .. 32*PAR+31]: the first five DIT stages stay inside
+// a half, so the even half can be prefetched early (64 registers) and the odd half fetched while the even half is transformed.
+// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned 64-bit loads are legal.
+__device__ __forceinline__ const float* frame_base_p(const StftArgs& p, const int64_t f) {
+  const int fps = static_cast<int>(p.frames_per_stream);
+  int stream, fr;
+  if (p.total_frames < (1ll << 31)) {
+    const unsigned uf = static_cast<unsigned>(f);
+    stream = static_cast<int>(uf / static_cast<unsigned>(fps));
+    fr = static_cast<int>(uf - static_cast<unsigned>(stream) * static_cast<unsigned>(fps));
+  } else {
+    stream = static_cast<int>(f / fps);
+    fr = static_cast<int>(f - static_cast<int64_t>(stream) * fps);
+  }
+  return p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
+}
+template <int PAR, bool kVec2, bool kFull>
+__device__ __forceinline__ void frame_load_p(c2 (&v)[64], const StftArgs& p, const float* __restrict__ xs, const int lane) {
+#pragma unroll
+  for (int n1 = PAR; n1 < 64; n1 += 2) {
+    const int idx = 64 * n1 + 2 * lane;
+    c2 s;
+    if (kVec2 && kFull) {
+      s = ldg_c2(xs + idx);
+    } else if (kVec2) {
+      s = (idx < p.window) ? ldg_c2(xs + idx) : pk(0.f, 0.f);
     } else {
-      const int col = l ? l : 32;
-      float s, c;
-      sincospif(2.f * static_cast<float>(col) / kN, &s, &c);
-      w = make_float2(-s, -c);
+      s = pk((kFull || idx < p.window) ? __ldg(xs + idx) : 0.f, (kFull || idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f);
     }
-    tab[i] = w;
+    v[bitrev(n1, 6)] = s;  // DIT: bit-reversed register order in
   }
 }
+// even half of frame (base xs) -> the staging area of the warp's buffer, asynchronously and without registers
+template <bool kVec2, bool kFull>
+__device__ __forceinline__ void frame_stage_even_p(c2* __restrict__ stage, const StftArgs& p, const float* __restrict__ xs,
+                                                   const int lane) {
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int idx = 128 * r + 2 * lane;
+    c2* dst = stage + 32 * r + lane;
+    if (kVec2) {
+      const bool in = kFull || idx < p.window;
+      cp_async8(dst, in ? xs + idx : xs, in ? 8 : 0);
+    } else {
+      const bool in0 = kFull || idx < p.window, in1 = kFull || idx + 1 < p.window;
+      cp_async4(dst, in0 ? xs + idx : xs, in0 ? 4 : 0);
+      cp_async4(reinterpret_cast<float*>(dst) + 1, in1 ? xs + idx + 1 : xs, in1 ? 4 : 0);
+    }
+  }
+  cp_async_commit();
+}
+// staged even half -> registers, windowed
+__device__ __forceinline__ void frame_take_even_p(c2 (&v)[64], const c2* __restrict__ stage, const c2* __restrict__ win_c,
+                                                  const int lane) {
+#pragma unroll
+  for (int r = 0; r < 32; ++r) v[bitrev(2 * r, 6)] = mul2(stage[32 * r + lane], win_c[64 * r + lane]);
+}
+template <int PAR>
+__device__ __forceinline__ void frame_window_p(c2 (&v)[64], const c2* __restrict__ win_c, const int lane) {
+#pragma unroll
+  for (int n1 = PAR; n1 < 64; n1 += 2) v[bitrev(n1, 6)] = mul2(v[bitrev(n1, 6)], win_c[32 * n1 + lane]);
+}
 
-// kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned float2 loads are legal.
-// kSync: the warps of the CTA walk the frame code in step (one __syncthreads per phase). The frame body is ~70 KB of
-// straight-line SASS; unsynchronised warps each stream it from L2 on their own and instruction fetch becomes the limiter
-// (ncu: stall_no_inst 26 % of samples, profiles/), in step they share the fetches.
-template <int WARPS, int MINB, int kSync, bool kVec2, bool kFull>
-__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_kernel(const __grid_constant__ StftArgs p) {
+template <int WARPS, int MINB, bool kVec2, bool kFull>
+__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __grid_constant__ StftArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* tab = reinterpret_cast<float2*>(smem_raw);  // [kTabRows][32]
-  float2* exch_all = tab + kTabRows * 32;             // [WARPS][kExchFloat2]
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);               // [kTab4Rows][32]
+  float2* tab2 = reinterpret_cast<float2*>(tab4 + kTab4Rows * 32);  // [32]
+  float2* win_s = tab2 + 32;                                        // [2048] window (pairs), pre-scaled
+  c2* exch_all = reinterpret_cast<c2*>(win_s + kM);                 // [WARPS][kExchFloat2]
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-
-  build_tables<WARPS>(tab);
+  build_tables_p<WARPS>(tab4, tab2, win_s, p.win);
   __syncthreads();
+  c2* exch = exch_all + warp * kExchFloat2;
+  const c2* win_c = reinterpret_cast<const c2*>(win_s);
 
-  float2* exch = exch_all + warp * kExchFloat2;
-
-  // CTA-uniform rounds: round r covers frames base .. base+WARPS-1, one per warp (the tail warps of the last round idle)
-  const int fps = static_cast<int>(p.frames_per_stream);
-  for (int64_t fbase = static_cast<int64_t>(blockIdx.x) * WARPS; fbase < p.total_frames;
-       fbase += static_cast<int64_t>(gridDim.x) * WARPS) {
-    const int64_t f = fbase + warp;
-    const bool active = f < p.total_frames;
-    if (kSync) __syncthreads();
-    if (!kSync && !active) break;
-    int stream, fr;
-    if (p.total_frames < (1ll << 31)) {
-      const unsigned uf = static_cast<unsigned>(active ? f : 0);
-      stream = static_cast<int>(uf / static_cast<unsigned>(fps));
-      fr = static_cast<int>(uf - static_cast<unsigned>(stream) * static_cast<unsigned>(fps));
-    } else {
-      stream = static_cast<int>((active ? f : 0) / fps);
-      fr = static_cast<int>((active ? f : 0) - static_cast<int64_t>(stream) * fps);
+  const int64_t fstep = static_cast<int64_t>(gridDim.x) * WARPS;
+  int64_t f = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+  if (f >= p.total_frames) return;
+  c2* stage = exch + kStageOff;
+  c2 v[64];
+  const float* xs = frame_base_p(p, f);
+  frame_stage_even_p<kVec2, kFull>(stage, p, xs, lane);
+  for (;;) {
+    frame_load_p<1, kVec2, kFull>(v, p, xs, lane);  // odd half: lands while the even half is transformed
+    cp_async_wait_all();
+    __syncwarp();
+    frame_take_even_p(v, stage, win_c, lane);
+    DitP<64, 32, 0>::run(v);
+    frame_window_p<1>(v, win_c, lane);
+    DitP<64, 32, 32>::run(v);
+    __syncwarp();  // every lane has taken its staged samples: the buffer may be overwritten by the transpose
+    frame_spectrum_p(v, p, tab4, tab2, exch, lane, f);
+    const int64_t fn = f + fstep;
+    const bool more = fn < p.total_frames;
+    if (more) {
+      xs = frame_base_p(p, fn);
+      frame_stage_even_p<kVec2, kFull>(stage, p, xs, lane);  // in flight during the peak extraction
     }
-    const float* xs = p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
-
-    // ---- load + window: lane n2 takes z[32*n1 + n2] = (x[64*n1+2*n2], x[64*n1+2*n2+1]) ----
-    float2 v[64];
-#pragma unroll
-    for (int n1 = 0; n1 < 64; ++n1) {
-      const int idx = 64 * n1 + 2 * lane;
-      float2 s;
-      if (kVec2 && kFull) {
-        s = ldg2(xs + idx);
-      } else if (kVec2) {
-        s = (idx < p.window) ? ldg2(xs + idx) : make_float2(0.f, 0.f);
-      } else {
-        s.x = (kFull || idx < p.window) ? __ldg(xs + idx) : 0.f;
-        s.y = (kFull || idx + 1 < p.window) ? __ldg(xs + idx + 1) : 0.f;
-      }
-      const float2 w = ldg2(p.win + idx);
-      v[bitrev(n1, 6)] = make_float2(s.x * w.x, s.y * w.y);  // DIT: bit-reversed register order in
-    }
-
-    frame_body<kSync, false>(v, p, tab, exch, lane, f, active);
+    if (p.peak_count) frame_peaks_p(p, reinterpret_cast<float*>(exch), lane, f);
+    if (!more) break;
+    f = fn;
   }
 }
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// Ring variant (window == 4096, hop % 4 == 0, hop <= 1024, 16-byte aligned streams): the CTA walks a CONTIGUOUS range of
-// frames of one stream, WARPS frames per round, and keeps the samples it needs in an 8192-float shared-memory ring that is
-// fed by 1-D bulk async copies (cp.async.bulk + mbarrier, SASS UBLKCP): the 4*hop new samples of the next round are in
-// flight during the whole arithmetic of the current round, so the load phase reads shared memory instead of waiting on
-// L2/HBM. Frames overlap by (window-hop)/window, so each sample crosses L2->SM once per CTA instead of 16 times.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kRing = 8192;  // floats; >= 4096 + 3*hop + 4*hop for hop <= 585, and window + 3*hop <= 8192 for hop <= 1024
-
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// copy samples [s0, s1) of a stream into the ring (position = sample index mod kRing); s0, s1 multiples of 4
-__device__ __forceinline__ uint32_t ring_fill(float* ring, const float* stream_base, int64_t s0, int64_t s1, uint64_t* bar) {
-  if (s1 <= s0) return 0;
-  const uint32_t bytes = static_cast<uint32_t>(s1 - s0) * 4u;
-  mbar_expect_tx(bar, bytes);
-  int64_t s = s0;
-  while (s < s1) {
-    const int pos = static_cast<int>(s & (kRing - 1));
-    const int64_t n = min(s1 - s, static_cast<int64_t>(kRing - pos));
-    bulk_g2s(ring + pos, stream_base + s, static_cast<uint32_t>(n) * 4u, bar);
-    s += n;
-  }
-  return bytes;
-}
-
-struct RingPlan {
-  int32_t units_per_stream;
-  int32_t frames_per_unit;  // multiple of WARPS
-  int32_t total_units;
-};
-
-template <int WARPS, int MINB, bool kSplit>
-__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096_ring_kernel(const __grid_constant__ StftArgs p,
-                                                                        const __grid_constant__ RingPlan rp) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* ring = reinterpret_cast<float*>(smem_raw);                    // [kRing]
-  float2* tab = reinterpret_cast<float2*>(ring + kRing);               // [kTabRows][32]
-  float2* exch_all = tab + kTabRows * 32;                              // [WARPS][kExchFloat2 (half of it when kSplit)]
-  __shared__ __align__(8) uint64_t bar;
-
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  build_tables<WARPS>(tab);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  float2* exch = exch_all + warp * (kSplit ? kExchFloat2 / 2 : kExchFloat2);
-  const int fps = static_cast<int>(p.frames_per_stream);
-  uint32_t parity = 0;
-
-  for (int u = blockIdx.x; u < rp.total_units; u += gridDim.x) {
-    const int stream = u / rp.units_per_stream;
-    const int fa = (u - stream * rp.units_per_stream) * rp.frames_per_unit;
-    const int fb = min(fps, fa + rp.frames_per_unit);
-    const float* xs = p.x + static_cast<int64_t>(stream) * p.stream_stride;
-    // all warps are past the load phase of the previous unit (barrier after its last load): the ring can be refilled
-    bool pending = false;
-    if (threadIdx.x == 0) {
-      const int last = min(fa + WARPS - 1, fb - 1);
-      ring_fill(ring, xs, static_cast<int64_t>(fa) * p.hop, static_cast<int64_t>(last) * p.hop + kN, &bar);
-    }
-    pending = true;
-    for (int f0 = fa; f0 < fb; f0 += WARPS) {
-      const int fr = f0 + warp;
-      const bool active = fr < fb;
-      const int64_t f = static_cast<int64_t>(stream) * fps + (active ? fr : fa);
-      if (pending) {
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-      }
-      // ---- load + window from the ring ----
-      float2 v[64];
-      const int pos0 = static_cast<int>((static_cast<int64_t>(active ? fr : fa) * p.hop) & (kRing - 1));
-#pragma unroll
-      for (int n1 = 0; n1 < 64; ++n1) {
-        const int idx = 64 * n1 + 2 * lane;
-        const float2 sm = *reinterpret_cast<const float2*>(ring + ((pos0 + idx) & (kRing - 1)));
-        const float2 w = ldg2(p.win + idx);
-        v[bitrev(n1, 6)] = make_float2(sm.x * w.x, sm.y * w.y);
-      }
-      __syncthreads();  // every warp has its samples in registers: the ring may take the next round's data
-      {
-        const int next_last = min(f0 + 2 * WARPS - 1, fb - 1);
-        const int this_last = min(f0 + WARPS - 1, fb - 1);
-        pending = next_last > this_last;  // CTA-uniform
-        if (pending && threadIdx.x == 0)
-          ring_fill(ring, xs, static_cast<int64_t>(this_last) * p.hop + kN, static_cast<int64_t>(next_last) * p.hop + kN, &bar);
-      }
-      frame_body<1, kSplit>(v, p, tab, exch, lane, f, active);
-    }
-    __syncthreads();
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Generic path for FFT lengths other than 4096 (1024 .. 32768; the reference default window of 0.1814 s is 8192 points
@@ -716,76 +635,19 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   }
   a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
 
-  // tuning knobs (defaults are the measured best): CA_STFT_VARIANT = 0..4
-  static const int variant = [] {
-    const char* e = getenv("CA_STFT_VARIANT");
-    return e ? atoi(e) : 4;
-  }();
   const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
                     (ctx->stft.window % 2 == 0);
   const bool full = ctx->stft.window == kN;
-  void (*kern)(StftArgs) = nullptr;
-  int WARPS = 4;
-#define CA_PICK(W, MB, SY)                                                                                       \
-  do {                                                                                                           \
-    WARPS = W;                                                                                                   \
-    kern = vec2 ? (full ? stft4096_kernel<W, MB, SY, true, true> : stft4096_kernel<W, MB, SY, true, false>)     \
-                : (full ? stft4096_kernel<W, MB, SY, false, true> : stft4096_kernel<W, MB, SY, false, false>);  \
-  } while (0)
-  // measured on B200, 32 x 60 s streams, Mframes/s (profiles/README.md): 0 (4 warps x 3 CTAs, free running) 144;
-  // 1 (8x1, in step) 127; 2 (8x1, free) 127; 3 (12x1, in step) 140; 4 (4x3, in step) 153 <- default;
-  // 5 (4x3, in step, bulk-copy ring + split transpose) 147; 6 (4x2, in step, bulk-copy ring) 150
-  switch (variant) {
-    case 0: CA_PICK(4, 3, 0); break;
-    case 1: CA_PICK(8, 1, 1); break;
-    case 3: CA_PICK(12, 1, 1); break;
-    case 7: CA_PICK(4, 3, 2); break;
-    case 8: CA_PICK(4, 3, 3); break;
-    default: CA_PICK(4, 3, 1); break;
-  }
-#undef CA_PICK
-  const bool ring_ok = full && ctx->stft.hop % 4 == 0 && ctx->stft.hop <= 1024 && stream_stride % 4 == 0 &&
-                       reinterpret_cast<uintptr_t>(d_x) % 16 == 0 && frames < (1ll << 30) && variant >= 5;
-  if (ring_ok) {
-    constexpr int RW = 4;
-    const bool split = variant != 6;
-    auto rk = split ? stft4096_ring_kernel<RW, 3, true> : stft4096_ring_kernel<RW, 2, false>;
-    const size_t rsmem = sizeof(float) * kRing + sizeof(float2) * (kTabRows * 32 + RW * (split ? kExchFloat2 / 2 : kExchFloat2));
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rsmem)));
-    int rper_sm = 0;
-    CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper_sm, rk, RW * 32, rsmem));
-    if (rper_sm < 1) rper_sm = 1;
-    const int64_t rgrid_full = static_cast<int64_t>(ctx->sm_count) * rper_sm;
-    // units: contiguous frame ranges inside a stream, about 4 per CTA for balance
-    RingPlan rp{};
-    int64_t ups = (4 * rgrid_full + n_streams - 1) / n_streams;
-    if (ups < 1) ups = 1;
-    int64_t fpu = (frames + ups - 1) / ups;
-    fpu = (fpu + RW - 1) / RW * RW;
-    if (fpu < 8 * RW) fpu = 8 * RW;  // amortise the unit prologue (a full window) over at least 8 rounds
-    ups = (frames + fpu - 1) / fpu;
-    rp.units_per_stream = static_cast<int32_t>(ups);
-    rp.frames_per_unit = static_cast<int32_t>(fpu);
-    const int64_t units = ups * n_streams;
-    if (units < (1ll << 31)) {
-      rp.total_units = static_cast<int32_t>(units);
-      const int64_t rgrid = std::min<int64_t>(rgrid_full, units);
-      rk<<<static_cast<unsigned>(rgrid), RW * 32, rsmem, stream>>>(a, rp);
-      CA_CUDA_OK(ctx, cudaGetLastError());
-      ctx->launches += 1;
-      return CA_OK;
-    }
-  }
-  const size_t smem = sizeof(float2) * (kTabRows * 32 + WARPS * kExchFloat2);
+  // 12 warps x 1 CTA per SM: 12 x 16.5 KB exchange buffers + 16 KB window + tables = 224 KB of shared memory, 168 registers
+  constexpr int PW = 12;
+  void (*kern)(StftArgs) = vec2 ? (full ? stft4096p_kernel<PW, 1, true, true> : stft4096p_kernel<PW, 1, true, false>)
+                                : (full ? stft4096p_kernel<PW, 1, false, true> : stft4096p_kernel<PW, 1, false, false>);
+  const size_t smem = sizeof(float4) * kTab4Rows * 32 + sizeof(float2) * (32 + kM + PW * kExchFloat2);
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int per_sm = 0;
-  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-  if (per_sm < 1) per_sm = 1;
-  if (const char* e = getenv("CA_STFT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning experiments
-  int64_t grid = static_cast<int64_t>(ctx->sm_count) * per_sm;
-  const int64_t need = (total + WARPS - 1) / WARPS;
+  int64_t grid = ctx->sm_count;
+  const int64_t need = (total + PW - 1) / PW;
   if (grid > need) grid = need;
-  kern<<<static_cast<unsigned>(grid), WARPS * 32, smem, stream>>>(a);
+  kern<<<static_cast<unsigned>(grid), PW * 32, smem, stream>>>(a);
   CA_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches += 1;
   return CA_OK;
