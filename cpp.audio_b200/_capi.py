@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libcpp_audio_b200.so")
+_LIB = os.environ.get("CA_B200_LIB") or os.path.join(_HERE, "libcpp_audio_b200.so")  # override: instrumented builds (profiles/)
 
 DECLARED_SYMBOLS = [
     "ca_version", "ca_init", "ca_destroy", "ca_last_error", "ca_sm_count", "ca_kernel_launches", "ca_host_alloc",

@@ -15,8 +15,11 @@
 // Restates PeriodicFFT<SqMagFftOperation<Window,T>> + extractLocalMaxFreqsMags for whole streams
 // (source/rt.resynth.lib.periodicfft.cpp:13-181,251-325; call site source/rt.resynth.lib.cpp:1592-1595);
 // the unpinned arithmetic follows oracle/SPEC.md S1-S6.
+#include <cuda.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -32,8 +35,13 @@ namespace {
 constexpr int kN = 4096;         // real FFT length
 constexpr int kM = 2048;         // complex FFT length
 constexpr int kBins = kM + 1;
-constexpr int kExchStride = 33;  // float2 per row of the 64 x 32 transpose buffer (conflict-free both ways)
-constexpr int kExchFloat2 = 64 * kExchStride;
+// transpose buffer of a warp: element (k1, n2) at (k1 >> 1)*kExchStride + 2*n2 + (k1 & 1), in complex units. A lane
+// stores two consecutive k1 with one 128-bit store; the readers (one column k1 per lane, consecutive columns in
+// consecutive lanes) are conflict-free because kExchStride = 2 (mod 16).
+constexpr int kExchStride = 66;
+constexpr int kExchFloat2 = 32 * kExchStride;
+constexpr int kWinStride = 66;  // window table: 64 pairs per lane (+2 pad), the 32 even-n1 pairs first, then the odd ones
+__device__ __forceinline__ int exch_idx(int k1, int n2) { return (k1 >> 1) * kExchStride + 2 * n2 + (k1 & 1); }
 
 struct StftArgs {
   const float* x;
@@ -55,7 +63,19 @@ struct StftArgs {
   float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
   float bin_to_hz;
   int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
+  int32_t stagger;         // start-up delay between the warps that share a scheduler, in clocks (see the kernel)
+  long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
 };
+#ifdef CA_STFT_TIMELINE
+#define CA_STAMP(i)                                                                                        \
+  do {                                                                                                     \
+    if (p.dbg && lane == 0 && blockIdx.x < 2 && dbg_frame < 24) p.dbg[((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 24 + dbg_frame) * 12 + (i)] = clock64(); \
+  } while (0)
+#else
+#define CA_STAMP(i) \
+  do {              \
+  } while (0)
+#endif
 
 __device__ __forceinline__ float2 cis_neg(float turns_times_two) {  // exp(-i*pi*arg)
   float s, c;
@@ -96,15 +116,41 @@ __device__ __forceinline__ int physp(int k) { return k == kM ? kSqFloats - 1 : k
 __device__ __forceinline__ int klist_slot(int s) { return kSqBlock * (s >> 2) + 64 + (s & 3); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
-// asynchronous global -> shared copy that bypasses the register file (LDGSTS); n_src = 0 writes zeros without reading
-__device__ __forceinline__ void cp_async8(void* dst, const void* src, int n_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n_src) : "memory");
+// 1-D bulk asynchronous copy global -> shared (TMA engine, SASS UBLKCP), completion counted in bytes on an mbarrier.
+// Unlike cp.async (LDGSTS) it is not tracked by the warp's scoreboard, so the shared-memory reads of the peak scan that
+// follow do not wait for it: the copy really overlaps them.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, int n_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n_src) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 3-D tiled tensor copy global -> shared (SASS UTMALDG): ONE instruction moves a strided box, here the 32 rows of 64
+// samples that make the even (or odd) half of a frame
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int WARPS>
 __device__ __forceinline__ void build_tables_p(float4* tab4, float2* tab2, float2* win_s, const float* __restrict__ win) {
@@ -141,21 +187,31 @@ __device__ __forceinline__ void build_tables_p(float4* tab4, float2* tab2, float
     sincospif(2.f * static_cast<float>(k) / kN, &s, &c);
     tab2[l] = make_float2(-s, -c);  // -i * W_4096^k
   }
-  for (int i = threadIdx.x; i < kM; i += WARPS * 32) win_s[i] = __ldg(reinterpret_cast<const float2*>(win) + i);
+  // win_s[lane][par][r] = (w[64*n1 + 2*lane], w[64*n1 + 2*lane + 1]), n1 = 2r + par: a lane reads two of its pairs with
+  // one conflict-free 128-bit load
+  for (int i = threadIdx.x; i < kM; i += WARPS * 32) {
+    const int n1 = i >> 5, l = i & 31;
+    win_s[l * kWinStride + (n1 & 1) * 32 + (n1 >> 1)] = __ldg(reinterpret_cast<const float2*>(win) + i);
+  }
 }
 
 template <int J>
-__device__ __forceinline__ void tw_store_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane) {
+__device__ __forceinline__ c2 tw_apply_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8]) {
   constexpr int a = J >> 3, b = J & 7;
   c2 y = v[J];
   if constexpr (b != 0) y = cmul_tw(y, wb[b]);
   if constexpr (a != 0) y = cmul_tw(y, wa[a]);
-  if constexpr (J != 0) exch[J * kExchStride + lane] = y;  // column 0 goes through the shuffle FFT
+  return y;
 }
-template <int... J>
+template <int M>
+__device__ __forceinline__ void tw_store_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane) {
+  const c2 y0 = tw_apply_p<2 * M>(v, wa, wb), y1 = tw_apply_p<2 * M + 1>(v, wa, wb);  // (column 0 is not read back)
+  *reinterpret_cast<ulonglong2*>(exch + M * kExchStride + 2 * lane) = make_ulonglong2(y0, y1);
+}
+template <int... M>
 __device__ __forceinline__ void tw_store_all_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane,
-                                               std::integer_sequence<int, J...>) {
-  (tw_store_p<J>(v, wa, wb, exch, lane), ...);
+                                               std::integer_sequence<int, M...>) {
+  (tw_store_p<M>(v, wa, wb, exch, lane), ...);
 }
 
 // untangle bins k = colA + 64*K2 and 2048-k = colB + 64*(31-K2) and store them at once (HBM row and/or the warp's padded
@@ -187,11 +243,30 @@ __device__ __forceinline__ void post_all_p(const c2 (&A)[32], const c2 (&B)[32],
   (post_pair_p<K2>(A, B, wpb, rowA, rowB, sqA, sqB), ...);
 }
 
+// Even half of frame (stream, fr) -> the staging area of the warp's buffer. The input is described to the copy engine as
+// a tensor [stream][row][128 samples]; with hop % 128 == 0 a frame starts on a row, its even half (n1 = 2r: samples
+// 128r .. 128r+63) is the box {64 samples, 32 rows} at column 0 and ONE tensor copy moves it. (32 separate 256-byte bulk
+// copies cost ~85 clocks of issue each, measured with the timeline build; cp.async / LDGSTS is tracked by the warp's
+// scoreboard, so the shared-memory reads of the peak scan would wait for it.)
+// No fence.proxy.async: the last generic-proxy accesses to the staging area are the transpose loads, which returned the
+// values of the stores before them, and every lane is past them (__syncwarp in the caller).
+__device__ __forceinline__ void frame_stage_even_p(c2* __restrict__ stage, const CUtensorMap* map, const StftArgs& p,
+                                                   const int64_t f, const int lane, uint64_t* bar) {
+  if (lane == 0) {
+    const int fps = static_cast<int>(p.frames_per_stream);
+    const int stream = static_cast<int>(f / fps);
+    const int fr = static_cast<int>(f - static_cast<int64_t>(stream) * fps);
+    mbar_expect_tx(bar, 32 * 256);
+    tma_load_3d(stage, map, 0, fr * (p.hop >> 7), stream, bar);
+  }
+}
+
 // windowed spectrum of the frame held (bit-reversed over n1, already windowed) in v[]: stage-1 FFT, transpose, stage-2
 // FFTs, untangling, |X|^2 to HBM and to the warp's shared buffer
 __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p, const float4* __restrict__ tab4,
                                                  const float2* __restrict__ tab2, c2* __restrict__ exch, const int lane,
-                                                 const int64_t f) {
+                                                 const int64_t f, const CUtensorMap* map, const int64_t f_next,
+                                                 uint64_t* bar, const int dbg_frame = 0) {
   float* sq = reinterpret_cast<float*>(exch);
   const int colA = lane ? lane : 32;
   const int colB = lane ? 64 - lane : 32;
@@ -207,19 +282,25 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
       wa[i] = make_twp(tab4[(6 + i) * 32 + lane]);
     }
     wa[0] = wb[0] = TwP{1.f, pk(0.f, 0.f)};
-    tw_store_all_p(v, wa, wb, exch, lane, std::make_integer_sequence<int, 64>{});
+    tw_store_all_p(v, wa, wb, exch, lane, std::make_integer_sequence<int, 32>{});
   }
+  CA_STAMP(3);
   // ---- stage 2: columns colA, colB of the transposed data ----
   c2 A[32], B[32];
   __syncwarp();
 #pragma unroll
   for (int n2 = 0; n2 < 32; ++n2) {
-    A[bitrev(n2, 5)] = exch[colA * kExchStride + n2];
-    B[bitrev(n2, 5)] = exch[colB * kExchStride + n2];
+    A[bitrev(n2, 5)] = exch[exch_idx(colA, n2)];
+    B[bitrev(n2, 5)] = exch[exch_idx(colB, n2)];
   }
   __syncwarp();  // exch is reused as the sqmag buffer below
+  // the upper half of the buffer is dead from here to the next transpose: stage the even half of the warp's next frame
+  // in it now, so that the copy has the rest of this frame (FFTs, untangling, peak extraction) to land
+  if (f_next >= 0) frame_stage_even_p(exch + kStageOff, map, p, f_next, lane, bar);
+  CA_STAMP(4);
   DitP<32, 32, 0>::run(A);
   DitP<32, 32, 0>::run(B);
+  CA_STAMP(5);
 
   // ---- column 0: 32-point FFT across lanes (DIF, bit-reversed result: lane L holds k2 = brev5(L)), branch-free ----
 #pragma unroll
@@ -240,6 +321,7 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
     untangle(uu, make_float2(mx, my), tab2[lane], sq0, sqM);
   }
 
+  CA_STAMP(6);
   // ---- untangle (bins k = colA + 64*k2 and 2048 - k), |X|^2 to the HBM row and to the warp's shared buffer ----
   float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
   float* sqw = p.peak_count ? sq : nullptr;
@@ -259,27 +341,28 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
 // peak list of the frame whose |X|^2 sits in the warp's shared buffer: lane owns bins [64*lane, 64*lane+64)
 __device__ __forceinline__ void frame_peaks_p(const StftArgs& p, float* __restrict__ sq, const int lane, const int64_t f) {
   __syncwarp();
-  // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold)
+  // strict local maximum at or above the threshold  <=>  c > max(l, r, largest float below the threshold).
+  // All 64 bins of the lane are fetched first (16 x LDS.128): one memory latency instead of one per chunk.
   const int base = kSqBlock * lane;
-  uint64_t mask = 0;
-  float l = lane ? sq[base - 5] : __int_as_float(0x7f800000);  // bin 0 is never a peak
-  float c = sq[base];
-#pragma unroll 1
-  for (int ch = 0; ch < 8; ++ch) {
-    const float4 q0 = *reinterpret_cast<const float4*>(sq + base + 8 * ch);
-    const float4 q1 = *reinterpret_cast<const float4*>(sq + base + 8 * ch + 4);
-    const float nxt = sq[base + 8 * ch + 8 + (ch == 7 ? (lane == 31 ? 3 : 4) : 0)];  // first bin of the next block (2048: last pad)
-    const float w[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, nxt};
-    uint32_t m8 = 0;
+  float w[66];
+  w[0] = lane ? sq[base - 5] : __int_as_float(0x7f800000);  // bin 0 is never a peak
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float r = w[j + 1];
-      if (c > fmaxf(fmaxf(l, r), p.thr_below)) m8 |= 1u << j;
-      l = c;
-      c = r;
-    }
-    mask |= static_cast<uint64_t>(m8) << (8 * ch);
+  for (int q = 0; q < 16; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(sq + base + 4 * q);
+    w[1 + 4 * q] = t.x;
+    w[2 + 4 * q] = t.y;
+    w[3 + 4 * q] = t.z;
+    w[4 + 4 * q] = t.w;
   }
+  w[65] = sq[base + (lane == 31 ? 67 : 68)];  // first bin of the next block (bin 2048 sits in the very last pad)
+  uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const bool is_peak = w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below);
+    if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
+    else mhi |= is_peak ? (1u << (j - 32)) : 0u;
+  }
+  uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
   const int cnt = __popcll(mask);
   int incl = cnt;
 #pragma unroll
@@ -357,76 +440,94 @@ __device__ __forceinline__ void frame_load_p(c2 (&v)[64], const StftArgs& p, con
     v[bitrev(n1, 6)] = s;  // DIT: bit-reversed register order in
   }
 }
-// even half of frame (base xs) -> the staging area of the warp's buffer, asynchronously and without registers
-template <bool kVec2, bool kFull>
-__device__ __forceinline__ void frame_stage_even_p(c2* __restrict__ stage, const StftArgs& p, const float* __restrict__ xs,
-                                                   const int lane) {
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    const int idx = 128 * r + 2 * lane;
-    c2* dst = stage + 32 * r + lane;
-    if (kVec2) {
-      const bool in = kFull || idx < p.window;
-      cp_async8(dst, in ? xs + idx : xs, in ? 8 : 0);
-    } else {
-      const bool in0 = kFull || idx < p.window, in1 = kFull || idx + 1 < p.window;
-      cp_async4(dst, in0 ? xs + idx : xs, in0 ? 4 : 0);
-      cp_async4(reinterpret_cast<float*>(dst) + 1, in1 ? xs + idx + 1 : xs, in1 ? 4 : 0);
-    }
-  }
-  cp_async_commit();
-}
 // staged even half -> registers, windowed
 __device__ __forceinline__ void frame_take_even_p(c2 (&v)[64], const c2* __restrict__ stage, const c2* __restrict__ win_c,
                                                   const int lane) {
 #pragma unroll
-  for (int r = 0; r < 32; ++r) v[bitrev(2 * r, 6)] = mul2(stage[32 * r + lane], win_c[64 * r + lane]);
+  for (int r = 0; r < 32; r += 2) {
+    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(win_c + lane * kWinStride + r);
+    v[bitrev(2 * r, 6)] = mul2(stage[32 * r + lane], w.x);
+    v[bitrev(2 * r + 2, 6)] = mul2(stage[32 * r + 32 + lane], w.y);
+  }
 }
 template <int PAR>
 __device__ __forceinline__ void frame_window_p(c2 (&v)[64], const c2* __restrict__ win_c, const int lane) {
 #pragma unroll
-  for (int n1 = PAR; n1 < 64; n1 += 2) v[bitrev(n1, 6)] = mul2(v[bitrev(n1, 6)], win_c[32 * n1 + lane]);
+  for (int r = 0; r < 32; r += 2) {
+    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(win_c + lane * kWinStride + 32 * PAR + r);
+    v[bitrev(2 * r + PAR, 6)] = mul2(v[bitrev(2 * r + PAR, 6)], w.x);
+    v[bitrev(2 * r + 2 + PAR, 6)] = mul2(v[bitrev(2 * r + 2 + PAR, 6)], w.y);
+  }
 }
 
-template <int WARPS, int MINB, bool kVec2, bool kFull>
-__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __grid_constant__ StftArgs p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// kBulk: the even half of the warp's next frame is staged by bulk copies during the peak extraction (needs window ==
+// 4096, hop % 4 == 0 and 16-byte aligned streams); otherwise both halves are loaded at the top of the frame.
+template <int WARPS, int MINB, bool kVec2, bool kFull, bool kBulk>
+__global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __grid_constant__ StftArgs p,
+                                                                     const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* tab4 = reinterpret_cast<float4*>(smem_raw);               // [kTab4Rows][32]
   float2* tab2 = reinterpret_cast<float2*>(tab4 + kTab4Rows * 32);  // [32]
-  float2* win_s = tab2 + 32;                                        // [2048] window (pairs), pre-scaled
-  c2* exch_all = reinterpret_cast<c2*>(win_s + kM);                 // [WARPS][kExchFloat2]
+  float2* win_s = tab2 + 32;                                        // [32][kWinStride] window (pairs), pre-scaled
+  c2* exch_all = reinterpret_cast<c2*>(win_s + 32 * kWinStride);    // [WARPS][kExchFloat2]
+  __shared__ __align__(8) uint64_t bars[WARPS];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   build_tables_p<WARPS>(tab4, tab2, win_s, p.win);
+  if (kBulk && lane == 0) {
+    mbar_init(&bars[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   c2* exch = exch_all + warp * kExchFloat2;
   const c2* win_c = reinterpret_cast<const c2*>(win_s);
+  uint64_t* bar = &bars[warp];
 
   const int64_t fstep = static_cast<int64_t>(gridDim.x) * WARPS;
   int64_t f = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
   if (f >= p.total_frames) return;
+  if (p.stagger > 0 && warp >= 4) {
+    // warps w, w+4, w+8 share a scheduler and run the same phase sequence: started together they stay in step, fight
+    // for the FMA pipe during the FFTs and leave it idle during the memory phases. A start-up offset spreads the phases.
+    const long long t0 = clock64();
+    const long long wait = static_cast<long long>(p.stagger) * (warp >> 2);
+    while (clock64() - t0 < wait) {
+    }
+  }
   c2* stage = exch + kStageOff;
   c2 v[64];
   const float* xs = frame_base_p(p, f);
-  frame_stage_even_p<kVec2, kFull>(stage, p, xs, lane);
+  uint32_t parity = 0;
+  int dbg_frame = 0;
+  if (kBulk) frame_stage_even_p(stage, &tmap, p, f, lane, bar);
   for (;;) {
+    CA_STAMP(0);
     frame_load_p<1, kVec2, kFull>(v, p, xs, lane);  // odd half: lands while the even half is transformed
-    cp_async_wait_all();
-    __syncwarp();
-    frame_take_even_p(v, stage, win_c, lane);
+    if (kBulk) {
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      CA_STAMP(1);
+      frame_take_even_p(v, stage, win_c, lane);
+    } else {
+      frame_load_p<0, kVec2, kFull>(v, p, xs, lane);
+      frame_window_p<0>(v, win_c, lane);
+    }
     DitP<64, 32, 0>::run(v);
     frame_window_p<1>(v, win_c, lane);
     DitP<64, 32, 32>::run(v);
     __syncwarp();  // every lane has taken its staged samples: the buffer may be overwritten by the transpose
-    frame_spectrum_p(v, p, tab4, tab2, exch, lane, f);
+    CA_STAMP(2);
     const int64_t fn = f + fstep;
     const bool more = fn < p.total_frames;
-    if (more) {
-      xs = frame_base_p(p, fn);
-      frame_stage_even_p<kVec2, kFull>(stage, p, xs, lane);  // in flight during the peak extraction
-    }
+    const float* xs_next = more ? frame_base_p(p, fn) : nullptr;
+    frame_spectrum_p(v, p, tab4, tab2, exch, lane, f, &tmap, (kBulk && more) ? fn : -1, bar, dbg_frame);
+    xs = xs_next;
+    CA_STAMP(7);
+    CA_STAMP(8);
     if (p.peak_count) frame_peaks_p(p, reinterpret_cast<float*>(exch), lane, f);
+    CA_STAMP(9);
+    ++dbg_frame;
     if (!more) break;
     f = fn;
   }
@@ -634,21 +735,92 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
     return CA_OK;
   }
   a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
+  static const int stagger_env = [] {
+    const char* e = getenv("CA_STFT_STAGGER");
+    return e ? atoi(e) : 0;
+  }();
+  a.stagger = stagger_env;
 
   const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
                     (ctx->stft.window % 2 == 0);
   const bool full = ctx->stft.window == kN;
   // 12 warps x 1 CTA per SM: 12 x 16.5 KB exchange buffers + 16 KB window + tables = 224 KB of shared memory, 168 registers
-  constexpr int PW = 12;
-  void (*kern)(StftArgs) = vec2 ? (full ? stft4096p_kernel<PW, 1, true, true> : stft4096p_kernel<PW, 1, true, false>)
-                                : (full ? stft4096p_kernel<PW, 1, false, true> : stft4096p_kernel<PW, 1, false, false>);
-  const size_t smem = sizeof(float4) * kTab4Rows * 32 + sizeof(float2) * (32 + kM + PW * kExchFloat2);
+  static const int warps_env = [] {
+    const char* e = getenv("CA_STFT_WARPS");  // tuning experiments: 11 (184 registers, no spills) or 12
+    return e ? atoi(e) : 12;
+  }();
+  // staged path: window 4096, hop a multiple of 128 samples, 16-byte aligned streams (see frame_stage_even_p)
+  bool bulk = full && ctx->stft.hop % 128 == 0 && stream_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d_x) % 16 == 0 &&
+              n_samples / 128 < (1ll << 31);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (bulk) {
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+          qres != cudaDriverEntryPointSuccess)
+        fn = nullptr;
+      return reinterpret_cast<EncodeFn>(fn);
+    }();
+    const cuuint64_t gdim[3] = {128, static_cast<cuuint64_t>(n_samples / 128), static_cast<cuuint64_t>(n_streams)};
+    const cuuint64_t gstride[2] = {512, static_cast<cuuint64_t>(stream_stride) * sizeof(float)};
+    const cuuint32_t box[3] = {64, 32, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    if (!encode || encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_x), gdim, gstride, box, estride,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      bulk = false;  // no tensor map: every lane loads its samples itself
+  }
+  int PW = 12;
+  void (*kern)(StftArgs, CUtensorMap) =
+      bulk   ? stft4096p_kernel<12, 1, true, true, true>
+      : vec2 ? (full ? stft4096p_kernel<12, 1, true, true, false> : stft4096p_kernel<12, 1, true, false, false>)
+             : (full ? stft4096p_kernel<12, 1, false, true, false> : stft4096p_kernel<12, 1, false, false, false>);
+  if (bulk && warps_env == 4) {
+    PW = 4;
+    kern = stft4096p_kernel<4, 1, true, true, true>;
+  }
+  const size_t smem = sizeof(float4) * kTab4Rows * 32 + sizeof(float2) * (32 + 32 * kWinStride + PW * kExchFloat2);
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int64_t grid = ctx->sm_count;
   const int64_t need = (total + PW - 1) / PW;
   if (grid > need) grid = need;
-  kern<<<static_cast<unsigned>(grid), PW * 32, smem, stream>>>(a);
+#ifdef CA_STFT_TIMELINE
+  static long long* d_dbg = nullptr;
+  const size_t dbg_n = 2 * 12 * 24 * 12;
+  if (!d_dbg) cudaMalloc(&d_dbg, dbg_n * sizeof(long long));
+  cudaMemset(d_dbg, 0, dbg_n * sizeof(long long));
+  a.dbg = d_dbg;
+#endif
+  kern<<<static_cast<unsigned>(grid), PW * 32, smem, stream>>>(a, tmap);
   CA_CUDA_OK(ctx, cudaGetLastError());
+#ifdef CA_STFT_TIMELINE
+  {
+    std::vector<long long> h(dbg_n);
+    cudaMemcpy(h.data(), d_dbg, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost);
+    const char* names[9] = {"wait_stage", "fft32x2", "last+tw+sts", "lds", "fft32x2", "col0", "untangle+st", "stage_issue", "peaks"};
+    for (int w = 0; w < 2 * PW; w += 1) {
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      int n = 0;
+      double period = 0;
+      for (int fr = 4; fr < 20; ++fr) {
+        const long long* t = &h[(static_cast<size_t>(w) * 24 + fr) * 12];
+        if (!t[9]) continue;
+        for (int i = 0; i < 9; ++i) acc[i] += static_cast<double>(t[i + 1] - t[i]);
+        period += static_cast<double>(h[(static_cast<size_t>(w) * 24 + fr + 1) * 12] - t[0]);
+        ++n;
+      }
+      if (!n) continue;
+      fprintf(stderr, "timeline cta %d warp %2d:", w / PW, w % PW);
+      for (int i = 0; i < 9; ++i) fprintf(stderr, " %s %.0f", names[i], acc[i] / n);
+      fprintf(stderr, " | frame period %.0f\n", period / n);
+    }
+  }
+#endif
   ctx->launches += 1;
   return CA_OK;
 }
