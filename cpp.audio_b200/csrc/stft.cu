@@ -195,23 +195,31 @@ __device__ __forceinline__ void build_tables_p(float4* tab4, float2* tab2, float
   }
 }
 
-template <int J>
-__device__ __forceinline__ c2 tw_apply_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8]) {
-  constexpr int a = J >> 3, b = J & 7;
-  c2 y = v[J];
-  if constexpr (b != 0) y = cmul_tw(y, wb[b]);
-  if constexpr (a != 0) y = cmul_tw(y, wa[a]);
-  return y;
+// inter-stage twiddle W_2048^(lane*k1), k1 = 8a + b, as wb[b] then wa[a]. One table twiddle is live at a time (3
+// registers) while it sweeps its 8 elements: with all 14 resident the kernel spilled its bookkeeping registers.
+template <int B, int... A>
+__device__ __forceinline__ void tw_b_p(c2 (&v)[64], const float4* __restrict__ tab4, int lane, std::integer_sequence<int, A...>) {
+  const TwP w = make_twp(tab4[(B - 1) * 32 + lane]);
+  ((v[8 * A + B] = cmul_tw(v[8 * A + B], w)), ...);
 }
-template <int M>
-__device__ __forceinline__ void tw_store_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane) {
-  const c2 y0 = tw_apply_p<2 * M>(v, wa, wb), y1 = tw_apply_p<2 * M + 1>(v, wa, wb);  // (column 0 is not read back)
-  *reinterpret_cast<ulonglong2*>(exch + M * kExchStride + 2 * lane) = make_ulonglong2(y0, y1);
+template <int A, int... B>
+__device__ __forceinline__ void tw_a_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane,
+                                       std::integer_sequence<int, B...>) {
+  if constexpr (A != 0) {
+    const TwP w = make_twp(tab4[(6 + A) * 32 + lane]);
+    ((v[8 * A + B] = cmul_tw(v[8 * A + B], w)), ...);
+  }
+  // 128-bit stores of (k1, k1+1) pairs (column 0 is stored but never read back)
+  ((B % 2 == 0 ? (void)(*reinterpret_cast<ulonglong2*>(exch + ((8 * A + B) >> 1) * kExchStride + 2 * lane) =
+                            make_ulonglong2(v[8 * A + B], v[8 * A + B + (B % 2 == 0 ? 1 : 0)]))
+               : (void)0),
+   ...);
 }
-template <int... M>
-__device__ __forceinline__ void tw_store_all_p(const c2 (&v)[64], const TwP (&wa)[8], const TwP (&wb)[8], c2* exch, int lane,
-                                               std::integer_sequence<int, M...>) {
-  (tw_store_p<M>(v, wa, wb, exch, lane), ...);
+template <int... I>
+__device__ __forceinline__ void tw_store_all_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane,
+                                               std::integer_sequence<int, I...>) {
+  ((I != 0 ? tw_b_p<(I != 0 ? I : 1)>(v, tab4, lane, std::make_integer_sequence<int, 8>{}) : (void)0), ...);
+  (tw_a_p<I>(v, tab4, exch, lane, std::make_integer_sequence<int, 8>{}), ...);
 }
 
 // untangle bins k = colA + 64*K2 and 2048-k = colB + 64*(31-K2) and store them at once (HBM row and/or the warp's padded
@@ -274,16 +282,7 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
   // ---- stage 1: last stage of the 64-point FFT over n1 (the two 32-point halves are done by the caller) ----
   DitP<64, 64, 0>::stage(v, std::make_integer_sequence<int, 32>{});
   c2 u = v[0];  // column k1 = 0 (no twiddle), one value per lane
-  {
-    TwP wa[8], wb[8];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      wb[i] = make_twp(tab4[(i - 1) * 32 + lane]);
-      wa[i] = make_twp(tab4[(6 + i) * 32 + lane]);
-    }
-    wa[0] = wb[0] = TwP{1.f, pk(0.f, 0.f)};
-    tw_store_all_p(v, wa, wb, exch, lane, std::make_integer_sequence<int, 32>{});
-  }
+  tw_store_all_p(v, tab4, exch, lane, std::make_integer_sequence<int, 8>{});
   CA_STAMP(3);
   // ---- stage 2: columns colA, colB of the transposed data ----
   c2 A[32], B[32];
