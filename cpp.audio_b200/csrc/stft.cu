@@ -195,31 +195,33 @@ __device__ __forceinline__ void build_tables_p(float4* tab4, float2* tab2, float
   }
 }
 
-// inter-stage twiddle W_2048^(lane*k1), k1 = 8a + b, as wb[b] then wa[a]. One table twiddle is live at a time (3
-// registers) while it sweeps its 8 elements: with all 14 resident the kernel spilled its bookkeeping registers.
-template <int B, int... A>
-__device__ __forceinline__ void tw_b_p(c2 (&v)[64], const float4* __restrict__ tab4, int lane, std::integer_sequence<int, A...>) {
-  const TwP w = make_twp(tab4[(B - 1) * 32 + lane]);
-  ((v[8 * A + B] = cmul_tw(v[8 * A + B], w)), ...);
+// inter-stage twiddle W_2048^(lane*k1), k1 = 8a + b, as wb[b] then wa[a]. Two table twiddles are live at a time (the one
+// sweeping its 8 elements and the next one, already requested): with all 14 resident the kernel spilled its bookkeeping
+// registers, with one the shared-memory latency of each load was exposed (14 x ~35 clocks per frame).
+// Table rows: 0..6 wb[1..7], 7..13 wa[1..7].
+template <int R, int... E>
+__device__ __forceinline__ void tw_row_p(c2 (&v)[64], const TwP& w, std::integer_sequence<int, E...>) {
+  if constexpr (R < 7) ((v[8 * E + R + 1] = cmul_tw(v[8 * E + R + 1], w)), ...);  // wb[R+1]: elements 8a + b, all a
+  else ((v[8 * (R - 6) + E] = cmul_tw(v[8 * (R - 6) + E], w)), ...);              // wa[R-6]: elements 8a + b, all b
 }
-template <int A, int... B>
-__device__ __forceinline__ void tw_a_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane,
-                                       std::integer_sequence<int, B...>) {
-  if constexpr (A != 0) {
-    const TwP w = make_twp(tab4[(6 + A) * 32 + lane]);
-    ((v[8 * A + B] = cmul_tw(v[8 * A + B], w)), ...);
-  }
+template <int A>
+__device__ __forceinline__ void tw_store8_p(const c2 (&v)[64], c2* exch, int lane) {
   // 128-bit stores of (k1, k1+1) pairs (column 0 is stored but never read back)
-  ((B % 2 == 0 ? (void)(*reinterpret_cast<ulonglong2*>(exch + ((8 * A + B) >> 1) * kExchStride + 2 * lane) =
-                            make_ulonglong2(v[8 * A + B], v[8 * A + B + (B % 2 == 0 ? 1 : 0)]))
-               : (void)0),
-   ...);
+#pragma unroll
+  for (int b = 0; b < 8; b += 2)
+    *reinterpret_cast<ulonglong2*>(exch + ((8 * A + b) >> 1) * kExchStride + 2 * lane) = make_ulonglong2(v[8 * A + b], v[8 * A + b + 1]);
 }
-template <int... I>
-__device__ __forceinline__ void tw_store_all_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane,
-                                               std::integer_sequence<int, I...>) {
-  ((I != 0 ? tw_b_p<(I != 0 ? I : 1)>(v, tab4, lane, std::make_integer_sequence<int, 8>{}) : (void)0), ...);
-  (tw_a_p<I>(v, tab4, exch, lane, std::make_integer_sequence<int, 8>{}), ...);
+template <int R>
+__device__ __forceinline__ void tw_chain_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane, const TwP& w) {
+  TwP wn = w;
+  if constexpr (R + 1 < 14) wn = make_twp(tab4[(R + 1) * 32 + lane]);  // requested before the current one is applied
+  tw_row_p<R>(v, w, std::make_integer_sequence<int, 8>{});
+  if constexpr (R == 6) tw_store8_p<0>(v, exch, lane);  // row a = 0 is complete once every wb has been applied
+  if constexpr (R >= 7) tw_store8_p<R - 6>(v, exch, lane);
+  if constexpr (R + 1 < 14) tw_chain_p<R + 1>(v, tab4, exch, lane, wn);
+}
+__device__ __forceinline__ void tw_store_all_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane) {
+  tw_chain_p<0>(v, tab4, exch, lane, make_twp(tab4[lane]));
 }
 
 // untangle bins k = colA + 64*K2 and 2048-k = colB + 64*(31-K2) and store them at once (HBM row and/or the warp's padded
@@ -282,7 +284,7 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
   // ---- stage 1: last stage of the 64-point FFT over n1 (the two 32-point halves are done by the caller) ----
   DitP<64, 64, 0>::stage(v, std::make_integer_sequence<int, 32>{});
   c2 u = v[0];  // column k1 = 0 (no twiddle), one value per lane
-  tw_store_all_p(v, tab4, exch, lane, std::make_integer_sequence<int, 8>{});
+  tw_store_all_p(v, tab4, exch, lane);
   CA_STAMP(3);
   // ---- stage 2: columns colA, colB of the transposed data ----
   c2 A[32], B[32];
