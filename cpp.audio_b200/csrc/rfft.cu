@@ -307,9 +307,9 @@ int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float
   int rc = ensure_twiddles(ctx, n_fft, stream);
   if (rc) return rc;
   switch (n_fft) {
-    case 1024: return launch_smem<512, 64, 4>(ctx, d_in, batch, d_out, stream);
-    case 2048: return launch_smem<1024, 128, 2>(ctx, d_in, batch, d_out, stream);
-    case 4096: return launch_smem<2048, 256, 1>(ctx, d_in, batch, d_out, stream);
+    case 1024:
+    case 2048:
+    case 4096: return rfft_warp(ctx, d_in, n_fft, batch, d_out, stream);  // one warp per frame (rfftw.cu)
     case 8192: return launch_smem<4096, 512, 1>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_smem<8192, 512, 1>(ctx, d_in, batch, d_out, stream);
     case 32768: return launch_smem<16384, 1024, 1>(ctx, d_in, batch, d_out, stream);
