@@ -180,6 +180,293 @@ int launch_warp(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cud
   return CA_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// N = 8192 / 16384 / 32768: one CTA per frame, M = N/2 = M1 x 1024 complex points (M1 = 4, 8, 16), n = 1024*n1 + n2,
+// k = k1 + M1*k2. The whole frame stays in shared memory between its single read and its single write of HBM:
+//   step A  every thread takes columns n2, transforms their M1 points (strided, coalesced loads) in registers and
+//           multiplies by W_M^(n2*k1) (powers of one table entry),
+//   step B  warp k1 runs the 1024-point warp-level FFT (32 x 32, as above) on row k1, in place,
+//   step C  untangling with k = t + T*i: coalesced stores, -i W_N^k = (per-thread table entry) * (immediate).
+// Rows are kRowC2 apart so that the row FFT's exchange layout fits and step C reads M1 rows without bank conflicts.
+// ---------------------------------------------------------------------------------------------------------------
+template <int M1>
+struct CtaFftCfg {
+  static constexpr int M2 = 1024;
+  static constexpr int M = M1 * M2;
+  static constexpr int T = 32 * M1;  // one warp per row
+  static constexpr int kRowC2 = 16 * kXStride + (M1 == 4 ? 4 : 2);
+  static constexpr int kRows = 7 + 3;  // row-FFT tables: wb[1..7], wa[1..3]
+};
+
+template <int K, int M1>
+__device__ __forceinline__ c2 cpow_p(const c2 (&w)[M1]) {  // w[K] = w[K/2] * w[K - K/2] (w[1] given): depth <= log2(M1)
+  const float2 a = upk(w[K / 2]);
+  return cmul_tw(w[K - K / 2], TwP{a.x, pk(-a.y, a.y)});
+}
+template <int M1, int... K>
+__device__ __forceinline__ void cpow_all(c2 (&w)[M1], std::integer_sequence<int, K...>) {
+  ((w[K + 2] = cpow_p<K + 2, M1>(w)), ...);
+}
+
+template <int I, int M1>
+__device__ __forceinline__ void cta_untangle(const c2* __restrict__ Zs, float2* __restrict__ o, const TwP& wpb, int t) {
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M;
+  const int k = t + C::T * I;
+  const int m = (M - k) & (M - 1);
+  const c2 zk = Zs[(k % M1) * C::kRowC2 + k / M1], zm = Zs[(m % M1) * C::kRowC2 + m / M1];
+  const c2 E = add2(zk, cconj(zm));
+  c2 D = csub(zk, cconj(zm));
+  if constexpr (I != 0) D = cmul_imm<Tw<2 * M, C::T * I>>(D);  // W_N^(T i)
+  const c2 Tt = cmul_tw(D, wpb);                                // wpb = 0.5 * (-i) * W_N^t
+  o[k] = upk(fma2(bc(0.5f), E, Tt));
+  o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
+}
+template <int M1, int... I>
+__device__ __forceinline__ void cta_untangle_all(const c2* Zs, float2* o, const TwP& wpb, int t, std::integer_sequence<int, I...>) {
+  (cta_untangle<I, M1>(Zs, o, wpb, t), ...);
+}
+
+// kComplexOut: the rows are complex and stay complex (M c2 in, M c2 out in natural order, no untangling): the row pass of
+// the three-pass path for N >= 65536, in place.
+template <int M1, bool kComplexOut>
+__global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* in, float2* out, const int64_t batch) {  // (may alias: complex mode is in place)
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M, M2 = C::M2, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);          // [kRows][32] row-FFT twiddles W_1024^(l*b), W_1024^(l*8a)
+  c2* Ys = reinterpret_cast<c2*>(tab4 + C::kRows * 32);        // [M1][kRowC2]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < C::kRows * 32; i += T) {
+    const int r = i >> 5, l = i & 31;
+    const float2 w = r < 7 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / M2) : cis_neg_w(2.f * static_cast<float>(l * 8 * (r - 6)) / M2);
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  TwP wpb;
+  {
+    float s, c;
+    sincospif(static_cast<float>(t) / M, &s, &c);  // W_N^t
+    wpb = TwP{-0.5f * s, pk(0.5f * c, -0.5f * c)};  // 0.5 * (-i) * W_N^t = (-s, -c)/2 in the (wr, (-wi, wi)) form
+  }
+  for (int64_t frame = blockIdx.x; frame < batch; frame += gridDim.x) {
+    const float* x = in + frame * (2 * M);
+    __syncthreads();  // tables ready / previous frame's step C done
+    // ---- step A: columns ----
+#pragma unroll
+    for (int j = 0; j < M2 / T; ++j) {
+      const int c = t + T * j;
+      c2 v[M1];
+#pragma unroll
+      for (int n1 = 0; n1 < M1; ++n1) v[bitrev(n1, ilog2(M1))] = *reinterpret_cast<const c2*>(x + 2 * (n1 * M2 + c));
+      DitP<M1, M1, 0>::run(v);
+      c2 w[M1];
+      {
+        float s, cs;
+        sincospif(2.f * static_cast<float>(c) / M, &s, &cs);  // W_M^c
+        w[1] = pk(cs, -s);
+      }
+      cpow_all<M1>(w, std::make_integer_sequence<int, M1 - 2>{});
+#pragma unroll
+      for (int k1 = 1; k1 < M1; ++k1) {
+        const float2 a = upk(w[k1]);
+        v[k1] = cmul_tw(v[k1], TwP{a.x, pk(-a.y, a.y)});
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < M1; ++k1) Ys[k1 * C::kRowC2 + c] = v[k1];
+    }
+    __syncthreads();
+    // ---- step B: warp k1 transforms row k1 (1024 points = 32 x 32), in place ----
+    {
+      c2* row = Ys + warp * C::kRowC2;
+      c2 v[32];
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = row[32 * n1 + lane];
+      __syncwarp();
+      DitP<32, 32, 0>::run(v);
+      tww_chain<32, 0>(v, tab4, lane, make_twp(tab4[lane]));
+#pragma unroll
+      for (int m = 0; m < 16; ++m) *reinterpret_cast<ulonglong2*>(row + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+      __syncwarp();
+      c2 A[32];
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) A[bitrev(n2, 5)] = row[(lane >> 1) * kXStride + 2 * n2 + (lane & 1)];
+      __syncwarp();
+      DitP<32, 32, 0>::run(A);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = A[k2];  // Z[k1 + M1*(lane + 32*k2')] at position k2 = lane + 32*k2'
+    }
+    __syncthreads();
+    if constexpr (kComplexOut) {
+      float2* o = out + frame * M;
+#pragma unroll 8
+      for (int k = t; k < M; k += T) o[k] = upk(Ys[(k % M1) * C::kRowC2 + k / M1]);
+    } else {
+      // ---- step C: untangle, k = t + T*i ----
+      float2* o = out + frame * (M + 1);
+      cta_untangle_all<M1>(Ys, o, wpb, t, std::make_integer_sequence<int, M / (2 * T)>{});
+      if (t == 0) {
+        const float2 z = upk(Ys[((M / 2) % M1) * C::kRowC2 + (M / 2) / M1]);
+        o[M / 2] = make_float2(z.x, -z.y);
+      }
+    }
+  }
+}
+
+template <int M1>
+int launch_cta(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
+  using C = CtaFftCfg<M1>;
+  auto kern = rfft_cta_kernel<M1, false>;
+  const size_t smem = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kRowC2 * M1;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, batch);
+  kern<<<static_cast<unsigned>(grid), C::T, smem, stream>>>(d_in, reinterpret_cast<float2*>(d_out), batch);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// N >= 65536: three passes through HBM, M = N/2 = MA x 8192 complex points, n = 8192*r + c, k = kA + MA*k2.
+//   pass A  one thread per column c: MA-point FFT over r in registers (coalesced strided loads), twiddle W_M^(c*kA),
+//           work[kA][c]                                                                         (streaming, 8M + 8M bytes)
+//   pass B  rfft_cta_kernel<8, complex>: 8192-point row FFTs, in place                          (8M + 8M bytes)
+//   pass C  untangling with the transposition [kA][k2] -> k: a CTA takes 32 consecutive k2 of every row and the
+//           mirrored range, and writes X[k] and X[M-k] as contiguous runs of 32*MA bins          (8M + 8M bytes)
+// 48M bytes moved for 16M algorithmic: the ceiling of this path is a third of the HBM roofline. (A frame that stays
+// on chip across a thread-block cluster is the next step; see DESIGN.md.)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRowLen = 8192;
+
+template <int MA>
+__global__ void __launch_bounds__(256) bigfft_cols_kernel(const float2* __restrict__ zin, float2* __restrict__ work, const int64_t n_frames) {
+  constexpr int M = MA * kRowLen;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t frame = gid / kRowLen;
+  const int c = static_cast<int>(gid - frame * kRowLen);
+  if (frame >= n_frames) return;
+  const c2* src = reinterpret_cast<const c2*>(zin) + frame * M + c;
+  c2 v[MA];
+#pragma unroll
+  for (int r = 0; r < MA; ++r) v[bitrev(r, ilog2(MA))] = __ldg(src + static_cast<int64_t>(r) * kRowLen);
+  DitP<MA, MA, 0>::run(v);
+  // twiddle W_M^(c*k), k = B*a + b: wb[b] = w^b and wa[a] = (w^B)^a by binary powers of w = W_M^c (depth <= 6)
+  constexpr int B = MA < 8 ? MA : 8, A = MA / B;
+  c2 wb[B];
+  {
+    float s, cs;
+    sincospif(static_cast<float>(c) / (M / 2), &s, &cs);  // exact argument: c < 2^13, M/2 a power of two
+    wb[1] = pk(cs, -s);
+  }
+  if constexpr (B > 2) cpow_all<B>(wb, std::make_integer_sequence<int, B - 2>{});
+  c2 wa[A > 1 ? A : 2];
+  if constexpr (A > 1) {
+    const float2 h = upk(wb[B / 2]);
+    wa[1] = cmul_tw(wb[B / 2], TwP{h.x, pk(-h.y, h.y)});  // w^B
+    if constexpr (A > 2) cpow_all<A>(wa, std::make_integer_sequence<int, A - 2>{});
+  }
+  c2* dst = reinterpret_cast<c2*>(work) + frame * M + c;
+#pragma unroll
+  for (int k = 0; k < MA; ++k) {
+    const int a = k / B, b = k % B;
+    c2 y = v[k];
+    if (b) {
+      const float2 q = upk(wb[b]);
+      y = cmul_tw(y, TwP{q.x, pk(-q.y, q.y)});
+    }
+    if (a) {
+      const float2 q = upk(wa[a]);
+      y = cmul_tw(y, TwP{q.x, pk(-q.y, q.y)});
+    }
+    dst[static_cast<int64_t>(k) * kRowLen] = y;
+  }
+}
+
+// pass C. grid (kRowLen/64, frames): CTA b takes k2 in [32b, 32b+32) and the mirrored rows' k2 in [R-32b-32, R-32b].
+template <int MA>
+__global__ void __launch_bounds__(256) bigfft_untangle_kernel(const float2* __restrict__ work, float2* __restrict__ out) {
+  constexpr int R = kRowLen, M = MA * R;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c2* ta = reinterpret_cast<c2*>(smem_raw);  // [MA][33]: Z[kA + MA*(k2_0 + j)]
+  c2* tb = ta + MA * 33;                     // [MA][34]: row kA, k2 = R - k2_0 - 32 + j, j = 0..32
+  const c2* z = reinterpret_cast<const c2*>(work) + static_cast<int64_t>(blockIdx.y) * M;
+  float2* o = out + static_cast<int64_t>(blockIdx.y) * (M + 1);
+  const int k2_0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < MA * 32; i += 256) {
+    const int kA = i >> 5, j = i & 31;
+    ta[kA * 33 + j] = __ldg(z + static_cast<int64_t>(kA) * R + k2_0 + j);
+  }
+  for (int i = threadIdx.x; i < MA * 33; i += 256) {
+    const int kA = i / 33, j = i - kA * 33;
+    const int k2 = (R - k2_0 - 32 + j) & (R - 1);  // j = 32 wraps to 0 for the first CTA
+    tb[kA * 34 + j] = __ldg(z + static_cast<int64_t>(kA) * R + k2);
+  }
+  __syncthreads();
+  // outputs k = kA + MA*k2 for k2 in the range (contiguous: 32*MA bins) and their mirrors M - k
+  for (int i = threadIdx.x; i < MA * 32; i += 256) {
+    const int j = i / MA, kA = i - j * MA;  // kA fastest: consecutive threads write consecutive bins
+    const int k2 = k2_0 + j;
+    const int64_t k = kA + static_cast<int64_t>(MA) * k2;
+    // M - k = (MA - kA) + MA*(R - 1 - k2) for kA > 0, MA*((R - k2) % R) for kA = 0
+    const int mA = kA ? MA - kA : 0;
+    const int mj = kA ? 31 - j : 32 - j;  // index into tb: k2' = R - k2_0 - 32 + mj
+    const c2 zk = ta[kA * 33 + j], zm = tb[mA * 34 + mj];
+    float s, c;
+    sincospif(static_cast<float>(k) / M, &s, &c);  // W_N^k = exp(-i pi k / M); k < 2^24 and M a power of two: exact argument
+    const TwP wp{-0.5f * s, pk(0.5f * c, -0.5f * c)};  // 0.5 * (-i) * W_N^k
+    const c2 E = add2(zk, cconj(zm));
+    const c2 T = cmul_tw(csub(zk, cconj(zm)), wp);
+    o[k] = upk(fma2(bc(0.5f), E, T));
+    o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(T))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // k = M/2 = 0 + MA*(R/2) pairs with itself: X[M/2] = conj(Z[M/2])
+    const float2 zh = upk(__ldg(z + R / 2));
+    o[M / 2] = make_float2(zh.x, -zh.y);
+  }
+}
+
+template <int MA>
+int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
+  constexpr int M = MA * kRowLen;
+  using C = CtaFftCfg<8>;
+  const size_t want = static_cast<size_t>(512) << 20;  // bounded work buffer: frames are processed in groups
+  const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
+  const size_t need = sizeof(float2) * M * static_cast<size_t>(group);
+  if (ctx->fft_work_bytes < need) {
+    if (ctx->d_fft_work) cudaFree(ctx->d_fft_work);
+    ctx->d_fft_work = nullptr;
+    ctx->fft_work_bytes = 0;
+    CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_fft_work, need));
+    ctx->fft_work_bytes = need;
+  }
+  auto rows = rfft_cta_kernel<8, true>;
+  const size_t smem_rows = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kRowC2 * 8;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows, C::T, smem_rows));
+  if (per_sm < 1) per_sm = 1;
+  const size_t smem_unt = sizeof(c2) * MA * (33 + 34);
+  for (int64_t b0 = 0; b0 < batch; b0 += group) {
+    const int64_t nb = std::min(group, batch - b0);
+    const float2* zin = reinterpret_cast<const float2*>(d_in) + b0 * M;
+    float2* out = reinterpret_cast<float2*>(d_out) + b0 * (M + 1);
+    bigfft_cols_kernel<MA><<<static_cast<unsigned>(nb * kRowLen / 256), 256, 0, stream>>>(zin, ctx->d_fft_work, nb);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    const int64_t n_rows = nb * MA;
+    const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, n_rows);
+    rows<<<static_cast<unsigned>(grid), C::T, smem_rows, stream>>>(reinterpret_cast<const float*>(ctx->d_fft_work), ctx->d_fft_work, n_rows);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    bigfft_untangle_kernel<MA><<<dim3(kRowLen / 64, static_cast<unsigned>(nb)), 256, smem_unt, stream>>>(ctx->d_fft_work, out);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 3;
+  }
+  return CA_OK;
+}
+
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
@@ -187,6 +474,14 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 1024: return launch_warp<16, 8>(ctx, d_in, batch, d_out, stream);
     case 2048: return launch_warp<32, 8>(ctx, d_in, batch, d_out, stream);
     case 4096: return launch_warp<64, 12>(ctx, d_in, batch, d_out, stream);
+    case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
+    case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
+    case 32768: return launch_cta<16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 16: return launch_big<4>(ctx, d_in, batch, d_out, stream);
+    case 1 << 17: return launch_big<8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 18: return launch_big<16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 19: return launch_big<32>(ctx, d_in, batch, d_out, stream);
+    case 1 << 20: return launch_big<64>(ctx, d_in, batch, d_out, stream);
     default: break;
   }
   return fail(ctx, CA_ERR_UNSUPPORTED, "rfft_warp: unsupported n_fft");
