@@ -41,6 +41,9 @@ struct ca_ctx {
   // scratch for the *_host entry points
   void* d_scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // pinned host staging of the round trip (peak lists coming down, segments going up)
+  void* h_pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t pinned_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace ca {
@@ -64,6 +67,17 @@ inline int ensure_scratch(ca_ctx* ctx, int slot, size_t bytes) {
   ctx->scratch_bytes[slot] = 0;
   CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_scratch[slot], bytes));
   ctx->scratch_bytes[slot] = bytes;
+  return CA_OK;
+}
+
+inline int ensure_pinned(ca_ctx* ctx, int slot, size_t bytes) {
+  if (ctx->pinned_bytes[slot] >= bytes) return CA_OK;
+  if (ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
+  ctx->h_pinned[slot] = nullptr;
+  ctx->pinned_bytes[slot] = 0;
+  bytes += bytes / 4;  // headroom: the segment count varies from call to call
+  CA_CUDA_OK(ctx, cudaHostAlloc(&ctx->h_pinned[slot], bytes, cudaHostAllocDefault));
+  ctx->pinned_bytes[slot] = bytes;
   return CA_OK;
 }
 

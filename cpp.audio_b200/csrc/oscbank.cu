@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "ctx.hpp"
+#include "packed.cuh"
 
 namespace ca {
 
@@ -298,56 +299,65 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
           base[lane] = make_float2(am * z.x, am * z.y);
         }
         __syncwarp();
-        float y[kNP], d[kNP], kap[kNP];
+        // two partials per register pair: the recurrence and the accumulation run on FFMA2 / FADD2 (packed.cuh), half
+        // the issue slots of the scalar form for the same FP32 work
+        c2 y[kNP / 2], d[kNP / 2], nkap[kNP / 2];
 #pragma unroll
-        for (int p = 0; p < kNP; ++p) {
-          const float2 z = cmul(base[p], E[(p0 + p) * 32 + lane]);
-          const float kp = sp[p0 + p].kappa;
-          kap[p] = kp;
-          y[p] = z.y;
-          d[p] = fmaf(z.x, sp[p0 + p].so, 0.5f * kp * z.y);  // y0 - y(-1) = Im(z * (1 - exp(-i Of)))
+        for (int p = 0; p < kNP; p += 2) {
+          const float2 z0 = cmul(base[p], E[(p0 + p) * 32 + lane]);
+          const float2 z1 = cmul(base[p + 1], E[(p0 + p + 1) * 32 + lane]);
+          const float k0 = sp[p0 + p].kappa, k1 = sp[p0 + p + 1].kappa;
+          nkap[p / 2] = pk(-k0, -k1);
+          y[p / 2] = pk(z0.y, z1.y);
+          // y0 - y(-1) = Im(z * (1 - exp(-i Of)))
+          d[p / 2] = pk(fmaf(z0.x, sp[p0 + p].so, 0.5f * k0 * z0.y), fmaf(z1.x, sp[p0 + p + 1].so, 0.5f * k1 * z1.y));
         }
         __syncwarp();
+        const c2* sgn2 = reinterpret_cast<const c2*>(sgn4) + (p0 >> 1);
 #pragma unroll 1
         for (int k = 0; k < kR; k += 2) {
           // even step: every partial enters with a plus sign
-          float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+          c2 acc0 = y[0], acc1 = y[1], acc2 = y[2], acc3 = y[3];
 #pragma unroll
-          for (int p = 0; p < kNP; p += 4) {
-            acc0 += y[p];
-            acc1 += y[p + 1];
-            acc2 += y[p + 2];
-            acc3 += y[p + 3];
+          for (int p = 4; p < kNP / 2; p += 4) {
+            acc0 = add2(acc0, y[p]);
+            acc1 = add2(acc1, y[p + 1]);
+            acc2 = add2(acc2, y[p + 2]);
+            acc3 = add2(acc3, y[p + 3]);
           }
           {
-            const float s = (acc0 + acc1) + (acc2 + acc3);
+            const float2 t = upk(add2(add2(acc0, acc1), add2(acc2, acc3)));
+            const float s = t.x + t.y;
             if (p0 == 0) outbuf[32 * k + lane] = s;
             else outbuf[32 * k + lane] += s;
           }
 #pragma unroll
-          for (int p = 0; p < kNP; ++p) {
-            d[p] = fmaf(-kap[p], y[p], d[p]);
-            y[p] += d[p];
+          for (int p = 0; p < kNP / 2; ++p) {
+            d[p] = fma2(nkap[p], y[p], d[p]);
+            y[p] = add2(y[p], d[p]);
           }
           // odd step: folded partials enter with a minus sign
-          acc0 = acc1 = acc2 = acc3 = 0.f;
+          acc0 = mul2(sgn2[0], y[0]);
+          acc1 = mul2(sgn2[1], y[1]);
+          acc2 = mul2(sgn2[2], y[2]);
+          acc3 = mul2(sgn2[3], y[3]);
 #pragma unroll
-          for (int p = 0; p < kNP; p += 4) {
-            const float4 sg = sgn4[(p0 + p) >> 2];
-            acc0 = fmaf(sg.x, y[p], acc0);
-            acc1 = fmaf(sg.y, y[p + 1], acc1);
-            acc2 = fmaf(sg.z, y[p + 2], acc2);
-            acc3 = fmaf(sg.w, y[p + 3], acc3);
+          for (int p = 4; p < kNP / 2; p += 4) {
+            acc0 = fma2(sgn2[p], y[p], acc0);
+            acc1 = fma2(sgn2[p + 1], y[p + 1], acc1);
+            acc2 = fma2(sgn2[p + 2], y[p + 2], acc2);
+            acc3 = fma2(sgn2[p + 3], y[p + 3], acc3);
           }
           {
-            const float s = (acc0 + acc1) + (acc2 + acc3);
+            const float2 t = upk(add2(add2(acc0, acc1), add2(acc2, acc3)));
+            const float s = t.x + t.y;
             if (p0 == 0) outbuf[32 * (k + 1) + lane] = s;
             else outbuf[32 * (k + 1) + lane] += s;
           }
 #pragma unroll
-          for (int p = 0; p < kNP; ++p) {
-            d[p] = fmaf(-kap[p], y[p], d[p]);
-            y[p] += d[p];
+          for (int p = 0; p < kNP / 2; ++p) {
+            d[p] = fma2(nkap[p], y[p], d[p]);
+            y[p] = add2(y[p], d[p]);
           }
         }
       }

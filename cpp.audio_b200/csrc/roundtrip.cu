@@ -20,7 +20,13 @@
 // from a hash of the note id instead of the external mersenne<> generator.
 #include <math.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <string.h>
+
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <thread>
 #include <vector>
@@ -221,9 +227,10 @@ double env_pressed_value(const Note& n, int64_t c, float sustain) {
   return sustain;
 }
 
+// peak_stride: entries per frame in the (compacted) peak arrays
 void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, const int32_t* peak_bin,
-                const float* peak_off, const float* peak_db, const int32_t* peak_count, StreamResult& res) {
-  const int W = prm.stft.window, hop = prm.stft.hop, sr = prm.stft.sample_rate, P = prm.stft.max_peaks;
+                const float* peak_off, const float* peak_db, const int32_t* peak_count, int peak_stride, StreamResult& res) {
+  const int W = prm.stft.window, hop = prm.stft.hop, sr = prm.stft.sample_rate, P = peak_stride;
   const int n_fft = ca_fft_length_for(W, 1);
   const double bin_hz = static_cast<double>(sr) / n_fft;
   // AHDSREnvelopeBase::setAHDSR (include/audioelement.h:923-952)
@@ -467,79 +474,127 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   const size_t total = static_cast<size_t>(n_streams) * n_samples;
   if (total == 0) return CA_OK;
   const size_t rows = static_cast<size_t>(frames) * n_streams;
+  static const bool timing = getenv("CA_RT_TIMING") != nullptr;  // stage times on stderr (profiles/time_roundtrip.py)
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "roundtrip: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
 
   // ---- 1. peaks on the GPU (sub-bin offsets instead of Hz so that the host forms k+p in double) ----
-  std::vector<int32_t> pbin(rows * P), pcnt(rows);
-  std::vector<float> poff(rows * P), pdb(rows * P);
+  // The input goes up in one copy, K2 runs on the whole batch, and only the USED part of the peak lists comes back: the
+  // capacity per frame is max_peaks (200 in the reference), a frame of music holds a few dozen. Host-side buffers are
+  // pinned and owned by the context (no page faults, DMA at PCIe speed, no allocation after the first call).
+  cudaStream_t st = ctx->own_stream;
+  const size_t out_bytes = sizeof(float) * 2 * total;
+  rc = ensure_scratch(ctx, 0, sizeof(float) * total);
+  if (!rc) rc = ensure_scratch(ctx, 7, out_bytes);
+  for (int i = 2; i <= 4 && !rc; ++i) rc = ensure_scratch(ctx, i, std::max<size_t>(16, sizeof(float) * rows * P));
+  if (!rc) rc = ensure_scratch(ctx, 5, std::max<size_t>(16, sizeof(int32_t) * rows));
+  if (!rc) rc = ensure_pinned(ctx, 0, std::max<size_t>(16, sizeof(int32_t) * rows));
+  if (rc) return rc;
+  int32_t* h_cnt = static_cast<int32_t*>(ctx->h_pinned[0]);
+  int cmax = 0;
   if (rows) {
+    float* d_x = static_cast<float*>(ctx->d_scratch[0]);
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x, h_x, sizeof(float) * total, cudaMemcpyHostToDevice, st));
     ctx->stft_freq_as_offset = true;
-    rc = ca_stft_analyze_host(ctx, h_x, n_samples, n_streams, n_samples, nullptr, 0, pbin.data(), poff.data(), pdb.data(), pcnt.data());
+    rc = stft_analyze(ctx, d_x, n_samples, n_streams, n_samples, nullptr, 0, static_cast<int32_t*>(ctx->d_scratch[2]),
+                      static_cast<float*>(ctx->d_scratch[3]), static_cast<float*>(ctx->d_scratch[4]),
+                      static_cast<int32_t*>(ctx->d_scratch[5]), st);
     ctx->stft_freq_as_offset = false;
     if (rc) return rc;
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, ctx->d_scratch[5], sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
+    CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    for (size_t r = 0; r < rows; ++r) cmax = std::max(cmax, h_cnt[r]);
+    cmax = std::min(cmax, P);
   }
+  const int PS = std::max(cmax, 1);  // compacted entries per frame
+  for (int i = 1; i <= 3 && !rc; ++i) rc = ensure_pinned(ctx, i, std::max<size_t>(16, sizeof(float) * rows * PS));
+  if (rc) return rc;
+  if (rows && cmax > 0)
+    for (int i = 0; i < 3; ++i)
+      CA_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_pinned[1 + i], sizeof(float) * PS, ctx->d_scratch[2 + i], sizeof(float) * P,
+                                        sizeof(float) * PS, rows, cudaMemcpyDeviceToHost, st));
+  CA_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scratch[7], 0, out_bytes, st));  // samples before the first frame are silent
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  const int32_t* pbin = static_cast<const int32_t*>(ctx->h_pinned[1]);
+  const float* poff = static_cast<const float*>(ctx->h_pinned[2]);
+  const float* pdb = static_cast<const float*>(ctx->h_pinned[3]);
+  lap("analysis (H2D, K2, D2H peaks)");
 
   // ---- 2. pitch pipeline on host threads, one stream at a time per thread ----
   std::vector<StreamResult> results(n_streams);
-  {
-    int nt = prm.host_threads > 0 ? prm.host_threads : static_cast<int>(std::thread::hardware_concurrency());
-    nt = std::max(1, std::min<int>(nt, static_cast<int>(n_streams)));
+  int nt = prm.host_threads > 0 ? prm.host_threads : static_cast<int>(std::thread::hardware_concurrency());
+  nt = std::max(1, std::min<int>(nt, static_cast<int>(std::max<int64_t>(n_streams, 1))));
+  auto parallel = [&](auto&& body) {
     std::vector<std::thread> pool;
     for (int t = 0; t < nt; ++t)
       pool.emplace_back([&, t] {
-        for (int64_t s = t; s < n_streams; s += nt)
-          run_stream(prm, n_samples, frames, pbin.data() + s * frames * P, poff.data() + s * frames * P, pdb.data() + s * frames * P,
-                     pcnt.data() + s * frames, results[s]);
+        for (int64_t s = t; s < n_streams; s += nt) body(s);
       });
     for (auto& th : pool) th.join();
-  }
+  };
+  parallel([&](int64_t s) {
+    run_stream(prm, n_samples, frames, pbin + s * frames * PS, poff + s * frames * PS, pdb + s * frames * PS, h_cnt + s * frames, PS,
+               results[s]);
+  });
+  lap("pitch pipeline (host)");
 
-  // ---- 3. flatten and render ----
-  size_t n_segs = 0;
-  for (auto& r : results) n_segs += r.segs.size();
+  // ---- 3. flatten (in parallel, into pinned memory) and render ----
   const int64_t n_tiles = frames * n_streams;
-  std::vector<int64_t> tile_begin(n_tiles + 1), tile_s0(std::max<int64_t>(n_tiles, 1));
-  std::vector<int32_t> tile_len(std::max<int64_t>(n_tiles, 1));
-  std::vector<Segment> segs;
-  segs.reserve(n_segs);
-  for (int64_t s = 0; s < n_streams; ++s) {
-    const int64_t base = static_cast<int64_t>(segs.size());
+  std::vector<int64_t> seg_base(n_streams + 1, 0);
+  for (int64_t s = 0; s < n_streams; ++s) seg_base[s + 1] = seg_base[s] + static_cast<int64_t>(results[s].segs.size());
+  const int64_t n_segs = seg_base[n_streams];
+  const size_t b_begin = sizeof(int64_t) * (n_tiles + 1), b_s0 = sizeof(int64_t) * std::max<int64_t>(n_tiles, 1),
+               b_len = sizeof(int32_t) * std::max<int64_t>(n_tiles, 1);
+  rc = ensure_pinned(ctx, 4, std::max<size_t>(16, sizeof(Segment) * n_segs));
+  if (!rc) rc = ensure_pinned(ctx, 5, b_begin + b_s0 + b_len);
+  if (rc) return rc;
+  Segment* h_segs = static_cast<Segment*>(ctx->h_pinned[4]);
+  int64_t* tile_begin = static_cast<int64_t*>(ctx->h_pinned[5]);
+  int64_t* tile_s0 = tile_begin + (n_tiles + 1);
+  int32_t* tile_len = reinterpret_cast<int32_t*>(tile_s0 + std::max<int64_t>(n_tiles, 1));
+  parallel([&](int64_t s) {
+    const int64_t base = seg_base[s];
     for (int64_t k = 0; k < frames; ++k) {
       const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;
       tile_begin[s * frames + k] = base + results[s].tile_seg_begin[k];
       tile_s0[s * frames + k] = s * n_samples + n_k;
       tile_len[s * frames + k] = static_cast<int32_t>(std::max<int64_t>(0, std::min<int64_t>(hop, n_samples - n_k)));
     }
-    segs.insert(segs.end(), results[s].segs.begin(), results[s].segs.end());
+    if (!results[s].segs.empty()) memcpy(h_segs + base, results[s].segs.data(), sizeof(Segment) * results[s].segs.size());
     if (h_stats) {
       h_stats[2 * s] = results[s].notes_started;
       h_stats[2 * s + 1] = results[s].notes_dropped;
     }
-  }
-  tile_begin[n_tiles] = static_cast<int64_t>(segs.size());
+  });
+  tile_begin[n_tiles] = n_segs;
+  lap("flatten segments");
 
-  const size_t out_bytes = sizeof(float) * 2 * total;
-  rc = ensure_scratch(ctx, 7, out_bytes);
-  if (!rc) rc = ensure_scratch(ctx, 6, std::max<size_t>(16, sizeof(Segment) * segs.size()));
-  if (!rc) rc = ensure_scratch(ctx, 1, sizeof(int64_t) * (n_tiles + 1));
-  if (!rc) rc = ensure_scratch(ctx, 2, std::max<size_t>(16, sizeof(int64_t) * n_tiles));
-  if (!rc) rc = ensure_scratch(ctx, 3, std::max<size_t>(16, sizeof(int32_t) * n_tiles));
+  rc = ensure_scratch(ctx, 6, std::max<size_t>(16, sizeof(Segment) * n_segs));
+  if (!rc) rc = ensure_scratch(ctx, 1, b_begin + b_s0 + b_len);
   if (rc) return rc;
-  cudaStream_t st = ctx->own_stream;
-  CA_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scratch[7], 0, out_bytes, st));  // samples before the first frame are silent
-  if (n_tiles > 0 && !segs.empty()) {
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[6], segs.data(), sizeof(Segment) * segs.size(), cudaMemcpyHostToDevice, st));
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[1], tile_begin.data(), sizeof(int64_t) * (n_tiles + 1), cudaMemcpyHostToDevice, st));
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[2], tile_s0.data(), sizeof(int64_t) * n_tiles, cudaMemcpyHostToDevice, st));
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[3], tile_len.data(), sizeof(int32_t) * n_tiles, cudaMemcpyHostToDevice, st));
-    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), static_cast<const int64_t*>(ctx->d_scratch[1]),
-                static_cast<const int64_t*>(ctx->d_scratch[2]), static_cast<const int32_t*>(ctx->d_scratch[3]), n_tiles,
-                static_cast<float*>(ctx->d_scratch[7])};
+  if (n_tiles > 0 && n_segs > 0) {
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[6], h_segs, sizeof(Segment) * n_segs, cudaMemcpyHostToDevice, st));
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_scratch[1], tile_begin, b_begin + b_s0 + b_len, cudaMemcpyHostToDevice, st));
+    const int64_t* d_begin = static_cast<const int64_t*>(ctx->d_scratch[1]);
+    const int64_t* d_s0 = d_begin + (n_tiles + 1);
+    const int32_t* d_len = reinterpret_cast<const int32_t*>(d_s0 + std::max<int64_t>(n_tiles, 1));
+    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin, d_s0, d_len, n_tiles, static_cast<float*>(ctx->d_scratch[7])};
     tracks_kernel<<<static_cast<unsigned>((n_tiles + 3) / 4), 128, 0, st>>>(ta);
     CA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
   }
+  if (timing) {
+    CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    lap("H2D segments + tracks kernel");
+  }
   CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], out_bytes, cudaMemcpyDeviceToHost, st));
   CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  lap("D2H output");
   return CA_OK;
 }
 
