@@ -11,6 +11,7 @@ from ._capi import (  # noqa: F401
     CaError,
     Context,
     OscBankDesc,
+    RampDesc,
     RoundtripParams,
     StftParams,
     fft_length_for,
@@ -21,6 +22,6 @@ from ._capi import (  # noqa: F401
     DECLARED_SYMBOLS,
 )
 from .analysis import SqMagAnalyzer, analyze_streams, rfft_batched  # noqa: F401
-from .synth import SineBank, render_bank  # noqa: F401
+from .synth import SineBank, render_bank, render_ramps  # noqa: F401
 from .roundtrip import pinned_empty, resynth_roundtrip  # noqa: F401
 from .sharding import frame_shard, gather_rows, reduce_bus, shard_range  # noqa: F401

@@ -11,7 +11,7 @@ DECLARED_SYMBOLS = [
     "ca_version", "ca_init", "ca_destroy", "ca_last_error", "ca_sm_count", "ca_kernel_launches", "ca_host_alloc",
     "ca_host_free", "ca_rfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
-    "ca_measure_fp32_peak", "ca_resynth_roundtrip_host",
+    "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host",
 ]
 
 
@@ -33,6 +33,13 @@ class RoundtripParams(C.Structure):
     _fields_ = [("stft", StftParams), ("nearby_distance_tones", C.c_float), ("min_volume", C.c_float),
                 ("max_track_pitches", C.c_float), ("gain", C.c_float), ("stereo_spread", C.c_float), ("env", Ahdsr),
                 ("max_channels", C.c_int32), ("host_threads", C.c_int32)]
+
+
+class RampDesc(C.Structure):
+    _fields_ = [("n_voices", C.c_int64), ("n_samples", C.c_int64), ("sample_rate", C.c_int32), ("mix", C.c_int32),
+                ("from_hz", C.c_void_p), ("to_hz", C.c_void_p), ("duration", C.c_void_p), ("start_sample", C.c_void_p),
+                ("volume", C.c_void_p), ("start_angle", C.c_void_p), ("key_delay", C.c_void_p), ("release_at", C.c_void_p),
+                ("env", Ahdsr)]
 
 
 class OscBankDesc(C.Structure):
@@ -84,6 +91,7 @@ def lib():
     L.ca_oscbank_render_host.argtypes = [p, C.POINTER(OscBankDesc), p]
     L.ca_measure_fp32_peak.argtypes = [p, C.POINTER(C.c_double)]
     L.ca_resynth_roundtrip_host.argtypes = [p, C.POINTER(RoundtripParams), p, i64, i64, p, p]
+    L.ca_ramp_render_host.argtypes = [p, C.POINTER(RampDesc), p]
     _lib = L
     return L
 

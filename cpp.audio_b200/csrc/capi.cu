@@ -274,6 +274,11 @@ int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, co
   return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
 }
 
+int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out) {
+  if (!ctx) return CA_ERR_INVALID;
+  return ramp_render_host(ctx, desc, h_out);
+}
+
 int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops) {
   if (!ctx) return CA_ERR_INVALID;
   return measure_fp32_peak(ctx, tflops);

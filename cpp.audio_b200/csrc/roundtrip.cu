@@ -33,113 +33,12 @@
 
 #include "common.cuh"
 #include "ctx.hpp"
+#include "tracks.cuh"
 
 namespace ca {
 
 namespace {
 
-struct __align__(8) Segment {
-  double phase_start;  // oscillator angle (units of pi rad, [0,2)) before the first step of the tile
-  double from, to;     // glide end points (angle increments)
-  double K, L;         // f_i = from + K*(exp(i*L) - 1) for glide steps i < m, f_i = to afterwards
-  double c1;           // K / lambda:  P_i = sum_{l<=i} f_l = (i+1)*(from-K) + c1*(exp((i+1)*L) - 1)
-  double P_before;     // P_{i0-1} (0 when i0 == 0)
-  double P_m1;         // P_{m-1}
-  int32_t i0;          // glide step index of the tile's first sample
-  int32_t m;           // first clamped glide step; 0 = steady at `to`
-  float vol_x, vol_dy; // volume = x + dy*exp(-pi*Mv)
-  float cap;           // max filter increment (2/stride)
-  int32_t regime;      // 0: Mv = cap*(j+1); 1: Mv = P-sum since tile start; 2: f-limited until istar then cap; 3: cap then f
-  int32_t istar;       // tile-relative index where a mixed regime switches
-  float m_star;        // Mv accumulated over [0, istar)
-  int32_t c0;          // envelope step counter at the tile's first sample
-  int32_t attack, hold, decay, release;
-  float sustain;
-  int32_t rel_base;    // tile-relative index of the first release step (may be negative); INT_MAX = not released
-  float top;           // envelope value when the release started
-  float gl, gr;
-};
-
-struct TileArgs {
-  const Segment* segs;
-  const int64_t* tile_seg_begin;  // [tiles+1] CSR into segs
-  const int64_t* tile_sample0;    // [tiles] first output sample (absolute index into out / 2)
-  const int32_t* tile_len;        // [tiles]
-  int64_t n_tiles;
-  float* out;                     // interleaved stereo
-};
-
-__device__ __forceinline__ float alias_gain(float ai) {  // freqAliasingMultiplicator, include/audioelement.h:466-483
-  if (ai == 0.f) return 1.f;
-  const float h = 1.f / ai;
-  if (h < 1.f) return 0.f;
-  if (h > 4.f) return 1.f;
-  return (h - 1.f) * (1.f / 3.f);
-}
-
-constexpr int kMaxTile = 1024;  // samples per tile (hop); 32 steps of 32 lanes
-
-__global__ void __launch_bounds__(128) tracks_kernel(const __grid_constant__ TileArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
-  if (tile >= a.n_tiles) return;
-  const int len = a.tile_len[tile];
-  const int64_t s_begin = a.tile_seg_begin[tile], s_end = a.tile_seg_begin[tile + 1];
-  float2* out = reinterpret_cast<float2*>(a.out) + a.tile_sample0[tile];
-  for (int j0 = 0; j0 < len; j0 += 32) {
-    const int j = j0 + lane;  // tile-relative sample index
-    float accl = 0.f, accr = 0.f;
-    for (int64_t si = s_begin; si < s_end; ++si) {
-      const Segment& g = a.segs[si];
-      // ---- frequency glide and phase (FP64) ----
-      const int i = g.i0 + j;  // glide step index
-      double f, P;             // emitted increment at this step, sum of increments over glide steps 0..i
-      if (i < g.m) {
-        // expm1, not exp()-1: when `to` is within 1e-10 of `from`, c1 = K/lambda is ~1e14 and the rounding of exp()-1
-        // (1e-16) would reach the phase
-        P = static_cast<double>(i + 1) * (g.from - g.K) + g.c1 * expm1(g.L * static_cast<double>(i + 1));
-        f = g.from + g.K * expm1(g.L * static_cast<double>(i));
-      } else {
-        P = g.P_m1 + static_cast<double>(i - g.m + 1) * g.to;
-        f = g.to;
-      }
-      const double adv = P - g.P_before;  // phase advance since the tile start, this step included
-      double ph = g.phase_start + adv;
-      ph -= 2.0 * floor(0.5 * ph);
-      const float s = sinpif(static_cast<float>(ph));
-      const float ff = static_cast<float>(f);
-      // ---- volume low-pass (SPEC S8): y = x + dy * exp(-pi * sum of min(cap, f)) ----
-      float mv;
-      if (g.regime == 0) mv = g.cap * static_cast<float>(j + 1);
-      else if (g.regime == 1) mv = static_cast<float>(adv);
-      else if (g.regime == 2) {  // f-limited first, cap from istar on
-        if (j < g.istar) mv = static_cast<float>(adv);
-        else mv = g.m_star + g.cap * static_cast<float>(j - g.istar + 1);
-      } else {  // cap first, f-limited from istar on: m_star holds cap*istar - (advance before istar)
-        if (j < g.istar) mv = g.cap * static_cast<float>(j + 1);
-        else mv = g.m_star + static_cast<float>(adv);
-      }
-      const float vol = g.vol_x + g.vol_dy * __expf(-3.14159265358979f * mv);
-      // ---- envelope (include/audioelement.h:960-1000, :733-742) ----
-      float env;
-      if (j >= g.rel_base) {
-        const int jr = j - g.rel_base + 1;
-        env = jr >= g.release ? 0.f : g.top - g.top * (static_cast<float>(jr) / static_cast<float>(g.release));
-      } else {
-        int c = g.c0 + j;
-        if (c < 1) env = 0.f;
-        else if (c <= g.attack) env = static_cast<float>(c) / static_cast<float>(g.attack);
-        else if ((c -= g.attack) <= g.hold) env = 1.f;
-        else if ((c -= g.hold) <= g.decay) env = 1.f + (g.sustain - 1.f) * (static_cast<float>(c) / static_cast<float>(g.decay));
-        else env = g.sustain;
-      }
-      const float y = vol * (alias_gain(ff) * s * env);
-      accl = fmaf(g.gl, y, accl);
-      accr = fmaf(g.gr, y, accr);
-    }
-    if (j < len) out[j] = make_float2(accl, accr);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Host side: pitch pipeline + note bookkeeping of one stream -> segments
@@ -152,42 +51,6 @@ inline float hash_unit(uint64_t id, uint64_t salt) {  // SPEC S10
   z ^= z >> 31;
   return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
 }
-
-struct Glide {  // InterpolatedFreq in closed form
-  double from = 0, to = 0, K = 0, L = 0, c1 = 0, P_m1 = 0;
-  int32_t m = 0;   // first clamped step
-  int64_t i = 0;   // next glide step index
-  void start(double from_, double to_, double dur) {
-    from = from_;
-    to = to_;
-    i = 0;
-    if (to == from) {  // C = 1: the first step emits `to`, after which the steady-state shortcut holds (:2765-2767)
-      m = 0;
-      K = L = c1 = P_m1 = 0;
-      return;
-    }
-    const double delta = to - from;
-    const double C = -log(from / to) / delta;            // :2815
-    const double lambda = C * delta / dur;               // cur' = (1+lambda)*cur + beta
-    const double beta = C * (from + 0.5 * delta / dur);  // :2783-2784
-    K = delta * beta / (dur * lambda);
-    L = log1p(lambda);
-    c1 = K / lambda;
-    // first step whose cur + .5 exceeds dur (:2768-2770): cur_i = beta*(alpha^i - 1)/lambda
-    const double x = log1p(lambda * (dur - 0.5) / beta) / L;
-    double mf = floor(x) + 1.0;
-    if (mf < 1.0) mf = 1.0;
-    if (mf > 1e9) mf = 1e9;
-    m = static_cast<int32_t>(mf);
-    P_m1 = P(m - 1);
-  }
-  double f_at(int64_t k) const { return k < m ? from + K * expm1(L * static_cast<double>(k)) : to; }
-  double P(int64_t k) const {  // sum of f over steps 0..k
-    if (k < 0) return 0.0;
-    if (k < m) return static_cast<double>(k + 1) * (from - K) + c1 * expm1(L * static_cast<double>(k + 1));
-    return P_m1 + static_cast<double>(k - m + 1) * to;
-  }
-};
 
 struct Note {
   int64_t id = 0;
@@ -583,8 +446,8 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
     const int64_t* d_begin = static_cast<const int64_t*>(ctx->d_scratch[1]);
     const int64_t* d_s0 = d_begin + (n_tiles + 1);
     const int32_t* d_len = reinterpret_cast<const int32_t*>(d_s0 + std::max<int64_t>(n_tiles, 1));
-    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin, d_s0, d_len, n_tiles, static_cast<float*>(ctx->d_scratch[7])};
-    tracks_kernel<<<static_cast<unsigned>((n_tiles + 3) / 4), 128, 0, st>>>(ta);
+    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin, d_s0, d_len, n_tiles, static_cast<float*>(ctx->d_scratch[7]), 0};
+    tracks_kernel<false><<<static_cast<unsigned>((n_tiles + 3) / 4), 128, 0, st>>>(ta);
     CA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
   }

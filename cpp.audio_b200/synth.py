@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from ._capi import Ahdsr, Context, OscBankDesc, lib
@@ -62,3 +63,24 @@ class SineBank:
 def render_bank(ctx: Context, n_samples: int, f0_hz, volume, partial_volume, partial_phase, env, sample_rate=48000, **kw):
     bank = SineBank(ctx, partial_volume.shape[0], partial_volume.shape[1], sample_rate)
     return bank.render(n_samples, f0_hz, volume, partial_volume, partial_phase, env, **kw)
+
+
+def render_ramps(ctx: Context, from_hz, to_hz, duration, n_samples: int, sample_rate: int = 48000, volume=None, start_sample=None,
+                 start_angle=None, key_delay=None, release_at=None, env: Ahdsr | None = None, mix: int = 0) -> np.ndarray:
+    """gen.voice ramp voices (ca_ramp_render_host): host arrays in, float32 [voices, samples] (mix=0) or [samples] (mix=2) out."""
+    import ctypes as C
+
+    from ._capi import RampDesc, lib
+
+    f = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)
+    from_hz, to_hz, duration = f(from_hz, np.float32), f(to_hz, np.float32), f(duration, np.float32)
+    V = int(from_hz.shape[0])
+    arrs = dict(volume=f(volume, np.float32), start_sample=f(start_sample, np.float32), start_angle=f(start_angle, np.float32),
+                key_delay=f(key_delay, np.int32), release_at=f(release_at, np.int64))
+    q = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    e = env if env is not None else Ahdsr(0, 0, 0, 0, 0, 0, 0, 1.0)
+    d = RampDesc(V, n_samples, sample_rate, mix, q(from_hz), q(to_hz), q(duration), q(arrs["start_sample"]), q(arrs["volume"]),
+                 q(arrs["start_angle"]), q(arrs["key_delay"]), q(arrs["release_at"]), e)
+    out = np.zeros((V, n_samples) if mix == 0 else (n_samples,), dtype=np.float32)
+    ctx.check(lib().ca_ramp_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p)), "ca_ramp_render_host")
+    return out

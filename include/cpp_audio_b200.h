@@ -159,6 +159,30 @@ typedef struct ca_roundtrip_params {
 int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
                               int64_t n_streams, float* h_out, int64_t* h_stats);
 
+/* ---- gen.voice ramp voices ---------------------------------------------------------------------------------------
+ * Stands in for the inner element of voice::Impl_::doProcessing / SoundEngine::step (include/gen.voice.h:1130-1189;
+ * include/soundengine.h:245-257, 412-464): Enveloped<FreqCtrl_<SineOscillatorAlgo, LogRamp>, AHDSREnvelope> with a constant
+ * volume. The oscillator's angle increment follows LogRamp::setup(from, to, duration_in_samples, start_sample, LINEAR)
+ * (include/audioelement.h:2464-2572): it glides from `from` to `to` in about `duration` samples and bounces back, for ever.
+ * A SoundEngine voice (up to three cross-faded ramps) is a sum of such voices with staggered key_delay / release_at.
+ * The equal-loudness volume of the full element (Mix<LoudnessAdjusted<Sine>>) is not applied. Host pointers. */
+typedef struct ca_ramp_desc {
+  int64_t n_voices;
+  int64_t n_samples;
+  int32_t sample_rate;
+  int32_t mix;                /* CA_MIX_NONE: h_out [voices][samples]; CA_MIX_MONO: h_out [samples] = sum of the voices */
+  const float* from_hz;       /* [voices] > 0 */
+  const float* to_hz;         /* [voices] > 0 */
+  const float* duration;      /* [voices] > 0, LogRamp duration_in_samples */
+  const float* start_sample;  /* nullable [voices]: initial ramp position, 0 <= start_sample <= duration */
+  const float* volume;        /* nullable [voices] (1) */
+  const float* start_angle;   /* nullable [voices]: oscillator start angle in units of pi rad */
+  const int32_t* key_delay;   /* nullable [voices]: onKeyPressed(delay) */
+  const int64_t* release_at;  /* nullable [voices]: onKeyReleased(0) just before this sample; < 0: never */
+  ca_ahdsr env;               /* one envelope for all voices; floors of 1 ms and 2.5 periods of `from` apply */
+} ca_ramp_desc;
+int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
+
 /* measured FP32 FMA throughput of this GPU in TFLOP/s (dependent-free FFMA chains, `ms` of work); used as the
  * denominator of the synthesis roofline */
 int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops);

@@ -717,6 +717,63 @@ private:
   double gl_ = 1, gr_ = 1;
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Frequency ramp (LogRamp, include/audioelement.h:2464-2572) and the gen.voice ramp element
+// VolumeAdjusted<Enveloped<FreqCtrl_<Sine, LogRamp>, AHDSR>> (include/soundengine.h:245-257) with a constant volume.
+// The loudness adjustment of the full element (Mix<LoudnessAdjusted<Sine>>, include/loudness.h) is not restated.
+// ------------------------------------------------------------------------------------------------------------
+
+template <class T>
+class LogRamp {
+public:
+  void setup(T from, T to, T duration, T start_sample, int itp) {  // :2491-2520 (start_sample >= 0 branch)
+    cur_ = start_sample;
+    from_ = from; to_ = to; duration_ = duration; itp_ = itp;
+    C_ = (to_ == from_) ? T(1) : -std::log(from_ / to_) / (to_ - from_);  // :2560-2571
+  }
+  T step() {  // do_step, :2522-2543
+    if (cur_ + T(.5f) > duration_) { cur_ = 0; std::swap(from_, to_); }
+    T f_result = interpolate<T>(itp_, cur_, from_, to_ - from_, duration_);
+    T f = from_ + (to_ - from_) * (cur_ + T(.5f)) / duration_;
+    cur_ += C_ * f;
+    return f_result;
+  }
+  T from() const { return from_; }
+
+private:
+  T from_ = 0, to_ = 0, cur_ = 0, duration_ = 1, C_ = 1;
+  int itp_ = LINEAR;
+};
+
+template <class T>
+class RampVoice {
+public:
+  void initialize(const Ahdsr& a, int sample_rate, T volume) { env_.set_ahdsr(a, sample_rate); volume_ = volume; }
+  void forget_past_signals() { env_.forget_past_signals(); }
+  void setup_ramp(T from, T to, T duration, T start_sample) { ctrl_.setup(from, to, duration, start_sample, LINEAR); }
+  void set_angle_increments(T a) {  // Enveloped :218-225 (the control ignores it, :2489)
+    T period = angle_increment_to_period_in_continuous_samples(a);
+    env_.set_min_change_duration_samples(static_cast<int>(0.5f + T(2.5) * period));
+  }
+  void set_start_angle(T a) { osc_.set_start_angle(a); }
+  void on_key_pressed(int32_t d) { env_.on_key_pressed(d); }
+  void on_key_released(int32_t d) { env_.on_key_released(d); }
+  bool try_acquire() { return env_.try_acquire(); }
+  bool rt_active() const { return env_.rt_active(); }
+  void step() {  // Enveloped::step -> FreqCtrl_::step (:3126-3129)
+    env_.step();
+    osc_.set_angle_increments(ctrl_.step());
+    osc_.step();
+  }
+  T imag() const { return volume_ * (osc_.imag() * env_.value()); }
+
+private:
+  Envelope<T> env_;
+  SineOsc<T> osc_;
+  LogRamp<T> ctrl_;
+  T volume_ = 1;
+};
+
 // ImplCRTP::compute (include/gen.crtp.h:350-378): voice-major accumulation of n_frames <= 16 frames into an interleaved,
 // pre-zeroed double buffer (caller: SimpleAudioOutContext::step, include/simple_audio_context.h:69-112).
 template <class Voice>

@@ -60,6 +60,7 @@ def lib():
         L.orc_stft_analyze.restype = C.c_int64
         L.orc_oscbank_render.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int, p, p, p, p, p, p, p, p, C.c_int64,
                                          p, C.c_int, p, C.c_int]
+        L.orc_ramp_render.argtypes = [C.c_int64, C.c_int64, C.c_int, p, p, p, p, p, p, p, p, p, C.c_int, p, C.c_int]
         L.orc_envelope_trace.argtypes = [p, C.c_int, C.c_double, C.c_int32, C.c_int64, C.c_int64, p, p]
         L.orc_freq_aliasing_multiplicator.argtypes = [C.c_double]
         L.orc_freq_aliasing_multiplicator.restype = C.c_double
@@ -159,6 +160,24 @@ def oscbank_render(f0_hz, volume, partial_volume, partial_phase, n_samples: int,
         out = np.zeros((n_samples,), dtype=np.float64)
     lib().orc_oscbank_render(nv, npart, n_samples, sample_rate, _ptr(f0), _ptr(vol), _ptr(sa), _ptr(kd), _ptr(ra),
                              _ptr(pv), _ptr(pp), C.cast(envs, C.c_void_p), n_env, _ptr(pn), mix, _ptr(out), threads)
+    return out
+
+
+def ramp_render(from_hz, to_hz, duration, n_samples: int, sample_rate: int = 48000, volume=None, start_sample=None,
+                start_angle=None, key_delay=None, release_at=None, env=None, mix: int = 0, threads: int = 0) -> np.ndarray:
+    """gen.voice ramp voices (LogRamp + sine + AHDSR, constant volume), float64 [voices, samples] or [samples] (mix=2)."""
+    f = lambda a, t: None if a is None else np.ascontiguousarray(a, dtype=t)
+    from_hz, to_hz, duration = f(from_hz, np.float32), f(to_hz, np.float32), f(duration, np.float32)
+    V = from_hz.shape[0]
+    volume = np.ones(V, np.float32) if volume is None else f(volume, np.float32)
+    start_sample, start_angle = f(start_sample, np.float32), f(start_angle, np.float32)
+    key_delay, release_at = f(key_delay, np.int32), f(release_at, np.int64)
+    e = env if env is not None else make_ahdsr()
+    out = np.zeros((V, n_samples) if mix == 0 else (n_samples,), dtype=np.float64)
+    q = lambda a: None if a is None else _ptr(a)
+    lib().orc_ramp_render(V, n_samples, sample_rate, _ptr(from_hz), _ptr(to_hz), _ptr(duration), q(start_sample), _ptr(volume),
+                          q(start_angle), q(key_delay), q(release_at), C.byref(e), mix, _ptr(out),
+                          threads if threads > 0 else hardware_threads())
     return out
 
 

@@ -195,6 +195,44 @@ void orc_oscbank_render(int64_t n_voices, int n_partials, int64_t n_samples, int
   }
 }
 
+// gen.voice ramp voices (LogRamp-controlled sine with AHDSR envelope and constant volume): out [voices][samples] (mix 0)
+// or their sum [samples] (mix 2). env_ai[v]: the angle increment that sets the envelope's minimum change durations.
+void orc_ramp_render(int64_t n_voices, int64_t n_samples, int sample_rate, const float* from_hz, const float* to_hz,
+                     const float* duration, const float* start_sample, const float* volume, const float* start_angle,
+                     const int32_t* key_delay, const int64_t* release_at, const Ahdsr* env, int mix, double* out, int threads) {
+  std::vector<double> tmp;
+  if (mix != 0) {
+    tmp.assign(static_cast<size_t>(n_voices) * n_samples, 0.0);
+    for (int64_t i = 0; i < n_samples; ++i) out[i] = 0;
+  }
+  double* dst = mix == 0 ? out : tmp.data();
+  parallel_for(n_voices, threads, [&](int64_t v) {
+    RampVoice<double> voice;
+    const double from = static_cast<double>(freq_to_angle_increment<float>(from_hz[v], sample_rate));
+    const double to = static_cast<double>(freq_to_angle_increment<float>(to_hz[v], sample_rate));
+    voice.try_acquire();
+    voice.initialize(*env, sample_rate, volume[v]);
+    voice.set_angle_increments(from);
+    voice.forget_past_signals();
+    voice.setup_ramp(from, to, duration[v], start_sample ? start_sample[v] : 0.f);
+    voice.set_start_angle(start_angle ? start_angle[v] : 0.f);
+    voice.on_key_pressed(key_delay ? key_delay[v] : 0);
+    double* o = dst + v * n_samples;
+    const int64_t rel = release_at ? release_at[v] : -1;
+    for (int64_t i = 0; i < n_samples; ++i) {
+      if (i == rel) voice.on_key_released(0);
+      o[i] = 0;
+      if (!voice.rt_active()) continue;
+      voice.step();
+      if (!voice.rt_active()) continue;
+      o[i] = voice.imag();
+    }
+  });
+  if (mix != 0)
+    for (int64_t v = 0; v < n_voices; ++v)
+      for (int64_t i = 0; i < n_samples; ++i) out[i] += tmp[v * n_samples + i];
+}
+
 // Envelope alone (known-answer tests): value after each of n_steps steps, note pressed with `delay`,
 // released (delay 0) just before step index release_at (<0: never), for an oscillator of angle increment ai.
 void orc_envelope_trace(const Ahdsr* env, int sample_rate, double angle_increment, int32_t key_delay, int64_t release_at,

@@ -92,3 +92,25 @@ def test_golden_synthesis(orc):
                              env=orc.make_ahdsr(*[int(v) for v in g["env_adhr"]], sustain=float(g["sustain"])),
                              release_at=g["release_at"], key_delay=g["key_delay"], start_angle=g["start_angle"])
     assert np.abs(out[:, ::7] - g["out_decimated"]).max() < 1e-13
+
+
+def test_log_ramp_known_answers(orc):
+    """LogRamp (include/audioelement.h:2464-2572): a leg lasts about `duration` samples, the emitted increment runs from
+    `from` to `to` and back, a constant ramp is a plain sine, the phase is the running sum of the increments."""
+    sr, n = 48000, 20000
+    # constant ramp == oscillator at that frequency: y[i] = sin(pi * (i+1) * ai)
+    y = orc.ramp_render([1000.0], [1000.0], [777.0], n)[0]
+    ai = float(np.float32(2 * np.float32(1000.0) / sr))
+    i = np.arange(n)
+    env_floor = max(sr // 1000, int(0.5 + 2.5 * 2 / ai))
+    ref = np.sin(np.pi * (i + 1) * ai) * np.minimum(1.0, (i + 1) / env_floor)
+    assert np.abs(y - ref).max() < 1e-9
+    # instantaneous frequency of a slow up-ramp: phase difference between consecutive samples, away from the attack
+    y = orc.ramp_render([500.0], [1000.0], [8000.0], n)[0]
+    zc = np.where((y[:-1] < 0) & (y[1:] >= 0))[0]
+    periods = np.diff(zc)
+    f_first, f_turn = sr / periods[3], sr / periods[np.searchsorted(zc, 7900) - 1]
+    assert abs(f_first - 500.0) < 25 and abs(f_turn - 1000.0) < 40
+    # it bounces: around 2 * duration the frequency is back near `from`
+    f_back = sr / periods[np.searchsorted(zc, 15900) - 1]
+    assert abs(f_back - 500.0) < 40
