@@ -48,6 +48,31 @@ struct ca_ctx {
 
 namespace ca {
 
+// arguments of the analysis kernels (stft.cu: the fused 4096-point kernel; rfftw.cu: the fused kernels of the other lengths)
+struct StftArgs {
+  const float* x;
+  int64_t n_samples;
+  int64_t stream_stride;
+  int64_t frames_per_stream;
+  int64_t total_frames;
+  int32_t n_streams;
+  int32_t hop;
+  int32_t window;       // samples actually read per frame (<= 4096); the rest is zero padding
+  const float* win;     // [4096] window * 1/(2W), zero beyond `window`
+  float* sqmag;         // nullable
+  int64_t sqmag_row_stride;
+  int32_t* peak_bin;    // nullable
+  float* peak_freq;
+  float* peak_db;
+  int32_t* peak_count;
+  int32_t max_peaks;
+  float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
+  float bin_to_hz;
+  int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
+  int32_t stagger;         // start-up delay between the warps that share a scheduler, in clocks (see the kernel)
+  long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
+};
+
 inline int fail(ca_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->last_error = msg;
   return code;
@@ -94,6 +119,8 @@ int measure_fp32_peak(ca_ctx* ctx, double* tflops);
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);
 int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
+// fused window -> FFT -> |X|^2 -> peaks for n_fft = 1024, 2048, 8192, 16384, 32768 (rfftw.cu); CA_ERR_UNSUPPORTED otherwise
+int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream);
 void stft_release(ca_ctx* ctx);
 void rfft_release(ca_ctx* ctx);
 void oscbank_release(ca_ctx* ctx);

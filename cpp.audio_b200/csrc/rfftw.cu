@@ -467,6 +467,417 @@ int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cuda
   return CA_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused analysis (window -> real FFT -> |X|^2 -> peaks) for the FFT lengths other than 4096: the transforms above with
+// the window applied on load and the untangling step producing |X|^2 (HBM row + a shared-memory copy) instead of complex
+// bins; the peak list is extracted from the shared-memory copy exactly as in stft.cu (strict local maxima above the
+// threshold, ascending, parabolic interpolation on log2 ratios). One pass over HBM instead of the three of
+// window_frames_kernel -> K1 -> sqmag_peaks_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* frame_ptr(const StftArgs& p, int64_t f) {
+  const int64_t stream = f / p.frames_per_stream;
+  const int64_t fr = f - stream * p.frames_per_stream;
+  return p.x + stream * p.stream_stride + fr * p.hop;
+}
+// windowed pair (x[idx], x[idx+1]) * (w[idx], w[idx+1]); samples at or beyond the window are zero padding
+template <bool kVec2>
+__device__ __forceinline__ c2 load_windowed(const StftArgs& p, const float* __restrict__ xs, int idx) {
+  c2 s;
+  if (kVec2) s = idx < p.window ? ldg_c2(xs + idx) : pk(0.f, 0.f);
+  else s = pk(idx < p.window ? __ldg(xs + idx) : 0.f, idx + 1 < p.window ? __ldg(xs + idx + 1) : 0.f);
+  return mul2(s, ldg_c2(p.win + idx));
+}
+// (freq, dB) of the peak at bin k from its neighbours (SPEC S6), as in stft.cu
+__device__ __forceinline__ void peak_interp_store(const StftArgs& p, int64_t out_base, int idx, int k, float sa, float sb, float sc,
+                                                  bool store_bin) {
+  const float fl = 1e-37f;
+  sa = fmaxf(sa, fl);
+  sb = fmaxf(sb, fl);
+  sc = fmaxf(sc, fl);
+  const float inv_b = __frcp_rn(sb);
+  const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);
+  const float num = la - lc, den = la + lc;
+  const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
+  constexpr float kDbPerLog2 = 3.01029995663981195f;  // 10*log10(2)
+  if (store_bin) p.peak_bin[out_base + idx] = k;
+  p.peak_freq[out_base + idx] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
+  p.peak_db[out_base + idx] = kDbPerLog2 * __log2f(sb) - 0.25f * (kDbPerLog2 * num) * pp;
+}
+
+// |X[k]|^2 and |X[M-k]|^2 from Z[k], Z[M-k]; wpb = 0.5 * (-i) * W_N^(k mod stride), imm = W_N^(stride * I)
+template <typename Imm, bool kHasImm>
+__device__ __forceinline__ void untangle_sq(c2 zk, c2 zm, const TwP& wpb, float& sk, float& sm) {
+  const c2 E = add2(zk, cconj(zm));
+  c2 D = csub(zk, cconj(zm));
+  if constexpr (kHasImm) D = cmul_imm<Imm>(D);
+  const c2 T = cmul_tw(D, wpb);
+  const float2 P = upk(fma2(bc(0.5f), E, T)), Q = upk(fma2(bc(0.5f), E, cneg(T)));
+  sk = fmaf(P.x, P.x, P.y * P.y);
+  sm = fmaf(Q.x, Q.x, Q.y * Q.y);
+}
+
+// ---- one warp per frame: n_fft = 1024 (R1 = 16, two frames per warp), 2048 (R1 = 32) ----
+template <int R1>
+struct WarpStftCfg {
+  using F = WarpFftCfg<R1>;
+  static constexpr int SB = R1 + 4;             // floats per lane block of the |X|^2 buffer (R1 bins + pad: LDS.128, no conflicts)
+  static constexpr int kSqFloats = 32 * SB + 4;  // bins 0..M (bin M at 32*SB)
+  static constexpr int kList = 256;              // peak-bin list capacity in shared memory (longer lists: through the output)
+  static constexpr int kWarpBytes = 8 * F::kBufC2 + 4 * (F::FPW * kSqFloats + kList);
+};
+template <int I, int R1>
+__device__ __forceinline__ void warp_untangle_sq(const c2* __restrict__ Z, float* __restrict__ row, float* __restrict__ sq,
+                                                 const TwP& wpb, int lane) {
+  using C = WarpFftCfg<R1>;
+  using S = WarpStftCfg<R1>;
+  constexpr int M = C::M;
+  const int k = lane + 32 * I, m = M - k;
+  float sk, sm;
+  untangle_sq<Tw<2 * M, 32 * I>, (I != 0)>(Z[k], Z[m & (M - 1)], wpb, sk, sm);
+  if (row) {
+    row[k] = sk;
+    row[m] = sm;
+  }
+  sq[(k / R1) * S::SB + (k % R1)] = sk;
+  sq[(m / R1) * S::SB + (m % R1)] = sm;
+}
+template <int R1, int... I>
+__device__ __forceinline__ void warp_untangle_sq_all(const c2* Z, float* row, float* sq, const TwP& wpb, int lane,
+                                                     std::integer_sequence<int, I...>) {
+  (warp_untangle_sq<I, R1>(Z, row, sq, wpb, lane), ...);
+}
+
+template <int R1, int WARPS, bool kVec2>
+__global__ void __launch_bounds__(WARPS * 32, 2) stft_warp_kernel(const __grid_constant__ StftArgs p) {
+  using C = WarpFftCfg<R1>;
+  using S = WarpStftCfg<R1>;
+  constexpr int M = C::M, FPW = C::FPW, CPL = C::CPL;
+  static_assert(CPL == 1, "the fused warp kernel covers R1 <= 32");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  unsigned char* warp_base = reinterpret_cast<unsigned char*>(tab4 + C::kRows * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < C::kRows * 32; i += WARPS * 32) {
+    const int r = i >> 5, l = i & 31;
+    float2 w;
+    if (r < C::B - 1) w = cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / M);
+    else if (r < C::B - 1 + C::A - 1) w = cis_neg_w(2.f * static_cast<float>(l * C::B * (r - (C::B - 2))) / M);
+    else {
+      float s, c;
+      sincospif(static_cast<float>(l) / M, &s, &c);
+      w = make_float2(-0.5f * s, -0.5f * c);  // 0.5 * (-i) * W_N^l
+    }
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  __syncthreads();
+  c2* buf = reinterpret_cast<c2*>(warp_base + static_cast<size_t>(warp) * S::kWarpBytes);
+  float* sq_all = reinterpret_cast<float*>(buf + C::kBufC2);
+  int* klist = reinterpret_cast<int*>(sq_all + FPW * S::kSqFloats);
+  const TwP wpb = make_twp(tab4[(C::kRows - 1) * 32 + lane]);
+
+  const int64_t groups = (p.total_frames + FPW - 1) / FPW;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp; g < groups; g += static_cast<int64_t>(gridDim.x) * WARPS) {
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+      const int64_t frame = g * FPW + fw;
+      c2 v[R1];
+      if (frame < p.total_frames) {
+        const float* xs = frame_ptr(p, frame);
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) v[bitrev(n1, ilog2(R1))] = load_windowed<kVec2>(p, xs, 64 * n1 + 2 * lane);
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) v[n1] = pk(0.f, 0.f);
+      }
+      DitP<R1, R1, 0>::run(v);
+      tww_chain<R1, 0>(v, tab4, lane, make_twp(tab4[lane]));
+      c2* xb = buf + fw * (R1 / 2) * kXStride;
+#pragma unroll
+      for (int m = 0; m < R1 / 2; ++m)
+        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+    }
+    __syncwarp();
+    c2 A[32];
+    {
+      const int col = FPW > 1 ? (lane & (R1 - 1)) : lane;
+      const c2* xb = buf + (FPW > 1 ? (lane / R1) * (R1 / 2) * kXStride : 0);
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) A[bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
+      __syncwarp();
+      DitP<32, 32, 0>::run(A);
+      c2* Z = buf + (FPW > 1 ? (lane / R1) * M : 0);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = A[k2];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+      const int64_t frame = g * FPW + fw;
+      if (frame >= p.total_frames) break;
+      const c2* Z = buf + fw * M;
+      float* sq = sq_all + fw * S::kSqFloats;
+      float* row = p.sqmag ? p.sqmag + frame * p.sqmag_row_stride : nullptr;
+      warp_untangle_sq_all<R1>(Z, row, sq, wpb, lane, std::make_integer_sequence<int, M / 64>{});
+      if (lane == 0) {  // X[M/2] = conj(Z[M/2])
+        const float2 z = upk(Z[M / 2]);
+        const float s = fmaf(z.x, z.x, z.y * z.y);
+        if (row) row[M / 2] = s;
+        sq[((M / 2) / R1) * S::SB + ((M / 2) % R1)] = s;
+      }
+      if (!p.peak_count) continue;
+      __syncwarp();
+      // ---- peaks: lane owns bins [R1*lane, R1*lane + R1) ----
+      const int base = S::SB * lane;
+      float w[R1 + 2];
+      w[0] = lane ? sq[base - 5] : __int_as_float(0x7f800000);  // bin 0 is never a peak
+#pragma unroll
+      for (int q = 0; q < R1 / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sq + base + 4 * q);
+        w[1 + 4 * q] = t.x;
+        w[2 + 4 * q] = t.y;
+        w[3 + 4 * q] = t.z;
+        w[4 + 4 * q] = t.w;
+      }
+      w[R1 + 1] = sq[base + S::SB];  // first bin of the next block (bin M for the last lane)
+      uint32_t mask = 0;
+#pragma unroll
+      for (int j = 0; j < R1; ++j)
+        if (w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below)) mask |= 1u << j;
+      const int cnt = __popc(mask);
+      int incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int slot = incl - cnt;
+      if (lane == 0) p.peak_count[frame] = total;
+      const int64_t out_base = frame * static_cast<int64_t>(p.max_peaks);
+      const bool list_in_smem = p.max_peaks <= S::kList;
+      const int n_store = min(total, p.max_peaks);
+      while (mask && slot < n_store) {
+        const int j = __ffs(static_cast<int>(mask)) - 1;
+        mask &= mask - 1;
+        if (list_in_smem) klist[slot] = R1 * lane + j;
+        else p.peak_bin[out_base + slot] = R1 * lane + j;
+        ++slot;
+      }
+      __syncwarp();
+      for (int idx = lane; idx < n_store; idx += 32) {
+        const int k = list_in_smem ? klist[idx] : *reinterpret_cast<volatile int*>(p.peak_bin + out_base + idx);
+        auto at = [&](int b) { return sq[(b / R1) * S::SB + (b % R1)]; };
+        peak_interp_store(p, out_base, idx, k, at(k - 1), at(k), at(k + 1), list_in_smem);
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
+// ---- one CTA per frame: n_fft = 8192, 16384, 32768 (M = M1 x 1024, one warp per row, 32 bins per thread) ----
+template <int M1>
+struct CtaStftCfg {
+  using F = CtaFftCfg<M1>;
+  static constexpr int SB = 36;                          // 32 bins per thread + pad
+  static constexpr int kSqFloats = F::T * SB + 4;         // bins 0..M (bin M at T*SB)
+  static constexpr int kList = 256;
+  static constexpr size_t kSmem = sizeof(float4) * F::kRows * 32 + sizeof(c2) * F::kRowC2 * M1 + 4 * (kSqFloats + kList + 32);
+};
+template <int I, int M1>
+__device__ __forceinline__ void cta_untangle_sq(const c2* __restrict__ Zs, float* __restrict__ row, float* __restrict__ sq,
+                                                const TwP& wpb, int t) {
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M, SB = CtaStftCfg<M1>::SB;
+  const int k = t + C::T * I, m = M - k, mm = m & (M - 1);
+  float sk, sm;
+  untangle_sq<Tw<2 * M, C::T * I>, (I != 0)>(Zs[(k % M1) * C::kRowC2 + k / M1], Zs[(mm % M1) * C::kRowC2 + mm / M1], wpb, sk, sm);
+  if (row) {
+    row[k] = sk;
+    row[m] = sm;
+  }
+  sq[(k >> 5) * SB + (k & 31)] = sk;
+  sq[(m >> 5) * SB + (m & 31)] = sm;
+}
+template <int M1, int... I>
+__device__ __forceinline__ void cta_untangle_sq_all(const c2* Zs, float* row, float* sq, const TwP& wpb, int t,
+                                                    std::integer_sequence<int, I...>) {
+  (cta_untangle_sq<I, M1>(Zs, row, sq, wpb, t), ...);
+}
+
+template <int M1, bool kVec2>
+__global__ void __launch_bounds__(32 * M1, 16 / M1 > 4 ? 4 : 16 / M1) stft_cta_kernel(const __grid_constant__ StftArgs p) {
+  using C = CtaFftCfg<M1>;
+  using S = CtaStftCfg<M1>;
+  constexpr int M = C::M, M2 = C::M2, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  c2* Ys = reinterpret_cast<c2*>(tab4 + C::kRows * 32);
+  float* sq = reinterpret_cast<float*>(Ys + C::kRowC2 * M1);
+  int* klist = reinterpret_cast<int*>(sq + S::kSqFloats);
+  int* warp_tot = klist + S::kList;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < C::kRows * 32; i += T) {
+    const int r = i >> 5, l = i & 31;
+    const float2 w = r < 7 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / M2) : cis_neg_w(2.f * static_cast<float>(l * 8 * (r - 6)) / M2);
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  TwP wpb;
+  {
+    float s, c;
+    sincospif(static_cast<float>(t) / M, &s, &c);
+    wpb = TwP{-0.5f * s, pk(0.5f * c, -0.5f * c)};
+  }
+  for (int64_t frame = blockIdx.x; frame < p.total_frames; frame += gridDim.x) {
+    const float* xs = frame_ptr(p, frame);
+    __syncthreads();
+    // ---- step A: windowed columns ----
+#pragma unroll
+    for (int j = 0; j < M2 / T; ++j) {
+      const int c = t + T * j;
+      c2 v[M1];
+#pragma unroll
+      for (int n1 = 0; n1 < M1; ++n1) v[bitrev(n1, ilog2(M1))] = load_windowed<kVec2>(p, xs, 2 * (n1 * M2 + c));
+      DitP<M1, M1, 0>::run(v);
+      c2 w[M1];
+      {
+        float s, cs;
+        sincospif(2.f * static_cast<float>(c) / M, &s, &cs);
+        w[1] = pk(cs, -s);
+      }
+      cpow_all<M1>(w, std::make_integer_sequence<int, M1 - 2>{});
+#pragma unroll
+      for (int k1 = 1; k1 < M1; ++k1) {
+        const float2 a = upk(w[k1]);
+        v[k1] = cmul_tw(v[k1], TwP{a.x, pk(-a.y, a.y)});
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < M1; ++k1) Ys[k1 * C::kRowC2 + c] = v[k1];
+    }
+    __syncthreads();
+    // ---- step B: warp k1 transforms row k1, in place (as rfft_cta_kernel) ----
+    {
+      c2* row = Ys + warp * C::kRowC2;
+      c2 v[32];
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = row[32 * n1 + lane];
+      __syncwarp();
+      DitP<32, 32, 0>::run(v);
+      tww_chain<32, 0>(v, tab4, lane, make_twp(tab4[lane]));
+#pragma unroll
+      for (int m = 0; m < 16; ++m) *reinterpret_cast<ulonglong2*>(row + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+      __syncwarp();
+      c2 A[32];
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) A[bitrev(n2, 5)] = row[(lane >> 1) * kXStride + 2 * n2 + (lane & 1)];
+      __syncwarp();
+      DitP<32, 32, 0>::run(A);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = A[k2];
+    }
+    __syncthreads();
+    // ---- step C: |X|^2 ----
+    float* rowo = p.sqmag ? p.sqmag + frame * p.sqmag_row_stride : nullptr;
+    cta_untangle_sq_all<M1>(Ys, rowo, sq, wpb, t, std::make_integer_sequence<int, M / (2 * T)>{});
+    if (t == 0) {
+      const float2 z = upk(Ys[((M / 2) % M1) * C::kRowC2 + (M / 2) / M1]);
+      const float s = fmaf(z.x, z.x, z.y * z.y);
+      if (rowo) rowo[M / 2] = s;
+      sq[((M / 2) >> 5) * S::SB + ((M / 2) & 31)] = s;
+    }
+    if (!p.peak_count) continue;
+    __syncthreads();
+    // ---- peaks: thread t owns bins [32t, 32t+32) ----
+    const int base = S::SB * t;
+    uint32_t mask = 0;
+    {
+      float w[34];
+      w[0] = t ? sq[base - 5] : __int_as_float(0x7f800000);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 u = *reinterpret_cast<const float4*>(sq + base + 4 * q);
+        w[1 + 4 * q] = u.x;
+        w[2 + 4 * q] = u.y;
+        w[3 + 4 * q] = u.z;
+        w[4 + 4 * q] = u.w;
+      }
+      w[33] = sq[base + S::SB];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below)) mask |= 1u << j;
+    }
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int wv = 0; wv < M1; ++wv) {
+      const int tw = warp_tot[wv];
+      if (wv < warp) before += tw;
+      total += tw;
+    }
+    int slot = before + incl - cnt;
+    if (t == 0) p.peak_count[frame] = total;
+    const int64_t out_base = frame * static_cast<int64_t>(p.max_peaks);
+    const bool list_in_smem = p.max_peaks <= S::kList;
+    const int n_store = min(total, p.max_peaks);
+    while (mask && slot < n_store) {
+      const int j = __ffs(static_cast<int>(mask)) - 1;
+      mask &= mask - 1;
+      if (list_in_smem) klist[slot] = 32 * t + j;
+      else p.peak_bin[out_base + slot] = 32 * t + j;
+      ++slot;
+    }
+    if (!list_in_smem) __threadfence_block();
+    __syncthreads();
+    for (int idx = t; idx < n_store; idx += T) {
+      const int k = list_in_smem ? klist[idx] : *reinterpret_cast<volatile int*>(p.peak_bin + out_base + idx);
+      auto at = [&](int b) { return sq[(b >> 5) * S::SB + (b & 31)]; };
+      peak_interp_store(p, out_base, idx, k, at(k - 1), at(k), at(k + 1), list_in_smem);
+    }
+  }
+}
+
+template <int R1, int WARPS>
+int launch_stft_warp(ca_ctx* ctx, const StftArgs& a, bool vec2, cudaStream_t stream) {
+  using C = WarpFftCfg<R1>;
+  using S = WarpStftCfg<R1>;
+  void (*kern)(StftArgs) = vec2 ? stft_warp_kernel<R1, WARPS, true> : stft_warp_kernel<R1, WARPS, false>;
+  const size_t smem = sizeof(float4) * C::kRows * 32 + static_cast<size_t>(S::kWarpBytes) * WARPS;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t groups = (a.total_frames + C::FPW - 1) / C::FPW;
+  const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, (groups + WARPS - 1) / WARPS);
+  kern<<<static_cast<unsigned>(grid), WARPS * 32, smem, stream>>>(a);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+template <int M1>
+int launch_stft_cta(ca_ctx* ctx, const StftArgs& a, bool vec2, cudaStream_t stream) {
+  using C = CtaFftCfg<M1>;
+  using S = CtaStftCfg<M1>;
+  void (*kern)(StftArgs) = vec2 ? stft_cta_kernel<M1, true> : stft_cta_kernel<M1, false>;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S::kSmem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, S::kSmem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, a.total_frames);
+  kern<<<static_cast<unsigned>(grid), C::T, S::kSmem, stream>>>(a);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
@@ -485,6 +896,22 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     default: break;
   }
   return fail(ctx, CA_ERR_UNSUPPORTED, "rfft_warp: unsupported n_fft");
+}
+
+}  // namespace ca
+
+namespace ca {
+
+int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream) {
+  switch (n_fft) {
+    case 1024: return launch_stft_warp<16, 8>(ctx, a, vec2, stream);
+    case 2048: return launch_stft_warp<32, 8>(ctx, a, vec2, stream);
+    case 8192: return launch_stft_cta<4>(ctx, a, vec2, stream);
+    case 16384: return launch_stft_cta<8>(ctx, a, vec2, stream);
+    case 32768: return launch_stft_cta<16>(ctx, a, vec2, stream);
+    default: break;
+  }
+  return CA_ERR_UNSUPPORTED;
 }
 
 }  // namespace ca

@@ -43,29 +43,6 @@ constexpr int kExchFloat2 = 32 * kExchStride;
 constexpr int kWinStride = 66;  // window table: 64 pairs per lane (+2 pad), the 32 even-n1 pairs first, then the odd ones
 __device__ __forceinline__ int exch_idx(int k1, int n2) { return (k1 >> 1) * kExchStride + 2 * n2 + (k1 & 1); }
 
-struct StftArgs {
-  const float* x;
-  int64_t n_samples;
-  int64_t stream_stride;
-  int64_t frames_per_stream;
-  int64_t total_frames;
-  int32_t n_streams;
-  int32_t hop;
-  int32_t window;       // samples actually read per frame (<= 4096); the rest is zero padding
-  const float* win;     // [4096] window * 1/(2W), zero beyond `window`
-  float* sqmag;         // nullable
-  int64_t sqmag_row_stride;
-  int32_t* peak_bin;    // nullable
-  float* peak_freq;
-  float* peak_db;
-  int32_t* peak_count;
-  int32_t max_peaks;
-  float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
-  float bin_to_hz;
-  int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
-  int32_t stagger;         // start-up delay between the warps that share a scheduler, in clocks (see the kernel)
-  long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
-};
 #ifdef CA_STFT_TIMELINE
 #define CA_STAMP(i)                                                                                        \
   do {                                                                                                     \
@@ -705,6 +682,14 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
   a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / ctx->n_fft);
   if (ctx->n_fft != kN) {
+    a.max_peaks = ctx->stft.max_peaks;
+    a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
+    {  // fused single-pass kernels for 1024, 2048, 8192, 16384, 32768 (rfftw.cu)
+      const bool v2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0);
+      static const bool force_3pass = getenv("CA_STFT_THREE_PASS") != nullptr;  // A/B against the three-pass path
+      const int rcf = force_3pass ? CA_ERR_UNSUPPORTED : stft_fused_generic(ctx, a, ctx->n_fft, v2, stream);
+      if (rcf != CA_ERR_UNSUPPORTED) return rcf;
+    }
     // generic three-pass path, frames processed in groups that bound the work buffers to ~256 MiB each
     const int n_fft = ctx->n_fft, half = n_fft / 2;
     if (frames >= (1ll << 31)) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_analyze: too many frames per stream");

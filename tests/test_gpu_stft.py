@@ -140,6 +140,27 @@ def test_other_fft_lengths_generic_path(pkg, orc, ctx, wl, window, hop, sr):
     assert ref["peak_count"].min() >= 1
 
 
+@pytest.mark.parametrize("window,hop", [(1024, 128), (2048, 511), (8192, 256), (16000, 700)])
+def test_fused_other_lengths_many_frames_and_options(pkg, orc, ctx, wl, window, hop):
+    """The single-pass kernels of the other FFT lengths (rfftw.cu): more frames than resident warps / CTAs, three streams of
+    odd length (unaligned second and third stream), peak capacity beyond the shared-memory list, peaks-only and
+    spectrum-only calls."""
+    x = np.ascontiguousarray(wl.c4_streams(3, 2.0)[:, :90001])
+    ref = orc.stft_analyze(x, window, hop, max_peaks=300)
+    res = run_gpu(pkg, ctx, x, window, hop, max_peaks=300)
+    compare(res, ref)
+    ref = orc.stft_analyze(x, window, hop)
+    res = run_gpu(pkg, ctx, x, window, hop, want_sqmag=False)
+    assert "sqmag" not in res
+    S, F = ref["peak_count"].shape
+    assert (res["peak_count"].reshape(S, F) == ref["peak_count"]).all()
+    m = np.arange(ref["peak_bin"].shape[-1])[None, None, :] < ref["peak_count"][..., None]
+    assert (res["peak_bin"].reshape(ref["peak_bin"].shape)[m] == ref["peak_bin"][m]).all()
+    res = run_gpu(pkg, ctx, x, window, hop, want_peaks=False)
+    mag = np.sqrt(res["sqmag"].reshape(ref["sqmag"].shape).astype(np.float64))
+    assert np.abs(mag - np.sqrt(ref["sqmag"])).max() < TOL
+
+
 def test_peaks_only_and_sqmag_only(pkg, orc, ctx, wl):
     x = wl.c4_streams(2, 0.4)
     ref = orc.stft_analyze(x, 4096, 256)
