@@ -70,7 +70,9 @@ struct Note {
 
 struct StreamResult {
   std::vector<Segment> segs;
-  std::vector<int64_t> tile_seg_begin;  // per tile
+  std::vector<int64_t> tile_seg_begin;  // per tile (a frame interval longer than kMaxTile samples is cut into several tiles)
+  std::vector<int64_t> tile_n0;         // first sample of the tile (stream-relative)
+  std::vector<int32_t> tile_len;
   int64_t notes_started = 0, notes_dropped = 0;
 };
 
@@ -111,7 +113,10 @@ void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frame
   std::vector<int> change, order, next_played;
   std::vector<char> keep;
 
-  res.tile_seg_begin.assign(frames + 1, 0);
+  res.tile_seg_begin.clear();
+  res.tile_n0.clear();
+  res.tile_len.clear();
+  res.tile_seg_begin.reserve(frames + 1);
   for (int64_t k = 0; k < frames; ++k) {
     const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;  // events of frame k act from this sample on
     const int len = static_cast<int>(std::min<int64_t>(hop, n_samples - n_k));
@@ -228,9 +233,16 @@ void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frame
     std::stable_sort(next_played.begin(), next_played.end(), [&](int x, int y) { return notes[x].pitch < notes[y].pitch; });
     played.swap(next_played);
 
-    // ---------------- one segment per sounding note for this tile, then advance the note states ----------------
-    res.tile_seg_begin[k] = static_cast<int64_t>(res.segs.size());
-    if (len > 0) {
+    // ---------------- one segment per sounding note and tile, then advance the note states ----------------
+    // (the interval up to the next frame is one tile, or several when the hop exceeds kMaxTile samples)
+    const int len_frame = len;
+    for (int off = 0; off < std::max(len_frame, 0) || off == 0; off += kMaxTile) {
+      const int len = std::min(kMaxTile, len_frame - off);
+      const int64_t n_k_tile = n_k + off;
+      res.tile_seg_begin.push_back(static_cast<int64_t>(res.segs.size()));
+      res.tile_n0.push_back(n_k_tile);
+      res.tile_len.push_back(std::max(len, 0));
+      if (len <= 0) break;
       for (auto& n : notes) {
         Segment g{};
         const int64_t i0 = n.glide.i;
@@ -280,15 +292,15 @@ void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frame
           }
         }
         // envelope
-        g.c0 = static_cast<int32_t>(n_k - n.n_on + 1);
-        if (n.decay < 0 && (n_k + len - n.n_on) > static_cast<int64_t>(n.attack) + n.hold)  // decay latched when entered
+        g.c0 = static_cast<int32_t>(n_k_tile - n.n_on + 1);
+        if (n.decay < 0 && (n_k_tile + len - n.n_on) > static_cast<int64_t>(n.attack) + n.hold)  // decay latched when entered
           n.decay = D == 0 ? 0 : std::max(n.next_min_change, D);
         g.attack = n.attack;
         g.hold = n.hold;
         g.decay = n.decay < 0 ? 0 : n.decay;
         g.sustain = sustain;
         g.release = n.release > 0 ? n.release : 1;
-        g.rel_base = n.n_off < 0 ? INT_MAX : static_cast<int32_t>(std::max<int64_t>(n.n_off - n_k, -(1ll << 30)));
+        g.rel_base = n.n_off < 0 ? INT_MAX : static_cast<int32_t>(std::max<int64_t>(n.n_off - n_k_tile, -(1ll << 30)));
         g.top = static_cast<float>(n.top);
         g.gl = n.gl;
         g.gr = n.gr;
@@ -300,8 +312,10 @@ void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frame
         n.glide.i = i0 + len;
         n.vol_y = n.vol_x + (n.vol_y - n.vol_x) * exp(-3.14159265358979323846 * mv_end);
       }
+    }
+    if (len_frame > 0) {
       // a released note leaves the pool once its envelope reached Done2: release steps + 16 more (:738-749)
-      const int64_t n_next = n_k + len;
+      const int64_t n_next = n_k + len_frame;
       size_t w = 0;
       std::vector<int> remap(notes.size(), -1);
       for (size_t i = 0; i < notes.size(); ++i) {
@@ -317,7 +331,7 @@ void run_stream(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frame
       for (auto& pi : played) pi = remap[pi];
     }
   }
-  res.tile_seg_begin[frames] = static_cast<int64_t>(res.segs.size());
+  res.tile_seg_begin.push_back(static_cast<int64_t>(res.segs.size()));
 }
 
 }  // namespace
@@ -327,7 +341,6 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (!params || !h_x || !h_out || n_samples < 0 || n_streams < 0)
     return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: null argument or negative size");
   ca_roundtrip_params prm = *params;
-  if (prm.stft.hop > kMaxTile) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: hop > 1024");
   if (prm.max_channels <= 0) prm.max_channels = 254;
   if (prm.stft.max_peaks <= 0) prm.stft.max_peaks = 200;
   int rc = stft_plan(ctx, &prm.stft);
@@ -407,7 +420,9 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   lap("pitch pipeline (host)");
 
   // ---- 3. flatten (in parallel, into pinned memory) and render ----
-  const int64_t n_tiles = frames * n_streams;
+  std::vector<int64_t> tile_base(n_streams + 1, 0);
+  for (int64_t s = 0; s < n_streams; ++s) tile_base[s + 1] = tile_base[s] + static_cast<int64_t>(results[s].tile_len.size());
+  const int64_t n_tiles = tile_base[n_streams];
   std::vector<int64_t> seg_base(n_streams + 1, 0);
   for (int64_t s = 0; s < n_streams; ++s) seg_base[s + 1] = seg_base[s] + static_cast<int64_t>(results[s].segs.size());
   const int64_t n_segs = seg_base[n_streams];
@@ -421,17 +436,17 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   int64_t* tile_s0 = tile_begin + (n_tiles + 1);
   int32_t* tile_len = reinterpret_cast<int32_t*>(tile_s0 + std::max<int64_t>(n_tiles, 1));
   parallel([&](int64_t s) {
-    const int64_t base = seg_base[s];
-    for (int64_t k = 0; k < frames; ++k) {
-      const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;
-      tile_begin[s * frames + k] = base + results[s].tile_seg_begin[k];
-      tile_s0[s * frames + k] = s * n_samples + n_k;
-      tile_len[s * frames + k] = static_cast<int32_t>(std::max<int64_t>(0, std::min<int64_t>(hop, n_samples - n_k)));
+    const int64_t base = seg_base[s], tb = tile_base[s];
+    const StreamResult& r = results[s];
+    for (size_t k = 0; k < r.tile_len.size(); ++k) {
+      tile_begin[tb + k] = base + r.tile_seg_begin[k];
+      tile_s0[tb + k] = s * n_samples + r.tile_n0[k];
+      tile_len[tb + k] = r.tile_len[k];
     }
-    if (!results[s].segs.empty()) memcpy(h_segs + base, results[s].segs.data(), sizeof(Segment) * results[s].segs.size());
+    if (!r.segs.empty()) memcpy(h_segs + base, r.segs.data(), sizeof(Segment) * r.segs.size());
     if (h_stats) {
-      h_stats[2 * s] = results[s].notes_started;
-      h_stats[2 * s + 1] = results[s].notes_dropped;
+      h_stats[2 * s] = r.notes_started;
+      h_stats[2 * s + 1] = r.notes_dropped;
     }
   });
   tile_begin[n_tiles] = n_segs;

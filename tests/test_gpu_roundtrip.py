@@ -52,3 +52,14 @@ def test_edge_cases(pkg, ctx):
     assert out.shape == (2, 3000, 2) and np.abs(out).max() == 0 and stats.sum() == 0
     out, stats = pkg.resynth_roundtrip(ctx, np.zeros((1, 20000), np.float32))     # silence in, silence out
     assert np.abs(out).max() == 0 and stats.sum() == 0
+
+
+def test_reference_default_window_and_stride(pkg, orc, ctx, wl):
+    """window 0.1814 s / stride 0.09 s at 48 kHz (source/rt.resynth.lib.cpp:945-946 -> 8706 samples, FFT length 16384, hop
+    4320): the frame interval is longer than a render tile (1024 samples) and is cut into several tiles."""
+    x = wl.c4_streams(2, 2.0)
+    out, stats = pkg.resynth_roundtrip(ctx, x, window=8706, hop=4320)
+    ref, rstats = orc.roundtrip(x, window=8706, hop=4320)
+    assert np.array_equal(stats, rstats) and stats[:, 0].min() >= 8
+    assert np.abs(ref).max() > 0.1
+    assert np.abs(out - ref).max() < 2e-5
