@@ -1,0 +1,123 @@
+"""The offline job front / back end (tools/rt_resynth_job: job + preset JSON, WAV in, WAV out; reference:
+source/rt.resynth.lib.params.cpp:57-386, source/rt.resynth.lib.cpp:1185-1235). CPU tests cover the host logic through
+--dry-run; the GPU test checks that a job file produces exactly what ca_resynth_roundtrip_host produces."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "tools", "rt_resynth_job")
+
+
+def write_wav(path, x, sr, fmt="f32"):
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64).T).T if np.ndim(x) == 1 else np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    ch = x.shape[1]
+    if fmt == "f32":
+        tag, bits, data = 3, 32, x.astype("<f4").tobytes()
+    elif fmt == "i16":
+        tag, bits, data = 1, 16, np.clip(np.round(x * 32768.0), -32768, 32767).astype("<i2").tobytes()
+    elif fmt == "i24":
+        v = np.clip(np.round(x * 8388608.0), -8388608, 8388607).astype("<i4")
+        tag, bits, data = 1, 24, b"".join(struct.pack("<i", int(s))[:3] for s in v.reshape(-1))
+    else:
+        raise ValueError(fmt)
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, tag, ch, sr, sr * ch * bits // 8,
+                                                                               ch * bits // 8, bits) + b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr + data)
+
+
+def read_wav_f32(path):
+    b = open(path, "rb").read()
+    assert b[:4] == b"RIFF" and b[8:12] == b"WAVE"
+    tag, ch, sr = struct.unpack("<HHI", b[20:28])
+    assert tag == 3 and b[36:40] == b"data"
+    n = struct.unpack("<I", b[40:44])[0]
+    return np.frombuffer(b[44:44 + n], dtype="<f4").reshape(-1, ch), sr
+
+
+def preset(**floats):
+    return {"bool_params": {"use_autotune": False}, "enum_params": {}, "int32_params": {}, "uint64_params": {}, "float_params": floats}
+
+
+def run_tool(*args):
+    return subprocess.run([TOOL, *args], capture_output=True, text=True)
+
+
+@pytest.fixture(scope="module")
+def tool():
+    if not os.path.exists(TOOL):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s"])
+    return TOOL
+
+
+def test_dry_run_derives_the_reference_defaults(tool, tmp_path):
+    sr = 48000
+    t = np.arange(sr // 2) / sr
+    write_wav(tmp_path / "voice.wav", np.stack([0.5 * np.sin(2 * np.pi * 440 * t), 0.25 * np.sin(2 * np.pi * 440 * t)], axis=1), sr, "i16")
+    (tmp_path / "preset.json").write_text(json.dumps(preset(window_size_seconds=0.1814, window_center_stride_seconds=0.09,
+                                                            min_volume=0.0001, nearby_distance_tones=0.4, max_track_pitches=1.0,
+                                                            stereo_spread=1.0, env_attack_seconds=0.01, env_hold_seconds=0.0,
+                                                            env_decay_seconds=0.0, env_release_seconds=0.02, env_sustain_level=1.0,
+                                                            analysis_volume=0.5, pitch_shift_pre_autotune=2.0)))
+    job = {"preset_file": str(tmp_path / "preset.json"), "input_voice_file": str(tmp_path / "voice.wav"), "input_carrier_file": "",
+           "output_file": str(tmp_path / "out.wav"), "post": "none"}
+    (tmp_path / "job.json").write_text(json.dumps(job, indent=2))
+    r = run_tool("--dry-run", str(tmp_path / "job.json"))
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    # getEvenWindowSizeFrames / stride of source/rt.resynth.lib.cpp:484-487, :1577-1578 at 48 kHz
+    assert d["window"] == 2 * int(0.5 * np.float32(0.1814) * sr) == 8706 and d["hop"] == 4320 and d["fft_length"] == 16384
+    assert d["sample_rate"] == sr and d["frames"] == sr // 2
+    assert d["env"][:4] == [480, 0, 0, 960] and abs(d["gain"] - 0.5) < 1e-7
+    assert "pitch_shift_pre_autotune" in r.stderr  # a stage outside the path: reported, not silently dropped
+
+
+def test_dry_run_without_preset_and_error_paths(tool, tmp_path):
+    write_wav(tmp_path / "v.wav", 0.1 * np.ones(1000), 44100, "i24")
+    r = run_tool("--dry-run", "--voice", str(tmp_path / "v.wav"), "--out", str(tmp_path / "o.wav"))
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    assert d["sample_rate"] == 44100 and d["window"] == 2 * int(0.5 * np.float32(0.1814) * 44100) and d["fft_length"] == 8192
+    # bad 'post' encoding (from_string, params.cpp:170-178), missing voice file, unreadable preset
+    bad = {"preset_file": "", "input_voice_file": str(tmp_path / "v.wav"), "input_carrier_file": "", "output_file": "o.wav", "post": "loud"}
+    (tmp_path / "bad.json").write_text(json.dumps(bad))
+    assert run_tool("--dry-run", str(tmp_path / "bad.json")).returncode != 0
+    bad["post"], bad["input_voice_file"] = "none", str(tmp_path / "missing.wav")
+    (tmp_path / "bad2.json").write_text(json.dumps(bad))
+    assert run_tool("--dry-run", str(tmp_path / "bad2.json")).returncode != 0
+    (tmp_path / "broken_preset.json").write_text("{ not json")
+    bad["input_voice_file"], bad["preset_file"] = str(tmp_path / "v.wav"), str(tmp_path / "broken_preset.json")
+    (tmp_path / "bad3.json").write_text(json.dumps(bad))
+    r = run_tool("--dry-run", str(tmp_path / "bad3.json"))
+    assert r.returncode != 0 and "Reading preset file" in r.stderr
+
+
+@pytest.mark.gpu
+def test_job_output_equals_the_library_call(tool, tmp_path, pkg, ctx, wl):
+    sr = 48000
+    x = wl.c4_streams(2, 1.0)
+    for i in range(2):
+        write_wav(tmp_path / f"voice{i}.wav", x[i], sr, "f32")
+        (tmp_path / f"preset{i}.json").write_text(json.dumps(preset(window_size_seconds=4096 / sr + 1e-6, window_center_stride_seconds=256 / sr,
+                                                                     stereo_spread=0.5, analysis_volume=0.8)))
+        job = {"preset_file": str(tmp_path / f"preset{i}.json"), "input_voice_file": str(tmp_path / f"voice{i}.wav"),
+               "input_carrier_file": "", "output_file": str(tmp_path / f"out{i}.wav"), "post": "none"}
+        (tmp_path / f"job{i}.json").write_text(json.dumps(job))
+    r = run_tool(str(tmp_path / "job0.json"), str(tmp_path / "job1.json"))   # one batch of two streams
+    assert r.returncode == 0, r.stderr
+    n = x.shape[1] + sr + 4096
+    xp = np.zeros((2, n), np.float32)
+    xp[:, :x.shape[1]] = x
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, stereo_spread=0.5, gain=0.8)
+    for i in range(2):
+        y, sr_out = read_wav_f32(tmp_path / f"out{i}.wav")
+        assert sr_out == sr and y.shape == (x.shape[1] + sr, 2)
+        assert np.abs(y).max() > 0.05
+        assert np.array_equal(y, ref[i, :y.shape[0]])

@@ -1,0 +1,231 @@
+// rt_resynth_job — the offline rt.resynth job (source/rt.resynth.lib.cpp:1185-1235, source/rt.resynth.lib.params.cpp:
+// 183-386) on the B200 path: a job file names a preset, a voice WAV file and an output file; the voice is analysed and
+// resynthesised (ca_resynth_roundtrip_host) and written as IEEE-float stereo.
+//
+//   rt_resynth_job job.json [more job files...]          every job of the command line goes to the GPU in ONE batch
+//   rt_resynth_job --voice in.wav --out out.wav [--preset preset.json]
+//   rt_resynth_job --dry-run job.json                    parse and print the derived parameters, no GPU needed
+//
+// Job file:    {"preset_file": "...", "input_voice_file": "...", "input_carrier_file": "", "output_file": "...",
+//               "post": "none" | "limit"}                                     (RtResynthOfflineJobConfig, params.cpp:183-212)
+// Preset file: {"bool_params": {..}, "enum_params": {..}, "int32_params": {..}, "uint64_params": {..},
+//               "float_params": {"window_size_seconds": 0.1814, ...}}         (Preset, params.cpp:57-141)
+// The float parameters of the analysis -> resynthesis path are honoured (names of rt.resynth.lib.cpp:1944-2040): window and
+// stride, min_volume, nearby_distance_tones, max_track_pitches, stereo_spread, env_*, analysis_volume. The vocoder /
+// carrier / autotune / pitch-shift parameters belong to stages outside this path: a non-default value is reported and
+// ignored. "limit" post-processing (an external compressor in the reference) clips to [-1, 1].
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../include/cpp_audio_b200.h"
+#include "mini_json.hpp"
+#include "wav_io.hpp"
+
+namespace {
+
+struct Job {
+  std::string preset_file, voice_file, carrier_file, output_file, post = "none";
+};
+
+struct Derived {  // what the preset means at a sample rate (RtResynth getters, rt.resynth.lib.cpp:484-487, :1576-1578)
+  int window = 0, hop = 0;
+  ca_roundtrip_params prm{};
+};
+
+std::string slurp(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) throw std::runtime_error("cannot open '" + path + "'");
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+Job read_job(const std::string& path) {
+  const mini_json::Value j = mini_json::parse(slurp(path));
+  Job job;
+  job.preset_file = j.at("preset_file").as_string();
+  job.voice_file = j.at("input_voice_file").as_string();
+  job.carrier_file = j.at("input_carrier_file").as_string();
+  job.output_file = j.at("output_file").as_string();
+  job.post = j.at("post").as_string();
+  if (job.post != "none" && job.post != "limit") throw std::runtime_error("bad encoding of 'post'");  // params.cpp:170-178
+  return job;
+}
+
+float preset_float(const mini_json::Value* preset, const char* name, float dflt) {
+  if (!preset) return dflt;
+  const mini_json::Value* fp = preset->find("float_params");
+  const mini_json::Value* v = fp ? fp->find(name) : nullptr;
+  if (!v) {
+    std::fprintf(stderr, "Preset param '%s' not found\n", name);  // Params::read, params.cpp:19-27
+    return dflt;
+  }
+  return static_cast<float>(v->as_number());
+}
+
+Derived derive(const mini_json::Value* preset, int sample_rate) {
+  Derived d;
+  // defaults: rt.resynth.lib.cpp:940-961
+  const float ws = preset_float(preset, "window_size_seconds", 0.1814f);
+  const float stride = preset_float(preset, "window_center_stride_seconds", 0.09f);
+  d.window = 2 * std::max(1, static_cast<int>(0.5 * ws * sample_rate));          // getEvenWindowSizeFrames, :484-487
+  d.hop = std::max(1, static_cast<int>(0.5f + stride * sample_rate));            // :1577-1578
+  ca_roundtrip_params& p = d.prm;
+  p.stft.window = d.window;
+  p.stft.hop = d.hop;
+  p.stft.window_type = CA_WINDOW_GAUSSIAN;
+  p.stft.sigma_factor = 4.f;  // periodicfft.cpp:288
+  p.stft.sample_rate = sample_rate;
+  p.stft.min_db = -INFINITY;  // the reference thresholds on volume (min_volume), not on the spectrum
+  p.stft.max_peaks = 200;     // reserve of rt.resynth.lib.cpp:1102
+  p.min_volume = preset_float(preset, "min_volume", 0.0001f);
+  p.nearby_distance_tones = preset_float(preset, "nearby_distance_tones", 0.4f);
+  p.max_track_pitches = preset_float(preset, "max_track_pitches", 1.f);
+  p.stereo_spread = preset_float(preset, "stereo_spread", 1.f);
+  p.gain = preset_float(preset, "analysis_volume", 1.f);
+  auto seconds = [&](const char* name) { return static_cast<int32_t>(0.5f + preset_float(preset, name, 0.f) * sample_rate); };
+  p.env.attack = seconds("env_attack_seconds");
+  p.env.hold = seconds("env_hold_seconds");
+  p.env.decay = seconds("env_decay_seconds");
+  p.env.release = seconds("env_release_seconds");
+  p.env.sustain = preset_float(preset, "env_sustain_level", 1.f);
+  p.max_channels = 254;
+  p.host_threads = 0;
+  if (preset) {  // stages outside the analysis -> resynthesis path
+    struct { const char* name; float neutral; } ignored[] = {
+        {"pitch_shift_pre_autotune", 0.f}, {"pitch_shift_post_autotune", 0.f}, {"pitch_harmonize_pre_autotune", 0.f},
+        {"pitch_harmonize_post_autotune", 0.f}, {"vocoder_volume", 0.f}, {"carrier_volume", 0.f}, {"voice_volume", 0.f}};
+    const mini_json::Value* fp = preset->find("float_params");
+    for (auto& ig : ignored) {
+      const mini_json::Value* v = fp ? fp->find(ig.name) : nullptr;
+      if (v && static_cast<float>(v->as_number()) != ig.neutral)
+        std::fprintf(stderr, "note: preset param '%s' = %g belongs to a stage outside the B200 path and is ignored\n", ig.name, v->as_number());
+    }
+    const mini_json::Value* bp = preset->find("bool_params");
+    const mini_json::Value* ua = bp ? bp->find("use_autotune") : nullptr;
+    if (ua && ua->as_number() != 0) std::fprintf(stderr, "note: autotune is outside the B200 path and is ignored\n");
+  }
+  return d;
+}
+
+void print_derived(const Job& job, const Derived& d, int sample_rate, size_t frames) {
+  std::printf("{\"voice\": \"%s\", \"output\": \"%s\", \"sample_rate\": %d, \"frames\": %zu, \"window\": %d, \"hop\": %d, "
+              "\"fft_length\": %d, \"min_volume\": %g, \"nearby_distance_tones\": %g, \"max_track_pitches\": %g, "
+              "\"stereo_spread\": %g, \"gain\": %g, \"env\": [%d, %d, %d, %d, %g], \"post\": \"%s\"}\n",
+              job.voice_file.c_str(), job.output_file.c_str(), sample_rate, frames, d.window, d.hop, ca_fft_length_for(d.window, 1),
+              d.prm.min_volume, d.prm.nearby_distance_tones, d.prm.max_track_pitches, d.prm.stereo_spread, d.prm.gain,
+              d.prm.env.attack, d.prm.env.hold, d.prm.env.decay, d.prm.env.release, d.prm.env.sustain, job.post.c_str());
+}
+
+bool same_params(const Derived& a, const Derived& b) { return std::memcmp(&a.prm, &b.prm, sizeof(a.prm)) == 0; }
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    std::vector<Job> jobs;
+    bool dry = false;
+    Job cli;
+    for (int i = 1; i < argc; ++i) {
+      const std::string a = argv[i];
+      auto next = [&]() -> std::string {
+        if (i + 1 >= argc) throw std::runtime_error("missing value after " + a);
+        return argv[++i];
+      };
+      if (a == "--dry-run") dry = true;
+      else if (a == "--voice") cli.voice_file = next();
+      else if (a == "--out") cli.output_file = next();
+      else if (a == "--preset") cli.preset_file = next();
+      else if (a == "--post") cli.post = next();
+      else jobs.push_back(read_job(a));
+    }
+    if (!cli.voice_file.empty()) jobs.push_back(cli);
+    if (jobs.empty()) {
+      std::fprintf(stderr, "usage: rt_resynth_job [--dry-run] job.json... | --voice in.wav --out out.wav [--preset p.json] [--post none|limit]\n");
+      return 2;
+    }
+    struct Loaded {
+      Job job;
+      Derived d;
+      int sample_rate;
+      std::vector<float> voice;
+    };
+    std::vector<Loaded> loaded;
+    for (const Job& job : jobs) {
+      if (job.voice_file.empty()) throw std::runtime_error("must have a voice file (the carrier / vocoder stage is outside the B200 path)");
+      if (job.output_file.empty()) throw std::runtime_error("no output file");  // params.cpp:344-346
+      if (!job.carrier_file.empty()) std::fprintf(stderr, "note: the carrier file feeds the vocoder, a stage outside the B200 path; ignored\n");
+      mini_json::Value preset;
+      const bool has_preset = !job.preset_file.empty();
+      if (has_preset) {
+        try {
+          preset = mini_json::parse(slurp(job.preset_file));
+        } catch (const std::exception& e) {
+          std::fprintf(stderr, "Reading preset file '%s': %s\n", job.preset_file.c_str(), e.what());  // params.cpp:262-268
+          throw;
+        }
+      }
+      const wav_io::Audio audio = wav_io::read(job.voice_file);
+      Loaded l{job, derive(has_preset ? &preset : nullptr, audio.sample_rate), audio.sample_rate, wav_io::as_one_float(audio)};
+      print_derived(job, l.d, l.sample_rate, l.voice.size());
+      loaded.push_back(std::move(l));
+    }
+    if (dry) return 0;
+
+    ca_ctx* ctx = nullptr;
+    if (int rc = ca_init(0, &ctx)) {
+      std::fprintf(stderr, "ca_init failed (%d): this tool needs a B200; there is no CPU fallback\n", rc);
+      return 1;
+    }
+    // jobs with identical parameters and sample rate are batched as streams of one call (zero padded to the longest)
+    std::vector<bool> done(loaded.size(), false);
+    for (size_t i = 0; i < loaded.size(); ++i) {
+      if (done[i]) continue;
+      std::vector<size_t> group;
+      size_t longest = 0;
+      for (size_t k = i; k < loaded.size(); ++k)
+        if (!done[k] && loaded[k].sample_rate == loaded[i].sample_rate && same_params(loaded[k].d, loaded[i].d)) {
+          group.push_back(k);
+          done[k] = true;
+          longest = std::max(longest, loaded[k].voice.size());
+        }
+      // the reference keeps running until the output has been silent for one second (rt.resynth.lib.cpp:1228-1234)
+      const size_t n = longest + loaded[i].sample_rate + loaded[i].d.window;
+      float* x = static_cast<float*>(ca_host_alloc(sizeof(float) * n * group.size()));
+      float* y = static_cast<float*>(ca_host_alloc(sizeof(float) * 2 * n * group.size()));
+      std::vector<int64_t> stats(2 * group.size());
+      if (!x || !y) throw std::runtime_error("pinned allocation failed");
+      std::memset(x, 0, sizeof(float) * n * group.size());
+      for (size_t g = 0; g < group.size(); ++g)
+        std::memcpy(x + g * n, loaded[group[g]].voice.data(), sizeof(float) * loaded[group[g]].voice.size());
+      if (int rc = ca_resynth_roundtrip_host(ctx, &loaded[i].d.prm, x, static_cast<int64_t>(n), static_cast<int64_t>(group.size()), y, stats.data())) {
+        std::fprintf(stderr, "ca_resynth_roundtrip_host failed (%d): %s\n", rc, ca_last_error(ctx));
+        return 1;
+      }
+      for (size_t g = 0; g < group.size(); ++g) {
+        const Loaded& l = loaded[group[g]];
+        float* out = y + 2 * g * n;
+        size_t frames = l.voice.size() + l.sample_rate;  // input length + the second of silence that ends the reference loop
+        frames = std::min(frames, n);
+        if (l.job.post == "limit")
+          for (size_t k = 0; k < 2 * frames; ++k) out[k] = std::min(1.f, std::max(-1.f, out[k]));
+        wav_io::write_float32(l.job.output_file, l.sample_rate, 2, out, frames);
+        std::fprintf(stderr, "%s: %zu frames written, %lld notes started, %lld dropped\n", l.job.output_file.c_str(), frames,
+                     static_cast<long long>(stats[2 * g]), static_cast<long long>(stats[2 * g + 1]));
+      }
+      ca_host_free(x);
+      ca_host_free(y);
+    }
+    ca_destroy(ctx);
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "rt_resynth_job: %s\n", e.what());
+    return 1;
+  }
+}
