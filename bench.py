@@ -300,6 +300,30 @@ def run_ours(args):
         }
         del sout
 
+    # ---- BASELINE configs 1 and 5 (batched real FFT), three sizes of the sweep; the full sweep is profiles/sweep_rfft.py ----
+    if not args.skip_rfft:
+        peak_gbs, _ = measured_peaks()
+        rf = {}
+        for n_fft, batch in ((1024, 4096), (1024, 262144), (4096, 65536), (16384, 16384), (1 << 18, 1024)):
+            xr = torch.empty((batch, n_fft), dtype=torch.float32, device=dev).uniform_(-1, 1)
+            for _ in range(3):
+                yr = pkg.rfft_batched(ctx, xr)
+            sync_all()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20 if batch * n_fft <= (1 << 22) else 5
+            r0.record()
+            for _ in range(reps):
+                yr = pkg.rfft_batched(ctx, xr)
+            r1.record()
+            sync_all()
+            rms = r0.elapsed_time(r1) / reps
+            gbs = batch * (4 * n_fft + 8 * (n_fft // 2 + 1)) / (rms * 1e-3) / 1e9
+            rf[f"n{n_fft}_b{batch}"] = {"ms": rms, "frames_per_s": batch / (rms * 1e-3), "algorithmic_gbs": gbs, "frac_hbm": gbs / peak_gbs}
+            del xr, yr
+        rf["note"] = ("per rank; n1024_b4096 is BASELINE config 1 (33.6 MB, L2 resident, launch latency included), the others "
+                      "are points of config 5 (1 GiB of input each)")
+        extra["rfft"] = rf
+
     # ---- BASELINE config 4 per rank: host audio -> analysis -> pitch pipeline -> resynthesis -> host stereo audio ----
     if not args.skip_roundtrip:
         rt_in = pkg.pinned_empty(x_host_np.shape)
@@ -382,6 +406,7 @@ def main():
     ap.add_argument("--skip-synth", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roundtrip", action="store_true")
+    ap.add_argument("--skip-rfft", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
