@@ -21,7 +21,7 @@ from ._capi import (  # noqa: F401
     version,
     DECLARED_SYMBOLS,
 )
-from .analysis import SqMagAnalyzer, analyze_streams, rfft_batched  # noqa: F401
+from .analysis import SqMagAnalyzer, analyze_streams, irfft_batched, rfft_batched  # noqa: F401
 from .synth import SineBank, render_bank, render_ramps  # noqa: F401
 from .roundtrip import pinned_empty, resynth_roundtrip  # noqa: F401
 from .sharding import frame_shard, gather_rows, reduce_bus, shard_range  # noqa: F401

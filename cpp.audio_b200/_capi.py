@@ -9,7 +9,7 @@ _LIB = os.environ.get("CA_B200_LIB") or os.path.join(_HERE, "libcpp_audio_b200.s
 
 DECLARED_SYMBOLS = [
     "ca_version", "ca_init", "ca_destroy", "ca_last_error", "ca_sm_count", "ca_kernel_launches", "ca_host_alloc",
-    "ca_host_free", "ca_rfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
+    "ca_host_free", "ca_rfft_batched", "ca_irfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
     "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.ca_host_free.restype = None
     L.ca_rfft_batched.argtypes = [p, p, i32, i64, p, p]
     L.ca_rfft_batched_host.argtypes = [p, p, i32, i64, p]
+    L.ca_irfft_batched.argtypes = [p, p, i32, i64, p, C.c_float, p]
     L.ca_fft_length_for.argtypes = [i32, i32]
     L.ca_stft_num_frames.argtypes = [i64, i32, i32]
     L.ca_stft_num_frames.restype = i64

@@ -32,6 +32,19 @@ def rfft_batched(ctx: Context, x: torch.Tensor) -> torch.Tensor:
     return torch.view_as_complex(out)
 
 
+def irfft_batched(ctx: Context, X: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """Inverse real FFT of every row of X [batch, n_fft/2+1] (complex64, CUDA). Returns float32 [batch, n_fft] =
+    scale * (unnormalised inverse): irfft_batched(rfft_batched(x)) = n_fft * x at scale 1."""
+    if not (X.is_cuda and X.dtype == torch.complex64 and X.dim() == 2 and X.is_contiguous()):
+        raise ValueError("X must be a contiguous complex64 CUDA tensor [batch, n_fft/2+1]")
+    batch, bins = X.shape
+    n = 2 * (bins - 1)
+    out = torch.empty((batch, n), dtype=torch.float32, device=X.device)
+    ctx.check(lib().ca_irfft_batched(ctx.handle, torch.view_as_real(X).data_ptr(), n, batch, out.data_ptr(), scale, _stream_ptr(X.device)),
+              "ca_irfft_batched")
+    return out
+
+
 class SqMagAnalyzer:
     """Windowed squared-magnitude spectra + spectral peaks of overlapping frames of many streams.
 

@@ -84,6 +84,11 @@ int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, fl
   return rfft_batched(ctx, d_in, n_fft, batch, d_out, static_cast<cudaStream_t>(stream));
 }
 
+int ca_irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, ca_stream stream) {
+  if (!ctx) return CA_ERR_INVALID;
+  return irfft_batched(ctx, d_in, n_fft, batch, d_out, scale, static_cast<cudaStream_t>(stream));
+}
+
 int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
   if (!h_in || !h_out || batch < 0 || n_fft < 2) return fail(ctx, CA_ERR_INVALID, "ca_rfft_batched_host: bad argument");

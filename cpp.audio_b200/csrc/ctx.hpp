@@ -112,6 +112,7 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
                  float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
                  int32_t* d_peak_count, cudaStream_t stream);
 int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream);
+int irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, cudaStream_t stream);
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream);  // N <= 4096
 int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
 int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream);

@@ -878,6 +878,231 @@ int launch_stft_cta(ca_ctx* ctx, const StftArgs& a, bool vec2, cudaStream_t stre
   return CA_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Inverse real FFT (N <= 32768), unscaled like the forward one: x[n] = scale * sum_k X[k] exp(+2 pi i k n / N) over the
+// Hermitian extension of the N/2+1 input bins (irfft(rfft(x)) = N*x at scale 1). Used by the vocoder's carrier path
+// (fft.inverse at source/rt.resynth.lib.vocoder.cpp:438-470). The same transforms as above run on
+//     Zc[k] = conj( (X[k] + conj X[M-k]) + i W_N^-k (X[k] - conj X[M-k]) ),   k < M = N/2,
+// formed while loading, and the result is conjugated while storing (IFFT = conj . FFT . conj); its real and imaginary
+// parts are the even and odd output samples.
+// ---------------------------------------------------------------------------------------------------------------
+// wmb = conj-rotation table entry i * W_N^-(k mod stride) in the (wr, (-wi, wi)) form; Imm = W_N^-(stride * I)
+template <typename Imm, bool kHasImm>
+__device__ __forceinline__ c2 tangle_conj(c2 xk, c2 xm, const TwP& wmb) {
+  const c2 E = add2(xk, cconj(xm));
+  c2 D = csub(xk, cconj(xm));
+  if constexpr (kHasImm) D = cmul_imm<Imm>(D);
+  return cconj(add2(E, cmul_tw(D, wmb)));
+}
+template <int N, int I>
+struct TwInv {  // W_N^-I = conj(W_N^I)
+  static constexpr float re = Tw<N, I>::re;
+  static constexpr float im = -Tw<N, I>::im;
+};
+
+template <int R1, int N1>
+__device__ __forceinline__ void irfft_load(c2 (&v)[R1], const c2* __restrict__ X, const TwP& wmb, int lane) {
+  using C = WarpFftCfg<R1>;
+  constexpr int M = C::M;
+  const int k = 32 * N1 + lane;
+  v[bitrev(N1, ilog2(R1))] = tangle_conj<TwInv<2 * M, 32 * N1>, (N1 != 0)>(__ldg(X + k), __ldg(X + (M - k)), wmb);
+}
+template <int R1, int... N1>
+__device__ __forceinline__ void irfft_load_all(c2 (&v)[R1], const c2* X, const TwP& wmb, int lane, std::integer_sequence<int, N1...>) {
+  (irfft_load<R1, N1>(v, X, wmb, lane), ...);
+}
+
+template <int R1, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) irfft_warp_kernel(const float2* __restrict__ in, float* __restrict__ out,
+                                                                   const int64_t batch, const float scale) {
+  using C = WarpFftCfg<R1>;
+  constexpr int M = C::M, FPW = C::FPW, CPL = C::CPL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  c2* buf_all = reinterpret_cast<c2*>(tab4 + C::kRows * 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < C::kRows * 32; i += WARPS * 32) {
+    const int r = i >> 5, l = i & 31;
+    float2 w;
+    if (r < C::B - 1) w = cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / M);
+    else if (r < C::B - 1 + C::A - 1) w = cis_neg_w(2.f * static_cast<float>(l * C::B * (r - (C::B - 2))) / M);
+    else {
+      float s, c;
+      sincospif(static_cast<float>(l) / M, &s, &c);  // W_N^-l = c + i s;  i * W_N^-l = -s + i c
+      w = make_float2(-s, c);
+    }
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  __syncthreads();
+  c2* buf = buf_all + warp * C::kBufC2;
+  const TwP wmb = make_twp(tab4[(C::kRows - 1) * 32 + lane]);
+  const c2 sc = pk(scale, -scale);  // conj and scale at once
+
+  const int64_t groups = (batch + FPW - 1) / FPW;
+  for (int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp; g < groups; g += static_cast<int64_t>(gridDim.x) * WARPS) {
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+      const int64_t frame = g * FPW + fw;
+      c2 v[R1];
+      if (frame < batch) {
+        irfft_load_all<R1>(v, reinterpret_cast<const c2*>(in) + frame * (M + 1), wmb, lane, std::make_integer_sequence<int, R1>{});
+      } else {
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) v[n1] = pk(0.f, 0.f);
+      }
+      DitP<R1, R1, 0>::run(v);
+      tww_chain<R1, 0>(v, tab4, lane, make_twp(tab4[lane]));
+      c2* xb = buf + fw * (R1 / 2) * kXStride;
+#pragma unroll
+      for (int m = 0; m < R1 / 2; ++m)
+        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int col = FPW > 1 ? (lane & (R1 - 1)) : lane + 32 * c;
+      const c2* xb = buf + (FPW > 1 ? (lane / R1) * (R1 / 2) * kXStride : 0);
+      c2 A[32];
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) A[bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
+      DitP<32, 32, 0>::run(A);
+      // y[col + R1*k2] = (x[2n], -x[2n+1]) at n = col + R1*k2: consecutive lanes, consecutive pairs
+      const int64_t frame = g * FPW + (FPW > 1 ? lane / R1 : 0);
+      if (frame < batch) {
+        c2* o = reinterpret_cast<c2*>(out + frame * (2 * M));
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) o[col + R1 * k2] = mul2(A[k2], sc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int M1, int J, int N1>
+__device__ __forceinline__ c2 irfft_cta_elem(const c2* __restrict__ X, const TwP& wmb, int t) {
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M, OFF = N1 * C::M2 + C::T * J;
+  const int k = OFF + t;
+  return tangle_conj<TwInv<2 * M, OFF>, (OFF != 0)>(__ldg(X + k), __ldg(X + (M - k)), wmb);
+}
+template <int M1, int J, int... N1>
+__device__ __forceinline__ void irfft_cta_col(c2 (&v)[M1], const c2* X, const TwP& wmb, int t, std::integer_sequence<int, N1...>) {
+  ((v[bitrev(N1, ilog2(M1))] = irfft_cta_elem<M1, J, N1>(X, wmb, t)), ...);
+}
+
+template <int M1, int J>
+__device__ __forceinline__ void irfft_cta_step_a(const c2* X, c2* Ys, const TwP& wmb, int t) {
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M;
+  const int c = t + C::T * J;
+  c2 v[M1];
+  irfft_cta_col<M1, J>(v, X, wmb, t, std::make_integer_sequence<int, M1>{});
+  DitP<M1, M1, 0>::run(v);
+  c2 w[M1];
+  {
+    float s, cs;
+    sincospif(2.f * static_cast<float>(c) / M, &s, &cs);
+    w[1] = pk(cs, -s);
+  }
+  cpow_all<M1>(w, std::make_integer_sequence<int, M1 - 2>{});
+#pragma unroll
+  for (int k1 = 1; k1 < M1; ++k1) {
+    const float2 a = upk(w[k1]);
+    v[k1] = cmul_tw(v[k1], TwP{a.x, pk(-a.y, a.y)});
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < M1; ++k1) Ys[k1 * C::kRowC2 + c] = v[k1];
+}
+template <int M1, int... J>
+__device__ __forceinline__ void irfft_cta_step_a_all(const c2* X, c2* Ys, const TwP& wmb, int t, std::integer_sequence<int, J...>) {
+  (irfft_cta_step_a<M1, J>(X, Ys, wmb, t), ...);
+}
+
+template <int M1>
+__global__ void __launch_bounds__(32 * M1) irfft_cta_kernel(const float2* __restrict__ in, float* __restrict__ out, const int64_t batch,
+                                                            const float scale) {
+  using C = CtaFftCfg<M1>;
+  constexpr int M = C::M, M2 = C::M2, T = C::T;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  c2* Ys = reinterpret_cast<c2*>(tab4 + C::kRows * 32);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < C::kRows * 32; i += T) {
+    const int r = i >> 5, l = i & 31;
+    const float2 w = r < 7 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / M2) : cis_neg_w(2.f * static_cast<float>(l * 8 * (r - 6)) / M2);
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  TwP wmb;
+  {
+    float s, c;
+    sincospif(static_cast<float>(t) / M, &s, &c);  // i * W_N^-t = -s + i c
+    wmb = TwP{-s, pk(-c, c)};
+  }
+  const c2 sc = pk(scale, -scale);
+  for (int64_t frame = blockIdx.x; frame < batch; frame += gridDim.x) {
+    const c2* X = reinterpret_cast<const c2*>(in) + frame * (M + 1);
+    __syncthreads();
+    irfft_cta_step_a_all<M1>(X, Ys, wmb, t, std::make_integer_sequence<int, M2 / T>{});
+    __syncthreads();
+    {
+      c2* row = Ys + warp * C::kRowC2;
+      c2 v[32];
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = row[32 * n1 + lane];
+      __syncwarp();
+      DitP<32, 32, 0>::run(v);
+      tww_chain<32, 0>(v, tab4, lane, make_twp(tab4[lane]));
+#pragma unroll
+      for (int m = 0; m < 16; ++m) *reinterpret_cast<ulonglong2*>(row + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+      __syncwarp();
+      c2 A[32];
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) A[bitrev(n2, 5)] = row[(lane >> 1) * kXStride + 2 * n2 + (lane & 1)];
+      __syncwarp();
+      DitP<32, 32, 0>::run(A);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = A[k2];
+    }
+    __syncthreads();
+    c2* o = reinterpret_cast<c2*>(out + frame * (2 * M));
+#pragma unroll 8
+    for (int n = t; n < M; n += T) o[n] = mul2(Ys[(n % M1) * C::kRowC2 + n / M1], sc);
+  }
+}
+
+template <int R1, int WARPS>
+int launch_iwarp(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, float scale, cudaStream_t stream) {
+  using C = WarpFftCfg<R1>;
+  auto kern = irfft_warp_kernel<R1, WARPS>;
+  const size_t smem = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kBufC2 * WARPS;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t groups = (batch + C::FPW - 1) / C::FPW;
+  const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, (groups + WARPS - 1) / WARPS);
+  kern<<<static_cast<unsigned>(grid), WARPS * 32, smem, stream>>>(reinterpret_cast<const float2*>(d_in), d_out, batch, scale);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+template <int M1>
+int launch_icta(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, float scale, cudaStream_t stream) {
+  using C = CtaFftCfg<M1>;
+  auto kern = irfft_cta_kernel<M1>;
+  const size_t smem = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kRowC2 * M1;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::T, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, batch);
+  kern<<<static_cast<unsigned>(grid), C::T, smem, stream>>>(reinterpret_cast<const float2*>(d_in), d_out, batch, scale);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
@@ -901,6 +1126,23 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
 }  // namespace ca
 
 namespace ca {
+
+int irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, cudaStream_t stream) {
+  if (!d_in || !d_out || batch < 0) return fail(ctx, CA_ERR_INVALID, "ca_irfft_batched: null pointer or negative batch");
+  if (reinterpret_cast<uintptr_t>(d_in) % 8 || reinterpret_cast<uintptr_t>(d_out) % 8)
+    return fail(ctx, CA_ERR_INVALID, "ca_irfft_batched: buffers must be 8-byte aligned");
+  if (batch == 0) return CA_OK;
+  switch (n_fft) {
+    case 1024: return launch_iwarp<16, 8>(ctx, d_in, batch, d_out, scale, stream);
+    case 2048: return launch_iwarp<32, 8>(ctx, d_in, batch, d_out, scale, stream);
+    case 4096: return launch_iwarp<64, 12>(ctx, d_in, batch, d_out, scale, stream);
+    case 8192: return launch_icta<4>(ctx, d_in, batch, d_out, scale, stream);
+    case 16384: return launch_icta<8>(ctx, d_in, batch, d_out, scale, stream);
+    case 32768: return launch_icta<16>(ctx, d_in, batch, d_out, scale, stream);
+    default: break;
+  }
+  return fail(ctx, CA_ERR_UNSUPPORTED, "ca_irfft_batched: n_fft must be a power of two in [2^10, 2^15]");
+}
 
 int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream) {
   switch (n_fft) {

@@ -54,6 +54,11 @@ void ca_host_free(void* p);
  * n_fft: power of two, 2^10 .. 2^20. */
 int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, ca_stream stream);
 int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out);
+/* Inverse: stands in for fft::Algo_<Tag,T>::inverse as the vocoder's carrier path uses it
+ * (source/rt.resynth.lib.vocoder.cpp:438-470). d_in [batch][n_fft/2+1] (re,im), Hermitian extension implied (bins 0 and n_fft/2 must
+ * be real); d_out [batch][n_fft] = scale * sum_k X[k] exp(+2 pi i k n / n_fft), so
+ * irfft(rfft(x)) = n_fft * x at scale 1. n_fft: power of two, 2^10 .. 2^15. */
+int ca_irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, ca_stream stream);
 
 /* ---- K2: periodic-FFT analysis ----------------------------------------------------------------------------------
  * Stands in for PeriodicFFT<SqMagFftOperation<Window,T>> (source/rt.resynth.lib.periodicfft.cpp:13-181, :251-325)

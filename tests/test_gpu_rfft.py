@@ -82,3 +82,37 @@ def test_batch_edge_cases(pkg, ctx):
         pkg.rfft_batched(ctx, torch.zeros((2, 512), device="cuda"))
     with pytest.raises(pkg.CaError):
         pkg.rfft_batched(ctx, torch.zeros((2, 3000), device="cuda"))
+
+
+@pytest.mark.parametrize("p", [10, 11, 12, 13, 14, 15])
+def test_inverse_real_fft(pkg, ctx, p):
+    """ca_irfft_batched against numpy.fft.irfft (the anchor of the oracle's FFT, oracle/SPEC.md S5) and as the inverse of
+    the forward transform: irfft(rfft(x)) = N x."""
+    n = 1 << p
+    rng = np.random.default_rng(7000 + p)
+    x = rng.uniform(-1, 1, (19, n)).astype(np.float32)
+    X = np.fft.rfft(x.astype(np.float64), axis=1)
+    Xt = torch.from_numpy(X.astype(np.complex64)).cuda()
+    y = pkg.irfft_batched(ctx, Xt, scale=1.0 / n)
+    torch.cuda.synchronize()
+    ref = np.fft.irfft(X.astype(np.complex64).astype(np.complex128), n=n, axis=1)
+    assert np.abs(y.cpu().numpy() - ref).max() < 1e-5
+    xt = torch.from_numpy(x).cuda()
+    back = pkg.irfft_batched(ctx, pkg.rfft_batched(ctx, xt), scale=1.0 / n)
+    torch.cuda.synchronize()
+    assert (back - xt).abs().max().item() < 1e-5
+    # a single bin k comes back as a cosine of amplitude 2 (1 for DC and Nyquist)
+    S = torch.zeros((3, n // 2 + 1), dtype=torch.complex64, device="cuda")
+    S[0, 0] = 1.0
+    S[1, 37] = 1.0
+    S[2, n // 2] = 1.0
+    c = pkg.irfft_batched(ctx, S).cpu().numpy()
+    t = np.arange(n)
+    assert np.abs(c[0] - 1.0).max() < 1e-6
+    assert np.abs(c[1] - 2 * np.cos(2 * np.pi * 37 * t / n)).max() < 1e-5
+    assert np.abs(c[2] - np.cos(np.pi * t)).max() < 1e-6
+
+
+def test_inverse_unsupported_length_fails_loudly(pkg, ctx):
+    with pytest.raises(pkg.CaError):
+        pkg.irfft_batched(ctx, torch.zeros((1, (1 << 16) // 2 + 1), dtype=torch.complex64, device="cuda"))
