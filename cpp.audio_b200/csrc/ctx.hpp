@@ -69,7 +69,6 @@ struct StftArgs {
   float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
   float bin_to_hz;
   int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
-  int32_t stagger;         // start-up delay between the warps that share a scheduler, in clocks (see the kernel)
   long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
 };
 

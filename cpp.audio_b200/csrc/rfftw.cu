@@ -549,7 +549,7 @@ __device__ __forceinline__ void warp_untangle_sq_all(const c2* Z, float* row, fl
 }
 
 template <int R1, int WARPS, bool kVec2>
-__global__ void __launch_bounds__(WARPS * 32, 2) stft_warp_kernel(const __grid_constant__ StftArgs p) {
+__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) stft_warp_kernel(const __grid_constant__ StftArgs p) {
   using C = WarpFftCfg<R1>;
   using S = WarpStftCfg<R1>;
   constexpr int M = C::M, FPW = C::FPW, CPL = C::CPL;
@@ -1146,8 +1146,8 @@ int irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, floa
 
 int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream) {
   switch (n_fft) {
-    case 1024: return launch_stft_warp<16, 8>(ctx, a, vec2, stream);
-    case 2048: return launch_stft_warp<32, 8>(ctx, a, vec2, stream);
+    case 1024: return launch_stft_warp<16, 4>(ctx, a, vec2, stream);  // 3 CTAs x 4 warps per SM (shared memory bound)
+    case 2048: return launch_stft_warp<32, 4>(ctx, a, vec2, stream);
     case 8192: return launch_stft_cta<4>(ctx, a, vec2, stream);
     case 16384: return launch_stft_cta<8>(ctx, a, vec2, stream);
     case 32768: return launch_stft_cta<16>(ctx, a, vec2, stream);

@@ -465,14 +465,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __gri
   const int64_t fstep = static_cast<int64_t>(gridDim.x) * WARPS;
   int64_t f = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
   if (f >= p.total_frames) return;
-  if (p.stagger > 0 && warp >= 4) {
-    // warps w, w+4, w+8 share a scheduler and run the same phase sequence: started together they stay in step, fight
-    // for the FMA pipe during the FFTs and leave it idle during the memory phases. A start-up offset spreads the phases.
-    const long long t0 = clock64();
-    const long long wait = static_cast<long long>(p.stagger) * (warp >> 2);
-    while (clock64() - t0 < wait) {
-    }
-  }
   c2* stage = exch + kStageOff;
   c2 v[64];
   const float* xs = frame_base_p(p, f);
@@ -721,18 +713,13 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
     return CA_OK;
   }
   a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
-  static const int stagger_env = [] {
-    const char* e = getenv("CA_STFT_STAGGER");
-    return e ? atoi(e) : 0;
-  }();
-  a.stagger = stagger_env;
 
   const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
                     (ctx->stft.window % 2 == 0);
   const bool full = ctx->stft.window == kN;
   // 12 warps x 1 CTA per SM: 12 x 16.5 KB exchange buffers + 16 KB window + tables = 224 KB of shared memory, 168 registers
   static const int warps_env = [] {
-    const char* e = getenv("CA_STFT_WARPS");  // tuning experiments: 11 (184 registers, no spills) or 12
+    const char* e = getenv("CA_STFT_WARPS");  // 4 = one warp per scheduler: the uncontended timeline (profiles/build_timeline.sh)
     return e ? atoi(e) : 12;
   }();
   // staged path: window 4096, hop a multiple of 128 samples, 16-byte aligned streams (see frame_stage_even_p)
