@@ -103,48 +103,67 @@ __global__ void __launch_bounds__(WARPS * 32, 1) rfft_warp_kernel(const float* _
   c2* buf = buf_all + warp * C::kBufC2;
   const TwP wpb = make_twp(tab4[(C::kRows - 1) * 32 + lane]);
 
+  // The samples of the warp's NEXT group are requested before the untangling / store phase of the current one (which
+  // needs few registers) and land while it runs: more bytes in flight per SM, which is what an HBM-bound kernel with 8-12
+  // warps per SM lacks.
   const int64_t groups = (batch + FPW - 1) / FPW;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp; g < groups; g += static_cast<int64_t>(gridDim.x) * WARPS) {
-    // ---- pass 1 per frame of the group: load, R1-point FFT, twiddle, transposed store ----
+  const int64_t gstep = static_cast<int64_t>(gridDim.x) * WARPS;
+  c2 v[FPW][R1];
+  // (not at R1 = 64: the 128 data registers do not fit next to the untangling phase — measured: spills, 70 % instead of 74 %)
+  constexpr int kPre = R1 > 32 ? 0 : R1;
+  auto load_group = [&](int64_t g, int n1_begin, int n1_end) {
 #pragma unroll
     for (int fw = 0; fw < FPW; ++fw) {
       const int64_t frame = g * FPW + fw;
-      c2 v[R1];
       if (frame < batch) {
         const float* x = in + frame * (2 * M);
 #pragma unroll
-        for (int n1 = 0; n1 < R1; ++n1) v[bitrev(n1, ilog2(R1))] = ldg_c2(x + 64 * n1 + 2 * lane);
+        for (int n1 = 0; n1 < R1; ++n1)
+          if (n1 >= n1_begin && n1 < n1_end) v[fw][bitrev(n1, ilog2(R1))] = ldg_c2(x + 64 * n1 + 2 * lane);
       } else {
 #pragma unroll
-        for (int n1 = 0; n1 < R1; ++n1) v[n1] = pk(0.f, 0.f);
+        for (int n1 = 0; n1 < R1; ++n1)
+          if (n1 >= n1_begin && n1 < n1_end) v[fw][bitrev(n1, ilog2(R1))] = pk(0.f, 0.f);
       }
-      DitP<R1, R1, 0>::run(v);
-      tww_chain<R1, 0>(v, tab4, lane, make_twp(tab4[lane]));
+    }
+  };
+  int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+  if (g < groups) load_group(g, 0, kPre);
+  for (; g < groups; g += gstep) {
+    if (kPre < R1) load_group(g, kPre, R1);
+    // ---- pass 1 per frame of the group: R1-point FFT, twiddle, transposed store ----
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+      DitP<R1, R1, 0>::run(v[fw]);
+      tww_chain<R1, 0>(v[fw], tab4, lane, make_twp(tab4[lane]));
       c2* xb = buf + fw * (R1 / 2) * kXStride;
 #pragma unroll
       for (int m = 0; m < R1 / 2; ++m)
-        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[fw][2 * m], v[fw][2 * m + 1]);
     }
     __syncwarp();
     // ---- pass 2: whole columns ----
-    c2 A[CPL][32];
+    {
+      c2 A[CPL][32];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      const int col = FPW > 1 ? (lane & (R1 - 1)) : lane + 32 * c;
-      const c2* xb = buf + (FPW > 1 ? (lane / R1) * (R1 / 2) * kXStride : 0);
+      for (int c = 0; c < CPL; ++c) {
+        const int col = FPW > 1 ? (lane & (R1 - 1)) : lane + 32 * c;
+        const c2* xb = buf + (FPW > 1 ? (lane / R1) * (R1 / 2) * kXStride : 0);
 #pragma unroll
-      for (int n2 = 0; n2 < 32; ++n2) A[c][bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
-    }
-    __syncwarp();  // the buffer is rewritten in Z order
+        for (int n2 = 0; n2 < 32; ++n2) A[c][bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
+      }
+      __syncwarp();  // the buffer is rewritten in Z order
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      DitP<32, 32, 0>::run(A[c]);
-      const int col = FPW > 1 ? (lane & (R1 - 1)) : lane + 32 * c;
-      c2* Z = buf + (FPW > 1 ? (lane / R1) * M : 0);
+      for (int c = 0; c < CPL; ++c) {
+        DitP<32, 32, 0>::run(A[c]);
+        const int col = FPW > 1 ? (lane & (R1 - 1)) : lane + 32 * c;
+        c2* Z = buf + (FPW > 1 ? (lane / R1) * M : 0);
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = A[c][k2];
+        for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = A[c][k2];
+      }
     }
     __syncwarp();
+    if (g + gstep < groups) load_group(g + gstep, 0, kPre);  // in flight during the untangling
     // ---- untangle + coalesced stores ----
 #pragma unroll
     for (int fw = 0; fw < FPW; ++fw) {
@@ -549,7 +568,7 @@ __device__ __forceinline__ void warp_untangle_sq_all(const c2* Z, float* row, fl
 }
 
 template <int R1, int WARPS, bool kVec2>
-__global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) stft_warp_kernel(const __grid_constant__ StftArgs p) {
+__global__ void __launch_bounds__(WARPS * 32, 3) stft_warp_kernel(const __grid_constant__ StftArgs p) {
   using C = WarpFftCfg<R1>;
   using S = WarpStftCfg<R1>;
   constexpr int M = C::M, FPW = C::FPW, CPL = C::CPL;
@@ -576,26 +595,43 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) stft_warp_kern
   int* klist = reinterpret_cast<int*>(sq_all + FPW * S::kSqFloats);
   const TwP wpb = make_twp(tab4[(C::kRows - 1) * 32 + lane]);
 
+  // raw samples of the warp's next group are requested before the |X|^2 / peak phase of the current one (see rfft_warp_kernel)
   const int64_t groups = (p.total_frames + FPW - 1) / FPW;
-  for (int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp; g < groups; g += static_cast<int64_t>(gridDim.x) * WARPS) {
+  const int64_t gstep = static_cast<int64_t>(gridDim.x) * WARPS;
+  c2 v[FPW][R1];
+  auto load_group = [&](int64_t g) {
 #pragma unroll
     for (int fw = 0; fw < FPW; ++fw) {
       const int64_t frame = g * FPW + fw;
-      c2 v[R1];
       if (frame < p.total_frames) {
         const float* xs = frame_ptr(p, frame);
 #pragma unroll
-        for (int n1 = 0; n1 < R1; ++n1) v[bitrev(n1, ilog2(R1))] = load_windowed<kVec2>(p, xs, 64 * n1 + 2 * lane);
+        for (int n1 = 0; n1 < R1; ++n1) {
+          const int idx = 64 * n1 + 2 * lane;
+          c2 s;
+          if (kVec2) s = idx < p.window ? ldg_c2(xs + idx) : pk(0.f, 0.f);
+          else s = pk(idx < p.window ? __ldg(xs + idx) : 0.f, idx + 1 < p.window ? __ldg(xs + idx + 1) : 0.f);
+          v[fw][bitrev(n1, ilog2(R1))] = s;
+        }
       } else {
 #pragma unroll
-        for (int n1 = 0; n1 < R1; ++n1) v[n1] = pk(0.f, 0.f);
+        for (int n1 = 0; n1 < R1; ++n1) v[fw][n1] = pk(0.f, 0.f);
       }
-      DitP<R1, R1, 0>::run(v);
-      tww_chain<R1, 0>(v, tab4, lane, make_twp(tab4[lane]));
+    }
+  };
+  int64_t g = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+  if (g < groups) load_group(g);
+  for (; g < groups; g += gstep) {
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) v[fw][bitrev(n1, ilog2(R1))] = mul2(v[fw][bitrev(n1, ilog2(R1))], ldg_c2(p.win + 64 * n1 + 2 * lane));
+      DitP<R1, R1, 0>::run(v[fw]);
+      tww_chain<R1, 0>(v[fw], tab4, lane, make_twp(tab4[lane]));
       c2* xb = buf + fw * (R1 / 2) * kXStride;
 #pragma unroll
       for (int m = 0; m < R1 / 2; ++m)
-        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(v[fw][2 * m], v[fw][2 * m + 1]);
     }
     __syncwarp();
     c2 A[32];
@@ -611,6 +647,7 @@ __global__ void __launch_bounds__(WARPS * 32, 512 / (WARPS * 32)) stft_warp_kern
       for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = A[k2];
     }
     __syncwarp();
+    if (g + gstep < groups) load_group(g + gstep);  // in flight during the |X|^2 / peak phase
 #pragma unroll
     for (int fw = 0; fw < FPW; ++fw) {
       const int64_t frame = g * FPW + fw;
