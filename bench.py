@@ -52,37 +52,85 @@ def ncu_traffic(kernel: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML from a background
+    thread every 10 ms (nvidia-smi -lms answers too slowly for a 40 ms region); nvidia-smi as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = False
+        self._thread = None
+        self._smi = None
+        self._smi_file = None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
-                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                ids = [int(t) for t in vis.split(",")]
+                if self.index < len(ids):
+                    phys = ids[self.index]
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
         except Exception:
-            self.p = None
+            self._thread = None
+        try:
+            self._smi_file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self._smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self._smi_file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self._smi = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                           samples=len(self.samples), source="nvml, 10 ms period, warm-up + timed region")
             return out
-        self.p.terminate()
+        if self._smi is None:
+            return out
+        self._smi.terminate()
         try:
-            self.p.wait(timeout=5)
+            self._smi.wait(timeout=5)
         except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
+            self._smi.kill()
+        self._smi_file.flush()
+        self._smi_file.seek(0)
         sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            parts = [s.strip() for s in line.split(",")]
+        for line in self._smi_file.read().splitlines():
+            parts = [t.strip() for t in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
@@ -94,9 +142,10 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 100")
         try:
-            os.unlink(self.f.name)
+            os.unlink(self._smi_file.name)
         except OSError:
             pass
         return out

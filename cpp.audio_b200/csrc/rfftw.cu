@@ -11,6 +11,8 @@
 //            lane l takes k = l + 32*i, so the stores to HBM are coalesced and -i W_N^k = wpbase(l) * W_N^(32 i) needs one
 //            per-lane table entry and an immediate.
 // The kernel is HBM-bound by design: 4N bytes in, 8(N/2+1) bytes out per frame, ~0.06 instructions per byte.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -452,7 +454,13 @@ template <int MA>
 int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
   constexpr int M = MA * kRowLen;
   using C = CtaFftCfg<8>;
-  const size_t want = static_cast<size_t>(512) << 20;  // bounded work buffer: frames are processed in groups
+  // The work buffer is sized to stay resident in the 126 MB L2: the column pass leaves it there, the row pass transforms it
+  // in place and the untangling pass reads it back, so only the input and the output cross HBM (CA_FFT_GROUP_MB: sweep).
+  static const size_t group_mb = [] {
+    const char* e = getenv("CA_FFT_GROUP_MB");
+    return static_cast<size_t>(e ? std::max(1, atoi(e)) : 512);
+  }();
+  const size_t want = group_mb << 20;
   const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
   const size_t need = sizeof(float2) * M * static_cast<size_t>(group);
   if (ctx->fft_work_bytes < need) {
