@@ -45,8 +45,8 @@ void ca_destroy(ca_ctx* ctx) {
   stft_release(ctx);
   rfft_release(ctx);
   oscbank_release(ctx);
-  for (int i = 0; i < 8; ++i)
-    if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+  for (void* d : ctx->d_scratch)
+    if (d) cudaFree(d);
   for (int i = 0; i < 6; ++i)
     if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -39,8 +39,8 @@ struct ca_ctx {
   void* d_osc_voices = nullptr;    // VoiceParams[max_voices]
 
   // scratch for the *_host entry points
-  void* d_scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* d_scratch[12] = {};
+  size_t scratch_bytes[12] = {};
   // pinned host staging of the round trip (peak lists coming down, segments going up)
   void* h_pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t pinned_bytes[6] = {0, 0, 0, 0, 0, 0};

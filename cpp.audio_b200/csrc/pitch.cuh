@@ -1,0 +1,313 @@
+// pitch.cuh — the pitch pipeline of RtResynth::step (source/rt.resynth.lib.cpp:1670-1759) and the note bookkeeping of
+// synthesize_sounds (:264-382) as functions shared by the device kernels (pitch.cu) and the host A/B path (roundtrip.cu).
+//
+//   peaks of one frame --pitch_prefix()--> "tuned" list (stateless: source/rt.resynth.lib.algo.cpp:10-230)
+//   tuned list + played notes --tracking--> NoteOn / NoteChange / NoteOff  (algo.cpp:232-440, frame-sequential)
+//   sounding notes --emit_segment()--> one closed-form Segment per note and render tile (tracks.cuh)
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include <climits>
+
+#include "tracks.cuh"
+
+#ifdef __CUDACC__
+#define CA_HD __host__ __device__
+#else
+#define CA_HD
+#endif
+
+namespace ca {
+
+constexpr int kMaxNotes = 256;   // voice pool bound of the device pipeline (reference: 254 channels, rt.resynth.lib.cpp:201-210)
+constexpr int kMaxTuned = 256;   // peak capacity per frame of the device pipeline (reference reserve: 200, :1102)
+
+// Everything the pipeline needs, resolved once on the host.
+struct PitchParams {
+  int32_t W, hop, sr, P;       // P: entries per frame of the peak / tuned arrays
+  double bin_hz;
+  float nearby, min_volume, max_track, gain, stereo_spread;
+  int32_t A, H, D, R;          // AHDSREnvelopeBase::setAHDSR (include/audioelement.h:923-952)
+  float sustain;
+  double cap;                  // setMaxFilterIncrement(2/stride), source/rt.resynth.lib.cpp:106
+  double semitone;             // pow(2., 1./12.) as the host's libm evaluates it
+  double decay_full;           // exp(-pi * cap * hop): volume low-pass decay over a whole frame interval at the capped rate
+  int32_t max_channels;
+  int64_t n_samples, frames;
+};
+
+inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, int peak_stride) {
+  PitchParams p{};
+  p.W = prm.stft.window;
+  p.hop = prm.stft.hop;
+  p.sr = prm.stft.sample_rate;
+  p.P = peak_stride;
+  p.bin_hz = static_cast<double>(p.sr) / ca_fft_length_for(p.W, 1);
+  p.nearby = prm.nearby_distance_tones;
+  p.min_volume = prm.min_volume;
+  p.max_track = prm.max_track_pitches;
+  p.gain = prm.gain;
+  p.stereo_spread = prm.stereo_spread;
+  const int32_t min_dt = p.sr / 1000;
+  const bool has_decay = prm.env.sustain < 0.999999;
+  p.sustain = has_decay ? fminf(fmaxf(prm.env.sustain, 0.f), 1.f) : 1.f;
+  p.A = prm.env.attack > min_dt ? prm.env.attack : min_dt;
+  p.H = prm.env.hold > 0 ? prm.env.hold : 0;
+  p.D = has_decay ? (prm.env.decay > min_dt ? prm.env.decay : min_dt) : 0;
+  p.R = prm.env.release > min_dt ? prm.env.release : min_dt;
+  p.cap = 2.0 / p.hop;
+  p.semitone = pow(2., 1. / 12.);
+  p.decay_full = exp(-3.14159265358979323846 * (p.cap * p.hop));
+  p.max_channels = prm.max_channels;
+  p.n_samples = n_samples;
+  p.frames = frames;
+  return p;
+}
+
+// render tiles of one stream: the interval up to the next frame is one tile, or several when the hop exceeds kMaxTile
+inline int64_t tiles_per_stream(const PitchParams& p) {
+  int64_t t = 0;
+  for (int64_t k = 0; k < p.frames; ++k) {
+    const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
+    const int64_t len = p.hop < p.n_samples - n_k ? p.hop : p.n_samples - n_k;
+    t += len <= 0 ? 1 : (len + kMaxTile - 1) / kMaxTile;
+  }
+  return t;
+}
+
+CA_HD inline float hash_unit(uint64_t id, uint64_t salt) {  // SPEC S10
+  uint64_t z = id * 0x9E3779B97F4A7C15ull + salt * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
+}
+
+CA_HD inline int32_t min_change_for(double ai) {  // Enveloped::setAngleIncrements, include/audioelement.h:218-225
+  const double period = ai == 0.0 ? 1.0 : 2.0 / fabs(ai);
+  return static_cast<int32_t>(0.5f + 2.5 * period);
+}
+
+// One entry of the list the stateless prefix of the pipeline produces for a frame, with the event parameters that follow
+// from it (synthesize_sounds, source/rt.resynth.lib.cpp:264-382) already evaluated.
+struct __align__(16) Tuned {
+  double pitch;        // midi pitch (tracking key)
+  double vol;          // summed volume of the aggregated peaks
+  double ai;           // angle increment of the note frequency (freq_to_angle_increment evaluated in float)
+  float volume;        // event volume: gain * vol / 0.1
+  int32_t min_change;  // min_change_for(ai)
+};
+
+// Peaks of one frame (ascending frequency) -> tuned list. Returns the number of entries written to `out` (<= cnt).
+//   freq -> midi pitch 69 + 12 log2(f/440) (include/midi.h:226-231), dB -> volume 10^(dB/20);
+//   aggregation of peaks closer than nearby_distance_tones (interval diameter), volume-weighted pitch, summed volume,
+//   min_volume cut (source/rt.resynth.lib.algo.cpp:10-230); entries that land on the same pitch are merged.
+CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
+                              Tuned* out) {
+  int T = 0;
+  bool open = false;
+  double mn = 0, mx = 0, sv = 0, spv = 0;
+  auto close = [&] {
+    if (open && !(sv < p.min_volume)) {
+      const double pitch = spv / sv;
+      if (T > 0 && fabs(out[T - 1].pitch - pitch) < 0.0001f) out[T - 1].vol += sv;
+      else {
+        out[T].pitch = pitch;
+        out[T].vol = sv;
+        ++T;
+      }
+    }
+    open = false;
+  };
+  for (int i = 0; i < cnt; ++i) {
+    const double freq = (static_cast<double>(peak_bin[i]) + static_cast<double>(peak_off[i])) * p.bin_hz;
+    if (!(freq > 0)) continue;
+    const double pitch = 69. + 12. * log2(freq / 440.f);
+    const double vol = pow(10.0, static_cast<double>(peak_db[i]) / 20.0);
+    if (open && fmax(fmax(mn, mx), pitch) - fmin(fmin(mn, mx), pitch) > p.nearby) close();
+    if (!open) {
+      open = true;
+      mn = mx = pitch;
+      sv = spv = 0;
+    } else {
+      mn = fmin(mn, pitch);
+      mx = fmax(mx, pitch);
+    }
+    sv += vol;
+    spv += pitch * vol;
+  }
+  close();
+  for (int i = 0; i < T; ++i) {
+    const float new_freq = static_cast<float>(440.f * pow(p.semitone, out[i].pitch - 69.));
+    out[i].volume = static_cast<float>(p.gain * out[i].vol / 0.1f);
+    out[i].ai = static_cast<double>(2 * new_freq / p.sr);  // freq_to_angle_increment in float
+    out[i].min_change = min_change_for(out[i].ai);
+  }
+  return T;
+}
+
+struct Note {
+  int64_t id = 0;
+  double pitch = 0;      // current midi pitch (tracking key)
+  Glide glide;
+  double phase = 0;      // units of pi rad, [0,2)
+  double f_last = 0;     // last emitted increment
+  double vol_x = 0, vol_y = 0;
+  int64_t n_on = 0;
+  int32_t attack = 0, hold = 0, decay = -1, release = 0;
+  int32_t next_min_change = 0;
+  int64_t n_off = -1;    // sample of the first release step
+  double top = 0;
+  float gl = 1, gr = 1;
+  bool tracked = true;   // still in played_pitches
+};
+
+CA_HD inline double env_pressed_value(const Note& n, int64_t c, float sustain) {
+  if (c < 1) return 0.0;
+  if (c <= n.attack) return static_cast<double>(c) / n.attack;
+  c -= n.attack;
+  if (c <= n.hold) return 1.0;
+  c -= n.hold;
+  const int32_t d = n.decay < 0 ? 0 : n.decay;
+  if (c <= d) return 1.0 + (static_cast<double>(sustain) - 1.0) * static_cast<double>(c) / d;
+  return sustain;
+}
+
+// NoteOff -> onKeyReleased(0), include/audioelement.h:769-781, :836-841
+CA_HD inline void note_off(const PitchParams& p, Note& n, int64_t n_k) {
+  n.tracked = false;
+  n.n_off = n_k;
+  n.top = env_pressed_value(n, n_k - n.n_on, p.sustain);
+  n.release = n.next_min_change > p.R ? n.next_min_change : p.R;
+}
+
+// NoteChange, include/gen.crtp.h:595-618
+CA_HD inline void note_change(const PitchParams& p, Note& n, const Tuned& t) {
+  n.pitch = t.pitch;
+  n.vol_x = static_cast<double>(0.1f * t.volume);
+  n.next_min_change = t.min_change;
+  n.glide.start(n.f_last, t.ai, p.hop);  // InterpolatedFreq::setAngleIncrements, include/audioelement.h:2752-2762
+}
+
+// NoteOn (include/gen.crtp.h:382-594; start phase and pan from a hash of the note id, SPEC S10)
+CA_HD inline Note note_on(const PitchParams& p, const Tuned& t, int64_t id, int64_t n_k) {
+  Note n;
+  n.id = id;
+  n.pitch = t.pitch;
+  n.vol_x = n.vol_y = static_cast<double>(0.1f * t.volume);
+  n.n_on = n_k;
+  n.next_min_change = t.min_change;
+  n.attack = n.next_min_change > p.A ? n.next_min_change : p.A;
+  n.hold = p.H;
+  n.decay = -1;
+  n.glide.start(t.ai, t.ai, p.hop);
+  n.f_last = t.ai;
+  double a0 = static_cast<double>(hash_unit(static_cast<uint64_t>(id), 2));
+  a0 -= 2.0 * floor(0.5 * a0);
+  n.phase = a0;
+  double pan = static_cast<double>(p.stereo_spread * hash_unit(static_cast<uint64_t>(id), 1));
+  pan = fmin(1.0, fmax(-1.0, pan));
+  n.gl = static_cast<float>(cos(0.25 * 3.14159265358979323846 * (pan + 1.0)));
+  n.gr = static_cast<float>(sin(0.25 * 3.14159265358979323846 * (pan + 1.0)));
+  return n;
+}
+
+// a released note leaves the pool once its envelope reached Done2: release steps + 16 more (include/audioelement.h:738-749)
+CA_HD inline bool note_done(const Note& n, int64_t n_next) { return n.n_off >= 0 && n_next >= n.n_off + n.release + 17; }
+
+// The closed-form description of note `n` over the tile [n_k_tile, n_k_tile + len) and the note state after it.
+CA_HD inline Segment emit_segment(const PitchParams& p, Note& n, int64_t n_k_tile, int len) {
+  Segment g{};
+  const double cap = p.cap;
+  const int64_t i0 = n.glide.i;
+  g.phase_start = n.phase;
+  g.from = n.glide.from;
+  g.to = n.glide.to;
+  g.K = n.glide.K;
+  g.L = n.glide.L;
+  g.c1 = n.glide.c1;
+  g.P_m1 = n.glide.P_m1;
+  g.m = n.glide.m;
+  g.i0 = static_cast<int32_t>(i0 < INT_MAX / 2 ? i0 : INT_MAX / 2);
+  const double P_before = n.glide.P(i0 - 1);
+  g.P_before = P_before;
+  if (i0 >= n.glide.m) {  // steady for the whole tile: re-base so that the step index stays small
+    g.i0 = 0;
+    g.m = 0;
+    g.P_m1 = 0;  // P(-1)
+    g.P_before = 0;
+  }
+  // volume regime over the tile
+  const double fa = n.glide.f_at(i0), fb = n.glide.f_at(i0 + len - 1);
+  g.cap = static_cast<float>(cap);
+  g.vol_x = static_cast<float>(n.vol_x);
+  g.vol_dy = static_cast<float>(n.vol_y - n.vol_x);
+  double mv_end;
+  bool full_cap = false;  // capped rate over a whole frame interval: the decay factor is a constant of the run
+  const double adv_end = n.glide.P(i0 + len - 1) - P_before;
+  if (fmin(fa, fb) >= cap) {
+    g.regime = 0;
+    mv_end = cap * len;
+    full_cap = len == p.hop;
+  } else if (fmax(fa, fb) < cap) {
+    g.regime = 1;
+    mv_end = adv_end;
+  } else {
+    // the glide crosses the cap inside the tile: first step on the other side of it (f is monotone along a glide, so the
+    // steps on the starting side form a prefix and a bisection finds its length)
+    const bool f_first = fa < cap;
+    int lo = 0, hi = len - 1;  // invariant: step lo is on the starting side, step hi is not
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((n.glide.f_at(i0 + mid) < cap) == f_first) lo = mid;
+      else hi = mid;
+    }
+    const int istar = hi;
+    g.istar = istar;
+    const double adv_star = n.glide.P(i0 + istar - 1) - P_before;
+    if (f_first) {
+      g.regime = 2;
+      g.m_star = static_cast<float>(adv_star);
+      mv_end = adv_star + cap * (len - istar);
+    } else {
+      g.regime = 3;
+      g.m_star = static_cast<float>(cap * istar - adv_star);
+      mv_end = cap * istar + (adv_end - adv_star);
+    }
+  }
+  // envelope
+  g.c0 = static_cast<int32_t>(n_k_tile - n.n_on + 1);
+  if (n.decay < 0 && (n_k_tile + len - n.n_on) > static_cast<int64_t>(n.attack) + n.hold)  // decay latched when entered
+    n.decay = p.D == 0 ? 0 : (n.next_min_change > p.D ? n.next_min_change : p.D);
+  g.attack = n.attack;
+  g.hold = n.hold;
+  g.decay = n.decay < 0 ? 0 : n.decay;
+  g.sustain = p.sustain;
+  g.release = n.release > 0 ? n.release : 1;
+  const int64_t rb = n.n_off - n_k_tile;
+  g.rel_base = n.n_off < 0 ? INT_MAX : static_cast<int32_t>(rb > -(1ll << 30) ? rb : -(1ll << 30));
+  g.top = static_cast<float>(n.top);
+  g.gl = n.gl;
+  g.gr = n.gr;
+  // advance
+  n.phase += adv_end;
+  n.phase -= 2.0 * floor(0.5 * n.phase);
+  n.f_last = fb;
+  n.glide.i = i0 + len;
+  n.vol_y = n.vol_x + (n.vol_y - n.vol_x) * (full_cap ? p.decay_full : exp(-3.14159265358979323846 * mv_end));
+  return g;
+}
+
+}  // namespace ca
+
+struct ca_ctx;
+namespace ca {
+// pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track_kernel, one warp per stream)
+int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const float* d_peak_off,
+                          const float* d_peak_db, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
+                          int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
+                          int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
+                          int32_t* d_overflow, bool run_prefix, cudaStream_t st);
+}  // namespace ca

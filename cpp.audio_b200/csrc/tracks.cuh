@@ -38,12 +38,13 @@ struct __align__(8) Segment {
 
 struct TileArgs {
   const Segment* segs;
-  const int64_t* tile_seg_begin;  // [tiles+1] CSR into segs
+  const int64_t* tile_seg_begin;  // [tiles+1] CSR into segs ([tiles] when tile_seg_end is given)
   const int64_t* tile_sample0;    // [tiles] first output sample (absolute index into out / 2)
   const int32_t* tile_len;        // [tiles]
   int64_t n_tiles;
   float* out;                     // interleaved stereo (mono for tracks_kernel<true>)
   int32_t accumulate;             // mono only: atomicAdd into out (tiles of different voices overlap) instead of storing
+  const int64_t* tile_seg_end = nullptr;  // [tiles] one past the last segment of each tile; null: tile_seg_begin[tile + 1]
 };
 
 __device__ __forceinline__ float alias_gain(float ai) {  // freqAliasingMultiplicator, include/audioelement.h:466-483
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(128) tracks_kernel(const __grid_constant__ Til
   const int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (tile >= a.n_tiles) return;
   const int len = a.tile_len[tile];
-  const int64_t s_begin = a.tile_seg_begin[tile], s_end = a.tile_seg_begin[tile + 1];
+  const int64_t s_begin = a.tile_seg_begin[tile], s_end = a.tile_seg_end ? a.tile_seg_end[tile] : a.tile_seg_begin[tile + 1];
   float2* out = reinterpret_cast<float2*>(a.out) + (kMono ? 0 : a.tile_sample0[tile]);
   float* out1 = a.out + (kMono ? a.tile_sample0[tile] : 0);
   for (int j0 = 0; j0 < len; j0 += 32) {
@@ -128,11 +129,27 @@ __global__ void __launch_bounds__(128) tracks_kernel(const __grid_constant__ Til
 // InterpolatedFreq / LogRamp in closed form: the control's position obeys cur' = (1+lambda)*cur + beta (it advances by
 // C*f with f linear in cur), so cur_i = beta*(alpha^i - 1)/lambda and the emitted value and its running sum are
 // exponentials of the step index.
+// 1/x to the last bit or two: hardware seed + two Newton steps on the device (~100 clocks instead of ~320)
+__host__ __device__ inline double rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+#else
+  return 1.0 / x;
+#endif
+}
+
 struct Glide {  // InterpolatedFreq in closed form
   double from = 0, to = 0, K = 0, L = 0, c1 = 0, P_m1 = 0;
   int32_t m = 0;   // first clamped step
   int64_t i = 0;   // next glide step index
-  void start(double from_, double to_, double dur) {
+  __host__ __device__ void start(double from_, double to_, double dur) {
     from = from_;
     to = to_;
     i = 0;
@@ -141,24 +158,37 @@ struct Glide {  // InterpolatedFreq in closed form
       K = L = c1 = P_m1 = 0;
       return;
     }
+    // Reference constants (:2783-2784, :2815): C = -log(from/to)/delta, cur' = (1+lambda)*cur + beta with lambda = C*delta/dur,
+    // beta = C*(from + delta/(2 dur)); the first clamped step is the first i with cur_i + .5 > dur, cur_i = beta*(alpha^i-1)/lambda.
+    // Arranged for the device: a correctly rounded FP64 division costs as much as a log() there (~320 clocks, measured), so
+    // quotients become products with reciprocals, and lambda*(dur-.5)/beta = (dur-.5)*delta/(dur*from + delta/2) is formed
+    // without the logarithm so that the two logarithm chains are independent.
     const double delta = to - from;
-    const double C = -log(from / to) / delta;            // :2815
-    const double lambda = C * delta / dur;               // cur' = (1+lambda)*cur + beta
-    const double beta = C * (from + 0.5 * delta / dur);  // :2783-2784
-    K = delta * beta / (dur * lambda);
+    const double inv_dur = rcp(dur);
+    const double lg = log1p(-delta * rcp(to));  // log(from/to); never 0 for from != to, however close
+    const double t = (dur - 0.5) * delta * rcp(dur * from + 0.5 * delta);
+    const double lt = log1p(t);
+    const double C = -lg * rcp(delta);
+    const double lambda = -lg * inv_dur;
+    const double beta = C * (from + 0.5 * delta * inv_dur);
+    const double inv_lambda = rcp(lambda);
+    K = delta * beta * inv_dur * inv_lambda;
     L = log1p(lambda);
-    c1 = K / lambda;
-    // first step whose cur + .5 exceeds dur (:2768-2770): cur_i = beta*(alpha^i - 1)/lambda
-    const double x = log1p(lambda * (dur - 0.5) / beta) / L;
+    c1 = K * inv_lambda;
+    const double x = lt * rcp(L);
     double mf = floor(x) + 1.0;
     if (mf < 1.0) mf = 1.0;
     if (mf > 1e9) mf = 1e9;
     m = static_cast<int32_t>(mf);
-    P_m1 = P(m - 1);
+    P_m1 = static_cast<double>(m) * (from - K) + c1 * expm1(L * static_cast<double>(m));  // P(m - 1)
   }
-  double f_at(int64_t k) const { return k < m ? from + K * expm1(L * static_cast<double>(k)) : to; }
-  double P(int64_t k) const {  // sum of f over steps 0..k
+  __host__ __device__ double f_at(int64_t k) const {
+    if (k >= m) return to;
+    return k == 0 ? from : from + K * expm1(L * static_cast<double>(k));  // expm1(0) == 0
+  }
+  __host__ __device__ double P(int64_t k) const {  // sum of f over steps 0..k
     if (k < 0) return 0.0;
+    if (k == m - 1) return P_m1;  // the same expression, evaluated by start()
     if (k < m) return static_cast<double>(k + 1) * (from - K) + c1 * expm1(L * static_cast<double>(k + 1));
     return P_m1 + static_cast<double>(k - m + 1) * to;
   }

@@ -63,3 +63,65 @@ def test_reference_default_window_and_stride(pkg, orc, ctx, wl):
     assert np.array_equal(stats, rstats) and stats[:, 0].min() >= 8
     assert np.abs(ref).max() > 0.1
     assert np.abs(out - ref).max() < 2e-5
+
+
+# ---- the pitch pipeline on the device (csrc/pitch.cu) against its host form (host_threads != 0 selects the host form) ----
+
+def _both(pkg, ctx, x, **kw):
+    dev, dstats = pkg.resynth_roundtrip(ctx, x, host_threads=0, **kw)
+    host, hstats = pkg.resynth_roundtrip(ctx, x, host_threads=-1, **kw)
+    return dev, dstats, host, hstats
+
+
+def test_device_pitch_pipeline_matches_host_form(pkg, ctx, wl):
+    x = wl.c4_streams(3, 1.5)
+    dev, dstats, host, hstats = _both(pkg, ctx, x)
+    assert np.array_equal(dstats, hstats) and dstats[:, 0].min() >= 16
+    assert np.abs(host).max() > 0.1
+    assert np.abs(dev - host).max() < 2e-6     # same formulas; libm vs CUDA math differ in the last bits only
+
+
+def test_device_pitch_pipeline_dense_spectrum(pkg, orc, ctx):
+    """120 partials, a quarter of them switching on and off: more than 32 tuned entries and notes per frame (the loops over
+    lane groups), competing matches (the serial fallback), more than 48 sounding notes per tile (segment buffer retry),
+    notes that die (pool compaction) and a pool limit below the demand (drops)."""
+    sr, n = 48000, 40000
+    rng = np.random.default_rng(77)
+    t = np.arange(n) / sr
+    x = np.zeros(n)
+    for h in range(120):
+        f = 130.0 * (h + 1) ** 0.93 + rng.uniform(-3, 3)
+        amp = 0.3 / (1 + 0.05 * h)
+        gate = 1.0
+        if h % 4 == 1:
+            gate = ((t * (3 + h % 5)) % 1.0) < 0.6
+        vib = 1.0 + 0.004 * np.sin(2 * np.pi * (2 + h % 3) * t)
+        x += amp * gate * np.sin(2 * np.pi * f * t * vib + rng.uniform(0, 6))
+    x = (x / np.abs(x).max() * 0.9).astype(np.float32)[None, :]
+    dev, dstats, host, hstats = _both(pkg, ctx, x, nearby_distance_tones=0.05, max_track_pitches=0.3)
+    assert np.array_equal(dstats, hstats)
+    assert dstats[0, 0] > 120 and dstats[0, 1] == 0
+    assert np.abs(dev - host).max() < 5e-6
+    dev1, dstats1 = pkg.resynth_roundtrip(ctx, x)             # reference defaults: checked against the oracle
+    ref, rstats = orc.roundtrip(x)
+    assert np.array_equal(dstats1, rstats)
+    assert np.abs(dev1 - ref).max() < 5e-5
+    dev2, dstats2, host2, hstats2 = _both(pkg, ctx, x, nearby_distance_tones=0.05, max_track_pitches=0.3, max_channels=40)
+    assert np.array_equal(dstats2, hstats2) and dstats2[0, 1] > 0
+    assert np.abs(dev2 - host2).max() < 5e-6
+
+
+def test_device_pitch_pipeline_wide_tracking_window(pkg, ctx, wl):
+    # a tracking window wider than the spacing of the partials makes neighbouring entries compete for the same played note
+    x = wl.c4_streams(2, 1.0)
+    dev, dstats, host, hstats = _both(pkg, ctx, x, max_track_pitches=9.0)
+    assert np.array_equal(dstats, hstats)
+    assert np.abs(dev - host).max() < 2e-6
+
+
+def test_device_pitch_pipeline_limits(pkg, ctx):
+    x = np.zeros((1, 8192), np.float32)
+    with pytest.raises(Exception):
+        pkg.resynth_roundtrip(ctx, x, max_peaks=300)
+    with pytest.raises(Exception):
+        pkg.resynth_roundtrip(ctx, x, max_channels=300)
