@@ -192,16 +192,36 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
       lap("pitch pipeline (device)");
     }
     CA_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scratch[7], 0, out_bytes, st));  // samples before the first frame are silent
-    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin, d_s0, d_len, n_tiles, static_cast<float*>(ctx->d_scratch[7]), 0, d_end};
-    tracks_kernel<false><<<static_cast<unsigned>((n_tiles + 3) / 4), 128, 0, st>>>(ta);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    // Rendering and the copy of the audio overlap: the streams are rendered in groups, and each group's audio leaves on the
+    // second stream while the next group renders.
+    const int groups = timing ? 1 : static_cast<int>(std::min<int64_t>(4, n_streams));
+    cudaStream_t st2 = ctx->own_stream2;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int g = 0; g < groups; ++g) {
+      const int64_t s0 = n_streams * g / groups, s1 = n_streams * (g + 1) / groups;
+      const int64_t t0 = s0 * tps, nt = (s1 - s0) * tps;
+      TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin + t0, d_s0 + t0, d_len + t0, nt, static_cast<float*>(ctx->d_scratch[7]), 0, d_end + t0};
+      tracks_kernel<false><<<static_cast<unsigned>((nt + 3) / 4), 128, 0, st>>>(ta);
+      CA_CUDA_OK(ctx, cudaGetLastError());
+      ctx->launches += 1;
+      if (groups > 1) {
+        CA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+        CA_CUDA_OK(ctx, cudaEventRecord(ev[g], st));
+        CA_CUDA_OK(ctx, cudaStreamWaitEvent(st2, ev[g], 0));
+        const size_t o0 = sizeof(float) * 2 * static_cast<size_t>(s0) * n_samples, o1 = sizeof(float) * 2 * static_cast<size_t>(s1) * n_samples;
+        CA_CUDA_OK(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(h_out) + o0, static_cast<char*>(ctx->d_scratch[7]) + o0, o1 - o0,
+                                        cudaMemcpyDeviceToHost, st2));
+      }
+    }
     if (timing) {
       CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
       lap("tracks kernel");
     }
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], out_bytes, cudaMemcpyDeviceToHost, st));
+    if (groups == 1) CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], out_bytes, cudaMemcpyDeviceToHost, st));
     CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    if (groups > 1) CA_CUDA_OK(ctx, cudaStreamSynchronize(st2));
+    for (int g = 0; g < groups; ++g)
+      if (ev[g]) cudaEventDestroy(ev[g]);
     lap("D2H output");
     const int64_t needed = h_misc[2 * n_streams];
     const int32_t overflow = *reinterpret_cast<const int32_t*>(h_misc + 2 * n_streams + 1);
