@@ -496,6 +496,192 @@ int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cuda
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// N >= 65536, two passes through HBM (default): M = N/2 = MA x 1024 complex points, n = 1024*r + c, k = kA + MA*k2.
+//   pass 1  big2_cols_kernel: a CTA takes 16 adjacent columns c (128-byte runs in HBM) and all MA rows: MA = A x B point FFT
+//           down each column in two register stages with one shared-memory exchange, twiddle W_M^(c*kA), work[kA][c]
+//   pass 2  big2_rows_kernel: a CTA takes 8 adjacent rows kA, the 8 mirrored rows MA - kA (and row MA/2 in the last CTA of a
+//           frame): one warp per row runs the 1024-point warp-level FFT in shared memory, then the whole CTA untangles
+//           X[k], X[M-k] from the two row sets and writes them in runs of 8 consecutive bins (64 bytes)
+// 32M bytes moved for 16M algorithmic: the ceiling is half of the HBM roofline (the three-pass path above: a third).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBig2Row = 1024;
+
+// CW: columns per CTA (CW*8-byte runs in HBM)
+template <int A, int B, int CW>
+__global__ void __launch_bounds__(256) big2_cols_kernel(const float2* __restrict__ zin, float2* __restrict__ work) {
+  constexpr int MA = A * B, R = kBig2Row, M = MA * R, QT = 256 / CW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c2* u = reinterpret_cast<c2*>(smem_raw);  // [A][B][CW]: element (k1, r2, column)
+  const int t = threadIdx.x, cl = t % CW, q = t / CW;
+  const int c = blockIdx.x * CW + cl;
+  const c2* src = reinterpret_cast<const c2*>(zin) + static_cast<int64_t>(blockIdx.y) * M + c;
+  c2* dst = reinterpret_cast<c2*>(work) + static_cast<int64_t>(blockIdx.y) * M + c;
+  // ---- stage 1: r = B*r1 + r2; A-point FFT over r1 for every (column, r2), twiddle W_MA^(r2*k1) ----
+  for (int r2 = q; r2 < B; r2 += QT) {
+    c2 v[A];
+#pragma unroll
+    for (int r1 = 0; r1 < A; ++r1) v[bitrev(r1, ilog2(A))] = __ldg(src + static_cast<int64_t>(B * r1 + r2) * R);
+    DitP<A, A, 0>::run(v);
+    if (r2 != 0) {
+      c2 w[A];
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(r2) / MA, &sn, &cs);
+      w[1] = pk(cs, -sn);
+      if constexpr (A > 2) cpow_all<A>(w, std::make_integer_sequence<int, A - 2>{});
+#pragma unroll
+      for (int k1 = 1; k1 < A; ++k1) {
+        const float2 a = upk(w[k1]);
+        v[k1] = cmul_tw(v[k1], TwP{a.x, pk(-a.y, a.y)});
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) u[(k1 * B + r2) * CW + cl] = v[k1];
+  }
+  __syncthreads();
+  // ---- stage 2: B-point FFT over r2 for every (column, k1): Y[k1 + A*k2], twiddle W_M^(c*(k1 + A*k2)) ----
+  for (int k1 = q; k1 < A; k1 += QT) {
+    c2 y[B];
+#pragma unroll
+    for (int r2 = 0; r2 < B; ++r2) y[bitrev(r2, ilog2(B))] = u[(k1 * B + r2) * CW + cl];
+    DitP<B, B, 0>::run(y);
+    c2 pw[B];  // pw[j] = W_M^(c*A*j) by binary powers (depth <= log2 B)
+    {
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(c * A) / M, &sn, &cs);  // exact argument: c*A < 2^15, M a power of two
+      pw[1] = pk(cs, -sn);
+    }
+    if constexpr (B > 2) cpow_all<B>(pw, std::make_integer_sequence<int, B - 2>{});
+    TwP base;
+    {
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(c * k1) / M, &sn, &cs);
+      base = TwP{cs, pk(sn, -sn)};  // W_M^(c*k1) = (cs, -sn) in the (wr, (-wi, wi)) form
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < B; ++k2) {
+      c2 val = cmul_tw(y[k2], base);
+      if (k2) {
+        const float2 a = upk(pw[k2]);
+        val = cmul_tw(val, TwP{a.x, pk(-a.y, a.y)});
+      }
+      dst[static_cast<int64_t>(k1 + A * k2) * R] = val;
+    }
+  }
+}
+
+// G: adjacent rows per CTA (G*8-byte runs in HBM)
+template <int MA, int G>
+__global__ void __launch_bounds__(32 * (2 * G + 1)) big2_rows_kernel(const float2* __restrict__ work, float2* __restrict__ out) {
+  constexpr int R = kBig2Row, M = MA * R, CPF = MA / (2 * G), T = 32 * (2 * G + 1);
+  constexpr int kRowC2 = 16 * kXStride + 2;  // = 2 (mod 16): 8 rows x 2 consecutive k2 cover the 32 banks once (G = 8)
+  constexpr int kTabRows = 7 + 3;            // row-FFT tables: wb[1..7], wa[1..3] (WarpFftCfg<32>)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  c2* rows = reinterpret_cast<c2*>(tab4 + kTabRows * 32);  // [2G+1][kRowC2]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t frame = blockIdx.x / CPF;
+  const int cc = blockIdx.x % CPF;
+  for (int i = t; i < kTabRows * 32; i += T) {
+    const int r = i >> 5, l = i & 31;
+    const float2 w = r < 7 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / R) : cis_neg_w(2.f * static_cast<float>(l * 8 * (r - 6)) / R);
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  // slot -> row of the frame: [0, G) the CTA's own rows, [G, 2G) their mirrors MA - kA, 2G the self-paired row MA/2
+  int kA_row;
+  bool valid = true;
+  if (warp < G) kA_row = cc * G + warp;
+  else if (warp < 2 * G) {
+    kA_row = (MA - cc * G - (warp - G)) & (MA - 1);
+    valid = !(cc == 0 && warp == G);  // row 0 pairs with itself (slot 0)
+  } else {
+    kA_row = MA / 2;
+    valid = cc == CPF - 1;
+  }
+  c2 v[32];
+  if (valid) {
+    const c2* src = reinterpret_cast<const c2*>(work) + frame * M + static_cast<int64_t>(kA_row) * R;
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = __ldg(src + 32 * n1 + lane);
+  }
+  __syncthreads();  // tables ready
+  if (valid) {      // 1024 = 32 x 32 point FFT of the row, warp-level (as step B of rfft_cta_kernel)
+    c2* row = rows + warp * kRowC2;
+    DitP<32, 32, 0>::run(v);
+    tww_chain<32, 0>(v, tab4, lane, make_twp(tab4[lane]));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) *reinterpret_cast<ulonglong2*>(row + m * kXStride + 2 * lane) = make_ulonglong2(v[2 * m], v[2 * m + 1]);
+    __syncwarp();
+    c2 Acol[32];
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) Acol[bitrev(n2, 5)] = row[(lane >> 1) * kXStride + 2 * n2 + (lane & 1)];
+    __syncwarp();
+    DitP<32, 32, 0>::run(Acol);
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = Acol[k2];  // Z[kA + MA*k2] at position k2
+  }
+  __syncthreads();
+  // ---- untangle: X[k] and X[M-k], k = kA + MA*k2; consecutive threads take consecutive kA ----
+  float2* o = out + frame * (M + 1);
+  auto emit = [&](int64_t k, c2 zk, c2 zm) {
+    float sn, cs;
+    sincospif(static_cast<float>(k) / M, &sn, &cs);      // W_N^k = exp(-i pi k / M); k < 2^24: exact argument
+    const TwP wp{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};  // 0.5 * (-i) * W_N^k
+    const c2 E = add2(zk, cconj(zm));
+    const c2 Tt = cmul_tw(csub(zk, cconj(zm)), wp);
+    o[k] = upk(fma2(bc(0.5f), E, Tt));
+    o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
+  };
+  for (int item = t; item < G * R; item += T) {
+    const int i = item & (G - 1), k2 = item / G;
+    const int kA = cc * G + i;
+    if (kA == 0) {  // M - k = MA*(R - k2): the same row
+      if (k2 > R / 2) continue;
+      emit(static_cast<int64_t>(MA) * k2, rows[k2], rows[(R - k2) & (R - 1)]);
+    } else {        // M - k = (MA - kA) + MA*(R - 1 - k2)
+      emit(kA + static_cast<int64_t>(MA) * k2, rows[i * kRowC2 + k2], rows[(G + i) * kRowC2 + R - 1 - k2]);
+    }
+  }
+  if (cc == CPF - 1) {  // kA = MA/2: M - k = MA/2 + MA*(R - 1 - k2)
+    const c2* rs = rows + 2 * G * kRowC2;
+    for (int k2 = t; k2 < R / 2; k2 += T) emit(MA / 2 + static_cast<int64_t>(MA) * k2, rs[k2], rs[R - 1 - k2]);
+  }
+}
+
+template <int A, int B, int CW, int G>
+int launch_big2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
+  constexpr int MA = A * B, M = MA * kBig2Row;
+  static_assert(MA % (2 * G) == 0, "rows per frame must split into CTAs of 2G rows");
+  const size_t want = static_cast<size_t>(512) << 20;  // bounded work buffer: frames are processed in groups
+  const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
+  const size_t need = sizeof(float2) * M * static_cast<size_t>(group);
+  if (ctx->fft_work_bytes < need) {
+    if (ctx->d_fft_work) cudaFree(ctx->d_fft_work);
+    ctx->d_fft_work = nullptr;
+    ctx->fft_work_bytes = 0;
+    CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_fft_work, need));
+    ctx->fft_work_bytes = need;
+  }
+  auto cols = big2_cols_kernel<A, B, CW>;
+  auto rowsk = big2_rows_kernel<MA, G>;
+  const size_t smem_cols = sizeof(c2) * MA * CW;
+  const size_t smem_rows = sizeof(float4) * 10 * 32 + sizeof(c2) * (16 * kXStride + 2) * (2 * G + 1);
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(rowsk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+  for (int64_t b0 = 0; b0 < batch; b0 += group) {
+    const int64_t nb = std::min(group, batch - b0);
+    const float2* zin = reinterpret_cast<const float2*>(d_in) + b0 * M;
+    float2* out = reinterpret_cast<float2*>(d_out) + b0 * (M + 1);
+    cols<<<dim3(kBig2Row / CW, static_cast<unsigned>(nb)), 256, smem_cols, stream>>>(zin, ctx->d_fft_work);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    rowsk<<<static_cast<unsigned>(nb * (MA / (2 * G))), 32 * (2 * G + 1), smem_rows, stream>>>(ctx->d_fft_work, out);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+  }
+  return CA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
 // Fused analysis (window -> real FFT -> |X|^2 -> peaks) for the FFT lengths other than 4096: the transforms above with
 // the window applied on load and the untangling step producing |X|^2 (HBM row + a shared-memory copy) instead of complex
 // bins; the peak list is extracted from the shared-memory copy exactly as in stft.cu (strict local maxima above the
@@ -1148,9 +1334,20 @@ int launch_icta(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, flo
   return CA_OK;
 }
 
+// tile shapes of the two-pass path (CA_FFT_CW = 16|32 columns per CTA in pass 1, CA_FFT_G = 4|8 rows per CTA in pass 2;
+// defaults from profiles/fft_tiles_sweep_r01.txt: the shapes differ by a few percent only, every one moves ~5.3 TB/s)
+template <int A, int B>
+int big2_variant(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
+  static const int cw = [] { const char* e = getenv("CA_FFT_CW"); return e ? atoi(e) : (A * B <= 64 ? 32 : 16); }();
+  static const int g = [] { const char* e = getenv("CA_FFT_G"); return e ? atoi(e) : (A * B <= 64 ? 4 : 8); }();
+  if (cw == 32 && A * B < 512) return g == 4 ? launch_big2<A, B, 32, 4>(ctx, d_in, batch, d_out, stream) : launch_big2<A, B, 32, 8>(ctx, d_in, batch, d_out, stream);
+  return g == 4 ? launch_big2<A, B, 16, 4>(ctx, d_in, batch, d_out, stream) : launch_big2<A, B, 16, 8>(ctx, d_in, batch, d_out, stream);
+}
+
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
+  static const bool three_pass = getenv("CA_FFT_THREE_PASS") != nullptr;  // N >= 65536: the previous path, for A/B
   switch (n_fft) {
     case 1024: return launch_warp<16, 8>(ctx, d_in, batch, d_out, stream);
     case 2048: return launch_warp<32, 8>(ctx, d_in, batch, d_out, stream);
@@ -1158,11 +1355,11 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
     case 32768: return launch_cta<16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 16: return launch_big<4>(ctx, d_in, batch, d_out, stream);
-    case 1 << 17: return launch_big<8>(ctx, d_in, batch, d_out, stream);
-    case 1 << 18: return launch_big<16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 19: return launch_big<32>(ctx, d_in, batch, d_out, stream);
-    case 1 << 20: return launch_big<64>(ctx, d_in, batch, d_out, stream);
+    case 1 << 16: return three_pass ? launch_big<4>(ctx, d_in, batch, d_out, stream) : big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 17: return three_pass ? launch_big<8>(ctx, d_in, batch, d_out, stream) : big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 18: return three_pass ? launch_big<16>(ctx, d_in, batch, d_out, stream) : big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 19: return three_pass ? launch_big<32>(ctx, d_in, batch, d_out, stream) : big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 20: return three_pass ? launch_big<64>(ctx, d_in, batch, d_out, stream) : big2_variant<32, 16>(ctx, d_in, batch, d_out, stream);
     default: break;
   }
   return fail(ctx, CA_ERR_UNSUPPORTED, "rfft_warp: unsupported n_fft");
