@@ -270,6 +270,8 @@ __global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* in, floa
     sincospif(static_cast<float>(t) / M, &s, &c);  // W_N^t
     wpb = TwP{-0.5f * s, pk(0.5f * c, -0.5f * c)};  // 0.5 * (-i) * W_N^t = (-s, -c)/2 in the (wr, (-wi, wi)) form
   }
+  // (Tried: requesting the CTA's next frame before the untangling / store phase, 32 packed values per thread held in
+  // registers. It spills at 128 registers and measured 5-12 % slower at all three lengths, profiles/fft_prefetch_sweep_r01.txt.)
   for (int64_t frame = blockIdx.x; frame < batch; frame += gridDim.x) {
     const float* x = in + frame * (2 * M);
     __syncthreads();  // tables ready / previous frame's step C done
