@@ -14,6 +14,7 @@ from ._capi import (  # noqa: F401
     RampDesc,
     RoundtripParams,
     StftParams,
+    VocoderParams,
     fft_length_for,
     lib,
     lib_path,
@@ -24,4 +25,5 @@ from ._capi import (  # noqa: F401
 from .analysis import SqMagAnalyzer, analyze_streams, irfft_batched, rfft_batched  # noqa: F401
 from .synth import SineBank, render_bank, render_ramps  # noqa: F401
 from .roundtrip import pinned_empty, resynth_roundtrip  # noqa: F401
+from .vocoder import vocoder  # noqa: F401
 from .sharding import frame_shard, gather_rows, reduce_bus, shard_range  # noqa: F401

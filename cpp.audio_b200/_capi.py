@@ -11,7 +11,7 @@ DECLARED_SYMBOLS = [
     "ca_version", "ca_init", "ca_destroy", "ca_last_error", "ca_sm_count", "ca_kernel_launches", "ca_host_alloc",
     "ca_host_free", "ca_rfft_batched", "ca_irfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
-    "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host",
+    "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host", "ca_vocoder_host",
 ]
 
 
@@ -33,6 +33,12 @@ class RoundtripParams(C.Structure):
     _fields_ = [("stft", StftParams), ("nearby_distance_tones", C.c_float), ("min_volume", C.c_float),
                 ("max_track_pitches", C.c_float), ("gain", C.c_float), ("stereo_spread", C.c_float), ("env", Ahdsr),
                 ("max_channels", C.c_int32), ("host_threads", C.c_int32)]
+
+
+class VocoderParams(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("modulator_window_size_seconds", C.c_float), ("stride_seconds", C.c_float),
+                ("count_bands", C.c_int32), ("min_freq", C.c_float), ("max_freq", C.c_float), ("vol_modulator", C.c_float),
+                ("vol_carrier", C.c_float), ("vol_vocoder", C.c_float)]
 
 
 class RampDesc(C.Structure):
@@ -93,6 +99,7 @@ def lib():
     L.ca_measure_fp32_peak.argtypes = [p, C.POINTER(C.c_double)]
     L.ca_resynth_roundtrip_host.argtypes = [p, C.POINTER(RoundtripParams), p, i64, i64, p, p]
     L.ca_ramp_render_host.argtypes = [p, C.POINTER(RampDesc), p]
+    L.ca_vocoder_host.argtypes = [p, C.POINTER(VocoderParams), p, p, i64, i64, p]
     _lib = L
     return L
 

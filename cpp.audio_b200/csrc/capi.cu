@@ -279,6 +279,13 @@ int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, co
   return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
 }
 
+int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
+                    int64_t n_samples, int64_t n_streams, float* h_out) {
+  if (!ctx) return CA_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  return vocoder_host(ctx, params, h_modulator, h_carrier, n_samples, n_streams, h_out);
+}
+
 int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
   return ramp_render_host(ctx, desc, h_out);

@@ -119,6 +119,8 @@ int measure_fp32_peak(ca_ctx* ctx, double* tflops);
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);
 int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
+int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modulator, const float* h_carrier, int64_t n_samples,
+                 int64_t n_streams, float* h_out);
 // fused window -> FFT -> |X|^2 -> peaks for n_fft = 1024, 2048, 8192, 16384, 32768 (rfftw.cu); CA_ERR_UNSUPPORTED otherwise
 int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream);
 void stft_release(ca_ctx* ctx);

@@ -21,8 +21,8 @@ void rfft_release(ca_ctx* ctx) {
 
 int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
   if (!d_in || !d_out || batch < 0) return fail(ctx, CA_ERR_INVALID, "ca_rfft_batched: null pointer or negative batch");
-  if (n_fft < 1024 || n_fft > (1 << 20) || (n_fft & (n_fft - 1)))
-    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_rfft_batched: n_fft must be a power of two in [2^10, 2^20]");
+  if (n_fft < 512 || n_fft > (1 << 20) || (n_fft & (n_fft - 1)))
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_rfft_batched: n_fft must be a power of two in [2^9, 2^20]");
   if (batch == 0) return CA_OK;
   if (reinterpret_cast<uintptr_t>(d_in) % 8 || reinterpret_cast<uintptr_t>(d_out) % 8)
     return fail(ctx, CA_ERR_INVALID, "ca_rfft_batched: buffers must be 8-byte aligned");

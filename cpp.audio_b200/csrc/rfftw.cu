@@ -1351,6 +1351,7 @@ int big2_variant(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cu
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
   static const bool three_pass = getenv("CA_FFT_THREE_PASS") != nullptr;  // N >= 65536: the previous path, for A/B
   switch (n_fft) {
+    case 512: return launch_warp<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1024: return launch_warp<16, 8>(ctx, d_in, batch, d_out, stream);
     case 2048: return launch_warp<32, 8>(ctx, d_in, batch, d_out, stream);
     case 4096: return launch_warp<64, 12>(ctx, d_in, batch, d_out, stream);
@@ -1377,6 +1378,7 @@ int irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, floa
     return fail(ctx, CA_ERR_INVALID, "ca_irfft_batched: buffers must be 8-byte aligned");
   if (batch == 0) return CA_OK;
   switch (n_fft) {
+    case 512: return launch_iwarp<8, 8>(ctx, d_in, batch, d_out, scale, stream);
     case 1024: return launch_iwarp<16, 8>(ctx, d_in, batch, d_out, scale, stream);
     case 2048: return launch_iwarp<32, 8>(ctx, d_in, batch, d_out, scale, stream);
     case 4096: return launch_iwarp<64, 12>(ctx, d_in, batch, d_out, scale, stream);

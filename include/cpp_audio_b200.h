@@ -51,13 +51,13 @@ void ca_host_free(void* p);
  * Stands in for fft::Algo_<Tag,T>::forward as used by FftOperation<T>::operator()
  * (source/rt.resynth.lib.periodicfft.cpp:210-235) and forward_fft (source/main.test_fft.cpp:78).
  * Unscaled: X[k] = sum_n x[n] exp(-2 pi i k n / n_fft). d_in [batch][n_fft] float, d_out [batch][n_fft/2+1] (re,im).
- * n_fft: power of two, 2^10 .. 2^20. */
+ * n_fft: power of two, 2^9 .. 2^20. */
 int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, ca_stream stream);
 int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out);
 /* Inverse: stands in for fft::Algo_<Tag,T>::inverse as the vocoder's carrier path uses it
  * (source/rt.resynth.lib.vocoder.cpp:438-470). d_in [batch][n_fft/2+1] (re,im), Hermitian extension implied (bins 0 and n_fft/2 must
  * be real); d_out [batch][n_fft] = scale * sum_k X[k] exp(+2 pi i k n / n_fft), so
- * irfft(rfft(x)) = n_fft * x at scale 1. n_fft: power of two, 2^10 .. 2^15. */
+ * irfft(rfft(x)) = n_fft * x at scale 1. n_fft: power of two, 2^9 .. 2^15. */
 int ca_irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, ca_stream stream);
 
 /* ---- K2: periodic-FFT analysis ----------------------------------------------------------------------------------
@@ -187,6 +187,26 @@ typedef struct ca_ramp_desc {
   ca_ahdsr env;               /* one envelope for all voices; floors of 1 ms and 2.5 periods of `from` apply */
 } ca_ramp_desc;
 int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
+
+/* ---- FFT vocoder --------------------------------------------------------------------------------------------------
+ * Stands in for Vocoder / FFTModulator / FFTCarrier (source/rt.resynth.lib.vocoder.cpp:100-257, :396-551, :734-856): the
+ * modulator's band amplitudes (PeriodicFFT<SqMagFftOperation<Gaussian>>, window modulator_window_size_seconds, hop = stride)
+ * scale the carrier's spectrum band by band (PeriodicFFT<FftOperation>, window 2*stride, hop stride), the frames go back
+ * through the inverse real FFT and consecutive frames are cross-faded; output = vol_modulator * modulator + vol_carrier *
+ * carrier + vol_vocoder * vocoded, with the vocoded signal 2*stride-1 samples late, as in the reference. Fields follow
+ * SetupParams (:5-44; defaults source/rt.resynth.lib.cpp:986-990) and Vocoder::Volumes (:741-745). Host pointers,
+ * [n_streams][n_samples] each; stride = good_stride(stride_seconds) (:84-92, odd). */
+typedef struct ca_vocoder_params {
+  int32_t sample_rate;
+  float modulator_window_size_seconds; /* 0.10 */
+  float stride_seconds;                /* 0.005 */
+  int32_t count_bands;                 /* 5; at most 50 (max_count_bands, :98) */
+  float min_freq;                      /* 100 */
+  float max_freq;                      /* 20000 */
+  float vol_modulator, vol_carrier, vol_vocoder;
+} ca_vocoder_params;
+int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
+                    int64_t n_samples, int64_t n_streams, float* h_out);
 
 /* measured FP32 FMA throughput of this GPU in TFLOP/s (dependent-free FFMA chains, `ms` of work); used as the
  * denominator of the synthesis roofline */

@@ -112,11 +112,24 @@ public:
     }
   }
 
+  // unscaled inverse: x[n] = sum over the Hermitian-extended spectrum of X[k] exp(+2 pi i k n / N); inverse(forward(x)) = N x
+  // (the reference's fft.inverse + extractRealOutput, source/rt.resynth.lib.vocoder.cpp:452-467). Plain full-size complex FFT.
+  void inverse(const std::complex<T>* X, T* x) {
+    if (!full_) full_.emplace(n_);
+    full_work_.resize(n_);
+    for (int k = 0; k <= n_ / 2; ++k) full_work_[k] = std::conj(X[k]);
+    for (int k = n_ / 2 + 1; k < n_; ++k) full_work_[k] = X[n_ - k];
+    full_->forward(full_work_.data());  // conj(sum X e^{+}) = sum conj(X) e^{-}
+    for (int i = 0; i < n_; ++i) x[i] = full_work_[i].real();
+  }
+
 private:
   int n_;
   ComplexFft<T> half_;
   std::vector<std::complex<T>> work_;
   std::vector<std::complex<T>> tw_;
+  std::optional<ComplexFft<T>> full_;
+  std::vector<std::complex<T>> full_work_;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -163,6 +176,7 @@ template <class T>
 class SqMagOp {
 public:
   using FPT = T;
+  using Result = std::vector<T>;
   SqMagOp(Window type, double sigma_factor) : type_(type), sigma_(sigma_factor) {}
 
   bool init_data(int window_size) {
@@ -206,13 +220,50 @@ private:
   std::vector<std::complex<T>> bins_;
 };
 
+// Restates FftOperation<T> (source/rt.resynth.lib.periodicfft.cpp:183-244): rectangular window (:228), zero padding to the
+// FFT length (:231), forward real FFT (:234), unscaled; the result is the complex half spectrum (N/2+1 bins).
+template <class T>
+class FftOp {
+public:
+  using FPT = T;
+  using Result = std::vector<std::complex<T>>;
+
+  bool init_data(int window_size) {
+    int n = fft_length_for(window_size, 1);
+    if (!fft_ || fft_->size() != n) {
+      fft_.emplace(n);
+      signal_.assign(n, T(0));
+      bins_.assign(n / 2 + 1, {});
+    }
+    return false;
+  }
+
+  template <class It>
+  void operator()(It begin, It end) {
+    int w = static_cast<int>(end - begin);
+    int n = fft_->size();
+    for (int i = 0; i < w; ++i) signal_[i] = static_cast<T>(begin[i]);
+    for (int i = w; i < n; ++i) signal_[i] = T(0);
+    fft_->forward(signal_.data(), bins_.data());
+  }
+
+  const Result& get_results() const { return bins_; }
+  int fft_length() const { return fft_ ? fft_->size() : 0; }
+  RealFft<T>& fft() { return *fft_; }
+
+private:
+  std::optional<RealFft<T>> fft_;
+  std::vector<T> signal_;
+  Result bins_;
+};
+
 // Restates PeriodicFFT<Op> (source/rt.resynth.lib.periodicfft.cpp:13-181): sample-at-a-time feed into a window
 // buffer, operator fired when the buffer is full, then the overlap is shifted left by the stride.
 template <class Op>
 class PeriodicFft {
 public:
   using FPT = typename Op::FPT;
-  using OnResult = std::function<void(int, const std::vector<FPT>&)>;
+  using OnResult = std::function<void(int, const typename Op::Result&)>;
 
   template <class... Args>
   explicit PeriodicFft(Args&&... args) : op_(std::forward<Args>(args)...) {}
@@ -995,6 +1046,141 @@ private:
   std::vector<PitchVolume> pv_, reduced_, tuned_;
   std::vector<PlayedNote> played_;
   int64_t next_noteid_ = 0, dropped_ = 0;
+};
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Vocoder (source/rt.resynth.lib.vocoder.cpp): FFTModulator (:100-257) measures band amplitudes of the modulator signal,
+// FFTCarrier (:396-551) scales the carrier's spectrum band by band, transforms back and cross-fades consecutive frames.
+// Unpinned (cpp.algorithms): RealFBins::modulate_bands -> SPEC S12, EqualGainXFade -> SPEC S13.
+// ------------------------------------------------------------------------------------------------------------
+
+struct VocoderSetup {  // SetupParams, :5-44
+  float modulator_window_size_seconds = 0.04f;
+  float stride_seconds = 0.005f;
+  int count_bands = 20;
+  float min_freq = 100.f;
+  float max_freq = 5000.f;
+};
+
+inline void vocoder_fill_freqs(const VocoderSetup& p, std::vector<double>& freqs) {  // :15-26
+  freqs.clear();
+  auto log_min = std::log(p.min_freq);
+  auto log_max = std::log(p.max_freq);
+  for (int i = 0; i <= p.count_bands; ++i) {
+    double const ratio = static_cast<double>(i) / p.count_bands;
+    freqs.push_back(std::exp(log_min + ratio * (log_max - log_min)));
+  }
+}
+
+inline int vocoder_good_stride(float seconds, int sample_rate) {  // :84-92
+  int res = std::max(1, static_cast<int>(0.5f + seconds * sample_rate));
+  if (0 == res % 2) ++res;
+  return res;
+}
+
+inline int vocoder_modulator_window(float seconds, int sample_rate) {  // :110-118
+  int sz = std::max(1, static_cast<int>(0.5f + sample_rate * seconds));
+  if (1 == sz % 2) ++sz;
+  return sz;
+}
+
+// band of a frequency: freqs[b] < Hz <= freqs[b+1] (the membership rule of the modulator's loop, :131-156), -1 outside
+inline int vocoder_band_of(const std::vector<double>& freqs, double hz) {
+  int nb = static_cast<int>(freqs.size()) - 1;
+  if (!(hz > freqs[0])) return -1;
+  for (int b = 0; b < nb; ++b)
+    if (hz <= freqs[b + 1]) return b;
+  return -1;
+}
+
+// SPEC S13: equal-gain sinusoidal cross-fade over `stride` steps: step p in [1, stride] gives the new signal the weight
+// (1 - cos(pi p / stride)) / 2 and the old one the rest (weights sum to 1; p = stride: new signal only).
+template <class T>
+inline void vocoder_xfade(int p, int stride, T& new_mult, T& old_mult) {
+  new_mult = T(0.5) * (T(1) - std::cos(static_cast<T>(kPi) * static_cast<T>(p) / static_cast<T>(stride)));
+  old_mult = T(1) - new_mult;
+}
+
+template <class T>
+class Vocoder {
+public:
+  Vocoder(int sample_rate, const VocoderSetup& setup, float vol_modulator, float vol_carrier, float vol_vocoder)
+      : sr_(sample_rate), vm_(vol_modulator), vc_(vol_carrier), vv_(vol_vocoder), modulator_(Window::Gaussian, 4.0) {
+    vocoder_fill_freqs(setup, freqs_);
+    nb_ = static_cast<int>(freqs_.size()) - 1;
+    amps_.assign(nb_, T(0));
+    stride_ = vocoder_good_stride(setup.stride_seconds, sr_);
+    int wm = vocoder_modulator_window(setup.modulator_window_size_seconds, sr_);
+    // FFTModulator::init_dynamic_allocs, :108-165
+    modulator_.set_lambdas([wm] { return wm; }, [this] { return stride_; }, [this](int, const std::vector<T>& sqmag) {
+      std::fill(amps_.begin(), amps_.end(), T(0));
+      int n_fft = modulator_.op().fft_length();
+      double const bin_to_Hz = static_cast<double>(sr_) / n_fft;
+      size_t lo = 0, hi = 1;
+      int band = 0;
+      for (int i = 0, sz = static_cast<int>(sqmag.size()); i < sz; ++i) {
+        double const Hz = bin_to_Hz * i;
+        if (Hz <= freqs_[lo]) continue;
+        while (Hz > freqs_[hi]) {
+          ++band;
+          ++hi;
+          ++lo;
+          if (hi == freqs_.size()) break;
+        }
+        if (hi == freqs_.size()) break;
+        amps_[band] += sqmag[i];
+      }
+      for (auto& a : amps_) a = std::sqrt(a);
+    });
+    // FFTCarrier::init_dynamic_allocs, :413-476
+    carrier_.set_lambdas([this] { return 2 * stride_; }, [this] { return stride_; },
+                         [this](int, const std::vector<std::complex<T>>& bins) {
+      int n_fft = carrier_.op().fft_length();
+      if (static_cast<int>(sig_new_.size()) != n_fft) {
+        sig_new_.assign(n_fft, T(0));
+        sig_old_.assign(n_fft, T(0));
+      }
+      sig_old_.swap(sig_new_);
+      tmp_ = bins;
+      for (int i = 0; i < static_cast<int>(tmp_.size()); ++i) {  // SPEC S12: modulate_bands
+        int b = vocoder_band_of(freqs_, static_cast<double>(sr_) / n_fft * i);
+        tmp_[i] *= b < 0 ? T(0) : amps_[b];
+      }
+      carrier_.op().fft().inverse(tmp_.data(), sig_new_.data());
+      T const scale = T(1) / static_cast<T>(n_fft);  // 1 / (Algo::scale * fft_length): forward o inverse = identity
+      for (auto& v : sig_new_) v *= scale;
+      idx_ = 0;
+    });
+  }
+
+  // one sample of each input -> one output sample (Vocoder::initialize's compute lambda, :777-812)
+  T feed(T modulator_sample, T carrier_sample) {
+    modulator_.feed(static_cast<float>(modulator_sample));
+    carrier_.feed(static_cast<float>(carrier_sample));
+    T vocoded = 0;
+    if (!sig_new_.empty() && idx_ < stride_) {  // FFTCarrier::feed, :501-531
+      T a, b;
+      vocoder_xfade<T>(idx_ + 1, stride_, a, b);
+      vocoded = sig_new_[idx_] * a + sig_old_[idx_ + stride_] * b;
+    }
+    ++idx_;
+    return vm_ * modulator_sample + vc_ * carrier_sample + vv_ * vocoded;
+  }
+
+  int stride() const { return stride_; }
+  const std::vector<T>& bands_amplitudes() const { return amps_; }
+
+private:
+  int sr_;
+  float vm_, vc_, vv_;
+  std::vector<double> freqs_;
+  int nb_ = 0, stride_ = 1, idx_ = 0;
+  std::vector<T> amps_;
+  PeriodicFft<SqMagOp<T>> modulator_;
+  PeriodicFft<FftOp<T>> carrier_;
+  std::vector<std::complex<T>> tmp_;
+  std::vector<T> sig_new_, sig_old_;
 };
 
 }  // namespace orc

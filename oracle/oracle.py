@@ -212,3 +212,22 @@ def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: in
     lib().orc_roundtrip(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
                         C.byref(e), _ptr(out), _ptr(stats), threads)
     return out, stats
+
+
+def vocoder(modulator: np.ndarray, carrier: np.ndarray, sample_rate: int = 48000, modulator_window_seconds: float = 0.04,
+            stride_seconds: float = 0.005, count_bands: int = 20, min_freq: float = 100.0, max_freq: float = 5000.0,
+            vol_modulator: float = 0.0, vol_carrier: float = 0.0, vol_vocoder: float = 1.0, threads: int = 1):
+    """Vocoder of the reference (source/rt.resynth.lib.vocoder.cpp), one sample at a time in double. modulator / carrier
+    float32 [streams, samples]. Returns (out float64 [streams, samples], stride in samples)."""
+    m = np.ascontiguousarray(np.atleast_2d(modulator), dtype=np.float32)
+    c = np.ascontiguousarray(np.atleast_2d(carrier), dtype=np.float32)
+    assert m.shape == c.shape
+    streams, n = m.shape
+    out = np.zeros((streams, n), dtype=np.float64)
+    L = lib()
+    L.orc_vocoder.restype = C.c_int
+    L.orc_vocoder.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                              C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int]
+    stride = L.orc_vocoder(_ptr(m), _ptr(c), n, streams, sample_rate, modulator_window_seconds, stride_seconds, count_bands,
+                           min_freq, max_freq, vol_modulator, vol_carrier, vol_vocoder, _ptr(out), threads)
+    return out, int(stride)

@@ -288,4 +288,22 @@ void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sam
   });
 }
 
+// Vocoder (source/rt.resynth.lib.vocoder.cpp) over n_streams independent (modulator, carrier) pairs, one sample at a time.
+// out [streams][samples] double. Returns the stride in samples.
+int orc_vocoder(const float* modulator, const float* carrier, int64_t n_samples, int64_t n_streams, int sample_rate,
+                float modulator_window_seconds, float stride_seconds, int count_bands, float min_freq, float max_freq,
+                float vol_modulator, float vol_carrier, float vol_vocoder, double* out, int threads) {
+  VocoderSetup su;
+  su.modulator_window_size_seconds = modulator_window_seconds;
+  su.stride_seconds = stride_seconds;
+  su.count_bands = count_bands;
+  su.min_freq = min_freq;
+  su.max_freq = max_freq;
+  parallel_for(n_streams, threads, [&](int64_t s) {
+    Vocoder<double> v(sample_rate, su, vol_modulator, vol_carrier, vol_vocoder);
+    for (int64_t n = 0; n < n_samples; ++n) out[s * n_samples + n] = v.feed(modulator[s * n_samples + n], carrier[s * n_samples + n]);
+  });
+  return vocoder_good_stride(stride_seconds, sample_rate);
+}
+
 }  // extern "C"

@@ -114,3 +114,27 @@ def test_log_ramp_known_answers(orc):
     # it bounces: around 2 * duration the frequency is back near `from`
     f_back = sr / periods[np.searchsorted(zc, 15900) - 1]
     assert abs(f_back - 500.0) < 40
+
+
+# ---- vocoder restatement (source/rt.resynth.lib.vocoder.cpp): properties that follow from the in-tree lines ----
+
+def test_vocoder_oracle_latency_linearity_and_band_membership(orc):
+    sr, n = 48000, 12000
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(2)
+    mod = (0.5 * np.sin(2 * np.pi * 300 * t)).astype(np.float32)
+    car = rng.uniform(-0.5, 0.5, n).astype(np.float32)
+    kw = dict(modulator_window_seconds=0.04, stride_seconds=0.005, count_bands=20, min_freq=100.0, max_freq=5000.0)
+    out, stride = orc.vocoder(mod, car, **kw)
+    assert stride == 241 and stride % 2 == 1                         # good_stride, vocoder.cpp:84-92
+    wm = 1920                                                        # 0.04 s at 48 kHz, even (:110-118)
+    assert np.abs(out[0, :wm - 1]).max() == 0.0                      # band amplitudes are zero before the first modulator frame
+    assert np.abs(out[0, wm + 2 * stride:]).max() > 1e-4
+    out2, _ = orc.vocoder(mod, 2 * car, **kw)
+    assert np.abs(out2 - 2 * out).max() < 1e-12                      # linear in the carrier
+    dry, _ = orc.vocoder(mod, car, vol_modulator=1.0, vol_carrier=0.5, vol_vocoder=0.0, **kw)
+    assert np.allclose(dry[0], mod.astype(np.float64) + 0.5 * car.astype(np.float64), atol=1e-12)
+    # a modulator below every band (50 Hz) leaves all amplitudes near zero: the carrier is muted
+    low = (0.5 * np.sin(2 * np.pi * 50 * t)).astype(np.float32)
+    muted, _ = orc.vocoder(low, car, **kw)
+    assert np.abs(muted).max() < 1e-3 * np.abs(out).max()
