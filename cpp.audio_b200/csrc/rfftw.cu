@@ -580,7 +580,10 @@ __global__ void __launch_bounds__(32 * (2 * G + 1)) big2_rows_kernel(const float
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tab4 = reinterpret_cast<float4*>(smem_raw);
   c2* rows = reinterpret_cast<c2*>(tab4 + kTabRows * 32);  // [2G+1][kRowC2]
+  float2* tw2r = reinterpret_cast<float2*>(rows + (2 * G + 1) * kRowC2);  // [R] W_2R^k2 for the untangling step
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  static_assert(T % G == 0, "a thread keeps its kA through the untangling loop");
+  for (int i = t; i < R; i += T) tw2r[i] = cis_neg_w(static_cast<float>(i) / R);  // exp(-i pi k2 / R)
   const int64_t frame = blockIdx.x / CPF;
   const int cc = blockIdx.x % CPF;
   for (int i = t; i < kTabRows * 32; i += T) {
@@ -623,29 +626,43 @@ __global__ void __launch_bounds__(32 * (2 * G + 1)) big2_rows_kernel(const float
   }
   __syncthreads();
   // ---- untangle: X[k] and X[M-k], k = kA + MA*k2; consecutive threads take consecutive kA ----
+  // 0.5 * (-i) * W_N^k = [0.5 * (-i) * W_N^kA] * W_2R^k2: kA is fixed per thread (T is a multiple of G), W_2R^k2 comes from a
+  // table in shared memory, so an output pair costs one complex multiply instead of a sincospif
   float2* o = out + frame * (M + 1);
-  auto emit = [&](int64_t k, c2 zk, c2 zm) {
-    float sn, cs;
-    sincospif(static_cast<float>(k) / M, &sn, &cs);      // W_N^k = exp(-i pi k / M); k < 2^24: exact argument
-    const TwP wp{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};  // 0.5 * (-i) * W_N^k
+  auto emit = [&](int64_t k, c2 zk, c2 zm, const TwP& wp) {
     const c2 E = add2(zk, cconj(zm));
     const c2 Tt = cmul_tw(csub(zk, cconj(zm)), wp);
     o[k] = upk(fma2(bc(0.5f), E, Tt));
     o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
   };
-  for (int item = t; item < G * R; item += T) {
-    const int i = item & (G - 1), k2 = item / G;
+  auto twiddle = [&](int kA, int k2) {  // 0.5 * (-i) * W_N^(kA + MA*k2) in the (wr, (-wi, wi)) form
+    float sn, cs;
+    sincospif(static_cast<float>(kA) / M, &sn, &cs);  // W_N^kA = (cs, -sn)
+    const float2 w2 = tw2r[k2];                        // W_2R^k2
+    const float wr = cs * w2.x + sn * w2.y, wi = cs * w2.y - sn * w2.x;  // W_N^k
+    return TwP{0.5f * wi, pk(0.5f * wr, -0.5f * wr)};  // (-i) * w = (wi, -wr)
+  };
+  {
+    const int i = t & (G - 1);
     const int kA = cc * G + i;
-    if (kA == 0) {  // M - k = MA*(R - k2): the same row
-      if (k2 > R / 2) continue;
-      emit(static_cast<int64_t>(MA) * k2, rows[k2], rows[(R - k2) & (R - 1)]);
-    } else {        // M - k = (MA - kA) + MA*(R - 1 - k2)
-      emit(kA + static_cast<int64_t>(MA) * k2, rows[i * kRowC2 + k2], rows[(G + i) * kRowC2 + R - 1 - k2]);
+    float sn, cs;
+    sincospif(static_cast<float>(kA) / M, &sn, &cs);
+    for (int item = t; item < G * R; item += T) {  // T % G == 0: item & (G-1) == i
+      const int k2 = item / G;
+      const float2 w2 = tw2r[k2];
+      const float wr = cs * w2.x + sn * w2.y, wi = cs * w2.y - sn * w2.x;
+      const TwP wp{0.5f * wi, pk(0.5f * wr, -0.5f * wr)};
+      if (kA == 0) {  // M - k = MA*(R - k2): the same row
+        if (k2 > R / 2) continue;
+        emit(static_cast<int64_t>(MA) * k2, rows[k2], rows[(R - k2) & (R - 1)], wp);
+      } else {        // M - k = (MA - kA) + MA*(R - 1 - k2)
+        emit(kA + static_cast<int64_t>(MA) * k2, rows[i * kRowC2 + k2], rows[(G + i) * kRowC2 + R - 1 - k2], wp);
+      }
     }
   }
   if (cc == CPF - 1) {  // kA = MA/2: M - k = MA/2 + MA*(R - 1 - k2)
     const c2* rs = rows + 2 * G * kRowC2;
-    for (int k2 = t; k2 < R / 2; k2 += T) emit(MA / 2 + static_cast<int64_t>(MA) * k2, rs[k2], rs[R - 1 - k2]);
+    for (int k2 = t; k2 < R / 2; k2 += T) emit(MA / 2 + static_cast<int64_t>(MA) * k2, rs[k2], rs[R - 1 - k2], twiddle(MA / 2, k2));
   }
 }
 
@@ -666,7 +683,7 @@ int launch_big2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cud
   auto cols = big2_cols_kernel<A, B, CW>;
   auto rowsk = big2_rows_kernel<MA, G>;
   const size_t smem_cols = sizeof(c2) * MA * CW;
-  const size_t smem_rows = sizeof(float4) * 10 * 32 + sizeof(c2) * (16 * kXStride + 2) * (2 * G + 1);
+  const size_t smem_rows = sizeof(float4) * 10 * 32 + sizeof(c2) * (16 * kXStride + 2) * (2 * G + 1) + sizeof(float2) * kBig2Row;
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
   CA_CUDA_OK(ctx, cudaFuncSetAttribute(rowsk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
   for (int64_t b0 = 0; b0 < batch; b0 += group) {

@@ -1,5 +1,6 @@
 """Small driver for ncu captures: runs one kernel family a few times on cuda:0 (never a bench number).
     python profiles/prof_driver.py stft [streams]     python profiles/prof_driver.py osc [voices]     ... rfft [log2n]
+    ... roundtrip [streams]     ... vocoder [streams]
 """
 import os
 import sys
@@ -36,5 +37,17 @@ elif what == "rfft":
     x = torch.from_numpy(wl.c5_frames(p, 26)).to(dev)
     for _ in range(4):
         pkg.rfft_batched(ctx, x)
+elif what == "roundtrip":
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    x = wl.tiled_streams(S, 60.0)
+    for _ in range(3):
+        pkg.resynth_roundtrip(ctx, x)
+elif what == "vocoder":
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    rng = np.random.default_rng(1)
+    mod = wl.tiled_streams(S, 60.0)
+    car = rng.uniform(-0.5, 0.5, mod.shape).astype(np.float32)
+    for _ in range(3):
+        pkg.vocoder(ctx, mod, car)
 torch.cuda.synchronize()
 print("done", ctx.kernel_launches)

@@ -9,4 +9,8 @@ python bench.py --steps 2 --warmup 3 --skip-cpu --skip-roundtrip > gpurun_out/pl
 python profiles/prof_driver.py stft > gpurun_out/plain_stft.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:stft4096 -s 2 -c 1 -f -o gpurun_out/prof_stft_r01 python profiles/prof_driver.py stft > gpurun_out/ncu_stft.log 2>&1
 python profiles/prof_driver.py osc > gpurun_out/plain_osc.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:oscbank_kernel -s 2 -c 1 -f -o gpurun_out/prof_osc_r01 python profiles/prof_driver.py osc > gpurun_out/ncu_osc.log 2>&1
 python profiles/prof_driver.py rfft 10 > gpurun_out/plain_rfft.log 2>&1 && ncu --set full --clock-control none -k regex:rfft_warp -s 2 -c 1 -f -o gpurun_out/prof_rfft1024_r01 python profiles/prof_driver.py rfft 10 > gpurun_out/ncu_rfft.log 2>&1
+python profiles/prof_driver.py rfft 19 > gpurun_out/plain_rfft19.log 2>&1 && ncu --set full --clock-control none -k regex:big2_ -s 4 -c 2 -f -o gpurun_out/prof_big2_r01 python profiles/prof_driver.py rfft 19 > gpurun_out/ncu_big2.log 2>&1
+python profiles/prof_driver.py roundtrip > gpurun_out/plain_roundtrip.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:pitch_ -s 2 -c 2 -f -o gpurun_out/prof_pitch_r01 python profiles/prof_driver.py roundtrip > gpurun_out/ncu_pitch.log 2>&1
+CA_RT_TIMING=1 python profiles/time_roundtrip.py 32 60 > gpurun_out/roundtrip_time.txt 2>&1
+python profiles/time_vocoder.py > gpurun_out/vocoder_time.txt 2>&1
 tail -n 2 gpurun_out/bench_r01.err gpurun_out/ncu_launch.log gpurun_out/ncu_stft.log gpurun_out/ncu_osc.log gpurun_out/ncu_rfft.log
