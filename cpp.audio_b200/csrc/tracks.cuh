@@ -147,6 +147,7 @@ __host__ __device__ inline double rcp(double x) {
 
 struct Glide {  // InterpolatedFreq in closed form
   double from = 0, to = 0, K = 0, L = 0, c1 = 0, P_m1 = 0;
+  double f_m1 = 0;  // f_at(m - 1), the last glide step before the clamp
   int32_t m = 0;   // first clamped step
   int64_t i = 0;   // next glide step index
   __host__ __device__ void start(double from_, double to_, double dur) {
@@ -156,6 +157,7 @@ struct Glide {  // InterpolatedFreq in closed form
     if (to == from) {  // C = 1: the first step emits `to`, after which the steady-state shortcut holds (:2765-2767)
       m = 0;
       K = L = c1 = P_m1 = 0;
+      f_m1 = to;
       return;
     }
     // Reference constants (:2783-2784, :2815): C = -log(from/to)/delta, cur' = (1+lambda)*cur + beta with lambda = C*delta/dur,
@@ -180,10 +182,15 @@ struct Glide {  // InterpolatedFreq in closed form
     if (mf < 1.0) mf = 1.0;
     if (mf > 1e9) mf = 1e9;
     m = static_cast<int32_t>(mf);
-    P_m1 = static_cast<double>(m) * (from - K) + c1 * expm1(L * static_cast<double>(m));  // P(m - 1)
+    // one expm1 serves both f_at(m - 1) and P(m - 1): exp(L) = 1 + lambda, so expm1(L m) = e + lambda e + lambda with
+    // e = expm1(L (m - 1))
+    const double e = m > 1 ? expm1(L * static_cast<double>(m - 1)) : 0.0;
+    f_m1 = from + K * e;
+    P_m1 = static_cast<double>(m) * (from - K) + c1 * (e + lambda * e + lambda);  // P(m - 1)
   }
   __host__ __device__ double f_at(int64_t k) const {
     if (k >= m) return to;
+    if (k == m - 1) return f_m1;
     return k == 0 ? from : from + K * expm1(L * static_cast<double>(k));  // expm1(0) == 0
   }
   __host__ __device__ double P(int64_t k) const {  // sum of f over steps 0..k
