@@ -505,63 +505,39 @@ int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cuda
 //           frame): one warp per row runs the 1024-point warp-level FFT in shared memory, then the whole CTA untangles
 //           X[k], X[M-k] from the two row sets and writes them in runs of 8 consecutive bins (64 bytes)
 // 32M bytes moved for 16M algorithmic: the ceiling is half of the HBM roofline (the three-pass path above: a third).
+// (Tried and removed: ONE persistent launch that runs both passes with in-order tickets and keeps the work frames in an L2-sized
+// ring. Correct, but 25-70 % slower, profiles/fft_fused_sweep_r01.txt: both passes must share one CTA shape, which leaves the
+// column pass at 9-17 warps per SM instead of 30, and the row pass is issue-bound rather than HBM-bound, profiles/ncu_big2_r01.json.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBig2Row = 1024;
-constexpr int kBig2TabRows = 7 + 3;              // row-FFT tables: wb[1..7], wa[1..3] (WarpFftCfg<32>)
-constexpr int kBig2RowC2 = 16 * kXStride + 2;    // = 2 (mod 16): 8 rows x 2 consecutive k2 cover the 32 banks once (G = 8)
 
-// v[k] *= w^k for k = 1 .. A-1 with w^k assembled from the binary powers w, w^2, w^4, ... (log2 A values live instead of A)
-template <int A, int K, int BIT>
-__device__ __forceinline__ c2 pow_from_bits(const c2 (&pw)[ilog2(A) > 0 ? ilog2(A) : 1]) {
-  if constexpr ((K >> BIT) == 0) return pk(1.f, 0.f);
-  else if constexpr (((K >> BIT) & 1) == 0) return pow_from_bits<A, K, BIT + 1>(pw);
-  else if constexpr ((K >> (BIT + 1)) == 0) return pw[BIT];
-  else {
-    const float2 a = upk(pw[BIT]);
-    return cmul_tw(pow_from_bits<A, K, BIT + 1>(pw), TwP{a.x, pk(-a.y, a.y)});
-  }
-}
-template <int A, int... K>
-__device__ __forceinline__ void mul_powers(c2 (&v)[A], const c2 (&pw)[ilog2(A) > 0 ? ilog2(A) : 1], std::integer_sequence<int, K...>) {
-  (([&] {
-     const float2 a = upk(pow_from_bits<A, K + 1, 0>(pw));
-     v[K + 1] = cmul_tw(v[K + 1], TwP{a.x, pk(-a.y, a.y)});
-   }()),
-   ...);
-}
-// binary powers of w = (cs, -sn): pw[j] = w^(2^j)
-template <int A>
-__device__ __forceinline__ void binary_powers(float cs, float sn, c2 (&pw)[ilog2(A) > 0 ? ilog2(A) : 1]) {
-  pw[0] = pk(cs, -sn);
-#pragma unroll
-  for (int j = 1; j < ilog2(A); ++j) {
-    const float2 a = upk(pw[j - 1]);
-    pw[j] = cmul_tw(pw[j - 1], TwP{a.x, pk(-a.y, a.y)});
-  }
-}
-
-// Pass 1 for one tile: CW adjacent columns (CW*8-byte runs in HBM) x all MA rows of one frame; T threads.
-template <int A, int B, int CW, int T>
-__device__ __forceinline__ void big2_cols_tile(const c2* __restrict__ src_frame, c2* __restrict__ dst_frame, int tile, c2* __restrict__ u,
-                                               int t) {
-  constexpr int MA = A * B, R = kBig2Row, M = MA * R, QT = T / CW;
-  static_assert(T % CW == 0, "threads = columns x row groups");
-  const int cl = t % CW, q = t / CW;
-  const int c = tile * CW + cl;
-  const c2* src = src_frame + c;
-  c2* dst = dst_frame + c;
+// CW: columns per CTA (CW*8-byte runs in HBM)
+template <int A, int B, int CW>
+__global__ void __launch_bounds__(256) big2_cols_kernel(const float2* __restrict__ zin, float2* __restrict__ work) {
+  constexpr int MA = A * B, R = kBig2Row, M = MA * R, QT = 256 / CW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c2* u = reinterpret_cast<c2*>(smem_raw);  // [A][B][CW]: element (k1, r2, column)
+  const int t = threadIdx.x, cl = t % CW, q = t / CW;
+  const int c = blockIdx.x * CW + cl;
+  const c2* src = reinterpret_cast<const c2*>(zin) + static_cast<int64_t>(blockIdx.y) * M + c;
+  c2* dst = reinterpret_cast<c2*>(work) + static_cast<int64_t>(blockIdx.y) * M + c;
   // ---- stage 1: r = B*r1 + r2; A-point FFT over r1 for every (column, r2), twiddle W_MA^(r2*k1) ----
   for (int r2 = q; r2 < B; r2 += QT) {
     c2 v[A];
 #pragma unroll
-    for (int r1 = 0; r1 < A; ++r1) v[bitrev(r1, ilog2(A))] = __ldcs(src + static_cast<int64_t>(B * r1 + r2) * R);  // streaming: read once
+    for (int r1 = 0; r1 < A; ++r1) v[bitrev(r1, ilog2(A))] = __ldg(src + static_cast<int64_t>(B * r1 + r2) * R);
     DitP<A, A, 0>::run(v);
     if (r2 != 0) {
+      c2 w[A];
       float sn, cs;
       sincospif(2.f * static_cast<float>(r2) / MA, &sn, &cs);
-      c2 pw[ilog2(A) > 0 ? ilog2(A) : 1];
-      binary_powers<A>(cs, sn, pw);
-      mul_powers<A>(v, pw, std::make_integer_sequence<int, A - 1>{});
+      w[1] = pk(cs, -sn);
+      if constexpr (A > 2) cpow_all<A>(w, std::make_integer_sequence<int, A - 2>{});
+#pragma unroll
+      for (int k1 = 1; k1 < A; ++k1) {
+        const float2 a = upk(w[k1]);
+        v[k1] = cmul_tw(v[k1], TwP{a.x, pk(-a.y, a.y)});
+      }
     }
 #pragma unroll
     for (int k1 = 0; k1 < A; ++k1) u[(k1 * B + r2) * CW + cl] = v[k1];
@@ -573,13 +549,13 @@ __device__ __forceinline__ void big2_cols_tile(const c2* __restrict__ src_frame,
 #pragma unroll
     for (int r2 = 0; r2 < B; ++r2) y[bitrev(r2, ilog2(B))] = u[(k1 * B + r2) * CW + cl];
     DitP<B, B, 0>::run(y);
+    c2 pw[B];  // pw[j] = W_M^(c*A*j) by binary powers (depth <= log2 B)
     {
       float sn, cs;
-      sincospif(2.f * static_cast<float>(c * A) / M, &sn, &cs);  // W_M^(c*A); exact argument: c*A < 2^15, M a power of two
-      c2 pw[ilog2(B) > 0 ? ilog2(B) : 1];
-      binary_powers<B>(cs, sn, pw);
-      mul_powers<B>(y, pw, std::make_integer_sequence<int, B - 1>{});
+      sincospif(2.f * static_cast<float>(c * A) / M, &sn, &cs);  // exact argument: c*A < 2^15, M a power of two
+      pw[1] = pk(cs, -sn);
     }
+    if constexpr (B > 2) cpow_all<B>(pw, std::make_integer_sequence<int, B - 2>{});
     TwP base;
     {
       float sn, cs;
@@ -587,32 +563,38 @@ __device__ __forceinline__ void big2_cols_tile(const c2* __restrict__ src_frame,
       base = TwP{cs, pk(sn, -sn)};  // W_M^(c*k1) = (cs, -sn) in the (wr, (-wi, wi)) form
     }
 #pragma unroll
-    for (int k2 = 0; k2 < B; ++k2) dst[static_cast<int64_t>(k1 + A * k2) * R] = cmul_tw(y[k2], base);
+    for (int k2 = 0; k2 < B; ++k2) {
+      c2 val = cmul_tw(y[k2], base);
+      if (k2) {
+        const float2 a = upk(pw[k2]);
+        val = cmul_tw(val, TwP{a.x, pk(-a.y, a.y)});
+      }
+      dst[static_cast<int64_t>(k1 + A * k2) * R] = val;
+    }
   }
 }
 
-// tables of pass 2 in shared memory (built once per CTA): row-FFT twiddles and W_2R^k2 for the untangling step
-template <int T>
-__device__ __forceinline__ void big2_rows_tables(float4* tab4, float2* tw2r, int t) {
-  constexpr int R = kBig2Row;
+// G: adjacent rows per CTA (G*8-byte runs in HBM)
+template <int MA, int G>
+__global__ void __launch_bounds__(32 * (2 * G + 1)) big2_rows_kernel(const float2* __restrict__ work, float2* __restrict__ out) {
+  constexpr int R = kBig2Row, M = MA * R, CPF = MA / (2 * G), T = 32 * (2 * G + 1);
+  constexpr int kRowC2 = 16 * kXStride + 2;  // = 2 (mod 16): 8 rows x 2 consecutive k2 cover the 32 banks once (G = 8)
+  constexpr int kTabRows = 7 + 3;            // row-FFT tables: wb[1..7], wa[1..3] (WarpFftCfg<32>)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
+  c2* rows = reinterpret_cast<c2*>(tab4 + kTabRows * 32);  // [2G+1][kRowC2]
+  float2* tw2r = reinterpret_cast<float2*>(rows + (2 * G + 1) * kRowC2);  // [R] W_2R^k2 for the untangling step
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  static_assert(T % G == 0, "a thread keeps its kA through the untangling loop");
   for (int i = t; i < R; i += T) tw2r[i] = cis_neg_w(static_cast<float>(i) / R);  // exp(-i pi k2 / R)
-  for (int i = t; i < kBig2TabRows * 32; i += T) {
+  const int64_t frame = blockIdx.x / CPF;
+  const int cc = blockIdx.x % CPF;
+  for (int i = t; i < kTabRows * 32; i += T) {
     const int r = i >> 5, l = i & 31;
     const float2 w = r < 7 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / R) : cis_neg_w(2.f * static_cast<float>(l * 8 * (r - 6)) / R);
     tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
   }
-}
-
-// Pass 2 for one tile: G adjacent rows cc*G .. cc*G+G-1 of one frame, their mirrors MA - kA and (last tile of the frame) the
-// self-paired row MA/2. kCoherent: the work buffer was written by other CTAs of the same launch (L2 loads, not the read-only path).
-// The caller synchronises the CTA after the tables are built and before the rows buffer is reused.
-template <int MA, int G, bool kCoherent>
-__device__ __forceinline__ void big2_rows_tile(const c2* __restrict__ work_frame, float2* __restrict__ o, int cc, const float4* tab4,
-                                               c2* rows, const float2* tw2r, int t) {
-  constexpr int R = kBig2Row, M = MA * R, CPF = MA / (2 * G), T = 32 * (2 * G + 1), kRowC2 = kBig2RowC2;
-  static_assert(T % G == 0, "a thread keeps its kA through the untangling loop");
-  const int lane = t & 31, warp = t >> 5;
-  // slot -> row of the frame: [0, G) the tile's own rows, [G, 2G) their mirrors MA - kA, 2G the self-paired row MA/2
+  // slot -> row of the frame: [0, G) the CTA's own rows, [G, 2G) their mirrors MA - kA, 2G the self-paired row MA/2
   int kA_row;
   bool valid = true;
   if (warp < G) kA_row = cc * G + warp;
@@ -623,11 +605,14 @@ __device__ __forceinline__ void big2_rows_tile(const c2* __restrict__ work_frame
     kA_row = MA / 2;
     valid = cc == CPF - 1;
   }
-  if (valid) {  // 1024 = 32 x 32 point FFT of the row, warp-level (as step B of rfft_cta_kernel)
-    c2 v[32];
-    const c2* src = work_frame + static_cast<int64_t>(kA_row) * R;
+  c2 v[32];
+  if (valid) {
+    const c2* src = reinterpret_cast<const c2*>(work) + frame * M + static_cast<int64_t>(kA_row) * R;
 #pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = kCoherent ? __ldcg(src + 32 * n1 + lane) : __ldg(src + 32 * n1 + lane);
+    for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = __ldg(src + 32 * n1 + lane);
+  }
+  __syncthreads();  // tables ready
+  if (valid) {      // 1024 = 32 x 32 point FFT of the row, warp-level (as step B of rfft_cta_kernel)
     c2* row = rows + warp * kRowC2;
     DitP<32, 32, 0>::run(v);
     tww_chain<32, 0>(v, tab4, lane, make_twp(tab4[lane]));
@@ -646,16 +631,19 @@ __device__ __forceinline__ void big2_rows_tile(const c2* __restrict__ work_frame
   // ---- untangle: X[k] and X[M-k], k = kA + MA*k2; consecutive threads take consecutive kA ----
   // 0.5 * (-i) * W_N^k = [0.5 * (-i) * W_N^kA] * W_2R^k2: kA is fixed per thread (T is a multiple of G), W_2R^k2 comes from a
   // table in shared memory, so an output pair costs one complex multiply instead of a sincospif
+  float2* o = out + frame * (M + 1);
   auto emit = [&](int64_t k, c2 zk, c2 zm, const TwP& wp) {
     const c2 E = add2(zk, cconj(zm));
     const c2 Tt = cmul_tw(csub(zk, cconj(zm)), wp);
-    __stcs(o + k, upk(fma2(bc(0.5f), E, Tt)));  // streaming stores: the output does not displace the work frames in L2
-    __stcs(o + (M - k), upk(cconj(fma2(bc(0.5f), E, cneg(Tt)))));
+    o[k] = upk(fma2(bc(0.5f), E, Tt));
+    o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
   };
-  auto twiddle = [&](float cs, float sn, int k2) {  // 0.5 * (-i) * W_N^kA * W_2R^k2 with W_N^kA = (cs, -sn)
-    const float2 w2 = tw2r[k2];
+  auto twiddle = [&](int kA, int k2) {  // 0.5 * (-i) * W_N^(kA + MA*k2) in the (wr, (-wi, wi)) form
+    float sn, cs;
+    sincospif(static_cast<float>(kA) / M, &sn, &cs);  // W_N^kA = (cs, -sn)
+    const float2 w2 = tw2r[k2];                        // W_2R^k2
     const float wr = cs * w2.x + sn * w2.y, wi = cs * w2.y - sn * w2.x;  // W_N^k
-    return TwP{0.5f * wi, pk(0.5f * wr, -0.5f * wr)};                     // (-i) * w = (wi, -wr)
+    return TwP{0.5f * wi, pk(0.5f * wr, -0.5f * wr)};  // (-i) * w = (wi, -wr)
   };
   {
     const int i = t & (G - 1);
@@ -664,7 +652,9 @@ __device__ __forceinline__ void big2_rows_tile(const c2* __restrict__ work_frame
     sincospif(static_cast<float>(kA) / M, &sn, &cs);
     for (int item = t; item < G * R; item += T) {  // T % G == 0: item & (G-1) == i
       const int k2 = item / G;
-      const TwP wp = twiddle(cs, sn, k2);
+      const float2 w2 = tw2r[k2];
+      const float wr = cs * w2.x + sn * w2.y, wi = cs * w2.y - sn * w2.x;
+      const TwP wp{0.5f * wi, pk(0.5f * wr, -0.5f * wr)};
       if (kA == 0) {  // M - k = MA*(R - k2): the same row
         if (k2 > R / 2) continue;
         emit(static_cast<int64_t>(MA) * k2, rows[k2], rows[(R - k2) & (R - 1)], wp);
@@ -675,103 +665,7 @@ __device__ __forceinline__ void big2_rows_tile(const c2* __restrict__ work_frame
   }
   if (cc == CPF - 1) {  // kA = MA/2: M - k = MA/2 + MA*(R - 1 - k2)
     const c2* rs = rows + 2 * G * kRowC2;
-    float sn, cs;
-    sincospif(static_cast<float>(MA / 2) / M, &sn, &cs);
-    for (int k2 = t; k2 < R / 2; k2 += T) emit(MA / 2 + static_cast<int64_t>(MA) * k2, rs[k2], rs[R - 1 - k2], twiddle(cs, sn, k2));
-  }
-}
-
-constexpr size_t big2_rows_smem(int G) { return sizeof(float4) * kBig2TabRows * 32 + sizeof(c2) * kBig2RowC2 * (2 * G + 1) + sizeof(float2) * kBig2Row; }
-
-// ---- two launches per group of frames (default) ----
-template <int A, int B, int CW>
-__global__ void __launch_bounds__(256) big2_cols_kernel(const float2* __restrict__ zin, float2* __restrict__ work) {
-  constexpr int M = A * B * kBig2Row;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  big2_cols_tile<A, B, CW, 256>(reinterpret_cast<const c2*>(zin) + static_cast<int64_t>(blockIdx.y) * M,
-                                reinterpret_cast<c2*>(work) + static_cast<int64_t>(blockIdx.y) * M, blockIdx.x,
-                                reinterpret_cast<c2*>(smem_raw), threadIdx.x);
-}
-template <int MA, int G>
-__global__ void __launch_bounds__(32 * (2 * G + 1)) big2_rows_kernel(const float2* __restrict__ work, float2* __restrict__ out) {
-  constexpr int M = MA * kBig2Row, CPF = MA / (2 * G), T = 32 * (2 * G + 1);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
-  c2* rows = reinterpret_cast<c2*>(tab4 + kBig2TabRows * 32);
-  float2* tw2r = reinterpret_cast<float2*>(rows + (2 * G + 1) * kBig2RowC2);
-  big2_rows_tables<T>(tab4, tw2r, threadIdx.x);
-  __syncthreads();
-  const int64_t frame = blockIdx.x / CPF;
-  big2_rows_tile<MA, G, false>(reinterpret_cast<const c2*>(work) + frame * M, out + frame * (M + 1), blockIdx.x % CPF, tab4, rows, tw2r,
-                               threadIdx.x);
-}
-
-// ---- one persistent launch (CA_FFT_PERSISTENT=1): both passes of every frame, the work buffer a ring of a few frames meant to
-// stay in L2. Tiles are handed out in order by an atomic ticket: step s hands out the T1 column tiles of frame s, then the T2
-// row tiles of frame s - lookahead. A row tile waits until its frame's column tiles are all done (done1[f] == T1); a column
-// tile of frame f waits until the frame that used its ring slot before has been read completely (done2[f - ring] == T2). Every
-// wait is on tiles with smaller tickets, which are held by running CTAs (the grid is sized to be co-resident; a CTA holds its
-// current ticket and at most the next one), so the lowest unfinished tile can always proceed.
-struct Big2Sync {
-  unsigned long long next;  // ticket counter
-  unsigned int pad[2];
-};
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-template <int A, int B, int CW, int G>
-__global__ void __launch_bounds__(32 * (2 * G + 1)) big2_fused_kernel(const float2* __restrict__ zin, float2* work_ring, float2* __restrict__ out,
-                                                                      int64_t n_frames, int ring, int lookahead, Big2Sync* sync,
-                                                                      unsigned int* done1, unsigned int* done2) {
-  constexpr int MA = A * B, R = kBig2Row, M = MA * R, T = 32 * (2 * G + 1), T1 = R / CW, T2 = MA / (2 * G);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* tab4 = reinterpret_cast<float4*>(smem_raw);
-  c2* rows = reinterpret_cast<c2*>(tab4 + kBig2TabRows * 32);
-  float2* tw2r = reinterpret_cast<float2*>(rows + (2 * G + 1) * kBig2RowC2);
-  c2* u = rows;  // pass-1 exchange buffer aliases the rows buffer
-  static_assert(MA * CW <= kBig2RowC2 * (2 * G + 1), "the exchange buffer of pass 1 must fit in the rows buffer");
-  __shared__ long long s_ticket;
-  const int t = threadIdx.x;
-  big2_rows_tables<T>(tab4, tw2r, t);
-  const long long n_tickets = (static_cast<long long>(n_frames) + lookahead) * (T1 + T2);
-  if (t == 0) s_ticket = static_cast<long long>(atomicAdd(&sync->next, 1ull));
-  for (;;) {
-    __syncthreads();  // tables ready / previous tile done with shared memory / ticket visible
-    const long long tk = s_ticket;
-    __syncthreads();
-    if (tk >= n_tickets) break;
-    if (t == 0) s_ticket = static_cast<long long>(atomicAdd(&sync->next, 1ull));  // next ticket: its latency hides behind this tile
-    const int64_t step = tk / (T1 + T2);
-    const int r = static_cast<int>(tk - step * (T1 + T2));
-    if (r < T1) {
-      const int64_t f = step;
-      if (f >= n_frames) continue;
-      c2* wf = reinterpret_cast<c2*>(work_ring) + (f % ring) * static_cast<int64_t>(M);
-      if (f >= ring) {
-        if (t == 0)
-          while (ld_acquire_u32(done2 + (f - ring)) < static_cast<unsigned>(T2)) __nanosleep(64);
-        __syncthreads();
-      }
-      big2_cols_tile<A, B, CW, T>(reinterpret_cast<const c2*>(zin) + f * M, wf, r, u, t);
-      __threadfence();
-      __syncthreads();
-      if (t == 0) atomicAdd(done1 + f, 1u);
-    } else {
-      const int64_t f = step - lookahead;
-      if (f < 0) continue;
-      const c2* wf = reinterpret_cast<const c2*>(work_ring) + (f % ring) * static_cast<int64_t>(M);
-      if (t == 0)
-        while (ld_acquire_u32(done1 + f) < static_cast<unsigned>(T1)) __nanosleep(64);
-      __syncthreads();
-      big2_rows_tile<MA, G, true>(wf, out + f * (M + 1), r - T1, tab4, rows, tw2r, t);
-      __syncthreads();  // every load of the work frame has returned
-      if (t == 0) {
-        __threadfence();
-        atomicAdd(done2 + f, 1u);
-      }
-    }
+    for (int k2 = t; k2 < R / 2; k2 += T) emit(MA / 2 + static_cast<int64_t>(MA) * k2, rs[k2], rs[R - 1 - k2], twiddle(MA / 2, k2));
   }
 }
 
@@ -779,68 +673,32 @@ template <int A, int B, int CW, int G>
 int launch_big2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
   constexpr int MA = A * B, M = MA * kBig2Row;
   static_assert(MA % (2 * G) == 0, "rows per frame must split into CTAs of 2G rows");
-  static const bool persistent = getenv("CA_FFT_PERSISTENT") != nullptr;
-  auto ensure_work = [&](size_t need) -> int {
-    if (ctx->fft_work_bytes >= need) return CA_OK;
+  const size_t want = static_cast<size_t>(512) << 20;  // bounded work buffer: frames are processed in groups
+  const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
+  const size_t need = sizeof(float2) * M * static_cast<size_t>(group);
+  if (ctx->fft_work_bytes < need) {
     if (ctx->d_fft_work) cudaFree(ctx->d_fft_work);
     ctx->d_fft_work = nullptr;
     ctx->fft_work_bytes = 0;
     CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_fft_work, need));
     ctx->fft_work_bytes = need;
-    return CA_OK;
-  };
-  constexpr size_t smem_cols = sizeof(c2) * MA * CW;
-  constexpr size_t smem_rows = big2_rows_smem(G);
-  if (!persistent) {
-    const size_t want = static_cast<size_t>(512) << 20;  // bounded work buffer: frames are processed in groups
-    const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
-    int rc = ensure_work(sizeof(float2) * M * static_cast<size_t>(group));
-    if (rc) return rc;
-    auto cols = big2_cols_kernel<A, B, CW>;
-    auto rowsk = big2_rows_kernel<MA, G>;
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(rowsk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
-    for (int64_t b0 = 0; b0 < batch; b0 += group) {
-      const int64_t nb = std::min(group, batch - b0);
-      const float2* zin = reinterpret_cast<const float2*>(d_in) + b0 * M;
-      float2* out = reinterpret_cast<float2*>(d_out) + b0 * (M + 1);
-      cols<<<dim3(kBig2Row / CW, static_cast<unsigned>(nb)), 256, smem_cols, stream>>>(zin, ctx->d_fft_work);
-      CA_CUDA_OK(ctx, cudaGetLastError());
-      rowsk<<<static_cast<unsigned>(nb * (MA / (2 * G))), 32 * (2 * G + 1), smem_rows, stream>>>(ctx->d_fft_work, out);
-      CA_CUDA_OK(ctx, cudaGetLastError());
-      ctx->launches += 2;
-    }
-    return CA_OK;
   }
-  // persistent form: ring of work frames, counters zeroed per launch
-  auto kern = big2_fused_kernel<A, B, CW, G>;
-  constexpr size_t smem = smem_rows > smem_cols + sizeof(float4) * kBig2TabRows * 32 ? smem_rows : smem_cols + sizeof(float4) * kBig2TabRows * 32;
-  constexpr int threads = 32 * (2 * G + 1);
-  constexpr int tiles_per_frame = kBig2Row / CW + MA / (2 * G);
-  CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int per_sm = 0;
-  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) return fail(ctx, CA_ERR_CUDA, "ca_rfft_batched: the persistent FFT kernel does not fit on an SM");
-  const int64_t tiles = batch * tiles_per_frame;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, tiles));
-  // a frame's row tiles are dispatched `lookahead` frames after its column tiles: one grid's worth of tickets later, plus slack
-  static const int la_env = [] { const char* e = getenv("CA_FFT_LOOKAHEAD"); return e ? atoi(e) : 0; }();
-  const int lookahead = la_env > 0 ? la_env : static_cast<int>(grid / tiles_per_frame) + 2;
-  static const int ring_mb = [] { const char* e = getenv("CA_FFT_RING_MB"); return e ? std::max(1, atoi(e)) : 0; }();
-  const int ring = static_cast<int>(std::max<int64_t>(2 * lookahead + 2, (static_cast<int64_t>(ring_mb) << 20) / (sizeof(float2) * M)));
-  const size_t b_ring = sizeof(float2) * M * static_cast<size_t>(ring);
-  const size_t b_sync = 64 + sizeof(unsigned int) * 2 * static_cast<size_t>(batch);
-  int rc = ensure_work(b_ring + b_sync);
-  if (rc) return rc;
-  unsigned char* base = reinterpret_cast<unsigned char*>(ctx->d_fft_work);
-  Big2Sync* sync = reinterpret_cast<Big2Sync*>(base + b_ring);
-  unsigned int* done1 = reinterpret_cast<unsigned int*>(base + b_ring + 64);
-  unsigned int* done2 = done1 + batch;
-  CA_CUDA_OK(ctx, cudaMemsetAsync(sync, 0, b_sync, stream));
-  kern<<<grid, threads, smem, stream>>>(reinterpret_cast<const float2*>(d_in), reinterpret_cast<float2*>(base), reinterpret_cast<float2*>(d_out),
-                                        batch, ring, lookahead, sync, done1, done2);
-  CA_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += 1;
+  auto cols = big2_cols_kernel<A, B, CW>;
+  auto rowsk = big2_rows_kernel<MA, G>;
+  const size_t smem_cols = sizeof(c2) * MA * CW;
+  const size_t smem_rows = sizeof(float4) * 10 * 32 + sizeof(c2) * (16 * kXStride + 2) * (2 * G + 1) + sizeof(float2) * kBig2Row;
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(cols, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cols)));
+  CA_CUDA_OK(ctx, cudaFuncSetAttribute(rowsk, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
+  for (int64_t b0 = 0; b0 < batch; b0 += group) {
+    const int64_t nb = std::min(group, batch - b0);
+    const float2* zin = reinterpret_cast<const float2*>(d_in) + b0 * M;
+    float2* out = reinterpret_cast<float2*>(d_out) + b0 * (M + 1);
+    cols<<<dim3(kBig2Row / CW, static_cast<unsigned>(nb)), 256, smem_cols, stream>>>(zin, ctx->d_fft_work);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    rowsk<<<static_cast<unsigned>(nb * (MA / (2 * G))), 32 * (2 * G + 1), smem_rows, stream>>>(ctx->d_fft_work, out);
+    CA_CUDA_OK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+  }
   return CA_OK;
 }
 
@@ -1504,8 +1362,7 @@ template <int A, int B>
 int big2_variant(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
   static const int cw = [] { const char* e = getenv("CA_FFT_CW"); return e ? atoi(e) : (A * B <= 64 ? 32 : 16); }();
   static const int g = [] { const char* e = getenv("CA_FFT_G"); return e ? atoi(e) : (A * B <= 64 ? 4 : 8); }();
-  if constexpr (A * B < 512)
-    if (cw == 32) return g == 4 ? launch_big2<A, B, 32, 4>(ctx, d_in, batch, d_out, stream) : launch_big2<A, B, 32, 8>(ctx, d_in, batch, d_out, stream);
+  if (cw == 32 && A * B < 512) return g == 4 ? launch_big2<A, B, 32, 4>(ctx, d_in, batch, d_out, stream) : launch_big2<A, B, 32, 8>(ctx, d_in, batch, d_out, stream);
   return g == 4 ? launch_big2<A, B, 16, 4>(ctx, d_in, batch, d_out, stream) : launch_big2<A, B, 16, 8>(ctx, d_in, batch, d_out, stream);
 }
 
