@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(32) pitch_track_kernel(const __grid_constant__
     __syncwarp();
     if (lane == 0 && k + kRing - 1 < p.frames) {  // the slot read a frame ago is free: stage frame k + kRing - 1 into it
       const int nslot = static_cast<int>((k + kRing - 1) % kRing);
-      fence_proxy_async();
+      // (no fence.proxy.async, a MEMBAR.ALL.CTA: the slot's last generic-proxy accesses were loads whose values were consumed a
+      // whole frame ago, with warp barriers since)
       mbar_expect_tx(&sm.bar[nslot], staged_bytes);
       bulk_g2s(sm.ring[nslot], tu + static_cast<int64_t>(kRing - 1) * P, staged_bytes, &sm.bar[nslot]);
     }
@@ -400,8 +401,9 @@ __global__ void __launch_bounds__(32) pitch_track_kernel(const __grid_constant__
     if (len_frame > 0) {
       const int64_t n_next = n_k + len_frame;
       bool dead = false;
-      for (int i = lane; i < N; i += 32) dead |= note_done(sm.notes[i], n_next);
-      if (__any_sync(kFull, dead)) {
+      if (N > Np)  // only releasing notes can be done; every other note is in the played list
+        for (int i = lane; i < N; i += 32) dead |= note_done(sm.notes[i], n_next);
+      if (N > Np && __any_sync(kFull, dead)) {
         int w = 0;
         for (int i0 = 0; i0 < N; i0 += 32) {
           const int i = i0 + lane;

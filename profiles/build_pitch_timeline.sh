@@ -4,4 +4,4 @@ set -e
 cd "$(dirname "$0")/../cpp.audio_b200/csrc"
 mkdir -p ../../profiles/_tl
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -DCA_PITCH_TIMELINE "$@" -c pitch.cu -o ../../profiles/_tl/pitch_tl.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../profiles/_tl/libpitchtl.so capi.o stft.o rfft.o rfftw.o oscbank.o roundtrip.o ../../profiles/_tl/pitch_tl.o ramp.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../profiles/_tl/libpitchtl.so capi.o stft.o rfft.o rfftw.o oscbank.o roundtrip.o ../../profiles/_tl/pitch_tl.o ramp.o vocoder.o -lcudart
