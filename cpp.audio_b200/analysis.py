@@ -21,15 +21,19 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def rfft_batched(ctx: Context, x: torch.Tensor) -> torch.Tensor:
-    """Forward real FFT of every row of x [batch, n_fft] (float32, CUDA). Returns complex64 [batch, n_fft/2+1], unscaled."""
+def rfft_batched(ctx: Context, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Forward real FFT of every row of x [batch, n_fft] (float32, CUDA). Returns complex64 [batch, n_fft/2+1], unscaled.
+    `out`: a complex64 tensor of that shape to write into (saves the allocation for small, latency-bound batches)."""
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()):
         raise ValueError("x must be a contiguous float32 CUDA tensor [batch, n_fft]")
     batch, n = x.shape
-    out = torch.empty((batch, n // 2 + 1, 2), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.view_as_complex(torch.empty((batch, n // 2 + 1, 2), dtype=torch.float32, device=x.device))
+    elif not (out.is_cuda and out.dtype == torch.complex64 and tuple(out.shape) == (batch, n // 2 + 1) and out.is_contiguous()):
+        raise ValueError("out must be a contiguous complex64 CUDA tensor [batch, n_fft/2+1]")
     ctx.check(lib().ca_rfft_batched(ctx.handle, x.data_ptr(), n, batch, out.data_ptr(), _stream_ptr(x.device)),
               "ca_rfft_batched")
-    return torch.view_as_complex(out)
+    return out
 
 
 def irfft_batched(ctx: Context, X: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
