@@ -13,6 +13,7 @@
 //                        Segment storage comes from a global bump allocator in chunks (one atomic per ~500 tiles); when the
 //                        capacity guess is too small the kernel keeps counting and the host re-runs it with the exact size.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -456,6 +457,447 @@ __global__ void __launch_bounds__(32) pitch_track_kernel(const __grid_constant__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two warps per stream (the default). Tracking needs nothing from the note arithmetic: the played list is keyed by the tuned
+// pitches, and a released note leaves the pool after n_off + release + 17 samples, all integers known to the tracker. So warp 0
+// (tracker) runs frame j while warp 1 (voices) applies frame j-1's events and writes its segments; they meet at one CTA barrier
+// per frame and exchange a small record: the pool slot of every tuned entry (note-change / note-on) and the slots released.
+// Both warps compact the pool by the same rule, so slot numbers stay in step without being exchanged. A frame then costs
+// max(tracking, note arithmetic) instead of their sum.
+// ---------------------------------------------------------------------------------------------------------------
+struct FrameRec {
+  int32_t T;          // tuned entries of the frame
+  int32_t N_before;   // pool size before the frame's note-ons: slots >= N_before are new notes
+  int32_t N_after;    // pool size after them (before compaction)
+  int32_t Np_after;   // tracked notes after the frame
+  int32_t n_off;      // released slots
+  int64_t id_base;    // notes started before this frame: note-on of slot s gets id id_base + (s - N_before) + 1
+  int32_t slot[kMaxTuned];   // per tuned entry: pool slot, or -1
+  int32_t off[kMaxNotes];    // released slots
+};
+
+struct Track2Smem {
+  Note notes[kMaxNotes];           // voices warp
+  Tuned ring[kRing][32];
+  uint64_t bar[kRing];
+  FrameRec rec[2];
+  // tracker warp
+  double pl_pitch[2][kMaxNotes];
+  int32_t played[2][kMaxNotes];
+  int64_t tr_noff[kMaxNotes];      // sample of the first release step, -1 while tracked
+  int32_t tr_release[kMaxNotes];
+  int32_t tr_nmc[kMaxNotes];       // next_min_change of the slot
+  int32_t remap[kMaxNotes];        // tracker scratch
+  int32_t remap2[kMaxNotes];       // voices scratch
+  int32_t t_lo[kMaxTuned];
+  int32_t t_match[kMaxTuned];
+  float t_fv[kMaxTuned];
+  uint8_t t_new[kMaxTuned];
+  uint8_t keep[kMaxNotes];
+};
+
+__global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant__ TrackArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Track2Smem& sm = *reinterpret_cast<Track2Smem*>(smem_raw);
+  const PitchParams& p = a.p;
+  const int lane = threadIdx.x & 31;
+  const bool is_tracker = threadIdx.x < 32;
+  const unsigned lt = lanemask_lt();
+  const int64_t s = blockIdx.x;
+  const int P = p.P;
+  const double dtrack = p.max_track;
+  const Tuned* tu_base = a.tuned + s * p.frames * P;
+  const int n_staged = min(P, 32);
+  const uint32_t staged_bytes = static_cast<uint32_t>(n_staged * sizeof(Tuned));
+  constexpr int kAhead = 2;  // frames staged ahead of the tracker (the voices warp still reads the slot of the frame before)
+
+  // ---- tracker state ----
+  int N = 0, Np = 0;
+  int64_t started = 0, dropped = 0;
+  int32_t* played = sm.played[0];
+  int32_t* next_played = sm.played[1];
+  double* pl_pitch = sm.pl_pitch[0];
+  double* np_pitch = sm.pl_pitch[1];
+  const int32_t* tc = a.tcount + s * p.frames;
+  auto load_counts = [&](int64_t k0) { return k0 + lane < p.frames ? tc[k0 + lane] : 0; };
+  int cnt_cur = 0, cnt_next = 0;
+  // ---- voices state ----
+  int64_t tile = s * a.tiles_per_stream;
+  int64_t chunk_next = 0, chunk_end = 0;
+
+  if (is_tracker) {
+    cnt_cur = load_counts(0);
+    cnt_next = load_counts(32);
+    if (lane == 0) {
+      for (int i = 0; i < kRing; ++i) mbar_init(&sm.bar[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fence_proxy_async();
+      for (int f = 0; f < kAhead && f < p.frames; ++f) {
+        mbar_expect_tx(&sm.bar[f], staged_bytes);
+        bulk_g2s(sm.ring[f], tu_base + static_cast<int64_t>(f) * P, staged_bytes, &sm.bar[f]);
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int64_t it = 0; it <= p.frames; ++it) {
+    if (is_tracker) {
+      // ================= tracker: frame k = it =================
+      const int64_t k = it;
+      if (k < p.frames) {
+        const Tuned* tu = tu_base + k * P;
+        FrameRec& rec = sm.rec[k & 1];
+        if ((k & 31) == 0 && k > 0) {
+          cnt_cur = cnt_next;
+          cnt_next = load_counts(k + 32);
+        }
+        const int T = __shfl_sync(kFull, cnt_cur, static_cast<int>(k & 31));
+        const int slot = static_cast<int>(k % kRing);
+        mbar_wait(&sm.bar[slot], static_cast<uint32_t>((k / kRing) & 1));
+        Tuned e0{};
+        if (lane < n_staged) e0 = sm.ring[slot][lane];
+        if (lane == 0 && k + kAhead < p.frames) {  // slot of frame k + kAhead: last read by the voices warp an iteration ago
+          const int nslot = static_cast<int>((k + kAhead) % kRing);
+          mbar_expect_tx(&sm.bar[nslot], staged_bytes);
+          bulk_g2s(sm.ring[nslot], tu + static_cast<int64_t>(kAhead) * P, staged_bytes, &sm.bar[nslot]);
+        }
+        const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
+        const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
+        auto entry = [&](int i0, int i) -> Tuned { return i0 == 0 ? e0 : tu[i]; };
+        int kept = 0, n_off = 0;
+        bool any_new = false;
+        if (T <= 32 && Np <= 32) {
+          const bool has = lane < T;
+          int lo = 0, mt = -1;
+          if (has) {
+            const double lo_t = e0.pitch - dtrack, hi_t = e0.pitch + dtrack;
+            for (int j = 0; j < Np; ++j) lo += pl_pitch[j] < lo_t ? 1 : 0;
+            if (lo < Np && pl_pitch[lo] <= hi_t) mt = lo;
+          }
+          const int prev_lo = __shfl_up_sync(kFull, lo, 1), prev_mt = __shfl_up_sync(kFull, mt, 1);
+          const bool bad = has && lane > 0 && lo < prev_lo + (prev_mt >= 0 ? 1 : 0);
+          if (__any_sync(kFull, bad)) {
+            if (lane == 0) {
+              int itp = 0;
+              for (int i = 0; i < T; ++i) {
+                const double tp = sm.ring[slot][i].pitch;
+                sm.t_match[i] = -1;
+                for (; itp < Np; ++itp) {
+                  const double pp = pl_pitch[itp];
+                  if (pp < tp - dtrack) continue;
+                  if (pp <= tp + dtrack) {
+                    sm.t_match[i] = itp;
+                    ++itp;
+                  }
+                  break;
+                }
+              }
+            }
+            __syncwarp();
+            if (has) mt = sm.t_match[lane];
+          }
+          const unsigned keepmask = __reduce_or_sync(kFull, mt >= 0 ? 1u << mt : 0u);
+          kept = __popc(keepmask);
+          const unsigned playedmask = Np >= 32 ? kFull : ((1u << Np) - 1u);
+          const unsigned offmask = playedmask & ~keepmask;
+          n_off = __popc(offmask);
+          if (lane < Np) {
+            const int note = played[lane];
+            if ((keepmask >> lane) & 1) next_played[__popc(keepmask & lt)] = note;
+            else {  // NoteOff
+              rec.off[__popc(offmask & lt)] = note;
+              sm.tr_noff[note] = n_k;
+              sm.tr_release[note] = max(sm.tr_nmc[note], p.R);
+            }
+          }
+          if (has) {
+            int sl = -1;
+            if (mt >= 0) {
+              sl = played[mt];
+              sm.tr_nmc[sl] = e0.min_change;
+              np_pitch[__popc(keepmask & ((1u << mt) - 1u))] = e0.pitch;
+            }
+            rec.slot[lane] = sl;
+            const bool is_new = mt < 0 && e0.volume > 0;
+            any_new = is_new;
+            sm.t_new[lane] = is_new;
+            sm.t_fv[lane] = static_cast<float>(e0.vol);
+          }
+          any_new = __any_sync(kFull, any_new);
+        } else {
+          bool bad = false;
+          for (int i0 = 0; i0 < T; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < T) {
+              const double tp = entry(i0, i).pitch;
+              const double lo_t = tp - dtrack, hi_t = tp + dtrack;
+              int lo = 0, hi = Np;
+              while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (pl_pitch[mid] < lo_t) lo = mid + 1;
+                else hi = mid;
+              }
+              sm.t_lo[i] = lo;
+              sm.t_match[i] = (lo < Np && pl_pitch[lo] <= hi_t) ? lo : -1;
+            }
+          }
+          for (int j = lane; j < Np; j += 32) sm.keep[j] = 0;
+          __syncwarp();
+          for (int i = lane; i < T; i += 32)
+            if (i > 0 && sm.t_lo[i] < sm.t_lo[i - 1] + (sm.t_match[i - 1] >= 0 ? 1 : 0)) bad = true;
+          if (__any_sync(kFull, bad)) {
+            if (lane == 0) {
+              int itp = 0;
+              for (int i = 0; i < T; ++i) {
+                const double tp = tu[i].pitch;
+                sm.t_match[i] = -1;
+                for (; itp < Np; ++itp) {
+                  const double pp = pl_pitch[itp];
+                  if (pp < tp - dtrack) continue;
+                  if (pp <= tp + dtrack) {
+                    sm.t_match[i] = itp;
+                    ++itp;
+                  }
+                  break;
+                }
+              }
+            }
+            __syncwarp();
+          }
+          for (int i = lane; i < T; i += 32)
+            if (sm.t_match[i] >= 0) sm.keep[sm.t_match[i]] = 1;
+          __syncwarp();
+          for (int j0 = 0; j0 < Np; j0 += 32) {
+            const int j = j0 + lane;
+            const bool in = j < Np;
+            const bool kp = in && sm.keep[j];
+            const bool off = in && !kp;
+            const unsigned m = __ballot_sync(kFull, kp), mo = __ballot_sync(kFull, off);
+            if (kp) {
+              const int pos = kept + __popc(m & lt);
+              next_played[pos] = played[j];
+              sm.remap[j] = pos;
+            }
+            if (off) {
+              const int note = played[j];
+              rec.off[n_off + __popc(mo & lt)] = note;
+              sm.tr_noff[note] = n_k;
+              sm.tr_release[note] = max(sm.tr_nmc[note], p.R);
+            }
+            kept += __popc(m);
+            n_off += __popc(mo);
+          }
+          __syncwarp();
+          for (int i0 = 0; i0 < T; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < T) {
+              const Tuned e = entry(i0, i);
+              const int mt = sm.t_match[i];
+              int sl = -1;
+              if (mt >= 0) {
+                sl = played[mt];
+                sm.tr_nmc[sl] = e.min_change;
+                np_pitch[sm.remap[mt]] = e.pitch;
+              }
+              rec.slot[i] = sl;
+              const bool is_new = mt < 0 && e.volume > 0;
+              sm.t_new[i] = is_new;
+              sm.t_fv[i] = static_cast<float>(e.vol);
+              any_new |= is_new;
+            }
+          }
+          any_new = __any_sync(kFull, any_new);
+        }
+        __syncwarp();
+        const int N_before = N;
+        const int64_t id_base = started;
+        int M = kept;
+        if (any_new) {
+          int n_new = 0;
+          for (int i0 = 0; i0 < T; i0 += 32) n_new += __popc(__ballot_sync(kFull, i0 + lane < T && sm.t_new[i0 + lane]));
+          const int room = max(0, p.max_channels - N);
+          const int accepted = min(n_new, room);
+          for (int i0 = 0; i0 < T; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < T && sm.t_new[i]) {
+              const float fv = sm.t_fv[i];
+              int rank = 0;
+              for (int j = 0; j < T; ++j)
+                if (sm.t_new[j] && (sm.t_fv[j] > fv || (sm.t_fv[j] == fv && j < i))) ++rank;
+              if (rank < accepted) {
+                const Tuned e = entry(i0, i);
+                const int sl = N + rank;
+                rec.slot[i] = sl;
+                sm.tr_noff[sl] = -1;
+                sm.tr_release[sl] = 0;
+                sm.tr_nmc[sl] = e.min_change;
+                next_played[kept + rank] = sl;
+                np_pitch[kept + rank] = e.pitch;
+              }
+            }
+          }
+          started += n_new;
+          dropped += n_new - accepted;
+          N += accepted;
+          M += accepted;
+          __syncwarp();
+        }
+        bool unsorted = false;
+        for (int j = lane; j < M; j += 32)
+          if (j > 0 && np_pitch[j - 1] > np_pitch[j]) unsorted = true;
+        if (__any_sync(kFull, unsorted)) {
+          for (int j = lane; j < M; j += 32) {
+            const double pj = np_pitch[j];
+            int rank = 0;
+            for (int l = 0; l < M; ++l) {
+              const double pl = np_pitch[l];
+              if (pl < pj || (pl == pj && l < j)) ++rank;
+            }
+            played[rank] = next_played[j];
+            pl_pitch[rank] = pj;
+          }
+          __syncwarp();
+        } else {
+          int32_t* ti = played;
+          played = next_played;
+          next_played = ti;
+          double* td = pl_pitch;
+          pl_pitch = np_pitch;
+          np_pitch = td;
+        }
+        Np = M;
+        if (lane == 0) {
+          rec.T = T;
+          rec.N_before = N_before;
+          rec.N_after = N;
+          rec.Np_after = Np;
+          rec.n_off = n_off;
+          rec.id_base = id_base;
+        }
+        // pool compaction, by the rule the voices warp applies to its own copy of the pool
+        if (len_frame > 0 && N > Np) {
+          const int64_t n_next = n_k + len_frame;
+          auto done = [&](int i) { return sm.tr_noff[i] >= 0 && n_next >= sm.tr_noff[i] + sm.tr_release[i] + 17; };
+          bool dead = false;
+          for (int i = lane; i < N; i += 32) dead |= done(i);
+          if (__any_sync(kFull, dead)) {
+            int w = 0;
+            for (int i0 = 0; i0 < N; i0 += 32) {
+              const int i = i0 + lane;
+              int64_t t_noff = 0;
+              int32_t t_rel = 0, t_nmc = 0;
+              bool alive = false;
+              if (i < N) {
+                alive = !done(i);
+                t_noff = sm.tr_noff[i];
+                t_rel = sm.tr_release[i];
+                t_nmc = sm.tr_nmc[i];
+              }
+              const unsigned m = __ballot_sync(kFull, alive);
+              const int pos = w + __popc(m & lt);
+              if (i < N) sm.remap[i] = alive ? pos : -1;
+              __syncwarp();
+              if (alive && pos != i) {
+                sm.tr_noff[pos] = t_noff;
+                sm.tr_release[pos] = t_rel;
+                sm.tr_nmc[pos] = t_nmc;
+              }
+              __syncwarp();
+              w += __popc(m);
+            }
+            for (int j = lane; j < Np; j += 32) played[j] = sm.remap[played[j]];
+            N = w;
+            __syncwarp();
+          }
+        }
+      }
+    } else {
+      // ================= voices: frame k = it - 1 =================
+      const int64_t k = it - 1;
+      if (k >= 0) {
+        const Tuned* tu = tu_base + k * P;
+        const FrameRec& rec = sm.rec[k & 1];
+        const int slot = static_cast<int>(k % kRing);
+        const int T = rec.T, N_before = rec.N_before, NN = rec.N_after;
+        const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
+        const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
+        for (int j = lane; j < rec.n_off; j += 32) note_off(p, sm.notes[rec.off[j]], n_k);
+        for (int i = lane; i < T; i += 32) {
+          const int sl = rec.slot[i];
+          if (sl >= 0) {
+            const Tuned e = i < 32 ? sm.ring[slot][i] : tu[i];
+            if (sl >= N_before) sm.notes[sl] = note_on(p, e, rec.id_base + (sl - N_before) + 1, n_k);
+            else note_change(p, sm.notes[sl], e);
+          }
+        }
+        __syncwarp();
+        for (int off = 0; off < max(len_frame, 0) || off == 0; off += kMaxTile) {
+          const int len = min(kMaxTile, len_frame - off);
+          const int64_t n_k_tile = n_k + off;
+          int64_t base = 0;
+          bool ok = true;
+          if (len > 0 && NN > 0) {
+            if (chunk_next + NN > chunk_end) {
+              unsigned long long got = 0;
+              if (lane == 0) got = atomicAdd(a.seg_counter, static_cast<unsigned long long>(kSegChunk));
+              got = __shfl_sync(kFull, got, 0);
+              chunk_next = static_cast<int64_t>(got);
+              chunk_end = chunk_next + kSegChunk;
+            }
+            base = chunk_next;
+            chunk_next += NN;
+            ok = base + NN <= a.seg_capacity;
+          }
+          if (lane == 0) {
+            const bool filled = ok && len > 0 && NN > 0;
+            a.tile_begin[tile] = filled ? base : 0;
+            a.tile_end[tile] = filled ? base + NN : 0;
+            a.tile_s0[tile] = s * p.n_samples + n_k_tile;
+            a.tile_len[tile] = max(len, 0);
+            if (!ok) *a.overflow = 1;
+          }
+          ++tile;
+          if (len <= 0) break;
+          for (int idx = lane; idx < NN; idx += 32) {
+            const Segment g = emit_segment(p, sm.notes[idx], n_k_tile, len);
+            if (ok) a.segs[base + idx] = g;
+          }
+          __syncwarp();
+        }
+        if (len_frame > 0 && NN > rec.Np_after) {
+          const int64_t n_next = n_k + len_frame;
+          bool dead = false;
+          for (int i = lane; i < NN; i += 32) dead |= note_done(sm.notes[i], n_next);
+          if (__any_sync(kFull, dead)) {
+            int w = 0;
+            for (int i0 = 0; i0 < NN; i0 += 32) {
+              const int i = i0 + lane;
+              Note tmp;
+              bool alive = false;
+              if (i < NN) {
+                tmp = sm.notes[i];
+                alive = !note_done(tmp, n_next);
+              }
+              const unsigned m = __ballot_sync(kFull, alive);
+              const int pos = w + __popc(m & lt);
+              __syncwarp();
+              if (alive && pos != i) sm.notes[pos] = tmp;
+              __syncwarp();
+              w += __popc(m);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (is_tracker && lane == 0) {
+    a.stats[2 * s] = started;
+    a.stats[2 * s + 1] = dropped;
+  }
+}
+
 }  // namespace
 
 // Tuned lists, then tracking and segments, for `n_streams` streams of `p.frames` frames whose peak lists are on the device.
@@ -479,10 +921,16 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
   }
   CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
   CA_CUDA_OK(ctx, cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
-  CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrackSmem))));
+  static const bool one_warp = getenv("CA_PITCH_ONE_WARP") != nullptr;  // the single-warp form of the tracking kernel, for A/B
   TrackArgs ta{p, d_tuned, d_tcount, d_segs, d_counter, seg_capacity, d_tile_begin, d_tile_end, d_tile_s0, d_tile_len,
                n_tiles_per_stream, d_stats, d_overflow};
-  pitch_track_kernel<<<static_cast<unsigned>(n_streams), 32, sizeof(TrackSmem), st>>>(ta);
+  if (one_warp) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrackSmem))));
+    pitch_track_kernel<<<static_cast<unsigned>(n_streams), 32, sizeof(TrackSmem), st>>>(ta);
+  } else {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
+    pitch_track2_kernel<<<static_cast<unsigned>(n_streams), 64, sizeof(Track2Smem), st>>>(ta);
+  }
   CA_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches += 1;
   return CA_OK;
