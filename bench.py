@@ -419,7 +419,7 @@ def run_ours(args):
             "workload": f"C4 share: {S} streams x {SECONDS:g} s per GPU, pinned host audio in, pinned host stereo audio out",
             "output_samples_per_s": world * S * n_samples / rt_s, "ms_per_call": 1e3 * rt_s,
             "notes_started": int(rt_stats[:, 0].sum()), "h2d_bytes": int(rt_in.nbytes), "d2h_bytes": int(rt_out.nbytes),
-            "note": "analysis, pitch pipeline (one warp per stream, frame-sequential) and rendering all run on the device; only the audio crosses PCIe",
+            "note": "analysis, pitch pipeline (three warps per stream pipelined over frames) and rendering all run on the device; only the audio crosses PCIe",
         }
         # ---- FFT vocoder (source/rt.resynth.lib.vocoder.cpp) at the reference defaults, same streams as the modulator ----
         vc_car = pkg.pinned_empty(x_host_np.shape)

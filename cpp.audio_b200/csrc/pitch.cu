@@ -466,22 +466,30 @@ __global__ void __launch_bounds__(32) pitch_track_kernel(const __grid_constant__
 // Both warps compact the pool by the same rule, so slot numbers stay in step without being exchanged. A frame then costs
 // max(tracking, note arithmetic) instead of their sum.
 // ---------------------------------------------------------------------------------------------------------------
+struct GlideC {  // what Glide::start leaves behind for a changed note
+  double from, to, K, L, c1, P_m1, f_m1;
+  int32_t m;
+};
 struct FrameRec {
   int32_t T;          // tuned entries of the frame
   int32_t N_before;   // pool size before the frame's note-ons: slots >= N_before are new notes
   int32_t N_after;    // pool size after them (before compaction)
-  int32_t Np_after;   // tracked notes after the frame
   int32_t n_off;      // released slots
+  int32_t N_compact;  // pool size after the frame's compaction, -1: nothing left the pool
   int64_t id_base;    // notes started before this frame: note-on of slot s gets id id_base + (s - N_before) + 1
   int32_t slot[kMaxTuned];   // per tuned entry: pool slot, or -1
   int32_t off[kMaxNotes];    // released slots
+  int32_t remap[kMaxNotes];  // compaction: new slot of every pool entry, -1: gone (valid when N_compact >= 0)
+  Tuned entry[kMaxTuned];    // the tuned entries that carry an event (slot >= 0)
+  GlideC glide[kMaxTuned];   // three-warp form: the glide of every changed note, computed by the glide warp
 };
 
 struct Track2Smem {
   Note notes[kMaxNotes];           // voices warp
   Tuned ring[kRing][32];
   uint64_t bar[kRing];
-  FrameRec rec[2];
+  FrameRec rec[3];
+  double f_last[kMaxNotes];        // glide warp (three-warp form): last emitted increment of every slot
   // tracker warp
   double pl_pitch[2][kMaxNotes];
   int32_t played[2][kMaxNotes];
@@ -489,7 +497,6 @@ struct Track2Smem {
   int32_t tr_release[kMaxNotes];
   int32_t tr_nmc[kMaxNotes];       // next_min_change of the slot
   int32_t remap[kMaxNotes];        // tracker scratch
-  int32_t remap2[kMaxNotes];       // voices scratch
   int32_t t_lo[kMaxTuned];
   int32_t t_match[kMaxTuned];
   float t_fv[kMaxTuned];
@@ -497,12 +504,14 @@ struct Track2Smem {
   uint8_t keep[kMaxNotes];
 };
 
-__global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant__ TrackArgs a) {
+template <int kWarps>
+__global__ void __launch_bounds__(32 * kWarps) pitch_track2_kernel(const __grid_constant__ TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Track2Smem& sm = *reinterpret_cast<Track2Smem*>(smem_raw);
   const PitchParams& p = a.p;
   const int lane = threadIdx.x & 31;
-  const bool is_tracker = threadIdx.x < 32;
+  const int role = threadIdx.x >> 5;  // 0: tracker; two warps: 1 = voices; three warps: 1 = glides, 2 = segments
+  const bool is_tracker = role == 0;
   const unsigned lt = lanemask_lt();
   const int64_t s = blockIdx.x;
   const int P = p.P;
@@ -541,13 +550,13 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
   }
   __syncthreads();
 
-  for (int64_t it = 0; it <= p.frames; ++it) {
+  for (int64_t it = 0; it < p.frames + kWarps - 1; ++it) {
     if (is_tracker) {
       // ================= tracker: frame k = it =================
       const int64_t k = it;
       if (k < p.frames) {
         const Tuned* tu = tu_base + k * P;
-        FrameRec& rec = sm.rec[k & 1];
+        FrameRec& rec = sm.rec[k % kWarps];
         if ((k & 31) == 0 && k > 0) {
           cnt_cur = cnt_next;
           cnt_next = load_counts(k + 32);
@@ -619,6 +628,7 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
               np_pitch[__popc(keepmask & ((1u << mt) - 1u))] = e0.pitch;
             }
             rec.slot[lane] = sl;
+            if (sl >= 0) rec.entry[lane] = e0;
             const bool is_new = mt < 0 && e0.volume > 0;
             any_new = is_new;
             sm.t_new[lane] = is_new;
@@ -701,6 +711,7 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
                 np_pitch[sm.remap[mt]] = e.pitch;
               }
               rec.slot[i] = sl;
+              if (sl >= 0) rec.entry[i] = e;
               const bool is_new = mt < 0 && e.volume > 0;
               sm.t_new[i] = is_new;
               sm.t_fv[i] = static_cast<float>(e.vol);
@@ -729,6 +740,7 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
                 const Tuned e = entry(i0, i);
                 const int sl = N + rank;
                 rec.slot[i] = sl;
+                rec.entry[i] = e;
                 sm.tr_noff[sl] = -1;
                 sm.tr_release[sl] = 0;
                 sm.tr_nmc[sl] = e.min_change;
@@ -771,10 +783,11 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
           rec.T = T;
           rec.N_before = N_before;
           rec.N_after = N;
-          rec.Np_after = Np;
           rec.n_off = n_off;
+          rec.N_compact = -1;
           rec.id_base = id_base;
         }
+        __syncwarp();
         // pool compaction, by the rule the voices warp applies to its own copy of the pool
         if (len_frame > 0 && N > Np) {
           const int64_t n_next = n_k + len_frame;
@@ -796,7 +809,10 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
               }
               const unsigned m = __ballot_sync(kFull, alive);
               const int pos = w + __popc(m & lt);
-              if (i < N) sm.remap[i] = alive ? pos : -1;
+              if (i < N) {
+                sm.remap[i] = alive ? pos : -1;
+                rec.remap[i] = alive ? pos : -1;
+              }
               __syncwarp();
               if (alive && pos != i) {
                 sm.tr_noff[pos] = t_noff;
@@ -808,17 +824,54 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
             }
             for (int j = lane; j < Np; j += 32) played[j] = sm.remap[played[j]];
             N = w;
+            if (lane == 0) rec.N_compact = w;
+            __syncwarp();
+          }
+        }
+      }
+    } else if (kWarps == 3 && role == 1) {
+      // ================= glides (three-warp form): frame k = it - 1 =================
+      // The only thing a note's next glide needs from its past is the last emitted increment, and that follows from the glide
+      // itself: f_at(len_frame - 1). So this warp owns that one value per slot, runs Glide::start for the changed notes and
+      // leaves the constants in the record for the segments warp.
+      const int64_t k = it - 1;
+      if (k >= 0 && k < p.frames) {
+        FrameRec& rec = sm.rec[k % kWarps];
+        const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
+        const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
+        for (int i = lane; i < rec.T; i += 32) {
+          const int sl = rec.slot[i];
+          if (sl < 0) continue;
+          const double ai = rec.entry[i].ai;
+          if (sl >= rec.N_before) sm.f_last[sl] = ai;  // NoteOn: steady at ai
+          else {
+            Glide g;
+            g.start(sm.f_last[sl], ai, p.hop);
+            rec.glide[i] = GlideC{g.from, g.to, g.K, g.L, g.c1, g.P_m1, g.f_m1, g.m};
+            if (len_frame > 0) sm.f_last[sl] = g.f_at(len_frame - 1);
+          }
+        }
+        __syncwarp();
+        if (rec.N_compact >= 0) {
+          for (int i0 = 0; i0 < rec.N_after; i0 += 32) {
+            const int i = i0 + lane;
+            double v = 0;
+            int pos = -1;
+            if (i < rec.N_after) {
+              v = sm.f_last[i];
+              pos = rec.remap[i];
+            }
+            __syncwarp();
+            if (pos >= 0 && pos != i) sm.f_last[pos] = v;
             __syncwarp();
           }
         }
       }
     } else {
-      // ================= voices: frame k = it - 1 =================
-      const int64_t k = it - 1;
+      // ================= voices / segments: frame k = it - (kWarps - 1) =================
+      const int64_t k = it - (kWarps - 1);
       if (k >= 0) {
-        const Tuned* tu = tu_base + k * P;
-        const FrameRec& rec = sm.rec[k & 1];
-        const int slot = static_cast<int>(k % kRing);
+        const FrameRec& rec = sm.rec[k % kWarps];
         const int T = rec.T, N_before = rec.N_before, NN = rec.N_after;
         const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
         const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
@@ -826,9 +879,25 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
         for (int i = lane; i < T; i += 32) {
           const int sl = rec.slot[i];
           if (sl >= 0) {
-            const Tuned e = i < 32 ? sm.ring[slot][i] : tu[i];
+            const Tuned e = rec.entry[i];
             if (sl >= N_before) sm.notes[sl] = note_on(p, e, rec.id_base + (sl - N_before) + 1, n_k);
-            else note_change(p, sm.notes[sl], e);
+            else if (kWarps == 2) note_change(p, sm.notes[sl], e);
+            else {  // NoteChange with the glide the glide warp prepared (note_change, pitch.cuh)
+              Note& n = sm.notes[sl];
+              const GlideC& g = rec.glide[i];
+              n.pitch = e.pitch;
+              n.vol_x = static_cast<double>(0.1f * e.volume);
+              n.next_min_change = e.min_change;
+              n.glide.from = g.from;
+              n.glide.to = g.to;
+              n.glide.K = g.K;
+              n.glide.L = g.L;
+              n.glide.c1 = g.c1;
+              n.glide.P_m1 = g.P_m1;
+              n.glide.f_m1 = g.f_m1;
+              n.glide.m = g.m;
+              n.glide.i = 0;
+            }
           }
         }
         __syncwarp();
@@ -865,27 +934,18 @@ __global__ void __launch_bounds__(64) pitch_track2_kernel(const __grid_constant_
           }
           __syncwarp();
         }
-        if (len_frame > 0 && NN > rec.Np_after) {
-          const int64_t n_next = n_k + len_frame;
-          bool dead = false;
-          for (int i = lane; i < NN; i += 32) dead |= note_done(sm.notes[i], n_next);
-          if (__any_sync(kFull, dead)) {
-            int w = 0;
-            for (int i0 = 0; i0 < NN; i0 += 32) {
-              const int i = i0 + lane;
-              Note tmp;
-              bool alive = false;
-              if (i < NN) {
-                tmp = sm.notes[i];
-                alive = !note_done(tmp, n_next);
-              }
-              const unsigned m = __ballot_sync(kFull, alive);
-              const int pos = w + __popc(m & lt);
-              __syncwarp();
-              if (alive && pos != i) sm.notes[pos] = tmp;
-              __syncwarp();
-              w += __popc(m);
+        if (rec.N_compact >= 0) {  // the tracker's compaction, applied to this warp's copy of the pool
+          for (int i0 = 0; i0 < NN; i0 += 32) {
+            const int i = i0 + lane;
+            Note tmp;
+            int pos = -1;
+            if (i < NN) {
+              pos = rec.remap[i];
+              if (pos >= 0 && pos != i) tmp = sm.notes[i];
             }
+            __syncwarp();
+            if (pos >= 0 && pos != i) sm.notes[pos] = tmp;
+            __syncwarp();
           }
         }
       }
@@ -921,15 +981,18 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
   }
   CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
   CA_CUDA_OK(ctx, cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
-  static const bool one_warp = getenv("CA_PITCH_ONE_WARP") != nullptr;  // the single-warp form of the tracking kernel, for A/B
+  static const int n_warps = [] { const char* e = getenv("CA_PITCH_WARPS"); return e ? atoi(e) : 3; }();  // 1 / 2 / 3 warps per stream (A/B)
   TrackArgs ta{p, d_tuned, d_tcount, d_segs, d_counter, seg_capacity, d_tile_begin, d_tile_end, d_tile_s0, d_tile_len,
                n_tiles_per_stream, d_stats, d_overflow};
-  if (one_warp) {
+  if (n_warps == 1) {
     CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(TrackSmem))));
     pitch_track_kernel<<<static_cast<unsigned>(n_streams), 32, sizeof(TrackSmem), st>>>(ta);
+  } else if (n_warps == 2) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
+    pitch_track2_kernel<2><<<static_cast<unsigned>(n_streams), 64, sizeof(Track2Smem), st>>>(ta);
   } else {
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
-    pitch_track2_kernel<<<static_cast<unsigned>(n_streams), 64, sizeof(Track2Smem), st>>>(ta);
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
+    pitch_track2_kernel<3><<<static_cast<unsigned>(n_streams), 96, sizeof(Track2Smem), st>>>(ta);
   }
   CA_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches += 1;
