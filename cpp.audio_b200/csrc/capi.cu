@@ -49,6 +49,8 @@ void ca_destroy(ca_ctx* ctx) {
     if (d) cudaFree(d);
   for (int i = 0; i < 6; ++i)
     if (ctx->h_pinned[i]) cudaFreeHost(ctx->h_pinned[i]);
+  for (cudaStream_t ps : ctx->pipe_streams)
+    if (ps) cudaStreamDestroy(ps);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->own_stream2) cudaStreamDestroy(ctx->own_stream2);
   delete ctx;

@@ -968,7 +968,7 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
                           const float* d_peak_db, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
-                          int32_t* d_overflow, bool run_prefix, cudaStream_t st) {
+                          int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters) {
   if (p.P > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_peaks above 256 is not supported by the device pitch pipeline");
   if (p.max_channels > kMaxNotes) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_channels above 256 is not supported");
   const int64_t rows = n_streams * p.frames;
@@ -979,8 +979,10 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
     CA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
   }
-  CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
-  CA_CUDA_OK(ctx, cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
+  if (reset_counters) {
+    CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+    CA_CUDA_OK(ctx, cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
+  }
   static const int n_warps = [] { const char* e = getenv("CA_PITCH_WARPS"); return e ? atoi(e) : 3; }();  // 1 / 2 / 3 warps per stream (A/B)
   TrackArgs ta{p, d_tuned, d_tcount, d_segs, d_counter, seg_capacity, d_tile_begin, d_tile_end, d_tile_s0, d_tile_len,
                n_tiles_per_stream, d_stats, d_overflow};

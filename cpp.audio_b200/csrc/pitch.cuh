@@ -309,5 +309,5 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
                           const float* d_peak_db, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
-                          int32_t* d_overflow, bool run_prefix, cudaStream_t st);
+                          int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters = true);
 }  // namespace ca

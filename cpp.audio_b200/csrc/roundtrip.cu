@@ -234,6 +234,89 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
   return CA_OK;
 }
 
+
+// The device path as a pipeline over groups of streams: every group runs H2D -> K2 -> pitch pipeline -> rendering -> D2H on its
+// own CUDA stream, so the copies of one group overlap the (latency-bound) tracking kernel of the others. Returns
+// CA_OK with *overflowed = true when the segment buffer was too small (the caller grows it and takes the sequential path).
+int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, const float* h_x, int64_t n_samples, int64_t n_streams,
+                               int64_t frames, float* h_out, int64_t* h_stats, bool* overflowed, int64_t* needed) {
+  const int P = prm.stft.max_peaks;
+  const PitchParams pp = make_pitch_params(prm, n_samples, frames, P);
+  const size_t rows = static_cast<size_t>(frames) * n_streams, total = static_cast<size_t>(n_streams) * n_samples;
+  const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
+  const size_t b_tiles = (3 * sizeof(int64_t) + sizeof(int32_t)) * static_cast<size_t>(n_tiles);
+  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 16;  // stats, allocator counter, overflow flag
+  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * P);
+  if (!rc) rc = ensure_scratch(ctx, 9, sizeof(int32_t) * rows);
+  if (!rc) rc = ensure_scratch(ctx, 10, b_misc);
+  if (!rc) rc = ensure_scratch(ctx, 1, b_tiles);
+  if (!rc) rc = ensure_pinned(ctx, 0, b_misc);
+  const int64_t guess = std::max<int64_t>(n_tiles * std::min(prm.max_channels, 48), n_streams * 8192);
+  if (!rc && ctx->scratch_bytes[6] < sizeof(Segment) * static_cast<size_t>(guess)) rc = ensure_scratch(ctx, 6, sizeof(Segment) * guess);
+  if (rc) return rc;
+  const int groups = static_cast<int>(std::min<int64_t>(4, n_streams));
+  for (int g = 0; g < groups; ++g)
+    if (!ctx->pipe_streams[g]) CA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_streams[g], cudaStreamNonBlocking));
+  float* d_x = static_cast<float*>(ctx->d_scratch[0]);
+  int32_t* d_pbin = static_cast<int32_t*>(ctx->d_scratch[2]);
+  float* d_poff = static_cast<float*>(ctx->d_scratch[3]);
+  float* d_pdb = static_cast<float*>(ctx->d_scratch[4]);
+  int32_t* d_pcnt = static_cast<int32_t*>(ctx->d_scratch[5]);
+  Tuned* d_tuned = static_cast<Tuned*>(ctx->d_scratch[8]);
+  int32_t* d_tcount = static_cast<int32_t*>(ctx->d_scratch[9]);
+  float* d_out = static_cast<float*>(ctx->d_scratch[7]);
+  int64_t* d_begin = static_cast<int64_t*>(ctx->d_scratch[1]);
+  int64_t* d_end = d_begin + n_tiles;
+  int64_t* d_s0 = d_end + n_tiles;
+  int32_t* d_len = reinterpret_cast<int32_t*>(d_s0 + n_tiles);
+  int64_t* d_stats = static_cast<int64_t*>(ctx->d_scratch[10]);
+  unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(d_stats + 2 * n_streams);
+  int32_t* d_overflow = reinterpret_cast<int32_t*>(d_counter + 1);
+  int64_t* h_misc = static_cast<int64_t*>(ctx->h_pinned[0]);
+  const int64_t capacity = static_cast<int64_t>(ctx->scratch_bytes[6] / sizeof(Segment));
+  // the allocator counter and the overflow flag are shared by the groups: reset once, before any group starts
+  cudaStream_t s0 = ctx->pipe_streams[0];
+  cudaEvent_t ready = nullptr;
+  CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, 16, s0));
+  CA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  CA_CUDA_OK(ctx, cudaEventRecord(ready, s0));
+  ctx->stft_freq_as_offset = true;
+  for (int g = 0; g < groups && !rc; ++g) {
+    cudaStream_t sg = ctx->pipe_streams[g];
+    const int64_t a0 = n_streams * g / groups, a1 = n_streams * (g + 1) / groups, ns = a1 - a0;
+    const size_t x0 = static_cast<size_t>(a0) * n_samples, r0 = static_cast<size_t>(a0) * frames;
+    const int64_t t0 = a0 * tps, nt = ns * tps;
+    if (g > 0) cudaStreamWaitEvent(sg, ready, 0);
+    cudaMemcpyAsync(d_x + x0, h_x + x0, sizeof(float) * ns * n_samples, cudaMemcpyHostToDevice, sg);
+    rc = stft_analyze(ctx, d_x + x0, n_samples, ns, n_samples, nullptr, 0, d_pbin + r0 * P, d_poff + r0 * P, d_pdb + r0 * P, d_pcnt + r0, sg);
+    if (rc) break;
+    rc = pitch_pipeline_device(ctx, pp, ns, d_pbin + r0 * P, d_poff + r0 * P, d_pdb + r0 * P, d_pcnt + r0, d_tuned + r0 * P, d_tcount + r0,
+                               static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps, d_begin + t0, d_end + t0, d_s0 + t0, d_len + t0,
+                               d_stats + 2 * a0, d_counter, d_overflow, true, sg, false);
+    if (rc) break;
+    float* out_g = d_out + 2 * x0;  // tile_s0 holds group-relative sample indices
+    cudaMemsetAsync(out_g, 0, sizeof(float) * 2 * ns * n_samples, sg);  // samples before the first frame are silent
+    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin + t0, d_s0 + t0, d_len + t0, nt, out_g, 0, d_end + t0};
+    tracks_kernel<false><<<static_cast<unsigned>((nt + 3) / 4), 128, 0, sg>>>(ta);
+    ctx->launches += 1;
+    cudaMemcpyAsync(h_out + 2 * x0, out_g, sizeof(float) * 2 * ns * n_samples, cudaMemcpyDeviceToHost, sg);
+  }
+  ctx->stft_freq_as_offset = false;
+  cudaError_t err = cudaGetLastError();
+  for (int g = 0; g < groups; ++g) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->pipe_streams[g]);
+    if (err == cudaSuccess) err = e;
+  }
+  cudaEventDestroy(ready);
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(ctx, CA_ERR_CUDA, std::string("round trip (pipelined): ") + cudaGetErrorString(err));
+  CA_CUDA_OK(ctx, cudaMemcpy(h_misc, d_stats, b_misc, cudaMemcpyDeviceToHost));
+  *needed = h_misc[2 * n_streams];
+  *overflowed = *reinterpret_cast<const int32_t*>(h_misc + 2 * n_streams + 1) != 0;
+  if (!*overflowed && h_stats) memcpy(h_stats, h_misc, sizeof(int64_t) * 2 * n_streams);
+  return CA_OK;
+}
+
 }  // namespace
 
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
@@ -274,6 +357,15 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (!rc) rc = ensure_scratch(ctx, 5, std::max<size_t>(16, sizeof(int32_t) * rows));
   if (!rc) rc = ensure_pinned(ctx, 0, std::max<size_t>(16, sizeof(int32_t) * rows));
   if (rc) return rc;
+  static const bool env_sequential = getenv("CA_RT_SEQUENTIAL") != nullptr;  // one stream group, for A/B
+  if (rows && !host_pitch && !timing && !env_sequential && n_streams >= 2) {
+    bool overflowed = false;
+    int64_t needed = 0;
+    rc = roundtrip_device_pipelined(ctx, prm, h_x, n_samples, n_streams, frames, h_out, h_stats, &overflowed, &needed);
+    if (rc || !overflowed) return rc;
+    rc = ensure_scratch(ctx, 6, sizeof(Segment) * static_cast<size_t>(needed));  // rare: redo in one group with the exact size
+    if (rc) return rc;
+  }
   int32_t* h_cnt = static_cast<int32_t*>(ctx->h_pinned[0]);
   int cmax = 0;
   if (rows) {
