@@ -261,10 +261,8 @@ __device__ __forceinline__ void cta_untangle_all(const c2* Zs, float2* o, const 
   (cta_untangle<I, M1>(Zs, o, wpb, t), ...);
 }
 
-// kComplexOut: the rows are complex and stay complex (M c2 in, M c2 out in natural order, no untangling): the row pass of
-// the three-pass path for N >= 65536, in place.
-template <int M1, bool kComplexOut>
-__global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* in, float2* out, const int64_t batch) {  // (may alias: complex mode is in place)
+template <int M1>
+__global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* __restrict__ in, float2* __restrict__ out, const int64_t batch) {
   using C = CtaFftCfg<M1>;
   constexpr int M = C::M, M2 = C::M2, T = C::T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -332,11 +330,7 @@ __global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* in, floa
       for (int k2 = 0; k2 < 32; ++k2) row[lane + 32 * k2] = A[k2];  // Z[k1 + M1*(lane + 32*k2')] at position k2 = lane + 32*k2'
     }
     __syncthreads();
-    if constexpr (kComplexOut) {
-      float2* o = out + frame * M;
-#pragma unroll 8
-      for (int k = t; k < M; k += T) o[k] = upk(Ys[(k % M1) * C::kRowC2 + k / M1]);
-    } else {
+    {
       // ---- step C: untangle, k = t + T*i ----
       float2* o = out + frame * (M + 1);
       cta_untangle_all<M1>(Ys, o, wpb, t, std::make_integer_sequence<int, M / (2 * T)>{});
@@ -351,7 +345,7 @@ __global__ void __launch_bounds__(32 * M1) rfft_cta_kernel(const float* in, floa
 template <int M1>
 int launch_cta(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
   using C = CtaFftCfg<M1>;
-  auto kern = rfft_cta_kernel<M1, false>;
+  auto kern = rfft_cta_kernel<M1>;
   const size_t smem = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kRowC2 * M1;
   int per_sm = 0;
   CA_KERNEL_SETUP(ctx, kern, C::T, smem, per_sm);
@@ -365,157 +359,14 @@ int launch_cta(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cuda
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// N >= 65536: three passes through HBM, M = N/2 = MA x 8192 complex points, n = 8192*r + c, k = kA + MA*k2.
-//   pass A  one thread per column c: MA-point FFT over r in registers (coalesced strided loads), twiddle W_M^(c*kA),
-//           work[kA][c]                                                                         (streaming, 8M + 8M bytes)
-//   pass B  rfft_cta_kernel<8, complex>: 8192-point row FFTs, in place                          (8M + 8M bytes)
-//   pass C  untangling with the transposition [kA][k2] -> k: a CTA takes 32 consecutive k2 of every row and the
-//           mirrored range, and writes X[k] and X[M-k] as contiguous runs of 32*MA bins          (8M + 8M bytes)
-// 48M bytes moved for 16M algorithmic: the ceiling of this path is a third of the HBM roofline. (A frame that stays
-// on chip across a thread-block cluster is the next step; see DESIGN.md.)
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kRowLen = 8192;
-
-template <int MA>
-__global__ void __launch_bounds__(256) bigfft_cols_kernel(const float2* __restrict__ zin, float2* __restrict__ work, const int64_t n_frames) {
-  constexpr int M = MA * kRowLen;
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t frame = gid / kRowLen;
-  const int c = static_cast<int>(gid - frame * kRowLen);
-  if (frame >= n_frames) return;
-  const c2* src = reinterpret_cast<const c2*>(zin) + frame * M + c;
-  c2 v[MA];
-#pragma unroll
-  for (int r = 0; r < MA; ++r) v[bitrev(r, ilog2(MA))] = __ldg(src + static_cast<int64_t>(r) * kRowLen);
-  DitP<MA, MA, 0>::run(v);
-  // twiddle W_M^(c*k), k = B*a + b: wb[b] = w^b and wa[a] = (w^B)^a by binary powers of w = W_M^c (depth <= 6)
-  constexpr int B = MA < 8 ? MA : 8, A = MA / B;
-  c2 wb[B];
-  {
-    float s, cs;
-    sincospif(static_cast<float>(c) / (M / 2), &s, &cs);  // exact argument: c < 2^13, M/2 a power of two
-    wb[1] = pk(cs, -s);
-  }
-  if constexpr (B > 2) cpow_all<B>(wb, std::make_integer_sequence<int, B - 2>{});
-  c2 wa[A > 1 ? A : 2];
-  if constexpr (A > 1) {
-    const float2 h = upk(wb[B / 2]);
-    wa[1] = cmul_tw(wb[B / 2], TwP{h.x, pk(-h.y, h.y)});  // w^B
-    if constexpr (A > 2) cpow_all<A>(wa, std::make_integer_sequence<int, A - 2>{});
-  }
-  c2* dst = reinterpret_cast<c2*>(work) + frame * M + c;
-#pragma unroll
-  for (int k = 0; k < MA; ++k) {
-    const int a = k / B, b = k % B;
-    c2 y = v[k];
-    if (b) {
-      const float2 q = upk(wb[b]);
-      y = cmul_tw(y, TwP{q.x, pk(-q.y, q.y)});
-    }
-    if (a) {
-      const float2 q = upk(wa[a]);
-      y = cmul_tw(y, TwP{q.x, pk(-q.y, q.y)});
-    }
-    dst[static_cast<int64_t>(k) * kRowLen] = y;
-  }
-}
-
-// pass C. grid (kRowLen/64, frames): CTA b takes k2 in [32b, 32b+32) and the mirrored rows' k2 in [R-32b-32, R-32b].
-template <int MA>
-__global__ void __launch_bounds__(256) bigfft_untangle_kernel(const float2* __restrict__ work, float2* __restrict__ out) {
-  constexpr int R = kRowLen, M = MA * R;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  c2* ta = reinterpret_cast<c2*>(smem_raw);  // [MA][33]: Z[kA + MA*(k2_0 + j)]
-  c2* tb = ta + MA * 33;                     // [MA][34]: row kA, k2 = R - k2_0 - 32 + j, j = 0..32
-  const c2* z = reinterpret_cast<const c2*>(work) + static_cast<int64_t>(blockIdx.y) * M;
-  float2* o = out + static_cast<int64_t>(blockIdx.y) * (M + 1);
-  const int k2_0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < MA * 32; i += 256) {
-    const int kA = i >> 5, j = i & 31;
-    ta[kA * 33 + j] = __ldg(z + static_cast<int64_t>(kA) * R + k2_0 + j);
-  }
-  for (int i = threadIdx.x; i < MA * 33; i += 256) {
-    const int kA = i / 33, j = i - kA * 33;
-    const int k2 = (R - k2_0 - 32 + j) & (R - 1);  // j = 32 wraps to 0 for the first CTA
-    tb[kA * 34 + j] = __ldg(z + static_cast<int64_t>(kA) * R + k2);
-  }
-  __syncthreads();
-  // outputs k = kA + MA*k2 for k2 in the range (contiguous: 32*MA bins) and their mirrors M - k
-  for (int i = threadIdx.x; i < MA * 32; i += 256) {
-    const int j = i / MA, kA = i - j * MA;  // kA fastest: consecutive threads write consecutive bins
-    const int k2 = k2_0 + j;
-    const int64_t k = kA + static_cast<int64_t>(MA) * k2;
-    // M - k = (MA - kA) + MA*(R - 1 - k2) for kA > 0, MA*((R - k2) % R) for kA = 0
-    const int mA = kA ? MA - kA : 0;
-    const int mj = kA ? 31 - j : 32 - j;  // index into tb: k2' = R - k2_0 - 32 + mj
-    const c2 zk = ta[kA * 33 + j], zm = tb[mA * 34 + mj];
-    float s, c;
-    sincospif(static_cast<float>(k) / M, &s, &c);  // W_N^k = exp(-i pi k / M); k < 2^24 and M a power of two: exact argument
-    const TwP wp{-0.5f * s, pk(0.5f * c, -0.5f * c)};  // 0.5 * (-i) * W_N^k
-    const c2 E = add2(zk, cconj(zm));
-    const c2 T = cmul_tw(csub(zk, cconj(zm)), wp);
-    o[k] = upk(fma2(bc(0.5f), E, T));
-    o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(T))));
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // k = M/2 = 0 + MA*(R/2) pairs with itself: X[M/2] = conj(Z[M/2])
-    const float2 zh = upk(__ldg(z + R / 2));
-    o[M / 2] = make_float2(zh.x, -zh.y);
-  }
-}
-
-template <int MA>
-int launch_big(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
-  constexpr int M = MA * kRowLen;
-  using C = CtaFftCfg<8>;
-  // The work buffer is sized to stay resident in the 126 MB L2: the column pass leaves it there, the row pass transforms it
-  // in place and the untangling pass reads it back, so only the input and the output cross HBM (CA_FFT_GROUP_MB: sweep).
-  static const size_t group_mb = [] {
-    const char* e = getenv("CA_FFT_GROUP_MB");
-    return static_cast<size_t>(e ? std::max(1, atoi(e)) : 512);
-  }();
-  const size_t want = group_mb << 20;
-  const int64_t group = std::max<int64_t>(1, std::min<int64_t>(batch, static_cast<int64_t>(want / (sizeof(float2) * M))));
-  const size_t need = sizeof(float2) * M * static_cast<size_t>(group);
-  if (ctx->fft_work_bytes < need) {
-    if (ctx->d_fft_work) cudaFree(ctx->d_fft_work);
-    ctx->d_fft_work = nullptr;
-    ctx->fft_work_bytes = 0;
-    CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_fft_work, need));
-    ctx->fft_work_bytes = need;
-  }
-  auto rows = rfft_cta_kernel<8, true>;
-  const size_t smem_rows = sizeof(float4) * C::kRows * 32 + sizeof(c2) * C::kRowC2 * 8;
-  CA_CUDA_OK(ctx, cudaFuncSetAttribute(rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_rows)));
-  int per_sm = 0;
-  CA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows, C::T, smem_rows));
-  if (per_sm < 1) per_sm = 1;
-  const size_t smem_unt = sizeof(c2) * MA * (33 + 34);
-  for (int64_t b0 = 0; b0 < batch; b0 += group) {
-    const int64_t nb = std::min(group, batch - b0);
-    const float2* zin = reinterpret_cast<const float2*>(d_in) + b0 * M;
-    float2* out = reinterpret_cast<float2*>(d_out) + b0 * (M + 1);
-    bigfft_cols_kernel<MA><<<static_cast<unsigned>(nb * kRowLen / 256), 256, 0, stream>>>(zin, ctx->d_fft_work, nb);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    const int64_t n_rows = nb * MA;
-    const int64_t grid = std::min<int64_t>(static_cast<int64_t>(ctx->sm_count) * per_sm, n_rows);
-    rows<<<static_cast<unsigned>(grid), C::T, smem_rows, stream>>>(reinterpret_cast<const float*>(ctx->d_fft_work), ctx->d_fft_work, n_rows);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    bigfft_untangle_kernel<MA><<<dim3(kRowLen / 64, static_cast<unsigned>(nb)), 256, smem_unt, stream>>>(ctx->d_fft_work, out);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches += 3;
-  }
-  return CA_OK;
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// N >= 65536, two passes through HBM (default): M = N/2 = MA x 1024 complex points, n = 1024*r + c, k = kA + MA*k2.
+// N >= 65536, two passes through HBM: M = N/2 = MA x 1024 complex points, n = 1024*r + c, k = kA + MA*k2.
 //   pass 1  big2_cols_kernel: a CTA takes 16 adjacent columns c (128-byte runs in HBM) and all MA rows: MA = A x B point FFT
 //           down each column in two register stages with one shared-memory exchange, twiddle W_M^(c*kA), work[kA][c]
 //   pass 2  big2_rows_kernel: a CTA takes 8 adjacent rows kA, the 8 mirrored rows MA - kA (and row MA/2 in the last CTA of a
 //           frame): one warp per row runs the 1024-point warp-level FFT in shared memory, then the whole CTA untangles
 //           X[k], X[M-k] from the two row sets and writes them in runs of 8 consecutive bins (64 bytes)
-// 32M bytes moved for 16M algorithmic: the ceiling is half of the HBM roofline (the three-pass path above: a third).
+// 32M bytes moved for 16M algorithmic: the ceiling is half of the HBM roofline. (The three-pass path this replaced — thread per
+// column MA-point FFTs, 8192-point rows in place, untangling transposition — reached 24-27 %, profiles/README.md.)
 // (Tried and removed: ONE persistent launch that runs both passes with in-order tickets and keeps the work frames in an L2-sized
 // ring. Correct, but 25-70 % slower, profiles/fft_fused_sweep_r01.txt: both passes must share one CTA shape, which leaves the
 // column pass at 9-17 warps per SM instead of 30, and the row pass is issue-bound rather than HBM-bound, profiles/ncu_big2_r01.json.)
@@ -1379,7 +1230,6 @@ int big2_variant(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cu
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
-  static const bool three_pass = getenv("CA_FFT_THREE_PASS") != nullptr;  // N >= 65536: the previous path, for A/B
   switch (n_fft) {
     case 512: return launch_warp<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1024: return launch_warp<16, 8>(ctx, d_in, batch, d_out, stream);
@@ -1388,11 +1238,11 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
     case 32768: return launch_cta<16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 16: return three_pass ? launch_big<4>(ctx, d_in, batch, d_out, stream) : big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
-    case 1 << 17: return three_pass ? launch_big<8>(ctx, d_in, batch, d_out, stream) : big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
-    case 1 << 18: return three_pass ? launch_big<16>(ctx, d_in, batch, d_out, stream) : big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 19: return three_pass ? launch_big<32>(ctx, d_in, batch, d_out, stream) : big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 20: return three_pass ? launch_big<64>(ctx, d_in, batch, d_out, stream) : big2_variant<32, 16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 16: return big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 17: return big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 18: return big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 19: return big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 20: return big2_variant<32, 16>(ctx, d_in, batch, d_out, stream);
     default: break;
   }
   return fail(ctx, CA_ERR_UNSUPPORTED, "rfft_warp: unsupported n_fft");
