@@ -121,3 +121,37 @@ def test_job_output_equals_the_library_call(tool, tmp_path, pkg, ctx, wl):
         assert sr_out == sr and y.shape == (x.shape[1] + sr, 2)
         assert np.abs(y).max() > 0.05
         assert np.array_equal(y, ref[i, :y.shape[0]])
+
+
+@pytest.mark.gpu
+def test_job_with_carrier_adds_the_vocoder_mix(tool, tmp_path, pkg, ctx, wl):
+    """voice = modulator, carrier file = carrier (rt.resynth.lib.cpp:1378-1420): output = resynthesis + voice_volume * voice +
+    carrier_volume * carrier + vocoder_volume * vocoded, the mix going to both channels."""
+    sr = 48000
+    x = wl.c4_streams(1, 1.0)[0]
+    car = np.random.default_rng(5).uniform(-0.4, 0.4, x.shape[0] + 5000).astype(np.float32)   # longer than the voice: truncated
+    write_wav(tmp_path / "voice.wav", x, sr, "f32")
+    write_wav(tmp_path / "carrier.wav", car, sr, "f32")
+    p = preset(window_size_seconds=4096 / sr + 1e-6, window_center_stride_seconds=256 / sr, analysis_volume=0.5, voice_volume=0.2,
+               carrier_volume=0.1, vocoder_volume=1.5, vocoder_modulator_window_size_seconds=0.04, vocoder_stride_seconds=0.01,
+               vocoder_min_freq=80.0, vocoder_max_freq=6000.0)
+    p["int32_params"]["vocoder_count_bands"] = 12
+    (tmp_path / "preset.json").write_text(json.dumps(p))
+    job = {"preset_file": str(tmp_path / "preset.json"), "input_voice_file": str(tmp_path / "voice.wav"),
+           "input_carrier_file": str(tmp_path / "carrier.wav"), "output_file": str(tmp_path / "out.wav"), "post": "none"}
+    (tmp_path / "job.json").write_text(json.dumps(job))
+    r = run_tool(str(tmp_path / "job.json"))
+    assert r.returncode == 0, r.stderr
+    n = x.shape[0] + sr + 4096
+    xp = np.zeros((1, n), np.float32)
+    xp[0, :x.shape[0]] = x
+    cp = np.zeros((1, n), np.float32)
+    m = min(n, car.shape[0])
+    cp[0, :m] = car[:m]
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, gain=0.5)
+    mix = pkg.vocoder(ctx, xp, cp, sample_rate=sr, modulator_window_seconds=0.04, stride_seconds=0.01, count_bands=12, min_freq=80.0,
+                      max_freq=6000.0, vol_modulator=0.2, vol_carrier=0.1, vol_vocoder=1.5)
+    y, _ = read_wav_f32(tmp_path / "out.wav")
+    want = ref[0, :y.shape[0]] + mix[0, :y.shape[0], None]
+    assert np.abs(mix).max() > 0.02
+    assert np.array_equal(y, want.astype(np.float32))

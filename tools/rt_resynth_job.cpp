@@ -1,6 +1,8 @@
 // rt_resynth_job — the offline rt.resynth job (source/rt.resynth.lib.cpp:1185-1235, source/rt.resynth.lib.params.cpp:
 // 183-386) on the B200 path: a job file names a preset, a voice WAV file and an output file; the voice is analysed and
-// resynthesised (ca_resynth_roundtrip_host) and written as IEEE-float stereo.
+// resynthesised (ca_resynth_roundtrip_host); when the preset gives the voice, the carrier or the vocoder a volume, the vocoder
+// stage (voice = modulator, carrier file = carrier: ca_vocoder_host) is mixed into both channels as the reference's compute
+// callbacks do (rt.resynth.lib.cpp:1378-1420, rt.resynth.lib.vocoder.cpp:777-812); the result is written as IEEE-float stereo.
 //
 //   rt_resynth_job job.json [more job files...]          every job of the command line goes to the GPU in ONE batch
 //   rt_resynth_job --voice in.wav --out out.wav [--preset preset.json]
@@ -11,9 +13,11 @@
 // Preset file: {"bool_params": {..}, "enum_params": {..}, "int32_params": {..}, "uint64_params": {..},
 //               "float_params": {"window_size_seconds": 0.1814, ...}}         (Preset, params.cpp:57-141)
 // The float parameters of the analysis -> resynthesis path are honoured (names of rt.resynth.lib.cpp:1944-2040): window and
-// stride, min_volume, nearby_distance_tones, max_track_pitches, stereo_spread, env_*, analysis_volume. The vocoder /
-// carrier / autotune / pitch-shift parameters belong to stages outside this path: a non-default value is reported and
-// ignored. "limit" post-processing (an external compressor in the reference) clips to [-1, 1].
+// stride, min_volume, nearby_distance_tones, max_track_pitches, stereo_spread, env_*, analysis_volume, and of the vocoder:
+// voice_volume, carrier_volume, vocoder_volume, vocoder_modulator_window_size_seconds, vocoder_stride_seconds,
+// vocoder_count_bands (int32), vocoder_min_freq, vocoder_max_freq. The autotune / pitch-shift parameters and the real-time
+// carrier synth belong to stages outside this path: a non-default value is reported and ignored. "limit" post-processing (an
+// external compressor in the reference) clips to [-1, 1].
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -36,6 +40,7 @@ struct Job {
 struct Derived {  // what the preset means at a sample rate (RtResynth getters, rt.resynth.lib.cpp:484-487, :1576-1578)
   int window = 0, hop = 0;
   ca_roundtrip_params prm{};
+  ca_vocoder_params voc{};  // Vocoder::Params, rt.resynth.lib.cpp:1378-1395
 };
 
 std::string slurp(const std::string& path) {
@@ -69,6 +74,17 @@ float preset_float(const mini_json::Value* preset, const char* name, float dflt)
   return static_cast<float>(v->as_number());
 }
 
+int preset_int(const mini_json::Value* preset, const char* name, int dflt) {
+  if (!preset) return dflt;
+  const mini_json::Value* ip = preset->find("int32_params");
+  const mini_json::Value* v = ip ? ip->find(name) : nullptr;
+  if (!v) {
+    std::fprintf(stderr, "Preset param '%s' not found\n", name);
+    return dflt;
+  }
+  return static_cast<int>(v->as_number());
+}
+
 Derived derive(const mini_json::Value* preset, int sample_rate) {
   Derived d;
   // defaults: rt.resynth.lib.cpp:940-961
@@ -97,10 +113,20 @@ Derived derive(const mini_json::Value* preset, int sample_rate) {
   p.env.sustain = preset_float(preset, "env_sustain_level", 1.f);
   p.max_channels = 254;
   p.host_threads = 0;
+  // vocoder stage (defaults: rt.resynth.lib.cpp:986-994)
+  d.voc.sample_rate = sample_rate;
+  d.voc.modulator_window_size_seconds = preset_float(preset, "vocoder_modulator_window_size_seconds", 0.10f);
+  d.voc.stride_seconds = preset_float(preset, "vocoder_stride_seconds", 0.005f);
+  d.voc.count_bands = preset_int(preset, "vocoder_count_bands", 5);
+  d.voc.min_freq = preset_float(preset, "vocoder_min_freq", 100.f);
+  d.voc.max_freq = preset_float(preset, "vocoder_max_freq", 20000.f);
+  d.voc.vol_modulator = preset_float(preset, "voice_volume", 0.f);
+  d.voc.vol_carrier = preset_float(preset, "carrier_volume", 0.1f);
+  d.voc.vol_vocoder = preset_float(preset, "vocoder_volume", 0.f);
   if (preset) {  // stages outside the analysis -> resynthesis path
     struct { const char* name; float neutral; } ignored[] = {
         {"pitch_shift_pre_autotune", 0.f}, {"pitch_shift_post_autotune", 0.f}, {"pitch_harmonize_pre_autotune", 0.f},
-        {"pitch_harmonize_post_autotune", 0.f}, {"vocoder_volume", 0.f}, {"carrier_volume", 0.f}, {"voice_volume", 0.f}};
+        {"pitch_harmonize_post_autotune", 0.f}};
     const mini_json::Value* fp = preset->find("float_params");
     for (auto& ig : ignored) {
       const mini_json::Value* v = fp ? fp->find(ig.name) : nullptr;
@@ -124,6 +150,11 @@ void print_derived(const Job& job, const Derived& d, int sample_rate, size_t fra
 }
 
 bool same_params(const Derived& a, const Derived& b) { return std::memcmp(&a.prm, &b.prm, sizeof(a.prm)) == 0; }
+
+// the vocoder stage contributes when the voice is mixed in, or when there is a carrier and it (or its vocoded form) is audible
+bool vocoder_active(const Derived& d, bool has_carrier) {
+  return d.voc.vol_modulator != 0.f || (has_carrier && (d.voc.vol_carrier != 0.f || d.voc.vol_vocoder != 0.f));
+}
 
 }  // namespace
 
@@ -155,12 +186,12 @@ int main(int argc, char** argv) {
       Derived d;
       int sample_rate;
       std::vector<float> voice;
+      std::vector<float> carrier;  // empty: no carrier file (the reference then feeds zeros, params.cpp:298-303)
     };
     std::vector<Loaded> loaded;
     for (const Job& job : jobs) {
-      if (job.voice_file.empty()) throw std::runtime_error("must have a voice file (the carrier / vocoder stage is outside the B200 path)");
+      if (job.voice_file.empty()) throw std::runtime_error("must have a voice file (carrier-only jobs have nothing to analyse)");
       if (job.output_file.empty()) throw std::runtime_error("no output file");  // params.cpp:344-346
-      if (!job.carrier_file.empty()) std::fprintf(stderr, "note: the carrier file feeds the vocoder, a stage outside the B200 path; ignored\n");
       mini_json::Value preset;
       const bool has_preset = !job.preset_file.empty();
       if (has_preset) {
@@ -172,7 +203,12 @@ int main(int argc, char** argv) {
         }
       }
       const wav_io::Audio audio = wav_io::read(job.voice_file);
-      Loaded l{job, derive(has_preset ? &preset : nullptr, audio.sample_rate), audio.sample_rate, wav_io::as_one_float(audio)};
+      Loaded l{job, derive(has_preset ? &preset : nullptr, audio.sample_rate), audio.sample_rate, wav_io::as_one_float(audio), {}};
+      if (!job.carrier_file.empty()) {
+        const wav_io::Audio car = wav_io::read(job.carrier_file);
+        if (car.sample_rate != audio.sample_rate) throw std::runtime_error("sample rate mismatch between carrier and voice");  // params.cpp:270-274
+        l.carrier = wav_io::as_one_float(car);
+      }
       print_derived(job, l.d, l.sample_rate, l.voice.size());
       loaded.push_back(std::move(l));
     }
@@ -207,6 +243,27 @@ int main(int argc, char** argv) {
       if (int rc = ca_resynth_roundtrip_host(ctx, &loaded[i].d.prm, x, static_cast<int64_t>(n), static_cast<int64_t>(group.size()), y, stats.data())) {
         std::fprintf(stderr, "ca_resynth_roundtrip_host failed (%d): %s\n", rc, ca_last_error(ctx));
         return 1;
+      }
+      // vocoder stage, one call per job that uses it: mixed[n] goes to both channels (rt.resynth.lib.vocoder.cpp:803-810)
+      for (size_t g = 0; g < group.size(); ++g) {
+        const Loaded& l = loaded[group[g]];
+        if (!vocoder_active(l.d, !l.carrier.empty())) continue;
+        float* car = static_cast<float*>(ca_host_alloc(sizeof(float) * n));
+        float* mix = static_cast<float*>(ca_host_alloc(sizeof(float) * n));
+        if (!car || !mix) throw std::runtime_error("pinned allocation failed");
+        std::memset(car, 0, sizeof(float) * n);
+        std::memcpy(car, l.carrier.data(), sizeof(float) * std::min(n, l.carrier.size()));
+        if (int rc = ca_vocoder_host(ctx, &l.d.voc, x + g * n, car, static_cast<int64_t>(n), 1, mix)) {
+          std::fprintf(stderr, "ca_vocoder_host failed (%d): %s\n", rc, ca_last_error(ctx));
+          return 1;
+        }
+        float* out = y + 2 * g * n;
+        for (size_t k = 0; k < n; ++k) {
+          out[2 * k] += mix[k];
+          out[2 * k + 1] += mix[k];
+        }
+        ca_host_free(car);
+        ca_host_free(mix);
       }
       for (size_t g = 0; g < group.size(); ++g) {
         const Loaded& l = loaded[group[g]];
