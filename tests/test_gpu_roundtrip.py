@@ -126,3 +126,17 @@ def test_device_pitch_pipeline_limits(pkg, ctx):
         pkg.resynth_roundtrip(ctx, x, max_peaks=300)
     with pytest.raises(Exception):
         pkg.resynth_roundtrip(ctx, x, max_channels=300)
+
+
+def test_full_length_streams_properties(pkg, ctx, wl):
+    """BASELINE config 4 length (60 s per stream), five streams (uneven stream groups in the pipelined path): the device and
+    host forms of the pitch pipeline agree, every stream tracks its 16 partials from the first frame on, nothing sounds before
+    the first window is full, and a stream's result does not depend on what it is batched with."""
+    x = wl.c4_streams(5, 60.0)
+    dev, dstats = pkg.resynth_roundtrip(ctx, x)
+    host, hstats = pkg.resynth_roundtrip(ctx, x, host_threads=-1)
+    assert np.array_equal(dstats, hstats) and dstats[:, 0].min() >= 16 and dstats[:, 1].max() == 0
+    assert np.abs(dev[:, :4095]).max() == 0.0 and np.abs(dev).max() > 0.1
+    assert np.abs(dev - host).max() < 1e-5
+    alone, astats = pkg.resynth_roundtrip(ctx, x[3:4])
+    assert np.array_equal(astats[0], dstats[3]) and np.array_equal(alone[0], dev[3])
