@@ -579,13 +579,24 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track2_kernel(const __grid_
         if (T <= 32 && Np <= 32) {
           const bool has = lane < T;
           int lo = 0, mt = -1;
+          // steady state of tracked tones: entry i continues played note i. Then the lower bound of entry i is i (the played
+          // list is ascending: played[i-1] below the window, played[i] inside it) and no two entries compete.
+          bool spec = true;
           if (has) {
+            const double lo_t = e0.pitch - dtrack, hi_t = e0.pitch + dtrack;
+            const double here = pl_pitch[min(lane, kMaxNotes - 1)];
+            spec = lane < Np && here >= lo_t && here <= hi_t && (lane == 0 || pl_pitch[lane - 1] < lo_t);
+          }
+          const bool steady = T == Np && __all_sync(kFull, spec);
+          if (steady) {
+            if (has) lo = mt = lane;
+          } else if (has) {
             const double lo_t = e0.pitch - dtrack, hi_t = e0.pitch + dtrack;
             for (int j = 0; j < Np; ++j) lo += pl_pitch[j] < lo_t ? 1 : 0;
             if (lo < Np && pl_pitch[lo] <= hi_t) mt = lo;
           }
           const int prev_lo = __shfl_up_sync(kFull, lo, 1), prev_mt = __shfl_up_sync(kFull, mt, 1);
-          const bool bad = has && lane > 0 && lo < prev_lo + (prev_mt >= 0 ? 1 : 0);
+          const bool bad = !steady && has && lane > 0 && lo < prev_lo + (prev_mt >= 0 ? 1 : 0);
           if (__any_sync(kFull, bad)) {
             if (lane == 0) {
               int itp = 0;
