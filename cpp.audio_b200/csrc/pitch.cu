@@ -550,7 +550,13 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track2_kernel(const __grid_
   }
   __syncthreads();
 
+#ifdef CA_PITCH_TIMELINE
+  long long busy = 0;  // clocks this warp spent working (between leaving a barrier and arriving at the next)
+#endif
   for (int64_t it = 0; it < p.frames + kWarps - 1; ++it) {
+#ifdef CA_PITCH_TIMELINE
+    const long long t_in = clock64();
+#endif
     if (is_tracker) {
       // ================= tracker: frame k = it =================
       const int64_t k = it;
@@ -961,8 +967,14 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track2_kernel(const __grid_
         }
       }
     }
+#ifdef CA_PITCH_TIMELINE
+    busy += clock64() - t_in;
+#endif
     __syncthreads();
   }
+#ifdef CA_PITCH_TIMELINE
+  if (s == 0 && lane == 0) printf("pitch_track2<%d> role %d: %lld busy clocks per frame\n", kWarps, role, busy / p.frames);
+#endif
   if (is_tracker && lane == 0) {
     a.stats[2 * s] = started;
     a.stats[2 * s + 1] = dropped;
