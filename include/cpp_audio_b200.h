@@ -146,8 +146,9 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
  * aggregate_pitches, reduce_pitches, track_pitches, order by loudness) and synthesize_sounds (:264-382) turns the result
  * into NoteOn / NoteChange / NoteOff on a pool of ResynthElement voices (:5-18: StereoPanned<VolumeAdjusted<Enveloped<
  * FreqCtrl_<SineOscillatorAlgo, InterpolatedFreq>, AHDSREnvelope>>>) whose output is the resynthesised audio.
- * Analysis and voice rendering run on the GPU; the per-stream, frame-sequential pitch tracking runs on host threads
- * (it is control-rate code in the reference too). Events of frame k act from sample window-1 + k*hop on. */
+ * Analysis, the pitch pipeline (frame-sequential per stream: one CTA per stream walks its frames) and voice rendering all run on
+ * the GPU; only the audio crosses PCIe. Events of frame k act from sample window-1 + k*hop on. max_peaks and max_channels are
+ * limited to 256 on this path. */
 typedef struct ca_roundtrip_params {
   ca_stft_params stft;          /* window / hop / sample rate / min_db; max_peaks = peak capacity per frame */
   float nearby_distance_tones;  /* 0.4   rt.resynth.lib.cpp:948 */
@@ -157,7 +158,7 @@ typedef struct ca_roundtrip_params {
   float stereo_spread;          /* :955 */
   ca_ahdsr env;                 /* :957-961 (all zero, sustain 1 by default) */
   int32_t max_channels;         /* 254 = 2*127, :201-210 */
-  int32_t host_threads;         /* 0 = all */
+  int32_t host_threads;         /* 0: pitch pipeline on the device (default). n > 0 / -1: its host form on n / all host threads (A/B) */
 } ca_roundtrip_params;
 /* h_x [n_streams][n_samples] -> h_out [n_streams][n_samples][2] float32 (stereo). h_stats nullable [n_streams][2]:
  * notes started, notes dropped (pool full). */
