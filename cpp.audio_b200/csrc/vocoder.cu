@@ -163,12 +163,9 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
   float* d_out = static_cast<float*>(ctx->d_scratch[6]);
   int32_t* d_band_begin = static_cast<int32_t*>(ctx->d_scratch[7]);
   int8_t* d_band_c = reinterpret_cast<int8_t*>(d_band_begin + nb + 1);
-  CA_CUDA_OK(ctx, cudaMemcpyAsync(d_xm, h_modulator, sizeof(float) * total, cudaMemcpyHostToDevice, st));
-  CA_CUDA_OK(ctx, cudaMemcpyAsync(d_xc, h_carrier, sizeof(float) * total, cudaMemcpyHostToDevice, st));
   CA_CUDA_OK(ctx, cudaMemcpyAsync(d_band_begin, band_begin.data(), sizeof(int32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
   CA_CUDA_OK(ctx, cudaMemcpyAsync(d_band_c, band_c.data(), band_c.size(), cudaMemcpyHostToDevice, st));
-
-  if (rows_m) {  // modulator: |X|^2 of every frame, then the band amplitudes
+  if (rows_m) {
     ca_stft_params sp{};
     sp.window = Wm;
     sp.hop = S;
@@ -178,33 +175,56 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
     sp.min_db = -INFINITY;
     sp.max_peaks = 1;
     rc = stft_plan(ctx, &sp);
-    if (!rc) rc = stft_analyze(ctx, d_xm, n_samples, n_streams, n_samples, d_sq, row_stride, nullptr, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
-    band_amps_kernel<<<static_cast<unsigned>((rows_m + 3) / 4), 128, 0, st>>>(d_sq, row_stride, static_cast<int64_t>(rows_m), d_band_begin, nb, d_amps);
-    CA_CUDA_OK(ctx, cudaGetLastError());
+  }
+  CA_CUDA_OK(ctx, cudaStreamSynchronize(st));  // tables and window are in place before the stream groups start
+  // carrier frame j is fired by sample 2S-1+jS and sees the modulator frames fired up to that sample (Wm-1+mS <= 2S-1+jS)
+  const int64_t num = 2ll * S - Wm;  // m(j) = floor((num + jS)/S) = j + floor(num/S)
+  const int first_m = static_cast<int>(num >= 0 ? num / S : -((-num + S - 1) / S));
+  // Streams are independent: they go through the stages in up to four groups, each on its own CUDA stream, so that the copies
+  // of one group overlap the kernels of the others (the call is PCIe-bound: 12 bytes per sample cross it).
+  const int groups = static_cast<int>(std::min<int64_t>(4, n_streams));
+  for (int g = 0; g < groups; ++g)
+    if (!ctx->pipe_streams[g]) CA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_streams[g], cudaStreamNonBlocking));
+  for (int g = 0; g < groups && !rc; ++g) {
+    cudaStream_t sg = ctx->pipe_streams[g];
+    const int64_t a0 = n_streams * g / groups, a1 = n_streams * (g + 1) / groups, ns = a1 - a0;
+    const size_t x0 = static_cast<size_t>(a0) * n_samples, nx = static_cast<size_t>(ns) * n_samples;
+    const size_t m0 = static_cast<size_t>(a0) * frames_m, nm = static_cast<size_t>(ns) * frames_m;
+    const size_t c0 = static_cast<size_t>(a0) * frames_c, nc = static_cast<size_t>(ns) * frames_c;
+    cudaMemcpyAsync(d_xm + x0, h_modulator + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
+    cudaMemcpyAsync(d_xc + x0, h_carrier + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
+    if (nm) {  // modulator: |X|^2 of every frame, then the band amplitudes
+      rc = stft_analyze(ctx, d_xm + x0, n_samples, ns, n_samples, d_sq + m0 * row_stride, row_stride, nullptr, nullptr, nullptr, nullptr, sg);
+      if (rc) break;
+      band_amps_kernel<<<static_cast<unsigned>((nm + 3) / 4), 128, 0, sg>>>(d_sq + m0 * row_stride, row_stride, static_cast<int64_t>(nm),
+                                                                           d_band_begin, nb, d_amps + m0 * nb);
+      ctx->launches += 1;
+    }
+    float* sig_g = d_sig + c0 * Nc;
+    if (nc) {  // carrier: frames -> spectrum -> band gains -> signal
+      float* bins_g = d_bins + c0 * 2 * (Nc / 2 + 1);
+      voc_frames_kernel<<<static_cast<unsigned>(nc), 256, 0, sg>>>(d_xc + x0, n_samples, frames_c, S, Nc, sig_g);
+      rc = rfft_batched(ctx, sig_g, Nc, static_cast<int64_t>(nc), bins_g, sg);
+      if (rc) break;
+      voc_modulate_kernel<<<static_cast<unsigned>(nc), 256, 0, sg>>>(reinterpret_cast<float2*>(bins_g), Nc / 2 + 1, frames_c, frames_m, first_m,
+                                                                    d_band_c, d_amps + m0 * nb, nb);
+      rc = irfft_batched(ctx, bins_g, Nc, static_cast<int64_t>(nc), sig_g, 1.f / Nc, sg);
+      if (rc) break;
+      ctx->launches += 2;
+    }
+    voc_mix_kernel<<<static_cast<unsigned>((nx + 255) / 256), 256, 0, sg>>>(d_xm + x0, d_xc + x0, sig_g, n_samples, ns, frames_c, S, Nc,
+                                                                           prm->vol_modulator, prm->vol_carrier, prm->vol_vocoder, d_out + x0);
     ctx->launches += 1;
+    cudaMemcpyAsync(h_out + x0, d_out + x0, sizeof(float) * nx, cudaMemcpyDeviceToHost, sg);
   }
-  if (rows_c) {  // carrier: frames -> spectrum -> band gains -> signal
-    voc_frames_kernel<<<static_cast<unsigned>(rows_c), 256, 0, st>>>(d_xc, n_samples, frames_c, S, Nc, d_sig);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    rc = rfft_batched(ctx, d_sig, Nc, static_cast<int64_t>(rows_c), d_bins, st);
-    if (rc) return rc;
-    // carrier frame j is fired by sample 2S-1+jS and sees the modulator frames fired up to that sample (Wm-1+mS <= 2S-1+jS)
-    const int64_t num = 2ll * S - Wm;  // m(j) = floor((num + jS)/S) = j + floor(num/S)
-    const int first_m = static_cast<int>(num >= 0 ? num / S : -((-num + S - 1) / S));
-    voc_modulate_kernel<<<static_cast<unsigned>(rows_c), 256, 0, st>>>(reinterpret_cast<float2*>(d_bins), Nc / 2 + 1, frames_c, frames_m, first_m,
-                                                                      d_band_c, d_amps, nb);
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    rc = irfft_batched(ctx, d_bins, Nc, static_cast<int64_t>(rows_c), d_sig, 1.f / Nc, st);
-    if (rc) return rc;
-    ctx->launches += 2;
+  cudaError_t err = cudaGetLastError();
+  for (int g = 0; g < groups; ++g) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->pipe_streams[g]);
+    if (err == cudaSuccess) err = e;
   }
-  voc_mix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d_xm, d_xc, d_sig, n_samples, n_streams, frames_c, S, Nc,
-                                                                             prm->vol_modulator, prm->vol_carrier, prm->vol_vocoder, d_out);
-  CA_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += 1;
-  CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, d_out, sizeof(float) * total, cudaMemcpyDeviceToHost, st));
-  CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(ctx, CA_ERR_CUDA, std::string("ca_vocoder_host: ") + cudaGetErrorString(err));
   return CA_OK;
 }
 
