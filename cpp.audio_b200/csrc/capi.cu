@@ -224,6 +224,12 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
   if (h.n_voices < 0 || h.n_partials < 1 || h.n_samples < 0 || !h.f0_hz || !h.volume || !h.partial_volume ||
       !h.partial_phase || !h.env || (h.n_env != 1 && h.n_env != h.n_voices))
     return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: bad descriptor");
+  for (int64_t i = 0; i < h.n_env; ++i) {
+    const ca_ahdsr& e = h.env[i];
+    if (e.attack_itp < 0 || e.attack_itp >= CA_ITP_COUNT || e.decay_itp < 0 || e.decay_itp >= CA_ITP_COUNT ||
+        e.release_itp < 0 || e.release_itp >= CA_ITP_COUNT)
+      return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: envelope interpolation is not a ca_itp value");
+  }
   if (h.n_voices == 0 || h.n_samples == 0) return CA_OK;
   const size_t nv = static_cast<size_t>(h.n_voices), np = static_cast<size_t>(h.n_partials);
   // one parameter block: f0 | volume | start_angle | pan | key_delay | release_at | pvol | pphase | env

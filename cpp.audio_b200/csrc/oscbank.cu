@@ -56,7 +56,7 @@ struct __align__(16) VoiceParams {
   float sustain;  // 1 + SMinusOne
   float gain_l;
   float gain_r;
-  int32_t pad;
+  int32_t itp;  // ca_itp of attack | decay << 8 | release << 16
 };
 static_assert(sizeof(VoiceParams) == 32, "VoiceParams must be 32 bytes");
 
@@ -98,7 +98,7 @@ __global__ void osc_prep_kernel(const __grid_constant__ PrepArgs a) {
     }
     vp.gain_l = static_cast<float>(gl);
     vp.gain_r = static_cast<float>(gr);
-    vp.pad = 0;
+    vp.itp = (env.attack_itp & 0xff) | ((env.decay_itp & 0xff) << 8) | ((env.release_itp & 0xff) << 16);
     a.voices[v] = vp;
   }
 
@@ -187,15 +187,37 @@ __device__ __forceinline__ float2 cis_turns_u64(uint64_t ph) {  // exp(2 pi i * 
   return make_float2(c, s);
 }
 
+// itp::interpolate as b + c*e(u), u = t/d in (0, 1]: Penner's easing set in the ca_itp numbering (oracle/SPEC.md S7;
+// call sites include/audioelement.h:733-737, 994-998). Only the chunks that contain an envelope transition get here.
+__device__ __forceinline__ float ease_in(int fam, float x) {
+  switch (fam) {
+    case 0: return x * x;
+    case 1: return x * x * x;
+    case 2: { const float x2 = x * x; return x2 * x2; }
+    case 3: { const float x2 = x * x; return x2 * x2 * x; }
+    case 4: return 1.f - cospif(0.5f * x);
+    case 5: return x == 0.f ? 0.f : exp2f(10.f * (x - 1.f));
+    default: return 1.f - sqrtf(fmaxf(0.f, 1.f - x * x));
+  }
+}
+__device__ __noinline__ float ease_nonlinear(int type, float u) {
+  const int fam = (type - 1) / 3, mode = (type - 1) - 3 * fam;
+  if (mode == 0) return ease_in(fam, u);
+  if (mode == 1) return 1.f - ease_in(fam, 1.f - u);
+  if (fam == 4) return 0.5f * (1.f - cospif(u));
+  return u < 0.5f ? 0.5f * ease_in(fam, 2.f * u) : 1.f - 0.5f * ease_in(fam, 2.f - 2.f * u);
+}
+__device__ __forceinline__ float ease(int type, float u) { return type == CA_ITP_LINEAR ? u : ease_nonlinear(type, u); }
+
 // value of the envelope while the key is pressed, c = step counter (>=1 once audible), :960-1000
-__device__ __forceinline__ float env_pressed(int64_t c, const PartialParams& q, int32_t hold, float sustain) {
+__device__ __forceinline__ float env_pressed(int64_t c, const PartialParams& q, const VoiceParams& vp) {
   if (c < 1) return 0.f;
-  if (c <= q.attack) return static_cast<float>(c) * q.inv_attack;
+  if (c <= q.attack) return c == q.attack ? 1.f : ease(vp.itp & 0xff, static_cast<float>(c) * q.inv_attack);
   c -= q.attack;
-  if (c <= hold) return 1.f;
-  c -= hold;
-  if (c <= q.decay) return 1.f + (sustain - 1.f) * (static_cast<float>(c) * q.inv_decay);
-  return sustain;
+  if (c <= vp.hold) return 1.f;
+  c -= vp.hold;
+  if (c < q.decay) return 1.f + (vp.sustain - 1.f) * ease((vp.itp >> 8) & 0xff, static_cast<float>(c) * q.inv_decay);
+  return vp.sustain;
 }
 
 __device__ __forceinline__ float env_value(int64_t n, const PartialParams& q, const VoiceParams& vp) {
@@ -205,10 +227,10 @@ __device__ __forceinline__ float env_value(int64_t n, const PartialParams& q, co
     if (crel <= 0) return 0.f;
     const int64_t j = n - rel + 1;
     if (j >= q.release) return 0.f;
-    const float top = env_pressed(crel, q, vp.hold, vp.sustain);
-    return top - top * (static_cast<float>(j) * q.inv_release);  // :733-737
+    const float top = env_pressed(crel, q, vp);
+    return top - top * ease((vp.itp >> 16) & 0xff, static_cast<float>(j) * q.inv_release);  // :733-737
   }
-  return env_pressed(n + 1 - vp.key_delay, q, vp.hold, vp.sustain);
+  return env_pressed(n + 1 - vp.key_delay, q, vp);
 }
 
 template <int WARPS>

@@ -161,6 +161,8 @@ int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out) {
   if (desc->mix != CA_MIX_NONE && desc->mix != CA_MIX_MONO)
     return fail(ctx, CA_ERR_UNSUPPORTED, "ca_ramp_render_host: mix must be CA_MIX_NONE or CA_MIX_MONO");
   const ca_ramp_desc d = *desc;
+  if (d.env.attack_itp != CA_ITP_LINEAR || d.env.decay_itp != CA_ITP_LINEAR || d.env.release_itp != CA_ITP_LINEAR)
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_ramp_render_host: the ramp voices render LINEAR envelopes only");
   for (int64_t v = 0; v < d.n_voices; ++v)
     if (!(d.from_hz[v] > 0.f) || !(d.to_hz[v] > 0.f) || !(d.duration[v] > 0.f))
       return fail(ctx, CA_ERR_INVALID, "ca_ramp_render_host: frequencies and durations must be positive (LogRamp asserts it)");

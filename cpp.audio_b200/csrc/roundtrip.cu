@@ -324,6 +324,8 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (!params || !h_x || !h_out || n_samples < 0 || n_streams < 0)
     return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: null argument or negative size");
   ca_roundtrip_params prm = *params;
+  if (prm.env.attack_itp != CA_ITP_LINEAR || prm.env.decay_itp != CA_ITP_LINEAR || prm.env.release_itp != CA_ITP_LINEAR)
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: LINEAR envelopes only (as rt.resynth.lib.cpp:75-81)");
   if (prm.max_channels <= 0) prm.max_channels = 254;
   if (prm.stft.max_peaks <= 0) prm.stft.max_peaks = 200;
   int rc = stft_plan(ctx, &prm.stft);

@@ -14,6 +14,8 @@ import torch
 from ._capi import Ahdsr, Context, OscBankDesc, lib
 
 MIX_NONE, MIX_STEREO, MIX_MONO = 0, 1, 2
+# enum ca_itp: 0 LINEAR, then 1 + 3*family + mode (family QUAD, CUBIC, QUART, QUINT, SINE, EXPO, CIRC; mode IN, OUT, INOUT)
+ITP_LINEAR, ITP_EASE_OUT_CUBIC, ITP_COUNT = 0, 5, 22
 BASE_VOLUME_SINE = 0.1  # reduceUnadjustedVolumes * soundBaseVolume(SINE), include/audioelement.h:2370,1270; include/sound.h:84-85
 
 
@@ -40,6 +42,9 @@ class SineBank:
             if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
                 raise ValueError("note parameters must be contiguous CUDA tensors of the documented dtype")
         envs = [env] if isinstance(env, Ahdsr) else list(env)
+        for e in envs:  # the descriptor's env block lives on the device: the library cannot check it there
+            if not all(0 <= t < ITP_COUNT for t in (e.attack_itp, e.decay_itp, e.release_itp)):
+                raise ValueError("envelope interpolation is not a ca_itp value")
         arr = (Ahdsr * len(envs))(*envs)
         env_host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         env_dev = env_host.to(dev)

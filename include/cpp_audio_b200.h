@@ -97,7 +97,23 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
  * Stands in for ImplCRTP::compute (include/gen.crtp.h:350-378) over elements
  * VolumeAdjusted<MultiEnveloped<SineOscillatorAlgo,AHDSREnvelope>> (include/audioelement.h:486-657, :1111-1265,
  * :2366-2452), for whole notes at once instead of 16-frame blocks. */
-enum ca_itp { CA_ITP_LINEAR = 0 }; /* itp::LINEAR; the only easing the rt.resynth path uses (rt.resynth.lib.cpp:75-81) */
+/* itp::interpolation of the envelope phases (include/audioelement.h:314-335, evaluated at :733-737, :994-998). The enum
+ * itself lives in cpp.algorithms (absent); the numbering is ours, the equations are Penner's (oracle/SPEC.md S7).
+ * rt.resynth uses LINEAR everywhere (rt.resynth.lib.cpp:75-81), tune EASE_OUT_CUBIC / LINEAR (main.tune.cpp:1146-1161).
+ * value = CA_ITP_EASE_IN_QUAD + 3*family + mode, family = QUAD, CUBIC, QUART, QUINT, SINE, EXPO, CIRC, mode = IN, OUT, INOUT.
+ * The oscillator bank (ca_oscbank_*) evaluates all of them; the round trip and the ramp voices take LINEAR only and
+ * fail with CA_ERR_UNSUPPORTED otherwise. */
+enum ca_itp {
+  CA_ITP_LINEAR = 0,
+  CA_ITP_EASE_IN_QUAD = 1, CA_ITP_EASE_OUT_QUAD = 2, CA_ITP_EASE_INOUT_QUAD = 3,
+  CA_ITP_EASE_IN_CUBIC = 4, CA_ITP_EASE_OUT_CUBIC = 5, CA_ITP_EASE_INOUT_CUBIC = 6,
+  CA_ITP_EASE_IN_QUART = 7, CA_ITP_EASE_OUT_QUART = 8, CA_ITP_EASE_INOUT_QUART = 9,
+  CA_ITP_EASE_IN_QUINT = 10, CA_ITP_EASE_OUT_QUINT = 11, CA_ITP_EASE_INOUT_QUINT = 12,
+  CA_ITP_EASE_IN_SINE = 13, CA_ITP_EASE_OUT_SINE = 14, CA_ITP_EASE_INOUT_SINE = 15,
+  CA_ITP_EASE_IN_EXPO = 16, CA_ITP_EASE_OUT_EXPO = 17, CA_ITP_EASE_INOUT_EXPO = 18,
+  CA_ITP_EASE_IN_CIRC = 19, CA_ITP_EASE_OUT_CIRC = 20, CA_ITP_EASE_INOUT_CIRC = 21,
+  CA_ITP_COUNT = 22
+};
 
 typedef struct ca_ahdsr { /* audioelement::AHDSR, include/audioelement.h:314-335 (durations in samples) */
   int32_t attack;

@@ -379,22 +379,52 @@ enum Itp : int {
   EASE_IN_CUBIC = 4, EASE_OUT_CUBIC = 5, EASE_INOUT_CUBIC = 6,
   EASE_IN_QUART = 7, EASE_OUT_QUART = 8, EASE_INOUT_QUART = 9,
   EASE_IN_QUINT = 10, EASE_OUT_QUINT = 11, EASE_INOUT_QUINT = 12,
+  EASE_IN_SINE = 13, EASE_OUT_SINE = 14, EASE_INOUT_SINE = 15,
+  EASE_IN_EXPO = 16, EASE_OUT_EXPO = 17, EASE_INOUT_EXPO = 18,
+  EASE_IN_CIRC = 19, EASE_OUT_CIRC = 20, EASE_INOUT_CIRC = 21,
 };
 
+// Penner's easing set, written as b + c*e(t/d) with e(0) = 0 and e(1) = 1 (the exponential family jumps at its
+// end points exactly as the published equations do: e(0+) = 2^-10 for "in", e(1-) = 1 - 2^-10 for "out").
 template <class T>
 T interpolate(int type, T t, T b, T c, T d) {
   T u = t / d;
   auto in_pow = [](T x, int p) { T r = 1; for (int i = 0; i < p; ++i) r *= x; return r; };
   if (type == LINEAR) return b + c * u;
-  int fam = (type - 1) / 3;      // 0 quad .. 3 quint
+  const T kHalfPi = T(1.5707963267948966192313216916398);
+  int fam = (type - 1) / 3;      // 0 quad .. 3 quint, 4 sine, 5 expo, 6 circ
   int mode = (type - 1) % 3;     // 0 in, 1 out, 2 inout
-  int p = fam + 2;
   T e;
-  if (mode == 0) e = in_pow(u, p);
-  else if (mode == 1) e = T(1) - in_pow(T(1) - u, p);
-  else {
-    if (u < T(0.5)) e = T(0.5) * in_pow(T(2) * u, p);
-    else e = T(1) - T(0.5) * in_pow(T(2) - T(2) * u, p);
+  if (fam <= 3) {
+    int p = fam + 2;
+    if (mode == 0) e = in_pow(u, p);
+    else if (mode == 1) e = T(1) - in_pow(T(1) - u, p);
+    else {
+      if (u < T(0.5)) e = T(0.5) * in_pow(T(2) * u, p);
+      else e = T(1) - T(0.5) * in_pow(T(2) - T(2) * u, p);
+    }
+  } else if (fam == 4) {
+    if (mode == 0) e = T(1) - std::cos(u * kHalfPi);
+    else if (mode == 1) e = std::sin(u * kHalfPi);
+    else e = T(0.5) * (T(1) - std::cos(T(2) * kHalfPi * u));
+  } else if (fam == 5) {
+    if (mode == 0) e = (t == T(0)) ? T(0) : std::exp2(T(10) * (u - T(1)));
+    else if (mode == 1) e = (t == d) ? T(1) : T(1) - std::exp2(T(-10) * u);
+    else {
+      if (t == T(0)) e = T(0);
+      else if (t == d) e = T(1);
+      else if (u < T(0.5)) e = T(0.5) * std::exp2(T(10) * (T(2) * u - T(1)));
+      else e = T(0.5) * (T(2) - std::exp2(T(-10) * (T(2) * u - T(1))));
+    }
+  } else {
+    auto root = [](T x) { return std::sqrt(x > T(0) ? x : T(0)); };
+    if (mode == 0) e = T(1) - root(T(1) - u * u);
+    else if (mode == 1) e = root(T(1) - (u - T(1)) * (u - T(1)));
+    else {
+      T w = T(2) * u;
+      if (w < T(1)) e = T(0.5) * (T(1) - root(T(1) - w * w));
+      else e = T(0.5) * (root(T(1) - (w - T(2)) * (w - T(2))) + T(1));
+    }
   }
   return b + c * e;
 }

@@ -26,7 +26,8 @@ def default_env(pkg):
 
 
 def orc_env(orc, e):
-    return orc.make_ahdsr(e.attack, e.hold, e.decay, e.release, e.sustain)
+    return orc.make_ahdsr(e.attack, e.hold, e.decay, e.release, e.sustain, attack_itp=e.attack_itp, decay_itp=e.decay_itp,
+                          release_itp=e.release_itp)
 
 
 def test_small_bank_default_envelope(pkg, orc, ctx, wl):
@@ -75,6 +76,51 @@ def test_full_ahdsr_with_release(pkg, orc, ctx, wl):
     assert np.abs(out - ref).max() < TOL * 0.1
     # voice 5 is released before its key delay elapsed: the note is skipped (audioelement.h:774-777)
     assert np.abs(out[5]).max() == 0.0
+
+
+def test_tune_envelope_ease_out_cubic(pkg, orc, ctx, wl):
+    # tune's bank envelopes: EASE_OUT_CUBIC attack and release around a LINEAR decay (source/main.tune.cpp:1146-1161)
+    b = wl.c3_bank(4, 16)
+    n = 24000
+    e = pkg.Ahdsr(2000, 5, 100, 3000, 0, 4000, 5, 0.7)
+    rel = np.array([12000, 1000, -1, 6100], np.int64)   # voice 1 is released in the middle of its eased attack
+    kd = np.array([0, 11, 300, 0], np.int32)
+    out = gpu_render(pkg, ctx, b, n, e, release_at=rel, key_delay=kd)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
+                             release_at=rel, key_delay=kd)
+    assert np.abs(out - ref).max() < TOL * 0.1
+    lin = gpu_render(pkg, ctx, b, n, pkg.Ahdsr(2000, 0, 100, 3000, 0, 4000, 0, 0.7), release_at=rel, key_delay=kd)
+    assert np.abs(out - lin).max() > 1e-3  # the easing is not a no-op
+
+
+@pytest.mark.parametrize("family", range(7))
+def test_every_easing_family(pkg, orc, ctx, wl, family):
+    # one voice per (attack, decay, release) rotation of the family's IN / OUT / INOUT modes (ca_itp = 1 + 3*family + mode)
+    b = wl.c3_bank(3, 8)
+    n = 9000
+    t = [1 + 3 * family + m for m in range(3)]
+    envs = [pkg.Ahdsr(700 + 10 * i, t[i % 3], 30, 900, t[(i + 1) % 3], 1500, t[(i + 2) % 3], 0.4) for i in range(3)]
+    rel = np.array([5000, 1200, 400], np.int64)  # after the decay, inside the decay, inside the attack
+    out = gpu_render(pkg, ctx, b, n, envs, release_at=rel)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n,
+                             env=[orc_env(orc, e) for e in envs], release_at=rel)
+    assert np.abs(out - ref).max() < TOL * 0.1
+
+
+def test_unknown_easing_is_rejected(pkg, ctx, wl):
+    b = wl.c3_bank(1, 2)
+    with pytest.raises(ValueError):
+        gpu_render(pkg, ctx, b, 100, pkg.Ahdsr(10, 22, 0, 0, 0, 10, 0, 1.0))
+    import ctypes as C
+    env = (pkg.Ahdsr * 1)(pkg.Ahdsr(10, 0, 0, 0, -1, 10, 0, 1.0))
+    out = np.empty((1, 100), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p).value
+    d = pkg.OscBankDesc(1, 2, 100, 48000, vp(b["f0_hz"]), vp(b["volume"]), None, None, None, vp(b["partial_volume"]),
+                        vp(b["partial_phase"]), C.cast(env, C.c_void_p).value, 1, None, 0, 0)
+    assert pkg.lib().ca_oscbank_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p)) == -1  # CA_ERR_INVALID
+    # the ramp voices take LINEAR envelopes only and say so
+    with pytest.raises(pkg.CaError):
+        pkg.render_ramps(ctx, [200.0], [400.0], [1000.0], 500, env=pkg.Ahdsr(10, 5, 0, 0, 0, 10, 0, 1.0))
 
 
 def test_per_voice_envelopes_and_odd_sizes(pkg, orc, ctx, wl):

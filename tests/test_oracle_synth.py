@@ -51,6 +51,51 @@ def test_envelope_hold_decay_and_delay(orc):
     assert (v == 0).all() and s[5] == 3
 
 
+def _penner(itp, u):
+    """Independent numpy statement of Penner's easing equations e(u), u = t/d in (0, 1]; enum values of SPEC S7 / ca_itp."""
+    u = np.asarray(u, dtype=np.float64)
+    if itp == 0:
+        return u
+    fam, mode = (itp - 1) // 3, (itp - 1) % 3
+    if fam <= 3:
+        ein = lambda x: x ** (fam + 2)
+    elif fam == 4:
+        ein = lambda x: 1 - np.cos(x * np.pi / 2)
+    elif fam == 5:
+        ein = lambda x: np.where(x == 0, 0.0, 2.0 ** (10 * (x - 1)))
+    else:
+        ein = lambda x: 1 - np.sqrt(np.maximum(0.0, 1 - x * x))
+    if fam == 4 and mode == 2:
+        return 0.5 * (1 - np.cos(np.pi * u))
+    if mode == 0:
+        return ein(u)
+    if mode == 1:
+        return 1 - ein(1 - u)
+    return np.where(u < 0.5, 0.5 * ein(np.minimum(2 * u, 1.0)), 1 - 0.5 * ein(np.maximum(2 - 2 * u, 0.0)))
+
+
+def test_envelope_easings_follow_penner(orc):
+    # audioelement.h:733-737,994-998: value = itp::interpolate(type, counter, from, delta, duration); SPEC S7 for the set.
+    # tune's envelopes are EASE_OUT_CUBIC attack / release with a LINEAR decay (main.tune.cpp:1146-1161).
+    A, H, D, R, S = 100, 10, 200, 300, 0.5
+    for itp in range(0, 22):
+        e = orc.make_ahdsr(attack=A, hold=H, decay=D, release=R, sustain=S, attack_itp=itp, decay_itp=itp, release_itp=itp)
+        v, _ = orc.envelope_trace(e, 2000, 2 * 4000 / 48000, key_delay=7, release_at=1000)
+        assert (v[:7] == 0).all()
+        assert np.allclose(v[7:107], _penner(itp, np.arange(1, A + 1) / A), atol=1e-12), itp
+        assert (v[107:117] == 1.0).all()
+        assert np.allclose(v[117:317], 1.0 + (S - 1.0) * _penner(itp, np.arange(1, D + 1) / D), atol=1e-12), itp
+        assert (v[317:1000] == S).all()
+        assert np.allclose(v[1000:1300], S - S * _penner(itp, np.arange(1, R + 1) / R), atol=1e-12), itp
+        assert (v[1300:] == 0).all()
+    # release in the middle of an eased attack: the release starts from the value reached (top), :836-841
+    e = orc.make_ahdsr(attack=400, release=100, attack_itp=5, release_itp=5)
+    v, _ = orc.envelope_trace(e, 600, 2 * 4000 / 48000, release_at=200)
+    top = _penner(5, 200 / 400)
+    assert abs(v[199] - top) < 1e-12
+    assert np.allclose(v[200:300], top - top * _penner(5, np.arange(1, 101) / 100), atol=1e-12)
+
+
 def test_bank_equals_sum_of_partials(orc):
     # KAT-7: 2 voices x 4 partials against the explicit MultiEnveloped formula (audioelement.h:529-545,590-594,614-619)
     f0 = np.array([440.0, 3000.0], np.float32)
