@@ -11,6 +11,7 @@ from ._capi import (  # noqa: F401
     CaError,
     Context,
     OscBankDesc,
+    PitchOptions,
     RampDesc,
     RoundtripParams,
     StftParams,
@@ -24,6 +25,6 @@ from ._capi import (  # noqa: F401
 )
 from .analysis import SqMagAnalyzer, analyze_streams, irfft_batched, rfft_batched  # noqa: F401
 from .synth import SineBank, render_bank, render_ramps  # noqa: F401
-from .roundtrip import pinned_empty, resynth_roundtrip  # noqa: F401
+from .roundtrip import pinned_empty, pitch_options, resynth_roundtrip  # noqa: F401
 from .vocoder import vocoder  # noqa: F401
 from .sharding import frame_shard, gather_rows, reduce_bus, shard_range  # noqa: F401

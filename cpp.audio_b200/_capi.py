@@ -29,10 +29,18 @@ class Ahdsr(C.Structure):
                 ("decay_itp", C.c_int32), ("release", C.c_int32), ("release_itp", C.c_int32), ("sustain", C.c_float)]
 
 
+class PitchOptions(C.Structure):
+    """ca_pitch_options: shift / harmonize / autotune stages of RtResynth::step (rt.resynth.lib.cpp:1687-1707); zero = off."""
+    _fields_ = [("shift_pre_autotune", C.c_float), ("harmonize_pre_autotune", C.c_float), ("shift_post_autotune", C.c_float),
+                ("harmonize_post_autotune", C.c_float), ("autotune", C.c_int32), ("autotune_max_pitch", C.c_float),
+                ("autotune_tolerance_pitches", C.c_float), ("n_table", C.c_int32), ("table", C.c_void_p),
+                ("scale_root_pitch", C.c_double)]
+
+
 class RoundtripParams(C.Structure):
     _fields_ = [("stft", StftParams), ("nearby_distance_tones", C.c_float), ("min_volume", C.c_float),
                 ("max_track_pitches", C.c_float), ("gain", C.c_float), ("stereo_spread", C.c_float), ("env", Ahdsr),
-                ("max_channels", C.c_int32), ("host_threads", C.c_int32)]
+                ("max_channels", C.c_int32), ("host_threads", C.c_int32), ("opts", PitchOptions)]
 
 
 class VocoderParams(C.Structure):

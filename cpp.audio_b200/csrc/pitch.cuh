@@ -8,6 +8,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <climits>
 
@@ -36,6 +37,15 @@ struct PitchParams {
   double decay_full;           // exp(-pi * cap * hop): volume low-pass decay over a whole frame interval at the capped rate
   int32_t max_channels;
   int64_t n_samples, frames;
+  // optional stages between reduce_pitches and track_pitches (source/rt.resynth.lib.cpp:1687-1707); opt_active == 0: none
+  int32_t opt_active;
+  int32_t tcap;                // capacity of a frame's list at every stage = stft.max_peaks (independent of the stride P)
+  float shift_pre, harm_pre, shift_post, harm_post;
+  int32_t autotune;            // ca_autotune
+  float at_max_pitch, at_tolerance;
+  int32_t n_table;
+  const double* table;         // allowed pitches / scale pitches; a HOST pointer in the host form, a DEVICE pointer in the kernels
+  double scale_root;
 };
 
 inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, int peak_stride) {
@@ -63,6 +73,22 @@ inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_s
   p.max_channels = prm.max_channels;
   p.n_samples = n_samples;
   p.frames = frames;
+  const ca_pitch_options& o = prm.opts;
+  p.opt_active = (o.shift_pre_autotune != 0.f || o.harmonize_pre_autotune != 0.f || o.shift_post_autotune != 0.f ||
+                  o.harmonize_post_autotune != 0.f || o.autotune != CA_AUTOTUNE_NONE)
+                     ? 1
+                     : 0;
+  p.tcap = prm.stft.max_peaks;
+  p.shift_pre = o.shift_pre_autotune;
+  p.harm_pre = o.harmonize_pre_autotune;
+  p.shift_post = o.shift_post_autotune;
+  p.harm_post = o.harmonize_post_autotune;
+  p.autotune = o.autotune;
+  p.at_max_pitch = o.autotune_max_pitch;
+  p.at_tolerance = o.autotune_tolerance_pitches;
+  p.n_table = o.n_table;
+  p.table = o.table;
+  p.scale_root = o.scale_root_pitch;
   return p;
 }
 
@@ -100,20 +126,141 @@ struct __align__(16) Tuned {
   int32_t min_change;  // min_change_for(ai)
 };
 
-// Peaks of one frame (ascending frequency) -> tuned list. Returns the number of entries written to `out` (<= cnt).
+// ---- optional stages of the stateless prefix: shift / harmonize / autotune (source/rt.resynth.lib.algo.cpp:186-229, 307-371) ----
+// They work on (pitch, volume) pairs kept in the raw bytes of the frame's Tuned row: tcap entries of 32 bytes hold the list
+// (pairs [0, tcap)) and the work vector of the merge (pairs [tcap, 2 tcap)). Lists are capped at tcap entries at every stage
+// (the reference's vectors grow; its peak list is capped the same way at max_peaks).
+struct PV {
+  double pitch, vol;
+};
+CA_HD inline PV pv_ld(const unsigned char* raw, int i) {
+  PV q;
+  memcpy(&q, raw + 16 * static_cast<size_t>(i), 16);
+  return q;
+}
+CA_HD inline void pv_st(unsigned char* raw, int i, PV q) { memcpy(raw + 16 * static_cast<size_t>(i), &q, 16); }
+
+// std::lower_bound's bisection, written out: harmonize_pitches runs it on a vector whose tail is not ordered, so the
+// probe sequence is part of the behaviour (find_closest_pitch, source/rt.resynth.lib.autotune.cpp:189-218)
+template <class Get>
+CA_HD inline int closest_index(double pitch, int n, Get&& get) {
+  if (n == 0) return -1;
+  int first = 0, len = n;
+  while (len > 0) {
+    const int half = len >> 1;
+    if (get(first + half) < pitch) {
+      first += half + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  if (first == n) return n - 1;
+  if (first == 0) return 0;
+  const float d_lb = static_cast<float>(fabs(pitch - get(first)));
+  const float d_prev = static_cast<float>(fabs(pitch - get(first - 1)));
+  return d_lb < d_prev ? first : first - 1;
+}
+
+CA_HD inline int harmonize_pairs(float amount, unsigned char* raw, int n, int cap) {  // algo.cpp:318-371
+  if (!amount) return n;
+  const int sz = n;
+  for (int i = 0; i < sz; ++i) {
+    const PV p = pv_ld(raw, i);
+    const double harmonized = p.pitch + amount;
+    const int c = closest_index(harmonized, n, [&](int j) { return pv_ld(raw, j).pitch; });
+    PV q = pv_ld(raw, c);
+    if (static_cast<float>(fabs(q.pitch - harmonized)) <= 0.0001f) {
+      q.vol += p.vol;
+      pv_st(raw, c, q);
+    } else if (n < cap) {
+      pv_st(raw, n++, PV{harmonized, p.vol});
+    }
+  }
+  // merge of the runs [0, sz) and [sz, n) by pitch into the work half, ties keep the first run first; then copy back
+  int a = 0, b = sz, w = cap;
+  while (a < sz && b < n) {
+    const PV x = pv_ld(raw, a), y = pv_ld(raw, b);
+    if (y.pitch < x.pitch) {
+      pv_st(raw, w++, y);
+      ++b;
+    } else {
+      pv_st(raw, w++, x);
+      ++a;
+    }
+  }
+  while (a < sz) pv_st(raw, w++, pv_ld(raw, a++));
+  while (b < n) pv_st(raw, w++, pv_ld(raw, b++));
+  for (int i = 0; i < n; ++i) pv_st(raw, i, pv_ld(raw, cap + i));
+  return n;
+}
+
+// MusicalScalePitches::closest_pitch, source/rt.resynth.lib.autotune.cpp:96-146
+CA_HD inline double scale_closest(const double* scale, int n_scale, double root, double pitch) {
+  const double octave_dist = (pitch - root) / 12;
+  const int octaves = octave_dist >= 0. ? static_cast<int>(octave_dist) : static_cast<int>(octave_dist) - 1;
+  const double rel = (pitch - octaves * 12) - root;
+  int i = 0;
+  for (; i < n_scale - 1; ++i)
+    if (rel < 0.5 * (scale[i] + scale[i + 1])) break;
+  return pitch - (rel - scale[i]);
+}
+
+CA_HD inline int autotune_pairs(const PitchParams& p, unsigned char* raw, int n) {  // algo.cpp:186-229; in place, output index <= input index
+  int o = 0;
+  for (int i = 0; i < n; ++i) {
+    const PV pv = pv_ld(raw, i);
+    double t = pv.pitch;
+    if (p.autotune != CA_AUTOTUNE_NONE) {
+      bool has = true;
+      if (pv.pitch <= p.at_max_pitch) {
+        if (p.autotune == CA_AUTOTUNE_TABLE) {
+          const int c = closest_index(pv.pitch, p.n_table, [&](int j) { return p.table[j]; });
+          has = c >= 0;
+          if (has) t = p.table[c];
+        } else {
+          t = scale_closest(p.table, p.n_table, p.scale_root, pv.pitch);
+        }
+        if (has && t > p.at_max_pitch) t = pv.pitch;  // keeps the output sorted
+      }
+      if (!has || !(fabs(t - pv.pitch) <= p.at_tolerance)) continue;
+    }
+    if (o > 0) {
+      PV last = pv_ld(raw, o - 1);
+      if (fabs(last.pitch - t) < 0.0001f) {
+        last.vol += pv.vol;
+        pv_st(raw, o - 1, last);
+        continue;
+      }
+    }
+    pv_st(raw, o++, PV{t, pv.vol});
+  }
+  return o;
+}
+
+static_assert(sizeof(Tuned) == 32 && sizeof(PV) == 16, "a Tuned row holds two (pitch, volume) pairs per entry");
+
+// Peaks of one frame (ascending frequency) -> tuned list. Returns the number of entries written to `out` (<= cnt, or
+// <= tcap with the optional stages; `out` then has room for tcap entries).
 //   freq -> midi pitch 69 + 12 log2(f/440) (include/midi.h:226-231), dB -> volume 10^(dB/20);
 //   aggregation of peaks closer than nearby_distance_tones (interval diameter), volume-weighted pitch, summed volume,
-//   min_volume cut (source/rt.resynth.lib.algo.cpp:10-230); entries that land on the same pitch are merged.
-CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
-                              Tuned* out) {
+//   min_volume cut (source/rt.resynth.lib.algo.cpp:10-230); entries that land on the same pitch are merged
+//   (autotune_pitches with the identity transform); OPTS: shift, harmonize, autotune, shift, harmonize in between.
+template <bool OPTS>
+CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
+                                Tuned* out) {
   int T = 0;
   bool open = false;
   double mn = 0, mx = 0, sv = 0, spv = 0;
+  unsigned char* raw = reinterpret_cast<unsigned char*>(out);
   auto close = [&] {
     if (open && !(sv < p.min_volume)) {
       const double pitch = spv / sv;
-      if (T > 0 && fabs(out[T - 1].pitch - pitch) < 0.0001f) out[T - 1].vol += sv;
-      else {
+      if (OPTS) {
+        pv_st(raw, T++, PV{pitch, sv});
+      } else if (T > 0 && fabs(out[T - 1].pitch - pitch) < 0.0001f) {
+        out[T - 1].vol += sv;
+      } else {
         out[T].pitch = pitch;
         out[T].vol = sv;
         ++T;
@@ -139,6 +286,35 @@ CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, con
     spv += pitch * vol;
   }
   close();
+  if (OPTS) {
+    const int cap = p.tcap;
+    if (p.shift_pre != 0.f)
+      for (int i = 0; i < T; ++i) {  // shift_pitches, algo.cpp:307-316
+        PV q = pv_ld(raw, i);
+        q.pitch += p.shift_pre;
+        pv_st(raw, i, q);
+      }
+    T = harmonize_pairs(p.harm_pre, raw, T, cap);
+    T = autotune_pairs(p, raw, T);
+    if (p.shift_post != 0.f)
+      for (int i = 0; i < T; ++i) {
+        PV q = pv_ld(raw, i);
+        q.pitch += p.shift_post;
+        pv_st(raw, i, q);
+      }
+    T = harmonize_pairs(p.harm_post, raw, T, cap);
+    // pairs -> Tuned entries, last first: entry i covers the bytes of pairs 2i and 2i+1, which are >= i
+    for (int i = T - 1; i >= 0; --i) {
+      const PV q = pv_ld(raw, i);
+      Tuned t;
+      t.pitch = q.pitch;
+      t.vol = q.vol;
+      t.ai = 0;
+      t.volume = 0;
+      t.min_change = 0;
+      memcpy(raw + 32 * static_cast<size_t>(i), &t, 32);
+    }
+  }
   for (int i = 0; i < T; ++i) {
     const float new_freq = static_cast<float>(440.f * pow(p.semitone, out[i].pitch - 69.));
     out[i].volume = static_cast<float>(p.gain * out[i].vol / 0.1f);
@@ -146,6 +322,12 @@ CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, con
     out[i].min_change = min_change_for(out[i].ai);
   }
   return T;
+}
+
+CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
+                              Tuned* out) {
+  return p.opt_active ? pitch_prefix_t<true>(p, peak_bin, peak_off, peak_db, cnt, out)
+                      : pitch_prefix_t<false>(p, peak_bin, peak_off, peak_db, cnt, out);
 }
 
 struct Note {

@@ -60,7 +60,7 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const float* peak
   const int P = p.P;
   std::vector<Note> notes;       // sounding notes (tracked or releasing)
   std::vector<int> played;       // indices into notes of tracked notes, sorted by pitch
-  std::vector<Tuned> tuned(std::max(P, 1));
+  std::vector<Tuned> tuned(std::max(std::max(P, p.opt_active ? p.tcap : 0), 1));
   std::vector<int> change, order, next_played;
   std::vector<char> keep;
 
@@ -148,6 +148,21 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const float* peak
 }
 
 
+// make_pitch_params for the kernels: the autotune table (a host pointer in the parameters) goes to the device first
+int device_pitch_params(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, int P, PitchParams* out) {
+  *out = make_pitch_params(prm, n_samples, frames, P);
+  if (out->autotune != CA_AUTOTUNE_NONE && out->n_table > 0) {
+    const size_t bytes = sizeof(double) * static_cast<size_t>(out->n_table);
+    const int rc = ensure_scratch(ctx, 11, bytes);
+    if (rc) return rc;
+    CA_CUDA_OK(ctx, cudaMemcpy(ctx->d_scratch[11], prm.opts.table, bytes, cudaMemcpyHostToDevice));
+    out->table = static_cast<const double*>(ctx->d_scratch[11]);
+  } else {
+    out->table = nullptr;
+  }
+  return CA_OK;
+}
+
 // Device form of steps 2-3: tuned lists, tracking and segments by the kernels of pitch.cu, rendering, audio back. Nothing
 // but the audio and 16 bytes of counters crosses PCIe, and the host does no per-frame work.
 template <class Lap>
@@ -155,7 +170,8 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
                           float* h_out, int64_t* h_stats, bool timing, Lap&& lap) {
   cudaStream_t st = ctx->own_stream;
   const int P = prm.stft.max_peaks;
-  const PitchParams pp = make_pitch_params(prm, n_samples, frames, P);
+  PitchParams pp;
+  if (int prc = device_pitch_params(ctx, prm, n_samples, frames, P, &pp)) return prc;
   const size_t rows = static_cast<size_t>(frames) * n_streams, total = static_cast<size_t>(n_streams) * n_samples;
   const size_t out_bytes = sizeof(float) * 2 * total;
   const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
@@ -241,7 +257,8 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
 int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, const float* h_x, int64_t n_samples, int64_t n_streams,
                                int64_t frames, float* h_out, int64_t* h_stats, bool* overflowed, int64_t* needed) {
   const int P = prm.stft.max_peaks;
-  const PitchParams pp = make_pitch_params(prm, n_samples, frames, P);
+  PitchParams pp;
+  if (int prc = device_pitch_params(ctx, prm, n_samples, frames, P, &pp)) return prc;
   const size_t rows = static_cast<size_t>(frames) * n_streams, total = static_cast<size_t>(n_streams) * n_samples;
   const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
   const size_t b_tiles = (3 * sizeof(int64_t) + sizeof(int32_t)) * static_cast<size_t>(n_tiles);
@@ -328,6 +345,19 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
     return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: LINEAR envelopes only (as rt.resynth.lib.cpp:75-81)");
   if (prm.max_channels <= 0) prm.max_channels = 254;
   if (prm.stft.max_peaks <= 0) prm.stft.max_peaks = 200;
+  {
+    const ca_pitch_options& o = prm.opts;
+    if (o.autotune != CA_AUTOTUNE_NONE && o.autotune != CA_AUTOTUNE_TABLE && o.autotune != CA_AUTOTUNE_SCALE)
+      return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: opts.autotune is not a ca_autotune value");
+    if (o.autotune == CA_AUTOTUNE_TABLE && (o.n_table < 0 || o.n_table > 4096 || (o.n_table > 0 && !o.table)))
+      return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: opts.table must hold 0 ... 4096 allowed pitches");
+    if (o.autotune == CA_AUTOTUNE_SCALE && (o.n_table < 2 || o.n_table > 16 || !o.table))
+      return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: opts.table must hold the 2 ... 16 pitches of the scale");
+    if (o.autotune != CA_AUTOTUNE_NONE)
+      for (int i = 1; i < o.n_table; ++i)
+        if (!(o.table[i - 1] <= o.table[i]))
+          return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: opts.table must be ascending");
+  }
   int rc = stft_plan(ctx, &prm.stft);
   if (rc) return rc;
   const int W = prm.stft.window, hop = prm.stft.hop, P = prm.stft.max_peaks;

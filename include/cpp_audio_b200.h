@@ -165,6 +165,27 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
  * Analysis, the pitch pipeline (frame-sequential per stream: one CTA per stream walks its frames) and voice rendering all run on
  * the GPU; only the audio crosses PCIe. Events of frame k act from sample window-1 + k*hop on. max_peaks and max_channels are
  * limited to 256 on this path. */
+/* Optional stages of RtResynth::step between reduce_pitches and track_pitches (source/rt.resynth.lib.cpp:1687-1707):
+ * shift_pitches / harmonize_pitches (source/rt.resynth.lib.algo.cpp:307-371) before and after autotune_pitches (:186-229).
+ * All zero = rt.resynth out of the box (pitch_shift_* = pitch_harmonize_* = 0, use_autotune = false). The transform of
+ * mkAutotuneFunction (:1762-1869) is passed as data: AutotuneType::Chord and ::FixedSizeIntervals both reduce to "closest
+ * entry of the sorted vector allowed_pitches" (CA_AUTOTUNE_TABLE: hand over that vector), ::MusicalScale to
+ * MusicalScalePitches::closest_pitch (source/rt.resynth.lib.autotune.cpp:96-146; CA_AUTOTUNE_SCALE: the scale's pitches
+ * 0 ... 12 and the root pitch). A frame's list is capped at stft.max_peaks entries at every stage. */
+enum ca_autotune { CA_AUTOTUNE_NONE = 0, CA_AUTOTUNE_TABLE = 1, CA_AUTOTUNE_SCALE = 2 };
+typedef struct ca_pitch_options {
+  float shift_pre_autotune;         /* pitch_shift_pre_autotune, semitones */
+  float harmonize_pre_autotune;     /* pitch_harmonize_pre_autotune */
+  float shift_post_autotune;
+  float harmonize_post_autotune;
+  int32_t autotune;                 /* ca_autotune */
+  float autotune_max_pitch;         /* pitches above are played but not tuned (autotune_max_pitch) */
+  float autotune_tolerance_pitches; /* pitches further than this from their tuned pitch are not played */
+  int32_t n_table;                  /* TABLE: <= 4096 entries, may be 0 (nothing is played below max_pitch); SCALE: 2 ... 16 */
+  const double* table;              /* HOST pointer. TABLE: allowed pitches, ascending; SCALE: scale pitches, first 0, last 12 */
+  double scale_root_pitch;          /* SCALE: A_pitch + transpose + half_tones_distance(La, root note), :1862-1865 */
+} ca_pitch_options;
+
 typedef struct ca_roundtrip_params {
   ca_stft_params stft;          /* window / hop / sample rate / min_db; max_peaks = peak capacity per frame */
   float nearby_distance_tones;  /* 0.4   rt.resynth.lib.cpp:948 */
@@ -175,6 +196,7 @@ typedef struct ca_roundtrip_params {
   ca_ahdsr env;                 /* :957-961 (all zero, sustain 1 by default) */
   int32_t max_channels;         /* 254 = 2*127, :201-210 */
   int32_t host_threads;         /* 0: pitch pipeline on the device (default). n > 0 / -1: its host form on n / all host threads (A/B) */
+  ca_pitch_options opts;        /* shift / harmonize / autotune, all zero = off */
 } ca_roundtrip_params;
 /* h_x [n_streams][n_samples] -> h_out [n_streams][n_samples][2] float32 (stereo). h_stats nullable [n_streams][2]:
  * notes started, notes dropped (pool full). */

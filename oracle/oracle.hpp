@@ -902,6 +902,95 @@ struct PitchVolume {
   double volume;
 };
 
+// Optional stages of RtResynth::step between reduce_pitches and track_pitches (source/rt.resynth.lib.cpp:1687-1707).
+// All zero = what rt.resynth does out of the box (no shift, no harmonisation, use_autotune == false).
+// Same layout as ca_pitch_options (include/cpp_audio_b200.h) so that a test hands one block to both sides.
+struct PitchOptions {
+  float shift_pre_autotune = 0;       // pitch_shift_pre_autotune
+  float harmonize_pre_autotune = 0;   // pitch_harmonize_pre_autotune
+  float shift_post_autotune = 0;
+  float harmonize_post_autotune = 0;
+  int32_t autotune = 0;               // 0: identity (:1763-1765); 1: closest of `table` = allowed_pitches (Chord and
+                                      // FixedSizeIntervals, :1767-1858); 2: musical scale, `table` = scale pitches 0 .. 12 (:1859-1868)
+  float autotune_max_pitch = 0;       // pitches above are played but not tuned
+  float autotune_tolerance_pitches = 0;
+  int32_t n_table = 0;
+  const double* table = nullptr;
+  double scale_root_pitch = 0;        // A_pitch + transpose + half_tones_distance(La, root note), :1862-1865
+};
+
+constexpr float kPitchEpsilon = 0.0001f;  // source/rt.resynth.lib.algo.cpp:3
+
+// find_closest_pitch, source/rt.resynth.lib.autotune.cpp:189-218 (precondition: ordered; harmonize_pitches calls it on a
+// vector whose tail is not, so the bisection of std::lower_bound is part of the behaviour)
+template <class V, class F>
+int find_closest_pitch(double pitch, const V& pitches, int n, F&& get) {
+  if (n == 0) return -1;
+  int lb = static_cast<int>(std::lower_bound(pitches, pitches + n, pitch, [&](const auto& a, double c) { return get(a) < c; }) - pitches);
+  if (lb == n) return lb - 1;
+  if (lb == 0) return 0;
+  const float dist_lb = static_cast<float>(std::abs(pitch - get(pitches[lb])));
+  const float dist_prev = static_cast<float>(std::abs(pitch - get(pitches[lb - 1])));
+  return dist_lb < dist_prev ? lb : lb - 1;
+}
+
+inline void shift_pitches(float amount, std::vector<PitchVolume>& v) {  // algo.cpp:307-316
+  if (!amount) return;
+  for (auto& q : v) q.midipitch += amount;
+}
+
+inline void harmonize_pitches(float amount, std::vector<PitchVolume>& work, std::vector<PitchVolume>& v) {  // algo.cpp:318-371
+  if (!amount) return;
+  const int sz = static_cast<int>(v.size());
+  for (int i = 0; i < sz; ++i) {
+    const double harmonized = v[i].midipitch + amount;
+    const int c = find_closest_pitch(harmonized, v.data(), static_cast<int>(v.size()), [](const PitchVolume& q) { return q.midipitch; });
+    const float dist = static_cast<float>(std::abs(v[c].midipitch - harmonized));
+    if (dist <= kPitchEpsilon) v[c].volume += v[i].volume;
+    else v.push_back({harmonized, v[i].volume});
+  }
+  // merge_sort_step (cpp.algorithms): the two sorted runs [0, sz) and [sz, end) merged by pitch; ties keep the first run first
+  work.resize(v.size());
+  std::merge(v.begin(), v.begin() + sz, v.begin() + sz, v.end(), work.begin(),
+             [](const PitchVolume& a, const PitchVolume& b) { return a.midipitch < b.midipitch; });
+  work.swap(v);
+}
+
+// MusicalScalePitches::closest_pitch / distance_to, source/rt.resynth.lib.autotune.cpp:96-146
+inline double scale_closest_pitch(const double* scale, int n_scale, double root_pitch, double pitch) {
+  const double octave_dist = (pitch - root_pitch) / 12;
+  const int octaves = octave_dist >= 0. ? static_cast<int>(octave_dist) : static_cast<int>(octave_dist) - 1;
+  const double rel = (pitch - octaves * 12) - root_pitch;
+  int i = 0;
+  for (; i < n_scale - 1; ++i)
+    if (rel < 0.5 * (scale[i] + scale[i + 1])) break;
+  return pitch - (rel - scale[i]);
+}
+
+// autotune_pitches, algo.cpp:186-229, with the transforms of mkAutotuneFunction (rt.resynth.lib.cpp:1762-1869)
+inline void autotune_pitches(const PitchOptions& o, const std::vector<PitchVolume>& in, std::vector<PitchVolume>& out) {
+  out.clear();
+  for (const auto& pv : in) {
+    double t = pv.midipitch;
+    bool has = true;
+    if (o.autotune != 0) {
+      if (pv.midipitch <= o.autotune_max_pitch) {
+        if (o.autotune == 1) {
+          const int c = find_closest_pitch(pv.midipitch, o.table, o.n_table, [](double q) { return q; });
+          has = c >= 0;
+          if (has) t = o.table[c];
+        } else {
+          t = scale_closest_pitch(o.table, o.n_table, o.scale_root_pitch, pv.midipitch);
+        }
+        if (has && t > o.autotune_max_pitch) t = pv.midipitch;  // keeps the output sorted
+      }
+      if (!has || !(std::abs(t - pv.midipitch) <= o.autotune_tolerance_pitches)) continue;
+    }
+    if (!out.empty() && std::abs(out.back().midipitch - t) < kPitchEpsilon) out.back().volume += pv.volume;
+    else out.push_back({t, pv.volume});
+  }
+}
+
 // SPEC S10: the reference draws start phases and pans from mersenne<> (external); the oracle and the product use this hash.
 inline float hash_unit(uint64_t id, uint64_t salt) {
   uint64_t z = id * 0x9E3779B97F4A7C15ull + salt * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
@@ -924,6 +1013,7 @@ struct RoundTripParams {
   float stereo_spread = 1.f;            // :955
   Ahdsr env{0, LINEAR, 0, 0, LINEAR, 0, LINEAR, 1.f};  // :957-961
   int max_channels = 254;               // 2 * 127 voices, :201-210, gen.crtp.h:225
+  PitchOptions opts;                    // shift / harmonize / autotune (:1687-1707), off by default
 };
 
 template <class T>
@@ -983,12 +1073,13 @@ private:
       sum_pv += q.midipitch * q.volume;
     }
     close();
-    // autotune_pitches with the identity transform (:192-229): merges pitches closer than pitch_epsilon
-    tuned_.clear();
-    for (auto& q : reduced_) {
-      if (!tuned_.empty() && std::abs(tuned_.back().midipitch - q.midipitch) < 0.0001f) tuned_.back().volume += q.volume;
-      else tuned_.push_back(q);
-    }
+    // shift / harmonize / autotune / shift / harmonize (rt.resynth.lib.cpp:1687-1707); with the default options only the
+    // merge of pitches closer than pitch_epsilon inside autotune_pitches (identity transform) acts
+    shift_pitches(prm_.opts.shift_pre_autotune, reduced_);
+    harmonize_pitches(prm_.opts.harmonize_pre_autotune, pitches_tmp_, reduced_);
+    autotune_pitches(prm_.opts, reduced_, tuned_);
+    shift_pitches(prm_.opts.shift_post_autotune, tuned_);
+    harmonize_pitches(prm_.opts.harmonize_post_autotune, pitches_tmp_, tuned_);
     // track_pitches (:256-305)
     std::vector<int> change(tuned_.size(), -1);
     std::vector<char> keep(played_.size(), 0);
@@ -1073,7 +1164,7 @@ private:
   std::vector<ResynthVoice<T>> channels_;
   std::vector<int64_t> note_of_;
   std::vector<FreqMag<double>> freqmags_;
-  std::vector<PitchVolume> pv_, reduced_, tuned_;
+  std::vector<PitchVolume> pv_, reduced_, tuned_, pitches_tmp_;
   std::vector<PlayedNote> played_;
   int64_t next_noteid_ = 0, dropped_ = 0;
 };

@@ -67,6 +67,10 @@ def lib():
         L.orc_sine_trace.argtypes = [C.c_double, C.c_double, C.c_int64, p]
         L.orc_roundtrip.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p, p,
                                     C.c_int]
+        L.orc_pitch_stages.argtypes = [p, p, p, C.c_int, C.c_int]
+        L.orc_pitch_stages.restype = C.c_int
+        L.orc_roundtrip_opts.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
+                                         p, p, C.c_int]
         _lib = L
     return _lib
 
@@ -124,6 +128,14 @@ def stft_analyze(x: np.ndarray, window: int, hop: int, window_type: int = 1, sig
                                  float(min_db), max_peaks, _ptr(sqmag), _ptr(pb), _ptr(pf), _ptr(pd), _ptr(pc), threads)
     assert got == frames
     return dict(frames=frames, n_fft=n_fft, sqmag=sqmag, peak_bin=pb, peak_freq=pf, peak_db=pd, peak_count=pc)
+
+
+class PitchOptions(C.Structure):
+    """Mirror of oracle::PitchOptions / ca_pitch_options: optional stages of RtResynth::step (rt.resynth.lib.cpp:1687-1707)."""
+    _fields_ = [("shift_pre_autotune", C.c_float), ("harmonize_pre_autotune", C.c_float), ("shift_post_autotune", C.c_float),
+                ("harmonize_post_autotune", C.c_float), ("autotune", C.c_int32), ("autotune_max_pitch", C.c_float),
+                ("autotune_tolerance_pitches", C.c_float), ("n_table", C.c_int32), ("table", C.c_void_p),
+                ("scale_root_pitch", C.c_double)]
 
 
 def make_ahdsr(attack=0, hold=0, decay=0, release=0, sustain=1.0, attack_itp=0, decay_itp=0, release_itp=0) -> Ahdsr:
@@ -201,7 +213,7 @@ def sine_trace(start_angle: float, angle_increment: float, n: int) -> np.ndarray
 
 
 def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: int = 48000, min_db: float = -80.0,
-              gain: float = 1.0, stereo_spread: float = 1.0, env: Ahdsr | None = None, threads: int = 1):
+              gain: float = 1.0, stereo_spread: float = 1.0, env: Ahdsr | None = None, threads: int = 1, opts=None):
     """Analysis -> pitch pipeline -> resynthesis of each row of x (offline loop of the reference). Returns
     (audio float64 [streams, samples, 2], stats int64 [streams, 2] = notes started, notes dropped)."""
     x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
@@ -209,9 +221,34 @@ def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: in
     out = np.zeros((streams, n, 2), dtype=np.float64)
     stats = np.zeros((streams, 2), dtype=np.int64)
     e = env if env is not None else make_ahdsr()
-    lib().orc_roundtrip(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
-                        C.byref(e), _ptr(out), _ptr(stats), threads)
+    lib().orc_roundtrip_opts(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
+                             C.byref(e), None if opts is None else C.byref(opts), _ptr(out), _ptr(stats), threads)
     return out, stats
+
+
+def pitch_stages(opts: PitchOptions, pitch, volume, cap: int = 1024):
+    """shift / harmonize / autotune / shift / harmonize on one (pitch, volume) list; returns the resulting arrays."""
+    n = len(pitch)
+    pp = np.zeros(max(cap, n), dtype=np.float64)
+    vv = np.zeros(max(cap, n), dtype=np.float64)
+    pp[:n] = pitch
+    vv[:n] = volume
+    m = lib().orc_pitch_stages(C.byref(opts), _ptr(pp), _ptr(vv), n, len(pp))
+    assert m <= len(pp)
+    return pp[:m].copy(), vv[:m].copy()
+
+
+def make_pitch_options(shift_pre=0.0, harmonize_pre=0.0, shift_post=0.0, harmonize_post=0.0, allowed_pitches=None, scale=None,
+                       scale_root_pitch=0.0, max_pitch=151.0, tolerance=0.0) -> PitchOptions:
+    o = PitchOptions(shift_pre, harmonize_pre, shift_post, harmonize_post, 0, max_pitch, tolerance, 0, None, scale_root_pitch)
+    tab = allowed_pitches if allowed_pitches is not None else scale
+    if tab is not None:
+        tab = np.ascontiguousarray(tab, dtype=np.float64)
+        o.autotune = 1 if allowed_pitches is not None else 2
+        o.n_table = int(tab.shape[0])
+        o.table = tab.ctypes.data
+        o._keep = tab
+    return o
 
 
 def vocoder(modulator: np.ndarray, carrier: np.ndarray, sample_rate: int = 48000, modulator_window_seconds: float = 0.04,

@@ -268,8 +268,27 @@ void orc_sine_trace(double start_angle, double angle_increment, int64_t n, doubl
 
 // Analysis -> pitch pipeline -> resynthesis of n_streams independent streams (BASELINE config 4), each through the offline
 // loop of the reference. out: [streams][samples][2] double. stats (nullable): [streams][2] = notes started, notes dropped.
-void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
-                   float gain, float stereo_spread, const Ahdsr* env, double* out, int64_t* stats, int threads) {
+// the optional stages alone (shift, harmonize, autotune, shift, harmonize; rt.resynth.lib.cpp:1687-1707) on one list;
+// pitch / volume hold n entries and have room for `cap`; returns the resulting count
+int orc_pitch_stages(const PitchOptions* o, double* pitch, double* volume, int n, int cap) {
+  std::vector<PitchVolume> reduced(n), tuned, tmp;
+  for (int i = 0; i < n; ++i) reduced[i] = {pitch[i], volume[i]};
+  shift_pitches(o->shift_pre_autotune, reduced);
+  harmonize_pitches(o->harmonize_pre_autotune, tmp, reduced);
+  autotune_pitches(*o, reduced, tuned);
+  shift_pitches(o->shift_post_autotune, tuned);
+  harmonize_pitches(o->harmonize_post_autotune, tmp, tuned);
+  const int m = static_cast<int>(std::min<size_t>(tuned.size(), cap));
+  for (int i = 0; i < m; ++i) {
+    pitch[i] = tuned[i].midipitch;
+    volume[i] = tuned[i].volume;
+  }
+  return static_cast<int>(tuned.size());
+}
+
+void orc_roundtrip_opts(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
+                        float gain, float stereo_spread, const Ahdsr* env, const PitchOptions* opts, double* out, int64_t* stats,
+                        int threads) {
   parallel_for(n_streams, threads, [&](int64_t s) {
     RoundTripParams p;
     p.sample_rate = sample_rate;
@@ -279,6 +298,7 @@ void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sam
     p.gain = gain;
     p.stereo_spread = stereo_spread;
     if (env) p.env = *env;
+    if (opts) p.opts = *opts;
     RoundTrip<double> rt(p);
     rt.run(x + s * n_samples, n_samples, out + s * n_samples * 2);
     if (stats) {
@@ -286,6 +306,11 @@ void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sam
       stats[2 * s + 1] = rt.dropped_notes();
     }
   });
+}
+
+void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
+                   float gain, float stereo_spread, const Ahdsr* env, double* out, int64_t* stats, int threads) {
+  orc_roundtrip_opts(x, n_samples, n_streams, sample_rate, window, hop, min_db, gain, stereo_spread, env, nullptr, out, stats, threads);
 }
 
 // Vocoder (source/rt.resynth.lib.vocoder.cpp) over n_streams independent (modulator, carrier) pairs, one sample at a time.
