@@ -52,8 +52,7 @@ def run_tool(*args):
 
 @pytest.fixture(scope="module")
 def tool():
-    if not os.path.exists(TOOL):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s"])  # incremental: rebuilt when the C ABI header changed
     return TOOL
 
 
@@ -76,7 +75,41 @@ def test_dry_run_derives_the_reference_defaults(tool, tmp_path):
     assert d["window"] == 2 * int(0.5 * np.float32(0.1814) * sr) == 8706 and d["hop"] == 4320 and d["fft_length"] == 16384
     assert d["sample_rate"] == sr and d["frames"] == sr // 2
     assert d["env"][:4] == [480, 0, 0, 960] and abs(d["gain"] - 0.5) < 1e-7
-    assert "pitch_shift_pre_autotune" in r.stderr  # a stage outside the path: reported, not silently dropped
+    po = d["pitch_options"]  # shift / harmonize / autotune are stages of the path (rt.resynth.lib.cpp:1687-1707)
+    assert po["shift"] == [2.0, 0.0] and po["harmonize"] == [0.0, 0.0] and po["autotune"] == 0 and po["n_table"] == 0
+
+
+def test_dry_run_autotune_presets(tool, tmp_path):
+    """mkAutotuneFunction (rt.resynth.lib.cpp:1762-1869) as data: scale, chord (three frequency layouts), fixed intervals."""
+    write_wav(tmp_path / "v.wav", 0.1 * np.ones(1000), 48000, "i16")
+
+    def derive(enums=None, ints=None, u64=None, floats=None):
+        pr = {"bool_params": {"use_autotune": True}, "enum_params": enums or {}, "int32_params": ints or {},
+              "uint64_params": u64 or {}, "float_params": floats or {}}
+        (tmp_path / "p.json").write_text(json.dumps(pr))
+        r = run_tool("--dry-run", "--voice", str(tmp_path / "v.wav"), "--out", str(tmp_path / "o.wav"), "--preset", str(tmp_path / "p.json"))
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout)["pitch_options"]
+
+    # defaults (:950-976): musical scale, major, root Do, tolerance 100, max pitch 150
+    po = derive()
+    assert po["autotune"] == 2 and po["n_table"] == 8 and po["table_first"] == 0 and po["table_last"] == 12
+    assert po["scale_root_pitch"] == 69 - 9 and po["tolerance"] == 100 and po["max_pitch"] == 150
+    po = derive(enums={"autotune_musical_scale_root_note": 2, "autotune_musical_scale_mode": 2}, ints={"autotune_root_note_halftones_transpose": -1})
+    assert po["scale_root_pitch"] == 69 - 1 + (2 - 9)
+    # chord 0b10010001 (root, major third, fifth) on Re, replicated on every octave: 11 octaves x 3 pitches around C5 + 2
+    po = derive(enums={"autotune_type": 1, "autotune_chord_frequencies": 2, "autotune_musical_scale_root_note": 2},
+                floats={"autotune_tolerance_pitches": 0.5})
+    assert po["autotune"] == 1 and po["n_table"] == 33 and po["table_first"] == 74 - 60 and po["table_last"] == 74 + 60 + 7
+    assert po["tolerance"] == 0.5
+    po = derive(enums={"autotune_type": 1, "autotune_chord_frequencies": 0}, u64={"autotune_bit_chord": 5})
+    assert po["n_table"] == 2 and po["table_first"] == 72 and po["table_last"] == 74
+    # harmonics (the default layout): 36 harmonics, up and down, per chord note; the 36-th harmonic lies 62 semitones up
+    po = derive(enums={"autotune_type": 1}, u64={"autotune_bit_chord": 1})
+    assert po["n_table"] == 72 and po["table_first"] == 72 - 62 and po["table_last"] == 72 + 62
+    # fixed intervals of 3 semitones through Mi + 1 = 5: 2, 5, 8 ... 149
+    po = derive(enums={"autotune_type": 2, "autotune_musical_scale_root_note": 4}, ints={"autotune_factor": 3, "autotune_root_note_halftones_transpose": 1})
+    assert po["autotune"] == 1 and po["table_first"] == 2 and po["table_last"] == 149 and po["n_table"] == 50
 
 
 def test_dry_run_without_preset_and_error_paths(tool, tmp_path):

@@ -15,9 +15,11 @@
 // The float parameters of the analysis -> resynthesis path are honoured (names of rt.resynth.lib.cpp:1944-2040): window and
 // stride, min_volume, nearby_distance_tones, max_track_pitches, stereo_spread, env_*, analysis_volume, and of the vocoder:
 // voice_volume, carrier_volume, vocoder_volume, vocoder_modulator_window_size_seconds, vocoder_stride_seconds,
-// vocoder_count_bands (int32), vocoder_min_freq, vocoder_max_freq. The autotune / pitch-shift parameters and the real-time
-// carrier synth belong to stages outside this path: a non-default value is reported and ignored. "limit" post-processing (an
-// external compressor in the reference) clips to [-1, 1].
+// vocoder_count_bands (int32), vocoder_min_freq, vocoder_max_freq; and the pitch stages of RtResynth::step (:1687-1707):
+// pitch_shift_*, pitch_harmonize_*, use_autotune with autotune_type / scale mode / root note / transpose / chord bits /
+// chord frequency layout / interval factor / tolerance / max pitch, turned into ca_pitch_options the way mkAutotuneFunction
+// (:1762-1869) builds its transform. The real-time carrier synth is outside this path. "limit" post-processing (an external
+// compressor in the reference) clips to [-1, 1].
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -39,7 +41,8 @@ struct Job {
 
 struct Derived {  // what the preset means at a sample rate (RtResynth getters, rt.resynth.lib.cpp:484-487, :1576-1578)
   int window = 0, hop = 0;
-  ca_roundtrip_params prm{};
+  ca_roundtrip_params prm{};  // prm.opts.table stays null here: the table lives in `table` and is attached at the call
+  std::vector<double> table;  // autotune: allowed pitches (Chord / FixedSizeIntervals) or the scale's pitches (MusicalScale)
   ca_vocoder_params voc{};  // Vocoder::Params, rt.resynth.lib.cpp:1378-1395
 };
 
@@ -123,19 +126,75 @@ Derived derive(const mini_json::Value* preset, int sample_rate) {
   d.voc.vol_modulator = preset_float(preset, "voice_volume", 0.f);
   d.voc.vol_carrier = preset_float(preset, "carrier_volume", 0.1f);
   d.voc.vol_vocoder = preset_float(preset, "vocoder_volume", 0.f);
-  if (preset) {  // stages outside the analysis -> resynthesis path
-    struct { const char* name; float neutral; } ignored[] = {
-        {"pitch_shift_pre_autotune", 0.f}, {"pitch_shift_post_autotune", 0.f}, {"pitch_harmonize_pre_autotune", 0.f},
-        {"pitch_harmonize_post_autotune", 0.f}};
-    const mini_json::Value* fp = preset->find("float_params");
-    for (auto& ig : ignored) {
-      const mini_json::Value* v = fp ? fp->find(ig.name) : nullptr;
-      if (v && static_cast<float>(v->as_number()) != ig.neutral)
-        std::fprintf(stderr, "note: preset param '%s' = %g belongs to a stage outside the B200 path and is ignored\n", ig.name, v->as_number());
+  // shift / harmonize / autotune stages of RtResynth::step (rt.resynth.lib.cpp:1687-1707; defaults :950-976)
+  ca_pitch_options& o = p.opts;
+  auto quiet_float = [&](const char* name, float dflt) {
+    const mini_json::Value* fp = preset ? preset->find("float_params") : nullptr;
+    const mini_json::Value* v = fp ? fp->find(name) : nullptr;
+    return v ? static_cast<float>(v->as_number()) : dflt;
+  };
+  auto quiet_num = [&](const char* section, const char* name, double dflt) {
+    const mini_json::Value* sp = preset ? preset->find(section) : nullptr;
+    const mini_json::Value* v = sp ? sp->find(name) : nullptr;
+    return v ? v->as_number() : dflt;
+  };
+  o.shift_pre_autotune = quiet_float("pitch_shift_pre_autotune", 0.f);
+  o.shift_post_autotune = quiet_float("pitch_shift_post_autotune", 0.f);
+  o.harmonize_pre_autotune = quiet_float("pitch_harmonize_pre_autotune", 0.f);
+  o.harmonize_post_autotune = quiet_float("pitch_harmonize_post_autotune", 0.f);
+  if (quiet_num("bool_params", "use_autotune", 0) != 0) {  // mkAutotuneFunction, rt.resynth.lib.cpp:1762-1869
+    o.autotune_tolerance_pitches = quiet_float("autotune_tolerance_pitches", 100.f);
+    o.autotune_max_pitch = static_cast<float>(static_cast<int>(quiet_num("int32_params", "autotune_max_pitch", 150)));
+    const int type = static_cast<int>(quiet_num("enum_params", "autotune_type", 0));  // MusicalScale, Chord, FixedSizeIntervals
+    const int root_note = static_cast<int>(quiet_num("enum_params", "autotune_musical_scale_root_note", 0));  // Note::Do = 0 ... Si = 11
+    const int transpose = static_cast<int>(quiet_num("int32_params", "autotune_root_note_halftones_transpose", 0));
+    constexpr int kLa = 9;  // include/midi.h:10-23
+    if (type == 0) {
+      static const double scales[3][8] = {{0, 2, 4, 5, 7, 9, 11, 12}, {0, 2, 3, 5, 7, 8, 10, 12}, {0, 2, 3, 5, 7, 8, 11, 12}};  // autotune.cpp:142-175
+      const int mode = static_cast<int>(quiet_num("enum_params", "autotune_musical_scale_mode", 0));
+      if (mode < 0 || mode > 2) throw std::runtime_error("bad autotune_musical_scale_mode");
+      o.autotune = CA_AUTOTUNE_SCALE;
+      d.table.assign(scales[mode], scales[mode] + 8);
+      o.scale_root_pitch = 69. + transpose + (root_note - kLa);  // A_pitch + transpose + half_tones_distance(La, root), :1862-1865
+    } else if (type == 1) {
+      int offset = root_note;  // half_tones_distance(Do, root) is never negative
+      offset += transpose;
+      const double root_pitch = 69. + (0 - kLa) + 12 + offset;  // C_pitch + offset, :1775-1777
+      const uint64_t chord = static_cast<uint64_t>(quiet_num("uint64_params", "autotune_bit_chord", 0b10010001));
+      const int freqs = static_cast<int>(quiet_num("enum_params", "autotune_chord_frequencies", 1));  // SingleFreq, Harmonics, OctavePeriodic
+      if (freqs == 0 || freqs == 2) {
+        const int lo = freqs == 0 ? 0 : -5, hi = freqs == 0 ? 0 : 5;
+        for (int octave = lo; octave <= hi; ++octave)
+          for (int i = 0; i < 64; ++i)
+            if ((chord >> i) & 1) d.table.push_back(root_pitch + i + 12 * octave);
+      } else if (freqs == 1) {
+        for (int h = 0; h < 36; ++h) {  // compute_harmonic_pitch_adds, include/midi.h:278-287
+          const double add = static_cast<int>(0.5 + 12. * std::log2(static_cast<float>(h + 1)));
+          for (int i = 0; i < 64; ++i)
+            if ((chord >> i) & 1) {
+              d.table.push_back(root_pitch + add + i);
+              d.table.push_back(root_pitch - add + i);
+            }
+        }
+      } else {
+        throw std::runtime_error("bad autotune_chord_frequencies");
+      }
+      std::sort(d.table.begin(), d.table.end());
+      o.autotune = CA_AUTOTUNE_TABLE;
+    } else if (type == 2) {
+      const double offset = root_note + transpose;
+      const int factor = static_cast<int>(quiet_num("int32_params", "autotune_factor", 2));
+      d.table.push_back(offset);
+      if (factor > 0) {
+        for (double val = offset - factor; val > 0.; val -= factor) d.table.push_back(val);
+        for (double val = offset + factor; val < 151.; val += factor) d.table.push_back(val);  // max_audible_midi_pitch, midi.h:134
+      }
+      std::sort(d.table.begin(), d.table.end());
+      o.autotune = CA_AUTOTUNE_TABLE;
+    } else {
+      throw std::runtime_error("bad autotune_type");
     }
-    const mini_json::Value* bp = preset->find("bool_params");
-    const mini_json::Value* ua = bp ? bp->find("use_autotune") : nullptr;
-    if (ua && ua->as_number() != 0) std::fprintf(stderr, "note: autotune is outside the B200 path and is ignored\n");
+    o.n_table = static_cast<int32_t>(d.table.size());
   }
   return d;
 }
@@ -143,13 +202,19 @@ Derived derive(const mini_json::Value* preset, int sample_rate) {
 void print_derived(const Job& job, const Derived& d, int sample_rate, size_t frames) {
   std::printf("{\"voice\": \"%s\", \"output\": \"%s\", \"sample_rate\": %d, \"frames\": %zu, \"window\": %d, \"hop\": %d, "
               "\"fft_length\": %d, \"min_volume\": %g, \"nearby_distance_tones\": %g, \"max_track_pitches\": %g, "
-              "\"stereo_spread\": %g, \"gain\": %g, \"env\": [%d, %d, %d, %d, %g], \"post\": \"%s\"}\n",
+              "\"stereo_spread\": %g, \"gain\": %g, \"env\": [%d, %d, %d, %d, %g], \"post\": \"%s\", "
+              "\"pitch_options\": {\"shift\": [%g, %g], \"harmonize\": [%g, %g], \"autotune\": %d, \"max_pitch\": %g, "
+              "\"tolerance\": %g, \"n_table\": %d, \"table_first\": %g, \"table_last\": %g, \"scale_root_pitch\": %g}}\n",
               job.voice_file.c_str(), job.output_file.c_str(), sample_rate, frames, d.window, d.hop, ca_fft_length_for(d.window, 1),
               d.prm.min_volume, d.prm.nearby_distance_tones, d.prm.max_track_pitches, d.prm.stereo_spread, d.prm.gain,
-              d.prm.env.attack, d.prm.env.hold, d.prm.env.decay, d.prm.env.release, d.prm.env.sustain, job.post.c_str());
+              d.prm.env.attack, d.prm.env.hold, d.prm.env.decay, d.prm.env.release, d.prm.env.sustain, job.post.c_str(),
+              d.prm.opts.shift_pre_autotune, d.prm.opts.shift_post_autotune, d.prm.opts.harmonize_pre_autotune,
+              d.prm.opts.harmonize_post_autotune, d.prm.opts.autotune, d.prm.opts.autotune_max_pitch,
+              d.prm.opts.autotune_tolerance_pitches, d.prm.opts.n_table, d.table.empty() ? 0. : d.table.front(),
+              d.table.empty() ? 0. : d.table.back(), d.prm.opts.scale_root_pitch);
 }
 
-bool same_params(const Derived& a, const Derived& b) { return std::memcmp(&a.prm, &b.prm, sizeof(a.prm)) == 0; }
+bool same_params(const Derived& a, const Derived& b) { return std::memcmp(&a.prm, &b.prm, sizeof(a.prm)) == 0 && a.table == b.table; }
 
 // the vocoder stage contributes when the voice is mixed in, or when there is a carrier and it (or its vocoded form) is audible
 bool vocoder_active(const Derived& d, bool has_carrier) {
@@ -240,7 +305,9 @@ int main(int argc, char** argv) {
       std::memset(x, 0, sizeof(float) * n * group.size());
       for (size_t g = 0; g < group.size(); ++g)
         std::memcpy(x + g * n, loaded[group[g]].voice.data(), sizeof(float) * loaded[group[g]].voice.size());
-      if (int rc = ca_resynth_roundtrip_host(ctx, &loaded[i].d.prm, x, static_cast<int64_t>(n), static_cast<int64_t>(group.size()), y, stats.data())) {
+      ca_roundtrip_params prm = loaded[i].d.prm;
+      prm.opts.table = loaded[i].d.table.empty() ? nullptr : loaded[i].d.table.data();
+      if (int rc = ca_resynth_roundtrip_host(ctx, &prm, x, static_cast<int64_t>(n), static_cast<int64_t>(group.size()), y, stats.data())) {
         std::fprintf(stderr, "ca_resynth_roundtrip_host failed (%d): %s\n", rc, ca_last_error(ctx));
         return 1;
       }
