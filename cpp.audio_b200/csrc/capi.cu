@@ -224,8 +224,10 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
   if (h.n_voices < 0 || h.n_partials < 1 || h.n_samples < 0 || !h.f0_hz || !h.volume || !h.partial_volume ||
       !h.partial_phase || !h.env || (h.n_env != 1 && h.n_env != h.n_voices))
     return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: bad descriptor");
+  int n_eased = 0;
   for (int64_t i = 0; i < h.n_env; ++i) {
     const ca_ahdsr& e = h.env[i];
+    n_eased += (e.attack_itp | e.decay_itp | e.release_itp) != 0;
     if (e.attack_itp < 0 || e.attack_itp >= CA_ITP_COUNT || e.decay_itp < 0 || e.decay_itp >= CA_ITP_COUNT ||
         e.release_itp < 0 || e.release_itp >= CA_ITP_COUNT)
       return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: envelope interpolation is not a ca_itp value");
@@ -274,7 +276,7 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
     rc = oscbank_plan(ctx, h.n_voices, h.n_partials);
     if (rc) return rc;
   }
-  rc = oscbank_render(ctx, &d, static_cast<float*>(ctx->d_scratch[7]), s);
+  rc = oscbank_render(ctx, &d, static_cast<float*>(ctx->d_scratch[7]), s, n_eased == 0 ? 0 : n_eased == h.n_env ? 2 : 1);
   if (rc) return rc;
   CA_CUDA_OK(ctx, cudaMemcpyAsync(h_out, ctx->d_scratch[7], sizeof(float) * n_out, cudaMemcpyDeviceToHost, s));
   CA_CUDA_OK(ctx, cudaStreamSynchronize(s));

@@ -115,7 +115,7 @@ int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float
 int irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, cudaStream_t stream);
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream);  // N <= 4096
 int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
-int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream);
+int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream, int eased = -1);
 int measure_fp32_peak(ca_ctx* ctx, double* tflops);
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);

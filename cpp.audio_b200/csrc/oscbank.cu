@@ -200,40 +200,54 @@ __device__ __forceinline__ float ease_in(int fam, float x) {
     default: return 1.f - sqrtf(fmaxf(0.f, 1.f - x * x));
   }
 }
-__device__ __noinline__ float ease_nonlinear(int type, float u) {
+__device__ __forceinline__ float ease(int type, float u) {
+  if (type == CA_ITP_LINEAR) return u;
   const int fam = (type - 1) / 3, mode = (type - 1) - 3 * fam;
   if (mode == 0) return ease_in(fam, u);
   if (mode == 1) return 1.f - ease_in(fam, 1.f - u);
   if (fam == 4) return 0.5f * (1.f - cospif(u));
   return u < 0.5f ? 0.5f * ease_in(fam, 2.f * u) : 1.f - 0.5f * ease_in(fam, 2.f - 2.f * u);
 }
-__device__ __forceinline__ float ease(int type, float u) { return type == CA_ITP_LINEAR ? u : ease_nonlinear(type, u); }
 
 // value of the envelope while the key is pressed, c = step counter (>=1 once audible), :960-1000
+template <bool EASED>
 __device__ __forceinline__ float env_pressed(int64_t c, const PartialParams& q, const VoiceParams& vp) {
   if (c < 1) return 0.f;
-  if (c <= q.attack) return c == q.attack ? 1.f : ease(vp.itp & 0xff, static_cast<float>(c) * q.inv_attack);
+  if (EASED) {
+    if (c <= q.attack) return c == q.attack ? 1.f : ease(vp.itp & 0xff, static_cast<float>(c) * q.inv_attack);
+    c -= q.attack;
+    if (c <= vp.hold) return 1.f;
+    c -= vp.hold;
+    if (c < q.decay) return 1.f + (vp.sustain - 1.f) * ease((vp.itp >> 8) & 0xff, static_cast<float>(c) * q.inv_decay);
+    return vp.sustain;
+  }
+  if (c <= q.attack) return static_cast<float>(c) * q.inv_attack;
   c -= q.attack;
   if (c <= vp.hold) return 1.f;
   c -= vp.hold;
-  if (c < q.decay) return 1.f + (vp.sustain - 1.f) * ease((vp.itp >> 8) & 0xff, static_cast<float>(c) * q.inv_decay);
+  if (c <= q.decay) return 1.f + (vp.sustain - 1.f) * (static_cast<float>(c) * q.inv_decay);
   return vp.sustain;
 }
 
-__device__ __forceinline__ float env_value(int64_t n, const PartialParams& q, const VoiceParams& vp) {
+template <bool EASED>
+__device__ __forceinline__ float env_value_t(int64_t n, const PartialParams& q, const VoiceParams& vp) {
   const int64_t rel = vp.release_at;
   if (rel >= 0 && n >= rel) {
     const int64_t crel = rel - vp.key_delay;  // counter when onKeyReleased(0) is called, :769-781
     if (crel <= 0) return 0.f;
     const int64_t j = n - rel + 1;
     if (j >= q.release) return 0.f;
-    const float top = env_pressed(crel, q, vp);
-    return top - top * ease((vp.itp >> 16) & 0xff, static_cast<float>(j) * q.inv_release);  // :733-737
+    const float top = env_pressed<EASED>(crel, q, vp);
+    const float u = static_cast<float>(j) * q.inv_release;
+    return top - top * (EASED ? ease((vp.itp >> 16) & 0xff, u) : u);  // :733-737
   }
-  return env_pressed(n + 1 - vp.key_delay, q, vp);
+  return env_pressed<EASED>(n + 1 - vp.key_delay, q, vp);
 }
 
-template <int WARPS>
+// EASED = false renders the voices whose three envelope phases are LINEAR (rt.resynth, every benchmark configuration) with the
+// code the kernel had before easings existed; EASED = true renders the other voices (and only those) with the easing switch
+// inlined in the transition chunks. Each launch skips the voices of the other kind, so a render is the sum of the two.
+template <int WARPS, bool EASED>
 __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_constant__ OscArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PartialParams* sp = reinterpret_cast<PartialParams*>(smem_raw);                 // [ppad]
@@ -267,7 +281,10 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
 
   const int64_t v_begin = static_cast<int64_t>(blockIdx.y) * a.voices_per_group;
   const int64_t v_end = min(a.n_voices, v_begin + a.voices_per_group);
+  bool any_voice = false;
   for (int64_t v = v_begin; v < v_end; ++v) {
+    if ((a.voices[v].itp != 0) != EASED) continue;  // uniform over the CTA
+    any_voice = true;
     __syncthreads();
     // ---- per-voice tables ----
     if (threadIdx.x == 0) {
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
           for (int p = 0; p < kNP; ++p) {
             const PartialParams& q = sp[p0 + p];
             float e = cval[p];
-            if (k < kend[p]) e = env_value(n, q, vp);
+            if (k < kend[p]) e = env_value_t<EASED>(n, q, vp);
             acc = fmaf(z[p].y, e, acc);
             z[p] = cmul(z[p], make_float2(q.rot_re, q.rot_im));
           }
@@ -452,7 +469,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
     __syncwarp();
   }
 
-  if (a.mix != CA_MIX_NONE && has_chunk) {
+  if (a.mix != CA_MIX_NONE && has_chunk && any_voice) {
     float* o = a.out + l0 * n_out;
     const int64_t lim = (min(l0 + kChunk, a.n_samples) - l0) * n_out;
     for (int i = lane; i < lim; i += 32) atomicAdd(o + i, bus[i]);
@@ -497,7 +514,10 @@ void oscbank_release(ca_ctx* ctx) {
   ctx->osc_max_partials = 0;
 }
 
-int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream) {
+// eased: what the caller knows about the envelopes of this call. 0: every phase of every envelope is LINEAR (only the LINEAR
+// pass is launched); 2: every envelope has an eased phase (only the eased pass); 1: both kinds; -1: unknown, the envelopes live
+// in device memory (both passes are launched, each skips the voices of the other kind).
+int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream, int eased) {
   if (!desc || !d_out) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render: null argument");
   const ca_oscbank_desc& d = *desc;
   if (d.n_voices < 0 || d.n_partials < 1 || d.n_samples < 0 || d.first_sample < 0 || d.sample_rate <= 0 || !d.f0_hz || !d.volume ||
@@ -532,17 +552,22 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
     constexpr int WARPS = 8;
     a.voices_per_group = 1;
     const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk);
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     dim3 grid(static_cast<unsigned>((a.n_chunks + WARPS - 1) / WARPS), static_cast<unsigned>(d.n_voices));
     if (d.n_voices > 65535) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_oscbank_render: more than 65535 voices per call");
-    oscbank_kernel<WARPS><<<grid, WARPS * 32, smem, stream>>>(a);
+    if (eased != 2) oscbank_kernel<WARPS, false><<<grid, WARPS * 32, smem, stream>>>(a);
+    if (eased != 0) oscbank_kernel<WARPS, true><<<grid, WARPS * 32, smem, stream>>>(a);
   } else {
     constexpr int WARPS = 4;
     const int n_out = d.mix == CA_MIX_STEREO ? 2 : 1;
     CA_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(float) * d.n_samples * n_out, stream));
     const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk * 3);
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     const int64_t tiles = (a.n_chunks + WARPS - 1) / WARPS;
     // enough voice groups to fill the GPU a few times over, few enough that the final atomics stay negligible
@@ -552,10 +577,11 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
     a.voices_per_group = static_cast<int32_t>((d.n_voices + groups - 1) / groups);
     groups = (d.n_voices + a.voices_per_group - 1) / a.voices_per_group;
     dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(groups));
-    oscbank_kernel<WARPS><<<grid, WARPS * 32, smem, stream>>>(a);
+    if (eased != 2) oscbank_kernel<WARPS, false><<<grid, WARPS * 32, smem, stream>>>(a);
+    if (eased != 0) oscbank_kernel<WARPS, true><<<grid, WARPS * 32, smem, stream>>>(a);
   }
   CA_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += 1;
+  ctx->launches += eased == -1 ? 2 : 1;
   return CA_OK;
 }
 

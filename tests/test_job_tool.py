@@ -188,3 +188,35 @@ def test_job_with_carrier_adds_the_vocoder_mix(tool, tmp_path, pkg, ctx, wl):
     want = ref[0, :y.shape[0]] + mix[0, :y.shape[0], None]
     assert np.abs(mix).max() > 0.02
     assert np.array_equal(y, want.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_job_with_autotune_preset_equals_the_library_call(tool, tmp_path, pkg, ctx, wl):
+    """use_autotune + chord (octave periodic, C major triad) + a fifth harmonised after autotune: the tool builds the same
+    ca_pitch_options as pitch_options() with the allowed pitches of mkAutotuneFunction (rt.resynth.lib.cpp:1767-1800)."""
+    sr = 48000
+    x = wl.c4_streams(1, 1.0)[0]
+    write_wav(tmp_path / "voice.wav", x, sr, "f32")
+    p = preset(window_size_seconds=4096 / sr + 1e-6, window_center_stride_seconds=256 / sr, autotune_tolerance_pitches=1.5,
+               pitch_harmonize_post_autotune=7.0, pitch_shift_pre_autotune=-0.25)
+    p["bool_params"]["use_autotune"] = True
+    p["enum_params"].update(autotune_type=1, autotune_chord_frequencies=2, autotune_musical_scale_root_note=0)
+    p["int32_params"].update(autotune_max_pitch=100)
+    p["uint64_params"].update(autotune_bit_chord=0b10010001)
+    (tmp_path / "preset.json").write_text(json.dumps(p))
+    job = {"preset_file": str(tmp_path / "preset.json"), "input_voice_file": str(tmp_path / "voice.wav"), "input_carrier_file": "",
+           "output_file": str(tmp_path / "out.wav"), "post": "none"}
+    (tmp_path / "job.json").write_text(json.dumps(job))
+    r = run_tool(str(tmp_path / "job.json"))
+    assert r.returncode == 0, r.stderr
+    n = x.shape[0] + sr + 4096
+    xp = np.zeros((1, n), np.float32)
+    xp[0, :x.shape[0]] = x
+    allowed = np.sort(np.array([72.0 + i + 12 * o for o in range(-5, 6) for i in (0, 4, 7)]))
+    opts = pkg.pitch_options(shift_pre=-0.25, harmonize_post=7.0, allowed_pitches=allowed, max_pitch=100.0, tolerance=1.5)
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, opts=opts)
+    plain, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf)
+    y, _ = read_wav_f32(tmp_path / "out.wav")
+    assert np.abs(y).max() > 0.05
+    assert np.array_equal(y, ref[0, :y.shape[0]])
+    assert np.abs(ref - plain).max() > 0.05
