@@ -60,7 +60,8 @@ class OscBankDesc(C.Structure):
     _fields_ = [("n_voices", C.c_int64), ("n_partials", C.c_int32), ("n_samples", C.c_int64), ("sample_rate", C.c_int32),
                 ("f0_hz", C.c_void_p), ("volume", C.c_void_p), ("start_angle", C.c_void_p), ("key_delay", C.c_void_p),
                 ("release_at", C.c_void_p), ("partial_volume", C.c_void_p), ("partial_phase", C.c_void_p),
-                ("env", C.c_void_p), ("n_env", C.c_int64), ("pan", C.c_void_p), ("mix", C.c_int32), ("first_sample", C.c_int64)]
+                ("env", C.c_void_p), ("n_env", C.c_int64), ("pan", C.c_void_p), ("mix", C.c_int32), ("first_sample", C.c_int64),
+                ("env_kind", C.c_int32)]
 
 
 _lib = None

@@ -214,7 +214,12 @@ int ca_oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials) {
 
 int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
-  return oscbank_render(ctx, desc, d_out, static_cast<cudaStream_t>(stream));
+  int eased = -1;
+  if (desc) {
+    if (desc->env_kind < CA_ENV_UNKNOWN || desc->env_kind > CA_ENV_MIXED) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render: bad env_kind");
+    eased = desc->env_kind == CA_ENV_ALL_LINEAR ? 0 : desc->env_kind == CA_ENV_ALL_EASED ? 2 : desc->env_kind == CA_ENV_MIXED ? 1 : -1;
+  }
+  return oscbank_render(ctx, desc, d_out, static_cast<cudaStream_t>(stream), eased);
 }
 
 int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_out) {

@@ -581,7 +581,7 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
     if (eased != 0) oscbank_kernel<WARPS, true><<<grid, WARPS * 32, smem, stream>>>(a);
   }
   CA_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += eased == -1 ? 2 : 1;
+  ctx->launches += (eased == -1 || eased == 1) ? 2 : 1;
   return CA_OK;
 }
 

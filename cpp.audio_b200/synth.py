@@ -33,8 +33,10 @@ class SineBank:
 
     def render(self, n_samples: int, f0_hz: torch.Tensor, volume: torch.Tensor, partial_volume: torch.Tensor,
                partial_phase: torch.Tensor, env, start_angle=None, key_delay=None, release_at=None, pan=None,
-               mix: int = MIX_NONE, out: torch.Tensor | None = None, first_sample: int = 0) -> torch.Tensor:
-        """All tensors on the same CUDA device. env: one Ahdsr or a list of Ahdsr (one per voice)."""
+               mix: int = MIX_NONE, out: torch.Tensor | None = None, first_sample: int = 0,
+               env_kind: int | None = None) -> torch.Tensor:
+        """All tensors on the same CUDA device. env: one Ahdsr or a list of Ahdsr (one per voice). env_kind: ca_env_kind
+        override (0 = unknown: both the LINEAR and the eased pass are launched); by default it is worked out from `env`."""
         dev = f0_hz.device
         nv, npart = partial_volume.shape
         for t, dt in ((f0_hz, torch.float32), (volume, torch.float32), (partial_volume, torch.float32),
@@ -45,6 +47,9 @@ class SineBank:
         for e in envs:  # the descriptor's env block lives on the device: the library cannot check it there
             if not all(0 <= t < ITP_COUNT for t in (e.attack_itp, e.decay_itp, e.release_itp)):
                 raise ValueError("envelope interpolation is not a ca_itp value")
+        n_eased = sum((e.attack_itp | e.decay_itp | e.release_itp) != 0 for e in envs)
+        if env_kind is None:
+            env_kind = 1 if n_eased == 0 else 2 if n_eased == len(envs) else 3  # ca_env_kind: ALL_LINEAR / ALL_EASED / MIXED
         arr = (Ahdsr * len(envs))(*envs)
         env_host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         env_dev = env_host.to(dev)
@@ -58,7 +63,7 @@ class SineBank:
             out = torch.empty(shape, dtype=torch.float32, device=dev)
         d = OscBankDesc(nv, npart, n_samples, self.sample_rate, f0_hz.data_ptr(), volume.data_ptr(), _opt_ptr(start_angle),
                         _opt_ptr(key_delay), _opt_ptr(release_at), partial_volume.data_ptr(), partial_phase.data_ptr(),
-                        env_dev.data_ptr(), len(envs), _opt_ptr(pan), mix, first_sample)
+                        env_dev.data_ptr(), len(envs), _opt_ptr(pan), mix, first_sample, env_kind)
         self.ctx.check(lib().ca_oscbank_render(self.ctx.handle, C.byref(d), out.data_ptr(),
                                                torch.cuda.current_stream(dev).cuda_stream), "ca_oscbank_render")
         self._keep = (env_dev,)  # the render is asynchronous: keep the parameter block alive

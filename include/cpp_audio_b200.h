@@ -127,6 +127,10 @@ typedef struct ca_ahdsr { /* audioelement::AHDSR, include/audioelement.h:314-335
 } ca_ahdsr;
 
 enum ca_mix { CA_MIX_NONE = 0, CA_MIX_STEREO = 1, CA_MIX_MONO = 2 };
+/* What the caller knows about the *_itp fields of the envelopes of a render (they live in device memory for ca_oscbank_render).
+ * LINEAR and eased voices are rendered by two passes; a pass that has nothing to do still costs a launch (90 us on 1024
+ * voices x 10 s), so a caller that knows says so. A wrong promise leaves the voices of the other kind silent. */
+enum ca_env_kind { CA_ENV_UNKNOWN = 0, CA_ENV_ALL_LINEAR = 1, CA_ENV_ALL_EASED = 2, CA_ENV_MIXED = 3 };
 
 typedef struct ca_oscbank_desc {
   int64_t n_voices;
@@ -146,6 +150,7 @@ typedef struct ca_oscbank_desc {
   int32_t mix;                 /* ca_mix */
   int64_t first_sample;        /* render samples [first_sample, first_sample+n_samples) of the notes' timeline (block-wise or
                                   time-sharded rendering; phases and envelopes are closed-form in the sample index) */
+  int32_t env_kind;            /* ca_env_kind; 0 = unknown (always correct). ca_oscbank_render_host works it out itself */
 } ca_oscbank_desc;
 
 /* sizes scratch for up to max_voices x max_partials; the only allocating call of the synthesis path */

@@ -16,7 +16,7 @@ def gpu_render(pkg, ctx, b, n_samples, env, sr=48000, **kw):
     tk = {k: T(v) for k, v in kw.items() if k in ("start_angle", "key_delay", "release_at", "pan")}
     mix = kw.get("mix", 0)
     out = pkg.render_bank(ctx, n_samples, T(b["f0_hz"]), T(b["volume"]), T(b["partial_volume"]), T(b["partial_phase"]), env,
-                          sample_rate=sr, mix=mix, first_sample=kw.get("first_sample", 0), **tk)
+                          sample_rate=sr, mix=mix, first_sample=kw.get("first_sample", 0), env_kind=kw.get("env_kind"), **tk)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -105,6 +105,22 @@ def test_every_easing_family(pkg, orc, ctx, wl, family):
     ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n,
                              env=[orc_env(orc, e) for e in envs], release_at=rel)
     assert np.abs(out - ref).max() < TOL * 0.1
+
+
+@pytest.mark.parametrize("mix", [0, 1, 2])
+@pytest.mark.parametrize("env_kind", [None, 0])
+def test_linear_and_eased_voices_in_one_render(pkg, orc, ctx, wl, mix, env_kind):
+    # LINEAR and eased voices are rendered by two passes of the kernel (each skips the voices of the other kind); the mixed
+    # buses are sums of both. env_kind 0 = the caller does not say what the envelopes are (ca_env_kind).
+    b = wl.c3_bank(6, 12)
+    n = 7000
+    envs = [pkg.Ahdsr(500 + 50 * i, 5 * (i % 2), 0, 300, 2 * (i % 2), 900, 8 * (i % 2), 0.6) for i in range(6)]
+    rel = np.array([4000, 4500, -1, 300, 6000, 2500], np.int64)
+    pan = np.linspace(-1, 1, 6).astype(np.float32)
+    out = gpu_render(pkg, ctx, b, n, envs, release_at=rel, pan=pan, mix=mix, env_kind=env_kind)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n,
+                             env=[orc_env(orc, e) for e in envs], release_at=rel, pan=pan, mix=mix)
+    assert np.abs(out - ref).max() < TOL * 0.1 * (1 if mix == 0 else 6)
 
 
 def test_unknown_easing_is_rejected(pkg, ctx, wl):
