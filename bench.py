@@ -163,6 +163,9 @@ def cpu_analysis_rate(orc, wl, threads: int, streams: int, seconds: float):
     return streams * r["frames"] / dt, dt
 
 
+_RESULT_LINE: list = []  # the one line of stdout, printed by main() after the run
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -193,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _RESULT_LINE.append(json.dumps(line))
     return 0
 
 
@@ -482,7 +485,7 @@ def run_ours(args):
                 "outputs": "peak lists (bin, freq, dB, count); the spectrum stays on the device"},
         "gpu_launches": launches_timed, "clocks": clocks, "extra": dict(extra, final_gather_ms=gather_ms),
     }
-    print(json.dumps(line), flush=True)
+    _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -502,9 +505,20 @@ def main():
     ap.add_argument("--skip-roundtrip", action="store_true")
     ap.add_argument("--skip-rfft", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    # stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints
+    # its version banner there) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rc = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[-1], flush=True)
+    return rc
 
 
 if __name__ == "__main__":
