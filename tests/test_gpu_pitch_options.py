@@ -85,3 +85,20 @@ def test_bad_options_are_rejected(pkg, ctx):
         pkg.resynth_roundtrip(ctx, x, opts=pkg.pitch_options(scale=[0.0], scale_root_pitch=60.0))
     with pytest.raises(pkg.CaError):  # the round trip renders LINEAR envelopes only
         pkg.resynth_roundtrip(ctx, x, env=pkg.Ahdsr(100, 5, 0, 0, 0, 100, 0, 1.0))
+
+
+def test_full_length_streams_with_options(pkg, ctx, wl):
+    """BASELINE config 4 length (60 s per stream) with every optional stage on: the device and host forms of the pipeline
+    agree, a shift by an octave after harmonising by an octave doubles the notes, and a stream's result does not depend on
+    what it is batched with."""
+    x = wl.c4_streams(3, 60.0)
+    opts = pkg.pitch_options(shift_pre=-12.0, harmonize_post=12.0, scale=MAJOR, scale_root_pitch=57.0, max_pitch=151.0, tolerance=1.0)
+    dev, dstats = pkg.resynth_roundtrip(ctx, x, opts=opts)
+    host, hstats = pkg.resynth_roundtrip(ctx, x, opts=opts, host_threads=-1)
+    plain, pstats = pkg.resynth_roundtrip(ctx, x)
+    assert np.array_equal(dstats, hstats) and dstats[:, 1].max() == 0
+    assert np.abs(dev[:, :4095]).max() == 0.0 and np.abs(dev).max() > 0.1
+    assert np.abs(dev - host).max() < 1e-5
+    assert np.abs(dev - plain).max() > 0.05
+    alone, astats = pkg.resynth_roundtrip(ctx, x[1:2], opts=opts)
+    assert np.array_equal(astats[0], dstats[1]) and np.array_equal(alone[0], dev[1])
