@@ -15,7 +15,7 @@ struct ca_ctx {
   std::string last_error;
   cudaStream_t own_stream = nullptr;   // used by the *_host entry points
   cudaStream_t own_stream2 = nullptr;  // second lane of the copy/compute pipeline of ca_stft_analyze_host
-  cudaStream_t pipe_streams[4] = {nullptr, nullptr, nullptr, nullptr};  // stream-group lanes of the round trip (created on first use)
+  cudaStream_t pipe_streams[8] = {};  // stream-group lanes of the round trip / vocoder (created on first use)
 
   // analysis plan
   bool stft_planned = false;

@@ -271,7 +271,8 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   const int64_t guess = std::max<int64_t>(n_tiles * std::min(prm.max_channels, 48), n_streams * 8192);
   if (!rc && ctx->scratch_bytes[6] < sizeof(Segment) * static_cast<size_t>(guess)) rc = ensure_scratch(ctx, 6, sizeof(Segment) * guess);
   if (rc) return rc;
-  const int groups = static_cast<int>(std::min<int64_t>(4, n_streams));
+  static const int max_groups = [] { const char* e = getenv("CA_RT_GROUPS"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : v > 8 ? 8 : v; }();
+  const int groups = static_cast<int>(std::min<int64_t>(max_groups, n_streams));
   for (int g = 0; g < groups; ++g)
     if (!ctx->pipe_streams[g]) CA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_streams[g], cudaStreamNonBlocking));
   float* d_x = static_cast<float*>(ctx->d_scratch[0]);
