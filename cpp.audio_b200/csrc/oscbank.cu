@@ -14,7 +14,9 @@
 //   * every chunk is re-seeded from an EXACT phase: phases are 64-bit fixed-point turns (phase0 + (n+1)*inc mod 2^64),
 //     so fp32 never accumulates phase over the 480,000-sample note (the reference runs in double).
 //   * chunks that contain an envelope transition (attack, decay, release) take a general path: complex rotation per
-//     32 samples + the piecewise-linear envelope evaluated per sample.
+//     32 samples + the envelope evaluated per sample (piecewise linear, or eased: itp::interpolate with the ca_itp set).
+//   * the kernel is instantiated twice, for voices with LINEAR phases only and for voices with an eased phase; a render
+//     launches the pass(es) its envelopes need and each pass skips the voices of the other kind.
 //   * partial parameters are prepared once per render by a small kernel, in double where the reference is in double.
 #include <math.h>
 
