@@ -8,6 +8,22 @@
 
 using namespace ca;
 
+namespace {
+// every entry point that takes a ctx runs on the ctx's device whatever the calling thread's current device is, and
+// leaves the thread's current device as it found it
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const ca_ctx* ctx) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+
 extern "C" {
 
 const char* ca_version(void) { return "cpp.audio_b200 0.1 (sm_100a)"; }
@@ -83,16 +99,19 @@ int64_t ca_stft_num_frames(int64_t n_samples, int window, int hop) {
 
 int ca_rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return rfft_batched(ctx, d_in, n_fft, batch, d_out, static_cast<cudaStream_t>(stream));
 }
 
 int ca_irfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, float scale, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return irfft_batched(ctx, d_in, n_fft, batch, d_out, scale, static_cast<cudaStream_t>(stream));
 }
 
 int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batch, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   if (!h_in || !h_out || batch < 0 || n_fft < 2) return fail(ctx, CA_ERR_INVALID, "ca_rfft_batched_host: bad argument");
   const size_t in_bytes = sizeof(float) * static_cast<size_t>(batch) * n_fft;
   const size_t out_bytes = sizeof(float) * 2 * static_cast<size_t>(batch) * (n_fft / 2 + 1);
@@ -111,14 +130,16 @@ int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batc
 
 int ca_stft_plan(ca_ctx* ctx, const ca_stft_params* params) {
   if (!ctx) return CA_ERR_INVALID;
-  return stft_plan(ctx, params);
+  DeviceGuard guard(ctx);
+  return stft_plan(ctx, ctx->plan_user, params);
 }
 
 int ca_stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
                     float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
                     int32_t* d_peak_count, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
-  return stft_analyze(ctx, d_x, n_samples, n_streams, stream_stride, d_sqmag, sqmag_row_stride, d_peak_bin, d_peak_freq,
+  DeviceGuard guard(ctx);
+  return stft_analyze(ctx, ctx->plan_user, d_x, n_samples, n_streams, stream_stride, d_sqmag, sqmag_row_stride, d_peak_bin, d_peak_freq,
                       d_peak_db, d_peak_count, static_cast<cudaStream_t>(stream));
 }
 
@@ -126,18 +147,19 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
                          float* h_sqmag, int64_t sqmag_row_stride, int32_t* h_peak_bin, float* h_peak_freq,
                          float* h_peak_db, int32_t* h_peak_count) {
   if (!ctx) return CA_ERR_INVALID;
-  if (!ctx->stft_planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze_host: call ca_stft_plan first");
+  DeviceGuard guard(ctx);
+  if (!ctx->plan_user.planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze_host: call ca_stft_plan first");
   if (!h_x || n_streams < 0 || n_samples < 0 || stream_stride < n_samples)
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze_host: bad input shape");
   const bool any_peak = h_peak_bin || h_peak_freq || h_peak_db || h_peak_count;
   if (any_peak && !(h_peak_bin && h_peak_freq && h_peak_db && h_peak_count))
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze_host: peak outputs must be all null or all non-null");
-  const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
+  const int64_t frames = ca_stft_num_frames(n_samples, ctx->plan_user.prm.window, ctx->plan_user.prm.hop);
   const size_t rows = static_cast<size_t>(frames) * n_streams;
   if (rows == 0) return CA_OK;
   const size_t x_bytes = sizeof(float) * static_cast<size_t>(n_streams) * stream_stride;
   const size_t sq_bytes = h_sqmag ? sizeof(float) * rows * sqmag_row_stride : 0;
-  const size_t pk_bytes = any_peak ? 4 * rows * ctx->stft.max_peaks : 0;
+  const size_t pk_bytes = any_peak ? 4 * rows * ctx->plan_user.prm.max_peaks : 0;
   const size_t cnt_bytes = any_peak ? 4 * rows : 0;
   int rc = ensure_scratch(ctx, 0, x_bytes);
   if (!rc && sq_bytes) rc = ensure_scratch(ctx, 1, sq_bytes);
@@ -148,7 +170,7 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
   if (rc) return rc;
   // Copy/compute pipeline over two streams: the work is cut into chunks (groups of whole streams, or frame ranges of a
   // stream with their window-hop halo); chunk c+1's H2D overlaps chunk c's kernel and D2H (separate copy engines).
-  const int W = ctx->stft.window, hop = ctx->stft.hop, P = ctx->stft.max_peaks;
+  const int W = ctx->plan_user.prm.window, hop = ctx->plan_user.prm.hop, P = ctx->plan_user.prm.max_peaks;
   float* d_x = static_cast<float*>(ctx->d_scratch[0]);
   float* d_sq = h_sqmag ? static_cast<float*>(ctx->d_scratch[1]) : nullptr;
   int32_t* d_pb = any_peak ? static_cast<int32_t*>(ctx->d_scratch[2]) : nullptr;
@@ -177,13 +199,13 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
         const size_t off = static_cast<size_t>(s0) * stream_stride;
         const size_t n = static_cast<size_t>(ns - 1) * stream_stride + n_samples;
         CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x + off, h_x + off, sizeof(float) * n, cudaMemcpyHostToDevice, s));
-        rcc = stft_analyze(ctx, d_x + off, n_samples, ns, stream_stride, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
+        rcc = stft_analyze(ctx, ctx->plan_user, d_x + off, n_samples, ns, stream_stride, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
                            d_pb ? d_pb + row0 * P : nullptr, d_pf ? d_pf + row0 * P : nullptr, d_pd ? d_pd + row0 * P : nullptr,
                            d_pc ? d_pc + row0 : nullptr, s);
       } else {  // ns == 1: a frame range of stream s0
         const size_t off = static_cast<size_t>(s0) * stream_stride + a0;
         CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x + off, h_x + off, sizeof(float) * (a1 - a0), cudaMemcpyHostToDevice, s));
-        rcc = stft_analyze(ctx, d_x + off, a1 - a0, 1, a1 - a0, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
+        rcc = stft_analyze(ctx, ctx->plan_user, d_x + off, a1 - a0, 1, a1 - a0, d_sq ? d_sq + row0 * sqmag_row_stride : nullptr, sqmag_row_stride,
                            d_pb ? d_pb + row0 * P : nullptr, d_pf ? d_pf + row0 * P : nullptr, d_pd ? d_pd + row0 * P : nullptr,
                            d_pc ? d_pc + row0 : nullptr, s);
       }
@@ -209,11 +231,13 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
 
 int ca_oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return oscbank_plan(ctx, max_voices, max_partials);
 }
 
 int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   int eased = -1;
   if (desc) {
     if (desc->env_kind < CA_ENV_UNKNOWN || desc->env_kind > CA_ENV_MIXED) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render: bad env_kind");
@@ -224,6 +248,7 @@ int ca_oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, ca
 
 int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   if (!desc || !h_out) return fail(ctx, CA_ERR_INVALID, "ca_oscbank_render_host: null argument");
   const ca_oscbank_desc& h = *desc;
   if (h.n_voices < 0 || h.n_partials < 1 || h.n_samples < 0 || !h.f0_hz || !h.volume || !h.partial_volume ||
@@ -291,23 +316,26 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
 int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
                               int64_t n_streams, float* h_out, int64_t* h_stats) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
 }
 
 int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
                     int64_t n_samples, int64_t n_streams, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx);
   return vocoder_host(ctx, params, h_modulator, h_carrier, n_samples, n_streams, h_out);
 }
 
 int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return ramp_render_host(ctx, desc, h_out);
 }
 
 int ca_measure_fp32_peak(ca_ctx* ctx, double* tflops) {
   if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
   return measure_fp32_peak(ctx, tflops);
 }
 

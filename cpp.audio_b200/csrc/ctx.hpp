@@ -8,6 +8,22 @@
 
 #include "../../include/cpp_audio_b200.h"
 
+namespace ca {
+// one planned analysis: parameters, FFT length and the window table on the device
+struct StftPlan {
+  bool planned = false;
+  ca_stft_params prm{};
+  int n_fft = 0;
+  float* d_window = nullptr;  // [n_fft] window, zero padded, pre-scaled (see stft.cu)
+  float thr_sq = 0.f;
+  bool freq_as_offset = false;  // internal (round trip, FP32 A/B form): peak_freq receives the sub-bin offset
+  // FP64 form of the analysis (stft64.cu; the round trip's default): window [n_fft] in double, twiddles W_{n_fft}^k, k <= n_fft/2
+  double* d_window64 = nullptr;
+  double2* d_tw64 = nullptr;
+  int n64 = 0;
+};
+}  // namespace ca
+
 struct ca_ctx {
   int device = 0;
   int sm_count = 0;
@@ -17,15 +33,9 @@ struct ca_ctx {
   cudaStream_t own_stream2 = nullptr;  // second lane of the copy/compute pipeline of ca_stft_analyze_host
   cudaStream_t pipe_streams[8] = {};  // stream-group lanes of the round trip / vocoder (created on first use)
 
-  // analysis plan
-  bool stft_planned = false;
-  ca_stft_params stft{};
-  int n_fft = 0;
-  float* d_window = nullptr;  // [n_fft] window, zero padded, pre-scaled (see stft.cu)
-  float thr_sq = 0.f;
-  void* d_stft_work = nullptr;  // generic (non-4096) path: windowed frames + complex bins of one group of frames
-  size_t stft_work_bytes = 0;
-  bool stft_freq_as_offset = false;  // internal switch used by the round trip (see stft.cu)
+  // analysis plans: the caller's (ca_stft_plan) and the private ones of the round trip and the vocoder, so that a
+  // ca_resynth_roundtrip_host / ca_vocoder_host call never disturbs what ca_stft_analyze was planned for
+  ca::StftPlan plan_user, plan_rt, plan_voc;
 
   // generic FFT scratch (twiddle tables, four-step buffers)
   float2* d_fft_tw = nullptr;
@@ -107,8 +117,8 @@ inline int ensure_pinned(ca_ctx* ctx, int slot, size_t bytes) {
 }
 
 // entry points implemented per kernel family
-int stft_plan(ca_ctx* ctx, const ca_stft_params* p);
-int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+int stft_plan(ca_ctx* ctx, StftPlan& plan, const ca_stft_params* p);
+int stft_analyze(ca_ctx* ctx, const StftPlan& plan, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
                  float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
                  int32_t* d_peak_count, cudaStream_t stream);
 int rfft_batched(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream);
@@ -125,6 +135,11 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
 // fused window -> FFT -> |X|^2 -> peaks for n_fft = 1024, 2048, 8192, 16384, 32768 (rfftw.cu); CA_ERR_UNSUPPORTED otherwise
 int stft_fused_generic(ca_ctx* ctx, const StftArgs& a, int n_fft, bool vec2, cudaStream_t stream);
 void stft_release(ca_ctx* ctx);
+// FP64 form of the analysis, peaks only (stft64.cu): n_fft 1024 .. 16384. d_peak_off = sub-bin offset p, d_peak_db = dB, both double.
+int stft64_plan(ca_ctx* ctx, StftPlan& plan);
+bool stft64_supported(const StftPlan& plan);
+int stft64_peaks(ca_ctx* ctx, const StftPlan& plan, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+                 int32_t* d_peak_bin, double* d_peak_off, double* d_peak_db, int32_t* d_peak_count, cudaStream_t stream);
 void rfft_release(ca_ctx* ctx);
 void oscbank_release(ca_ctx* ctx);
 

@@ -29,18 +29,20 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kSegChunk = 8192;  // segments per allocation chunk (>= kMaxNotes)
 constexpr int kRing = 4;          // frames of tuned entries in flight
 
+template <class R>
 struct PrefixArgs {
   PitchParams p;
   const int32_t* peak_bin;   // [rows][P]
-  const float* peak_off;
-  const float* peak_db;
+  const R* peak_off;         // R = float (float32 analysis kernels) or double (stft64.cu)
+  const R* peak_db;
   const int32_t* peak_count; // [rows]
   Tuned* tuned;              // [rows][P]
   int32_t* tcount;           // [rows]
   int64_t rows;
 };
 
-__global__ void __launch_bounds__(128) pitch_prefix_kernel(const __grid_constant__ PrefixArgs a) {
+template <class R>
+__global__ void __launch_bounds__(128) pitch_prefix_kernel(const __grid_constant__ PrefixArgs<R> a) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= a.rows) return;
   const int P = a.p.P;
@@ -987,8 +989,8 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track2_kernel(const __grid_
 // Outputs (device): segments, per-tile [begin, end) into them, first output sample and length of every tile, stats.
 // `needed` receives the number of segments the allocator handed out; when it exceeds seg_capacity the tiles past the
 // capacity carry no segments and the caller re-runs with a larger buffer.
-int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const float* d_peak_off,
-                          const float* d_peak_db, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
+int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
+                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
                           int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters) {
@@ -997,8 +999,13 @@ int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, 
   const int64_t rows = n_streams * p.frames;
   if (rows == 0) return CA_OK;
   if (run_prefix) {
-    PrefixArgs pa{p, d_peak_bin, d_peak_off, d_peak_db, d_peak_count, d_tuned, d_tcount, rows};
-    pitch_prefix_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
+    if (peaks_f64) {
+      PrefixArgs<double> pa{p, d_peak_bin, static_cast<const double*>(d_peak_off), static_cast<const double*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows};
+      pitch_prefix_kernel<double><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
+    } else {
+      PrefixArgs<float> pa{p, d_peak_bin, static_cast<const float*>(d_peak_off), static_cast<const float*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows};
+      pitch_prefix_kernel<float><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
+    }
     CA_CUDA_OK(ctx, cudaGetLastError());
     ctx->launches += 1;
   }

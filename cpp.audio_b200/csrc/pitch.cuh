@@ -246,8 +246,9 @@ static_assert(sizeof(Tuned) == 32 && sizeof(PV) == 16, "a Tuned row holds two (p
 //   aggregation of peaks closer than nearby_distance_tones (interval diameter), volume-weighted pitch, summed volume,
 //   min_volume cut (source/rt.resynth.lib.algo.cpp:10-230); entries that land on the same pitch are merged
 //   (autotune_pitches with the identity transform); OPTS: shift, harmonize, autotune, shift, harmonize in between.
-template <bool OPTS>
-CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
+// R: float (peak lists of the float32 analysis kernels) or double (stft64.cu).
+template <bool OPTS, class R>
+CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, const R* peak_off, const R* peak_db, int cnt,
                                 Tuned* out) {
   int T = 0;
   bool open = false;
@@ -324,10 +325,11 @@ CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, c
   return T;
 }
 
-CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db, int cnt,
+template <class R>
+CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const R* peak_off, const R* peak_db, int cnt,
                               Tuned* out) {
-  return p.opt_active ? pitch_prefix_t<true>(p, peak_bin, peak_off, peak_db, cnt, out)
-                      : pitch_prefix_t<false>(p, peak_bin, peak_off, peak_db, cnt, out);
+  return p.opt_active ? pitch_prefix_t<true, R>(p, peak_bin, peak_off, peak_db, cnt, out)
+                      : pitch_prefix_t<false, R>(p, peak_bin, peak_off, peak_db, cnt, out);
 }
 
 struct Note {
@@ -491,8 +493,9 @@ CA_HD inline Segment emit_segment(const PitchParams& p, Note& n, int64_t n_k_til
 struct ca_ctx;
 namespace ca {
 // pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track_kernel, one warp per stream)
-int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const float* d_peak_off,
-                          const float* d_peak_db, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
+// d_peak_off / d_peak_db: float arrays, or double arrays when peaks_f64 is set (the FP64 analysis of stft64.cu)
+int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
+                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
                           int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters = true);

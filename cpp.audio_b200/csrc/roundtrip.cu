@@ -55,7 +55,8 @@ struct StreamResult {
 
 // The host form of the pipeline (A/B against the device kernels of pitch.cu; host_threads != 0 selects it).
 // peak_stride: entries per frame in the (compacted) peak arrays
-void run_stream(const PitchParams& p, const int32_t* peak_bin, const float* peak_off, const float* peak_db,
+template <class R>
+void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off, const R* peak_db,
                 const int32_t* peak_count, StreamResult& res) {
   const int P = p.P;
   std::vector<Note> notes;       // sounding notes (tracked or releasing)
@@ -167,7 +168,7 @@ int device_pitch_params(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n_s
 // but the audio and 16 bytes of counters crosses PCIe, and the host does no per-frame work.
 template <class Lap>
 int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n_samples, int64_t n_streams, int64_t frames,
-                          float* h_out, int64_t* h_stats, bool timing, Lap&& lap) {
+                          float* h_out, int64_t* h_stats, bool timing, bool use64, Lap&& lap) {
   cudaStream_t st = ctx->own_stream;
   const int P = prm.stft.max_peaks;
   PitchParams pp;
@@ -196,8 +197,7 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
   int64_t* h_misc = static_cast<int64_t*>(ctx->h_pinned[0]);
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int64_t capacity = static_cast<int64_t>(ctx->scratch_bytes[6] / sizeof(Segment));
-    rc = pitch_pipeline_device(ctx, pp, n_streams, static_cast<const int32_t*>(ctx->d_scratch[2]),
-                               static_cast<const float*>(ctx->d_scratch[3]), static_cast<const float*>(ctx->d_scratch[4]),
+    rc = pitch_pipeline_device(ctx, pp, n_streams, static_cast<const int32_t*>(ctx->d_scratch[2]), ctx->d_scratch[3], ctx->d_scratch[4], use64,
                                static_cast<const int32_t*>(ctx->d_scratch[5]), static_cast<Tuned*>(ctx->d_scratch[8]),
                                static_cast<int32_t*>(ctx->d_scratch[9]), static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps,
                                d_begin, d_end, d_s0, d_len, d_stats, d_counter, d_overflow, attempt == 0, st);
@@ -255,7 +255,7 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
 // own CUDA stream, so the copies of one group overlap the (latency-bound) tracking kernel of the others. Returns
 // CA_OK with *overflowed = true when the segment buffer was too small (the caller grows it and takes the sequential path).
 int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, const float* h_x, int64_t n_samples, int64_t n_streams,
-                               int64_t frames, float* h_out, int64_t* h_stats, bool* overflowed, int64_t* needed) {
+                               int64_t frames, float* h_out, int64_t* h_stats, bool use64, bool* overflowed, int64_t* needed) {
   const int P = prm.stft.max_peaks;
   PitchParams pp;
   if (int prc = device_pitch_params(ctx, prm, n_samples, frames, P, &pp)) return prc;
@@ -277,8 +277,9 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
     if (!ctx->pipe_streams[g]) CA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_streams[g], cudaStreamNonBlocking));
   float* d_x = static_cast<float*>(ctx->d_scratch[0]);
   int32_t* d_pbin = static_cast<int32_t*>(ctx->d_scratch[2]);
-  float* d_poff = static_cast<float*>(ctx->d_scratch[3]);
-  float* d_pdb = static_cast<float*>(ctx->d_scratch[4]);
+  char* d_poff = static_cast<char*>(ctx->d_scratch[3]);  // float or double entries (use64)
+  char* d_pdb = static_cast<char*>(ctx->d_scratch[4]);
+  const size_t esz = use64 ? sizeof(double) : sizeof(float);
   int32_t* d_pcnt = static_cast<int32_t*>(ctx->d_scratch[5]);
   Tuned* d_tuned = static_cast<Tuned*>(ctx->d_scratch[8]);
   int32_t* d_tcount = static_cast<int32_t*>(ctx->d_scratch[9]);
@@ -298,7 +299,6 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, 16, s0));
   CA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   CA_CUDA_OK(ctx, cudaEventRecord(ready, s0));
-  ctx->stft_freq_as_offset = true;
   for (int g = 0; g < groups && !rc; ++g) {
     cudaStream_t sg = ctx->pipe_streams[g];
     const int64_t a0 = n_streams * g / groups, a1 = n_streams * (g + 1) / groups, ns = a1 - a0;
@@ -306,9 +306,14 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
     const int64_t t0 = a0 * tps, nt = ns * tps;
     if (g > 0) cudaStreamWaitEvent(sg, ready, 0);
     cudaMemcpyAsync(d_x + x0, h_x + x0, sizeof(float) * ns * n_samples, cudaMemcpyHostToDevice, sg);
-    rc = stft_analyze(ctx, d_x + x0, n_samples, ns, n_samples, nullptr, 0, d_pbin + r0 * P, d_poff + r0 * P, d_pdb + r0 * P, d_pcnt + r0, sg);
+    if (use64)
+      rc = stft64_peaks(ctx, ctx->plan_rt, d_x + x0, n_samples, ns, n_samples, d_pbin + r0 * P, reinterpret_cast<double*>(d_poff + r0 * P * esz),
+                        reinterpret_cast<double*>(d_pdb + r0 * P * esz), d_pcnt + r0, sg);
+    else
+      rc = stft_analyze(ctx, ctx->plan_rt, d_x + x0, n_samples, ns, n_samples, nullptr, 0, d_pbin + r0 * P, reinterpret_cast<float*>(d_poff + r0 * P * esz),
+                        reinterpret_cast<float*>(d_pdb + r0 * P * esz), d_pcnt + r0, sg);
     if (rc) break;
-    rc = pitch_pipeline_device(ctx, pp, ns, d_pbin + r0 * P, d_poff + r0 * P, d_pdb + r0 * P, d_pcnt + r0, d_tuned + r0 * P, d_tcount + r0,
+    rc = pitch_pipeline_device(ctx, pp, ns, d_pbin + r0 * P, d_poff + r0 * P * esz, d_pdb + r0 * P * esz, use64, d_pcnt + r0, d_tuned + r0 * P, d_tcount + r0,
                                static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps, d_begin + t0, d_end + t0, d_s0 + t0, d_len + t0,
                                d_stats + 2 * a0, d_counter, d_overflow, true, sg, false);
     if (rc) break;
@@ -319,7 +324,6 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
     ctx->launches += 1;
     cudaMemcpyAsync(h_out + 2 * x0, out_g, sizeof(float) * 2 * ns * n_samples, cudaMemcpyDeviceToHost, sg);
   }
-  ctx->stft_freq_as_offset = false;
   cudaError_t err = cudaGetLastError();
   for (int g = 0; g < groups; ++g) {
     const cudaError_t e = cudaStreamSynchronize(ctx->pipe_streams[g]);
@@ -359,8 +363,19 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
         if (!(o.table[i - 1] <= o.table[i]))
           return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: opts.table must be ascending");
   }
-  int rc = stft_plan(ctx, &prm.stft);
+  int rc = stft_plan(ctx, ctx->plan_rt, &prm.stft);
   if (rc) return rc;
+  ctx->plan_rt.freq_as_offset = true;  // float32 form: sub-bin offsets instead of Hz, so that k + p is formed in double
+  // The peaks come from the FP64 form of the analysis (stft64.cu: the reference analyses in double and the resynthesised
+  // phase integrates the peak frequencies); CA_RT_F32_ANALYSIS=1 selects the float32 kernels for A/B, and they also serve the
+  // shapes the FP64 kernel does not take (32768-point frames, odd hops).
+  static const bool env_f32 = getenv("CA_RT_F32_ANALYSIS") != nullptr;
+  const bool use64 = !env_f32 && stft64_supported(ctx->plan_rt) && n_samples % 2 == 0;
+  if (use64) {
+    rc = stft64_plan(ctx, ctx->plan_rt);
+    if (rc) return rc;
+  }
+  const size_t esz = use64 ? sizeof(double) : sizeof(float);
   const int W = prm.stft.window, hop = prm.stft.hop, P = prm.stft.max_peaks;
   const int64_t frames = ca_stft_num_frames(n_samples, W, hop);
   const size_t total = static_cast<size_t>(n_streams) * n_samples;
@@ -386,7 +401,8 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   const size_t out_bytes = sizeof(float) * 2 * total;
   rc = ensure_scratch(ctx, 0, sizeof(float) * total);
   if (!rc) rc = ensure_scratch(ctx, 7, out_bytes);
-  for (int i = 2; i <= 4 && !rc; ++i) rc = ensure_scratch(ctx, i, std::max<size_t>(16, sizeof(float) * rows * P));
+  rc = rc ? rc : ensure_scratch(ctx, 2, std::max<size_t>(16, sizeof(int32_t) * rows * P));
+  for (int i = 3; i <= 4 && !rc; ++i) rc = ensure_scratch(ctx, i, std::max<size_t>(16, esz * rows * P));
   if (!rc) rc = ensure_scratch(ctx, 5, std::max<size_t>(16, sizeof(int32_t) * rows));
   if (!rc) rc = ensure_pinned(ctx, 0, std::max<size_t>(16, sizeof(int32_t) * rows));
   if (rc) return rc;
@@ -394,7 +410,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (rows && !host_pitch && !timing && !env_sequential && n_streams >= 2) {
     bool overflowed = false;
     int64_t needed = 0;
-    rc = roundtrip_device_pipelined(ctx, prm, h_x, n_samples, n_streams, frames, h_out, h_stats, &overflowed, &needed);
+    rc = roundtrip_device_pipelined(ctx, prm, h_x, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed);
     if (rc || !overflowed) return rc;
     rc = ensure_scratch(ctx, 6, sizeof(Segment) * static_cast<size_t>(needed));  // rare: redo in one group with the exact size
     if (rc) return rc;
@@ -404,18 +420,21 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (rows) {
     float* d_x = static_cast<float*>(ctx->d_scratch[0]);
     CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x, h_x, sizeof(float) * total, cudaMemcpyHostToDevice, st));
-    ctx->stft_freq_as_offset = true;
-    rc = stft_analyze(ctx, d_x, n_samples, n_streams, n_samples, nullptr, 0, static_cast<int32_t*>(ctx->d_scratch[2]),
-                      static_cast<float*>(ctx->d_scratch[3]), static_cast<float*>(ctx->d_scratch[4]),
-                      static_cast<int32_t*>(ctx->d_scratch[5]), st);
-    ctx->stft_freq_as_offset = false;
+    if (use64)
+      rc = stft64_peaks(ctx, ctx->plan_rt, d_x, n_samples, n_streams, n_samples, static_cast<int32_t*>(ctx->d_scratch[2]),
+                        static_cast<double*>(ctx->d_scratch[3]), static_cast<double*>(ctx->d_scratch[4]),
+                        static_cast<int32_t*>(ctx->d_scratch[5]), st);
+    else
+      rc = stft_analyze(ctx, ctx->plan_rt, d_x, n_samples, n_streams, n_samples, nullptr, 0, static_cast<int32_t*>(ctx->d_scratch[2]),
+                        static_cast<float*>(ctx->d_scratch[3]), static_cast<float*>(ctx->d_scratch[4]),
+                        static_cast<int32_t*>(ctx->d_scratch[5]), st);
     if (rc) return rc;
     if (!host_pitch) {
       if (timing) {
         CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
         lap("analysis (H2D, K2)");
       }
-      return roundtrip_device_tail(ctx, prm, n_samples, n_streams, frames, h_out, h_stats, timing, lap);
+      return roundtrip_device_tail(ctx, prm, n_samples, n_streams, frames, h_out, h_stats, timing, use64, lap);
     }
     CA_CUDA_OK(ctx, cudaMemcpyAsync(h_cnt, ctx->d_scratch[5], sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
     CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
@@ -423,17 +442,16 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
     cmax = std::min(cmax, P);
   }
   const int PS = std::max(cmax, 1);  // compacted entries per frame
-  for (int i = 1; i <= 3 && !rc; ++i) rc = ensure_pinned(ctx, i, std::max<size_t>(16, sizeof(float) * rows * PS));
+  for (int i = 1; i <= 3 && !rc; ++i) rc = ensure_pinned(ctx, i, std::max<size_t>(16, (i == 1 ? sizeof(int32_t) : esz) * rows * PS));
   if (rc) return rc;
   if (rows && cmax > 0)
-    for (int i = 0; i < 3; ++i)
-      CA_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_pinned[1 + i], sizeof(float) * PS, ctx->d_scratch[2 + i], sizeof(float) * P,
-                                        sizeof(float) * PS, rows, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < 3; ++i) {
+      const size_t e = i == 0 ? sizeof(int32_t) : esz;
+      CA_CUDA_OK(ctx, cudaMemcpy2DAsync(ctx->h_pinned[1 + i], e * PS, ctx->d_scratch[2 + i], e * P, e * PS, rows, cudaMemcpyDeviceToHost, st));
+    }
   CA_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_scratch[7], 0, out_bytes, st));  // samples before the first frame are silent
   CA_CUDA_OK(ctx, cudaStreamSynchronize(st));
   const int32_t* pbin = static_cast<const int32_t*>(ctx->h_pinned[1]);
-  const float* poff = static_cast<const float*>(ctx->h_pinned[2]);
-  const float* pdb = static_cast<const float*>(ctx->h_pinned[3]);
   lap("analysis (H2D, K2, D2H peaks)");
 
   // ---- 2. pitch pipeline on host threads, one stream at a time per thread ----
@@ -450,7 +468,13 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
     for (auto& th : pool) th.join();
   };
   parallel([&](int64_t s) {
-    run_stream(pp, pbin + s * frames * PS, poff + s * frames * PS, pdb + s * frames * PS, h_cnt + s * frames, results[s]);
+    const size_t o = static_cast<size_t>(s) * frames * PS;
+    if (use64)
+      run_stream(pp, pbin + o, static_cast<const double*>(ctx->h_pinned[2]) + o, static_cast<const double*>(ctx->h_pinned[3]) + o,
+                 h_cnt + s * frames, results[s]);
+    else
+      run_stream(pp, pbin + o, static_cast<const float*>(ctx->h_pinned[2]) + o, static_cast<const float*>(ctx->h_pinned[3]) + o,
+                 h_cnt + s * frames, results[s]);
   });
   lap("pitch pipeline (host)");
 

@@ -476,94 +476,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __gri
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Generic path for FFT lengths other than 4096 (1024 .. 32768; the reference default window of 0.1814 s is 8192 points
-// at 44.1 kHz): frames are windowed into a work buffer, transformed by K1 (rfft.cu) and a third kernel forms |X|^2 and
-// extracts the peaks. Three passes over HBM instead of one — correct for every size, tuned for none.
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) window_frames_kernel(const float* __restrict__ x, const float* __restrict__ win,
-                                                            float* __restrict__ out, int64_t stream_stride, int frames_per_stream,
-                                                            int hop, int window, int n_fft, int64_t f_begin, int64_t n_frames) {
-  // grid.x: frames of this group, threads stride over the frame
-  const int64_t f = f_begin + blockIdx.x;
-  if (blockIdx.x >= n_frames) return;
-  const int64_t stream = f / frames_per_stream;
-  const int64_t fr = f - stream * frames_per_stream;
-  const float* xs = x + stream * stream_stride + fr * hop;
-  float* o = out + static_cast<int64_t>(blockIdx.x) * n_fft;
-  for (int n = threadIdx.x; n < n_fft; n += 256) o[n] = n < window ? __ldg(xs + n) * __ldg(win + n) : 0.f;
-}
-
-// one warp per frame: |X|^2 (scale folded into the window), HBM row, peaks as in the fused kernel
-__global__ void __launch_bounds__(128) sqmag_peaks_kernel(const float2* __restrict__ bins, int n_fft, int64_t f_begin,
-                                                          int64_t n_frames, const __grid_constant__ StftArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t local = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
-  if (local >= n_frames) return;
-  const int64_t f = f_begin + local;
-  const int half = n_fft / 2;
-  const float2* X = bins + local * (half + 1);
-  float* row = p.sqmag ? p.sqmag + f * p.sqmag_row_stride : nullptr;
-  if (row)
-    for (int k = lane; k <= half; k += 32) {
-      const float2 z = X[k];
-      row[k] = fmaf(z.x, z.x, z.y * z.y);
-    }
-  if (!p.peak_count) return;
-  auto sq = [&](int k) {
-    const float2 z = X[k];
-    return fmaf(z.x, z.x, z.y * z.y);
-  };
-  // lane owns bins [lane*B, lane*B + B), B = half/32; bins 1 .. half-1 are candidates
-  const int B = half / 32;
-  const int k0 = lane * B;
-  int cnt = 0;
-  {
-    float l = k0 > 0 ? sq(k0 - 1) : __int_as_float(0x7f800000);
-    float c = sq(k0);
-    for (int j = 0; j < B; ++j) {
-      const float r = sq(k0 + j + 1);
-      cnt += (c > fmaxf(fmaxf(l, r), p.thr_below)) ? 1 : 0;
-      l = c;
-      c = r;
-    }
-  }
-  int incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  int slot = incl - cnt;
-  if (lane == 0) p.peak_count[f] = total;
-  const int64_t out_base = f * static_cast<int64_t>(p.max_peaks);
-  float l = k0 > 0 ? sq(k0 - 1) : __int_as_float(0x7f800000);
-  float c = sq(k0);
-  for (int j = 0; j < B && slot < p.max_peaks; ++j) {
-    const float r = sq(k0 + j + 1);
-    if (c > fmaxf(fmaxf(l, r), p.thr_below)) {
-      const int k = k0 + j;
-      const float fl = 1e-37f;
-      const float sa = fmaxf(l, fl), sb = fmaxf(c, fl), sc = fmaxf(r, fl);
-      const float inv_b = __frcp_rn(sb);
-      const float la = __log2f(sa * inv_b), lc = __log2f(sc * inv_b);
-      const float num = la - lc, den = la + lc;
-      const float pp = den != 0.f ? 0.5f * __fdividef(num, den) : 0.f;
-      constexpr float kDbPerLog2 = 3.01029995663981195f;
-      p.peak_bin[out_base + slot] = k;
-      p.peak_freq[out_base + slot] = p.freq_as_offset ? pp : (static_cast<float>(k) + pp) * p.bin_to_hz;
-      p.peak_db[out_base + slot] = kDbPerLog2 * __log2f(sb) - 0.25f * (kDbPerLog2 * num) * pp;
-      ++slot;
-    }
-    l = c;
-    c = r;
-  }
-}
-
 }  // namespace
 
-int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
+int stft_plan(ca_ctx* ctx, StftPlan& plan, const ca_stft_params* p) {
   if (!p || p->window < 2 || (p->window & 1) || p->hop < 1 || p->max_peaks < 0 || p->sample_rate <= 0)
     return fail(ctx, CA_ERR_INVALID, "ca_stft_plan: window must be even and >= 2, hop >= 1");
   if (p->window_type != CA_WINDOW_RECTANGULAR && p->window_type != CA_WINDOW_GAUSSIAN)
@@ -588,40 +503,41 @@ int stft_plan(ca_ctx* ctx, const ca_stft_params* p) {
   const double norm = static_cast<double>(H / sum) * (n_fft == kN ? 0.5 : 1.0) / W;
   std::vector<float> full(n_fft, 0.f);
   for (int n = 0; n < W; ++n) full[n] = static_cast<float>((n < H ? hw[H - 1 - n] : hw[n - H]) * norm);
-  if (!ctx->d_window || ctx->n_fft != n_fft) {
-    if (ctx->d_window) cudaFree(ctx->d_window);
-    ctx->d_window = nullptr;
-    CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_window, sizeof(float) * n_fft));
+  plan.planned = false;
+  if (!plan.d_window || plan.n_fft != n_fft) {
+    if (plan.d_window) cudaFree(plan.d_window);
+    plan.d_window = nullptr;
+    CA_CUDA_OK(ctx, cudaMalloc(&plan.d_window, sizeof(float) * n_fft));
   }
-  CA_CUDA_OK(ctx, cudaMemcpy(ctx->d_window, full.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
-  ctx->n_fft = n_fft;
-  ctx->stft = *p;
-  ctx->thr_sq = isinf(p->min_db) && p->min_db < 0 ? 0.f : static_cast<float>(pow(10.0, p->min_db / 10.0));
-  ctx->stft_planned = true;
+  CA_CUDA_OK(ctx, cudaMemcpy(plan.d_window, full.data(), sizeof(float) * n_fft, cudaMemcpyHostToDevice));
+  plan.n_fft = n_fft;
+  plan.prm = *p;
+  plan.thr_sq = isinf(p->min_db) && p->min_db < 0 ? 0.f : static_cast<float>(pow(10.0, p->min_db / 10.0));
+  plan.planned = true;
   return CA_OK;
 }
 
 void stft_release(ca_ctx* ctx) {
-  if (ctx->d_stft_work) cudaFree(ctx->d_stft_work);
-  ctx->d_stft_work = nullptr;
-  ctx->stft_work_bytes = 0;
-  if (ctx->d_window) cudaFree(ctx->d_window);
-  ctx->d_window = nullptr;
-  ctx->stft_planned = false;
+  for (StftPlan* pl : {&ctx->plan_user, &ctx->plan_rt, &ctx->plan_voc}) {
+    if (pl->d_window) cudaFree(pl->d_window);
+    if (pl->d_window64) cudaFree(pl->d_window64);
+    if (pl->d_tw64) cudaFree(pl->d_tw64);
+    *pl = StftPlan{};
+  }
 }
 
-int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
+int stft_analyze(ca_ctx* ctx, const StftPlan& plan, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,
                  float* d_sqmag, int64_t sqmag_row_stride, int32_t* d_peak_bin, float* d_peak_freq, float* d_peak_db,
                  int32_t* d_peak_count, cudaStream_t stream) {
-  if (!ctx->stft_planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze: call ca_stft_plan first");
+  if (!plan.planned) return fail(ctx, CA_ERR_NOT_PLANNED, "ca_stft_analyze: call ca_stft_plan first");
   if (!d_x || n_streams < 0 || n_samples < 0 || stream_stride < n_samples)
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: bad input shape");
   const bool any_peak = d_peak_bin || d_peak_freq || d_peak_db || d_peak_count;
   if (any_peak && !(d_peak_bin && d_peak_freq && d_peak_db && d_peak_count))
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: peak outputs must be all null or all non-null");
-  if (d_sqmag && sqmag_row_stride < ctx->n_fft / 2 + 1)
+  if (d_sqmag && sqmag_row_stride < plan.n_fft / 2 + 1)
     return fail(ctx, CA_ERR_INVALID, "ca_stft_analyze: sqmag_row_stride < n_fft/2+1");
-  const int64_t frames = ca_stft_num_frames(n_samples, ctx->stft.window, ctx->stft.hop);
+  const int64_t frames = ca_stft_num_frames(n_samples, plan.prm.window, plan.prm.hop);
   const int64_t total = frames * n_streams;
   if (total == 0) return CA_OK;
   if (frames >= (1ll << 31) - (1 << 20) || n_streams >= (1ll << 31))
@@ -634,69 +550,40 @@ int stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_str
   a.frames_per_stream = frames;
   a.total_frames = total;
   a.n_streams = static_cast<int32_t>(n_streams);
-  a.hop = ctx->stft.hop;
-  a.window = ctx->stft.window;
-  a.win = ctx->d_window;
+  a.hop = plan.prm.hop;
+  a.window = plan.prm.window;
+  a.win = plan.d_window;
   a.sqmag = d_sqmag;
   a.sqmag_row_stride = sqmag_row_stride;
   a.peak_bin = d_peak_bin;
   a.peak_freq = d_peak_freq;
   a.peak_db = d_peak_db;
   a.peak_count = d_peak_count;
-  a.max_peaks = ctx->stft.max_peaks;
-  a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
-  a.bin_to_hz = static_cast<float>(static_cast<double>(ctx->stft.sample_rate) / ctx->n_fft);
-  if (ctx->n_fft != kN) {
-    a.max_peaks = ctx->stft.max_peaks;
-    a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
+  a.max_peaks = plan.prm.max_peaks;
+  a.thr_below = plan.thr_sq > 0.f ? nextafterf(plan.thr_sq, 0.f) : -1.f;
+  a.bin_to_hz = static_cast<float>(static_cast<double>(plan.prm.sample_rate) / plan.n_fft);
+  if (plan.n_fft != kN) {
+    a.max_peaks = plan.prm.max_peaks;
+    a.freq_as_offset = plan.freq_as_offset ? 1 : 0;
     {  // fused single-pass kernels for 1024, 2048, 8192, 16384, 32768 (rfftw.cu)
-      const bool v2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0);
-      static const bool force_3pass = getenv("CA_STFT_THREE_PASS") != nullptr;  // A/B against the three-pass path
-      const int rcf = force_3pass ? CA_ERR_UNSUPPORTED : stft_fused_generic(ctx, a, ctx->n_fft, v2, stream);
+      const bool v2 = (plan.prm.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0);
+      const int rcf = stft_fused_generic(ctx, a, plan.n_fft, v2, stream);
       if (rcf != CA_ERR_UNSUPPORTED) return rcf;
     }
-    // generic three-pass path, frames processed in groups that bound the work buffers to ~256 MiB each
-    const int n_fft = ctx->n_fft, half = n_fft / 2;
-    if (frames >= (1ll << 31)) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_analyze: too many frames per stream");
-    const int64_t group = std::max<int64_t>(1, std::min<int64_t>(total, (256ll << 20) / (sizeof(float) * n_fft)));
-    const size_t need = sizeof(float) * n_fft * group + sizeof(float2) * (half + 1) * group;
-    if (ctx->stft_work_bytes < need) {
-      if (ctx->d_stft_work) cudaFree(ctx->d_stft_work);
-      ctx->d_stft_work = nullptr;
-      ctx->stft_work_bytes = 0;
-      CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_stft_work, need));
-      ctx->stft_work_bytes = need;
-    }
-    float* wbuf = static_cast<float*>(ctx->d_stft_work);
-    float* bbuf = wbuf + static_cast<size_t>(n_fft) * group;
-    a.thr_below = ctx->thr_sq > 0.f ? nextafterf(ctx->thr_sq, 0.f) : -1.f;
-    a.max_peaks = ctx->stft.max_peaks;
-    a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
-    for (int64_t f0 = 0; f0 < total; f0 += group) {
-      const int64_t nf = std::min(group, total - f0);
-      window_frames_kernel<<<static_cast<unsigned>(nf), 256, 0, stream>>>(d_x, ctx->d_window, wbuf, stream_stride, static_cast<int>(frames),
-                                                                         ctx->stft.hop, ctx->stft.window, n_fft, f0, nf);
-      CA_CUDA_OK(ctx, cudaGetLastError());
-      int rc = rfft_batched(ctx, wbuf, n_fft, nf, bbuf, stream);
-      if (rc) return rc;
-      sqmag_peaks_kernel<<<static_cast<unsigned>((nf + 3) / 4), 128, 0, stream>>>(reinterpret_cast<const float2*>(bbuf), n_fft, f0, nf, a);
-      CA_CUDA_OK(ctx, cudaGetLastError());
-      ctx->launches += 2;
-    }
-    return CA_OK;
+    return fail(ctx, CA_ERR_UNSUPPORTED, "ca_stft_analyze: no kernel for this fft length");
   }
-  a.freq_as_offset = ctx->stft_freq_as_offset ? 1 : 0;
+  a.freq_as_offset = plan.freq_as_offset ? 1 : 0;
 
-  const bool vec2 = (ctx->stft.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
-                    (ctx->stft.window % 2 == 0);
-  const bool full = ctx->stft.window == kN;
+  const bool vec2 = (plan.prm.hop % 2 == 0) && (stream_stride % 2 == 0) && (reinterpret_cast<uintptr_t>(d_x) % 8 == 0) &&
+                    (plan.prm.window % 2 == 0);
+  const bool full = plan.prm.window == kN;
   // 12 warps x 1 CTA per SM: 12 x 16.5 KB exchange buffers + 16 KB window + tables = 224 KB of shared memory, 168 registers
   static const int warps_env = [] {
     const char* e = getenv("CA_STFT_WARPS");  // 4 = one warp per scheduler: the uncontended timeline (profiles/build_timeline.sh)
     return e ? atoi(e) : 12;
   }();
   // staged path: window 4096, hop a multiple of 128 samples, 16-byte aligned streams (see frame_stage_even_p)
-  bool bulk = full && ctx->stft.hop % 128 == 0 && stream_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d_x) % 16 == 0 &&
+  bool bulk = full && plan.prm.hop % 128 == 0 && stream_stride % 4 == 0 && reinterpret_cast<uintptr_t>(d_x) % 16 == 0 &&
               n_samples / 128 < (1ll << 31);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

@@ -174,7 +174,7 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
     sp.sample_rate = sr;
     sp.min_db = -INFINITY;
     sp.max_peaks = 1;
-    rc = stft_plan(ctx, &sp);
+    rc = stft_plan(ctx, ctx->plan_voc, &sp);
     if (rc) return rc;
   }
   CA_CUDA_OK(ctx, cudaStreamSynchronize(st));  // tables and window are in place before the stream groups start
@@ -195,7 +195,7 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
     cudaMemcpyAsync(d_xm + x0, h_modulator + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
     cudaMemcpyAsync(d_xc + x0, h_carrier + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
     if (nm) {  // modulator: |X|^2 of every frame, then the band amplitudes
-      rc = stft_analyze(ctx, d_xm + x0, n_samples, ns, n_samples, d_sq + m0 * row_stride, row_stride, nullptr, nullptr, nullptr, nullptr, sg);
+      rc = stft_analyze(ctx, ctx->plan_voc, d_xm + x0, n_samples, ns, n_samples, d_sq + m0 * row_stride, row_stride, nullptr, nullptr, nullptr, nullptr, sg);
       if (rc) break;
       band_amps_kernel<<<static_cast<unsigned>((nm + 3) / 4), 128, 0, sg>>>(d_sq + m0 * row_stride, row_stride, static_cast<int64_t>(nm),
                                                                            d_band_begin, nb, d_amps + m0 * nb);

@@ -173,12 +173,15 @@ def test_peaks_only_and_sqmag_only(pkg, orc, ctx, wl):
     assert np.abs(np.sqrt(b["sqmag"].reshape(ref["sqmag"].shape)) - np.sqrt(ref["sqmag"])).max() < TOL
 
 
-def test_full_c2_size_properties(pkg, ctx, wl):
-    """BASELINE config 2 at full size (60 s): size-independent properties instead of the oracle."""
+def test_full_c2_against_oracle(pkg, orc, ctx, wl):
+    """BASELINE config 2 at its full size (60 s, 11,235 frames) against the oracle: spectrum, peak bins, frequencies, dB;
+    then the size-independent properties of the signal."""
     x = wl.c2_signal(60.0)[None, :]
     res = run_gpu(pkg, ctx, x, 4096, 256)
+    ref = orc.stft_analyze(x, 4096, 256)
     F = 11235
-    assert res["peak_count"].shape[0] == F
+    assert ref["frames"] == F and res["peak_count"].shape[0] == F
+    compare(res, ref)
     assert (res["peak_count"] == 16).all()
     f = res["peak_freq"][:, :16]
     assert (np.diff(f, axis=1) > 0).all()  # ascending (invariant asserted at rt.resynth.lib.algo.cpp:14-21)
@@ -186,7 +189,7 @@ def test_full_c2_size_properties(pkg, ctx, wl):
     # stationarity: the spectrum of a periodic signal is the same in every frame
     mag = np.sqrt(res["sqmag"])
     assert np.abs(mag - mag[0:1]).max() < 1e-4  # residual = leakage between partials (-85 dB), phase dependent
-    # Parseval-style linearity check: scaling the input by 0.5 scales |X| by 0.5
+    # linearity: scaling the input by 0.5 scales |X| by 0.5
     res2 = run_gpu(pkg, ctx, 0.5 * x[:, :48000], 4096, 256, want_peaks=False)
     assert np.abs(np.sqrt(res2["sqmag"]) - 0.5 * mag[: res2["sqmag"].shape[0]]).max() < 1e-5
 
