@@ -42,6 +42,10 @@ elif what == "roundtrip":
     x = wl.tiled_streams(S, 60.0)
     for _ in range(3):
         pkg.resynth_roundtrip(ctx, x)
+elif what == "roundtrip_small":   # the FP64 analysis kernel (stft64) with its neighbours: 8 streams x 10 s
+    x = wl.tiled_streams(8, 10.0)
+    for _ in range(3):
+        pkg.resynth_roundtrip(ctx, x)
 elif what == "vocoder":
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     rng = np.random.default_rng(1)

@@ -19,6 +19,26 @@ want = {
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct2",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts", "sm__cycles_elapsed.avg": "cycles",
+    # cycles-active (not instruction-issue) view of the pipes, issue-slot and L1 wavefront utilisation
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "fma_pipe_cycles_active_pct",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active": "fmaheavy_cycles_active_pct",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active": "alu_pipe_cycles_active_pct",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_cycles_active_pct",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "smsp__inst_executed.avg.per_cycle_active": "ipc_per_scheduler",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_wavefronts_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active": "l1tex_throughput_pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct": "stall_barrier_pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct": "stall_short_scoreboard_pct",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct": "stall_long_scoreboard_pct",
+    "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct": "stall_math_pipe_pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct": "stall_mio_throttle_pct",
+    "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct": "stall_lg_throttle_pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct": "stall_wait_pct",
+    "smsp__warp_issue_stalled_not_selected_per_warp_active.pct": "stall_not_selected_pct",
 }
 out = []
 for r in rows[2:]:
