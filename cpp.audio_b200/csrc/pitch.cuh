@@ -346,7 +346,16 @@ struct Note {
   double top = 0;
   float gl = 1, gr = 1;
   bool tracked = true;   // still in played_pitches
+  int32_t chan = 0;      // channel of the voice pool (ImplCRTP channels, include/gen.crtp.h:221-233): lowest free index at note-on
 };
+
+// setPhase<SynchronizePhase::Yes> (include/gen.crtp.h:127-156, instantiated at source/rt.resynth.lib.cpp:201-210): a new note
+// takes over the oscillator phase of the first other RT-active channel, in channel order, whose angleIncrements() equals its
+// own. angleIncrements() (FreqCtrl_, include/audioelement.h:3117-3124) is the increment the channel's OSCILLATOR last
+// stepped with when that is non-zero -- the oscillator forgets nothing when a channel is reused (:2387-2388), so for a
+// channel keyed in this frame it is still the last increment of the channel's previous note -- and the glide's start
+// value (= the note's own increment) on a channel that never sounded.
+CA_HD inline double chan_angle_increments(double osc_ai, double ctrl_from) { return osc_ai != 0.0 ? osc_ai : ctrl_from; }
 
 CA_HD inline double env_pressed_value(const Note& n, int64_t c, float sustain) {
   if (c < 1) return 0.0;

@@ -61,6 +61,9 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
   const int P = p.P;
   std::vector<Note> notes;       // sounding notes (tracked or releasing)
   std::vector<int> played;       // indices into notes of tracked notes, sorted by pitch
+  // the voice pool's channels: which note sits on each (-1: free) and the increment its oscillator last stepped with
+  std::vector<int> chan_note(std::max(p.max_channels, 1), -1);
+  std::vector<double> chan_osc_ai(std::max(p.max_channels, 1), 0.0);
   std::vector<Tuned> tuned(std::max(std::max(P, p.opt_active ? p.tcap : 0), 1));
   std::vector<int> change, order, next_played;
   std::vector<char> keep;
@@ -112,7 +115,21 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
           ++res.notes_dropped;
           continue;
         }
-        notes.push_back(note_on(p, tuned[idx], res.notes_started, n_k));
+        Note nn = note_on(p, tuned[idx], res.notes_started, n_k);
+        int c = 0;
+        while (chan_note[c] >= 0) ++c;  // first free channel, include/gen.crtp.h:398-410
+        nn.chan = c;
+        const double ai = chan_angle_increments(chan_osc_ai[c], nn.glide.from);
+        for (int o = 0; o < p.max_channels; ++o) {
+          if (o == c || chan_note[o] < 0) continue;
+          const Note& other = notes[chan_note[o]];
+          if (chan_angle_increments(chan_osc_ai[o], other.glide.from) == ai) {
+            nn.phase = other.phase;  // synchronizeAngles: the other oscillator's phasor as of its last step
+            break;
+          }
+        }
+        notes.push_back(nn);
+        chan_note[c] = static_cast<int>(notes.size()) - 1;
         next_played.push_back(static_cast<int>(notes.size()) - 1);
       }
     }
@@ -128,7 +145,10 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
       res.tile_n0.push_back(n_k_tile);
       res.tile_len.push_back(std::max(len, 0));
       if (len <= 0) break;
-      for (auto& n : notes) res.segs.push_back(emit_segment(p, n, n_k_tile, len));
+      for (auto& n : notes) {
+        res.segs.push_back(emit_segment(p, n, n_k_tile, len));
+        chan_osc_ai[n.chan] = n.f_last;  // the oscillator has stepped: its increment is the last one emitted
+      }
     }
     if (len_frame > 0) {
       const int64_t n_next = n_k + len_frame;
@@ -143,6 +163,8 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
       }
       notes.resize(w);
       for (auto& pi : played) pi = remap[pi];
+      std::fill(chan_note.begin(), chan_note.end(), -1);
+      for (size_t i = 0; i < w; ++i) chan_note[notes[i].chan] = static_cast<int>(i);
     }
   }
   res.tile_seg_begin.push_back(static_cast<int64_t>(res.segs.size()));

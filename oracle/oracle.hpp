@@ -11,6 +11,7 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <complex>
 #include <cstdint>
@@ -762,11 +763,15 @@ public:
     ctrl_.set_angle_increments(a);
   }
   void set_start_angle(T a) { osc_.set_start_angle(a); }
+  void synchronize_angles(const ResynthVoice& o) { osc_.synchronize_angles(o.osc_); }  // :209-211 -> :3080-3082 -> :2397-2399
   void on_key_pressed(int32_t d) { env_.on_key_pressed(d); }
   void on_key_released(int32_t d) { env_.on_key_released(d); }
   bool try_acquire() { return env_.try_acquire(); }
   bool rt_active() const { return env_.rt_active(); }
-  T angle_increments() const {  // FreqCtrl_::angleIncrements :3117-3124
+  // FreqCtrl_::angleIncrements :3117-3124. The oscillator's own increment wins when it is non-zero, and nothing resets it
+  // when a channel is reused (SineOscillatorAlgo::forgetPastSignals is empty, :2387-2388): on a reused channel this is the
+  // last increment of the channel's PREVIOUS note until the first step of the new one.
+  T angle_increments() const {
     T ai = osc_.angle_increments();
     return ai != T(0) ? ai : ctrl_.from();
   }
@@ -1000,6 +1005,11 @@ inline float hash_unit(uint64_t id, uint64_t salt) {
   return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
 }
 
+// Test hooks: SynchronizePhase::Yes is what rt.resynth instantiates; a test switches it off to show that a case depends on it,
+// and reads how often the rule fired.
+inline std::atomic<bool>& sync_phase() { static std::atomic<bool> v{true}; return v; }
+inline std::atomic<int64_t>& sync_count() { static std::atomic<int64_t> v{0}; return v; }
+
 struct RoundTripParams {
   int sample_rate = 48000;
   int window = 4096;
@@ -1138,7 +1148,24 @@ private:
       e.set_volume_target(static_cast<T>(0.1f * velocity));
       e.initialize(prm_.env, prm_.sample_rate, stride, prm_.stereo_spread * hash_unit(static_cast<uint64_t>(id), 1));
       e.set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, prm_.sample_rate)));
-      e.set_start_angle(static_cast<T>(hash_unit(static_cast<uint64_t>(id), 2)));
+      // setPhase<SynchronizePhase::Yes, DefaultStartPhase::Random> (include/gen.crtp.h:127-156; Synth instantiated with these
+      // at source/rt.resynth.lib.cpp:201-210): the first OTHER channel, in channel order, whose envelope is RT-active
+      // (releasing channels included) and whose angleIncrements() equals this element's hands over its oscillator phase;
+      // otherwise the start phase is random (SPEC S10: a hash of the note id).
+      bool synced = false;
+      if (sync_phase()) {
+        const T ai = e.angle_increments();
+        for (size_t o = 0; o < channels_.size(); ++o) {
+          if (o == c || !channels_[o].rt_active()) continue;
+          if (channels_[o].angle_increments() == ai) {
+            e.synchronize_angles(channels_[o]);
+            synced = true;
+            ++sync_count();
+            break;
+          }
+        }
+      }
+      if (!synced) e.set_start_angle(static_cast<T>(hash_unit(static_cast<uint64_t>(id), 2)));
       e.on_key_pressed(0);
       return true;
     }

@@ -71,6 +71,11 @@ def lib():
         L.orc_pitch_stages.restype = C.c_int
         L.orc_roundtrip_opts.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
                                          p, p, C.c_int]
+        L.orc_roundtrip_full.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
+                                         p, C.c_int, p, p, C.c_int]
+        L.orc_set_sync_phase.argtypes = [C.c_int]
+        L.orc_sync_count.argtypes = [C.c_int]
+        L.orc_sync_count.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -213,7 +218,8 @@ def sine_trace(start_angle: float, angle_increment: float, n: int) -> np.ndarray
 
 
 def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: int = 48000, min_db: float = -80.0,
-              gain: float = 1.0, stereo_spread: float = 1.0, env: Ahdsr | None = None, threads: int = 1, opts=None):
+              gain: float = 1.0, stereo_spread: float = 1.0, env: Ahdsr | None = None, threads: int = 1, opts=None,
+              nearby_distance_tones: float = 0.4, min_volume: float = 1e-4, max_track_pitches: float = 1.0, max_channels: int = 254):
     """Analysis -> pitch pipeline -> resynthesis of each row of x (offline loop of the reference). Returns
     (audio float64 [streams, samples, 2], stats int64 [streams, 2] = notes started, notes dropped)."""
     x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
@@ -221,9 +227,22 @@ def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: in
     out = np.zeros((streams, n, 2), dtype=np.float64)
     stats = np.zeros((streams, 2), dtype=np.int64)
     e = env if env is not None else make_ahdsr()
-    lib().orc_roundtrip_opts(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
-                             C.byref(e), None if opts is None else C.byref(opts), _ptr(out), _ptr(stats), threads)
+    # the tracking parameters travel as the floats the product's parameter block holds (ca_roundtrip_params)
+    trk = np.array([np.float32(nearby_distance_tones), np.float32(min_volume), np.float32(max_track_pitches)], dtype=np.float64)
+    lib().orc_roundtrip_full(_ptr(x), n, streams, sample_rate, window, hop, float(min_db), float(gain), float(stereo_spread),
+                             C.byref(e), None if opts is None else C.byref(opts), _ptr(trk), int(max_channels), _ptr(out), _ptr(stats),
+                             threads)
     return out, stats
+
+
+def set_sync_phase(on: bool) -> None:
+    """Test hook: SynchronizePhase::Yes (the reference's setting, default) or off."""
+    lib().orc_set_sync_phase(1 if on else 0)
+
+
+def sync_count(reset: bool = True) -> int:
+    """Test hook: how often a NoteOn took over the phase of a channel with the same angle increment."""
+    return int(lib().orc_sync_count(1 if reset else 0))
 
 
 def pitch_stages(opts: PitchOptions, pitch, volume, cap: int = 1024):

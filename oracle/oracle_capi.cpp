@@ -286,9 +286,10 @@ int orc_pitch_stages(const PitchOptions* o, double* pitch, double* volume, int n
   return static_cast<int>(tuned.size());
 }
 
-void orc_roundtrip_opts(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
-                        float gain, float stereo_spread, const Ahdsr* env, const PitchOptions* opts, double* out, int64_t* stats,
-                        int threads) {
+// tracking[3] (nullable): nearby_distance_tones, min_volume, max_track_pitches; max_channels <= 0: the reference's 254
+void orc_roundtrip_full(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
+                        float gain, float stereo_spread, const Ahdsr* env, const PitchOptions* opts, const double* tracking,
+                        int max_channels, double* out, int64_t* stats, int threads) {
   parallel_for(n_streams, threads, [&](int64_t s) {
     RoundTripParams p;
     p.sample_rate = sample_rate;
@@ -299,6 +300,12 @@ void orc_roundtrip_opts(const float* x, int64_t n_samples, int64_t n_streams, in
     p.stereo_spread = stereo_spread;
     if (env) p.env = *env;
     if (opts) p.opts = *opts;
+    if (tracking) {
+      p.nearby_distance_tones = tracking[0];
+      p.min_volume = tracking[1];
+      p.max_track_pitches = tracking[2];
+    }
+    if (max_channels > 0) p.max_channels = max_channels;
     RoundTrip<double> rt(p);
     rt.run(x + s * n_samples, n_samples, out + s * n_samples * 2);
     if (stats) {
@@ -306,6 +313,20 @@ void orc_roundtrip_opts(const float* x, int64_t n_samples, int64_t n_streams, in
       stats[2 * s + 1] = rt.dropped_notes();
     }
   });
+}
+
+// test hooks of the start-phase rule (oracle.hpp sync_phase / sync_count)
+void orc_set_sync_phase(int on) { sync_phase() = on != 0; }
+int64_t orc_sync_count(int reset) {
+  const int64_t v = sync_count();
+  if (reset) sync_count() = 0;
+  return v;
+}
+
+void orc_roundtrip_opts(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,
+                        float gain, float stereo_spread, const Ahdsr* env, const PitchOptions* opts, double* out, int64_t* stats,
+                        int threads) {
+  orc_roundtrip_full(x, n_samples, n_streams, sample_rate, window, hop, min_db, gain, stereo_spread, env, opts, nullptr, 0, out, stats, threads);
 }
 
 void orc_roundtrip(const float* x, int64_t n_samples, int64_t n_streams, int sample_rate, int window, int hop, double min_db,

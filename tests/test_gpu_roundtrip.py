@@ -37,10 +37,10 @@ def test_envelope_with_decay_and_pool_limit(pkg, orc, ctx, wl):
     x = wl.c4_streams(1, 0.6)
     env = pkg.Ahdsr(300, 0, 100, 600, 0, 2000, 0, 0.5)
     out, stats = pkg.resynth_roundtrip(ctx, x, env=env, max_channels=8, gain=0.7, stereo_spread=0.3)
-    ref, rstats = orc.roundtrip(x, env=orc.make_ahdsr(300, 100, 600, 2000, 0.5), gain=0.7, stereo_spread=0.3) \
-        if False else (None, None)
-    # the oracle entry point has no max_channels knob: check the pool limit on its own
+    ref, rstats = orc.roundtrip(x, env=orc.make_ahdsr(300, 100, 600, 2000, 0.5), gain=0.7, stereo_spread=0.3, max_channels=8)
+    assert np.array_equal(stats, rstats)
     assert stats[0, 1] == stats[0, 0] - 8 and stats[0, 1] > 0
+    assert np.abs(out - ref).max() < 1e-5
     out2, stats2 = pkg.resynth_roundtrip(ctx, x, env=env, gain=0.7, stereo_spread=0.3)
     ref2, rstats2 = orc.roundtrip(x, env=orc.make_ahdsr(300, 100, 600, 2000, 0.5), gain=0.7, stereo_spread=0.3)
     assert np.array_equal(stats2, rstats2)
@@ -167,3 +167,26 @@ def test_float32_analysis_switch_still_tracks(pkg, orc, ctx, wl):
     ref, rstats = orc.roundtrip(x, hop=255)
     assert np.array_equal(stats, rstats)
     assert np.abs(out - ref).max() < 2e-5
+
+
+def test_start_phase_synchronisation(pkg, orc, ctx):
+    """setPhase<SynchronizePhase::Yes> (include/gen.crtp.h:127-156): note-ons at the increment of a sounding channel take over
+    its phase, on fresh channels and -- the second click -- on reused ones, whose oscillators still hold the increment of
+    their previous note (tests/test_oracle_sync_phase.py explains the signal). Device and host forms against the oracle."""
+    from test_oracle_sync_phase import sync_signal
+    x = sync_signal()
+    orc.sync_count()
+    ref, rstats = orc.roundtrip(x, env=orc.make_ahdsr(0, 0, 0, 20000, 1.0), max_track_pitches=0.0)
+    assert orc.sync_count() >= 50                 # 34 on stream 0, most of stream 1
+    env = pkg.Ahdsr(0, 0, 0, 0, 0, 20000, 0, 1.0)
+    dev, dstats = pkg.resynth_roundtrip(ctx, x, env=env, max_track_pitches=0.0)
+    host, hstats = pkg.resynth_roundtrip(ctx, x, env=env, max_track_pitches=0.0, host_threads=-1)
+    assert np.array_equal(dstats, rstats) and np.array_equal(hstats, rstats)
+    assert np.abs(ref).max() > 0.5
+    assert np.abs(host - ref).max() < 1e-5
+    assert np.abs(dev - ref).max() < 1e-5
+    # a pool smaller than the demand: drops and channel reuse while the rule is at work
+    ref8, rstats8 = orc.roundtrip(x, env=orc.make_ahdsr(0, 0, 0, 20000, 1.0), max_track_pitches=0.0, max_channels=8)
+    dev8, dstats8 = pkg.resynth_roundtrip(ctx, x, env=env, max_track_pitches=0.0, max_channels=8)
+    assert np.array_equal(dstats8, rstats8) and rstats8[:, 1].min() > 0
+    assert np.abs(dev8 - ref8).max() < 1e-5
