@@ -12,6 +12,7 @@ DECLARED_SYMBOLS = [
     "ca_host_free", "ca_rfft_batched", "ca_irfft_batched", "ca_rfft_batched_host", "ca_fft_length_for", "ca_stft_num_frames", "ca_stft_plan",
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
     "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host", "ca_vocoder_host",
+    "ca_oscbank_render_tracks", "ca_oscbank_render_tracks_host",
 ]
 
 
@@ -54,6 +55,18 @@ class RampDesc(C.Structure):
                 ("from_hz", C.c_void_p), ("to_hz", C.c_void_p), ("duration", C.c_void_p), ("start_sample", C.c_void_p),
                 ("volume", C.c_void_p), ("start_angle", C.c_void_p), ("key_delay", C.c_void_p), ("release_at", C.c_void_p),
                 ("env", Ahdsr)]
+
+
+class TrackEvent(C.Structure):
+    """ca_track_event: Event of include/events.h:12-107 with the sample time at which it takes effect."""
+    _fields_ = [("at_sample", C.c_int64), ("noteid", C.c_int64), ("type", C.c_int32), ("frequency", C.c_float),
+                ("velocity", C.c_float), ("reserved", C.c_int32)]
+
+
+class TracksDesc(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("events", C.c_void_p), ("n_samples", C.c_int64), ("sample_rate", C.c_int32),
+                ("glide_samples", C.c_int32), ("env", Ahdsr), ("max_channels", C.c_int32), ("stereo_spread", C.c_float),
+                ("mix", C.c_int32)]
 
 
 class OscBankDesc(C.Structure):
@@ -109,6 +122,8 @@ def lib():
     L.ca_resynth_roundtrip_host.argtypes = [p, C.POINTER(RoundtripParams), p, i64, i64, p, p]
     L.ca_ramp_render_host.argtypes = [p, C.POINTER(RampDesc), p]
     L.ca_vocoder_host.argtypes = [p, C.POINTER(VocoderParams), p, p, i64, i64, p]
+    L.ca_oscbank_render_tracks.argtypes = [p, C.POINTER(TracksDesc), p, p, p]
+    L.ca_oscbank_render_tracks_host.argtypes = [p, C.POINTER(TracksDesc), p, p]
     _lib = L
     return L
 

@@ -320,6 +320,18 @@ int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, co
   return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
 }
 
+int ca_oscbank_render_tracks(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, ca_stream stream) {
+  if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  return tracks_render(ctx, desc, d_out, h_stats, static_cast<cudaStream_t>(stream));
+}
+
+int ca_oscbank_render_tracks_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats) {
+  if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  return tracks_render_host(ctx, desc, h_out, h_stats);
+}
+
 int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
                     int64_t n_samples, int64_t n_streams, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;

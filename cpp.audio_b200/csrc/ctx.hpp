@@ -129,6 +129,8 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
 int measure_fp32_peak(ca_ctx* ctx, double* tflops);
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);
+int tracks_render(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, cudaStream_t st);
+int tracks_render_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats);
 int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
 int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modulator, const float* h_carrier, int64_t n_samples,
                  int64_t n_streams, float* h_out);

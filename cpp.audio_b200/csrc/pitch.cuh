@@ -499,9 +499,46 @@ CA_HD inline Segment emit_segment(const PitchParams& p, Note& n, int64_t n_k_til
 
 }  // namespace ca
 
+#include <algorithm>
+#include <vector>
+namespace ca {
+// Host form of the voice pool's channels (ImplCRTP, include/gen.crtp.h:221-233): which note of `notes` sits on each channel
+// (-1: free) and the increment the channel's oscillator last stepped with (it survives the note).
+struct HostChannels {
+  std::vector<int> note;
+  std::vector<double> osc_ai;
+  explicit HostChannels(int n) : note(n > 0 ? n : 1, -1), osc_ai(n > 0 ? n : 1, 0.0) {}
+  void rebuild(const std::vector<Note>& notes) {
+    std::fill(note.begin(), note.end(), -1);
+    for (size_t i = 0; i < notes.size(); ++i) note[notes[i].chan] = static_cast<int>(i);
+  }
+};
+// NoteOn on the first free channel (include/gen.crtp.h:398-410) with the start-phase rule of setPhase (:127-156).
+// Returns the index of the new note in `notes`, or -1 when every channel is taken (DROPPED_NOTE, :412-414).
+inline int pool_note_on(const PitchParams& p, std::vector<Note>& notes, HostChannels& ch, const Tuned& t, int64_t id, int64_t n_k) {
+  if (static_cast<int>(notes.size()) >= p.max_channels) return -1;  // every entry of `notes` still holds a channel
+  Note nn = note_on(p, t, id, n_k);
+  int c = 0;
+  while (ch.note[c] >= 0) ++c;
+  nn.chan = c;
+  const double ai = chan_angle_increments(ch.osc_ai[c], nn.glide.from);
+  for (int o = 0; o < p.max_channels; ++o) {
+    if (o == c || ch.note[o] < 0) continue;
+    const Note& other = notes[ch.note[o]];
+    if (chan_angle_increments(ch.osc_ai[o], other.glide.from) == ai) {
+      nn.phase = other.phase;  // synchronizeAngles: the other oscillator's phasor as of its last step
+      break;
+    }
+  }
+  notes.push_back(nn);
+  ch.note[c] = static_cast<int>(notes.size()) - 1;
+  return ch.note[c];
+}
+}  // namespace ca
+
 struct ca_ctx;
 namespace ca {
-// pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track_kernel, one warp per stream)
+// pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track3_kernel, three warps per stream)
 // d_peak_off / d_peak_db: float arrays, or double arrays when peaks_f64 is set (the FP64 analysis of stft64.cu)
 int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
                           const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,

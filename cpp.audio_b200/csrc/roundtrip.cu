@@ -61,9 +61,7 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
   const int P = p.P;
   std::vector<Note> notes;       // sounding notes (tracked or releasing)
   std::vector<int> played;       // indices into notes of tracked notes, sorted by pitch
-  // the voice pool's channels: which note sits on each (-1: free) and the increment its oscillator last stepped with
-  std::vector<int> chan_note(std::max(p.max_channels, 1), -1);
-  std::vector<double> chan_osc_ai(std::max(p.max_channels, 1), 0.0);
+  HostChannels ch(p.max_channels);
   std::vector<Tuned> tuned(std::max(std::max(P, p.opt_active ? p.tcap : 0), 1));
   std::vector<int> change, order, next_played;
   std::vector<char> keep;
@@ -111,25 +109,10 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
       } else {
         if (tuned[idx].volume <= 0) continue;
         ++res.notes_started;
-        if (static_cast<int>(notes.size()) >= p.max_channels) {  // every entry of `notes` still holds a channel
+        if (pool_note_on(p, notes, ch, tuned[idx], res.notes_started, n_k) < 0) {
           ++res.notes_dropped;
           continue;
         }
-        Note nn = note_on(p, tuned[idx], res.notes_started, n_k);
-        int c = 0;
-        while (chan_note[c] >= 0) ++c;  // first free channel, include/gen.crtp.h:398-410
-        nn.chan = c;
-        const double ai = chan_angle_increments(chan_osc_ai[c], nn.glide.from);
-        for (int o = 0; o < p.max_channels; ++o) {
-          if (o == c || chan_note[o] < 0) continue;
-          const Note& other = notes[chan_note[o]];
-          if (chan_angle_increments(chan_osc_ai[o], other.glide.from) == ai) {
-            nn.phase = other.phase;  // synchronizeAngles: the other oscillator's phasor as of its last step
-            break;
-          }
-        }
-        notes.push_back(nn);
-        chan_note[c] = static_cast<int>(notes.size()) - 1;
         next_played.push_back(static_cast<int>(notes.size()) - 1);
       }
     }
@@ -147,7 +130,7 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
       if (len <= 0) break;
       for (auto& n : notes) {
         res.segs.push_back(emit_segment(p, n, n_k_tile, len));
-        chan_osc_ai[n.chan] = n.f_last;  // the oscillator has stepped: its increment is the last one emitted
+        ch.osc_ai[n.chan] = n.f_last;  // the oscillator has stepped: its increment is the last one emitted
       }
     }
     if (len_frame > 0) {
@@ -163,8 +146,7 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
       }
       notes.resize(w);
       for (auto& pi : played) pi = remap[pi];
-      std::fill(chan_note.begin(), chan_note.end(), -1);
-      for (size_t i = 0; i < w; ++i) chan_note[notes[i].chan] = static_cast<int>(i);
+      ch.rebuild(notes);
     }
   }
   res.tile_seg_begin.push_back(static_cast<int64_t>(res.segs.size()));

@@ -94,3 +94,40 @@ def render_ramps(ctx: Context, from_hz, to_hz, duration, n_samples: int, sample_
     out = np.zeros((V, n_samples) if mix == 0 else (n_samples,), dtype=np.float32)
     ctx.check(lib().ca_ramp_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p)), "ca_ramp_render_host")
     return out
+
+
+NOTE_ON, NOTE_OFF, NOTE_CHANGE = 0, 1, 2  # enum ca_event_type = EventType of include/events.h:12-17
+
+
+def track_events(events):
+    """[(at_sample, noteid, type, frequency_hz, velocity), ...] -> ctypes array of ca_track_event."""
+    from ._capi import TrackEvent
+
+    arr = (TrackEvent * max(len(events), 1))()
+    for i, (at, nid, typ, freq, vel) in enumerate(events):
+        arr[i] = TrackEvent(int(at), int(nid), int(typ), float(freq), float(vel), 0)
+    return arr
+
+
+def render_tracks(ctx: Context, events, n_samples: int, sample_rate: int = 48000, glide_samples: int = 256, env: Ahdsr | None = None,
+                  max_channels: int = 254, stereo_spread: float = 1.0, mono: bool = False, device_out: torch.Tensor | None = None):
+    """A note schedule on the rt.resynth voice pool (ca_oscbank_render_tracks[_host]). Returns (audio, stats): audio float32
+    [n_samples, 2] (or [n_samples] when mono) as a numpy array, or the CUDA tensor `device_out` when given; stats = (notes
+    started, notes dropped)."""
+    from ._capi import TracksDesc
+
+    arr = track_events(events)
+    e = env if env is not None else Ahdsr(0, 0, 0, 0, 0, 0, 0, 1.0)
+    d = TracksDesc(len(events), C.cast(arr, C.c_void_p), n_samples, sample_rate, glide_samples, e, max_channels, stereo_spread,
+                   MIX_MONO if mono else MIX_STEREO)
+    stats = (C.c_int64 * 2)()
+    shape = (n_samples,) if mono else (n_samples, 2)
+    if device_out is not None:
+        assert device_out.is_cuda and device_out.dtype == torch.float32 and device_out.is_contiguous() and tuple(device_out.shape) == shape
+        ctx.check(lib().ca_oscbank_render_tracks(ctx.handle, C.byref(d), device_out.data_ptr(), stats,
+                                                 torch.cuda.current_stream(device_out.device).cuda_stream), "ca_oscbank_render_tracks")
+        return device_out, (int(stats[0]), int(stats[1]))
+    out = np.empty(shape, dtype=np.float32)
+    ctx.check(lib().ca_oscbank_render_tracks_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p), stats),
+              "ca_oscbank_render_tracks_host")
+    return out, (int(stats[0]), int(stats[1]))

@@ -208,6 +208,44 @@ typedef struct ca_roundtrip_params {
 int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
                               int64_t n_streams, float* h_out, int64_t* h_stats);
 
+/* ---- a note schedule on the rt.resynth voice pool -------------------------------------------------------------------
+ * Stands in for ImplCRTP::onEvent + ImplCRTP::compute (include/gen.crtp.h:382-622, :350-378) of the synth rt.resynth drives
+ * (sine::Synth<2, ResynthElement, ..., SynchronizePhase::Yes, DefaultStartPhase::Random, HandleNoteOff::Yes, 127,
+ * ResynthElementInitializer>, source/rt.resynth.lib.cpp:201-210), for a host that owns its note schedule: the synthesis half of
+ * the round trip on its own. Events are the reference's (include/events.h:12-107) plus the sample time at which they take
+ * effect: the events of sample n are applied, in array order, before the pool steps to produce output sample n
+ * (SimpleAudioOutContext::step, include/simple_audio_context.h:69-112).
+ *   NoteOn     takes the first free channel (DROPPED_NOTE when none is, counted in h_stats[1]); volume target 0.1 * velocity;
+ *              start phase: that of the first other sounding channel with the same angle increment, else random
+ *              (setPhase, gen.crtp.h:127-156; random = a hash of the note id, also used for the pan: oracle/SPEC.md S10)
+ *   NoteChange new volume target and a frequency glide of `glide_samples` samples on every channel that holds the id
+ *   NoteOff    releases the first channel that holds the id
+ * Note ids should be unique per note (the reference asks for the same, gen.crtp.h:575-577). */
+enum ca_event_type { CA_NOTE_ON = 0, CA_NOTE_OFF = 1, CA_NOTE_CHANGE = 2 }; /* EventType, include/events.h:12-17 */
+typedef struct ca_track_event {
+  int64_t at_sample;  /* >= 0, non-decreasing along the array */
+  int64_t noteid;     /* NoteId */
+  int32_t type;       /* ca_event_type */
+  float frequency;    /* Hz: noteOn.frequency / noteChange.changed_frequency */
+  float velocity;     /* noteOn.velocity / noteChange.changed_velocity */
+  int32_t reserved;
+} ca_track_event;
+typedef struct ca_tracks_desc {
+  int64_t n_events;
+  const ca_track_event* events; /* HOST pointer in both forms (control-rate data) */
+  int64_t n_samples;
+  int32_t sample_rate;
+  int32_t glide_samples;        /* ResynthElementInitializer's stride: glide duration, volume filter limit 2/stride */
+  ca_ahdsr env;                 /* LINEAR interpolations */
+  int32_t max_channels;         /* 254 in rt.resynth */
+  float stereo_spread;          /* pan = stereo_spread * U(-1,1) per note (CA_MIX_STEREO) */
+  int32_t mix;                  /* CA_MIX_STEREO: out [n_samples][2]; CA_MIX_MONO: out [n_samples], no pan */
+} ca_tracks_desc;
+/* d_out: DEVICE memory, every sample is written; asynchronous on `stream`. h_stats (nullable, host): notes started, dropped. */
+int ca_oscbank_render_tracks(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, ca_stream stream);
+/* h_out: HOST memory; returns when it is filled */
+int ca_oscbank_render_tracks_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats);
+
 /* ---- gen.voice ramp voices ---------------------------------------------------------------------------------------
  * Stands in for the inner element of voice::Impl_::doProcessing / SoundEngine::step (include/gen.voice.h:1130-1189;
  * include/soundengine.h:245-257, 412-464): Enveloped<FreqCtrl_<SineOscillatorAlgo, LogRamp>, AHDSREnvelope> with a constant

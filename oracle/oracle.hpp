@@ -877,6 +877,22 @@ bool pool_compute_mono(std::vector<Voice>& voices, double* buffer, int n_frames,
   return !silence;
 }
 
+// nOuts == 1 with an element that is not StereoPanned: imag_mono() of the round-trip element
+template <class Voice>
+bool pool_compute_mono_unpanned(std::vector<Voice>& voices, double* buffer, int n_frames) {
+  bool silence = true;
+  for (auto& v : voices) {
+    if (!v.rt_active()) continue;
+    silence = false;
+    for (int i = 0; i < n_frames; ++i) {
+      v.step();
+      if (!v.rt_active()) break;
+      buffer[i] += v.imag_mono();
+    }
+  }
+  return !silence;
+}
+
 template <class Voice>
 bool pool_compute_stereo(std::vector<Voice>& voices, double* buffer, int n_frames) {
   bool silence = true;
@@ -1026,11 +1042,124 @@ struct RoundTripParams {
   PitchOptions opts;                    // shift / harmonize / autotune (:1687-1707), off by default
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// The voice pool of sine::Synth<..., ResynthElement, ..., SynchronizePhase::Yes, DefaultStartPhase::Random, HandleNoteOff::Yes,
+// 127, ResynthElementInitializer> (source/rt.resynth.lib.cpp:201-210): ImplCRTP::onEvent (include/gen.crtp.h:382-622) over
+// 2 * 127 channels (:221-233) of StereoPanned<VolumeAdjusted<Enveloped<FreqCtrl_<Sine, InterpolatedFreq>, AHDSR>>>.
+// ------------------------------------------------------------------------------------------------------------
+template <class T>
+class VoicePool {
+public:
+  VoicePool(const Ahdsr& env, int sample_rate, int max_channels, float stereo_spread)
+      : env_(env), sample_rate_(sample_rate), stereo_spread_(stereo_spread), channels_(max_channels), note_of_(max_channels, -1) {}
+
+  // NoteOn (:389-531) with ResynthElementInitializer (rt.resynth.lib.cpp:96-118); false: no free channel (DROPPED_NOTE, :412-414)
+  bool note_on(int64_t id, float freq, float velocity, int stride) {
+    for (size_t c = 0; c < channels_.size(); ++c) {
+      if (!channels_[c].try_acquire()) continue;
+      auto& e = channels_[c];
+      note_of_[c] = id;
+      e.forget_past_signals();
+      e.set_volume_target(static_cast<T>(0.1f * velocity));
+      e.initialize(env_, sample_rate_, stride, stereo_spread_ * hash_unit(static_cast<uint64_t>(id), 1));
+      e.set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, sample_rate_)));
+      // setPhase<SynchronizePhase::Yes, DefaultStartPhase::Random> (include/gen.crtp.h:127-156; Synth instantiated with these
+      // at source/rt.resynth.lib.cpp:201-210): the first OTHER channel, in channel order, whose envelope is RT-active
+      // (releasing channels included) and whose angleIncrements() equals this element's hands over its oscillator phase;
+      // otherwise the start phase is random (SPEC S10: a hash of the note id).
+      bool synced = false;
+      if (sync_phase()) {
+        const T ai = e.angle_increments();
+        for (size_t o = 0; o < channels_.size(); ++o) {
+          if (o == c || !channels_[o].rt_active()) continue;
+          if (channels_[o].angle_increments() == ai) {
+            e.synchronize_angles(channels_[o]);
+            synced = true;
+            ++sync_count();
+            break;
+          }
+        }
+      }
+      if (!synced) e.set_start_angle(static_cast<T>(hash_unit(static_cast<uint64_t>(id), 2)));
+      e.on_key_pressed(0);
+      return true;
+    }
+    return false;
+  }
+  // NoteChange (:595-618): every channel that holds the note id
+  void note_change(int64_t id, float velocity, float freq) {
+    for (size_t c = 0; c < channels_.size(); ++c)
+      if (note_of_[c] == id) {
+        channels_[c].set_volume_target(static_cast<T>(0.1f * velocity));
+        channels_[c].set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, sample_rate_)));
+      }
+  }
+  // NoteOff (:532-593): the first channel that holds the note id, released if its key is pressed (:802-811)
+  void note_off(int64_t id) {
+    for (size_t c = 0; c < channels_.size(); ++c)
+      if (note_of_[c] == id) {
+        channels_[c].on_key_released(0);
+        return;
+      }
+  }
+  std::vector<ResynthVoice<T>>& channels() { return channels_; }
+
+private:
+  Ahdsr env_;
+  int sample_rate_;
+  float stereo_spread_;
+  std::vector<ResynthVoice<T>> channels_;
+  std::vector<int64_t> note_of_;
+};
+
+// A note schedule played on the pool: the events of sample n are applied, in order, before the pool steps to produce output
+// sample n (what SimpleAudioOutContext::step does with its one-shots, include/simple_audio_context.h:69-112).
+struct TrackEvent {  // same layout as ca_track_event (include/cpp_audio_b200.h)
+  int64_t at_sample;
+  int64_t noteid;
+  int32_t type;  // EventType, include/events.h:12-17: 0 NoteOn, 1 NoteOff, 2 NoteChange
+  float frequency;
+  float velocity;
+  int32_t reserved;
+};
+
+template <class T>
+void render_tracks(const TrackEvent* ev, int64_t n_events, int64_t n_samples, int sample_rate, int glide_samples, const Ahdsr& env,
+                   int max_channels, float stereo_spread, bool mono, double* out, int64_t* stats) {
+  VoicePool<T> pool(env, sample_rate, max_channels, stereo_spread);
+  int64_t started = 0, dropped = 0, e = 0;
+  for (int64_t i = 0; i < n_samples; ++i) {
+    for (; e < n_events && ev[e].at_sample <= i; ++e) {
+      if (ev[e].type == 0) {
+        ++started;
+        if (!pool.note_on(ev[e].noteid, ev[e].frequency, ev[e].velocity, glide_samples)) ++dropped;
+      } else if (ev[e].type == 1) {
+        pool.note_off(ev[e].noteid);
+      } else {
+        pool.note_change(ev[e].noteid, ev[e].velocity, ev[e].frequency);
+      }
+    }
+    double buf[2] = {0, 0};
+    if (mono) {
+      pool_compute_mono_unpanned(pool.channels(), buf, 1);
+      out[i] = buf[0];
+    } else {
+      pool_compute_stereo(pool.channels(), buf, 1);
+      out[2 * i] = buf[0];
+      out[2 * i + 1] = buf[1];
+    }
+  }
+  if (stats) {
+    stats[0] = started;
+    stats[1] = dropped;
+  }
+}
+
 template <class T>
 class RoundTrip {
 public:
   explicit RoundTrip(const RoundTripParams& p)
-      : prm_(p), pfft_(Window::Gaussian, p.sigma_factor), channels_(p.max_channels), note_of_(p.max_channels, -1) {
+      : prm_(p), pfft_(Window::Gaussian, p.sigma_factor), pool_(p.env, p.sample_rate, p.max_channels, p.stereo_spread) {
     pfft_.set_lambdas([this] { return prm_.window; }, [this] { return prm_.hop; },
                       [this](int stride, const std::vector<double>& sq) { on_frame(stride, sq); });
   }
@@ -1040,7 +1169,7 @@ public:
     for (int64_t i = 0; i < n; ++i) {
       pfft_.feed(x[i]);
       double buf[2] = {0, 0};
-      pool_compute_stereo(channels_, buf, 1);
+      pool_compute_stereo(pool_.channels(), buf, 1);
       out[2 * i] = buf[0];
       out[2 * i + 1] = buf[1];
     }
@@ -1138,58 +1267,13 @@ private:
     played_.swap(alive);
   }
 
-  // ImplCRTP::onEvent (include/gen.crtp.h:382-622) with ResynthElementInitializer (rt.resynth.lib.cpp:96-118)
-  bool note_on(int64_t id, float freq, float velocity, int stride) {
-    for (size_t c = 0; c < channels_.size(); ++c) {
-      if (!channels_[c].try_acquire()) continue;
-      auto& e = channels_[c];
-      note_of_[c] = id;
-      e.forget_past_signals();
-      e.set_volume_target(static_cast<T>(0.1f * velocity));
-      e.initialize(prm_.env, prm_.sample_rate, stride, prm_.stereo_spread * hash_unit(static_cast<uint64_t>(id), 1));
-      e.set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, prm_.sample_rate)));
-      // setPhase<SynchronizePhase::Yes, DefaultStartPhase::Random> (include/gen.crtp.h:127-156; Synth instantiated with these
-      // at source/rt.resynth.lib.cpp:201-210): the first OTHER channel, in channel order, whose envelope is RT-active
-      // (releasing channels included) and whose angleIncrements() equals this element's hands over its oscillator phase;
-      // otherwise the start phase is random (SPEC S10: a hash of the note id).
-      bool synced = false;
-      if (sync_phase()) {
-        const T ai = e.angle_increments();
-        for (size_t o = 0; o < channels_.size(); ++o) {
-          if (o == c || !channels_[o].rt_active()) continue;
-          if (channels_[o].angle_increments() == ai) {
-            e.synchronize_angles(channels_[o]);
-            synced = true;
-            ++sync_count();
-            break;
-          }
-        }
-      }
-      if (!synced) e.set_start_angle(static_cast<T>(hash_unit(static_cast<uint64_t>(id), 2)));
-      e.on_key_pressed(0);
-      return true;
-    }
-    return false;
-  }
-  void note_change(int64_t id, float velocity, float freq) {
-    for (size_t c = 0; c < channels_.size(); ++c)
-      if (note_of_[c] == id) {
-        channels_[c].set_volume_target(static_cast<T>(0.1f * velocity));
-        channels_[c].set_angle_increments(static_cast<T>(freq_to_angle_increment<float>(freq, prm_.sample_rate)));
-      }
-  }
-  void note_off(int64_t id) {
-    for (size_t c = 0; c < channels_.size(); ++c)
-      if (note_of_[c] == id) {
-        channels_[c].on_key_released(0);
-        return;
-      }
-  }
+  bool note_on(int64_t id, float freq, float velocity, int stride) { return pool_.note_on(id, freq, velocity, stride); }
+  void note_change(int64_t id, float velocity, float freq) { pool_.note_change(id, velocity, freq); }
+  void note_off(int64_t id) { pool_.note_off(id); }
 
   RoundTripParams prm_;
   PeriodicFft<SqMagOp<double>> pfft_;
-  std::vector<ResynthVoice<T>> channels_;
-  std::vector<int64_t> note_of_;
+  VoicePool<T> pool_;
   std::vector<FreqMag<double>> freqmags_;
   std::vector<PitchVolume> pv_, reduced_, tuned_, pitches_tmp_;
   std::vector<PlayedNote> played_;

@@ -73,6 +73,7 @@ def lib():
                                          p, p, C.c_int]
         L.orc_roundtrip_full.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
                                          p, C.c_int, p, p, C.c_int]
+        L.orc_render_tracks.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, p, C.c_int, C.c_float, C.c_int, p, p]
         L.orc_set_sync_phase.argtypes = [C.c_int]
         L.orc_sync_count.argtypes = [C.c_int]
         L.orc_sync_count.restype = C.c_int64
@@ -233,6 +234,27 @@ def roundtrip(x: np.ndarray, window: int = 4096, hop: int = 256, sample_rate: in
                              C.byref(e), None if opts is None else C.byref(opts), _ptr(trk), int(max_channels), _ptr(out), _ptr(stats),
                              threads)
     return out, stats
+
+
+class TrackEvent(C.Structure):
+    """orc::TrackEvent = ca_track_event: type 0 NoteOn, 1 NoteOff, 2 NoteChange (EventType, include/events.h:12-17)."""
+    _fields_ = [("at_sample", C.c_int64), ("noteid", C.c_int64), ("type", C.c_int32), ("frequency", C.c_float),
+                ("velocity", C.c_float), ("reserved", C.c_int32)]
+
+
+def render_tracks(events, n_samples: int, sample_rate: int = 48000, glide_samples: int = 256, env: Ahdsr | None = None,
+                  max_channels: int = 254, stereo_spread: float = 1.0, mono: bool = False):
+    """events: [(at_sample, noteid, type, frequency_hz, velocity)] played on the rt.resynth voice pool one sample at a time.
+    Returns (audio float64 [n_samples, 2] or [n_samples], (notes started, notes dropped))."""
+    arr = (TrackEvent * max(len(events), 1))()
+    for i, (at, nid, typ, freq, vel) in enumerate(events):
+        arr[i] = TrackEvent(int(at), int(nid), int(typ), float(freq), float(vel), 0)
+    out = np.zeros((n_samples,) if mono else (n_samples, 2), dtype=np.float64)
+    stats = np.zeros(2, dtype=np.int64)
+    e = env if env is not None else make_ahdsr()
+    lib().orc_render_tracks(C.cast(arr, C.c_void_p), len(events), n_samples, sample_rate, glide_samples, C.byref(e), max_channels,
+                            float(stereo_spread), 1 if mono else 0, _ptr(out), _ptr(stats))
+    return out, (int(stats[0]), int(stats[1]))
 
 
 def set_sync_phase(on: bool) -> None:

@@ -315,6 +315,12 @@ void orc_roundtrip_full(const float* x, int64_t n_samples, int64_t n_streams, in
   });
 }
 
+// A note schedule rendered by the rt.resynth voice pool (VoicePool, oracle.hpp). out: [n_samples][2], or [n_samples] when mono.
+void orc_render_tracks(const TrackEvent* events, int64_t n_events, int64_t n_samples, int sample_rate, int glide_samples,
+                       const Ahdsr* env, int max_channels, float stereo_spread, int mono, double* out, int64_t* stats) {
+  render_tracks<double>(events, n_events, n_samples, sample_rate, glide_samples, *env, max_channels, stereo_spread, mono != 0, out, stats);
+}
+
 // test hooks of the start-phase rule (oracle.hpp sync_phase / sync_count)
 void orc_set_sync_phase(int on) { sync_phase() = on != 0; }
 int64_t orc_sync_count(int reset) {
