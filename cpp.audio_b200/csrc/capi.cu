@@ -332,6 +332,24 @@ int ca_oscbank_render_tracks_host(ca_ctx* ctx, const ca_tracks_desc* desc, float
   return tracks_render_host(ctx, desc, h_out, h_stats);
 }
 
+int ca_tracks_open(ca_ctx* ctx, const ca_tracks_desc* desc, ca_tracks** tracks) {
+  if (!ctx) return CA_ERR_INVALID;
+  return tracks_open(ctx, desc, tracks);
+}
+int ca_tracks_post(ca_tracks* tracks, const ca_track_event* events, int64_t n_events) { return tracks_post(tracks, events, n_events); }
+int ca_tracks_pull(ca_tracks* tracks, int64_t n_samples, float* d_out, ca_stream stream) {
+  if (!tracks) return CA_ERR_INVALID;
+  DeviceGuard guard(tracks_ctx(tracks));
+  return tracks_pull(tracks, n_samples, d_out, static_cast<cudaStream_t>(stream));
+}
+int ca_tracks_pull_host(ca_tracks* tracks, int64_t n_samples, float* h_out) {
+  if (!tracks) return CA_ERR_INVALID;
+  DeviceGuard guard(tracks_ctx(tracks));
+  return tracks_pull_host(tracks, n_samples, h_out);
+}
+int ca_tracks_state(const ca_tracks* tracks, int64_t state[5]) { return tracks_state(tracks, state); }
+void ca_tracks_close(ca_tracks* tracks) { tracks_close(tracks); }
+
 int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
                     int64_t n_samples, int64_t n_streams, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;

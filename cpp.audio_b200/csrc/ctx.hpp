@@ -129,6 +129,13 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
 int measure_fp32_peak(ca_ctx* ctx, double* tflops);
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);
+int tracks_open(ca_ctx* ctx, const ca_tracks_desc* desc, ca_tracks** out);
+int tracks_post(ca_tracks* tp, const ca_track_event* events, int64_t n);
+int tracks_pull(ca_tracks* tp, int64_t n_samples, float* d_out, cudaStream_t st);
+int tracks_pull_host(ca_tracks* tp, int64_t n_samples, float* h_out);
+ca_ctx* tracks_ctx(const ca_tracks* tp);
+int tracks_state(const ca_tracks* tp, int64_t state[5]);
+void tracks_close(ca_tracks* tp);
 int tracks_render(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, cudaStream_t st);
 int tracks_render_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats);
 int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);

@@ -246,6 +246,19 @@ int ca_oscbank_render_tracks(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_o
 /* h_out: HOST memory; returns when it is filled */
 int ca_oscbank_render_tracks_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats);
 
+/* The same pool as an object, for a host that posts events as they become known and pulls audio block by block (what
+ * ImplCRTP::onEvent + compute(double*, int) do in the reference): ca_tracks_open takes the parameters of `desc` (its events,
+ * if any, are posted; n_samples is ignored), ca_tracks_post adds events (ordered; an event earlier than the position acts at
+ * the position, as a late MIDI event does, gen.crtp.h:503-510), ca_tracks_pull* renders the next n_samples and advances the
+ * position. ca_tracks_state: [0] position, [1] notes started, [2] notes dropped, [3] sounding notes, [4] pending events. */
+typedef struct ca_tracks ca_tracks;
+int ca_tracks_open(ca_ctx* ctx, const ca_tracks_desc* desc, ca_tracks** tracks);
+int ca_tracks_post(ca_tracks* tracks, const ca_track_event* events, int64_t n_events);
+int ca_tracks_pull(ca_tracks* tracks, int64_t n_samples, float* d_out, ca_stream stream);
+int ca_tracks_pull_host(ca_tracks* tracks, int64_t n_samples, float* h_out);
+int ca_tracks_state(const ca_tracks* tracks, int64_t state[5]);
+void ca_tracks_close(ca_tracks* tracks);
+
 /* ---- gen.voice ramp voices ---------------------------------------------------------------------------------------
  * Stands in for the inner element of voice::Impl_::doProcessing / SoundEngine::step (include/gen.voice.h:1130-1189;
  * include/soundengine.h:245-257, 412-464): Enveloped<FreqCtrl_<SineOscillatorAlgo, LogRamp>, AHDSREnvelope> with a constant

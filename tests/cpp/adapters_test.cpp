@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../cpp.audio_b200/host/cuda_periodic_fft.hpp"
+#include "../../cpp.audio_b200/host/cuda_resynth_synth.hpp"
 #include "../../cpp.audio_b200/host/cuda_sine_bank.hpp"
 #include "../../oracle/oracle.hpp"
 
@@ -145,6 +146,69 @@ static void test_sine_bank(ca_ctx* ctx) {
   std::printf("OK dropped_note\n");
 }
 
+// The rt.resynth synth through the reference's own calls: onEvent(sample_rate, Event, out, chans, maybeTime) + compute(buffer, n)
+// in 16-frame blocks, events posted just before the block they belong to (the offline loop, rt.resynth.lib.cpp:1204-1234),
+// against the oracle's VoicePool stepping the reference elements one sample at a time.
+static void test_resynth_synth(ca_ctx* ctx) {
+  using namespace ca_host::resynth;
+  int const sr = 48000, n = 48000, stride = 256;
+  struct E { int64_t at; int64_t id; int type; float f, v; };  // type: 0 on, 1 off, 2 change (orc::TrackEvent)
+  std::vector<E> ev = {{0, 1, 0, 440.f, 0.9f},      {2560, 1, 2, 466.16f, 0.7f}, {2816, 1, 2, 493.88f, 0.8f}, {4096, 2, 0, 1320.f, 0.5f},
+                       {8192, 1, 1, 0, 0},          {8704, 3, 0, 493.88f, 0.6f}, {12800, 2, 2, 1100.f, 0.9f}, {20480, 2, 1, 0, 0},
+                       {20992, 4, 0, 3000.f, 0.4f}, {30000 / 16 * 16, 3, 1, 0, 0}};
+  ResynthElementInitializer init;
+  init.sample_rate = sr;
+  init.stride = stride;
+  init.stereo_spread = 0.7f;
+  init.ahdsr = ca_ahdsr{300, 0, 100, 500, 0, 4000, 0, 0.7f};
+  CudaResynthSynth<2> synth(ctx, 127, 16);
+  synth.setSynchronousElementInitializer(init);
+  NoOut out_stub;
+  NoChans chans_stub;
+  std::vector<double> out(static_cast<size_t>(n) * 2, 0.0);
+  size_t next = 0;
+  for (int i = 0; i < n; i += 16) {
+    for (; next < ev.size() && ev[next].at <= i; ++next) {
+      E const& e = ev[next];
+      Event const x = e.type == 0 ? mkNoteOn(NoteId{e.id}, e.f, e.v) : e.type == 1 ? mkNoteOff(NoteId{e.id}) : mkNoteChange(NoteId{e.id}, e.v, e.f);
+      EXPECT(synth.onEvent(sr, x, out_stub, chans_stub, std::nullopt) == onEventResult::OK, "event %zu dropped", next);
+    }
+    synth.compute(out.data() + static_cast<size_t>(i) * 2, std::min(16, n - i));
+  }
+  std::vector<orc::TrackEvent> oev;
+  for (auto const& e : ev) oev.push_back({e.at, e.id, e.type, e.f, e.v, 0});
+  orc::Ahdsr oenv{300, 0, 100, 500, 0, 4000, 0, 0.7f};
+  std::vector<double> ref(static_cast<size_t>(n) * 2, 0.0);
+  int64_t stats[2];
+  orc::render_tracks<double>(oev.data(), static_cast<int64_t>(oev.size()), n, sr, stride, oenv, 254, 0.7f, false, ref.data(), stats);
+  double err = 0, peak = 0;
+  for (size_t i = 0; i < out.size(); ++i) { err = std::max(err, std::fabs(out[i] - ref[i])); peak = std::max(peak, std::fabs(ref[i])); }
+  EXPECT(err < 1e-5, "resynth synth error %g", err);
+  EXPECT(peak > 0.05 && stats[0] == 4 && stats[1] == 0, "reference: peak %g notes %lld", peak, static_cast<long long>(stats[0]));
+  std::printf("OK resynth_synth frames=%d max err=%.3g (peak %.3g)\n", n, err, peak);
+
+  // a timestamped event lands on its sample; allNotesOff releases what is on; a full pool reports DROPPED_NOTE
+  CudaResynthSynth<1> mono(ctx, 1, 64);  // 2 channels
+  mono.setSynchronousElementInitializer(init);
+  EXPECT(mono.onEvent(sr, mkNoteOn(NoteId{1}, 500.f, 1.f), TimestampAndSource{1000000000ull * 1000 / sr, 0}) == onEventResult::OK, "timed note on");
+  EXPECT(mono.onEvent(sr, mkNoteOn(NoteId{2}, 700.f, 1.f)) == onEventResult::OK, "second channel");
+  EXPECT(mono.onEvent(sr, mkNoteOn(NoteId{3}, 900.f, 1.f)) == onEventResult::DROPPED_NOTE, "third note must be dropped");
+  std::vector<double> m(4096, 0.0);
+  for (int i = 0; i < 2048; i += 16) mono.compute(m.data() + i, 16);
+  mono.allNotesOff();
+  bool sounding = true;
+  for (int i = 2048; i < 4096; i += 16) sounding = mono.compute(m.data() + i, 16);
+  std::vector<orc::TrackEvent> mev = {{1000, 1, 0, 500.f, 1.f, 0}, {1000, 2, 0, 700.f, 1.f, 0}, {2048, 1, 1, 0, 0, 0}, {2048, 2, 1, 0, 0, 0}};
+  std::vector<double> mref(4096, 0.0);
+  orc::render_tracks<double>(mev.data(), 4, 4096, sr, stride, oenv, 2, 0.7f, true, mref.data(), stats);
+  double merr = 0;
+  for (size_t i = 0; i < m.size(); ++i) merr = std::max(merr, std::fabs(m[i] - mref[i]));
+  EXPECT(merr < 1e-5, "timed events / allNotesOff error %g", merr);
+  EXPECT(mono.dropped_notes() == 1, "dropped count");
+  (void)sounding;
+  std::printf("OK resynth_synth timed events, allNotesOff, dropped note: max err=%.3g\n", merr);
+}
+
 int main() {
   ca_ctx* ctx = nullptr;
   int rc = ca_init(0, &ctx);
@@ -154,6 +218,7 @@ int main() {
   }
   test_periodic_fft(ctx);
   test_sine_bank(ctx);
+  test_resynth_synth(ctx);
   ca_destroy(ctx);
   std::printf(fails ? "FAILED %d\n" : "ALL OK %d\n", fails);
   return fails ? 1 : 0;
