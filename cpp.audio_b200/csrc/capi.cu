@@ -320,6 +320,8 @@ int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, co
   return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
 }
 
+int64_t ca_resynth_truncated_frames(const ca_ctx* ctx) { return ctx ? ctx->rt_truncated_frames : 0; }
+
 int ca_oscbank_render_tracks(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, ca_stream stream) {
   if (!ctx) return CA_ERR_INVALID;
   DeviceGuard guard(ctx);

@@ -37,6 +37,8 @@ struct ca_ctx {
   // ca_resynth_roundtrip_host / ca_vocoder_host call never disturbs what ca_stft_analyze was planned for
   ca::StftPlan plan_user, plan_rt, plan_voc;
 
+  int64_t rt_truncated_frames = 0;  // last round trip: frames with more peaks than stft.max_peaks (ca_resynth_truncated_frames)
+
   // generic FFT scratch (twiddle tables, four-step buffers)
   float2* d_fft_tw = nullptr;
   int fft_tw_n = 0;

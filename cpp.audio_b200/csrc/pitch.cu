@@ -36,9 +36,10 @@ struct PrefixArgs {
   const R* peak_off;         // R = float (float32 analysis kernels) or double (stft64.cu)
   const R* peak_db;
   const int32_t* peak_count; // [rows]
-  Tuned* tuned;              // [rows][P]
+  Tuned* tuned;              // [rows][PT]
   int32_t* tcount;           // [rows]
   int64_t rows;
+  unsigned long long* truncated;  // frames whose raw or tuned list did not fit its capacity
 };
 
 template <class R>
@@ -46,8 +47,10 @@ __global__ void __launch_bounds__(128) pitch_prefix_kernel(const __grid_constant
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= a.rows) return;
   const int P = a.p.P;
-  const int cnt = min(a.peak_count[r], P);
-  a.tcount[r] = pitch_prefix(a.p, a.peak_bin + r * P, a.peak_off + r * P, a.peak_db + r * P, cnt, a.tuned + r * P);
+  const int found = a.peak_count[r];
+  int cut = found > P ? 1 : 0;
+  a.tcount[r] = pitch_prefix(a.p, a.peak_bin + r * P, a.peak_off + r * P, a.peak_db + r * P, min(found, P), a.tuned + r * a.p.PT, &cut);
+  if (cut) atomicAdd(a.truncated, 1ull);
 }
 
 struct TrackArgs {
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
   const bool is_tracker = role == 0;
   const unsigned lt = lanemask_lt();
   const int64_t s = blockIdx.x;
-  const int P = p.P;
+  const int P = p.PT;  // entries per frame of the tuned lists
   const double dtrack = p.max_track;
   const Tuned* tu_base = a.tuned + s * p.frames * P;
   const int n_staged = min(P, 32);
@@ -705,20 +708,20 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
 // `needed` receives the number of segments the allocator handed out; when it exceeds seg_capacity the tiles past the
 // capacity carry no segments and the caller re-runs with a larger buffer.
 int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
-                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
+                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
                           int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters) {
-  if (p.P > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_peaks above 256 is not supported by the device pitch pipeline");
+  if (p.PT > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: more than 256 tuned entries per frame are not supported by the device pitch pipeline");
   if (p.max_channels > kMaxNotes) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_channels above 256 is not supported");
   const int64_t rows = n_streams * p.frames;
   if (rows == 0) return CA_OK;
   if (run_prefix) {
     if (peaks_f64) {
-      PrefixArgs<double> pa{p, d_peak_bin, static_cast<const double*>(d_peak_off), static_cast<const double*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows};
+      PrefixArgs<double> pa{p, d_peak_bin, static_cast<const double*>(d_peak_off), static_cast<const double*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
       pitch_prefix_kernel<double><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
     } else {
-      PrefixArgs<float> pa{p, d_peak_bin, static_cast<const float*>(d_peak_off), static_cast<const float*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows};
+      PrefixArgs<float> pa{p, d_peak_bin, static_cast<const float*>(d_peak_off), static_cast<const float*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
       pitch_prefix_kernel<float><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
     }
     CA_CUDA_OK(ctx, cudaGetLastError());

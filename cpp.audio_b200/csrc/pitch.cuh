@@ -27,7 +27,9 @@ constexpr int kMaxTuned = 256;   // peak capacity per frame of the device pipeli
 
 // Everything the pipeline needs, resolved once on the host.
 struct PitchParams {
-  int32_t W, hop, sr, P;       // P: entries per frame of the peak / tuned arrays
+  int32_t W, hop, sr, P;       // P: entries per frame of the peak arrays (capacity of a frame's raw peak list)
+  int32_t PT;                  // entries per frame of the tuned arrays: min(stft.max_peaks, kMaxTuned)
+  int32_t cap_raw;             // peaks the analysis keeps per frame (= P, except in the host form, which compacts the lists)
   double bin_hz;
   float nearby, min_volume, max_track, gain, stereo_spread;
   int32_t A, H, D, R;          // AHDSREnvelopeBase::setAHDSR (include/audioelement.h:923-952)
@@ -54,6 +56,9 @@ inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_s
   p.hop = prm.stft.hop;
   p.sr = prm.stft.sample_rate;
   p.P = peak_stride;
+  p.cap_raw = peak_stride;
+  p.PT = prm.stft.max_peaks < kMaxTuned ? prm.stft.max_peaks : kMaxTuned;
+  if (p.PT < 1) p.PT = 1;
   p.bin_hz = static_cast<double>(p.sr) / ca_fft_length_for(p.W, 1);
   p.nearby = prm.nearby_distance_tones;
   p.min_volume = prm.min_volume;
@@ -78,7 +83,7 @@ inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_s
                   o.harmonize_post_autotune != 0.f || o.autotune != CA_AUTOTUNE_NONE)
                      ? 1
                      : 0;
-  p.tcap = prm.stft.max_peaks;
+  p.tcap = p.PT;
   p.shift_pre = o.shift_pre_autotune;
   p.harm_pre = o.harmonize_pre_autotune;
   p.shift_post = o.shift_post_autotune;
@@ -249,8 +254,9 @@ static_assert(sizeof(Tuned) == 32 && sizeof(PV) == 16, "a Tuned row holds two (p
 // R: float (peak lists of the float32 analysis kernels) or double (stft64.cu).
 template <bool OPTS, class R>
 CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, const R* peak_off, const R* peak_db, int cnt,
-                                Tuned* out) {
+                                Tuned* out, int* cut) {
   int T = 0;
+  const int room = p.PT;  // entries of `out`; what does not fit is dropped and counted in *cut
   bool open = false;
   double mn = 0, mx = 0, sv = 0, spv = 0;
   unsigned char* raw = reinterpret_cast<unsigned char*>(out);
@@ -258,13 +264,16 @@ CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, c
     if (open && !(sv < p.min_volume)) {
       const double pitch = spv / sv;
       if (OPTS) {
-        pv_st(raw, T++, PV{pitch, sv});
+        if (T < room) pv_st(raw, T++, PV{pitch, sv});
+        else ++*cut;
       } else if (T > 0 && fabs(out[T - 1].pitch - pitch) < 0.0001f) {
         out[T - 1].vol += sv;
-      } else {
+      } else if (T < room) {
         out[T].pitch = pitch;
         out[T].vol = sv;
         ++T;
+      } else {
+        ++*cut;
       }
     }
     open = false;
@@ -327,9 +336,9 @@ CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, c
 
 template <class R>
 CA_HD inline int pitch_prefix(const PitchParams& p, const int32_t* peak_bin, const R* peak_off, const R* peak_db, int cnt,
-                              Tuned* out) {
-  return p.opt_active ? pitch_prefix_t<true, R>(p, peak_bin, peak_off, peak_db, cnt, out)
-                      : pitch_prefix_t<false, R>(p, peak_bin, peak_off, peak_db, cnt, out);
+                              Tuned* out, int* cut) {
+  return p.opt_active ? pitch_prefix_t<true, R>(p, peak_bin, peak_off, peak_db, cnt, out, cut)
+                      : pitch_prefix_t<false, R>(p, peak_bin, peak_off, peak_db, cnt, out, cut);
 }
 
 struct Note {
@@ -541,7 +550,7 @@ namespace ca {
 // pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track3_kernel, three warps per stream)
 // d_peak_off / d_peak_db: float arrays, or double arrays when peaks_f64 is set (the FP64 analysis of stft64.cu)
 int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
-                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
+                          const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
                           int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters = true);

@@ -51,6 +51,7 @@ struct StreamResult {
   std::vector<int64_t> tile_n0;         // first sample of the tile (stream-relative)
   std::vector<int32_t> tile_len;
   int64_t notes_started = 0, notes_dropped = 0;
+  int64_t truncated = 0;  // frames whose raw or tuned list did not fit its capacity
 };
 
 // The host form of the pipeline (A/B against the device kernels of pitch.cu; host_threads != 0 selects it).
@@ -74,7 +75,9 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
     const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;  // events of frame k act from this sample on
     const int len_frame = static_cast<int>(std::min<int64_t>(p.hop, p.n_samples - n_k));
     // ---------------- stateless prefix (source/rt.resynth.lib.algo.cpp:10-230) ----------------
-    const int T = pitch_prefix(p, peak_bin + k * P, peak_off + k * P, peak_db + k * P, std::min(peak_count[k], P), tuned.data());
+    int cut = peak_count[k] > p.cap_raw ? 1 : 0;
+    const int T = pitch_prefix(p, peak_bin + k * P, peak_off + k * P, peak_db + k * P, std::min(peak_count[k], P), tuned.data(), &cut);
+    res.truncated += cut != 0;
     // ---------------- tracking (greedy, monotone in pitch) ----------------
     change.assign(T, -1);
     keep.assign(played.size(), 0);
@@ -181,8 +184,8 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
   const size_t out_bytes = sizeof(float) * 2 * total;
   const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
   const size_t b_tiles = (3 * sizeof(int64_t) + sizeof(int32_t)) * static_cast<size_t>(n_tiles);
-  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 16;  // stats, allocator counter, overflow flag
-  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * P);
+  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 24;  // stats, allocator counter, overflow flag, truncated frames
+  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * pp.PT);
   if (!rc) rc = ensure_scratch(ctx, 9, sizeof(int32_t) * rows);
   if (!rc) rc = ensure_scratch(ctx, 10, b_misc);
   if (!rc) rc = ensure_scratch(ctx, 1, b_tiles);
@@ -198,11 +201,13 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
   int64_t* d_stats = static_cast<int64_t*>(ctx->d_scratch[10]);
   unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(d_stats + 2 * n_streams);
   int32_t* d_overflow = reinterpret_cast<int32_t*>(d_counter + 1);
+  unsigned long long* d_trunc = d_counter + 2;
   int64_t* h_misc = static_cast<int64_t*>(ctx->h_pinned[0]);
+  CA_CUDA_OK(ctx, cudaMemsetAsync(d_trunc, 0, sizeof(unsigned long long), st));
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int64_t capacity = static_cast<int64_t>(ctx->scratch_bytes[6] / sizeof(Segment));
     rc = pitch_pipeline_device(ctx, pp, n_streams, static_cast<const int32_t*>(ctx->d_scratch[2]), ctx->d_scratch[3], ctx->d_scratch[4], use64,
-                               static_cast<const int32_t*>(ctx->d_scratch[5]), static_cast<Tuned*>(ctx->d_scratch[8]),
+                               static_cast<const int32_t*>(ctx->d_scratch[5]), d_trunc, static_cast<Tuned*>(ctx->d_scratch[8]),
                                static_cast<int32_t*>(ctx->d_scratch[9]), static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps,
                                d_begin, d_end, d_s0, d_len, d_stats, d_counter, d_overflow, attempt == 0, st);
     if (rc) return rc;
@@ -251,6 +256,7 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
     if (rc) return rc;
   }
   if (h_stats) memcpy(h_stats, h_misc, sizeof(int64_t) * 2 * n_streams);
+  ctx->rt_truncated_frames = h_misc[2 * n_streams + 2];
   return CA_OK;
 }
 
@@ -266,8 +272,8 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   const size_t rows = static_cast<size_t>(frames) * n_streams, total = static_cast<size_t>(n_streams) * n_samples;
   const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
   const size_t b_tiles = (3 * sizeof(int64_t) + sizeof(int32_t)) * static_cast<size_t>(n_tiles);
-  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 16;  // stats, allocator counter, overflow flag
-  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * P);
+  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 24;  // stats, allocator counter, overflow flag, truncated frames
+  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * pp.PT);
   if (!rc) rc = ensure_scratch(ctx, 9, sizeof(int32_t) * rows);
   if (!rc) rc = ensure_scratch(ctx, 10, b_misc);
   if (!rc) rc = ensure_scratch(ctx, 1, b_tiles);
@@ -300,7 +306,8 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   // the allocator counter and the overflow flag are shared by the groups: reset once, before any group starts
   cudaStream_t s0 = ctx->pipe_streams[0];
   cudaEvent_t ready = nullptr;
-  CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, 16, s0));
+  unsigned long long* d_trunc = d_counter + 2;
+  CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, 24, s0));
   CA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   CA_CUDA_OK(ctx, cudaEventRecord(ready, s0));
   for (int g = 0; g < groups && !rc; ++g) {
@@ -317,7 +324,7 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
       rc = stft_analyze(ctx, ctx->plan_rt, d_x + x0, n_samples, ns, n_samples, nullptr, 0, d_pbin + r0 * P, reinterpret_cast<float*>(d_poff + r0 * P * esz),
                         reinterpret_cast<float*>(d_pdb + r0 * P * esz), d_pcnt + r0, sg);
     if (rc) break;
-    rc = pitch_pipeline_device(ctx, pp, ns, d_pbin + r0 * P, d_poff + r0 * P * esz, d_pdb + r0 * P * esz, use64, d_pcnt + r0, d_tuned + r0 * P, d_tcount + r0,
+    rc = pitch_pipeline_device(ctx, pp, ns, d_pbin + r0 * P, d_poff + r0 * P * esz, d_pdb + r0 * P * esz, use64, d_pcnt + r0, d_trunc, d_tuned + r0 * pp.PT, d_tcount + r0,
                                static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps, d_begin + t0, d_end + t0, d_s0 + t0, d_len + t0,
                                d_stats + 2 * a0, d_counter, d_overflow, true, sg, false);
     if (rc) break;
@@ -340,6 +347,7 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   *needed = h_misc[2 * n_streams];
   *overflowed = *reinterpret_cast<const int32_t*>(h_misc + 2 * n_streams + 1) != 0;
   if (!*overflowed && h_stats) memcpy(h_stats, h_misc, sizeof(int64_t) * 2 * n_streams);
+  ctx->rt_truncated_frames = h_misc[2 * n_streams + 2];
   return CA_OK;
 }
 
@@ -354,6 +362,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
     return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: LINEAR envelopes only (as rt.resynth.lib.cpp:75-81)");
   if (prm.max_channels <= 0) prm.max_channels = 254;
   if (prm.stft.max_peaks <= 0) prm.stft.max_peaks = 200;
+  if (prm.stft.max_peaks > 16384) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_resynth_roundtrip_host: stft.max_peaks above 16384");
   {
     const ca_pitch_options& o = prm.opts;
     if (o.autotune != CA_AUTOTUNE_NONE && o.autotune != CA_AUTOTUNE_TABLE && o.autotune != CA_AUTOTUNE_SCALE)
@@ -383,6 +392,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   const int W = prm.stft.window, hop = prm.stft.hop, P = prm.stft.max_peaks;
   const int64_t frames = ca_stft_num_frames(n_samples, W, hop);
   const size_t total = static_cast<size_t>(n_streams) * n_samples;
+  ctx->rt_truncated_frames = 0;
   if (total == 0) return CA_OK;
   const size_t rows = static_cast<size_t>(frames) * n_streams;
   static const bool timing = getenv("CA_RT_TIMING") != nullptr;  // stage times on stderr (profiles/time_roundtrip.py)
@@ -459,7 +469,8 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   lap("analysis (H2D, K2, D2H peaks)");
 
   // ---- 2. pitch pipeline on host threads, one stream at a time per thread ----
-  const PitchParams pp = make_pitch_params(prm, n_samples, frames, PS);
+  PitchParams pp = make_pitch_params(prm, n_samples, frames, PS);
+  pp.cap_raw = P;  // the lists were compacted to PS entries per frame; the analysis kept at most P
   std::vector<StreamResult> results(n_streams);
   int nt = prm.host_threads > 0 ? prm.host_threads : static_cast<int>(std::thread::hardware_concurrency());
   nt = std::max(1, std::min<int>(nt, static_cast<int>(std::max<int64_t>(n_streams, 1))));
@@ -512,6 +523,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
       h_stats[2 * s + 1] = r.notes_dropped;
     }
   });
+  for (const auto& r : results) ctx->rt_truncated_frames += r.truncated;
   tile_begin[n_tiles] = n_segs;
   lap("flatten segments");
 

@@ -7,6 +7,9 @@
 // argument meaning, so host code written against the reference shapes compiles against them:
 //
 //   ca_host::SqMagFftOperation<Window::Gaussian, double>   ~ rtresynth::SqMagFftOperation  (periodicfft.cpp:251-325)
+//   ca_host::FftOperation<double>                          ~ rtresynth::FftOperation       (periodicfft.cpp:183-244; consumed as
+//                                                            PeriodicFFT<FftOperation<double>> by the vocoder's carrier,
+//                                                            source/rt.resynth.lib.vocoder.cpp:544)
 //   ca_host::PeriodicFFT<Op>                               ~ rtresynth::PeriodicFFT<Op>    (periodicfft.cpp:13-181)
 //   ca_host::FrequenciesSqMag<T>, FreqMag<T>               ~ the cpp.algorithms result types used at
 //                                                            source/rt.resynth.lib.cpp:1579-1595
@@ -20,7 +23,9 @@
 // Everything here is header-only C++17 and needs only include/cpp_audio_b200.h + libcpp_audio_b200.so (no CUDA headers).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <functional>
 #include <stdexcept>
@@ -95,7 +100,31 @@ struct SqMagFftOperation {
 
   Result const& get_results() const { return result_; }
 
-  // used by PeriodicFFT
+  // ---- used by PeriodicFFT: `frames` consecutive frames of `samples` (hop apart) in one GPU call ----
+  template <typename OnFrame>
+  void process_frames(float const* samples, int64_t n, int frames, OnFrame&& on_frame) {
+    int const n_bins = fft_length_ / 2 + 1;
+    int const P = cfg_.max_peaks;
+    bsq_.resize(static_cast<size_t>(frames) * n_bins);
+    pb_.resize(static_cast<size_t>(frames) * P);
+    pf_.resize(pb_.size());
+    pd_.resize(pb_.size());
+    pc_.resize(frames);
+    check(ctx_, ca_stft_analyze_host(ctx_, samples, n, 1, n, bsq_.data(), n_bins, pb_.data(), pf_.data(), pd_.data(), pc_.data()),
+          "ca_stft_analyze_host");
+    batch_result_.fft_length = fft_length_;
+    for (int f = 0; f < frames; ++f) {
+      batch_result_.frequencies_sqmag.assign(bsq_.begin() + static_cast<size_t>(f) * n_bins, bsq_.begin() + static_cast<size_t>(f + 1) * n_bins);
+      found_ = pc_[f];
+      int const stored = found_ < P ? found_ : P;
+      peaks_.resize(stored);
+      for (int i = 0; i < stored; ++i) peaks_[i] = {static_cast<T>(pf_[static_cast<size_t>(f) * P + i]), static_cast<T>(pd_[static_cast<size_t>(f) * P + i])};
+      on_frame(batch_result_);
+    }
+  }
+  std::vector<FreqMag<T>> const& last_peaks() const { return peaks_; }
+  int last_peak_count_found() const { return found_; }
+
   void plan(int window_size, int hop) {
     ca_stft_params p{};
     p.window = window_size;
@@ -118,9 +147,90 @@ struct SqMagFftOperation {
  private:
   ca_ctx* ctx_;
   AnalysisConfig cfg_;
-  int window_ = 0, hop_ = 0, fft_length_ = 0;
-  std::vector<float> staging_, sq_;
-  Result result_;
+  int window_ = 0, hop_ = 0, fft_length_ = 0, found_ = 0;
+  std::vector<float> staging_, sq_, bsq_, pf_, pd_;
+  std::vector<int32_t> pb_, pc_;
+  std::vector<FreqMag<T>> peaks_;
+  Result result_, batch_result_;
+};
+
+// The complex half spectrum of a frame: what the reference keeps in fft::RealFBins_<Tag, T, Alloc>::type, whose packing depends on
+// the FFT backend; here plainly bins 0 .. N/2.
+template <typename T>
+struct RealFBins {
+  std::vector<std::complex<T>> bins;
+  int fft_length = 0;
+  int get_fft_length() const { return fft_length; }
+};
+
+// FftOperation<T> (source/rt.resynth.lib.periodicfft.cpp:183-244): rectangular window (:228), zero padding to the FFT length
+// (:231), forward real FFT, unscaled (:234; fft::Algo_::forward) on K1 (ca_rfft_batched_host).
+template <typename T>
+struct FftOperation {
+  using FPT = T;
+  using Result = RealFBins<T>;
+  static int constexpr zero_padding_factor = 1;
+
+  FftOperation(int reserve_for_max_fft_size, ca_ctx* ctx) : ctx_(ctx) {
+    int const max_fft_length = ca_fft_length_for(reserve_for_max_fft_size, zero_padding_factor);
+    result_.bins.reserve(max_fft_length / 2 + 1);
+    frames_.reserve(max_fft_length);
+    out_.reserve(2 * (max_fft_length / 2 + 1));
+  }
+
+  bool init_data(int const window_size) {  // :192-208: nothing depends on the window but the FFT length
+    int const n = ca_fft_length_for(window_size, zero_padding_factor);
+    if (n < 512 || n > (1 << 20)) throw std::logic_error("FftOperation: fft length must be within 2^9 .. 2^20");
+    window_ = window_size;
+    fft_length_ = n;
+    return false;
+  }
+
+  template <typename It>
+  void operator()(It const& it, It const& end) {
+    frames_.assign(static_cast<size_t>(fft_length_), 0.f);
+    size_t i = 0;
+    for (It p = it; p != end && i < frames_.size(); ++p, ++i) frames_[i] = static_cast<float>(*p);
+    transform(1);
+    take(0, result_);
+  }
+  Result const& get_results() const { return result_; }
+
+  template <typename OnFrame>
+  void process_frames(float const* samples, int64_t n, int frames, OnFrame&& on_frame) {
+    (void)n;
+    frames_.assign(static_cast<size_t>(frames) * fft_length_, 0.f);
+    for (int f = 0; f < frames; ++f)
+      std::copy(samples + static_cast<int64_t>(f) * hop_, samples + static_cast<int64_t>(f) * hop_ + window_, frames_.begin() + static_cast<size_t>(f) * fft_length_);
+    transform(frames);
+    for (int f = 0; f < frames; ++f) {
+      take(f, batch_result_);
+      on_frame(batch_result_);
+    }
+  }
+  void plan(int window_size, int hop) {
+    init_data(window_size);
+    hop_ = hop;
+  }
+  ca_ctx* ctx() const { return ctx_; }
+  int fft_length() const { return fft_length_; }
+
+ private:
+  void transform(int frames) {
+    out_.resize(static_cast<size_t>(frames) * 2 * (fft_length_ / 2 + 1));
+    check(ctx_, ca_rfft_batched_host(ctx_, frames_.data(), fft_length_, frames, out_.data()), "ca_rfft_batched_host");
+  }
+  void take(int f, Result& r) const {
+    int const nb = fft_length_ / 2 + 1;
+    r.bins.resize(nb);
+    r.fft_length = fft_length_;
+    float const* o = out_.data() + static_cast<size_t>(f) * 2 * nb;
+    for (int k = 0; k < nb; ++k) r.bins[k] = {static_cast<T>(o[2 * k]), static_cast<T>(o[2 * k + 1])};
+  }
+  ca_ctx* ctx_;
+  int window_ = 0, hop_ = 1, fft_length_ = 0;
+  std::vector<float> frames_, out_;
+  Result result_, batch_result_;
 };
 
 template <typename FftOperation>
@@ -165,33 +275,15 @@ struct PeriodicFFT {
 
   void reset_samples() { pending_.clear(); }
 
-  std::vector<FreqMag<FPT>> const& last_peaks() const { return peaks_; }
-  int last_peak_count_found() const { return found_; }
-  auto const& getResults() const { return result_; }
+  // the peak list of the frame the callback is being called for (SqMagFftOperation only)
+  auto const& last_peaks() const { return fft_op.last_peaks(); }
+  int last_peak_count_found() const { return fft_op.last_peak_count_found(); }
 
  private:
   int64_t needed_for(int frames) const { return static_cast<int64_t>(window_) + static_cast<int64_t>(frames - 1) * hop_; }
 
   void process(int frames) {
-    int const n_bins = fft_op.fft_length() / 2 + 1;
-    int const P = fft_op.config().max_peaks;
-    int64_t const n = needed_for(frames);
-    sq_.resize(static_cast<size_t>(frames) * n_bins);
-    pb_.resize(static_cast<size_t>(frames) * P);
-    pf_.resize(pb_.size());
-    pd_.resize(pb_.size());
-    pc_.resize(frames);
-    check(fft_op.ctx(), ca_stft_analyze_host(fft_op.ctx(), pending_.data(), n, 1, n, sq_.data(), n_bins, pb_.data(), pf_.data(), pd_.data(), pc_.data()),
-          "ca_stft_analyze_host");
-    result_.fft_length = fft_op.fft_length();
-    for (int f = 0; f < frames; ++f) {
-      result_.frequencies_sqmag.assign(sq_.begin() + static_cast<size_t>(f) * n_bins, sq_.begin() + static_cast<size_t>(f + 1) * n_bins);
-      found_ = pc_[f];
-      int const stored = found_ < P ? found_ : P;
-      peaks_.resize(stored);
-      for (int i = 0; i < stored; ++i) peaks_[i] = {static_cast<FPT>(pf_[static_cast<size_t>(f) * P + i]), static_cast<FPT>(pd_[static_cast<size_t>(f) * P + i])};
-      on_fft_result(hop_, result_);
-    }
+    fft_op.process_frames(pending_.data(), needed_for(frames), frames, [this](Result const& r) { on_fft_result(hop_, r); });
     // keep the overlap: the next frame starts `frames * hop` samples later (periodicfft.cpp:167-172)
     int64_t const consumed = static_cast<int64_t>(frames) * hop_;
     if (consumed >= static_cast<int64_t>(pending_.size())) pending_.clear();
@@ -209,11 +301,8 @@ struct PeriodicFFT {
   OnFftResult on_fft_result;
   GetWindowSizeFunc get_window_size;
   GetWindowCenterStrideFramesFunc get_window_center_stride_frames;
-  int window_ = 0, hop_ = 1, batch_frames_ = 64, found_ = 0;
-  std::vector<float> pending_, sq_, pf_, pd_;
-  std::vector<int32_t> pb_, pc_;
-  std::vector<FreqMag<FPT>> peaks_;
-  Result result_;
+  int window_ = 0, hop_ = 1, batch_frames_ = 64;
+  std::vector<float> pending_;
 };
 
 }  // namespace ca_host

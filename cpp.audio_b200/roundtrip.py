@@ -37,6 +37,11 @@ def resynth_roundtrip(ctx: Context, x: np.ndarray, window: int = 4096, hop: int 
     return out, stats
 
 
+def truncated_frames(ctx: Context) -> int:
+    """Frames of the last round trip whose peak list exceeded max_peaks (ca_resynth_truncated_frames); 0 = nothing was cut."""
+    return int(lib().ca_resynth_truncated_frames(ctx.handle))
+
+
 def pitch_options(shift_pre=0.0, harmonize_pre=0.0, shift_post=0.0, harmonize_post=0.0, allowed_pitches=None, scale=None,
                   scale_root_pitch=0.0, max_pitch=151.0, tolerance=0.0) -> PitchOptions:
     """ca_pitch_options. allowed_pitches (ascending float64): the vector mkAutotuneFunction builds for AutotuneType::Chord /

@@ -168,8 +168,8 @@ int ca_oscbank_render_host(ca_ctx* ctx, const ca_oscbank_desc* desc, float* h_ou
  * into NoteOn / NoteChange / NoteOff on a pool of ResynthElement voices (:5-18: StereoPanned<VolumeAdjusted<Enveloped<
  * FreqCtrl_<SineOscillatorAlgo, InterpolatedFreq>, AHDSREnvelope>>>) whose output is the resynthesised audio.
  * Analysis, the pitch pipeline (frame-sequential per stream: one CTA per stream walks its frames) and voice rendering all run on
- * the GPU; only the audio crosses PCIe. Events of frame k act from sample window-1 + k*hop on. max_peaks and max_channels are
- * limited to 256 on this path. */
+ * the GPU; only the audio crosses PCIe. Events of frame k act from sample window-1 + k*hop on. max_channels is limited to 256 on
+ * this path, stft.max_peaks to 16384; see ca_resynth_truncated_frames. */
 /* Optional stages of RtResynth::step between reduce_pitches and track_pitches (source/rt.resynth.lib.cpp:1687-1707):
  * shift_pitches / harmonize_pitches (source/rt.resynth.lib.algo.cpp:307-371) before and after autotune_pitches (:186-229).
  * All zero = rt.resynth out of the box (pitch_shift_* = pitch_harmonize_* = 0, use_autotune = false). The transform of
@@ -207,6 +207,14 @@ typedef struct ca_roundtrip_params {
  * notes started, notes dropped (pool full). */
 int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
                               int64_t n_streams, float* h_out, int64_t* h_stats);
+
+/* Frames of the last ca_resynth_roundtrip_host call on this ctx that lost something to a capacity: more than stft.max_peaks
+ * peaks (only the first max_peaks, in ascending frequency, took part), or more than 256 entries left after aggregation and the
+ * min_volume cut (the device pitch pipeline's list; the voice pool has 254 channels). The reference's lists are unbounded
+ * (reserve(200) at rt.resynth.lib.cpp:1102 is a reserve, not a cap), so a non-zero value means the result is NOT what the
+ * reference computes. stft.max_peaks = n_fft/4 can never overflow (a spectrum has at most that many strict local maxima); it
+ * costs 20 bytes of scratch per peak and frame. */
+int64_t ca_resynth_truncated_frames(const ca_ctx* ctx);
 
 /* ---- a note schedule on the rt.resynth voice pool -------------------------------------------------------------------
  * Stands in for ImplCRTP::onEvent + ImplCRTP::compute (include/gen.crtp.h:382-622, :350-378) of the synth rt.resynth drives

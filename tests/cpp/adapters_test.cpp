@@ -101,6 +101,43 @@ static void test_periodic_fft(ca_ctx* ctx) {
   std::printf("OK sqmag_operator max|X|err=%.3g\n", e2);
 }
 
+// PeriodicFFT<FftOperation<double>>, the vocoder carrier's analysis (source/rt.resynth.lib.vocoder.cpp:544): frames of 2 * stride
+// samples every stride, rectangular window, zero padded to the FFT length, complex bins.
+static void test_fft_operation(ca_ctx* ctx) {
+  using namespace ca_host;
+  int const W = 482, hop = 241, n = 20000;  // the vocoder's default stride at 48 kHz -> 512-point frames
+  auto x = harmonic_tone(n, 330.0, 48000);
+  std::vector<std::vector<std::complex<double>>> ref;
+  orc::PeriodicFft<orc::FftOp<double>> opf;
+  opf.set_lambdas([&] { return W; }, [&] { return hop; }, [&](int, const std::vector<std::complex<double>>& b) { ref.push_back(b); });
+  for (float s : x) opf.feed(s);
+  PeriodicFFT<FftOperation<double>> pf(1 << 10, ctx);
+  pf.set_batch_frames(16);
+  size_t frame = 0;
+  double err = 0, peak = 0;
+  pf.setLambdas([&] { return W; }, [&] { return hop; }, [&](int const stride, RealFBins<double> const& r) {
+    EXPECT(stride == hop && r.get_fft_length() == 512 && r.bins.size() == 257, "shape");
+    if (frame < ref.size())
+      for (size_t k = 0; k < r.bins.size(); ++k) {
+        err = std::max(err, std::abs(r.bins[k] - ref[frame][k]));
+        peak = std::max(peak, std::abs(ref[frame][k]));
+      }
+    ++frame;
+  });
+  for (float s : x) pf.feed(s);
+  pf.flush();
+  EXPECT(frame == ref.size() && frame > 70, "frames %zu vs %zu", frame, ref.size());
+  EXPECT(err < 1e-5 * peak, "bins error %g (peak %g)", err, peak);   // unscaled transform: relative to the largest bin
+  FftOperation<double> op(1 << 10, ctx);
+  op.init_data(W);
+  std::vector<double> f0(x.begin(), x.begin() + W);
+  op(f0.begin(), f0.end());
+  double e2 = 0;
+  for (size_t k = 0; k < ref[0].size(); ++k) e2 = std::max(e2, std::abs(op.get_results().bins[k] - ref[0][k]));
+  EXPECT(e2 < 1e-5 * peak, "operator() error %g", e2);
+  std::printf("OK fft_operation frames=%zu max bin err=%.3g (largest bin %.3g)\n", frame, err, peak);
+}
+
 static void test_sine_bank(ca_ctx* ctx) {
   using namespace ca_host;
   int const sr = 48000, n = 40000, np = 8;
@@ -217,6 +254,7 @@ int main() {
     return 2;
   }
   test_periodic_fft(ctx);
+  test_fft_operation(ctx);
   test_sine_bank(ctx);
   test_resynth_synth(ctx);
   ca_destroy(ctx);

@@ -42,7 +42,8 @@ int main() {
   prm.max_channels = 254;
   const ca::PitchParams pp = ca::make_pitch_params(prm, 48000, 172, P);
   std::vector<ca::Tuned> row(tcap > P ? tcap : P);
-  const int T = ca::pitch_prefix(pp, bin.data(), off.data(), db.data(), cnt, row.data());
+  int cut = 0;
+  const int T = ca::pitch_prefix(pp, bin.data(), off.data(), db.data(), cnt, row.data(), &cut);
   printf("%d\n", T);
   for (int i = 0; i < T; ++i) printf("%.17g %.17g %.9g %.17g %d\n", row[i].pitch, row[i].vol, row[i].volume, row[i].ai, row[i].min_change);
   return 0;

@@ -122,10 +122,25 @@ def test_device_pitch_pipeline_wide_tracking_window(pkg, ctx, wl):
 
 def test_device_pitch_pipeline_limits(pkg, ctx):
     x = np.zeros((1, 8192), np.float32)
+    pkg.resynth_roundtrip(ctx, x, max_peaks=1024)        # n_fft/4: every local maximum of a frame fits
     with pytest.raises(Exception):
-        pkg.resynth_roundtrip(ctx, x, max_peaks=300)
+        pkg.resynth_roundtrip(ctx, x, max_peaks=20000)
     with pytest.raises(Exception):
         pkg.resynth_roundtrip(ctx, x, max_channels=300)
+
+
+def test_peak_capacity_beyond_the_tuned_list(pkg, orc, ctx, wl):
+    """With stft.max_peaks = n_fft/4 the weak ripples of the window's side lobes all reach the pitch pipeline (hundreds per frame,
+    as in the reference, whose peak list is unbounded); min_volume removes them and the result equals the oracle's, which
+    thresholds nothing either (min_db = -inf)."""
+    x = wl.c4_streams(2, 1.0)
+    out, stats = pkg.resynth_roundtrip(ctx, x, min_db=-np.inf, max_peaks=1024)
+    assert pkg.truncated_frames(ctx) == 0
+    ref, rstats = orc.roundtrip(x, min_db=-np.inf)
+    assert np.array_equal(stats, rstats)
+    assert np.abs(out - ref).max() < 1e-5
+    pkg.resynth_roundtrip(ctx, x, min_db=-np.inf, max_peaks=64)
+    assert pkg.truncated_frames(ctx) > 0                 # 64 slots do not hold them: reported
 
 
 def test_full_length_streams_against_oracle(pkg, orc, ctx, wl):

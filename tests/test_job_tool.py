@@ -148,7 +148,7 @@ def test_job_output_equals_the_library_call(tool, tmp_path, pkg, ctx, wl):
     n = x.shape[1] + sr + 4096
     xp = np.zeros((2, n), np.float32)
     xp[:, :x.shape[1]] = x
-    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, stereo_spread=0.5, gain=0.8)
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, max_peaks=1024, stereo_spread=0.5, gain=0.8)
     for i in range(2):
         y, sr_out = read_wav_f32(tmp_path / f"out{i}.wav")
         assert sr_out == sr and y.shape == (x.shape[1] + sr, 2)
@@ -181,7 +181,7 @@ def test_job_with_carrier_adds_the_vocoder_mix(tool, tmp_path, pkg, ctx, wl):
     cp = np.zeros((1, n), np.float32)
     m = min(n, car.shape[0])
     cp[0, :m] = car[:m]
-    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, gain=0.5)
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, max_peaks=1024, gain=0.5)
     mix = pkg.vocoder(ctx, xp, cp, sample_rate=sr, modulator_window_seconds=0.04, stride_seconds=0.01, count_bands=12, min_freq=80.0,
                       max_freq=6000.0, vol_modulator=0.2, vol_carrier=0.1, vol_vocoder=1.5)
     y, _ = read_wav_f32(tmp_path / "out.wav")
@@ -214,9 +214,33 @@ def test_job_with_autotune_preset_equals_the_library_call(tool, tmp_path, pkg, c
     xp[0, :x.shape[0]] = x
     allowed = np.sort(np.array([72.0 + i + 12 * o for o in range(-5, 6) for i in (0, 4, 7)]))
     opts = pkg.pitch_options(shift_pre=-0.25, harmonize_post=7.0, allowed_pitches=allowed, max_pitch=100.0, tolerance=1.5)
-    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, opts=opts)
-    plain, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf)
+    ref, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, max_peaks=1024, opts=opts)
+    plain, _ = pkg.resynth_roundtrip(ctx, xp, window=4096, hop=256, min_db=-np.inf, max_peaks=1024)
     y, _ = read_wav_f32(tmp_path / "out.wav")
     assert np.abs(y).max() > 0.05
     assert np.array_equal(y, ref[0, :y.shape[0]])
     assert np.abs(ref - plain).max() > 0.05
+
+
+@pytest.mark.gpu
+def test_truncation_is_reported(pkg, ctx, tool, tmp_path):
+    """White noise: thousands of peaks per frame. With the capacity the tool uses (n_fft/4: every local maximum fits) nothing is
+    cut at the peak level; more than 256 pitches above min_volume per frame are, the library counts those frames
+    (ca_resynth_truncated_frames) and the tool refuses to write a result the reference would not produce, unless it is told to."""
+    rng = np.random.default_rng(9)
+    x = (0.3 * rng.standard_normal(30000)).astype(np.float32)
+    pkg.resynth_roundtrip(ctx, x[None, :], window=8706, hop=4320, min_db=-np.inf, max_peaks=200)
+    assert pkg.truncated_frames(ctx) > 0          # 200 slots for ~2700 peaks
+    pkg.resynth_roundtrip(ctx, x[None, :], window=8706, hop=4320, min_db=-np.inf, max_peaks=4096, nearby_distance_tones=0.01)
+    assert pkg.truncated_frames(ctx) > 0          # every peak fits, but far more than 256 pitches are audible
+    pkg.resynth_roundtrip(ctx, 1e-5 * x[None, :], window=8706, hop=4320, min_db=-np.inf, max_peaks=4096)
+    assert pkg.truncated_frames(ctx) == 0         # the same peaks below min_volume: nothing reaches a capacity
+    voice = tmp_path / "noise.wav"
+    write_wav(str(voice), x, 48000)
+    dst = tmp_path / "noise_out.wav"
+    pre = tmp_path / "p.json"
+    pre.write_text(json.dumps(preset(nearby_distance_tones=0.01)))
+    r = subprocess.run([tool, "--voice", str(voice), "--out", str(dst), "--preset", str(pre)], capture_output=True, text=True)
+    assert r.returncode == 3 and "pitches" in r.stderr and not dst.exists()
+    r = subprocess.run([tool, "--allow-truncation", "--voice", str(voice), "--out", str(dst), "--preset", str(pre)], capture_output=True, text=True)
+    assert r.returncode == 0 and dst.exists()

@@ -101,9 +101,12 @@ Derived derive(const mini_json::Value* preset, int sample_rate) {
   p.stft.window_type = CA_WINDOW_GAUSSIAN;
   p.stft.sigma_factor = 4.f;  // periodicfft.cpp:288
   p.stft.sample_rate = sample_rate;
-  p.stft.min_db = -INFINITY;  // the reference thresholds on volume (min_volume), not on the spectrum
-  p.stft.max_peaks = 200;     // reserve of rt.resynth.lib.cpp:1102
   p.min_volume = preset_float(preset, "min_volume", 0.0001f);
+  // The reference thresholds on volume (reduce_pitches, rt.resynth.lib.algo.cpp:166-184), not on the spectrum, and its peak list
+  // is unbounded (reserve(200) at rt.resynth.lib.cpp:1102 grows): a spectrum of n_fft points has at most n_fft/4 strict local
+  // maxima, so that capacity never cuts a list.
+  p.stft.min_db = -INFINITY;
+  p.stft.max_peaks = std::max(200, ca_fft_length_for(d.window, 1) / 4);
   p.nearby_distance_tones = preset_float(preset, "nearby_distance_tones", 0.4f);
   p.max_track_pitches = preset_float(preset, "max_track_pitches", 1.f);
   p.stereo_spread = preset_float(preset, "stereo_spread", 1.f);
@@ -226,7 +229,7 @@ bool vocoder_active(const Derived& d, bool has_carrier) {
 int main(int argc, char** argv) {
   try {
     std::vector<Job> jobs;
-    bool dry = false;
+    bool dry = false, allow_truncation = false;
     Job cli;
     for (int i = 1; i < argc; ++i) {
       const std::string a = argv[i];
@@ -235,6 +238,7 @@ int main(int argc, char** argv) {
         return argv[++i];
       };
       if (a == "--dry-run") dry = true;
+      else if (a == "--allow-truncation") allow_truncation = true;
       else if (a == "--voice") cli.voice_file = next();
       else if (a == "--out") cli.output_file = next();
       else if (a == "--preset") cli.preset_file = next();
@@ -243,7 +247,7 @@ int main(int argc, char** argv) {
     }
     if (!cli.voice_file.empty()) jobs.push_back(cli);
     if (jobs.empty()) {
-      std::fprintf(stderr, "usage: rt_resynth_job [--dry-run] job.json... | --voice in.wav --out out.wav [--preset p.json] [--post none|limit]\n");
+      std::fprintf(stderr, "usage: rt_resynth_job [--dry-run] [--allow-truncation] job.json... | --voice in.wav --out out.wav [--preset p.json] [--post none|limit]\n");
       return 2;
     }
     struct Loaded {
@@ -310,6 +314,13 @@ int main(int argc, char** argv) {
       if (int rc = ca_resynth_roundtrip_host(ctx, &prm, x, static_cast<int64_t>(n), static_cast<int64_t>(group.size()), y, stats.data())) {
         std::fprintf(stderr, "ca_resynth_roundtrip_host failed (%d): %s\n", rc, ca_last_error(ctx));
         return 1;
+      }
+      if (const long long cut = static_cast<long long>(ca_resynth_truncated_frames(ctx))) {
+        std::fprintf(stderr,
+                     "rt_resynth_job: %lld analysis frames held more than 256 pitches above min_volume; the excess (highest pitches) was "
+                     "dropped, which the reference would not do. %s\n",
+                     cut, allow_truncation ? "Continuing (--allow-truncation)." : "Raise min_volume in the preset, or pass --allow-truncation.");
+        if (!allow_truncation) return 3;
       }
       // vocoder stage, one call per job that uses it: mixed[n] goes to both channels (rt.resynth.lib.vocoder.cpp:803-810)
       for (size_t g = 0; g < group.size(); ++g) {

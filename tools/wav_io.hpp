@@ -4,6 +4,7 @@
 // one float per frame = the mean of the frame's channels) and writes IEEE-float stereo (:342-356).
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -63,6 +64,9 @@ inline Audio read(const std::string& path) {
     pos = body + len + (len & 1);
   }
   if (!data || !a.channels || !bits) throw std::runtime_error("'" + path + "': missing fmt or data chunk");
+  const bool pcm_ok = format == 1 && (bits == 8 || bits == 16 || bits == 24 || bits == 32);
+  const bool float_ok = format == 3 && (bits == 32 || bits == 64);
+  if (!pcm_ok && !float_ok) throw std::runtime_error("'" + path + "': unsupported sample format");
   const int bytes = bits / 8;
   const size_t n = data_bytes / bytes;
   a.samples.resize(n - n % a.channels);
@@ -107,6 +111,8 @@ inline std::vector<float> as_one_float(const Audio& a) {
 inline void write_float32(const std::string& path, int sample_rate, int channels, const float* interleaved, size_t frames) {
   FILE* f = std::fopen(path.c_str(), "wb");
   if (!f) throw std::runtime_error("cannot create '" + path + "'");
+  if (frames * static_cast<size_t>(channels) * 4 > 0xFFFFFFFFull - 36)
+    throw std::runtime_error("'" + path + "': more than 4 GiB of samples do not fit a RIFF/WAVE header");
   const uint32_t data_bytes = static_cast<uint32_t>(frames * channels * 4);
   unsigned char h[44];
   auto w32 = [&](int o, uint32_t v) { h[o] = v & 255; h[o + 1] = (v >> 8) & 255; h[o + 2] = (v >> 16) & 255; h[o + 3] = (v >> 24) & 255; };
