@@ -31,6 +31,7 @@ SR, WINDOW, HOP, NFFT = 48000, 4096, 256, 4096
 SECONDS = 60.0
 MAX_PEAKS = 32
 MIN_DB = -80.0
+FLOP_PER_FRAME = 5 * NFFT // 2 * 12 + 3 * NFFT // 2  # 2.5 N log2 N for the transform + 3 N/2 for |X|^2: 129,024
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
 
 
@@ -151,6 +152,17 @@ class ClockSampler:
         return out
 
 
+def workload_config(n_gpus: int, streams_per_gpu: int) -> dict:
+    """The `config` object of the JSON line: the WORKLOAD, identical for both arms (the reference arm times a bounded sample of
+    it and says which in cpu_baseline.sample)."""
+    frames = streams_per_gpu * (1 + (int(round(SECONDS * SR)) - WINDOW) // HOP)
+    return {"workload": "C2: rt.resynth periodic-FFT analysis, 60 s mono 48 kHz harmonic tone per stream, window 4096, hop "
+                        "256, Gaussian window (sigma factor 4), |X|^2 spectrum + peak extraction",
+            "streams_per_gpu": streams_per_gpu, "frames_per_step_per_gpu": frames, "window": WINDOW, "hop": HOP, "n_fft": NFFT,
+            "max_peaks": MAX_PEAKS, "min_db": MIN_DB, "parallelism": f"{n_gpus} x independent streams, no data-path collective",
+            "l2": "inputs+outputs per step (0.37 GB + 2.9 GB) exceed the 126 MB L2; no flush needed"}
+
+
 def cpu_analysis_rate(orc, wl, threads: int, streams: int, seconds: float):
     """frames/s of the CPU oracle (the reference's structure: per-sample feed, double precision, one FFT per hop, peak
     extraction per frame) over `streams` independent streams of `seconds` each on `threads` host threads."""
@@ -189,10 +201,10 @@ def run_reference(args):
         "impl": "reference", "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: rt.resynth periodic-FFT analysis, 48 kHz harmonic tone, window 4096, hop 256, Gaussian "
-                               "window, peak extraction (CPU oracle port of the reference, bounded sample)",
-                   "window": WINDOW, "hop": HOP, "n_fft": NFFT, "max_peaks": MAX_PEAKS, "min_db": MIN_DB},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.gpus, args.streams_per_gpu),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": sample + "; the CPU oracle port of the reference (double precision, per-sample feed, one FFT "
+                                            "per hop, peak extraction per frame; the spectrum is computed, not stored)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -294,6 +306,30 @@ def run_ours(args):
     assert int(h_cnt.min()) == 16 and int(h_cnt.max()) == 16
     h2d = x_pinned.numel() * 4
     d2h = (h_bin.numel() + h_freq.numel() + h_db.numel() + h_cnt.numel()) * 4
+
+    # ---- the same call with the spectrum copied back as well (2.9 GB per step: what the device-timed step writes to HBM) ----
+    e2e_sq = None
+    if not args.skip_e2e_spectrum:
+        h_sq = torch.empty((rows, NFFT // 2 + 1), dtype=torch.float32).pin_memory()
+
+        def e2e_sq_step():
+            ctx.check(L.ca_stft_analyze_host(ctx.handle, x_pinned.data_ptr(), n_samples, S, n_samples, h_sq.data_ptr(), NFFT // 2 + 1,
+                                             h_bin.data_ptr(), h_freq.data_ptr(), h_db.data_ptr(), h_cnt.data_ptr()), "ca_stft_analyze_host")
+
+        e2e_sq_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            e2e_sq_step()
+        sq_s = (time.perf_counter() - t0) / 2
+        if world > 1:
+            t = torch.tensor([sq_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sq_s = float(t.item())
+        e2e_sq = {"value": world * rows / sq_s, "unit": "frames/s", "ms_per_step": 1e3 * sq_s, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": d2h + h_sq.numel() * 4,
+                  "note": "peak lists AND the |X|^2 spectrum copied to the host: bound by the device-to-host copy of 8.2 KB per frame"}
+        del h_sq
 
     # ---- final gather of the peak lists over NVLink (reported separately) ----
     gather_ms = None
@@ -422,7 +458,9 @@ def run_ours(args):
             "workload": f"C4 share: {S} streams x {SECONDS:g} s per GPU, pinned host audio in, pinned host stereo audio out",
             "output_samples_per_s": world * S * n_samples / rt_s, "ms_per_call": 1e3 * rt_s,
             "notes_started": int(rt_stats[:, 0].sum()), "h2d_bytes": int(rt_in.nbytes), "d2h_bytes": int(rt_out.nbytes),
-            "note": "analysis, pitch pipeline (three warps per stream pipelined over frames) and rendering all run on the device; only the audio crosses PCIe",
+            "truncated_frames": pkg.truncated_frames(ctx),
+            "note": "analysis (in FP64 on this path: the resynthesised phase integrates the peak frequencies), pitch pipeline (three "
+                    "warps per stream pipelined over frames) and rendering all run on the device; only the audio crosses PCIe",
         }
         # ---- FFT vocoder (source/rt.resynth.lib.vocoder.cpp) at the reference defaults, same streams as the modulator ----
         vc_car = pkg.pinned_empty(x_host_np.shape)
@@ -464,6 +502,7 @@ def run_ours(args):
                "value_1_thread": rate_1t}
 
     peak, peak_src = measured_peaks()
+    fp32_peak_stft = ctx.measure_fp32_peak()
     per_frame = 4 * HOP + 4 * (NFFT // 2 + 1) + 4 + 12 * 16
     achieved = rows * per_frame / (kernel_ms * 1e-3) / 1e9
     noreuse = rows * (4 * WINDOW + 4 * (NFFT // 2 + 1)) / (kernel_ms * 1e-3) / 1e9
@@ -471,19 +510,20 @@ def run_ours(args):
         "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: rt.resynth periodic-FFT analysis, 60 s mono 48 kHz harmonic tone per stream, window 4096, hop "
-                               "256, Gaussian window (sigma factor 4), |X|^2 spectrum written + peak extraction",
-                   "streams_per_gpu": S, "frames_per_step_per_gpu": rows, "window": WINDOW, "hop": HOP, "n_fft": NFFT,
-                   "max_peaks": MAX_PEAKS, "min_db": MIN_DB, "parallelism": f"{world} x independent streams, no data-path collective",
-                   "l2": "inputs+outputs per step (0.37 GB + 2.9 GB) exceed the 126 MB L2; no flush needed"},
+        "config": workload_config(world, S),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("stft4096p_kernel"), "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": per_frame, "kernel": "stft4096p_kernel", "kernel_ms": kernel_ms,
-                     "achieved_no_reuse_convention_gbs": noreuse, "frac_no_reuse_convention": noreuse / peak},
+                     "achieved_no_reuse_convention_gbs": noreuse, "frac_no_reuse_convention": noreuse / peak,
+                     # the kernel sits on the ridge (13 FLOP/B against a machine balance of 11.5): FP32 view next to the HBM view
+                     "fp32_pipe_frac": rows * FLOP_PER_FRAME / (kernel_ms * 1e-3) / 1e12 / fp32_peak_stft,
+                     "fp32_peak_tflops_measured": fp32_peak_stft, "algorithmic_flop_per_frame": FLOP_PER_FRAME,
+                     "ncu": ncu_traffic("stft4096p_kernel_counters")},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "outputs": "peak lists (bin, freq, dB, count); the spectrum stays on the device"},
-        "gpu_launches": launches_timed, "clocks": clocks, "extra": dict(extra, final_gather_ms=gather_ms),
+                "outputs": "peak lists (bin, freq, dB, count) copied to the host; the spectrum, which the device-timed step also "
+                           "writes, stays in HBM here (extra.e2e_with_spectrum copies it too)"},
+        "gpu_launches": launches_timed, "clocks": clocks, "extra": dict(extra, final_gather_ms=gather_ms, e2e_with_spectrum=e2e_sq),
     }
     _RESULT_LINE.append(json.dumps(line))
     if world > 1:
@@ -504,6 +544,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-roundtrip", action="store_true")
     ap.add_argument("--skip-rfft", action="store_true")
+    ap.add_argument("--skip-e2e-spectrum", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints
     # its version banner there) are sent to stderr for the duration of the run

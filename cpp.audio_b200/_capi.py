@@ -13,7 +13,7 @@ DECLARED_SYMBOLS = [
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
     "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host", "ca_vocoder_host",
     "ca_oscbank_render_tracks", "ca_oscbank_render_tracks_host", "ca_tracks_open", "ca_tracks_post", "ca_tracks_pull",
-    "ca_tracks_pull_host", "ca_tracks_state", "ca_tracks_close", "ca_resynth_truncated_frames",
+    "ca_tracks_pull_host", "ca_tracks_state", "ca_tracks_close", "ca_resynth_truncated_frames", "ca_stft_plan_generation",
 ]
 
 
@@ -125,6 +125,8 @@ def lib():
     L.ca_vocoder_host.argtypes = [p, C.POINTER(VocoderParams), p, p, i64, i64, p]
     L.ca_oscbank_render_tracks.argtypes = [p, C.POINTER(TracksDesc), p, p, p]
     L.ca_oscbank_render_tracks_host.argtypes = [p, C.POINTER(TracksDesc), p, p]
+    L.ca_stft_plan_generation.argtypes = [p]
+    L.ca_stft_plan_generation.restype = C.c_uint64
     L.ca_resynth_truncated_frames.argtypes = [p]
     L.ca_resynth_truncated_frames.restype = i64
     L.ca_tracks_open.argtypes = [p, C.POINTER(TracksDesc), C.POINTER(p)]

@@ -72,12 +72,16 @@ class SqMagAnalyzer:
     def init_data(self, window: int) -> bool:
         if window == self.window:
             return False
+        self._plan(window)
+        return True
+
+    def _plan(self, window: int) -> None:
         p = StftParams(window, self.hop, self.window_type, self.sigma_factor, self.sample_rate,
                        self.min_db if math.isfinite(self.min_db) else -math.inf, self.max_peaks)
         self.ctx.check(lib().ca_stft_plan(self.ctx.handle, C.byref(p)), "ca_stft_plan")
+        self._generation = int(lib().ca_stft_plan_generation(self.ctx.handle))
         self.window = window
         self.n_fft = int(lib().ca_fft_length_for(window, 1))
-        return True
 
     @property
     def bins(self) -> int:
@@ -103,6 +107,8 @@ class SqMagAnalyzer:
         if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1):
             raise ValueError("x must be a float32 CUDA tensor [streams, samples] with unit inner stride")
         n_streams, n_samples = x.shape
+        if int(lib().ca_stft_plan_generation(self.ctx.handle)) != self._generation:
+            self._plan(self.window)  # another analyzer planned on this context since: the context holds one plan
         if out is None:
             out = self.allocate(n_streams, n_samples, x.device, want_sqmag, want_peaks)
         sq = out.get("sqmag")

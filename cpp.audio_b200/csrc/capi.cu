@@ -131,7 +131,11 @@ int ca_rfft_batched_host(ca_ctx* ctx, const float* h_in, int n_fft, int64_t batc
 int ca_stft_plan(ca_ctx* ctx, const ca_stft_params* params) {
   if (!ctx) return CA_ERR_INVALID;
   DeviceGuard guard(ctx);
+  ++ctx->plan_generation;
   return stft_plan(ctx, ctx->plan_user, params);
+}
+
+uint64_t ca_stft_plan_generation(const ca_ctx* ctx) { return ctx ? ctx->plan_generation : 0;
 }
 
 int ca_stft_analyze(ca_ctx* ctx, const float* d_x, int64_t n_samples, int64_t n_streams, int64_t stream_stride,

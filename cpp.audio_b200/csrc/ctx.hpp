@@ -36,6 +36,7 @@ struct ca_ctx {
   // analysis plans: the caller's (ca_stft_plan) and the private ones of the round trip and the vocoder, so that a
   // ca_resynth_roundtrip_host / ca_vocoder_host call never disturbs what ca_stft_analyze was planned for
   ca::StftPlan plan_user, plan_rt, plan_voc;
+  uint64_t plan_generation = 0;  // ca_stft_plan calls so far
 
   int64_t rt_truncated_frames = 0;  // last round trip: frames with more peaks than stft.max_peaks (ca_resynth_truncated_frames)
 

@@ -88,6 +88,7 @@ struct SqMagFftOperation {
 
   template <typename It>
   void operator()(It const& it, It const& end) {
+    replan_if_stale();
     staging_.assign(it, end);  // T -> float: the device path is float32
     int const n_bins = fft_length_ / 2 + 1;
     sq_.resize(n_bins);
@@ -103,6 +104,7 @@ struct SqMagFftOperation {
   // ---- used by PeriodicFFT: `frames` consecutive frames of `samples` (hop apart) in one GPU call ----
   template <typename OnFrame>
   void process_frames(float const* samples, int64_t n, int frames, OnFrame&& on_frame) {
+    replan_if_stale();
     int const n_bins = fft_length_ / 2 + 1;
     int const P = cfg_.max_peaks;
     bsq_.resize(static_cast<size_t>(frames) * n_bins);
@@ -135,6 +137,7 @@ struct SqMagFftOperation {
     p.min_db = cfg_.min_db;
     p.max_peaks = cfg_.max_peaks;
     check(ctx_, ca_stft_plan(ctx_, &p), "ca_stft_plan");
+    generation_ = ca_stft_plan_generation(ctx_);
     window_ = window_size;
     hop_ = hop;
     fft_length_ = ca_fft_length_for(window_size, zero_padding_factor);
@@ -147,7 +150,12 @@ struct SqMagFftOperation {
  private:
   ca_ctx* ctx_;
   AnalysisConfig cfg_;
+  // a ctx holds one analysis plan: when another operator planned on it since, plan again
+  void replan_if_stale() {
+    if (window_ > 0 && ca_stft_plan_generation(ctx_) != generation_) plan(window_, hop_);
+  }
   int window_ = 0, hop_ = 0, fft_length_ = 0, found_ = 0;
+  uint64_t generation_ = 0;
   std::vector<float> staging_, sq_, bsq_, pf_, pd_;
   std::vector<int32_t> pb_, pc_;
   std::vector<FreqMag<T>> peaks_;

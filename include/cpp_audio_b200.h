@@ -78,8 +78,12 @@ typedef struct ca_stft_params {
 
 int ca_fft_length_for(int n_samples, int zero_padding_factor);
 int64_t ca_stft_num_frames(int64_t n_samples, int window, int hop);
-/* builds the window table on the device; the only allocating call of the analysis path */
+/* builds the window table on the device; the only allocating call of the analysis path. A ctx holds ONE plan for
+ * ca_stft_analyze*: a second ca_stft_plan replaces it (the round trip and the vocoder keep plans of their own). */
 int ca_stft_plan(ca_ctx* ctx, const ca_stft_params* params);
+/* counts the ca_stft_plan calls of the ctx: an operator that shares its ctx with others remembers the value its own plan got
+ * and plans again when it has moved on (cpp.audio_b200/host/cuda_periodic_fft.hpp, cpp.audio_b200/analysis.py do) */
+uint64_t ca_stft_plan_generation(const ca_ctx* ctx);
 /* d_x [n_streams][stream_stride] (n_samples used per stream).
  * d_sqmag (nullable) [n_streams*frames][sqmag_row_stride], row holds n_fft/2+1 values (sqmag_row_stride >= that).
  * peaks (all nullable together): d_peak_bin/freq/db [n_streams*frames][max_peaks] ascending in frequency,

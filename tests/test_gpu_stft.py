@@ -211,3 +211,17 @@ def test_host_entry_point(pkg, orc, ctx, wl):
     assert rc == 0
     ref = orc.stft_analyze(x, 4096, 256)
     compare(dict(sqmag=sq, peak_bin=pb, peak_freq=pf, peak_db=pd, peak_count=pc), ref)
+
+
+def test_two_analyzers_share_a_context(pkg, orc, ctx, wl):
+    """A context holds one analysis plan (ca_stft_plan): analyzers that share it plan again when another one, or nothing but a
+    round trip / vocoder call (they keep plans of their own), came in between."""
+    x = wl.c4_streams(1, 0.5)
+    a = pkg.SqMagAnalyzer(ctx, 4096, 256, max_peaks=32)
+    b = pkg.SqMagAnalyzer(ctx, 2048, 512, max_peaks=8)
+    xt = torch.from_numpy(x).cuda()
+    ra = {k: v.cpu().numpy() for k, v in a(xt).items()}          # a's plan was replaced by b's: a plans again
+    pkg.resynth_roundtrip(ctx, x, window=1024, hop=128, max_peaks=64)
+    rb = {k: v.cpu().numpy() for k, v in b(xt).items()}
+    compare(ra, orc.stft_analyze(x, 4096, 256, max_peaks=32))
+    compare(rb, orc.stft_analyze(x, 2048, 512, max_peaks=8))
