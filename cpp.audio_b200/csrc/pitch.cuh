@@ -25,6 +25,27 @@ namespace ca {
 constexpr int kMaxNotes = 256;   // voice pool bound of the device pipeline (reference: 254 channels, rt.resynth.lib.cpp:201-210)
 constexpr int kMaxTuned = 256;   // peak capacity per frame of the device pipeline (reference reserve: 200, :1102)
 
+// Equal-loudness contours: the ISO 226:2003 tables as include/loudness.h:9-149 holds them, and the contour arithmetic of
+// compute_equal_loudness_volume (:188-197, float). order_pitches_by_perceived_loudness (source/rt.resynth.lib.algo.cpp:377-411)
+// ranks the new notes by volume / equal_loudness_volume_db(pitches, pitch, phons_to_index(60)) (rt.resynth.lib.cpp:1716-1724).
+constexpr int kLoudN = 29;
+inline void loudness_tables(float phons, double (&pitch)[kLoudN], float (&elv)[kLoudN]) {
+  static const float freqs[kLoudN] = {20.f,  25.f,  31.5f, 40.f,   50.f,   63.f,   80.f,   100.f,  125.f,  160.f,
+                                      200.f, 250.f, 315.f, 400.f,  500.f,  630.f,  800.f,  1000.f, 1250.f, 1600.f,
+                                      2000.f, 2500.f, 3150.f, 4000.f, 5000.f, 6300.f, 8000.f, 10000.f, 12500.f};
+  static const float alpha_f[kLoudN] = {.532f, .506f, .480f, .455f, .432f, .409f, .387f, .367f, .349f, .330f, .315f, .301f, .288f, .276f, .267f,
+                                        .259f, .253f, .250f, .246f, .244f, .243f, .243f, .243f, .242f, .242f, .245f, .254f, .271f, .301f};
+  static const float Lu[kLoudN] = {-31.6f, -27.2f, -23.0f, -19.1f, -15.9f, -13.0f, -10.3f, -8.1f, -6.2f, -4.5f, -3.1f, -2.0f, -1.1f, -0.4f, 0.f,
+                                   .3f,    .5f,    0.f,    -2.7f,  -4.1f,  -1.0f,  1.7f,   2.5f,  1.2f,  -2.1f, -7.1f, -11.2f, -10.7f, -3.1f};
+  static const float Tf[kLoudN] = {78.5f, 68.7f, 59.5f, 51.1f, 44.0f, 37.5f, 31.5f, 26.5f, 22.1f, 17.9f, 14.4f, 11.4f, 8.6f, 6.2f, 4.4f,
+                                   3.0f,  2.2f,  2.4f,  3.5f,  1.7f,  -1.3f, -4.2f, -6.0f, -5.4f, -1.5f, 6.0f,  12.6f, 13.9f, 12.3f};
+  for (int i = 0; i < kLoudN; ++i) {
+    pitch[i] = 69. + 12. * log2(static_cast<double>(freqs[i]) / 440.f);  // include/loudness.h:43-54, include/midi.h:224-232
+    const float Af = 4.47e-3f * (powf(10.f, .025f * phons) - 1.14f) + powf(.4f * powf(10.f, ((Tf[i] + Lu[i]) * .1f) - 9.f), alpha_f[i]);
+    elv[i] = 94.f - Lu[i] + (10.f / alpha_f[i]) * logf(Af) / logf(10.f);
+  }
+}
+
 // Everything the pipeline needs, resolved once on the host.
 struct PitchParams {
   int32_t W, hop, sr, P;       // P: entries per frame of the peak arrays (capacity of a frame's raw peak list)
@@ -48,6 +69,8 @@ struct PitchParams {
   int32_t n_table;
   const double* table;         // allowed pitches / scale pitches; a HOST pointer in the host form, a DEVICE pointer in the kernels
   double scale_root;
+  double loud_pitch[kLoudN];   // the 60-phon equal-loudness contour in dB over midi pitch (loudness_tables)
+  float loud_elv[kLoudN];
 };
 
 inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, int peak_stride) {
@@ -94,6 +117,7 @@ inline PitchParams make_pitch_params(const ca_roundtrip_params& prm, int64_t n_s
   p.n_table = o.n_table;
   p.table = o.table;
   p.scale_root = o.scale_root_pitch;
+  loudness_tables(60.f, p.loud_pitch, p.loud_elv);  // phons_to_index(60.f), rt.resynth.lib.cpp:1717
   return p;
 }
 
@@ -116,6 +140,20 @@ CA_HD inline float hash_unit(uint64_t id, uint64_t salt) {  // SPEC S10
   return static_cast<float>(static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0);
 }
 
+// equal_loudness_volume_db (include/loudness.h:232-244) over closest() (:155-186)
+CA_HD inline float equal_loudness_db(const PitchParams& p, double pitch) {
+  int lo = 0, hi = kLoudN - 1;
+  do {
+    const int c = (lo + hi) / 2;
+    if (pitch < p.loud_pitch[c]) hi = c;
+    else lo = c;
+  } while (hi - lo >= 2);
+  if (pitch <= p.loud_pitch[lo]) return p.loud_elv[lo];
+  if (pitch >= p.loud_pitch[hi]) return p.loud_elv[hi];
+  const float ratio = static_cast<float>((pitch - p.loud_pitch[lo]) / (p.loud_pitch[hi] - p.loud_pitch[lo]));
+  return ratio * p.loud_elv[hi] + (1.f - ratio) * p.loud_elv[lo];
+}
+
 CA_HD inline int32_t min_change_for(double ai) {  // Enveloped::setAngleIncrements, include/audioelement.h:218-225
   const double period = ai == 0.0 ? 1.0 : 2.0 / fabs(ai);
   return static_cast<int32_t>(0.5f + 2.5 * period);
@@ -125,7 +163,7 @@ CA_HD inline int32_t min_change_for(double ai) {  // Enveloped::setAngleIncremen
 // from it (synthesize_sounds, source/rt.resynth.lib.cpp:264-382) already evaluated.
 struct __align__(16) Tuned {
   double pitch;        // midi pitch (tracking key)
-  double vol;          // summed volume of the aggregated peaks
+  double vol;          // summed volume of the aggregated peaks; on leaving pitch_prefix: their perceived loudness (the ranking key)
   double ai;           // angle increment of the note frequency (freq_to_angle_increment evaluated in float)
   float volume;        // event volume: gain * vol / 0.1
   int32_t min_change;  // min_change_for(ai)
@@ -330,6 +368,8 @@ CA_HD inline int pitch_prefix_t(const PitchParams& p, const int32_t* peak_bin, c
     out[i].volume = static_cast<float>(p.gain * out[i].vol / 0.1f);
     out[i].ai = static_cast<double>(2 * new_freq / p.sr);  // freq_to_angle_increment in float
     out[i].min_change = min_change_for(out[i].ai);
+    // from here on `vol` is the key the new notes are ranked by: the perceived loudness, as the float the reference sorts
+    out[i].vol = static_cast<double>(static_cast<float>(out[i].vol / equal_loudness_db(p, out[i].pitch)));
   }
   return T;
 }

@@ -11,6 +11,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <complex>
@@ -923,6 +924,47 @@ struct PitchVolume {
   double volume;
 };
 
+// Equal-loudness contours (include/loudness.h): the ISO 226:2003 tables (:9-149), compute_equal_loudness_volume (:188-197, float
+// arithmetic; the reference evaluates it at compile time with sprout::pow / sprout::log), the table over midi pitch (:43-54),
+// closest() (:155-186) and equal_loudness_volume_db (:232-244).
+struct EqualLoudness {
+  static constexpr int n_freq = 29;
+  std::array<double, n_freq> pitches;
+  std::array<float, n_freq> elv;  // contour of one loudness level, dB
+  explicit EqualLoudness(float phons) {
+    static const float freqs[n_freq] = {20.f,  25.f,  31.5f, 40.f,   50.f,   63.f,   80.f,   100.f,  125.f,  160.f,
+                                        200.f, 250.f, 315.f, 400.f,  500.f,  630.f,  800.f,  1000.f, 1250.f, 1600.f,
+                                        2000.f, 2500.f, 3150.f, 4000.f, 5000.f, 6300.f, 8000.f, 10000.f, 12500.f};
+    static const float alpha_f_[n_freq] = {.532f, .506f, .480f, .455f, .432f, .409f, .387f, .367f, .349f, .330f, .315f, .301f, .288f, .276f, .267f,
+                                           .259f, .253f, .250f, .246f, .244f, .243f, .243f, .243f, .242f, .242f, .245f, .254f, .271f, .301f};
+    static const float Lu_[n_freq] = {-31.6f, -27.2f, -23.0f, -19.1f, -15.9f, -13.0f, -10.3f, -8.1f, -6.2f, -4.5f, -3.1f, -2.0f, -1.1f, -0.4f, 0.f,
+                                      .3f,    .5f,    0.f,    -2.7f,  -4.1f,  -1.0f,  1.7f,   2.5f,  1.2f,  -2.1f, -7.1f, -11.2f, -10.7f, -3.1f};
+    static const float Tf_[n_freq] = {78.5f, 68.7f, 59.5f, 51.1f, 44.0f, 37.5f, 31.5f, 26.5f, 22.1f, 17.9f, 14.4f, 11.4f, 8.6f, 6.2f, 4.4f,
+                                      3.0f,  2.2f,  2.4f,  3.5f,  1.7f,  -1.3f, -4.2f, -6.0f, -5.4f, -1.5f, 6.0f,  12.6f, 13.9f, 12.3f};
+    // phons_to_index (:220-229) picks one of the contours 20, 30, .. 100 phons
+    int level = static_cast<int>(phons * .1f) - 2;
+    level = std::max(0, std::min(8, level));
+    const float LN = (level + 2) * 10.f;
+    for (int i = 0; i < n_freq; ++i) {
+      pitches[i] = frequency_to_midi_pitch(freqs[i]);
+      const float Af = 4.47e-3f * (std::pow(10.f, .025f * LN) - 1.14f) + std::pow(.4f * std::pow(10.f, ((Tf_[i] + Lu_[i]) * .1f) - 9.f), alpha_f_[i]);
+      elv[i] = 94.f - Lu_[i] + (10.f / alpha_f_[i]) * std::log(Af) / std::log(10.f);
+    }
+  }
+  float volume_db(double pitch) const {  // equal_loudness_volume_db(pitches, pitch, level)
+    int min_ = 0, max_ = n_freq - 1;
+    do {
+      const int center = (min_ + max_) / 2;
+      if (pitch < pitches[center]) max_ = center;
+      else min_ = center;
+    } while (max_ - min_ >= 2);
+    if (pitch <= pitches[min_]) return elv[min_];
+    if (pitch >= pitches[max_]) return elv[max_];
+    const float ratio = static_cast<float>((pitch - pitches[min_]) / (pitches[max_] - pitches[min_]));
+    return ratio * elv[max_] + (1.f - ratio) * elv[max_ - 1];
+  }
+};
+
 // Optional stages of RtResynth::step between reduce_pitches and track_pitches (source/rt.resynth.lib.cpp:1687-1707).
 // All zero = what rt.resynth does out of the box (no shift, no harmonisation, use_autotune == false).
 // Same layout as ca_pitch_options (include/cpp_audio_b200.h) so that a test hands one block to both sides.
@@ -1236,12 +1278,15 @@ private:
         }
       }
     }
-    // order_pitches_by_perceived_loudness (:377-411), SPEC S9: raw volume
+    // order_pitches_by_perceived_loudness (:377-411) with the key of rt.resynth.lib.cpp:1716-1724: volume over the 60-phon
+    // equal-loudness contour at the pitch, kept as float. (The reference uses std::sort; ties, which need equal float keys, keep
+    // the pitch order here.)
+    static const EqualLoudness contour(60.f);
+    std::vector<float> loud(tuned_.size());
+    for (size_t i = 0; i < loud.size(); ++i) loud[i] = static_cast<float>(tuned_[i].volume / contour.volume_db(tuned_[i].midipitch));
     std::vector<int> order(tuned_.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-      return static_cast<float>(tuned_[a].volume) > static_cast<float>(tuned_[b].volume);
-    });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return loud[a] > loud[b]; });
     // synthesize_sounds (rt.resynth.lib.cpp:264-382)
     for (size_t i = 0; i < played_.size(); ++i)
       if (!keep[i]) note_off(played_[i].noteid);

@@ -74,6 +74,8 @@ def lib():
         L.orc_roundtrip_full.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
                                          p, C.c_int, p, p, C.c_int]
         L.orc_render_tracks.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, p, C.c_int, C.c_float, C.c_int, p, p]
+        L.orc_equal_loudness_db.argtypes = [C.c_double, C.c_float]
+        L.orc_equal_loudness_db.restype = C.c_float
         L.orc_set_sync_phase.argtypes = [C.c_int]
         L.orc_sync_count.argtypes = [C.c_int]
         L.orc_sync_count.restype = C.c_int64
@@ -255,6 +257,11 @@ def render_tracks(events, n_samples: int, sample_rate: int = 48000, glide_sample
     lib().orc_render_tracks(C.cast(arr, C.c_void_p), len(events), n_samples, sample_rate, glide_samples, C.byref(e), max_channels,
                             float(stereo_spread), 1 if mono else 0, _ptr(out), _ptr(stats))
     return out, (int(stats[0]), int(stats[1]))
+
+
+def equal_loudness_db(pitch: float, phons: float = 60.0) -> float:
+    """The equal-loudness contour of `phons` at a midi pitch, in dB (include/loudness.h:232-244)."""
+    return float(lib().orc_equal_loudness_db(float(pitch), float(phons)))
 
 
 def set_sync_phase(on: bool) -> None:

@@ -321,6 +321,9 @@ void orc_render_tracks(const TrackEvent* events, int64_t n_events, int64_t n_sam
   render_tracks<double>(events, n_events, n_samples, sample_rate, glide_samples, *env, max_channels, stereo_spread, mono != 0, out, stats);
 }
 
+// equal_loudness_volume_db(pitches, pitch, phons_to_index(phons)) of include/loudness.h
+float orc_equal_loudness_db(double pitch, float phons) { return EqualLoudness(phons).volume_db(pitch); }
+
 // test hooks of the start-phase rule (oracle.hpp sync_phase / sync_count)
 void orc_set_sync_phase(int on) { sync_phase() = on != 0; }
 int64_t orc_sync_count(int reset) {

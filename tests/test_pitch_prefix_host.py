@@ -84,12 +84,31 @@ def random_case(rng):
     return peaks, opt, table
 
 
+def check_loudness_key(orc, rows, vol):
+    """column 1: the key new notes are ranked by = float(volume / 60-phon equal-loudness contour at the pitch)
+    (order_pitches_by_perceived_loudness, rt.resynth.lib.cpp:1716-1724)"""
+    key = np.array([np.float32(v / orc.equal_loudness_db(p)) for p, v in zip(rows[:, 0], vol)], dtype=np.float64)
+    assert np.allclose(rows[:, 1], key, rtol=1e-6, atol=0)   # a few float ulps: the contour is interpolated in float
+
+
+def test_equal_loudness_contour_known_values(orc):
+    # ISO 226:2003, 60 phon: 1 kHz is the reference (60 dB SPL by definition); the ear is most sensitive near 3-4 kHz
+    p = lambda f: 69.0 + 12.0 * np.log2(f / 440.0)
+    assert abs(orc.equal_loudness_db(p(1000.0)) - 60.0) < 0.05
+    assert abs(orc.equal_loudness_db(p(100.0)) - 78.5) < 0.3      # published contour value
+    assert orc.equal_loudness_db(p(3150.0)) < orc.equal_loudness_db(p(1000.0)) < orc.equal_loudness_db(p(200.0))
+    assert orc.equal_loudness_db(p(5.0)) == orc.equal_loudness_db(p(20.0))            # clamped below the table
+    mid = orc.equal_loudness_db(0.5 * (p(1000.0) + p(1250.0)))                        # linear in pitch between entries
+    assert abs(mid - 0.5 * (orc.equal_loudness_db(p(1000.0)) + orc.equal_loudness_db(p(1250.0)))) < 1e-4
+
+
 def test_defaults_take_the_fast_path_and_agree(orc, harness):
     peaks = [(37, 0.5, -10.0), (85, 0.25, -20.0), (400, -0.3, -35.5)]
     opt = dict(shift_pre=0.0, harm_pre=0.0, shift_post=0.0, harm_post=0.0, autotune=0, max_pitch=0.0, tol=0.0, root=0.0)
     rows = run(harness, 8, 8, opt, [], peaks)
     pitch, vol = reduced_of(peaks)
-    assert np.allclose(rows[:, 0], pitch, atol=1e-12) and np.allclose(rows[:, 1], vol, rtol=1e-14)
+    assert np.allclose(rows[:, 0], pitch, atol=1e-12) and np.allclose(rows[:, 2], vol / np.float32(0.1), rtol=1e-6)
+    check_loudness_key(orc, rows, vol)
 
 
 def test_product_stages_match_the_oracle_on_random_lists(orc, harness):
@@ -105,7 +124,8 @@ def test_product_stages_match_the_oracle_on_random_lists(orc, harness):
         assert rows.shape[0] == len(ep), (opt, peaks)
         if len(ep):
             assert np.allclose(rows[:, 0], ep, rtol=0, atol=1e-11), (opt, peaks)
-            assert np.allclose(rows[:, 1], ev, rtol=1e-13, atol=0), (opt, peaks)
+            assert np.allclose(rows[:, 2], ev / np.float32(0.1), rtol=1e-6, atol=0), (opt, peaks)   # event volume = gain * vol / 0.1
+            check_loudness_key(orc, rows, ev)
             # event parameters of synthesize_sounds (rt.resynth.lib.cpp:264-382) follow from the final pitch
             freq = np.float32(440.0 * (2.0 ** (1 / 12)) ** (rows[:, 0] - 69.0))
             assert np.allclose(rows[:, 3], (np.float32(2) * freq / np.float32(48000)).astype(np.float64), rtol=1e-6)
