@@ -26,7 +26,10 @@ from ._capi import (  # noqa: F401
     DECLARED_SYMBOLS,
 )
 from .analysis import SqMagAnalyzer, analyze_streams, irfft_batched, rfft_batched  # noqa: F401
-from .synth import NOTE_CHANGE, NOTE_OFF, NOTE_ON, SineBank, render_bank, render_ramps, render_tracks  # noqa: F401
+from .synth import (  # noqa: F401
+    NOTE_CHANGE, NOTE_OFF, NOTE_ON, SineBank, render_bank, render_ramps, render_sound_engine, render_tracks, sound_engine_specs,
+    waveform_harmonics,
+)
 from .roundtrip import pinned_empty, pitch_options, resynth_roundtrip, truncated_frames  # noqa: F401
 from .vocoder import vocoder  # noqa: F401
 from .sharding import frame_shard, gather_rows, reduce_bus, shard_range  # noqa: F401

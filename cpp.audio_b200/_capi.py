@@ -13,7 +13,8 @@ DECLARED_SYMBOLS = [
     "ca_stft_analyze", "ca_stft_analyze_host", "ca_oscbank_plan", "ca_oscbank_render", "ca_oscbank_render_host",
     "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host", "ca_vocoder_host",
     "ca_oscbank_render_tracks", "ca_oscbank_render_tracks_host", "ca_tracks_open", "ca_tracks_post", "ca_tracks_pull",
-    "ca_tracks_pull_host", "ca_tracks_state", "ca_tracks_close", "ca_resynth_truncated_frames", "ca_stft_plan_generation",
+    "ca_tracks_pull_host", "ca_tracks_state", "ca_tracks_close", "ca_resynth_truncated_frames", "ca_stft_plan_generation", "ca_sound_engine_render_host", "ca_sound_engine_specs",
+    "ca_waveform_harmonics",
 ]
 
 
@@ -68,6 +69,29 @@ class TracksDesc(C.Structure):
     _fields_ = [("n_events", C.c_int64), ("events", C.c_void_p), ("n_samples", C.c_int64), ("sample_rate", C.c_int32),
                 ("glide_samples", C.c_int32), ("env", Ahdsr), ("max_channels", C.c_int32), ("stereo_spread", C.c_float),
                 ("mix", C.c_int32)]
+
+
+class RampSpec(C.Structure):
+    """ca_ramp_spec: one entry of SoundEngine::RampSpecs (include/soundengine.h:1030-1122)."""
+    _fields_ = [("from_hz", C.c_float), ("to_hz", C.c_float), ("duration", C.c_float), ("start_sample", C.c_float),
+                ("itp", C.c_int32), ("volume", C.c_float), ("silence_follows", C.c_int32)]
+
+
+class SoundEngineDesc(C.Structure):
+    _fields_ = [("n_voices", C.c_int64), ("spec_begin", C.c_void_p), ("specs", C.c_void_p), ("key_on", C.c_void_p),
+                ("key_off", C.c_void_p), ("velocity", C.c_void_p), ("pan", C.c_void_p), ("n_samples", C.c_int64),
+                ("sample_rate", C.c_int32), ("mix", C.c_int32), ("xfade_len", C.c_int32), ("articulative_pause", C.c_int32),
+                ("loudness_on", C.c_int32), ("loudness_ref_index", C.c_int32), ("loudness_compensation", C.c_float),
+                ("loudness_level", C.c_float), ("sine_gain", C.c_float)]
+
+
+class SoundEngineGen(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("sample_rate", C.c_int32), ("seed", C.c_uint32), ("base_freq", C.c_float),
+                ("length_ms", C.c_float), ("length_exp_min", C.c_float), ("length_exp_max", C.c_float), ("freq_scatter", C.c_float),
+                ("phase_ratio1", C.c_float), ("itp", C.c_int32), ("xfade_freq", C.c_int32), ("freq_xfade_samples", C.c_int32),
+                ("freq_itp", C.c_int32), ("d1", C.c_float), ("d2", C.c_float), ("har_att", C.c_float), ("low_freq", C.c_float),
+                ("high_freq", C.c_float), ("start_node", C.c_int32), ("pre_tries", C.c_int32), ("min_path_length", C.c_int32),
+                ("additional_tries", C.c_int32)]
 
 
 class OscBankDesc(C.Structure):
@@ -125,6 +149,9 @@ def lib():
     L.ca_vocoder_host.argtypes = [p, C.POINTER(VocoderParams), p, p, i64, i64, p]
     L.ca_oscbank_render_tracks.argtypes = [p, C.POINTER(TracksDesc), p, p, p]
     L.ca_oscbank_render_tracks_host.argtypes = [p, C.POINTER(TracksDesc), p, p]
+    L.ca_sound_engine_render_host.argtypes = [p, C.POINTER(SoundEngineDesc), p]
+    L.ca_sound_engine_specs.argtypes = [C.POINTER(SoundEngineGen), p, C.c_int32]
+    L.ca_waveform_harmonics.argtypes = [C.c_int32, C.c_int32, p, p]
     L.ca_stft_plan_generation.argtypes = [p]
     L.ca_stft_plan_generation.restype = C.c_uint64
     L.ca_resynth_truncated_frames.argtypes = [p]

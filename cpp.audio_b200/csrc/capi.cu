@@ -356,6 +356,16 @@ int ca_tracks_pull_host(ca_tracks* tracks, int64_t n_samples, float* h_out) {
 int ca_tracks_state(const ca_tracks* tracks, int64_t state[5]) { return tracks_state(tracks, state); }
 void ca_tracks_close(ca_tracks* tracks) { tracks_close(tracks); }
 
+int ca_sound_engine_render_host(ca_ctx* ctx, const ca_sound_engine_desc* desc, float* h_out) {
+  if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  return sound_engine_render_host(ctx, desc, h_out);
+}
+int ca_sound_engine_specs(const ca_sound_engine_gen* gen, ca_ramp_spec* specs, int32_t capacity) { return sound_engine_specs(gen, specs, capacity); }
+int ca_waveform_harmonics(int32_t waveform, int32_t n_harmonics, float* volume, float* phase) {
+  return waveform_harmonics(waveform, n_harmonics, volume, phase);
+}
+
 int ca_vocoder_host(ca_ctx* ctx, const ca_vocoder_params* params, const float* h_modulator, const float* h_carrier,
                     int64_t n_samples, int64_t n_streams, float* h_out) {
   if (!ctx) return CA_ERR_INVALID;

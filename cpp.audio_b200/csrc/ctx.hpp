@@ -141,6 +141,9 @@ int tracks_state(const ca_tracks* tp, int64_t state[5]);
 void tracks_close(ca_tracks* tp);
 int tracks_render(ca_ctx* ctx, const ca_tracks_desc* desc, float* d_out, int64_t* h_stats, cudaStream_t st);
 int tracks_render_host(ca_ctx* ctx, const ca_tracks_desc* desc, float* h_out, int64_t* h_stats);
+int sound_engine_render_host(ca_ctx* ctx, const ca_sound_engine_desc* desc, float* h_out);
+int sound_engine_specs(const ca_sound_engine_gen* gen, ca_ramp_spec* specs, int32_t capacity);
+int waveform_harmonics(int32_t waveform, int32_t n, float* volume, float* phase);
 int ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
 int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modulator, const float* h_carrier, int64_t n_samples,
                  int64_t n_streams, float* h_out);

@@ -23,40 +23,6 @@ namespace ca {
 
 namespace {
 
-struct Leg {  // closed form of one ramp leg that starts at position c_start
-  double from1 = 0, K1 = 0, L = 0, c1 = 0;  // f_i = from1 + K1*expm1(L*i),  P_i = (i+1)*(from1-K1) + c1*expm1(L*(i+1))
-  int64_t m = 0;                            // steps before the ramp turns around
-  bool steady = false;                      // from == to
-  void start(double from, double to, double dur, double c_start) {
-    steady = (to == from);
-    if (steady) {
-      from1 = from;
-      K1 = L = c1 = 0;
-      m = LLONG_MAX / 4;
-      return;
-    }
-    const double delta = to - from;
-    const double C = -log(from / to) / delta;            // get_linear_proportionality_constant, :2560-2571
-    const double lambda = C * delta / dur;
-    const double beta = C * (from + 0.5 * delta / dur);  // do_step, :2537-2540
-    L = log1p(lambda);
-    K1 = (delta / dur) * (c_start + beta / lambda);
-    from1 = from + delta * c_start / dur;
-    c1 = K1 / lambda;
-    // first step i with cur_i + .5 > dur (:2523): cur_i = (c_start + beta/lambda)*alpha^i - beta/lambda
-    const double x = (log1p(lambda * (dur - 0.5) / beta) - log1p(lambda * c_start / beta)) / L;
-    double mf = floor(x) + 1.0;
-    if (!(mf >= 0.0)) mf = 0.0;
-    if (mf > 4e18) mf = 4e18;
-    m = static_cast<int64_t>(mf);
-  }
-  double P(int64_t k) const {  // sum of the emitted increments over steps 0..k
-    if (k < 0) return 0.0;
-    if (steady) return static_cast<double>(k + 1) * from1;
-    return static_cast<double>(k + 1) * (from1 - K1) + c1 * expm1(L * static_cast<double>(k + 1));
-  }
-};
-
 inline int32_t min_change_for_ramp(double ai) {  // Enveloped::setAngleIncrements, include/audioelement.h:218-225
   const double period = ai == 0.0 ? 1.0 : 2.0 / fabs(ai);
   return static_cast<int32_t>(0.5f + 2.5 * period);

@@ -131,3 +131,64 @@ def render_tracks(ctx: Context, events, n_samples: int, sample_rate: int = 48000
     ctx.check(lib().ca_oscbank_render_tracks_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p), stats),
               "ca_oscbank_render_tracks_host")
     return out, (int(stats[0]), int(stats[1]))
+
+
+MODE_BIRDS, MODE_ROBOTS, MODE_SWEEP = 0, 1, 2  # SoundEngineMode, include/soundengine.h:30-39
+WAVE_SAW, WAVE_SQUARE, WAVE_TRIANGLE = 0, 1, 2
+
+
+def render_sound_engine(ctx: Context, voices, n_samples: int, sample_rate: int = 48000, xfade_len: int = 480, articulative_pause: int = 0,
+                        loudness_on: bool = True, loudness_ref_index: int = 0, loudness_compensation: float = 1.0,
+                        loudness_level: float = 40.0, sine_gain: float = 1.0, mix: int = MIX_MONO) -> np.ndarray:
+    """gen.voice voices (ca_sound_engine_render_host). voices: [dict(specs=[(from_hz, to_hz, duration, start_sample, itp, volume,
+    silence_follows), ...], key_on=int, key_off=int or -1, velocity=float, pan=float)]. Returns float32 [voices, samples] (MIX_NONE),
+    [samples] (MIX_MONO) or [samples, 2] (MIX_STEREO)."""
+    from ._capi import RampSpec, SoundEngineDesc
+
+    V = len(voices)
+    begin = np.zeros(V + 1, dtype=np.int32)
+    flat = []
+    for i, v in enumerate(voices):
+        flat += list(v["specs"])
+        begin[i + 1] = len(flat)
+    arr = (RampSpec * max(len(flat), 1))()
+    for i, t in enumerate(flat):
+        arr[i] = RampSpec(float(t[0]), float(t[1]), float(t[2]), float(t[3]), int(t[4]), float(t[5]), int(t[6]))
+    key_on = np.array([v.get("key_on", 0) for v in voices], dtype=np.int64)
+    key_off = np.array([v.get("key_off", -1) for v in voices], dtype=np.int64)
+    vel = np.array([v.get("velocity", 1.0) for v in voices], dtype=np.float32)
+    pan = np.array([v.get("pan", 0.0) for v in voices], dtype=np.float32)
+    q = lambda a: a.ctypes.data_as(C.c_void_p)
+    d = SoundEngineDesc(V, q(begin), C.cast(arr, C.c_void_p), q(key_on), q(key_off), q(vel), q(pan), n_samples, sample_rate, mix, xfade_len,
+                        articulative_pause, 1 if loudness_on else 0, loudness_ref_index, loudness_compensation, loudness_level, sine_gain)
+    shape = (V, n_samples) if mix == MIX_NONE else (n_samples, 2) if mix == MIX_STEREO else (n_samples,)
+    out = np.zeros(shape, dtype=np.float32)
+    ctx.check(lib().ca_sound_engine_render_host(ctx.handle, C.byref(d), q(out)), "ca_sound_engine_render_host")
+    return out
+
+
+def sound_engine_specs(mode: int, seed: int, base_freq: float = 440.0, length_ms: float = 100.0, length_exp=(0.0, 0.0),
+                       freq_scatter: float = 0.0, phase_ratio1: float = 0.0, itp: int = 0, xfade_freq: int = 0, freq_xfade_samples: int = 480,
+                       freq_itp: int = 16, d1: float = 0.0, d2: float = 0.0, har_att: float = 0.9, low_freq: float = 100.0,
+                       high_freq: float = 1000.0, start_node: int = 0, pre_tries: int = 0, min_path_length: int = 4,
+                       additional_tries: int = 0, sample_rate: int = 48000):
+    """The ramp specs of one note (ca_sound_engine_specs): list of (from_hz, to_hz, duration, start_sample, itp, volume, silence_follows)."""
+    from ._capi import RampSpec, SoundEngineGen
+
+    g = SoundEngineGen(mode, sample_rate, seed, base_freq, length_ms, length_exp[0], length_exp[1], freq_scatter, phase_ratio1, itp, xfade_freq,
+                       freq_xfade_samples, freq_itp, d1, d2, har_att, low_freq, high_freq, start_node, pre_tries, min_path_length, additional_tries)
+    arr = (RampSpec * 30)()
+    n = lib().ca_sound_engine_specs(C.byref(g), C.cast(arr, C.c_void_p), 30)
+    if n < 0:
+        raise ValueError(f"ca_sound_engine_specs failed ({n})")
+    return [(a.from_hz, a.to_hz, a.duration, a.start_sample, a.itp, a.volume, a.silence_follows) for a in arr[:n]]
+
+
+def waveform_harmonics(waveform: int, n_harmonics: int):
+    """(volume, phase) float32 arrays of the first n harmonics of the reference's saw / square / triangle (ca_waveform_harmonics)."""
+    vol = np.zeros(n_harmonics, dtype=np.float32)
+    ph = np.zeros(n_harmonics, dtype=np.float32)
+    rc = lib().ca_waveform_harmonics(waveform, n_harmonics, vol.ctypes.data_as(C.c_void_p), ph.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError(f"ca_waveform_harmonics failed ({rc})")
+    return vol, ph

@@ -295,6 +295,74 @@ typedef struct ca_ramp_desc {
 } ca_ramp_desc;
 int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
 
+/* ---- gen.voice voices: SoundEngine ---------------------------------------------------------------------------------
+ * Stands in for voice::Impl_::doProcessing (include/gen.voice.h:1130-1189) over channels of VolumeAdjusted<SoundEngine>
+ * (include/soundengine.h:240-468, :738-803): every voice plays its list of ramp specs, each on one of three ramp elements
+ * VolumeAdjusted<Enveloped<FreqCtrl_<Mix<LoudnessVolumeAdjusted<Sine>>, LogRamp>, AHDSR>> that fade in and out over xfade_len samples
+ * (the orchestration of orchestrate_algos / playNextSpec, :744-803). The specs are what the engine's Markov chain produces at
+ * note-on (:496-736): ca_sound_engine_specs below builds them (the chain and the random generator live in cpp.algorithms: its
+ * decisions are oracle/SPEC.md S14), or the host supplies its own. Events: NoteOn at key_on (the first spec starts on that sample),
+ * NoteOff at key_off (nothing starts any more, the sounding ramp is released). Host pointers. */
+typedef struct ca_ramp_spec { /* one entry of SoundEngine::RampSpecs (include/soundengine.h:1030-1122) */
+  float from_hz, to_hz;    /* LogRamp::setup(freq_to_angle_increment(from), freq_to_angle_increment(to), duration, start_sample, itp) */
+  float duration;          /* samples, > 0 */
+  float start_sample;      /* initial ramp position, 0 <= start_sample <= duration */
+  int32_t itp;             /* ca_itp: interpolation of the emitted frequency (LINEAR and the 21 easings) */
+  float volume;            /* setVolume */
+  int32_t silence_follows; /* silenceFollows: the articulative pause applies after this spec */
+} ca_ramp_spec;
+typedef struct ca_sound_engine_desc {
+  int64_t n_voices;
+  const int32_t* spec_begin;   /* [voices + 1]: the specs of voice v are specs[spec_begin[v] .. spec_begin[v+1]), at most 30 */
+  const ca_ramp_spec* specs;
+  const int64_t* key_on;       /* nullable [voices] (0) */
+  const int64_t* key_off;      /* nullable [voices]; < 0: never */
+  const float* velocity;       /* nullable [voices] (1): the voice's volume (base volume 1, include/audioelement.h:1278) */
+  const float* pan;            /* nullable [voices], CA_MIX_STEREO (include/stereo.h:18-27; gen.voice.h:992-1008) */
+  int64_t n_samples;
+  int32_t sample_rate;
+  int32_t mix;                 /* CA_MIX_NONE: h_out [voices][samples]; CA_MIX_MONO: [samples]; CA_MIX_STEREO: [samples][2] */
+  int32_t xfade_len;           /* setEnvelopeCharacTime: attack = release of every ramp, samples (at least 1 ms) */
+  int32_t articulative_pause;  /* articulative_pause_length, samples */
+  int32_t loudness_on;         /* 1: LoudnessVolumeAdjusted<Sine> as in the reference; 0: plain sine */
+  int32_t loudness_ref_index;  /* setLoudnessParams (gen.voice.h:934-937): index of the reference frequency in the ISO 226 table */
+  float loudness_compensation; /* log_ratio in [0,1] */
+  float loudness_level;        /* phons (20 .. 100) */
+  float sine_gain;             /* Mix gain of the sine (SetGains, gen.voice.h:951-956) */
+} ca_sound_engine_desc;
+int ca_sound_engine_render_host(ca_ctx* ctx, const ca_sound_engine_desc* desc, float* h_out);
+
+/* The ramp specs of one note as SoundEngine::initialize_{birds,robot,sweep} + do_initialize produce them (include/soundengine.h
+ * :496-736, :883-1003): the Markov chain is run on the host at note-on, min_path_length normalised steps then additional_tries plain
+ * steps. mode: 0 BIRDS, 1 ROBOTS, 2 SWEEP (SoundEngineMode). The chain class and mersenne<> are in cpp.algorithms: the walk and the
+ * draws follow oracle/SPEC.md S14 with a generator seeded by `seed`. Returns the number of specs written (<= 30), negative on error. */
+typedef struct ca_sound_engine_gen {
+  int32_t mode;
+  int32_t sample_rate;
+  uint32_t seed;
+  float base_freq;                    /* the note's frequency */
+  float length_ms;                    /* set_length */
+  float length_exp_min, length_exp_max; /* set_length_exp */
+  float freq_scatter;                 /* BIRDS, ROBOTS */
+  float phase_ratio1;                 /* ROBOTS, SWEEP: start position = phase_ratio1 * duration */
+  int32_t itp;                        /* set_itp */
+  int32_t xfade_freq;                 /* BIRDS: FreqXfade 0 No, 1 NonTrivial, 2 All */
+  int32_t freq_xfade_samples;         /* BIRDS: set_freq_xfade */
+  int32_t freq_itp;                   /* BIRDS: set_freq_interpolation */
+  float d1, d2, har_att;              /* ROBOTS */
+  float low_freq, high_freq;          /* SWEEP */
+  int32_t start_node, pre_tries, min_path_length, additional_tries;
+} ca_sound_engine_gen;
+int ca_sound_engine_specs(const ca_sound_engine_gen* gen, ca_ramp_spec* specs, int32_t capacity);
+
+/* Harmonics of the reference's non-sine oscillators (FOscillator: saw, square, triangle, include/audioelement.h:1612-1675; wave
+ * shapes include/sound.functions.h:86-139) for additive synthesis on the oscillator bank, as the author plans
+ * (source/rt.resynth.txt:17-23): volume[h] and phase[h] (units of pi rad) of harmonic h+1 for ca_oscbank_desc.partial_volume /
+ * partial_phase, so that sum_h volume[h] sin(pi (h+1) a + pi phase[h]) is the Fourier series of the wave over the angle a in [0,2).
+ * The bank's aliasing gain fades harmonics between sr/8 and sr/2 (include/audioelement.h:466-483). waveform: 0 saw, 1 square, 2 triangle. */
+enum ca_waveform { CA_WAVE_SAW = 0, CA_WAVE_SQUARE = 1, CA_WAVE_TRIANGLE = 2 };
+int ca_waveform_harmonics(int32_t waveform, int32_t n_harmonics, float* volume, float* phase);
+
 /* ---- FFT vocoder --------------------------------------------------------------------------------------------------
  * Stands in for Vocoder / FFTModulator / FFTCarrier (source/rt.resynth.lib.vocoder.cpp:100-257, :396-551, :734-856): the
  * modulator's band amplitudes (PeriodicFFT<SqMagFftOperation<Gaussian>>, window modulator_window_size_seconds, hop = stride)

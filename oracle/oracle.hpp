@@ -556,6 +556,7 @@ public:
   EnvState state() const { return state_; }
   bool rt_active() const { return state_ != EnvState::SoonKeyPressed && state_ != EnvState::Done2; }
   bool finished() const { return state_ == EnvState::Done2; }
+  int count_steps_to_release() const { return release_delay_; }  // :783-785
 
 private:
   // ahd_: 0 attacking, 1 holding, 2 decaying, 3 none (sustain)
@@ -930,6 +931,7 @@ struct PitchVolume {
 struct EqualLoudness {
   static constexpr int n_freq = 29;
   std::array<double, n_freq> pitches;
+  std::array<float, n_freq> freqs_hz;
   std::array<float, n_freq> elv;  // contour of one loudness level, dB
   explicit EqualLoudness(float phons) {
     static const float freqs[n_freq] = {20.f,  25.f,  31.5f, 40.f,   50.f,   63.f,   80.f,   100.f,  125.f,  160.f,
@@ -947,6 +949,7 @@ struct EqualLoudness {
     const float LN = (level + 2) * 10.f;
     for (int i = 0; i < n_freq; ++i) {
       pitches[i] = frequency_to_midi_pitch(freqs[i]);
+      freqs_hz[i] = freqs[i];
       const float Af = 4.47e-3f * (std::pow(10.f, .025f * LN) - 1.14f) + std::pow(.4f * std::pow(10.f, ((Tf_[i] + Lu_[i]) * .1f) - 9.f), alpha_f_[i]);
       elv[i] = 94.f - Lu_[i] + (10.f / alpha_f_[i]) * std::log(Af) / std::log(10.f);
     }
@@ -962,6 +965,26 @@ struct EqualLoudness {
     if (pitch >= pitches[max_]) return elv[max_];
     const float ratio = static_cast<float>((pitch - pitches[min_]) / (pitches[max_] - pitches[min_]));
     return ratio * elv[max_] + (1.f - ratio) * elv[max_ - 1];
+  }
+  // equal_loudness_volume_from_freq (:258-275): the amplitude that equalises the loudness of a sine of `freq` with the one at
+  // freqs[index_freq_ref]; log_ratio in [0,1] scales the compensation
+  float volume_from_freq(float freq, int index_freq_ref, float log_ratio) const {
+    int min_ = 0, max_ = n_freq - 1;
+    do {
+      const int center = (min_ + max_) / 2;
+      if (freq < freqs_hz[center]) max_ = center;
+      else min_ = center;
+    } while (max_ - min_ >= 2);
+    float db;
+    if (freq <= freqs_hz[min_]) db = elv[min_];
+    else if (freq >= freqs_hz[max_]) db = elv[max_];
+    else {
+      const float ratio = (freq - freqs_hz[min_]) / (freqs_hz[max_] - freqs_hz[min_]);
+      db = ratio * elv[max_] + (1.f - ratio) * elv[max_ - 1];
+    }
+    const float max_db = elv[index_freq_ref];
+    if (db > max_db) return 1.f;                                   // db_to_amplitude, :246-255
+    return std::pow(10.f, log_ratio * (db - max_db) / 20.f);
   }
 };
 
@@ -1082,6 +1105,168 @@ struct RoundTripParams {
   Ahdsr env{0, LINEAR, 0, 0, LINEAR, 0, LINEAR, 1.f};  // :957-961
   int max_channels = 254;               // 2 * 127 voices, :201-210, gen.crtp.h:225
   PitchOptions opts;                    // shift / harmonize / autotune (:1687-1707), off by default
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// SoundEngine (include/soundengine.h:240-468, :738-803): a voice of gen.voice. Up to three ramp elements
+//   VolumeAdjusted<Enveloped<FreqCtrl_<Mix<LoudnessVolumeAdjusted<Sine>>, LogRamp>, AHDSR>>   (:245-257, MixOf :209-216)
+// play a list of ramp specs one after the other; a new ramp fades in (attack = xfade_len) while the previous one fades out
+// (release = xfade_len). The specs come from a Markov chain at note-on (:565-736, RNG and chain are external): here they
+// are an input.
+// ------------------------------------------------------------------------------------------------------------
+struct RampSpec {  // same layout as ca_ramp_spec
+  float from_hz, to_hz;   // LogRamp::setup(freq_to_angle_increment(from), freq_to_angle_increment(to), ...)
+  float duration;         // samples
+  float start_sample;
+  int32_t itp;            // interpolation of the emitted frequency
+  float volume;           // RampSpecs::Ctrl::setVolume
+  int32_t silence_follows;
+};
+
+struct SoundEngineParams {
+  int sample_rate = 48000;
+  int xfade_len = 480;            // setEnvelopeCharacTime
+  int articulative_pause = 0;     // articulative_pause_length
+  int loudness_on = 1;            // the Mix element is LoudnessVolumeAdjusted<Sine> (0: plain sine, for tests of the ramps alone)
+  int loudness_ref_index = 0;     // setLoudnessParams(sample_rate, low_index, log_ratio, loudness_level), gen.voice.h:934-937
+  float loudness_compensation = 1.f;
+  float loudness_level = 40.f;
+  float sine_gain = 1.f;          // Mix gain of the sine (SetGains, gen.voice.h:951-956)
+};
+
+template <class T>
+class RampElement {
+public:
+  void set_sample_rate(int sr) { sample_rate_ = sr; }
+  void set_loudness(const EqualLoudness* contour, int ref_index, float log_ratio) { contour_ = contour; ref_index_ = ref_index; log_ratio_ = log_ratio; }
+  void set_gain(float g) { gain_ = g; }
+  void set_stereo(double gl, double gr) { gl_ = gl; gr_ = gr; }
+  LogRamp<T>& ctrl() { return ctrl_; }
+  Envelope<T>& env() { return env_; }
+  const Envelope<T>& env() const { return env_; }
+  void forget_past_signals() { env_.forget_past_signals(); lvol_.reset(); ltarget_.reset(); }  // Enveloped :192-195, BaseVolumeAdjusted :1168-1172
+  void set_start_angle(T a) { osc_.set_start_angle(a); }
+  void set_volume_target(T v) { volume_ = v; }  // the outer VolumeAdjusted: constant target, so its filter is the identity
+  void step() {
+    env_.step();                                  // Enveloped::step :197-200
+    const T f = ctrl_.step();                     // FreqCtrl_::step :3126-3129 -> Mix::setAngleIncrements :1843-1847
+    if (contour_) {                               // LoudnessVolumeAdjusted::setAngleIncrements :1291-1298
+      const float freq = static_cast<float>(f * sample_rate_ / 2);  // angle_increment_to_freq
+      ltarget_ = static_cast<T>(contour_->volume_from_freq(freq, ref_index_, log_ratio_));
+    }
+    osc_.set_angle_increments(f);
+    osc_.step();                                  // BaseVolumeAdjusted::step :1195-1216 (max_filter_increment at its default)
+    if (contour_) {
+      const T inc = std::abs(f);
+      if (!lvol_) {
+        lfilter_inc_ = inc;
+        lfilter_.init_with_angle_increment(inc);
+        lfilter_.set_initial_value(*ltarget_);
+      } else if (*lvol_ != *ltarget_ && lfilter_inc_ != inc) {
+        lfilter_inc_ = inc;
+        lfilter_.init_with_angle_increment(inc);
+      }
+      lvol_ = lfilter_.feed(*ltarget_);
+    }
+  }
+  T imag_mono() const {  // VolumeAdjusted( Enveloped( Mix( Loudness( Sine ) ) ) )
+    const T tone = contour_ ? *lvol_ * osc_.imag() : osc_.imag();
+    return volume_ * ((static_cast<T>(gain_) * tone) * env_.value());
+  }
+  T imag(int ch) const { return (ch == 0 ? gl_ : gr_) * imag_mono(); }  // StereoPanned :1376-1380
+
+private:
+  Envelope<T> env_;
+  SineOsc<T> osc_;
+  LogRamp<T> ctrl_;
+  const EqualLoudness* contour_ = nullptr;
+  int ref_index_ = 0, sample_rate_ = 48000;
+  float log_ratio_ = 1.f, gain_ = 1.f;
+  std::optional<T> lvol_, ltarget_;
+  T lfilter_inc_ = 0, volume_ = 1;
+  OnePole<T> lfilter_;
+  double gl_ = 1, gr_ = 1;
+};
+
+template <class T>
+class SoundEngineVoice {
+public:
+  SoundEngineVoice(const SoundEngineParams& p, const RampSpec* specs, int n_specs, bool stereo, double pan)
+      : prm_(p), specs_(specs, specs + n_specs), contour_(p.loudness_level), stereo_(stereo) {
+    double gl = 1, gr = 1;
+    if (stereo) stereo_gains(pan, gl, gr);
+    for (auto& r : ramps_) {
+      r.set_sample_rate(p.sample_rate);
+      if (p.loudness_on) r.set_loudness(&contour_, p.loudness_ref_index, p.loudness_compensation);
+      r.set_gain(p.sine_gain);
+      r.set_stereo(gl, gr);
+    }
+  }
+  void on_key_pressed() { go_on_ = true; }       // tryAcquire + onKeyPressed :297-312, :349-353
+  void on_key_released(int32_t delay) {           // :357-365
+    if (!go_on_) return;
+    go_on_ = false;
+    for (auto& r : ramps_) r.env().on_key_released(delay);
+  }
+  void step() {  // :738-741
+    orchestrate();
+    for (auto& r : ramps_)  // step_algos :412-426
+      if (r.env().state() != EnvState::Done2) r.step();
+  }
+  T imag(int ch) const {  // :428-464
+    T v = 0;
+    for (auto& r : ramps_)
+      if (r.env().state() == EnvState::KeyReleased || r.env().state() == EnvState::KeyPressed) v += stereo_ ? r.imag(ch) : r.imag_mono();
+    return v;
+  }
+
+private:
+  void orchestrate() {  // :744-772
+    if (it_ == static_cast<int>(specs_.size())) return;  // ramp_specs.done()
+    const RampSpec* cur = it_ >= 0 && it_ < static_cast<int>(specs_.size()) ? &specs_[it_] : nullptr;
+    RampElement<T>* pressed = nullptr;
+    RampElement<T>* done = nullptr;
+    for (auto& r : ramps_) {  // get_ramps :277-295: the last ramp of each kind wins
+      if (r.env().state() == EnvState::Done2) {
+        if (go_on_) done = &r;
+      } else if (r.env().state() == EnvState::KeyPressed) {
+        pressed = &r;
+      }
+    }
+    if (pressed) {
+      const int remaining = pressed->env().count_steps_to_release();
+      if (remaining > 0) return;
+      if (remaining == 0 && cur && cur->silence_follows) remaining_silence_steps_ = prm_.articulative_pause;
+    }
+    if (cur && cur->silence_follows && remaining_silence_steps_ > 0) {
+      --remaining_silence_steps_;
+      return;
+    }
+    // playNextSpec :774-803
+    if (!done) return;
+    ++it_;
+    if (it_ == static_cast<int>(specs_.size())) return;
+    const RampSpec& sp = specs_[it_];
+    const T from = static_cast<T>(freq_to_angle_increment<float>(sp.from_hz, prm_.sample_rate));
+    const T to = static_cast<T>(freq_to_angle_increment<float>(sp.to_hz, prm_.sample_rate));
+    done->ctrl().setup(from, to, static_cast<T>(sp.duration), static_cast<T>(sp.start_sample), sp.itp);
+    done->forget_past_signals();
+    done->set_start_angle(0);  // start_angle: forgetPastSignals zeroes it (:320-323), DefaultStartPhase::Zero (gen.voice.h:1100)
+    done->set_volume_target(static_cast<T>(sp.volume));
+    done->env().set_ahdsr(Ahdsr{prm_.xfade_len, LINEAR, 0, 0, LINEAR, prm_.xfade_len, LINEAR, 1.f}, prm_.sample_rate);
+    done->env().try_acquire();
+    const int time_to_release = static_cast<int>(.5f + sp.duration) - prm_.xfade_len;
+    done->env().on_key_pressed(0);
+    done->env().on_key_released(std::max(time_to_release, 0));
+  }
+
+  SoundEngineParams prm_;
+  std::vector<RampSpec> specs_;
+  EqualLoudness contour_;
+  bool stereo_;
+  std::array<RampElement<T>, 3> ramps_;
+  int it_ = -1, remaining_silence_steps_ = 0;
+  bool go_on_ = false;
 };
 
 // ------------------------------------------------------------------------------------------------------------

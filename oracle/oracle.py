@@ -74,6 +74,9 @@ def lib():
         L.orc_roundtrip_full.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_float, p, p,
                                          p, C.c_int, p, p, C.c_int]
         L.orc_render_tracks.argtypes = [p, C.c_int64, C.c_int64, C.c_int, C.c_int, p, C.c_int, C.c_float, C.c_int, p, p]
+        L.orc_sound_engine_render.argtypes = [p, C.c_int, p, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_float, C.c_int64, p]
+        L.orc_equal_loudness_volume_from_freq.argtypes = [C.c_float, C.c_int, C.c_float, C.c_float]
+        L.orc_equal_loudness_volume_from_freq.restype = C.c_float
         L.orc_equal_loudness_db.argtypes = [C.c_double, C.c_float]
         L.orc_equal_loudness_db.restype = C.c_float
         L.orc_set_sync_phase.argtypes = [C.c_int]
@@ -257,6 +260,40 @@ def render_tracks(events, n_samples: int, sample_rate: int = 48000, glide_sample
     lib().orc_render_tracks(C.cast(arr, C.c_void_p), len(events), n_samples, sample_rate, glide_samples, C.byref(e), max_channels,
                             float(stereo_spread), 1 if mono else 0, _ptr(out), _ptr(stats))
     return out, (int(stats[0]), int(stats[1]))
+
+
+class RampSpec(C.Structure):
+    """orc::RampSpec = ca_ramp_spec: one entry of SoundEngine::RampSpecs (include/soundengine.h:1030-1122)."""
+    _fields_ = [("from_hz", C.c_float), ("to_hz", C.c_float), ("duration", C.c_float), ("start_sample", C.c_float),
+                ("itp", C.c_int32), ("volume", C.c_float), ("silence_follows", C.c_int32)]
+
+
+class SoundEngineParams(C.Structure):
+    _fields_ = [("sample_rate", C.c_int), ("xfade_len", C.c_int), ("articulative_pause", C.c_int), ("loudness_on", C.c_int),
+                ("loudness_ref_index", C.c_int), ("loudness_compensation", C.c_float), ("loudness_level", C.c_float),
+                ("sine_gain", C.c_float)]
+
+
+def sound_engine_render(voices, n_samples: int, sample_rate: int = 48000, xfade_len: int = 480, articulative_pause: int = 0,
+                        loudness_on: bool = True, loudness_ref_index: int = 0, loudness_compensation: float = 1.0,
+                        loudness_level: float = 40.0, sine_gain: float = 1.0, stereo: bool = False) -> np.ndarray:
+    """voices: [dict(specs=[(from_hz, to_hz, duration, start_sample, itp, volume, silence_follows), ...], key_on=int,
+    key_off=int or -1, velocity=float, pan=float)]. Returns the sum of the voices, float64 [n_samples] or [n_samples, 2]."""
+    out = np.zeros((n_samples, 2) if stereo else (n_samples,), dtype=np.float64)
+    prm = SoundEngineParams(sample_rate, xfade_len, articulative_pause, 1 if loudness_on else 0, loudness_ref_index,
+                            loudness_compensation, loudness_level, sine_gain)
+    for v in voices:
+        sp = v["specs"]
+        arr = (RampSpec * max(len(sp), 1))()
+        for i, t in enumerate(sp):
+            arr[i] = RampSpec(float(t[0]), float(t[1]), float(t[2]), float(t[3]), int(t[4]), float(t[5]), int(t[6]))
+        lib().orc_sound_engine_render(C.cast(arr, C.c_void_p), len(sp), C.byref(prm), int(v.get("key_on", 0)), int(v.get("key_off", -1)),
+                                      float(v.get("velocity", 1.0)), 1 if stereo else 0, float(v.get("pan", 0.0)), n_samples, _ptr(out))
+    return out
+
+
+def equal_loudness_volume_from_freq(freq: float, ref_index: int = 0, log_ratio: float = 1.0, phons: float = 40.0) -> float:
+    return float(lib().orc_equal_loudness_volume_from_freq(float(freq), int(ref_index), float(log_ratio), float(phons)))
 
 
 def equal_loudness_db(pitch: float, phons: float = 60.0) -> float:

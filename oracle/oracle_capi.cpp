@@ -321,6 +321,33 @@ void orc_render_tracks(const TrackEvent* events, int64_t n_events, int64_t n_sam
   render_tracks<double>(events, n_events, n_samples, sample_rate, glide_samples, *env, max_channels, stereo_spread, mono != 0, out, stats);
 }
 
+// One gen.voice voice (VolumeAdjusted<SoundEngine>, include/gen.voice.h:1093-1110) playing `specs` from sample key_on on, released at
+// key_off (< 0: never), ACCUMULATED into out ([n_samples][2] when stereo, else [n_samples]). The voice-level volume is the velocity
+// (base volume 1: include/audioelement.h:1278, a constant target, so its filter is the identity).
+void orc_sound_engine_render(const RampSpec* specs, int n_specs, const SoundEngineParams* prm, int64_t key_on, int64_t key_off,
+                             float velocity, int stereo, float pan, int64_t n_samples, double* out) {
+  SoundEngineVoice<double> v(*prm, specs, n_specs, stereo != 0, pan);
+  bool on = false;
+  for (int64_t i = std::max<int64_t>(key_on, 0); i < n_samples; ++i) {
+    if (i == std::max<int64_t>(key_on, 0)) {
+      v.on_key_pressed();
+      on = true;
+    }
+    if (on && key_off >= 0 && i == key_off) v.on_key_released(0);
+    v.step();
+    if (stereo) {
+      out[2 * i] += velocity * v.imag(0);
+      out[2 * i + 1] += velocity * v.imag(1);
+    } else {
+      out[i] += velocity * v.imag(0);
+    }
+  }
+}
+
+float orc_equal_loudness_volume_from_freq(float freq, int ref_index, float log_ratio, float phons) {
+  return EqualLoudness(phons).volume_from_freq(freq, ref_index, log_ratio);
+}
+
 // equal_loudness_volume_db(pitches, pitch, phons_to_index(phons)) of include/loudness.h
 float orc_equal_loudness_db(double pitch, float phons) { return EqualLoudness(phons).volume_db(pitch); }
 
