@@ -175,6 +175,51 @@ def cpu_analysis_rate(orc, wl, threads: int, streams: int, seconds: float):
     return streams * r["frames"] / dt, dt
 
 
+def measure_copy_ceiling(torch, dist, dev, world, mib: int = 256, reps: int = 4):
+    """Pinned host <-> device copy rates of this box with every rank copying at once (one cudaMemcpyAsync per direction in flight,
+    `mib` MiB each): H2D alone, D2H alone, both directions together. Per rank and summed over the ranks, GB/s. This is the
+    ceiling of every host-buffer entry point; it is a property of the host (PCIe root complexes, memory, virtualisation)."""
+    n = mib << 20
+    h_up = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_dn = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_up = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(n, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(up: bool, dn: bool):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s_up.wait_event(e0)
+        s_dn.wait_event(e0)
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+            if dn:
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s_up)
+        torch.cuda.current_stream(dev).wait_stream(s_dn)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return reps * n / (ms * 1e-3) / 1e9  # GB/s per direction per rank (slowest rank)
+
+    run(True, True)  # warm-up
+    h2d, d2h, duplex = run(True, False), run(False, True), run(True, True)
+    return {"mib_per_copy": mib, "ranks": world, "h2d_gbs_per_rank": h2d, "d2h_gbs_per_rank": d2h,
+            "duplex_gbs_per_rank_per_direction": duplex, "h2d_gbs_all_ranks": h2d * world, "d2h_gbs_all_ranks": d2h * world,
+            "duplex_gbs_all_ranks_both_directions": 2 * duplex * world,
+            "note": "every rank copies at once; rates of the slowest rank (max time over ranks)"}
+
+
 _RESULT_LINE: list = []  # the one line of stdout, printed by main() after the run
 
 
@@ -438,6 +483,16 @@ def run_ours(args):
                       "are points of config 5 (1 GiB of input each)")
         extra["rfft"] = rf
 
+    # ---- what the host can copy with all ranks at it: the ceiling of the host-buffer paths below ----
+    ceiling = None
+    if not args.skip_roundtrip:
+        ceiling = measure_copy_ceiling(torch, dist, dev, world)
+        extra["host_copy_ceiling"] = ceiling
+
+    def copy_bound_ms(h2d_bytes, d2h_bytes):
+        """time the copies alone need on this box when both directions run together (the measured duplex rate)"""
+        return 1e3 * max(h2d_bytes, d2h_bytes) / (ceiling["duplex_gbs_per_rank_per_direction"] * 1e9)
+
     # ---- BASELINE config 4 per rank: host audio -> analysis -> pitch pipeline -> resynthesis -> host stereo audio ----
     if not args.skip_roundtrip:
         rt_in = pkg.pinned_empty(x_host_np.shape)
@@ -459,9 +514,31 @@ def run_ours(args):
             "output_samples_per_s": world * S * n_samples / rt_s, "ms_per_call": 1e3 * rt_s,
             "notes_started": int(rt_stats[:, 0].sum()), "h2d_bytes": int(rt_in.nbytes), "d2h_bytes": int(rt_out.nbytes),
             "truncated_frames": pkg.truncated_frames(ctx),
+            "copy_bound_ms": copy_bound_ms(int(rt_in.nbytes), int(rt_out.nbytes)),
+            "frac_of_copy_ceiling": copy_bound_ms(int(rt_in.nbytes), int(rt_out.nbytes)) / (1e3 * rt_s),
             "note": "analysis (in FP64 on this path: the resynthesised phase integrates the peak frequencies), pitch pipeline (three "
                     "warps per stream pipelined over frames) and rendering all run on the device; only the audio crosses PCIe",
         }
+        # ---- the same call fed with 16-bit PCM (the job's WAV files): half the input bytes ----
+        rt_pcm = pkg.pinned_empty(x_host_np.shape, dtype=np.int16)
+        rt_pcm[:] = np.round(x_host_np * 32767.0).astype(np.int16)
+        pkg.resynth_roundtrip(ctx, rt_pcm, out=rt_out)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(rt_reps):
+            pkg.resynth_roundtrip(ctx, rt_pcm, out=rt_out)
+        pcm_s = (time.perf_counter() - t0) / rt_reps
+        if world > 1:
+            t = torch.tensor([pcm_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pcm_s = float(t.item())
+        extra["roundtrip_pcm16"] = {
+            "workload": f"C4 share with 16-bit PCM input: {S} streams x {SECONDS:g} s per GPU",
+            "output_samples_per_s": world * S * n_samples / pcm_s, "ms_per_call": 1e3 * pcm_s, "h2d_bytes": int(rt_pcm.nbytes),
+            "d2h_bytes": int(rt_out.nbytes), "copy_bound_ms": copy_bound_ms(int(rt_pcm.nbytes), int(rt_out.nbytes)),
+            "frac_of_copy_ceiling": copy_bound_ms(int(rt_pcm.nbytes), int(rt_out.nbytes)) / (1e3 * pcm_s),
+        }
+        del rt_pcm
         # ---- FFT vocoder (source/rt.resynth.lib.vocoder.cpp) at the reference defaults, same streams as the modulator ----
         vc_car = pkg.pinned_empty(x_host_np.shape)
         vc_car[:] = np.random.default_rng(77 + rank).uniform(-0.5, 0.5, x_host_np.shape).astype(np.float32)
@@ -480,6 +557,8 @@ def run_ours(args):
             "workload": f"{S} streams x {SECONDS:g} s per GPU, window 0.10 s, stride 0.005 s (241 samples, 512-point carrier FFT), 5 bands; pinned host audio in and out",
             "output_samples_per_s": world * S * n_samples / vc_s, "ms_per_call": 1e3 * vc_s,
             "h2d_bytes": int(2 * rt_in.nbytes), "d2h_bytes": int(vc_out.nbytes),
+            "copy_bound_ms": copy_bound_ms(int(2 * rt_in.nbytes), int(vc_out.nbytes)),
+            "frac_of_copy_ceiling": copy_bound_ms(int(2 * rt_in.nbytes), int(vc_out.nbytes)) / (1e3 * vc_s),
         }
         del rt_in, rt_out, vc_car, vc_out
 
@@ -506,6 +585,10 @@ def run_ours(args):
     per_frame = 4 * HOP + 4 * (NFFT // 2 + 1) + 4 + 12 * 16
     achieved = rows * per_frame / (kernel_ms * 1e-3) / 1e9
     noreuse = rows * (4 * WINDOW + 4 * (NFFT // 2 + 1)) / (kernel_ms * 1e-3) / 1e9
+    e2e_bound = None
+    if ceiling:
+        bound_s = max(h2d, d2h) / (ceiling["duplex_gbs_per_rank_per_direction"] * 1e9)
+        e2e_bound = {"copy_bound_ms_per_step": 1e3 * bound_s, "frac_of_copy_ceiling": bound_s / (e2e_s / e2e_steps)}
     line = {
         "metric": "stft_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -522,7 +605,8 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "outputs": "peak lists (bin, freq, dB, count) copied to the host; the spectrum, which the device-timed step also "
-                           "writes, stays in HBM here (extra.e2e_with_spectrum copies it too)"},
+                           "writes, stays in HBM here (extra.e2e_with_spectrum copies it too)",
+                "copy_ceiling": e2e_bound},
         "gpu_launches": launches_timed, "clocks": clocks, "extra": dict(extra, final_gather_ms=gather_ms, e2e_with_spectrum=e2e_sq),
     }
     _RESULT_LINE.append(json.dumps(line))

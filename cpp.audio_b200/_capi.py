@@ -14,7 +14,7 @@ DECLARED_SYMBOLS = [
     "ca_measure_fp32_peak", "ca_resynth_roundtrip_host", "ca_ramp_render_host", "ca_vocoder_host",
     "ca_oscbank_render_tracks", "ca_oscbank_render_tracks_host", "ca_tracks_open", "ca_tracks_post", "ca_tracks_pull",
     "ca_tracks_pull_host", "ca_tracks_state", "ca_tracks_close", "ca_resynth_truncated_frames", "ca_stft_plan_generation", "ca_sound_engine_render_host", "ca_sound_engine_specs",
-    "ca_waveform_harmonics",
+    "ca_waveform_harmonics", "ca_resynth_roundtrip_pcm16_host",
 ]
 
 
@@ -145,6 +145,7 @@ def lib():
     L.ca_oscbank_render_host.argtypes = [p, C.POINTER(OscBankDesc), p]
     L.ca_measure_fp32_peak.argtypes = [p, C.POINTER(C.c_double)]
     L.ca_resynth_roundtrip_host.argtypes = [p, C.POINTER(RoundtripParams), p, i64, i64, p, p]
+    L.ca_resynth_roundtrip_pcm16_host.argtypes = [p, C.POINTER(RoundtripParams), p, i64, i64, p, p]
     L.ca_ramp_render_host.argtypes = [p, C.POINTER(RampDesc), p]
     L.ca_vocoder_host.argtypes = [p, C.POINTER(VocoderParams), p, p, i64, i64, p]
     L.ca_oscbank_render_tracks.argtypes = [p, C.POINTER(TracksDesc), p, p, p]

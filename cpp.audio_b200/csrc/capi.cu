@@ -321,7 +321,14 @@ int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, co
                               int64_t n_streams, float* h_out, int64_t* h_stats) {
   if (!ctx) return CA_ERR_INVALID;
   DeviceGuard guard(ctx);
-  return roundtrip_host(ctx, params, h_x, n_samples, n_streams, h_out, h_stats);
+  return roundtrip_host(ctx, params, h_x, false, n_samples, n_streams, h_out, h_stats);
+}
+
+int ca_resynth_roundtrip_pcm16_host(ca_ctx* ctx, const ca_roundtrip_params* params, const int16_t* h_x, int64_t n_samples,
+                                    int64_t n_streams, float* h_out, int64_t* h_stats) {
+  if (!ctx) return CA_ERR_INVALID;
+  DeviceGuard guard(ctx);
+  return roundtrip_host(ctx, params, h_x, true, n_samples, n_streams, h_out, h_stats);
 }
 
 int64_t ca_resynth_truncated_frames(const ca_ctx* ctx) { return ctx ? ctx->rt_truncated_frames : 0; }

@@ -53,8 +53,8 @@ struct ca_ctx {
   void* d_osc_voices = nullptr;    // VoiceParams[max_voices]
 
   // scratch for the *_host entry points
-  void* d_scratch[12] = {};
-  size_t scratch_bytes[12] = {};
+  void* d_scratch[16] = {};
+  size_t scratch_bytes[16] = {};
   // pinned host staging of the round trip (peak lists coming down, segments going up)
   void* h_pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t pinned_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -130,7 +130,8 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
 int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials);
 int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaStream_t stream, int eased = -1);
 int measure_fp32_peak(ca_ctx* ctx, double* tflops);
-int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
+// h_x: float32 samples, or int16 PCM when pcm16 is set (converted on the device: x / 32768, exact)
+int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const void* h_x, bool pcm16, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats);
 int tracks_open(ca_ctx* ctx, const ca_tracks_desc* desc, ca_tracks** out);
 int tracks_post(ca_tracks* tp, const ca_track_event* events, int64_t n);

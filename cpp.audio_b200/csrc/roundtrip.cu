@@ -156,6 +156,37 @@ void run_stream(const PitchParams& p, const int32_t* peak_bin, const R* peak_off
 }
 
 
+// 16-bit PCM -> float as a WAV reader does it (x / 32768, exact in float32): the job's input crosses PCIe at 2 bytes per sample
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const short2 v = *reinterpret_cast<const short2*>(in + i);
+    *reinterpret_cast<float2*>(out + i) = make_float2(static_cast<float>(v.x) * (1.f / 32768.f), static_cast<float>(v.y) * (1.f / 32768.f));
+  } else if (i < n) {
+    out[i] = static_cast<float>(in[i]) * (1.f / 32768.f);
+  }
+}
+
+// host samples -> d_x on stream st: float32 goes straight up, 16-bit PCM goes up at half the bytes and is converted on the device
+int upload_samples(ca_ctx* ctx, const void* h_x, bool pcm16, size_t first, size_t count, float* d_x, cudaStream_t st) {
+  if (!pcm16) {
+    CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x + first, static_cast<const float*>(h_x) + first, sizeof(float) * count, cudaMemcpyHostToDevice, st));
+    return CA_OK;
+  }
+  int16_t* d_pcm = static_cast<int16_t*>(ctx->d_scratch[12]);
+  CA_CUDA_OK(ctx, cudaMemcpyAsync(d_pcm + first, static_cast<const int16_t*>(h_x) + first, sizeof(int16_t) * count, cudaMemcpyHostToDevice, st));
+  // (first is even whenever count is: streams of even length; an odd first only loses the 4-byte alignment of the pair loads)
+  if (first % 2 == 0) {
+    pcm16_to_float_kernel<<<static_cast<unsigned>((count / 2 + 256) / 256), 256, 0, st>>>(d_pcm + first, d_x + first, static_cast<int64_t>(count));
+  } else {
+    pcm16_to_float_kernel<<<1, 32, 0, st>>>(d_pcm + first, d_x + first, 1);
+    pcm16_to_float_kernel<<<static_cast<unsigned>((count / 2 + 256) / 256), 256, 0, st>>>(d_pcm + first + 1, d_x + first + 1, static_cast<int64_t>(count) - 1);
+  }
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
 // make_pitch_params for the kernels: the autotune table (a host pointer in the parameters) goes to the device first
 int device_pitch_params(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n_samples, int64_t frames, int P, PitchParams* out) {
   *out = make_pitch_params(prm, n_samples, frames, P);
@@ -264,7 +295,7 @@ int roundtrip_device_tail(ca_ctx* ctx, const ca_roundtrip_params& prm, int64_t n
 // The device path as a pipeline over groups of streams: every group runs H2D -> K2 -> pitch pipeline -> rendering -> D2H on its
 // own CUDA stream, so the copies of one group overlap the (latency-bound) tracking kernel of the others. Returns
 // CA_OK with *overflowed = true when the segment buffer was too small (the caller grows it and takes the sequential path).
-int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, const float* h_x, int64_t n_samples, int64_t n_streams,
+int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, const void* h_x, bool pcm16, int64_t n_samples, int64_t n_streams,
                                int64_t frames, float* h_out, int64_t* h_stats, bool use64, bool* overflowed, int64_t* needed) {
   const int P = prm.stft.max_peaks;
   PitchParams pp;
@@ -316,7 +347,8 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
     const size_t x0 = static_cast<size_t>(a0) * n_samples, r0 = static_cast<size_t>(a0) * frames;
     const int64_t t0 = a0 * tps, nt = ns * tps;
     if (g > 0) cudaStreamWaitEvent(sg, ready, 0);
-    cudaMemcpyAsync(d_x + x0, h_x + x0, sizeof(float) * ns * n_samples, cudaMemcpyHostToDevice, sg);
+    rc = upload_samples(ctx, h_x, pcm16, x0, static_cast<size_t>(ns) * n_samples, d_x, sg);
+    if (rc) break;
     if (use64)
       rc = stft64_peaks(ctx, ctx->plan_rt, d_x + x0, n_samples, ns, n_samples, d_pbin + r0 * P, reinterpret_cast<double*>(d_poff + r0 * P * esz),
                         reinterpret_cast<double*>(d_pdb + r0 * P * esz), d_pcnt + r0, sg);
@@ -353,7 +385,7 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
 
 }  // namespace
 
-int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples, int64_t n_streams,
+int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const void* h_x, bool pcm16, int64_t n_samples, int64_t n_streams,
                    float* h_out, int64_t* h_stats) {
   if (!params || !h_x || !h_out || n_samples < 0 || n_streams < 0)
     return fail(ctx, CA_ERR_INVALID, "ca_resynth_roundtrip_host: null argument or negative size");
@@ -414,6 +446,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   cudaStream_t st = ctx->own_stream;
   const size_t out_bytes = sizeof(float) * 2 * total;
   rc = ensure_scratch(ctx, 0, sizeof(float) * total);
+  if (!rc && pcm16) rc = ensure_scratch(ctx, 12, sizeof(int16_t) * total);
   if (!rc) rc = ensure_scratch(ctx, 7, out_bytes);
   rc = rc ? rc : ensure_scratch(ctx, 2, std::max<size_t>(16, sizeof(int32_t) * rows * P));
   for (int i = 3; i <= 4 && !rc; ++i) rc = ensure_scratch(ctx, i, std::max<size_t>(16, esz * rows * P));
@@ -424,7 +457,7 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   if (rows && !host_pitch && !timing && !env_sequential && n_streams >= 2) {
     bool overflowed = false;
     int64_t needed = 0;
-    rc = roundtrip_device_pipelined(ctx, prm, h_x, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed);
+    rc = roundtrip_device_pipelined(ctx, prm, h_x, pcm16, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed);
     if (rc || !overflowed) return rc;
     rc = ensure_scratch(ctx, 6, sizeof(Segment) * static_cast<size_t>(needed));  // rare: redo in one group with the exact size
     if (rc) return rc;
@@ -433,7 +466,8 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* 
   int cmax = 0;
   if (rows) {
     float* d_x = static_cast<float*>(ctx->d_scratch[0]);
-    CA_CUDA_OK(ctx, cudaMemcpyAsync(d_x, h_x, sizeof(float) * total, cudaMemcpyHostToDevice, st));
+    rc = upload_samples(ctx, h_x, pcm16, 0, total, d_x, st);
+    if (rc) return rc;
     if (use64)
       rc = stft64_peaks(ctx, ctx->plan_rt, d_x, n_samples, n_streams, n_samples, static_cast<int32_t*>(ctx->d_scratch[2]),
                         static_cast<double*>(ctx->d_scratch[3]), static_cast<double*>(ctx->d_scratch[4]),

@@ -21,7 +21,8 @@ def resynth_roundtrip(ctx: Context, x: np.ndarray, window: int = 4096, hop: int 
 
     Any host memory works; page-locked buffers (`pinned_empty`) let the copies run at PCIe speed: pageable memory is
     staged by the driver at a fraction of it."""
-    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float32)
+    pcm16 = np.asarray(x).dtype == np.int16   # 16-bit PCM: ca_resynth_roundtrip_pcm16_host (x / 32768 on the device)
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.int16 if pcm16 else np.float32)
     streams, n = x.shape
     if out is None:
         out = np.empty((streams, n, 2), dtype=np.float32)
@@ -32,8 +33,8 @@ def resynth_roundtrip(ctx: Context, x: np.ndarray, window: int = 4096, hop: int 
                         nearby_distance_tones, min_volume, max_track_pitches, gain, stereo_spread, e, max_channels, host_threads,
                         opts if opts is not None else PitchOptions())
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    ctx.check(lib().ca_resynth_roundtrip_host(ctx.handle, C.byref(p), vp(x), n, streams, vp(out), vp(stats)),
-              "ca_resynth_roundtrip_host")
+    fn = lib().ca_resynth_roundtrip_pcm16_host if pcm16 else lib().ca_resynth_roundtrip_host
+    ctx.check(fn(ctx.handle, C.byref(p), vp(x), n, streams, vp(out), vp(stats)), "ca_resynth_roundtrip_host")
     return out, stats
 
 

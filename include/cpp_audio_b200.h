@@ -212,6 +212,12 @@ typedef struct ca_roundtrip_params {
 int ca_resynth_roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const float* h_x, int64_t n_samples,
                               int64_t n_streams, float* h_out, int64_t* h_stats);
 
+/* The same with 16-bit PCM input, the usual content of the job's WAV files (RtResynthOfflineJob::read_voice,
+ * source/rt.resynth.lib.params.cpp:183-386): h_x [n_streams][n_samples] int16, taken as x / 32768 like a WAV reader does (exact in
+ * float32). The input crosses PCIe at 2 bytes per sample instead of 4; the call is copy-bound (multi-GPU). */
+int ca_resynth_roundtrip_pcm16_host(ca_ctx* ctx, const ca_roundtrip_params* params, const int16_t* h_x, int64_t n_samples,
+                                    int64_t n_streams, float* h_out, int64_t* h_stats);
+
 /* Frames of the last ca_resynth_roundtrip_host call on this ctx that lost something to a capacity: more than stft.max_peaks
  * peaks (only the first max_peaks, in ascending frequency, took part), or more than 256 entries left after aggregation and the
  * min_volume cut (the device pitch pipeline's list; the voice pool has 254 channels). The reference's lists are unbounded

@@ -205,3 +205,19 @@ def test_start_phase_synchronisation(pkg, orc, ctx):
     dev8, dstats8 = pkg.resynth_roundtrip(ctx, x, env=env, max_track_pitches=0.0, max_channels=8)
     assert np.array_equal(dstats8, rstats8) and rstats8[:, 1].min() > 0
     assert np.abs(dev8 - ref8).max() < 1e-5
+
+
+def test_pcm16_input(pkg, orc, ctx, wl):
+    """16-bit PCM input (the job's WAV files): converted on the device exactly as a WAV reader would, x / 32768."""
+    x = wl.c4_streams(3, 1.0)
+    pcm = np.round(x * 32767.0).astype(np.int16)
+    as_float = pcm.astype(np.float32) / np.float32(32768.0)
+    out, stats = pkg.resynth_roundtrip(ctx, pcm)
+    same, sstats = pkg.resynth_roundtrip(ctx, as_float)
+    assert np.array_equal(stats, sstats) and np.array_equal(out, same)
+    ref, rstats = orc.roundtrip(as_float)
+    assert np.array_equal(stats, rstats) and np.abs(out - ref).max() < 1e-5
+    odd = pcm[:1, :47999]                                          # odd length, one stream: the sequential path and its scalar tail
+    a, _ = pkg.resynth_roundtrip(ctx, odd)
+    b, _ = pkg.resynth_roundtrip(ctx, odd.astype(np.float32) / np.float32(32768.0))
+    assert np.array_equal(a, b)
