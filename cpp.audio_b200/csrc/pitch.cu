@@ -67,6 +67,18 @@ struct TrackArgs {
   int64_t tiles_per_stream;
   int64_t* stats;            // [streams][2]: notes started, notes dropped
   int32_t* overflow;         // set when a tile did not get its segments
+  // A launch walks the frames [k_begin, k_end) of every stream; tuned / tcount hold those frames only, [streams][chunk_frames].
+  // Between launches the whole state of a stream (the shared-memory image and a few registers) rests in `state`, so that the
+  // audio of the frames already tracked can be rendered and copied out while the tracker goes on (roundtrip.cu).
+  int64_t k_begin, k_end, chunk_frames;
+  unsigned char* state;      // [streams][state_stride]; null: a single launch over all frames
+  int64_t state_stride;
+  int32_t resume;            // take the state up from `state` instead of starting afresh
+};
+
+struct TrackRegs {  // what a stream keeps in registers between frames
+  int32_t N, Np, played_sel, pad;
+  int64_t started, dropped, tile, chunk_next, chunk_end;
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -162,7 +174,8 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
   const int64_t s = blockIdx.x;
   const int P = p.PT;  // entries per frame of the tuned lists
   const double dtrack = p.max_track;
-  const Tuned* tu_base = a.tuned + s * p.frames * P;
+  const int64_t n_frames = a.k_end - a.k_begin;  // frames of this launch; kr = k - k_begin indexes them
+  const Tuned* tu_base = a.tuned + s * a.chunk_frames * P;
   const int n_staged = min(P, 32);
   const uint32_t staged_bytes = static_cast<uint32_t>(n_staged * sizeof(Tuned));
   constexpr int kAhead = 2;  // frames staged ahead of the tracker (the voices warp still reads the slot of the frame before)
@@ -174,17 +187,39 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
   int32_t* next_played = sm.played[1];
   double* pl_pitch = sm.pl_pitch[0];
   double* np_pitch = sm.pl_pitch[1];
-  const int32_t* tc = a.tcount + s * p.frames;
-  auto load_counts = [&](int64_t k0) { return k0 + lane < p.frames ? tc[k0 + lane] : 0; };
+  const int32_t* tc = a.tcount + s * a.chunk_frames;
+  auto load_counts = [&](int64_t k0) { return k0 + lane < n_frames ? tc[k0 + lane] : 0; };
   int cnt_cur = 0, cnt_next = 0;
   // ---- voices state ----
   int64_t tile = s * a.tiles_per_stream;
   int64_t chunk_next = 0, chunk_end = 0;
 
-  for (int c = threadIdx.x; c < kMaxNotes; c += blockDim.x) sm.osc_ai_ch[c] = 0.0;
-  if (threadIdx.x < kMaxNotes / 32) {
-    const int lo = 32 * threadIdx.x;  // channels [0, max_channels) are free
-    sm.free_mask[threadIdx.x] = p.max_channels >= lo + 32 ? kFull : p.max_channels > lo ? (1u << (p.max_channels - lo)) - 1u : 0u;
+  uint4* st_img = a.state ? reinterpret_cast<uint4*>(a.state + s * a.state_stride) : nullptr;
+  TrackRegs* st_regs = a.state ? reinterpret_cast<TrackRegs*>(a.state + s * a.state_stride + sizeof(Track2Smem)) : nullptr;
+  static_assert(sizeof(Track2Smem) % 16 == 0, "the state image is copied in 16-byte words");
+  if (a.resume) {
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Track2Smem) / 16); i += blockDim.x) reinterpret_cast<uint4*>(smem_raw)[i] = st_img[i];
+    const TrackRegs r = *st_regs;
+    N = r.N;
+    Np = r.Np;
+    started = r.started;
+    dropped = r.dropped;
+    tile = r.tile;
+    chunk_next = r.chunk_next;
+    chunk_end = r.chunk_end;
+    if (r.played_sel) {
+      played = sm.played[1];
+      next_played = sm.played[0];
+      pl_pitch = sm.pl_pitch[1];
+      np_pitch = sm.pl_pitch[0];
+    }
+    __syncthreads();  // the image is in place before the barriers inside it are initialised again
+  } else {
+    for (int c = threadIdx.x; c < kMaxNotes; c += blockDim.x) sm.osc_ai_ch[c] = 0.0;
+    if (threadIdx.x < kMaxNotes / 32) {
+      const int lo = 32 * threadIdx.x;  // channels [0, max_channels) are free
+      sm.free_mask[threadIdx.x] = p.max_channels >= lo + 32 ? kFull : p.max_channels > lo ? (1u << (p.max_channels - lo)) - 1u : 0u;
+    }
   }
   if (is_tracker) {
     cnt_cur = load_counts(0);
@@ -193,7 +228,7 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
       for (int i = 0; i < kRing; ++i) mbar_init(&sm.bar[i], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       fence_proxy_async();
-      for (int f = 0; f < kAhead && f < p.frames; ++f) {
+      for (int f = 0; f < kAhead && f < n_frames; ++f) {
         mbar_expect_tx(&sm.bar[f], staged_bytes);
         bulk_g2s(sm.ring[f], tu_base + static_cast<int64_t>(f) * P, staged_bytes, &sm.bar[f]);
       }
@@ -204,27 +239,27 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
 #ifdef CA_PITCH_TIMELINE
   long long busy = 0;  // clocks this warp spent working (between leaving a barrier and arriving at the next)
 #endif
-  for (int64_t it = 0; it < p.frames + kWarps - 1; ++it) {
+  for (int64_t it = 0; it < n_frames + kWarps - 1; ++it) {
 #ifdef CA_PITCH_TIMELINE
     const long long t_in = clock64();
 #endif
     if (is_tracker) {
       // ================= tracker: frame k = it =================
-      const int64_t k = it;
-      if (k < p.frames) {
-        const Tuned* tu = tu_base + k * P;
-        FrameRec& rec = sm.rec[k % kWarps];
-        if ((k & 31) == 0 && k > 0) {
+      const int64_t kr = it, k = a.k_begin + kr;
+      if (kr < n_frames) {
+        const Tuned* tu = tu_base + kr * P;
+        FrameRec& rec = sm.rec[kr % kWarps];
+        if ((kr & 31) == 0 && kr > 0) {
           cnt_cur = cnt_next;
-          cnt_next = load_counts(k + 32);
+          cnt_next = load_counts(kr + 32);
         }
-        const int T = __shfl_sync(kFull, cnt_cur, static_cast<int>(k & 31));
-        const int slot = static_cast<int>(k % kRing);
-        mbar_wait(&sm.bar[slot], static_cast<uint32_t>((k / kRing) & 1));
+        const int T = __shfl_sync(kFull, cnt_cur, static_cast<int>(kr & 31));
+        const int slot = static_cast<int>(kr % kRing);
+        mbar_wait(&sm.bar[slot], static_cast<uint32_t>((kr / kRing) & 1));
         Tuned e0{};
         if (lane < n_staged) e0 = sm.ring[slot][lane];
-        if (lane == 0 && k + kAhead < p.frames) {  // slot of frame k + kAhead: last read by the voices warp an iteration ago
-          const int nslot = static_cast<int>((k + kAhead) % kRing);
+        if (lane == 0 && kr + kAhead < n_frames) {  // slot of frame kr + kAhead: last read by the voices warp an iteration ago
+          const int nslot = static_cast<int>((kr + kAhead) % kRing);
           mbar_expect_tx(&sm.bar[nslot], staged_bytes);
           bulk_g2s(sm.ring[nslot], tu + static_cast<int64_t>(kAhead) * P, staged_bytes, &sm.bar[nslot]);
         }
@@ -519,9 +554,9 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
       // The only thing a note's next glide needs from its past is the last emitted increment, and that follows from the glide
       // itself: f_at(len_frame - 1). So this warp owns that one value per slot, runs Glide::start for the changed notes and
       // leaves the constants in the record for the segments warp.
-      const int64_t k = it - 1;
-      if (k >= 0 && k < p.frames) {
-        FrameRec& rec = sm.rec[k % kWarps];
+      const int64_t kr = it - 1, k = a.k_begin + kr;
+      if (kr >= 0 && kr < n_frames) {
+        FrameRec& rec = sm.rec[kr % kWarps];
         const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
         const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
         // ---- start phase of the new notes (before this frame's glides move f_last) ----
@@ -599,9 +634,9 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
       }
     } else {
       // ================= voices / segments: frame k = it - (kWarps - 1) =================
-      const int64_t k = it - (kWarps - 1);
-      if (k >= 0) {
-        const FrameRec& rec = sm.rec[k % kWarps];
+      const int64_t kr = it - (kWarps - 1), k = a.k_begin + kr;
+      if (kr >= 0) {
+        const FrameRec& rec = sm.rec[kr % kWarps];
         const int T = rec.T, N_before = rec.N_before, NN = rec.N_after;
         const int64_t n_k = static_cast<int64_t>(p.W) - 1 + k * p.hop;
         const int len_frame = static_cast<int>(min(static_cast<int64_t>(p.hop), p.n_samples - n_k));
@@ -699,45 +734,88 @@ __global__ void __launch_bounds__(32 * kWarps) pitch_track3_kernel(const __grid_
     a.stats[2 * s] = started;
     a.stats[2 * s + 1] = dropped;
   }
+  if (st_img) {  // the stream's state rests in global memory until the launch of the next frames
+    __syncthreads();
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Track2Smem) / 16); i += blockDim.x) st_img[i] = reinterpret_cast<const uint4*>(smem_raw)[i];
+    if (is_tracker && lane == 0) {
+      st_regs->N = N;
+      st_regs->Np = Np;
+      st_regs->played_sel = played == sm.played[1] ? 1 : 0;
+      st_regs->started = started;
+      st_regs->dropped = dropped;
+    }
+    if (role == kWarps - 1 && lane == 0) {
+      st_regs->tile = tile;
+      st_regs->chunk_next = chunk_next;
+      st_regs->chunk_end = chunk_end;
+    }
+  }
 }
 
 }  // namespace
 
-// Tuned lists, then tracking and segments, for `n_streams` streams of `p.frames` frames whose peak lists are on the device.
+// Tuned lists of `rows` frames (any frames of any streams: the stage is stateless) from their peak lists.
+int pitch_prefix_device(ca_ctx* ctx, const PitchParams& p, int64_t rows, const int32_t* d_peak_bin, const void* d_peak_off, const void* d_peak_db,
+                        bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount,
+                        cudaStream_t st) {
+  if (p.PT > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: more than 256 tuned entries per frame are not supported by the device pitch pipeline");
+  if (rows == 0) return CA_OK;
+  if (peaks_f64) {
+    PrefixArgs<double> pa{p, d_peak_bin, static_cast<const double*>(d_peak_off), static_cast<const double*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
+    pitch_prefix_kernel<double><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
+  } else {
+    PrefixArgs<float> pa{p, d_peak_bin, static_cast<const float*>(d_peak_off), static_cast<const float*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
+    pitch_prefix_kernel<float><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
+  }
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
+size_t pitch_track_state_bytes() { return sizeof(Track2Smem) + sizeof(TrackRegs); }
+
+// Tracking and segments of the frames [k_begin, k_end) of `n_streams` streams; d_tuned / d_tcount hold those frames,
+// [streams][k_end - k_begin]. d_state (nullable: one launch over all frames) carries the streams from launch to launch.
+int pitch_track_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const Tuned* d_tuned, const int32_t* d_tcount, int64_t k_begin,
+                       int64_t k_end, unsigned char* d_state, Segment* d_segs, int64_t seg_capacity, int64_t n_tiles_per_stream,
+                       int64_t* d_tile_begin, int64_t* d_tile_end, int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats,
+                       unsigned long long* d_counter, int32_t* d_overflow, cudaStream_t st) {
+  if (p.PT > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: more than 256 tuned entries per frame are not supported by the device pitch pipeline");
+  if (p.max_channels > kMaxNotes) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_channels above 256 is not supported");
+  if (n_streams == 0 || k_end <= k_begin) return CA_OK;
+  TrackArgs ta{p, d_tuned, d_tcount, d_segs, d_counter, seg_capacity, d_tile_begin, d_tile_end, d_tile_s0, d_tile_len,
+               n_tiles_per_stream, d_stats, d_overflow, k_begin, k_end, k_end - k_begin, d_state,
+               static_cast<int64_t>((pitch_track_state_bytes() + 15) / 16 * 16), (d_state && k_begin > 0) ? 1 : 0};
+  static bool attr_set = false;
+  if (!attr_set) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
+    attr_set = true;
+  }
+  pitch_track3_kernel<<<static_cast<unsigned>(n_streams), 32 * kWarps, sizeof(Track2Smem), st>>>(ta);
+  CA_CUDA_OK(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return CA_OK;
+}
+
+// Both stages over all frames of `n_streams` streams in one go.
 // Outputs (device): segments, per-tile [begin, end) into them, first output sample and length of every tile, stats.
-// `needed` receives the number of segments the allocator handed out; when it exceeds seg_capacity the tiles past the
-// capacity carry no segments and the caller re-runs with a larger buffer.
+// When the allocator hands out more than seg_capacity segments the tiles past the capacity carry none, *d_overflow is set and
+// the caller re-runs with a larger buffer.
 int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
                           const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,
                           int64_t seg_capacity, int64_t n_tiles_per_stream, int64_t* d_tile_begin, int64_t* d_tile_end,
                           int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats, unsigned long long* d_counter,
                           int32_t* d_overflow, bool run_prefix, cudaStream_t st, bool reset_counters) {
-  if (p.PT > kMaxTuned) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: more than 256 tuned entries per frame are not supported by the device pitch pipeline");
-  if (p.max_channels > kMaxNotes) return fail(ctx, CA_ERR_UNSUPPORTED, "round trip: max_channels above 256 is not supported");
   const int64_t rows = n_streams * p.frames;
   if (rows == 0) return CA_OK;
-  if (run_prefix) {
-    if (peaks_f64) {
-      PrefixArgs<double> pa{p, d_peak_bin, static_cast<const double*>(d_peak_off), static_cast<const double*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
-      pitch_prefix_kernel<double><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
-    } else {
-      PrefixArgs<float> pa{p, d_peak_bin, static_cast<const float*>(d_peak_off), static_cast<const float*>(d_peak_db), d_peak_count, d_tuned, d_tcount, rows, d_truncated};
-      pitch_prefix_kernel<float><<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(pa);
-    }
-    CA_CUDA_OK(ctx, cudaGetLastError());
-    ctx->launches += 1;
-  }
+  if (run_prefix)
+    if (int rc = pitch_prefix_device(ctx, p, rows, d_peak_bin, d_peak_off, d_peak_db, peaks_f64, d_peak_count, d_truncated, d_tuned, d_tcount, st)) return rc;
   if (reset_counters) {
     CA_CUDA_OK(ctx, cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
     CA_CUDA_OK(ctx, cudaMemsetAsync(d_overflow, 0, sizeof(int32_t), st));
   }
-  TrackArgs ta{p, d_tuned, d_tcount, d_segs, d_counter, seg_capacity, d_tile_begin, d_tile_end, d_tile_s0, d_tile_len,
-               n_tiles_per_stream, d_stats, d_overflow};
-  CA_CUDA_OK(ctx, cudaFuncSetAttribute(pitch_track3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Track2Smem))));
-  pitch_track3_kernel<<<static_cast<unsigned>(n_streams), 32 * kWarps, sizeof(Track2Smem), st>>>(ta);
-  CA_CUDA_OK(ctx, cudaGetLastError());
-  ctx->launches += 1;
-  return CA_OK;
+  return pitch_track_device(ctx, p, n_streams, d_tuned, d_tcount, 0, p.frames, nullptr, d_segs, seg_capacity, n_tiles_per_stream, d_tile_begin,
+                            d_tile_end, d_tile_s0, d_tile_len, d_stats, d_counter, d_overflow, st);
 }
 
 }  // namespace ca

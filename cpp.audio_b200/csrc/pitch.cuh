@@ -588,6 +588,14 @@ inline int pool_note_on(const PitchParams& p, std::vector<Note>& notes, HostChan
 struct ca_ctx;
 namespace ca {
 // pitch.cu: tuned lists (pitch_prefix_kernel), then tracking and segments (pitch_track3_kernel, three warps per stream)
+int pitch_prefix_device(ca_ctx* ctx, const PitchParams& p, int64_t rows, const int32_t* d_peak_bin, const void* d_peak_off, const void* d_peak_db,
+                        bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount,
+                        cudaStream_t st);
+size_t pitch_track_state_bytes();
+int pitch_track_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const Tuned* d_tuned, const int32_t* d_tcount, int64_t k_begin,
+                       int64_t k_end, unsigned char* d_state, Segment* d_segs, int64_t seg_capacity, int64_t n_tiles_per_stream,
+                       int64_t* d_tile_begin, int64_t* d_tile_end, int64_t* d_tile_s0, int32_t* d_tile_len, int64_t* d_stats,
+                       unsigned long long* d_counter, int32_t* d_overflow, cudaStream_t st);
 // d_peak_off / d_peak_db: float arrays, or double arrays when peaks_f64 is set (the FP64 analysis of stft64.cu)
 int pitch_pipeline_device(ca_ctx* ctx, const PitchParams& p, int64_t n_streams, const int32_t* d_peak_bin, const void* d_peak_off,
                           const void* d_peak_db, bool peaks_f64, const int32_t* d_peak_count, unsigned long long* d_truncated, Tuned* d_tuned, int32_t* d_tcount, Segment* d_segs,

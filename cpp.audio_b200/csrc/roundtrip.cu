@@ -167,6 +167,15 @@ __global__ void __launch_bounds__(256) pcm16_to_float_kernel(const int16_t* __re
   }
 }
 
+// the same over a range of samples of every stream ([streams][stride] arrays)
+__global__ void __launch_bounds__(256) pcm16_to_float_2d_kernel(const int16_t* __restrict__ in, float* __restrict__ out, int64_t w, int64_t stride) {
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  const int16_t* row_in = in + static_cast<int64_t>(blockIdx.y) * stride;
+  float* row_out = out + static_cast<int64_t>(blockIdx.y) * stride;
+  if (i < w) row_out[i] = static_cast<float>(row_in[i]) * (1.f / 32768.f);
+  if (i + 1 < w) row_out[i + 1] = static_cast<float>(row_in[i + 1]) * (1.f / 32768.f);
+}
+
 // host samples -> d_x on stream st: float32 goes straight up, 16-bit PCM goes up at half the bytes and is converted on the device
 int upload_samples(ca_ctx* ctx, const void* h_x, bool pcm16, size_t first, size_t count, float* d_x, cudaStream_t st) {
   if (!pcm16) {
@@ -383,6 +392,151 @@ int roundtrip_device_pipelined(ca_ctx* ctx, const ca_roundtrip_params& prm, cons
   return CA_OK;
 }
 
+// The device path as a pipeline over TIME: the streams are cut into chunks of consecutive frames, and chunk c goes through
+//   copy engine (up)   samples the chunk's frames read, all streams (one 2-D copy)
+//   stream A           analysis + tuned lists of the chunk's frames
+//   stream B           tracking of the chunk's frames (the tracker is sequential over frames; its state rests in global memory
+//                      between launches, pitch.cu), one launch per chunk, in order
+//   stream C + copy engine (down)   rendering of the chunk's tiles, then the chunk's audio goes back (one 2-D copy)
+// so the audio of the first chunk is on its way to the host while the tracker is still walking the later ones. The tracker is
+// latency-bound (a fixed ~1.5 us per frame whatever the number of streams) and the copy back is the largest transfer of the call:
+// run one after the other they add up, overlapped the call takes the longer of the two. Returns CA_OK with *overflowed = true when
+// the segment buffer was too small (the caller grows it and takes the sequential path).
+int roundtrip_device_chunked(ca_ctx* ctx, const ca_roundtrip_params& prm, const void* h_x, bool pcm16, int64_t n_samples, int64_t n_streams,
+                             int64_t frames, float* h_out, int64_t* h_stats, bool use64, bool* overflowed, int64_t* needed) {
+  const int P = prm.stft.max_peaks, W = prm.stft.window, hop = prm.stft.hop;
+  PitchParams pp;
+  if (int prc = device_pitch_params(ctx, prm, n_samples, frames, P, &pp)) return prc;
+  const size_t rows = static_cast<size_t>(frames) * n_streams;
+  const int64_t tps = tiles_per_stream(pp), n_tiles = tps * n_streams;
+  const size_t b_tiles = (3 * sizeof(int64_t) + sizeof(int32_t)) * static_cast<size_t>(n_tiles);
+  const size_t b_misc = sizeof(int64_t) * 2 * n_streams + 24;  // stats, allocator counter, overflow flag, truncated frames
+  const size_t state_stride = (pitch_track_state_bytes() + 15) / 16 * 16;
+  int rc = ensure_scratch(ctx, 8, sizeof(Tuned) * rows * pp.PT);
+  if (!rc) rc = ensure_scratch(ctx, 9, sizeof(int32_t) * rows);
+  if (!rc) rc = ensure_scratch(ctx, 10, b_misc);
+  if (!rc) rc = ensure_scratch(ctx, 1, b_tiles);
+  if (!rc) rc = ensure_scratch(ctx, 13, state_stride * static_cast<size_t>(n_streams));
+  if (!rc) rc = ensure_pinned(ctx, 0, b_misc);
+  const int64_t guess = std::max<int64_t>(n_tiles * std::min(prm.max_channels, 48), n_streams * 8192);
+  if (!rc && ctx->scratch_bytes[6] < sizeof(Segment) * static_cast<size_t>(guess)) rc = ensure_scratch(ctx, 6, sizeof(Segment) * guess);
+  if (rc) return rc;
+  static const int max_chunks = [] { const char* e = getenv("CA_RT_CHUNKS"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : v > 64 ? 64 : v; }();
+  const int chunks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(max_chunks, frames / 64)));
+  for (int g = 0; g < 4; ++g)
+    if (!ctx->pipe_streams[g]) CA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->pipe_streams[g], cudaStreamNonBlocking));
+  cudaStream_t s_up = ctx->pipe_streams[0], s_ana = ctx->pipe_streams[1], s_trk = ctx->pipe_streams[2], s_out = ctx->pipe_streams[3];
+  float* d_x = static_cast<float*>(ctx->d_scratch[0]);
+  int32_t* d_pbin = static_cast<int32_t*>(ctx->d_scratch[2]);
+  char* d_poff = static_cast<char*>(ctx->d_scratch[3]);  // float or double entries (use64)
+  char* d_pdb = static_cast<char*>(ctx->d_scratch[4]);
+  const size_t esz = use64 ? sizeof(double) : sizeof(float);
+  int32_t* d_pcnt = static_cast<int32_t*>(ctx->d_scratch[5]);
+  Tuned* d_tuned = static_cast<Tuned*>(ctx->d_scratch[8]);
+  int32_t* d_tcount = static_cast<int32_t*>(ctx->d_scratch[9]);
+  float* d_out = static_cast<float*>(ctx->d_scratch[7]);
+  int64_t* d_begin = static_cast<int64_t*>(ctx->d_scratch[1]);
+  int64_t* d_end = d_begin + n_tiles;
+  int64_t* d_s0 = d_end + n_tiles;
+  int32_t* d_len = reinterpret_cast<int32_t*>(d_s0 + n_tiles);
+  int64_t* d_stats = static_cast<int64_t*>(ctx->d_scratch[10]);
+  unsigned long long* d_counter = reinterpret_cast<unsigned long long*>(d_stats + 2 * n_streams);
+  int32_t* d_overflow = reinterpret_cast<int32_t*>(d_counter + 1);
+  unsigned long long* d_trunc = d_counter + 2;
+  unsigned char* d_state = static_cast<unsigned char*>(ctx->d_scratch[13]);
+  int64_t* h_misc = static_cast<int64_t*>(ctx->h_pinned[0]);
+  const int64_t capacity = static_cast<int64_t>(ctx->scratch_bytes[6] / sizeof(Segment));
+  // tiles before every frame (a frame interval is one tile, or several when the hop exceeds kMaxTile; the last ones are shorter)
+  std::vector<int64_t> tile_of(frames + 1, 0);
+  for (int64_t k = 0; k < frames; ++k) {
+    const int64_t n_k = static_cast<int64_t>(W) - 1 + k * hop;
+    const int64_t len = std::min<int64_t>(hop, n_samples - n_k);
+    tile_of[k + 1] = tile_of[k] + (len <= 0 ? 1 : (len + kMaxTile - 1) / kMaxTile);
+  }
+  std::vector<cudaEvent_t> ev(3 * chunks + 1, nullptr);
+  for (auto& e : ev) CA_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto cleanup = [&] {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  };
+  cudaError_t err = cudaSuccess;
+  auto ok = [&](cudaError_t e) {
+    if (err == cudaSuccess && e != cudaSuccess) err = e;
+  };
+  // counters shared by the chunks are reset before anything else runs; silence before the first frame
+  ok(cudaMemsetAsync(d_counter, 0, 24, s_up));
+  ok(cudaEventRecord(ev[3 * chunks], s_up));
+  ok(cudaStreamWaitEvent(s_ana, ev[3 * chunks], 0));
+  ok(cudaStreamWaitEvent(s_trk, ev[3 * chunks], 0));
+  ok(cudaMemsetAsync(d_out, 0, sizeof(float) * 2 * static_cast<size_t>(n_streams) * n_samples, s_out));
+  const size_t in_sz = pcm16 ? sizeof(int16_t) : sizeof(float);
+  int16_t* d_pcm = pcm16 ? static_cast<int16_t*>(ctx->d_scratch[12]) : nullptr;
+  int64_t up_to = 0;  // samples [0, up_to) of every stream are on their way to the device
+  for (int c = 0; c < chunks && !rc; ++c) {
+    const int64_t k0 = frames * c / chunks, k1 = frames * (c + 1) / chunks, fc = k1 - k0;
+    const size_t r0 = static_cast<size_t>(n_streams) * k0;  // rows before this chunk: its arrays are [streams][fc] from there
+    // ---- up: the samples this chunk's frames read ----
+    const int64_t need = c + 1 == chunks ? n_samples : std::min<int64_t>(n_samples, ((k1 - 1) * hop + W + 1) & ~int64_t(1));
+    if (need > up_to) {
+      const size_t w = static_cast<size_t>(need - up_to);
+      if (pcm16) {
+        ok(cudaMemcpy2DAsync(d_pcm + up_to, sizeof(int16_t) * n_samples, static_cast<const int16_t*>(h_x) + up_to, sizeof(int16_t) * n_samples,
+                             sizeof(int16_t) * w, n_streams, cudaMemcpyHostToDevice, s_up));
+        pcm16_to_float_2d_kernel<<<dim3(static_cast<unsigned>((w / 2 + 256) / 256), static_cast<unsigned>(n_streams)), 256, 0, s_up>>>(
+            d_pcm + up_to, d_x + up_to, static_cast<int64_t>(w), n_samples);
+        ctx->launches += 1;
+      } else {
+        ok(cudaMemcpy2DAsync(d_x + up_to, in_sz * n_samples, static_cast<const float*>(h_x) + up_to, in_sz * n_samples, in_sz * w, n_streams,
+                             cudaMemcpyHostToDevice, s_up));
+      }
+      up_to = need;
+    }
+    ok(cudaEventRecord(ev[3 * c], s_up));
+    // ---- analysis and tuned lists of frames [k0, k1) ----
+    ok(cudaStreamWaitEvent(s_ana, ev[3 * c], 0));
+    const int64_t span = (fc - 1) * hop + W;
+    if (use64)
+      rc = stft64_peaks(ctx, ctx->plan_rt, d_x + k0 * hop, span, n_streams, n_samples, d_pbin + r0 * P, reinterpret_cast<double*>(d_poff + r0 * P * esz),
+                        reinterpret_cast<double*>(d_pdb + r0 * P * esz), d_pcnt + r0, s_ana);
+    else
+      rc = stft_analyze(ctx, ctx->plan_rt, d_x + k0 * hop, span, n_streams, n_samples, nullptr, 0, d_pbin + r0 * P,
+                        reinterpret_cast<float*>(d_poff + r0 * P * esz), reinterpret_cast<float*>(d_pdb + r0 * P * esz), d_pcnt + r0, s_ana);
+    if (rc) break;
+    rc = pitch_prefix_device(ctx, pp, n_streams * fc, d_pbin + r0 * P, d_poff + r0 * P * esz, d_pdb + r0 * P * esz, use64, d_pcnt + r0, d_trunc,
+                             d_tuned + r0 * pp.PT, d_tcount + r0, s_ana);
+    if (rc) break;
+    ok(cudaEventRecord(ev[3 * c + 1], s_ana));
+    // ---- tracking of frames [k0, k1), every stream taking its state up where the chunk before left it ----
+    ok(cudaStreamWaitEvent(s_trk, ev[3 * c + 1], 0));
+    rc = pitch_track_device(ctx, pp, n_streams, d_tuned + r0 * pp.PT, d_tcount + r0, k0, k1, chunks > 1 ? d_state : nullptr,
+                            static_cast<Segment*>(ctx->d_scratch[6]), capacity, tps, d_begin, d_end, d_s0, d_len, d_stats, d_counter, d_overflow, s_trk);
+    if (rc) break;
+    ok(cudaEventRecord(ev[3 * c + 2], s_trk));
+    // ---- rendering of the chunk's tiles and its audio back to the host ----
+    ok(cudaStreamWaitEvent(s_out, ev[3 * c + 2], 0));
+    const int64_t t0 = tile_of[k0], nt = tile_of[k1] - t0;
+    TileArgs ta{static_cast<const Segment*>(ctx->d_scratch[6]), d_begin, d_s0, d_len, nt * n_streams, d_out, 0, d_end, tps, t0, nt};
+    tracks_kernel<false><<<static_cast<unsigned>((nt * n_streams + 3) / 4), 128, 0, s_out>>>(ta);
+    ctx->launches += 1;
+    const int64_t o0 = c == 0 ? 0 : std::min<int64_t>(n_samples, static_cast<int64_t>(W) - 1 + k0 * hop);
+    const int64_t o1 = c + 1 == chunks ? n_samples : std::min<int64_t>(n_samples, static_cast<int64_t>(W) - 1 + k1 * hop);
+    if (o1 > o0)
+      ok(cudaMemcpy2DAsync(h_out + 2 * o0, sizeof(float) * 2 * n_samples, d_out + 2 * o0, sizeof(float) * 2 * n_samples, sizeof(float) * 2 * (o1 - o0),
+                           n_streams, cudaMemcpyDeviceToHost, s_out));
+  }
+  ok(cudaGetLastError());
+  for (int g = 0; g < 4; ++g) ok(cudaStreamSynchronize(ctx->pipe_streams[g]));
+  cleanup();
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(ctx, CA_ERR_CUDA, std::string("round trip (time chunks): ") + cudaGetErrorString(err));
+  CA_CUDA_OK(ctx, cudaMemcpy(h_misc, d_stats, b_misc, cudaMemcpyDeviceToHost));
+  *needed = h_misc[2 * n_streams];
+  *overflowed = *reinterpret_cast<const int32_t*>(h_misc + 2 * n_streams + 1) != 0;
+  if (!*overflowed && h_stats) memcpy(h_stats, h_misc, sizeof(int64_t) * 2 * n_streams);
+  ctx->rt_truncated_frames = h_misc[2 * n_streams + 2];
+  return CA_OK;
+}
+
 }  // namespace
 
 int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const void* h_x, bool pcm16, int64_t n_samples, int64_t n_streams,
@@ -454,10 +608,12 @@ int roundtrip_host(ca_ctx* ctx, const ca_roundtrip_params* params, const void* h
   if (!rc) rc = ensure_pinned(ctx, 0, std::max<size_t>(16, sizeof(int32_t) * rows));
   if (rc) return rc;
   static const bool env_sequential = getenv("CA_RT_SEQUENTIAL") != nullptr;  // one stream group, for A/B
-  if (rows && !host_pitch && !timing && !env_sequential && n_streams >= 2) {
+  if (rows && !host_pitch && !timing && !env_sequential) {
     bool overflowed = false;
     int64_t needed = 0;
-    rc = roundtrip_device_pipelined(ctx, prm, h_x, pcm16, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed);
+    static const bool by_streams = [] { const char* e = getenv("CA_RT_PIPELINE"); return e && !strcmp(e, "streams"); }();  // A/B: the stream-group pipeline
+    rc = by_streams ? roundtrip_device_pipelined(ctx, prm, h_x, pcm16, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed)
+                    : roundtrip_device_chunked(ctx, prm, h_x, pcm16, n_samples, n_streams, frames, h_out, h_stats, use64, &overflowed, &needed);
     if (rc || !overflowed) return rc;
     rc = ensure_scratch(ctx, 6, sizeof(Segment) * static_cast<size_t>(needed));  // rare: redo in one group with the exact size
     if (rc) return rc;

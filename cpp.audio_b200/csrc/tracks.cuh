@@ -45,6 +45,9 @@ struct TileArgs {
   float* out;                     // interleaved stereo (mono for tracks_kernel<true>)
   int32_t accumulate;             // mono only: atomicAdd into out (tiles of different voices overlap) instead of storing
   const int64_t* tile_seg_end = nullptr;  // [tiles] one past the last segment of each tile; null: tile_seg_begin[tile + 1]
+  // a launch over a tile range of every row of a [rows][row_tiles] tile table: flat index i -> row i / range_tiles, tile
+  // range_first + i % range_tiles of that row (row_tiles == 0: the flat index is the tile)
+  int64_t row_tiles = 0, range_first = 0, range_tiles = 0;
 };
 
 __device__ __forceinline__ float alias_gain(float ai) {  // freqAliasingMultiplicator, include/audioelement.h:466-483
@@ -61,8 +64,9 @@ constexpr int kMaxTile = 1024;  // samples per tile (hop); 32 steps of 32 lanes
 template <bool kMono>
 __global__ void __launch_bounds__(128) tracks_kernel(const __grid_constant__ TileArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  int64_t tile = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (tile >= a.n_tiles) return;
+  if (a.row_tiles) tile = (tile / a.range_tiles) * a.row_tiles + a.range_first + tile % a.range_tiles;
   const int len = a.tile_len[tile];
   const int64_t s_begin = a.tile_seg_begin[tile], s_end = a.tile_seg_end ? a.tile_seg_end[tile] : a.tile_seg_begin[tile + 1];
   float2* out = reinterpret_cast<float2*>(a.out) + (kMono ? 0 : a.tile_sample0[tile]);
