@@ -430,6 +430,8 @@ def run_ours(args):
             "note": "official count = 8 FLOP per partial-sample (rotate 6 + MAC 2, SURVEY §8d); the kernel executes 3 FP32 "
                     "instructions (4 FLOP) per partial-sample via the Reinsch recurrence, so the official fraction can exceed 1",
             "hbm_write_gbs": voice_samples * 4 / world / 1e9,
+            # FP32-pipe utilisation as ncu counts it (sm__pipe_fma_cycles_active of the committed capture; a constant, not measured here)
+            "ncu": ncu_traffic("oscbank_kernel_counters"),
         }
         del sout
 

@@ -6,12 +6,15 @@
 //
 //   pitch_prefix_kernel  one THREAD per frame: peaks -> tuned list. Stateless, so all frames of all streams run at once and the
 //                        double-precision log2 / pow of every peak leave the sequential part.
-//   pitch_track_kernel   one WARP per stream walks the frames in order (the played-notes state is carried from frame to frame,
-//                        :1710-1758). Inside a frame lanes = tuned entries / notes: greedy monotone matching by bisection with an
-//                        exact serial fallback, note-off / note-change / note-on, ordering by rank counting, one Segment per
-//                        sounding note and render tile (the closed forms of tracks.cuh), pool compaction by ballot prefix sums.
-//                        Segment storage comes from a global bump allocator in chunks (one atomic per ~500 tiles); when the
-//                        capacity guess is too small the kernel keeps counting and the host re-runs it with the exact size.
+//   pitch_track3_kernel  three WARPS per stream walk the frames in order (the played-notes state is carried from frame to
+//                        frame, :1710-1758) as a pipeline: tracker, glides, segments (see the comment above the kernel). Inside a
+//                        frame lanes = tuned entries / notes: greedy monotone matching with an exact serial fallback, note-off /
+//                        note-change / note-on on the lowest free channel, ordering by rank counting, the start-phase rule of the
+//                        voice pool, one Segment per sounding note and render tile (the closed forms of tracks.cuh), pool
+//                        compaction by ballot prefix sums. Segment storage comes from a global bump allocator in chunks; when
+//                        the capacity guess is too small the kernel keeps counting and the host re-runs it with the exact size.
+//                        A launch takes a range of frames: the state of a stream rests in global memory in between, so the
+//                        caller can render and ship the audio of the frames already tracked (roundtrip.cu).
 #include <stdio.h>
 #include <stdlib.h>
 

@@ -4,7 +4,8 @@
 // forward_fft (source/main.test_fft.cpp:78). The kernels live in rfftw.cu:
 //   N <= 4096           one warp per frame (two frames per warp at N = 1024), frame in registers + one shared-memory exchange
 //   N = 8192 .. 32768   one CTA per frame, frame resident in shared memory between its single read and single write of HBM
-//   N >= 65536          three passes through HBM (column FFTs, 8192-point row FFTs, untangling transposition)
+//   N >= 65536          two passes through HBM: column FFTs (big2_cols_kernel), then 1024-point row FFTs with the untangling
+//                       (big2_rows_kernel)
 #include "common.cuh"
 #include "ctx.hpp"
 

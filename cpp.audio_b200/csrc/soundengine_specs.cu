@@ -3,7 +3,7 @@
 // and the harmonic tables of the non-sine oscillators. Control-rate host code: a note is a few dozen draws.
 //
 // The lambdas attached to the chains' nodes are in the reference tree and are restated here. The MarkovChain class itself and
-// the random generator (mersenne<SEEDED::Yes>()) are in cpp.algorithms, which is absent: oracle/SPEC.md S14 fixes
+// the random generator (mersenne<SEEDED::Yes>()) are in cpp.algorithms, which is absent: oracle/SPEC.md S15 fixes
 //   step_normalized(u)  the outgoing transitions of the current node, probabilities rescaled to sum 1, picked by u in [0,1)
 //   step(u)             the raw probabilities; u beyond their sum: stay (no lambda runs)
 //   a move from a to b  runs a's lambda with LEAVE_NODE, then b's with ENTER_NODE

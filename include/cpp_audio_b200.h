@@ -307,7 +307,7 @@ int ca_ramp_render_host(ca_ctx* ctx, const ca_ramp_desc* desc, float* h_out);
  * VolumeAdjusted<Enveloped<FreqCtrl_<Mix<LoudnessVolumeAdjusted<Sine>>, LogRamp>, AHDSR>> that fade in and out over xfade_len samples
  * (the orchestration of orchestrate_algos / playNextSpec, :744-803). The specs are what the engine's Markov chain produces at
  * note-on (:496-736): ca_sound_engine_specs below builds them (the chain and the random generator live in cpp.algorithms: its
- * decisions are oracle/SPEC.md S14), or the host supplies its own. Events: NoteOn at key_on (the first spec starts on that sample),
+ * decisions are oracle/SPEC.md S15), or the host supplies its own. Events: NoteOn at key_on (the first spec starts on that sample),
  * NoteOff at key_off (nothing starts any more, the sounding ramp is released). Host pointers. */
 typedef struct ca_ramp_spec { /* one entry of SoundEngine::RampSpecs (include/soundengine.h:1030-1122) */
   float from_hz, to_hz;    /* LogRamp::setup(freq_to_angle_increment(from), freq_to_angle_increment(to), duration, start_sample, itp) */
@@ -341,7 +341,7 @@ int ca_sound_engine_render_host(ca_ctx* ctx, const ca_sound_engine_desc* desc, f
 /* The ramp specs of one note as SoundEngine::initialize_{birds,robot,sweep} + do_initialize produce them (include/soundengine.h
  * :496-736, :883-1003): the Markov chain is run on the host at note-on, min_path_length normalised steps then additional_tries plain
  * steps. mode: 0 BIRDS, 1 ROBOTS, 2 SWEEP (SoundEngineMode). The chain class and mersenne<> are in cpp.algorithms: the walk and the
- * draws follow oracle/SPEC.md S14 with a generator seeded by `seed`. Returns the number of specs written (<= 30), negative on error. */
+ * draws follow oracle/SPEC.md S15 with a generator seeded by `seed`. Returns the number of specs written (<= 30), negative on error. */
 typedef struct ca_sound_engine_gen {
   int32_t mode;
   int32_t sample_rate;

@@ -131,7 +131,7 @@ def test_unsupported_fft_length_fails_loudly(pkg, ctx):
 @pytest.mark.parametrize("window,hop,sr", [(1024, 256, 48000), (2000, 300, 48000), (8000, 3969, 44100), (16384, 1024, 48000),
                                            (30000, 5000, 48000)])
 def test_other_fft_lengths_generic_path(pkg, orc, ctx, wl, window, hop, sr):
-    """Windows whose FFT length is not 4096 take the three-pass path (window 8000 / stride 3969 at 44.1 kHz are the
+    """Windows whose FFT length is not 4096 take the fused kernels of csrc/rfftw.cu (window 8000 / stride 3969 at 44.1 kHz are the
     reference defaults: 0.1814 s and 0.09 s, source/rt.resynth.lib.cpp:945-946)."""
     x = wl.c4_streams(2, 1.5)
     res = run_gpu(pkg, ctx, x, window, hop, sample_rate=sr)
