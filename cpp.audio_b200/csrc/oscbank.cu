@@ -7,10 +7,14 @@
 //
 // B200 design (not a translation of the per-sample phasor loop):
 //   * lanes = 32 consecutive samples; a warp renders a chunk of R*32 samples of one voice.
-//   * in the sustain regime a partial is advanced 32 samples at a time by the Reinsch form of the two-term
-//     recurrence  d -= kappa*y ; y += d  (1 FFMA + 1 FADD, + 1 FADD to accumulate) instead of a 4-instruction complex
-//     rotation; the 32-sample rotation angle is folded into (-pi/2, pi/2] (alternating sign for the other half) so
-//     the recurrence stays as accurate as the rotation (measured: 2.5e-6 max abs after 64 steps, tests/test_oscbank.py).
+//   * in the sustain regime the chunk is a small matrix product on the FP32 pipe: sample 32k+l of the chunk is
+//         sum_p Im( e_p[l] * F_p[k] ),   e_p[l] = amp_p exp(i theta_p(n0+l))  (32 values per partial, per chunk),
+//                                        F_p[k] = exp(i 32 k w_p)             (64 values per partial, per voice),
+//     i.e. TWO fused multiply-adds per partial-sample and no serial dependence between steps. A thread owns 8 l x 8 k
+//     outputs (32 packed accumulators) and reads 8+8 complex operands per partial, so one partial costs 64 FFMA2 for
+//     8 LDS.128; the k operand enters FFMA2 as a 32-bit broadcast register. (Round 1's Reinsch recurrence
+//     d -= kappa*y ; y += d ; acc += y was 3 operations per partial-sample in a dependent chain that the register-file
+//     ports held to 2.2-2.6 of 4 warp-instructions per clock, profiles/microbench/fp32_ports_b200.txt.)
 //   * every chunk is re-seeded from an EXACT phase: phases are 64-bit fixed-point turns (phase0 + (n+1)*inc mod 2^64),
 //     so fp32 never accumulates phase over the 480,000-sample note (the reference runs in double).
 //   * chunks that contain an envelope transition (attack, decay, release) take a general path: complex rotation per
@@ -19,6 +23,8 @@
 //     launches the pass(es) its envelopes need and each pass skips the voices of the other kind.
 //   * partial parameters are prepared once per render by a small kernel, in double where the reference is in double.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ctx.hpp"
@@ -32,14 +38,13 @@ constexpr int kNP = 32;       // partials per pass (register resident)
 constexpr int kR = 64;        // 32-sample steps per chunk
 constexpr int kChunk = 32 * kR;
 constexpr int kMaxPartials = 128;
+constexpr int kEP = 40;       // row pitch of the lane-offset table in float2: rows p, p+1 start 16 banks apart
 
 struct __align__(16) PartialParams {
   uint64_t inc;   // phase increment per sample, turns * 2^64
   uint64_t ph0;   // phase before the first step
   float amp;      // volume * partial volume * aliasing gain (0 for padding / dropped harmonics)
-  float kappa;    // 4 sin^2(Of/2), Of = 32-sample rotation folded into (-pi/2, pi/2]
-  float so;       // sin(Of)
-  float sgn;      // +1, or -1 when Of = O -+ pi (output alternates sign every step)
+  float pad0[3];
   float rot_re;   // exp(i*O), unfolded 32-sample rotation
   float rot_im;
   int32_t attack;   // effective durations in samples (floors applied)
@@ -156,16 +161,7 @@ __global__ void osc_prep_kernel(const __grid_constant__ PrepArgs a) {
   sincospi(2.0 * (static_cast<double>(s_unf) / two64), &sn, &cs);
   pp.rot_re = static_cast<float>(cs);
   pp.rot_im = static_cast<float>(sn);
-  int64_t s_f = s_unf;
-  pp.sgn = 1.f;
-  if (s_f >= (1ll << 62) || s_f < -(1ll << 62)) {
-    s_f = static_cast<int64_t>(step ^ 0x8000000000000000ull);
-    pp.sgn = -1.f;
-  }
-  const double of_turns = static_cast<double>(s_f) / two64;  // in [-1/4, 1/4]
-  const double sh = sinpi(of_turns);                          // sin(Of/2)
-  pp.kappa = static_cast<float>(4.0 * sh * sh);
-  pp.so = static_cast<float>(sinpi(2.0 * of_turns));
+  pp.pad0[0] = pp.pad0[1] = pp.pad0[2] = 0.f;
   a.partials[v * a.ppad + p] = pp;
 }
 
@@ -177,6 +173,7 @@ struct OscArgs {
   int32_t ppad;
   int32_t mix;
   int32_t voices_per_group;
+  int32_t chunks_per_warp;
   int64_t n_chunks;
   int64_t first_sample;  // global index of output sample 0 (phases and envelopes are closed-form in the global index)
   float* out;
@@ -187,6 +184,20 @@ __device__ __forceinline__ float2 cis_turns_u64(uint64_t ph) {  // exp(2 pi i * 
   float s, c;
   sincospif(static_cast<float>(top) * (1.f / 2147483648.f), &s, &c);  // top/2^31 = 2*turns
   return make_float2(c, s);
+}
+
+// x = hi + lo with hi, lo representable in TF32 (10-bit mantissa): hi*hi' + lo*hi' + hi*lo' reproduces the FP32 product of two
+// such pairs to ~2^-22 relative (the dropped lo*lo' term), accumulated in FP32 by the tensor core
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col), TF32 operands, FP32 accumulation (SASS HMMA.1688.F32.TF32)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // itp::interpolate as b + c*e(u), u = t/d in (0, 1]: Penner's easing set in the ca_itp numbering (oracle/SPEC.md S7;
@@ -249,13 +260,16 @@ __device__ __forceinline__ float env_value_t(int64_t n, const PartialParams& q, 
 // EASED = false renders the voices whose three envelope phases are LINEAR (rt.resynth, every benchmark configuration) with the
 // code the kernel had before easings existed; EASED = true renders the other voices (and only those) with the easing switch
 // inlined in the transition chunks. Each launch skips the voices of the other kind, so a render is the sum of the two.
-template <int WARPS, bool EASED>
-__global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_constant__ OscArgs a) {
+// TENSOR = true runs the sustain-regime product on the tensor cores (3xTF32, below), TENSOR = false on FFMA2.
+template <int WARPS, int MINB, bool EASED, bool TENSOR>
+__global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_constant__ OscArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PartialParams* sp = reinterpret_cast<PartialParams*>(smem_raw);                 // [ppad]
-  float2* E = reinterpret_cast<float2*>(sp + a.ppad);                             // [ppad][32] lane offsets
-  float4* sgn4 = reinterpret_cast<float4*>(E + a.ppad * 32);                      // [ppad/4]
-  float2* base_all = reinterpret_cast<float2*>(sgn4 + a.ppad / 4);                // [WARPS][kNP]
+  float2* E = reinterpret_cast<float2*>(sp + a.ppad);                             // [ppad][kEP] exp(i l w_p), l < 32
+  float* Fx = reinterpret_cast<float*>(E + a.ppad * kEP);                         // [ppad][kR] Re exp(i 32 k w_p)
+  float* Fy = Fx + a.ppad * kR;                                                   // [ppad][kR] Im
+  float4* Ft = reinterpret_cast<float4*>(Fx);                                     // TENSOR: [ppad/4][8][32] fragments
+  float2* base_all = reinterpret_cast<float2*>(Fx + a.ppad * kR * (TENSOR ? 4 : 2));  // [WARPS][kNP]
   int* kend_all = reinterpret_cast<int*>(base_all + WARPS * kNP);                 // [WARPS][kNP]
   float* cval_all = reinterpret_cast<float*>(kend_all + WARPS * kNP);             // [WARPS][kNP]
   float* outbuf_all = cval_all + WARPS * kNP;                                     // [WARPS][kChunk]
@@ -271,10 +285,6 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
   float* outbuf = outbuf_all + warp * kChunk;
   float* bus = bus_all + warp * (kChunk * 2);
 
-  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
-  const bool has_chunk = chunk < a.n_chunks;
-  const int64_t l0 = chunk * kChunk;         // local (output) index of the chunk
-  const int64_t n0 = a.first_sample + l0;    // global sample index of the chunk
   const int64_t n_end = a.first_sample + a.n_samples;
   const int n_out = a.mix == CA_MIX_STEREO ? 2 : 1;
 
@@ -302,10 +312,32 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
     __syncthreads();
     for (int i = threadIdx.x; i < a.ppad * 32; i += WARPS * 32) {
       const int p = i >> 5, l = i & 31;
-      E[i] = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(l));
+      E[p * kEP + l] = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(l));
+    }
+    if (TENSOR) {
+      // B fragments of mma.m16n8k8, ready to load: entry (s, i, ln) serves lane ln = 4 g + t in step s (partials 4s .. 4s+3)
+      // for the n tile i: partial 4 s + t, k = 8 i + g, as (Im hi, Im lo, Re hi, Re lo). A lane reads 16 bytes next to its
+      // neighbours' (no bank conflict).
+      for (int i = threadIdx.x; i < a.ppad * kR; i += WARPS * 32) {  // (ppad / 4) steps x 8 tiles x 32 lanes
+        const int ln = i & 31, nt = (i >> 5) & 7, st = i >> 8;
+        const int p = 4 * st + (ln & 3), k = 8 * nt + (ln >> 2);
+        const float2 f = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(32 * k));
+        uint32_t yh, yl, xh, xl;
+        tf32_split(f.y, yh, yl);
+        tf32_split(f.x, xh, xl);
+        Ft[i] = make_float4(__uint_as_float(yh), __uint_as_float(yl), __uint_as_float(xh), __uint_as_float(xl));
+      }
+    }
+    for (int i = threadIdx.x; i < (TENSOR ? 0 : a.ppad * kR); i += WARPS * 32) {
+      // row p holds k = 8 tk + 4 h + j at position 32 h + 4 tk + j: the two 16-byte loads of a thread (h = 0, 1) are then
+      // contiguous across the eight tk of a quarter warp (no bank conflict)
+      const int p = i / kR, k = i - p * kR;
+      const float2 f = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(32 * k));
+      const int pos = p * kR + ((k >> 2) & 1) * 32 + (k >> 3) * 4 + (k & 3);
+      Fx[pos] = f.x;
+      Fy[pos] = f.y;
     }
     for (int p = threadIdx.x; p < a.ppad; p += WARPS * 32) {
-      reinterpret_cast<float*>(sgn4)[p] = sp[p].sgn;
       if (sp[p].amp != 0.f) {
         atomicMax(&s_max_press, sp[p].attack + sp[p].decay);
         atomicMax(&s_max_release, sp[p].release);
@@ -313,165 +345,244 @@ __global__ void __launch_bounds__(WARPS * 32, 2) oscbank_kernel(const __grid_con
     }
     __syncthreads();
     const VoiceParams vp = s_vp;
-    if (!has_chunk) continue;
-
-    const int64_t n1 = min(n0 + kChunk, n_end);
     const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
     const bool released = vp.release_at >= 0;
     const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
-    bool silent = (n1 - vp.key_delay < 1);  // chunk entirely before the attack starts
-    if (released) {
-      if (dead_note) silent = true;  // released before the key delay elapsed: the note is skipped (:774-777)
-      else if (n0 >= vp.release_at + s_max_release - 1) silent = true;  // every partial has finished its release
-    }
-    const bool steady = !silent && (n0 + 1 > press_end) && (!released || n1 <= vp.release_at);
 
-    if (silent) {
-#pragma unroll 4
-      for (int k = 0; k < kR; ++k) outbuf[32 * k + lane] = 0.f;
-    } else if (steady) {
-      // ================= fast path: Reinsch recurrence, constant envelope =================
-      for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
-        // exact seeds: lane p computes amp*S*exp(i*theta(n0)) for partial p0+lane
-        {
-          const PartialParams& q = sp[p0 + lane];
-          const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
-          const float am = q.amp * vp.sustain;
-          base[lane] = make_float2(am * z.x, am * z.y);
-        }
-        __syncwarp();
-        // two partials per register pair: the recurrence and the accumulation run on FFMA2 / FADD2 (packed.cuh), half
-        // the issue slots of the scalar form for the same FP32 work
-        c2 y[kNP / 2], d[kNP / 2], nkap[kNP / 2];
-#pragma unroll
-        for (int p = 0; p < kNP; p += 2) {
-          const float2 z0 = cmul(base[p], E[(p0 + p) * 32 + lane]);
-          const float2 z1 = cmul(base[p + 1], E[(p0 + p + 1) * 32 + lane]);
-          const float k0 = sp[p0 + p].kappa, k1 = sp[p0 + p + 1].kappa;
-          nkap[p / 2] = pk(-k0, -k1);
-          y[p / 2] = pk(z0.y, z1.y);
-          // y0 - y(-1) = Im(z * (1 - exp(-i Of)))
-          d[p / 2] = pk(fmaf(z0.x, sp[p0 + p].so, 0.5f * k0 * z0.y), fmaf(z1.x, sp[p0 + p + 1].so, 0.5f * k1 * z1.y));
-        }
-        __syncwarp();
-        const c2* sgn2 = reinterpret_cast<const c2*>(sgn4) + (p0 >> 1);
 #pragma unroll 1
-        for (int k = 0; k < kR; k += 2) {
-          // even step: every partial enters with a plus sign
-          c2 acc0 = y[0], acc1 = y[1], acc2 = y[2], acc3 = y[3];
-#pragma unroll
-          for (int p = 4; p < kNP / 2; p += 4) {
-            acc0 = add2(acc0, y[p]);
-            acc1 = add2(acc1, y[p + 1]);
-            acc2 = add2(acc2, y[p + 2]);
-            acc3 = add2(acc3, y[p + 3]);
-          }
-          {
-            const float2 t = upk(add2(add2(acc0, acc1), add2(acc2, acc3)));
-            const float s = t.x + t.y;
-            if (p0 == 0) outbuf[32 * k + lane] = s;
-            else outbuf[32 * k + lane] += s;
-          }
-#pragma unroll
-          for (int p = 0; p < kNP / 2; ++p) {
-            d[p] = fma2(nkap[p], y[p], d[p]);
-            y[p] = add2(y[p], d[p]);
-          }
-          // odd step: folded partials enter with a minus sign
-          acc0 = mul2(sgn2[0], y[0]);
-          acc1 = mul2(sgn2[1], y[1]);
-          acc2 = mul2(sgn2[2], y[2]);
-          acc3 = mul2(sgn2[3], y[3]);
-#pragma unroll
-          for (int p = 4; p < kNP / 2; p += 4) {
-            acc0 = fma2(sgn2[p], y[p], acc0);
-            acc1 = fma2(sgn2[p + 1], y[p + 1], acc1);
-            acc2 = fma2(sgn2[p + 2], y[p + 2], acc2);
-            acc3 = fma2(sgn2[p + 3], y[p + 3], acc3);
-          }
-          {
-            const float2 t = upk(add2(add2(acc0, acc1), add2(acc2, acc3)));
-            const float s = t.x + t.y;
-            if (p0 == 0) outbuf[32 * (k + 1) + lane] = s;
-            else outbuf[32 * (k + 1) + lane] += s;
-          }
-#pragma unroll
-          for (int p = 0; p < kNP / 2; ++p) {
-            d[p] = fma2(nkap[p], y[p], d[p]);
-            y[p] = add2(y[p], d[p]);
-          }
-        }
+    for (int ci = 0; ci < a.chunks_per_warp; ++ci) {
+      const int64_t chunk = (static_cast<int64_t>(blockIdx.x) * a.chunks_per_warp + ci) * WARPS + warp;
+      if (chunk >= a.n_chunks) break;
+      const int64_t l0 = chunk * kChunk;         // local (output) index of the chunk
+      const int64_t n0 = a.first_sample + l0;    // global sample index of the chunk
+      const int64_t n1 = min(n0 + kChunk, n_end);
+      bool silent = (n1 - vp.key_delay < 1);  // chunk entirely before the attack starts
+      if (released) {
+        if (dead_note) silent = true;  // released before the key delay elapsed: the note is skipped (:774-777)
+        else if (n0 >= vp.release_at + s_max_release - 1) silent = true;  // every partial has finished its release
       }
-    } else {
-      // ================= general path: complex rotation + envelope =================
-      // The envelope of a partial is piecewise linear and becomes constant (sustain level, or 0 after the release) at a
-      // sample T_p; only the steps of the chunk before T_p evaluate it per sample, the others use the constant.
-      for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
-        {
-          const PartialParams& q = sp[p0 + lane];
-          const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
-          base[lane] = make_float2(q.amp * z.x, q.amp * z.y);
-          const bool rel_seen = released && vp.release_at < n1;
-          const int64_t T = rel_seen ? vp.release_at + q.release - 1
-                                     : static_cast<int64_t>(vp.key_delay) + q.attack + vp.hold + q.decay;
-          const int64_t ke = (T - n0 + 31) >> 5;
-          kend[lane] = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kR), ke)));
-          cval[lane] = rel_seen ? 0.f : vp.sustain;
-        }
-        __syncwarp();
-        float2 z[kNP];
-#pragma unroll
-        for (int p = 0; p < kNP; ++p) z[p] = cmul(base[p], E[(p0 + p) * 32 + lane]);
-#pragma unroll 1
-        for (int k = 0; k < kR; ++k) {
-          const int64_t n = n0 + 32 * k + lane;
-          float acc = 0.f;
-#pragma unroll
-          for (int p = 0; p < kNP; ++p) {
-            const PartialParams& q = sp[p0 + p];
-            float e = cval[p];
-            if (k < kend[p]) e = env_value_t<EASED>(n, q, vp);
-            acc = fmaf(z[p].y, e, acc);
-            z[p] = cmul(z[p], make_float2(q.rot_re, q.rot_im));
-          }
-          if (p0 == 0) outbuf[32 * k + lane] = acc;
-          else outbuf[32 * k + lane] += acc;
-        }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
+      const bool steady = !silent && (n0 + 1 > press_end) && (!released || n1 <= vp.release_at);
 
-    // ---- emit ----
-    if (a.mix == CA_MIX_NONE) {
-      float* o = a.out + v * a.n_samples + l0;
+      // the constant part of the chunk: every partial at the level its envelope settles on (sustain; 0 once the release
+      // is in sight). A steady chunk is nothing else; a chunk with a transition adds corrections below.
+      const bool rel_seen = released && vp.release_at < n1;
+      const float cv = rel_seen ? 0.f : vp.sustain;
+      if (silent || cv == 0.f) {
 #pragma unroll 4
-      for (int k = 0; k < kR; ++k) {
-        const int i = 32 * k + lane;
-        if (l0 + i < a.n_samples) o[i] = outbuf[i];
-      }
-    } else if (!silent) {
-      if (a.mix == CA_MIX_STEREO) {
-        float2* b2 = reinterpret_cast<float2*>(bus);
-        for (int k = 0; k < kR; ++k) {
-          const int i = 32 * k + lane;
-          const float s = outbuf[i];
-          float2 acc = b2[i];
-          acc.x = fmaf(vp.gain_l, s, acc.x);
-          acc.y = fmaf(vp.gain_r, s, acc.y);
-          b2[i] = acc;
+        for (int k = 0; k < kR; ++k) outbuf[32 * k + lane] = 0.f;
+      } else if (TENSOR) {
+        // ================= fast path on the tensor cores: chunk(32 l x 64 k) = A(32 x 2P) B(2P x 64), 3xTF32 =================
+        // A[l][2p], A[l][2p+1] = Re, Im of e_p[l] = amp_p exp(i theta_p(n0 + l));  B[2p][k], B[2p+1][k] = Im, Re of exp(i 32 k w_p).
+        // One mma step takes four partials (eight columns of A); lane (g, t) of the warp holds partial 4s + t: its A values
+        // are e_p at l = g, g+8, g+16, g+24 (computed here from the seed and the lane-offset table, split hi/lo in registers),
+        // its B values come from the per-voice fragment table.
+        const int g = lane >> 2, t = lane & 3;
+        float acc[2][8][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+        for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
+          {
+            const PartialParams& q = sp[p0 + lane];
+            const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
+            const float am = q.amp * cv;
+            base[lane] = make_float2(am * z.x, am * z.y);
+          }
+          __syncwarp();
+#pragma unroll 2
+          for (int s8 = 0; s8 < kNP / 4; ++s8) {
+            const float2 b = base[4 * s8 + t];
+            const float2* er = E + (p0 + 4 * s8 + t) * kEP + g;
+            uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const float2 e0 = cmul(b, er[16 * mt]), e1 = cmul(b, er[16 * mt + 8]);
+              tf32_split(e0.x, ahi[mt][0], alo[mt][0]);
+              tf32_split(e1.x, ahi[mt][1], alo[mt][1]);
+              tf32_split(e0.y, ahi[mt][2], alo[mt][2]);
+              tf32_split(e1.y, ahi[mt][3], alo[mt][3]);
+            }
+            const float4* fq = Ft + ((p0 >> 2) + s8) * 256 + lane;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              const float4 f = fq[nt * 32];
+              const uint32_t yh = __float_as_uint(f.x), yl = __float_as_uint(f.y), xh = __float_as_uint(f.z), xl = __float_as_uint(f.w);
+              mma_tf32(acc[0][nt], alo[0], yh, xh);
+              mma_tf32(acc[1][nt], alo[1], yh, xh);
+              mma_tf32(acc[0][nt], ahi[0], yl, xl);
+              mma_tf32(acc[1][nt], ahi[1], yl, xl);
+              mma_tf32(acc[0][nt], ahi[0], yh, xh);
+              mma_tf32(acc[1][nt], ahi[1], yh, xh);
+            }
+          }
+          __syncwarp();
         }
+        // accumulator (mt, nt): c0, c1 = (l = 16 mt + g, k = 8 nt + 2t, +1), c2, c3 = (l + 8, same k)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            float* o = outbuf + 32 * (8 * nt + 2 * t) + 16 * mt + g;
+            o[0] = acc[mt][nt][0];
+            o[32] = acc[mt][nt][1];
+            o[8] = acc[mt][nt][2];
+            o[40] = acc[mt][nt][3];
+          }
       } else {
-        for (int k = 0; k < kR; ++k) {
-          const int i = 32 * k + lane;
-          bus[i] += outbuf[i];
+        // ================= fast path: constant envelope, chunk = Im(e F) on FFMA2 =================
+        const int tl = lane >> 3, tk = lane & 7;  // the thread owns l = 8 tl .. 8 tl + 7 and k = 8 tk .. 8 tk + 7
+        c2 acc[4][8];                             // [pair of l][k]
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0ull;
+        float* ex = outbuf;              // [kNP][32] Re e_p[l]   (the operand planes live in the output staging buffer,
+        float* ey = outbuf + kNP * 32;   // [kNP][32] Im e_p[l]    which is written after the last pass)
+        for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
+          // exact seeds: lane p computes amp*S*exp(i*theta(n0)) for partial p0+lane
+          {
+            const PartialParams& q = sp[p0 + lane];
+            const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
+            const float am = q.amp * cv;
+            base[lane] = make_float2(am * z.x, am * z.y);
+          }
+          __syncwarp();
+#pragma unroll 8
+          for (int p = 0; p < kNP; ++p) {
+            const float2 z = cmul(base[p], E[(p0 + p) * kEP + lane]);
+            ex[p * 32 + lane] = z.x;
+            ey[p * 32 + lane] = z.y;
+          }
+          __syncwarp();
+          const float4* ex4 = reinterpret_cast<const float4*>(ex + 8 * tl);
+          const float4* ey4 = reinterpret_cast<const float4*>(ey + 8 * tl);
+          const float4* fx4 = reinterpret_cast<const float4*>(Fx + p0 * kR + 4 * tk);
+          const float4* fy4 = reinterpret_cast<const float4*>(Fy + p0 * kR + 4 * tk);
+#pragma unroll 2
+          for (int p = 0; p < kNP; ++p) {
+            const float4 a0 = ex4[p * 8], a1 = ex4[p * 8 + 1];
+            const float4 b0 = ey4[p * 8], b1 = ey4[p * 8 + 1];
+            const float4 f0 = fx4[p * (kR / 4)], f1 = fx4[p * (kR / 4) + 8];
+            const float4 g0 = fy4[p * (kR / 4)], g1 = fy4[p * (kR / 4) + 8];
+            const c2 xr[4] = {pk(a0.x, a0.y), pk(a0.z, a0.w), pk(a1.x, a1.y), pk(a1.z, a1.w)};
+            const c2 xi[4] = {pk(b0.x, b0.y), pk(b0.z, b0.w), pk(b1.x, b1.y), pk(b1.z, b1.w)};
+            const float fr[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            const float fi[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[i][j] = fma2(xi[i], bc(fr[j]), fma2(xr[i], bc(fi[j]), acc[i][j]));
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float* o = outbuf + 32 * (8 * tk + j) + 8 * tl;
+          const float2 v0 = upk(acc[0][j]), v1 = upk(acc[1][j]), v2 = upk(acc[2][j]), v3 = upk(acc[3][j]);
+          *reinterpret_cast<float4*>(o) = make_float4(v0.x, v0.y, v1.x, v1.y);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v2.x, v2.y, v3.x, v3.y);
         }
       }
+      __syncwarp();
+      if (!silent && !steady) {
+        // ================= envelope transitions =================
+        // The envelope of a partial is piecewise and settles (sustain level, or 0 after the release) at a sample T_p; the
+        // steps of the chunk before T_p get (env(n) - settled level) * amp * sin(theta) added, one partial and one step at a
+        // time: sin(theta(n0 + 32k + l)) = Im(e[l] F[k]) from the same tables as the product.
+        const float lane_f = static_cast<float>(lane);
+        for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
+          {
+            const PartialParams& q = sp[p0 + lane];
+            const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
+            base[lane] = make_float2(q.amp * z.x, q.amp * z.y);
+            const int64_t T = rel_seen ? vp.release_at + q.release - 1
+                                       : static_cast<int64_t>(vp.key_delay) + q.attack + vp.hold + q.decay;
+            const int64_t ke = (T - n0 + 31) >> 5;
+            kend[lane] = q.amp == 0.f ? 0 : static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kR), ke)));
+            // value the release starts from (:769-781), per partial
+            cval[lane] = rel_seen ? env_pressed<EASED>(vp.release_at - vp.key_delay, q, vp) : 0.f;
+          }
+          __syncwarp();
+          // step counter of sample n0 (+1: the envelope steps before it is read), clamped where float holds it exactly enough
+          const float c0 = static_cast<float>(max(static_cast<int64_t>(-(1 << 30)), min(static_cast<int64_t>(1 << 30), n0 + 1 - vp.key_delay)));
+          const float crel = static_cast<float>(max(static_cast<int64_t>(-(1 << 30)), min(static_cast<int64_t>(1 << 30), vp.release_at - vp.key_delay)));
+#pragma unroll 1
+          for (int p = 0; p < kNP; ++p) {
+            const int ke = kend[p];
+            if (ke == 0) continue;
+            const int P = p0 + p;
+            const PartialParams& q = sp[P];
+            const float2 e = cmul(base[p], E[P * kEP + lane]);
+            const float inv_a = q.inv_attack, ah = static_cast<float>(q.attack + vp.hold), slope_d = (vp.sustain - 1.f) * q.inv_decay;
+            const float inv_r = q.inv_release, top = cval[p];
+#pragma unroll 2
+            for (int k = 0; k < ke; ++k) {
+              float2 f;
+              if (TENSOR) {
+                const float4 t4 = Ft[((P >> 2) * 8 + (k >> 3)) * 32 + 4 * (k & 7) + (P & 3)];
+                f = make_float2(t4.z + t4.w, t4.x + t4.y);
+              } else {
+                const int pos = P * kR + ((k >> 2) & 1) * 32 + (k >> 3) * 4 + (k & 3);
+                f = make_float2(Fx[pos], Fy[pos]);
+              }
+              const float im = fmaf(e.x, f.y, e.y * f.x);
+              float env;
+              if (EASED) {
+                env = env_value_t<true>(n0 + 32 * k + lane, q, vp);
+              } else {
+                // LINEAR phases, branch free: attack ramp, hold, decay ramp, sustain; the release ramp from `top`
+                const float c = c0 + static_cast<float>(32 * k) + lane_f;
+                const float up = c * inv_a;
+                const float dn = fmaxf(fmaf(c - ah, slope_d, 1.f), vp.sustain);
+                env = fmaxf(fminf(fminf(up, 1.f), dn), 0.f);
+                const float j = c - crel;
+                if (rel_seen && j >= 1.f) env = top * fmaxf(1.f - j * inv_r, 0.f);
+              }
+              outbuf[32 * k + lane] = fmaf(env - cv, im, outbuf[32 * k + lane]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+
+      // ---- emit ----
+      if (a.mix == CA_MIX_NONE) {
+        float* o = a.out + v * a.n_samples + l0;
+#pragma unroll 4
+        for (int k = 0; k < kR; ++k) {
+          const int i = 32 * k + lane;
+          if (l0 + i < a.n_samples) o[i] = outbuf[i];
+        }
+      } else if (!silent) {
+        if (a.mix == CA_MIX_STEREO) {
+          float2* b2 = reinterpret_cast<float2*>(bus);
+          for (int k = 0; k < kR; ++k) {
+            const int i = 32 * k + lane;
+            const float s = outbuf[i];
+            float2 acc = b2[i];
+            acc.x = fmaf(vp.gain_l, s, acc.x);
+            acc.y = fmaf(vp.gain_r, s, acc.y);
+            b2[i] = acc;
+          }
+        } else {
+          for (int k = 0; k < kR; ++k) {
+            const int i = 32 * k + lane;
+            bus[i] += outbuf[i];
+          }
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 
-  if (a.mix != CA_MIX_NONE && has_chunk && any_voice) {
+  // mix modes: one chunk per warp (chunks_per_warp = 1), the voices of the group were accumulated on the warp's bus
+  const int64_t chunk = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+  if (a.mix != CA_MIX_NONE && chunk < a.n_chunks && any_voice) {
+    const int64_t l0 = chunk * kChunk;
     float* o = a.out + l0 * n_out;
     const int64_t lim = (min(l0 + kChunk, a.n_samples) - l0) * n_out;
     for (int i = lane; i < lim; i += 32) atomicAdd(o + i, bus[i]);
@@ -493,6 +604,28 @@ __global__ void fp32_peak_kernel(float* out, int iters) {
   if (s == 12345.678f) out[0] = s;
 }
 
+}  // namespace
+
+namespace {
+// bufs = staging buffers of kChunk floats per warp (1: output; 3: output + stereo bus)
+template <int WARPS, int MINB, bool TENSOR>
+int launch_osc(ca_ctx* ctx, const OscArgs& a, int bufs, int64_t grid_y, int eased, cudaStream_t stream) {
+  const size_t smem = sizeof(PartialParams) * a.ppad + sizeof(float2) * a.ppad * kEP + sizeof(float) * a.ppad * kR * (TENSOR ? 4 : 2) +
+                      WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk * bufs);
+  const int64_t per_cta = static_cast<int64_t>(WARPS) * a.chunks_per_warp;
+  dim3 grid(static_cast<unsigned>((a.n_chunks + per_cta - 1) / per_cta), static_cast<unsigned>(grid_y));
+  if (eased != 2) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, MINB, false, TENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    oscbank_kernel<WARPS, MINB, false, TENSOR><<<grid, WARPS * 32, smem, stream>>>(a);
+  }
+  if (eased != 0) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, MINB, true, TENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    oscbank_kernel<WARPS, MINB, true, TENSOR><<<grid, WARPS * 32, smem, stream>>>(a);
+  }
+  return CA_OK;
+}
 }  // namespace
 
 int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials) {
@@ -549,39 +682,44 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
   a.first_sample = d.first_sample;
   a.out = d_out;
 
-  const size_t common = sizeof(PartialParams) * ppad + sizeof(float2) * ppad * 32 + sizeof(float) * ppad;
+  if (d.n_voices > 65535) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_oscbank_render: more than 65535 voices per call");
+  // CA_OSC_PATH=fp32 keeps the sustain-regime product on the FP32 pipe (FFMA2); the default runs it on the tensor cores (3xTF32)
+  const char* path = getenv("CA_OSC_PATH");
+  // (more than 64 partials: the fragment table of the tensor path does not fit next to the staging buffers)
+  const bool tensor = !(path && !strcmp(path, "fp32")) && ppad <= 64;
+  int rc;
   if (d.mix == CA_MIX_NONE) {
-    constexpr int WARPS = 8;
     a.voices_per_group = 1;
-    const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk);
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    dim3 grid(static_cast<unsigned>((a.n_chunks + WARPS - 1) / WARPS), static_cast<unsigned>(d.n_voices));
-    if (d.n_voices > 65535) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_oscbank_render: more than 65535 voices per call");
-    if (eased != 2) oscbank_kernel<WARPS, false><<<grid, WARPS * 32, smem, stream>>>(a);
-    if (eased != 0) oscbank_kernel<WARPS, true><<<grid, WARPS * 32, smem, stream>>>(a);
+    // shape of the per-voice render: warps per CTA (the per-voice tables are built once per CTA, so a CTA takes chunks_per_warp
+    // chunks per warp). Measured on config 3 (profiles/oscbank_shapes_r02.txt); CA_OSC_SHAPE / CA_OSC_CPW are the A/B switches.
+    const char* shape = getenv("CA_OSC_SHAPE");
+    const char* cpw = getenv("CA_OSC_CPW");
+    const int sh = shape ? atoi(shape) : (tensor ? 12 : 6);
+    a.chunks_per_warp = cpw ? max(1, atoi(cpw)) : (tensor ? 4 : 8);
+    if (tensor) {
+      if (sh == 8) rc = launch_osc<8, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
+      else if (sh == 16) rc = launch_osc<16, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
+      else rc = launch_osc<12, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
+    } else {
+      if (sh == 16) rc = launch_osc<16, 1, false>(ctx, a, 1, d.n_voices, eased, stream);
+      else if (sh == 12) rc = launch_osc<12, 1, false>(ctx, a, 1, d.n_voices, eased, stream);
+      else rc = launch_osc<6, 2, false>(ctx, a, 1, d.n_voices, eased, stream);
+    }
   } else {
     constexpr int WARPS = 4;
     const int n_out = d.mix == CA_MIX_STEREO ? 2 : 1;
     CA_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(float) * d.n_samples * n_out, stream));
-    const size_t smem = common + WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk * 3);
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
-    CA_CUDA_OK(ctx, cudaFuncSetAttribute(oscbank_kernel<WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem)));
     const int64_t tiles = (a.n_chunks + WARPS - 1) / WARPS;
     // enough voice groups to fill the GPU a few times over, few enough that the final atomics stay negligible
     int64_t groups = (static_cast<int64_t>(ctx->sm_count) * 8 + tiles - 1) / tiles;
     if (groups < 1) groups = 1;
     if (groups > d.n_voices) groups = d.n_voices;
     a.voices_per_group = static_cast<int32_t>((d.n_voices + groups - 1) / groups);
+    a.chunks_per_warp = 1;
     groups = (d.n_voices + a.voices_per_group - 1) / a.voices_per_group;
-    dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(groups));
-    if (eased != 2) oscbank_kernel<WARPS, false><<<grid, WARPS * 32, smem, stream>>>(a);
-    if (eased != 0) oscbank_kernel<WARPS, true><<<grid, WARPS * 32, smem, stream>>>(a);
+    rc = tensor ? launch_osc<WARPS, 1, true>(ctx, a, 3, groups, eased, stream) : launch_osc<WARPS, 2, false>(ctx, a, 3, groups, eased, stream);
   }
+  if (rc != CA_OK) return rc;
   CA_CUDA_OK(ctx, cudaGetLastError());
   ctx->launches += (eased == -1 || eased == 1) ? 2 : 1;
   return CA_OK;
