@@ -22,6 +22,7 @@
 //   * the kernel is instantiated twice, for voices with LINEAR phases only and for voices with an eased phase; a render
 //     launches the pass(es) its envelopes need and each pass skips the voices of the other kind.
 //   * partial parameters are prepared once per render by a small kernel, in double where the reference is in double.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,7 +39,7 @@ constexpr int kNP = 32;       // partials per pass (register resident)
 constexpr int kR = 64;        // 32-sample steps per chunk
 constexpr int kChunk = 32 * kR;
 constexpr int kMaxPartials = 128;
-constexpr int kEP = 40;       // row pitch of the lane-offset table in float2: rows p, p+1 start 16 banks apart
+constexpr int kEP = 36;       // row pitch of the lane-offset table in float2: rows p .. p+3 start 8 banks apart
 
 struct __align__(16) PartialParams {
   uint64_t inc;   // phase increment per sample, turns * 2^64
@@ -186,19 +187,29 @@ __device__ __forceinline__ float2 cis_turns_u64(uint64_t ph) {  // exp(2 pi i * 
   return make_float2(c, s);
 }
 
-// x = hi + lo with hi, lo representable in TF32 (10-bit mantissa): hi*hi' + lo*hi' + hi*lo' reproduces the FP32 product of two
-// such pairs to ~2^-22 relative (the dropped lo*lo' term), accumulated in FP32 by the tensor core
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+// The tensor-core form of the sustain-regime product: 3 x FP16. An operand pair (x, y) is split into hi = fp16(x, y) and
+// lo = fp16((x, y) - hi); hi*hi' + lo*hi' + hi*lo' reproduces the FP32 product to 2^-22 relative (the dropped lo*lo' term) as long
+// as the lo parts are normal FP16 numbers, which the power-of-two operand scales (kScaleB, the per-voice scale of A) arrange; the
+// tensor core accumulates in FP32. mma.m16n8k16 on FP16 issues at the rate of mma.m16n8k8 on TF32 and does twice the work
+// (profiles/microbench/mma_tf32_b200.txt), which is why this is not 3 x TF32.
+__device__ __forceinline__ void f16_split(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// D(16x8) += A(16x8, row) * B(8x8, col), TF32 operands, FP32 accumulation (SASS HMMA.1688.F32.TF32)
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ float2 f16_join(uint32_t hi, uint32_t lo) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi)), b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return make_float2(a.x + b.x, a.y + b.y);
+}
+// D(16x8) += A(16x16, row) * B(16x8, col), FP16 operands, FP32 accumulation (SASS HMMA.16816.F32)
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+constexpr float kScaleB = 256.f;  // exp(i x) * 2^8: lo parts are normal down to |value| = 5e-4, below that exact to 1e-10
 
 // itp::interpolate as b + c*e(u), u = t/d in (0, 1]: Penner's easing set in the ca_itp numbering (oracle/SPEC.md S7;
 // call sites include/audioelement.h:733-737, 994-998). Only the chunks that contain an envelope transition get here.
@@ -260,7 +271,7 @@ __device__ __forceinline__ float env_value_t(int64_t n, const PartialParams& q, 
 // EASED = false renders the voices whose three envelope phases are LINEAR (rt.resynth, every benchmark configuration) with the
 // code the kernel had before easings existed; EASED = true renders the other voices (and only those) with the easing switch
 // inlined in the transition chunks. Each launch skips the voices of the other kind, so a render is the sum of the two.
-// TENSOR = true runs the sustain-regime product on the tensor cores (3xTF32, below), TENSOR = false on FFMA2.
+// TENSOR = true runs the sustain-regime product on the tensor cores (3 x FP16, above), TENSOR = false on FFMA2.
 template <int WARPS, int MINB, bool EASED, bool TENSOR>
 __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_constant__ OscArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -268,14 +279,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
   float2* E = reinterpret_cast<float2*>(sp + a.ppad);                             // [ppad][kEP] exp(i l w_p), l < 32
   float* Fx = reinterpret_cast<float*>(E + a.ppad * kEP);                         // [ppad][kR] Re exp(i 32 k w_p)
   float* Fy = Fx + a.ppad * kR;                                                   // [ppad][kR] Im
-  float4* Ft = reinterpret_cast<float4*>(Fx);                                     // TENSOR: [ppad/4][8][32] fragments
-  float2* base_all = reinterpret_cast<float2*>(Fx + a.ppad * kR * (TENSOR ? 4 : 2));  // [WARPS][kNP]
+  uint4* Ft = reinterpret_cast<uint4*>(Fx);                                       // TENSOR: [ppad/8][8][32] B fragments
+  float2* base_all = reinterpret_cast<float2*>(Fx + a.ppad * kR * 2);             // [WARPS][kNP]
   int* kend_all = reinterpret_cast<int*>(base_all + WARPS * kNP);                 // [WARPS][kNP]
   float* cval_all = reinterpret_cast<float*>(kend_all + WARPS * kNP);             // [WARPS][kNP]
   float* outbuf_all = cval_all + WARPS * kNP;                                     // [WARPS][kChunk]
   float* bus_all = outbuf_all + WARPS * kChunk;                                   // [WARPS][kChunk*2] (mix only)
   __shared__ VoiceParams s_vp;
   __shared__ int s_max_press, s_max_release;
+  __shared__ float s_amp_max;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -303,6 +315,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       s_vp = a.voices[v];
       s_max_press = 0;
       s_max_release = 0;
+      s_amp_max = 0.f;
     }
     {
       const uint4* src = reinterpret_cast<const uint4*>(a.partials + v * a.ppad);
@@ -315,17 +328,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       E[p * kEP + l] = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(l));
     }
     if (TENSOR) {
-      // B fragments of mma.m16n8k8, ready to load: entry (s, i, ln) serves lane ln = 4 g + t in step s (partials 4s .. 4s+3)
-      // for the n tile i: partial 4 s + t, k = 8 i + g, as (Im hi, Im lo, Re hi, Re lo). A lane reads 16 bytes next to its
-      // neighbours' (no bank conflict).
-      for (int i = threadIdx.x; i < a.ppad * kR; i += WARPS * 32) {  // (ppad / 4) steps x 8 tiles x 32 lanes
+      // B fragments of mma.m16n8k16, ready to load: entry (s, i, ln) serves lane ln = 4 g + t in step s (partials 8s .. 8s+7) for
+      // the n tile i, k = 8 i + g: rows 2t, 2t+1 = (Im, Re) of partial 8s + t, rows 2t+8, 2t+9 = the same of partial 8s + 4 + t,
+      // as (hi, hi', lo, lo'): two register pairs, as the instruction wants them. A lane reads 16 bytes next to its neighbours'.
+      for (int i = threadIdx.x; i < a.ppad * 32; i += WARPS * 32) {  // (ppad / 8) steps x 8 tiles x 32 lanes
         const int ln = i & 31, nt = (i >> 5) & 7, st = i >> 8;
-        const int p = 4 * st + (ln & 3), k = 8 * nt + (ln >> 2);
-        const float2 f = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(32 * k));
-        uint32_t yh, yl, xh, xl;
-        tf32_split(f.y, yh, yl);
-        tf32_split(f.x, xh, xl);
-        Ft[i] = make_float4(__uint_as_float(yh), __uint_as_float(yl), __uint_as_float(xh), __uint_as_float(xl));
+        const int p = 8 * st + (ln & 3), k = 8 * nt + (ln >> 2);
+        const float2 f0 = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(32 * k));
+        const float2 f1 = cis_turns_u64(sp[p + 4].inc * static_cast<uint64_t>(32 * k));
+        uint4 e;
+        f16_split(kScaleB * f0.y, kScaleB * f0.x, e.x, e.z);
+        f16_split(kScaleB * f1.y, kScaleB * f1.x, e.y, e.w);
+        Ft[i] = e;
       }
     }
     for (int i = threadIdx.x; i < (TENSOR ? 0 : a.ppad * kR); i += WARPS * 32) {
@@ -339,6 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
     }
     for (int p = threadIdx.x; p < a.ppad; p += WARPS * 32) {
       if (sp[p].amp != 0.f) {
+        atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(sp[p].amp)));  // non-negative floats order as ints
         atomicMax(&s_max_press, sp[p].attack + sp[p].decay);
         atomicMax(&s_max_release, sp[p].release);
       }
@@ -348,7 +363,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
     const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
     const bool released = vp.release_at >= 0;
     const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
-
 #pragma unroll 1
     for (int ci = 0; ci < a.chunks_per_warp; ++ci) {
       const int64_t chunk = (static_cast<int64_t>(blockIdx.x) * a.chunks_per_warp + ci) * WARPS + warp;
@@ -367,15 +381,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       // is in sight). A steady chunk is nothing else; a chunk with a transition adds corrections below.
       const bool rel_seen = released && vp.release_at < n1;
       const float cv = rel_seen ? 0.f : vp.sustain;
+      // a whole steady chunk of a per-voice render goes from the accumulators to HBM (8 lanes = one 32-byte sector)
+      const bool direct = TENSOR && a.mix == CA_MIX_NONE && steady && l0 + kChunk <= a.n_samples;
+      // scale of the A operand (TENSOR): the power of two that brings the loudest partial of the voice just below 2^15, so that
+      // the lo halves of all but the faintest partials are normal FP16 numbers
+      int amp_exp;
+      frexpf(s_amp_max * cv, &amp_exp);
+      const float scale_a = exp2f(static_cast<float>(min(100, 15 - amp_exp)));
+      const float unscale = 1.f / (scale_a * kScaleB);
       if (silent || cv == 0.f) {
 #pragma unroll 4
         for (int k = 0; k < kR; ++k) outbuf[32 * k + lane] = 0.f;
       } else if (TENSOR) {
-        // ================= fast path on the tensor cores: chunk(32 l x 64 k) = A(32 x 2P) B(2P x 64), 3xTF32 =================
+        // ================= fast path on the tensor cores: chunk(32 l x 64 k) = A(32 x 2P) B(2P x 64), 3 x FP16 =================
         // A[l][2p], A[l][2p+1] = Re, Im of e_p[l] = amp_p exp(i theta_p(n0 + l));  B[2p][k], B[2p+1][k] = Im, Re of exp(i 32 k w_p).
-        // One mma step takes four partials (eight columns of A); lane (g, t) of the warp holds partial 4s + t: its A values
-        // are e_p at l = g, g+8, g+16, g+24 (computed here from the seed and the lane-offset table, split hi/lo in registers),
-        // its B values come from the per-voice fragment table.
+        // One mma step takes eight partials (sixteen columns of A); lane (g, t) of the warp holds partials 8s + t and 8s + 4 + t:
+        // its A values are e_p at l = g, g+8, g+16, g+24 (computed here from the seed and the lane-offset table, split hi/lo in
+        // registers), its B values come from the per-voice fragment table.
         const int g = lane >> 2, t = lane & 3;
         float acc[2][8][4];
 #pragma unroll
@@ -384,52 +406,69 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
           for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
-        for (int p0 = 0; p0 < a.ppad; p0 += kNP) {
-          {
-            const PartialParams& q = sp[p0 + lane];
-            const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
-            const float am = q.amp * cv;
-            base[lane] = make_float2(am * z.x, am * z.y);
-          }
-          __syncwarp();
-#pragma unroll 2
-          for (int s8 = 0; s8 < kNP / 4; ++s8) {
-            const float2 b = base[4 * s8 + t];
-            const float2* er = E + (p0 + 4 * s8 + t) * kEP + g;
-            uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              const float2 e0 = cmul(b, er[16 * mt]), e1 = cmul(b, er[16 * mt + 8]);
-              tf32_split(e0.x, ahi[mt][0], alo[mt][0]);
-              tf32_split(e1.x, ahi[mt][1], alo[mt][1]);
-              tf32_split(e0.y, ahi[mt][2], alo[mt][2]);
-              tf32_split(e1.y, ahi[mt][3], alo[mt][3]);
-            }
-            const float4* fq = Ft + ((p0 >> 2) + s8) * 256 + lane;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-              const float4 f = fq[nt * 32];
-              const uint32_t yh = __float_as_uint(f.x), yl = __float_as_uint(f.y), xh = __float_as_uint(f.z), xl = __float_as_uint(f.w);
-              mma_tf32(acc[0][nt], alo[0], yh, xh);
-              mma_tf32(acc[1][nt], alo[1], yh, xh);
-              mma_tf32(acc[0][nt], ahi[0], yl, xl);
-              mma_tf32(acc[1][nt], ahi[1], yl, xl);
-              mma_tf32(acc[0][nt], ahi[0], yh, xh);
-              mma_tf32(acc[1][nt], ahi[1], yh, xh);
-            }
-          }
-          __syncwarp();
+        // exact seeds of every partial, amp * scale * exp(i theta(n0)), in the (still unused) output staging buffer
+        float2* seed = reinterpret_cast<float2*>(outbuf);
+        for (int p = lane; p < a.ppad; p += 32) {
+          const PartialParams& q = sp[p];
+          const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
+          const float am = q.amp * cv * scale_a;
+          seed[p] = make_float2(am * z.x, am * z.y);
         }
+        __syncwarp();
+        // A fragments of step st (partials 8 st + t and 8 st + 4 + t)
+        auto gen_a = [&](int st, uint32_t (&hi)[2][4], uint32_t (&lo)[2][4]) {
+          const float2 b0 = seed[8 * st + t], b1 = seed[8 * st + 4 + t];
+          const float2* er0 = E + (8 * st + t) * kEP + g;
+          const float2* er1 = er0 + 4 * kEP;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const float2 e0 = cmul(b0, er0[16 * mt]), e1 = cmul(b0, er0[16 * mt + 8]);
+            const float2 e2 = cmul(b1, er1[16 * mt]), e3 = cmul(b1, er1[16 * mt + 8]);
+            f16_split(e0.x, e0.y, hi[mt][0], lo[mt][0]);  // row g,     columns 2t, 2t+1
+            f16_split(e1.x, e1.y, hi[mt][1], lo[mt][1]);  // row g + 8
+            f16_split(e2.x, e2.y, hi[mt][2], lo[mt][2]);  // row g,     columns 2t+8, 2t+9
+            f16_split(e3.x, e3.y, hi[mt][3], lo[mt][3]);  // row g + 8
+          }
+        };
+        // one step: three sweeps over the sixteen accumulator tiles, so that consecutive tensor instructions never wait for each
+        // other. (Preparing the A operands of the next step between the tensor instructions of this one, by hand or by ptxas,
+        // measured the same: the other warps of the scheduler already fill those slots.)
+        const int n_steps = a.ppad >> 3;
+#pragma unroll 1
+        for (int st = 0; st < n_steps; ++st) {
+          uint32_t hi[2][4], lo[2][4];
+          gen_a(st, hi, lo);
+          const uint4* fq = Ft + st * 256 + lane;
+          uint4 f[8];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) f[nt] = fq[nt * 32];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            mma_f16(acc[0][nt], lo[0], f[nt].x, f[nt].y);
+            mma_f16(acc[1][nt], lo[1], f[nt].x, f[nt].y);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            mma_f16(acc[0][nt], hi[0], f[nt].z, f[nt].w);
+            mma_f16(acc[1][nt], hi[1], f[nt].z, f[nt].w);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            mma_f16(acc[0][nt], hi[0], f[nt].x, f[nt].y);
+            mma_f16(acc[1][nt], hi[1], f[nt].x, f[nt].y);
+          }
+        }
+        __syncwarp();
         // accumulator (mt, nt): c0, c1 = (l = 16 mt + g, k = 8 nt + 2t, +1), c2, c3 = (l + 8, same k)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 8; ++nt) {
-            float* o = outbuf + 32 * (8 * nt + 2 * t) + 16 * mt + g;
-            o[0] = acc[mt][nt][0];
-            o[32] = acc[mt][nt][1];
-            o[8] = acc[mt][nt][2];
-            o[40] = acc[mt][nt][3];
+            float* o = (direct ? a.out + v * a.n_samples + l0 : outbuf) + 32 * (8 * nt + 2 * t) + 16 * mt + g;
+            o[0] = acc[mt][nt][0] * unscale;
+            o[32] = acc[mt][nt][1] * unscale;
+            o[8] = acc[mt][nt][2] * unscale;
+            o[40] = acc[mt][nt][3] * unscale;
           }
       } else {
         // ================= fast path: constant envelope, chunk = Im(e F) on FFMA2 =================
@@ -522,8 +561,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
             for (int k = 0; k < ke; ++k) {
               float2 f;
               if (TENSOR) {
-                const float4 t4 = Ft[((P >> 2) * 8 + (k >> 3)) * 32 + 4 * (k & 7) + (P & 3)];
-                f = make_float2(t4.z + t4.w, t4.x + t4.y);
+                const uint4 t4 = Ft[((P >> 3) * 8 + (k >> 3)) * 32 + 4 * (k & 7) + (P & 3)];
+                const float2 yx = (P & 4) ? f16_join(t4.y, t4.w) : f16_join(t4.x, t4.z);  // (Im, Re) * kScaleB
+                f = make_float2(yx.y * (1.f / kScaleB), yx.x * (1.f / kScaleB));
               } else {
                 const int pos = P * kR + ((k >> 2) & 1) * 32 + (k >> 3) * 4 + (k & 3);
                 f = make_float2(Fx[pos], Fy[pos]);
@@ -550,7 +590,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       __syncwarp();
 
       // ---- emit ----
-      if (a.mix == CA_MIX_NONE) {
+      if (direct) {
+      } else if (a.mix == CA_MIX_NONE) {
         float* o = a.out + v * a.n_samples + l0;
 #pragma unroll 4
         for (int k = 0; k < kR; ++k) {
@@ -610,7 +651,7 @@ namespace {
 // bufs = staging buffers of kChunk floats per warp (1: output; 3: output + stereo bus)
 template <int WARPS, int MINB, bool TENSOR>
 int launch_osc(ca_ctx* ctx, const OscArgs& a, int bufs, int64_t grid_y, int eased, cudaStream_t stream) {
-  const size_t smem = sizeof(PartialParams) * a.ppad + sizeof(float2) * a.ppad * kEP + sizeof(float) * a.ppad * kR * (TENSOR ? 4 : 2) +
+  const size_t smem = sizeof(PartialParams) * a.ppad + sizeof(float2) * a.ppad * kEP + sizeof(float) * a.ppad * kR * 2 +
                       WARPS * (sizeof(float2) * kNP * 2 + sizeof(float) * kChunk * bufs);
   const int64_t per_cta = static_cast<int64_t>(WARPS) * a.chunks_per_warp;
   dim3 grid(static_cast<unsigned>((a.n_chunks + per_cta - 1) / per_cta), static_cast<unsigned>(grid_y));
@@ -683,10 +724,9 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
   a.out = d_out;
 
   if (d.n_voices > 65535) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_oscbank_render: more than 65535 voices per call");
-  // CA_OSC_PATH=fp32 keeps the sustain-regime product on the FP32 pipe (FFMA2); the default runs it on the tensor cores (3xTF32)
+  // CA_OSC_PATH=fp32 keeps the sustain-regime product on the FP32 pipe (FFMA2); the default runs it on the tensor cores (3 x FP16)
   const char* path = getenv("CA_OSC_PATH");
-  // (more than 64 partials: the fragment table of the tensor path does not fit next to the staging buffers)
-  const bool tensor = !(path && !strcmp(path, "fp32")) && ppad <= 64;
+  const bool tensor = !(path && !strcmp(path, "fp32"));
   int rc;
   if (d.mix == CA_MIX_NONE) {
     a.voices_per_group = 1;
@@ -694,11 +734,12 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
     // chunks per warp). Measured on config 3 (profiles/oscbank_shapes_r02.txt); CA_OSC_SHAPE / CA_OSC_CPW are the A/B switches.
     const char* shape = getenv("CA_OSC_SHAPE");
     const char* cpw = getenv("CA_OSC_CPW");
-    const int sh = shape ? atoi(shape) : (tensor ? 12 : 6);
-    a.chunks_per_warp = cpw ? max(1, atoi(cpw)) : (tensor ? 4 : 8);
+    const int sh = shape ? atoi(shape) : 6;
+    a.chunks_per_warp = cpw ? max(1, atoi(cpw)) : 8;
     if (tensor) {
       if (sh == 8) rc = launch_osc<8, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
-      else if (sh == 16) rc = launch_osc<16, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
+      else if (sh == 6 && ppad <= 64) rc = launch_osc<6, 2, true>(ctx, a, 1, d.n_voices, eased, stream);
+      else if (sh == 16 && ppad <= 64) rc = launch_osc<16, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
       else rc = launch_osc<12, 1, true>(ctx, a, 1, d.n_voices, eased, stream);
     } else {
       if (sh == 16) rc = launch_osc<16, 1, false>(ctx, a, 1, d.n_voices, eased, stream);

@@ -11,6 +11,37 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int TILES, int KIND>
+__global__ void mma16_kernel(float* out, int iters) {
+  float d[TILES][4];
+  uint32_t a[4], b[2];
+  for (int i = 0; i < 4; ++i) a[i] = 0x3c003c00u + threadIdx.x + i;
+  for (int i = 0; i < 2; ++i) b[i] = 0x38003800u + threadIdx.x + i;
+  for (int t = 0; t < TILES; ++t)
+    for (int i = 0; i < 4; ++i) d[t][i] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int t = 0; t < TILES; ++t) {
+      if (KIND == 0) mma_f16(d[t], a, b);
+      else mma_bf16(d[t], a, b);
+    }
+  }
+  float s = 0;
+  for (int t = 0; t < TILES; ++t)
+    for (int i = 0; i < 4; ++i) s += d[t][i];
+  if (s == 1234.5f) out[0] = s;
+}
+
 template <int TILES>
 __global__ void mma_kernel(float* out, int iters) {
   float d[TILES][4];
@@ -66,7 +97,7 @@ int main() {
   printf("%s, %d SMs (rates at %.3f GHz)\n", p.name, p.multiProcessorCount, ghz);
   float* d; cudaMalloc(&d, 4);
   const int sms = p.multiProcessorCount, iters = 4096;
-  for (int warps : {4, 8, 16, 32}) {
+  for (int warps : {4, 8, 16}) {
     auto report = [&](const char* name, int tiles, float ms) {
       const double n = double(tiles) * iters * warps * sms;  // warp-level mma instructions
       printf("%-34s %2d warps/SM  %.3f ms  %.3f mma/clk/SM  %.1f TFLOP/s dense tf32 (1x)\n", name, warps, ms, n / (ms * 1e-3) / (ghz * 1e9) / sms,
@@ -74,6 +105,8 @@ int main() {
     };
     report("mma.m16n8k8.tf32, 8 acc tiles", 8, time_ms([&] { mma_kernel<8><<<sms, warps * 32>>>(d, iters); }));
     report("mma.m16n8k8.tf32, 16 acc tiles", 16, time_ms([&] { mma_kernel<16><<<sms, warps * 32>>>(d, iters); }));
+    report("mma.m16n8k16.f16 (x2 flop), 16 tiles", 16, time_ms([&] { mma16_kernel<16, 0><<<sms, warps * 32>>>(d, iters); }));
+    report("mma.m16n8k16.bf16 (x2 flop), 16 tiles", 16, time_ms([&] { mma16_kernel<16, 1><<<sms, warps * 32>>>(d, iters); }));
   }
   for (int warps : {8, 16}) {
     auto report = [&](const char* name, float ms) {

@@ -18,7 +18,7 @@ def run(n):
     for _ in range(n):
         bank.render(ns, b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], env, out=out)
 ref = None
-for path, shape, cpw in [(pa, sh, c) for pa, shapes in (("tensor", ("8", "12", "16")), ("fp32", ("6", "12", "16"))) for sh in shapes for c in ("1", "2", "4", "8")]:
+for path, shape, cpw in [(pa, sh, c) for pa, shapes in (("tensor", ("6", "8", "12", "16")), ("fp32", ("6", "12", "16"))) for sh in shapes for c in ("1", "2", "4", "8")]:
     if True:
         os.environ["CA_OSC_PATH"], os.environ["CA_OSC_SHAPE"], os.environ["CA_OSC_CPW"] = path, shape, cpw
         run(2)

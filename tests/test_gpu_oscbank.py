@@ -162,7 +162,7 @@ def test_inaudible_trailing_harmonics_dropped(pkg, orc, ctx):
     assert np.abs(b - c).max() > 5e-7    # the one in the middle is played
     bb = bank([0.5, 9e-7, 0.25, 9e-7, 0.0, 5e-7])
     ref = orc.oscbank_render(bb["f0_hz"], bb["volume"], bb["partial_volume"], bb["partial_phase"], 4000)
-    assert np.abs(a - ref).max() < 3e-6  # full-scale voice (volume 1): fp32 recurrence error over a 64-step chunk
+    assert np.abs(a - ref).max() < 3e-6  # full-scale voice (volume 1)
 
 
 @pytest.mark.parametrize("mix", [1, 2])
@@ -238,4 +238,61 @@ def test_host_entry_point(pkg, orc, ctx, wl):
     rc = pkg.lib().ca_oscbank_render_host(ctx.handle, C.byref(d), out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    assert np.abs(out - ref).max() < TOL * 0.1
+
+
+@pytest.mark.parametrize("path", ["tensor", "fp32"])
+def test_sustain_product_on_both_pipes(pkg, orc, ctx, wl, path, monkeypatch):
+    # the sustain regime is a 32 x 64 x 2P matrix product per chunk: on the tensor cores (3 x FP16 split, the default) or on the
+    # FP32 pipe (CA_OSC_PATH=fp32). Full-scale voices (volume 1) hold the bar of the normalised signal on either.
+    monkeypatch.setenv("CA_OSC_PATH", path)
+    b = wl.c3_bank(5, 64)
+    b["volume"][:] = 1.0
+    n = 3 * 2048 + 777
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    assert np.abs(out - ref).max() < 2e-6
+
+
+@pytest.mark.parametrize("mix", [0, 2])
+def test_128_partials(pkg, orc, ctx, mix):
+    # the largest partial count the bank takes (ca_oscbank_plan): four passes of 32 through the product
+    rng = np.random.default_rng(9)
+    V, P, n = 3, 128, 9000
+    pv = rng.uniform(0.1, 1.0, (V, P)).astype(np.float32)
+    b = dict(f0_hz=np.array([31.0, 60.5, 111.0], np.float32), volume=np.full(V, 0.1, np.float32),
+             partial_volume=(pv / pv.sum(axis=1, keepdims=True)).astype(np.float32),
+             partial_phase=rng.uniform(-1, 1, (V, P)).astype(np.float32))
+    e = pkg.Ahdsr(400, 0, 50, 700, 0, 1500, 0, 0.5)
+    rel = np.array([6000, -1, 2500], np.int64)
+    out = gpu_render(pkg, ctx, b, n, e, release_at=rel, mix=mix)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
+                             release_at=rel, mix=mix)
+    assert np.abs(out - ref).max() < TOL * 0.1 * (1 if mix == 0 else 3)
+
+
+def test_loud_and_faint_voices_share_a_render(pkg, orc, ctx):
+    # the FP16 operands of the tensor path are scaled per voice by a power of two chosen from the loudest partial: a voice far
+    # above full scale and one at -100 dB keep their relative accuracy
+    P, n = 16, 2 * 2048 + 100
+    rng = np.random.default_rng(4)
+    pv = np.tile((1.0 / np.arange(1, P + 1)).astype(np.float32), (3, 1))
+    b = dict(f0_hz=np.array([220.0, 330.0, 95.0], np.float32), volume=np.array([40.0, 1e-5, 1.0], np.float32), partial_volume=pv,
+             partial_phase=rng.uniform(-1, 1, (3, P)).astype(np.float32))
+    out = gpu_render(pkg, ctx, b, n, default_env(pkg))
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n)
+    for v in range(3):
+        assert np.abs(out[v] - ref[v]).max() < 2e-6 * np.abs(ref[v]).max(), v
+
+
+def test_long_release_and_slow_attack(pkg, orc, ctx, wl):
+    # envelope transitions that span many chunks (1 s attack, 1.5 s release): every chunk on the way is product + corrections
+    b = wl.c3_bank(3, 24)
+    n = 4 * 48000
+    e = pkg.Ahdsr(48000, 0, 1000, 20000, 0, 72000, 0, 0.7)
+    rel = np.array([100000, 30000, -1], np.int64)   # after the decay; inside the attack; never
+    kd = np.array([0, 5000, 47000], np.int32)
+    out = gpu_render(pkg, ctx, b, n, e, release_at=rel, key_delay=kd)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
+                             release_at=rel, key_delay=kd)
     assert np.abs(out - ref).max() < TOL * 0.1
