@@ -51,6 +51,8 @@ struct ca_ctx {
   int32_t osc_max_partials = 0;
   void* d_osc_partials = nullptr;  // PartialParams[max_voices][padded partials]
   void* d_osc_voices = nullptr;    // VoiceParams[max_voices]
+  void* d_osc_umma = nullptr;      // operand tables of the tcgen05 kernel, 128 KB per voice (allocated on first use)
+  size_t osc_umma_bytes = 0;
 
   // scratch for the *_host entry points
   void* d_scratch[16] = {};

@@ -23,6 +23,8 @@
 //     launches the pass(es) its envelopes need and each pass skips the voices of the other kind.
 //   * partial parameters are prepared once per render by a small kernel, in double where the reference is in double.
 #include <cuda_fp16.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,6 +41,7 @@ constexpr int kNP = 32;       // partials per pass (register resident)
 constexpr int kR = 64;        // 32-sample steps per chunk
 constexpr int kChunk = 32 * kR;
 constexpr int kMaxPartials = 128;
+constexpr int kUmmaChunk = 128 * 128;  // samples per chunk of the tcgen05 kernel (osc_umma_kernel)
 constexpr int kEP = 36;       // row pitch of the lane-offset table in float2: rows p .. p+3 start 8 banks apart
 
 struct __align__(16) PartialParams {
@@ -175,6 +178,7 @@ struct OscArgs {
   int32_t mix;
   int32_t voices_per_group;
   int32_t chunks_per_warp;
+  int32_t umma_skip;  // 1: the steady 16,384-sample chunks are rendered by osc_umma_kernel, this launch fills in the rest
   int64_t n_chunks;
   int64_t first_sample;  // global index of output sample 0 (phases and envelopes are closed-form in the global index)
   float* out;
@@ -323,6 +327,33 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       for (int i = threadIdx.x; i < a.ppad * 4; i += WARPS * 32) dst[i] = src[i];
     }
     __syncthreads();
+    for (int p = threadIdx.x; p < a.ppad; p += WARPS * 32) {
+      if (sp[p].amp != 0.f) {
+        atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(sp[p].amp)));  // non-negative floats order as ints
+        atomicMax(&s_max_press, sp[p].attack + sp[p].decay);
+        atomicMax(&s_max_release, sp[p].release);
+      }
+    }
+    __syncthreads();
+    const VoiceParams vp = s_vp;
+    const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
+    const bool released = vp.release_at >= 0;
+    const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
+    // is the 2048-sample chunk `chunk` rendered by the tcgen05 kernel (as part of a whole, steady 16,384-sample chunk)?
+    auto umma_renders = [&](int64_t chunk) {
+      if (!a.umma_skip || vp.itp != 0) return false;
+      const int64_t uc = (chunk * kChunk) / kUmmaChunk;
+      if ((uc + 1) * kUmmaChunk > a.n_samples) return false;
+      const int64_t u0 = a.first_sample + uc * kUmmaChunk, u1 = u0 + kUmmaChunk;
+      return (u1 - vp.key_delay >= 1) && (u0 + 1 > press_end) && (!released || u1 <= vp.release_at);
+    };
+    if (a.umma_skip) {  // nothing to do for this voice in this CTA: skip the tables too (uniform)
+      bool needed = false;
+      const int64_t first = static_cast<int64_t>(blockIdx.x) * a.chunks_per_warp * WARPS;
+      const int64_t last = min(a.n_chunks, first + static_cast<int64_t>(a.chunks_per_warp) * WARPS);
+      for (int64_t c = first; c < last && !needed; ++c) needed = !umma_renders(c);
+      if (!needed) continue;
+    }
     for (int i = threadIdx.x; i < a.ppad * 32; i += WARPS * 32) {
       const int p = i >> 5, l = i & 31;
       E[p * kEP + l] = cis_turns_u64(sp[p].inc * static_cast<uint64_t>(l));
@@ -351,22 +382,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
       Fx[pos] = f.x;
       Fy[pos] = f.y;
     }
-    for (int p = threadIdx.x; p < a.ppad; p += WARPS * 32) {
-      if (sp[p].amp != 0.f) {
-        atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(sp[p].amp)));  // non-negative floats order as ints
-        atomicMax(&s_max_press, sp[p].attack + sp[p].decay);
-        atomicMax(&s_max_release, sp[p].release);
-      }
-    }
     __syncthreads();
-    const VoiceParams vp = s_vp;
-    const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
-    const bool released = vp.release_at >= 0;
-    const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
 #pragma unroll 1
     for (int ci = 0; ci < a.chunks_per_warp; ++ci) {
       const int64_t chunk = (static_cast<int64_t>(blockIdx.x) * a.chunks_per_warp + ci) * WARPS + warp;
       if (chunk >= a.n_chunks) break;
+      if (umma_renders(chunk)) continue;
       const int64_t l0 = chunk * kChunk;         // local (output) index of the chunk
       const int64_t n0 = a.first_sample + l0;    // global sample index of the chunk
       const int64_t n1 = min(n0 + kChunk, n_end);
@@ -630,6 +651,234 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
   }
 }
 
+// =====================================================================================================================
+// tcgen05 form of the sustain regime (per-voice renders of up to 64 partials): D[l][k] = sum_q A[l][q] B[k][q] on the
+// 5th-generation tensor cores, accumulator in tensor memory.
+//   l = sample inside a block of 128 (M = 128: the 128 TMEM lanes), k = block of the chunk (N = 128 columns): a chunk is
+//   16,384 samples; q = (partial, Re/Im), K = 2 * ppad.
+//   A[l][2p], A[l][2p+1] = Re, Im of e_p[l] = amp_p exp(i theta_p(n0 + l))      per chunk: seed_p (exact 64-bit phase) times the
+//                                                                                thread's own exp(i l w_p), kept in registers
+//   B[k][2p], B[k][2p+1] = Im, Re of exp(i 128 k w_p)                           per voice: built once by osc_umma_tables_kernel,
+//                                                                                bulk-copied (TMA) into shared memory
+// Both operands are FP16 pairs hi + lo (f16_split above; three MMAs per K slice: lo*hi, hi*lo, hi*hi), stored K-major without
+// swizzle in the canonical core-matrix layout the shared-memory descriptors describe: 8 rows x 16 bytes contiguous (128 B),
+// the next 8 rows 128 B further (SBO), the next 16 bytes of K 128 rows * 16 B = 2048 B further (LBO).
+// One CTA (8 warps) per SM: every warp prepares A for chunk c+1 and drains the accumulator of chunk c-1 while the tensor core
+// works on chunk c (A and D are double-buffered; one elected thread issues the MMAs and commits them to an mbarrier).
+// Lane = sample makes the epilogue stores coalesced: a warp writes 32 consecutive samples per accumulator column.
+constexpr int kUM = 128, kUN = 128;
+constexpr int kUChunk = kUmmaChunk;                   // samples per chunk
+static_assert(kUM * kUN == kUmmaChunk, "chunk of the tcgen05 kernel");
+constexpr uint32_t kUOperand = 128 * 128 * 2;         // bytes of one 128 x 128 FP16 operand (ppad = 64)
+constexpr uint32_t kUTableBytes = 2 * kUOperand + 64 * 128 * sizeof(float2);  // per voice: B hi, B lo, exp(i l w_p) for l < 128
+
+struct UmmaArgs {
+  const PartialParams* partials;
+  const VoiceParams* voices;
+  unsigned char* tables;
+  int64_t n_voices, n_samples, first_sample;
+  int32_t ppad;
+  int32_t chunks_per_cta;
+  float* out;
+};
+
+__device__ __forceinline__ uint32_t canon_off(int row, int q) {  // byte offset of element (row, q) of a K-major operand
+  return static_cast<uint32_t>((q >> 3) * 2048 + (row >> 3) * 128 + (row & 7) * 16 + (q & 7) * 2);
+}
+
+__global__ void osc_umma_tables_kernel(const __grid_constant__ UmmaArgs a) {
+  const int64_t v = blockIdx.x;
+  unsigned char* base = a.tables + v * kUTableBytes;
+  const PartialParams* pp = a.partials + v * a.ppad;
+  for (int idx = threadIdx.x; idx < 64 * 128; idx += blockDim.x) {
+    const int k = idx & 127, p = idx >> 7;
+    uint32_t hi = 0, lo = 0;
+    float2 e = make_float2(0.f, 0.f);
+    if (p < a.ppad) {
+      const uint64_t inc = pp[p].inc;
+      const float2 f = cis_turns_u64(inc * static_cast<uint64_t>(128 * k));
+      f16_split(kScaleB * f.y, kScaleB * f.x, hi, lo);
+      e = cis_turns_u64(inc * static_cast<uint64_t>(k));
+    }
+    const uint32_t off = canon_off(k, 2 * p);
+    *reinterpret_cast<uint32_t*>(base + off) = hi;
+    *reinterpret_cast<uint32_t*>(base + kUOperand + off) = lo;
+    reinterpret_cast<float2*>(base + 2 * kUOperand)[p * 128 + k] = e;
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {  // a lost arrival must not hang the GPU
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets in 16-byte units, version 1, no swizzle
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (static_cast<uint64_t>(2048 >> 4) << 16) |
+         (static_cast<uint64_t>(128 >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major (0), N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kUmmaIdesc = (1u << 4) | (static_cast<uint32_t>(kUN >> 3) << 17) | (static_cast<uint32_t>(kUM >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(da), "l"(db), "r"(kUmmaIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) osc_umma_kernel(const __grid_constant__ UmmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sA = smem_raw;                          // [2 buffers][hi, lo][32 KB]
+  unsigned char* sB = smem_raw + 4 * kUOperand;          // [hi, lo][32 KB]
+  float2* seed = reinterpret_cast<float2*>(sB + 2 * kUOperand);  // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(seed + 128);      // [0]: table copy, [1], [2]: accumulator buffers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  __shared__ float s_amp_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t v = blockIdx.y;
+  const VoiceParams vp = a.voices[v];
+  if (vp.itp != 0) return;  // eased envelopes: everything is left to the other kernel (uniform over the CTA)
+  const PartialParams* pp = a.partials + v * a.ppad;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_amp_max = 0.f;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const unsigned char* tab = a.tables + v * kUTableBytes;
+  if (tid == 0) {
+    mbar_expect_tx(&bars[0], 2 * kUOperand);
+    bulk_g2s(sB, tab, kUOperand, &bars[0]);
+    bulk_g2s(sB + kUOperand, tab + kUOperand, kUOperand, &bars[0]);
+  }
+  // the thread's row of A: sample l of every block, partials 32 h .. 32 h + 31
+  const int l = tid & 127, h = tid >> 7;
+  float2 eg[32];
+  {
+    const float2* e128 = reinterpret_cast<const float2*>(tab + 2 * kUOperand);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) eg[i] = e128[(32 * h + i) * 128 + l];
+  }
+  if (tid < a.ppad && pp[tid].amp != 0.f) atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(pp[tid].amp)));
+  int max_press = 0;
+  for (int p = 0; p < a.ppad; ++p)
+    if (pp[p].amp != 0.f) max_press = max(max_press, pp[p].attack + pp[p].decay);
+  __syncthreads();
+  int amp_exp;
+  frexpf(s_amp_max * vp.sustain, &amp_exp);
+  const float scale_a = exp2f(static_cast<float>(min(100, 15 - amp_exp)));
+  const float unscale = 1.f / (scale_a * kScaleB);
+  const int64_t press_end = static_cast<int64_t>(vp.key_delay) + max_press + vp.hold;
+  const bool released = vp.release_at >= 0;
+  const int n_slices = a.ppad >> 3;  // K slices of 16 = eight partials
+
+  mbar_wait_or_trap(&bars[0], 0);
+
+  // epilogue of the chunk whose accumulator is buffer b: 128 lanes (samples) x 128 columns (blocks)
+  auto drain = [&](int64_t chunk, int b, uint32_t parity) {
+    mbar_wait_or_trap(&bars[1 + b], parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* o = a.out + v * a.n_samples + chunk * kUChunk + 32 * (warp & 3) + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(b * kUN + 64 * (warp >> 2));
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      uint32_t r[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+          "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr + 32 * part));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[(64 * (warp >> 2) + 32 * part + j) * kUM] = __uint_as_float(r[j]) * unscale;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  const int64_t n_full = a.n_samples / kUChunk;
+  const int64_t c_begin = static_cast<int64_t>(blockIdx.x) * a.chunks_per_cta;
+  const int64_t c_end = min(n_full, c_begin + a.chunks_per_cta);
+  int it = 0;
+  int64_t prev = -1;
+  for (int64_t c = c_begin; c < c_end; ++c) {
+    const int64_t n0 = a.first_sample + c * kUChunk, n1 = n0 + kUChunk;
+    const bool steady = (n1 - vp.key_delay >= 1) && (n0 + 1 > press_end) && (!released || n1 <= vp.release_at);
+    if (!steady) continue;  // uniform over the CTA: the other kernel renders this chunk
+    const int b = it & 1;
+    if (tid < a.ppad) {
+      const PartialParams q = pp[tid];
+      const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
+      const float am = q.amp * vp.sustain * scale_a;
+      seed[b * 64 + tid] = make_float2(am * z.x, am * z.y);
+    }
+    __syncthreads();
+    if (32 * h < a.ppad) {
+      unsigned char* dst_hi = sA + (2 * b) * kUOperand + canon_off(l, 64 * h);
+      unsigned char* dst_lo = dst_hi + kUOperand;
+#pragma unroll
+      for (int gq = 0; gq < 8; ++gq) {  // four partials = eight columns of K = one 16-byte store per half
+        uint4 vh, vl;
+        float2 e;
+        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 0], eg[4 * gq + 0]);
+        f16_split(e.x, e.y, vh.x, vl.x);
+        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 1], eg[4 * gq + 1]);
+        f16_split(e.x, e.y, vh.y, vl.y);
+        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 2], eg[4 * gq + 2]);
+        f16_split(e.x, e.y, vh.z, vl.z);
+        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 3], eg[4 * gq + 3]);
+        f16_split(e.x, e.y, vh.w, vl.w);
+        *reinterpret_cast<uint4*>(dst_hi + gq * 2048) = vh;
+        *reinterpret_cast<uint4*>(dst_lo + gq * 2048) = vl;
+      }
+    }
+    fence_proxy_async();  // the tensor core reads shared memory through the async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem_base + static_cast<uint32_t>(b * kUN);
+      const uint32_t a_hi = smem_u32(sA + (2 * b) * kUOperand), a_lo = a_hi + kUOperand;
+      const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + kUOperand;
+      for (int ks = 0; ks < n_slices; ++ks) {
+        const uint32_t o = static_cast<uint32_t>(ks) * 4096;  // two 16-byte K columns of 128 rows
+        umma_f16(d, umma_desc(a_lo + o), umma_desc(b_hi + o), ks > 0);
+        umma_f16(d, umma_desc(a_hi + o), umma_desc(b_lo + o), 1);
+        umma_f16(d, umma_desc(a_hi + o), umma_desc(b_hi + o), 1);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1 + b])) : "memory");
+    }
+    if (prev >= 0) drain(prev, b ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+    prev = c;
+    ++it;
+  }
+  if (prev >= 0) drain(prev, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+}
+
 __global__ void fp32_peak_kernel(float* out, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
         a7 = a0 + 7.f;
@@ -685,7 +934,9 @@ int oscbank_plan(ca_ctx* ctx, int64_t max_voices, int32_t max_partials) {
 void oscbank_release(ca_ctx* ctx) {
   if (ctx->d_osc_partials) cudaFree(ctx->d_osc_partials);
   if (ctx->d_osc_voices) cudaFree(ctx->d_osc_voices);
-  ctx->d_osc_partials = ctx->d_osc_voices = nullptr;
+  if (ctx->d_osc_umma) cudaFree(ctx->d_osc_umma);
+  ctx->d_osc_partials = ctx->d_osc_voices = ctx->d_osc_umma = nullptr;
+  ctx->osc_umma_bytes = 0;
   ctx->osc_max_voices = 0;
   ctx->osc_max_partials = 0;
 }
@@ -725,11 +976,46 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
 
   if (d.n_voices > 65535) return fail(ctx, CA_ERR_UNSUPPORTED, "ca_oscbank_render: more than 65535 voices per call");
   // CA_OSC_PATH=fp32 keeps the sustain-regime product on the FP32 pipe (FFMA2); the default runs it on the tensor cores (3 x FP16)
+  // (CA_OSC_PATH=mma: tensor cores through mma.sync only, without the tcgen05 kernel for the long steady stretches)
   const char* path = getenv("CA_OSC_PATH");
   const bool tensor = !(path && !strcmp(path, "fp32"));
   int rc;
   if (d.mix == CA_MIX_NONE) {
     a.voices_per_group = 1;
+    // Per-voice renders of up to 64 partials: the whole steady 16,384-sample chunks go to the tcgen05 kernel (operand tables
+    // of 128 KB per voice in device memory, at most 2 GB of them), everything else (attack, release, the tail, eased voices)
+    // to the kernel below, which skips what the other one renders.
+    const int64_t n_full = d.n_samples / kUChunk;
+    const size_t table_bytes = static_cast<size_t>(d.n_voices) * kUTableBytes;
+    if (tensor && !(path && !strcmp(path, "mma")) && ppad <= 64 && n_full > 0 && eased != 2 && table_bytes <= (size_t{2} << 30)) {
+      if (ctx->osc_umma_bytes < table_bytes) {
+        if (ctx->d_osc_umma) cudaFree(ctx->d_osc_umma);
+        ctx->d_osc_umma = nullptr;
+        ctx->osc_umma_bytes = 0;
+        CA_CUDA_OK(ctx, cudaMalloc(&ctx->d_osc_umma, table_bytes));
+        ctx->osc_umma_bytes = table_bytes;
+      }
+      UmmaArgs u{};
+      u.partials = pa.partials;
+      u.voices = pa.voices;
+      u.tables = static_cast<unsigned char*>(ctx->d_osc_umma);
+      u.n_voices = d.n_voices;
+      u.n_samples = d.n_samples;
+      u.first_sample = d.first_sample;
+      u.ppad = ppad;
+      u.out = d_out;
+      // one CTA per SM; enough CTAs per voice to fill the GPU twice when there are few voices
+      const int64_t per_voice = std::min<int64_t>(n_full, std::max<int64_t>(1, (2 * ctx->sm_count + d.n_voices - 1) / d.n_voices));
+      u.chunks_per_cta = static_cast<int32_t>((n_full + per_voice - 1) / per_voice);
+      osc_umma_tables_kernel<<<static_cast<unsigned>(d.n_voices), 256, 0, stream>>>(u);
+      const size_t usmem = 6 * kUOperand + 128 * sizeof(float2) + 64;
+      CA_CUDA_OK(ctx, cudaFuncSetAttribute(osc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(usmem)));
+      dim3 ugrid(static_cast<unsigned>((n_full + u.chunks_per_cta - 1) / u.chunks_per_cta), static_cast<unsigned>(d.n_voices));
+      osc_umma_kernel<<<ugrid, 256, usmem, stream>>>(u);
+      CA_CUDA_OK(ctx, cudaGetLastError());
+      ctx->launches += 2;
+      a.umma_skip = 1;
+    }
     // shape of the per-voice render: warps per CTA (the per-voice tables are built once per CTA, so a CTA takes chunks_per_warp
     // chunks per warp). Measured on config 3 (profiles/oscbank_shapes_r02.txt); CA_OSC_SHAPE / CA_OSC_CPW are the A/B switches.
     const char* shape = getenv("CA_OSC_SHAPE");

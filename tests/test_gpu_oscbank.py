@@ -296,3 +296,30 @@ def test_long_release_and_slow_attack(pkg, orc, ctx, wl):
     ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
                              release_at=rel, key_delay=kd)
     assert np.abs(out - ref).max() < TOL * 0.1
+
+
+@pytest.mark.parametrize("path", ["umma", "mma"])
+@pytest.mark.parametrize("n_partials", [64, 20])
+def test_long_steady_stretches_on_tcgen05(pkg, orc, ctx, wl, path, n_partials, monkeypatch):
+    # whole steady 16,384-sample chunks of a per-voice render go to the tcgen05 kernel (accumulator in tensor memory), the rest
+    # (attack, release, tail) to the mma.sync kernel; CA_OSC_PATH=mma renders everything with the latter. Full-scale voices.
+    monkeypatch.setenv("CA_OSC_PATH", path)
+    b = wl.c3_bank(6, n_partials)
+    b["volume"][:] = 1.0
+    n = 5 * 16384 + 1000
+    e = pkg.Ahdsr(300, 0, 200, 500, 0, 2000, 0, 0.8)
+    rel = np.array([-1, 70000, 40000, -1, 100, 16384 * 3], np.int64)   # never; in chunk 4; in chunk 2; never; at once; on a boundary
+    kd = np.array([0, 0, 20000, 16384, 0, 5], np.int32)
+    out = gpu_render(pkg, ctx, b, n, e, release_at=rel, key_delay=kd)
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n, env=orc_env(orc, e),
+                             release_at=rel, key_delay=kd)
+    assert np.abs(out - ref).max() < 2e-6
+
+
+def test_tcgen05_chunks_with_a_block_offset(pkg, orc, ctx, wl):
+    # block-wise rendering (first_sample > 0): the chunk grid is relative to the block, the phases to the note
+    b = wl.c3_bank(3, 40)
+    n_total, first, n = 200000, 61234, 2 * 16384 + 77
+    ref = orc.oscbank_render(b["f0_hz"], b["volume"], b["partial_volume"], b["partial_phase"], n_total)
+    part = gpu_render(pkg, ctx, b, n, default_env(pkg), first_sample=first)
+    assert np.abs(part - ref[:, first:first + n]).max() < TOL * 0.1
