@@ -339,20 +339,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) oscbank_kernel(const __grid_
     const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;  // last non-sustain counter
     const bool released = vp.release_at >= 0;
     const bool dead_note = released && (vp.release_at - vp.key_delay <= 0);
-    // is the 2048-sample chunk `chunk` rendered by the tcgen05 kernel (as part of a whole, steady 16,384-sample chunk)?
-    auto umma_renders = [&](int64_t chunk) {
-      if (!a.umma_skip || vp.itp != 0) return false;
-      const int64_t uc = (chunk * kChunk) / kUmmaChunk;
-      if ((uc + 1) * kUmmaChunk > a.n_samples) return false;
-      const int64_t u0 = a.first_sample + uc * kUmmaChunk, u1 = u0 + kUmmaChunk;
-      return (u1 - vp.key_delay >= 1) && (u0 + 1 > press_end) && (!released || u1 <= vp.release_at);
-    };
+    // Which 2048-sample chunks does the tcgen05 kernel render? The steady ones, m_lo .. m_hi: first sample at or after the end
+    // of the pressed transitions, last sample before the release (the same closed form as in osc_umma_kernel; it also writes
+    // sustain-level signal over the other chunks of its 16,384-sample chunks, which this kernel, launched after it, renders).
+    int64_t m_lo = 1, m_hi = 0;
+    if (a.umma_skip && vp.itp == 0) {
+      const int64_t d0 = press_end - a.first_sample;
+      m_lo = d0 <= 0 ? 0 : (d0 + kChunk - 1) / kChunk;
+      m_hi = a.n_chunks - 1;
+      if (released && vp.release_at < n_end) {
+        const int64_t d1 = vp.release_at - a.first_sample;
+        m_hi = d1 < kChunk ? -1 : min(m_hi, d1 / kChunk - 1);
+      }
+    }
+    auto umma_renders = [&](int64_t chunk) { return chunk >= m_lo && chunk <= m_hi; };
     if (a.umma_skip) {  // nothing to do for this voice in this CTA: skip the tables too (uniform)
-      bool needed = false;
       const int64_t first = static_cast<int64_t>(blockIdx.x) * a.chunks_per_warp * WARPS;
       const int64_t last = min(a.n_chunks, first + static_cast<int64_t>(a.chunks_per_warp) * WARPS);
-      for (int64_t c = first; c < last && !needed; ++c) needed = !umma_renders(c);
-      if (!needed) continue;
+      if (first >= last || (first >= m_lo && last - 1 <= m_hi)) continue;
     }
     for (int i = threadIdx.x; i < a.ppad * 32; i += WARPS * 32) {
       const int p = i >> 5, l = i & 31;
@@ -679,6 +683,7 @@ struct UmmaArgs {
   int64_t n_voices, n_samples, first_sample;
   int32_t ppad;
   int32_t chunks_per_cta;
+  int32_t ablate;  // profiling only (CA_OSC_ABLATE): 1 no MMA, 2 no operand preparation, 4 no stores, 8 no seeds
   float* out;
 };
 
@@ -719,6 +724,14 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
   }
   __trap();
 }
+// 1-D bulk copy shared -> global through the TMA engine (the LSU sees none of it), tracked in bulk groups of the issuing thread
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // shared-memory matrix descriptor (tcgen05): start address, leading / stride byte offsets in 16-byte units, version 1, no swizzle
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return static_cast<uint64_t>((smem_addr >> 4) & 0x3fff) | (static_cast<uint64_t>(2048 >> 4) << 16) |
@@ -734,16 +747,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1) osc_umma_kernel(const __grid_constant__ UmmaArgs a) {
+// Two teams of eight warps per CTA, each a pipeline of its own over every other chunk: prepare A (256 threads: four... two per
+// row, 32 partials each) -> team barrier -> one thread issues the 24 MMAs and commits them to the team's mbarrier -> all wait
+// for it and drain the accumulator (128 lanes x 128 columns, 32 x 64 per warp). A team's waits (barrier, tensor core, stores)
+// are the other team's issue slots; nothing is shared between the teams but the B tables and the tensor core itself.
+constexpr int kUWarps = 16;
+
+__global__ void __launch_bounds__(kUWarps * 32, 1) osc_umma_kernel(const __grid_constant__ UmmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* sA = smem_raw;                          // [2 buffers][hi, lo][32 KB]
+  unsigned char* sA = smem_raw;                          // [2 teams][hi, lo][32 KB]
   unsigned char* sB = smem_raw + 4 * kUOperand;          // [hi, lo][32 KB]
-  float2* seed = reinterpret_cast<float2*>(sB + 2 * kUOperand);  // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(seed + 128);      // [0]: table copy, [1], [2]: accumulator buffers
+  float2* seed = reinterpret_cast<float2*>(sB + 2 * kUOperand);  // [2 teams][2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(seed + 256);      // [0]: table copy, [1], [2]: the teams' accumulators
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   __shared__ float s_amp_max;
+  __shared__ int s_max_press;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int team = warp >> 3, tt = tid & 255, tw = warp & 7;  // thread and warp inside the team
   const int64_t v = blockIdx.y;
   const VoiceParams vp = a.voices[v];
   if (vp.itp != 0) return;  // eased envelopes: everything is left to the other kernel (uniform over the CTA)
@@ -755,6 +776,7 @@ __global__ void __launch_bounds__(256, 1) osc_umma_kernel(const __grid_constant_
     mbar_init(&bars[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_amp_max = 0.f;
+    s_max_press = 0;
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
@@ -763,7 +785,7 @@ __global__ void __launch_bounds__(256, 1) osc_umma_kernel(const __grid_constant_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d = *tmem_slot + static_cast<uint32_t>(team * kUN);
 
   const unsigned char* tab = a.tables + v * kUTableBytes;
   if (tid == 0) {
@@ -771,112 +793,167 @@ __global__ void __launch_bounds__(256, 1) osc_umma_kernel(const __grid_constant_
     bulk_g2s(sB, tab, kUOperand, &bars[0]);
     bulk_g2s(sB + kUOperand, tab + kUOperand, kUOperand, &bars[0]);
   }
-  // the thread's row of A: sample l of every block, partials 32 h .. 32 h + 31
-  const int l = tid & 127, h = tid >> 7;
-  float2 eg[32];
+  // the thread's part of A: sample l of every block, partials 32 h .. 32 h + 31, as packed pairs (Re, Im) of exp(i l w_p)
+  const int l = tt & 127, h = tt >> 7;
+  c2 eg[32];
   {
-    const float2* e128 = reinterpret_cast<const float2*>(tab + 2 * kUOperand);
+    const c2* e128 = reinterpret_cast<const c2*>(tab + 2 * kUOperand);
 #pragma unroll
     for (int i = 0; i < 32; ++i) eg[i] = e128[(32 * h + i) * 128 + l];
   }
-  if (tid < a.ppad && pp[tid].amp != 0.f) atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(pp[tid].amp)));
-  int max_press = 0;
-  for (int p = 0; p < a.ppad; ++p)
-    if (pp[p].amp != 0.f) max_press = max(max_press, pp[p].attack + pp[p].decay);
+  if (tid < a.ppad && pp[tid].amp != 0.f) {
+    atomicMax(reinterpret_cast<int*>(&s_amp_max), __float_as_int(fabsf(pp[tid].amp)));
+    atomicMax(&s_max_press, pp[tid].attack + pp[tid].decay);
+  }
   __syncthreads();
   int amp_exp;
   frexpf(s_amp_max * vp.sustain, &amp_exp);
   const float scale_a = exp2f(static_cast<float>(min(100, 15 - amp_exp)));
   const float unscale = 1.f / (scale_a * kScaleB);
-  const int64_t press_end = static_cast<int64_t>(vp.key_delay) + max_press + vp.hold;
+  const int64_t press_end = static_cast<int64_t>(vp.key_delay) + s_max_press + vp.hold;
   const bool released = vp.release_at >= 0;
   const int n_slices = a.ppad >> 3;  // K slices of 16 = eight partials
+  const int64_t n_end = a.first_sample + a.n_samples;
+  unsigned char* myA = sA + (2 * team) * kUOperand;
+  float2* myseed = seed + team * 128;
 
-  mbar_wait_or_trap(&bars[0], 0);
+  auto make_seed = [&](int64_t c, int b) {  // threads 0 .. ppad-1 of the team: exact phase of the chunk's first sample
+    const PartialParams q = pp[tt];
+    const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(a.first_sample + c * kUChunk + 1));
+    const float am = q.amp * vp.sustain * scale_a;
+    myseed[b * 64 + tt] = make_float2(am * z.x, am * z.y);
+  };
+  auto team_barrier = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory"); };
 
-  // epilogue of the chunk whose accumulator is buffer b: 128 lanes (samples) x 128 columns (blocks)
-  auto drain = [&](int64_t chunk, int b, uint32_t parity) {
-    mbar_wait_or_trap(&bars[1 + b], parity);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* o = a.out + v * a.n_samples + chunk * kUChunk + 32 * (warp & 3) + lane;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(b * kUN + 64 * (warp >> 2));
+  // Epilogue: 128 lanes (samples) x 128 columns (blocks of 128 samples); the warp takes the lanes it may read
+  // (32 (warp % 4) ..) and 64 columns, 16 at a time. The 64 KB of a whole chunk are staged in the team's A operand (the tensor
+  // core is done with it: same size, and in the order of the output) and handed to the TMA engine as ONE bulk copy: the output
+  // never enters the LSU's global queue, which 32 stores per thread kept full (lg_throttle) while the other team's shared-
+  // memory traffic queued behind them. The copy must have read the buffer before the team prepares its next A.
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(a.out + v * a.n_samples) & 15) == 0 && !(a.ablate & 16);  // uniform
+  bool staged = false;
+  auto drain = [&](int64_t chunk) {
+    const int smp = 32 * (tw & 3) + lane;  // sample inside the block
+    const int col0 = 64 * (tw >> 2);
+    float* o = a.out + v * a.n_samples + chunk * kUChunk;
+    const bool whole = (chunk + 1) * kUChunk <= a.n_samples;
+    float* stage = reinterpret_cast<float*>(myA);
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-      uint32_t r[32];
+    for (int part = 0; part < 4; ++part) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_d + (static_cast<uint32_t>(32 * (tw & 3)) << 16) + static_cast<uint32_t>(col0 + 16 * part);
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-          "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
           : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr + 32 * part));
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if ((a.ablate & 4) && r[0] != 0x12345678u) continue;
+      if (whole && tma_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[(64 * (warp >> 2) + 32 * part + j) * kUM] = __uint_as_float(r[j]) * unscale;
+        for (int j = 0; j < 16; ++j) stage[(col0 + 16 * part + j) * kUM + smp] = __uint_as_float(r[j]) * unscale;
+      } else if (whole) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[(col0 + 16 * part + j) * kUM + smp] = __uint_as_float(r[j]) * unscale;
+      } else {  // the last, partial chunk of the render
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (chunk * kUChunk + (col0 + 16 * part + j) * kUM + smp < a.n_samples)
+            o[(col0 + 16 * part + j) * kUM + smp] = __uint_as_float(r[j]) * unscale;
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    staged = whole && tma_ok;
+    if (staged) {
+      fence_proxy_async();
+      team_barrier();
+      if (tt == 0) {
+        bulk_s2g(o, stage, kUChunk * sizeof(float));
+        bulk_commit();
+      }
+    }
   };
 
-  const int64_t n_full = a.n_samples / kUChunk;
+  // which chunks of this CTA are rendered here: at least one of the eight 2048-sample chunks inside is steady in the sense of
+  // oscbank_kernel (the envelope sits at the sustain level); that kernel, launched afterwards, renders the ones that are not.
+  // The teams take them alternately.
+  const int64_t n_chunks = (a.n_samples + kUChunk - 1) / kUChunk;
   const int64_t c_begin = static_cast<int64_t>(blockIdx.x) * a.chunks_per_cta;
-  const int64_t c_end = min(n_full, c_begin + a.chunks_per_cta);
+  const int n_mine = static_cast<int>(min(n_chunks, c_begin + a.chunks_per_cta) - c_begin);  // <= 64
+  // steady 2048-sample chunks of the render: m_lo .. m_hi (first sample first_sample + 2048 m at or after the end of the
+  // pressed transitions, last sample before the release)
+  const int64_t n_small = (a.n_samples + kChunk - 1) / kChunk;
+  const int64_t d0 = press_end - a.first_sample;
+  const int64_t m_lo = d0 <= 0 ? 0 : (d0 + kChunk - 1) / kChunk;
+  int64_t m_hi = n_small - 1;
+  if (released && vp.release_at < n_end) {
+    const int64_t d1 = vp.release_at - a.first_sample;
+    m_hi = d1 < kChunk ? -1 : min(m_hi, d1 / kChunk - 1);
+  }
+  uint64_t todo = 0;
+  int taken = 0;
+  for (int i = 0; i < n_mine; ++i) {
+    const int64_t s0 = (c_begin + i) * (kUChunk / kChunk);
+    const bool any = max(s0, m_lo) <= min(s0 + kUChunk / kChunk - 1, m_hi);
+    if (any && (taken++ & 1) == team) todo |= 1ull << i;
+  }
+  if (todo && tt < a.ppad) make_seed(c_begin + __ffsll(static_cast<long long>(todo)) - 1, 0);
+  mbar_wait_or_trap(&bars[0], 0);
+  __syncthreads();
   int it = 0;
-  int64_t prev = -1;
-  for (int64_t c = c_begin; c < c_end; ++c) {
-    const int64_t n0 = a.first_sample + c * kUChunk, n1 = n0 + kUChunk;
-    const bool steady = (n1 - vp.key_delay >= 1) && (n0 + 1 > press_end) && (!released || n1 <= vp.release_at);
-    if (!steady) continue;  // uniform over the CTA: the other kernel renders this chunk
+  while (todo) {  // every condition in this loop is uniform over the team
     const int b = it & 1;
-    if (tid < a.ppad) {
-      const PartialParams q = pp[tid];
-      const float2 z = cis_turns_u64(q.ph0 + q.inc * static_cast<uint64_t>(n0 + 1));
-      const float am = q.amp * vp.sustain * scale_a;
-      seed[b * 64 + tid] = make_float2(am * z.x, am * z.y);
+    const int64_t c = c_begin + __ffsll(static_cast<long long>(todo)) - 1;
+    todo &= todo - 1;
+    if (staged) {  // the bulk copy of the previous chunk must have read the buffer
+      if (tt == 0) bulk_wait_read();
+      team_barrier();
     }
-    __syncthreads();
-    if (32 * h < a.ppad) {
-      unsigned char* dst_hi = sA + (2 * b) * kUOperand + canon_off(l, 64 * h);
+    if (32 * h < a.ppad && !(a.ablate & 2)) {
+      unsigned char* dst_hi = myA + canon_off(l, 64 * h);
       unsigned char* dst_lo = dst_hi + kUOperand;
+      const float4* sd = reinterpret_cast<const float4*>(myseed + b * 64 + 32 * h);
 #pragma unroll
       for (int gq = 0; gq < 8; ++gq) {  // four partials = eight columns of K = one 16-byte store per half
-        uint4 vh, vl;
-        float2 e;
-        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 0], eg[4 * gq + 0]);
-        f16_split(e.x, e.y, vh.x, vl.x);
-        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 1], eg[4 * gq + 1]);
-        f16_split(e.x, e.y, vh.y, vl.y);
-        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 2], eg[4 * gq + 2]);
-        f16_split(e.x, e.y, vh.z, vl.z);
-        e = cmul(seed[b * 64 + 32 * h + 4 * gq + 3], eg[4 * gq + 3]);
-        f16_split(e.x, e.y, vh.w, vl.w);
-        *reinterpret_cast<uint4*>(dst_hi + gq * 2048) = vh;
-        *reinterpret_cast<uint4*>(dst_lo + gq * 2048) = vl;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; i += 2) {
+          const float4 s2 = sd[2 * gq + (i >> 1)];  // two seeds
+          // e = seed * exp(i l w): (sx gx - sy gy, sx gy + sy gx) = sx * (gx, gy) + sy * (-gy, gx), packed
+          const c2 e0 = fma2(bc(s2.y), cmuli(eg[4 * gq + i]), mul2(bc(s2.x), eg[4 * gq + i]));
+          const c2 e1 = fma2(bc(s2.w), cmuli(eg[4 * gq + i + 1]), mul2(bc(s2.z), eg[4 * gq + i + 1]));
+          const float2 f0 = upk(e0), f1 = upk(e1);
+          f16_split(f0.x, f0.y, hi[i], lo[i]);
+          f16_split(f1.x, f1.y, hi[i + 1], lo[i + 1]);
+        }
+        *reinterpret_cast<uint4*>(dst_hi + gq * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst_lo + gq * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
+    if (todo && tt < a.ppad && !(a.ablate & 8)) make_seed(c_begin + __ffsll(static_cast<long long>(todo)) - 1, b ^ 1);  // published by the barrier
     fence_proxy_async();  // the tensor core reads shared memory through the async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
+    team_barrier();
+    if (tt == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d = tmem_base + static_cast<uint32_t>(b * kUN);
-      const uint32_t a_hi = smem_u32(sA + (2 * b) * kUOperand), a_lo = a_hi + kUOperand;
+      const uint32_t a_hi = smem_u32(myA), a_lo = a_hi + kUOperand;
       const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + kUOperand;
-      for (int ks = 0; ks < n_slices; ++ks) {
+      for (int ks = 0; ks < ((a.ablate & 1) ? 0 : n_slices); ++ks) {
         const uint32_t o = static_cast<uint32_t>(ks) * 4096;  // two 16-byte K columns of 128 rows
-        umma_f16(d, umma_desc(a_lo + o), umma_desc(b_hi + o), ks > 0);
-        umma_f16(d, umma_desc(a_hi + o), umma_desc(b_lo + o), 1);
-        umma_f16(d, umma_desc(a_hi + o), umma_desc(b_hi + o), 1);
+        umma_f16(tmem_d, umma_desc(a_lo + o), umma_desc(b_hi + o), ks > 0);
+        umma_f16(tmem_d, umma_desc(a_hi + o), umma_desc(b_lo + o), 1);
+        umma_f16(tmem_d, umma_desc(a_hi + o), umma_desc(b_hi + o), 1);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1 + b])) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1 + team])) : "memory");
     }
-    if (prev >= 0) drain(prev, b ^ 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
-    prev = c;
+    mbar_wait_or_trap(&bars[1 + team], static_cast<uint32_t>(it & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    drain(c);
     ++it;
   }
-  if (prev >= 0) drain(prev, (it - 1) & 1, static_cast<uint32_t>(((it - 1) >> 1) & 1));
+  if (tt == 0) bulk_wait_all();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"(256));
 }
 
 __global__ void fp32_peak_kernel(float* out, int iters) {
@@ -982,12 +1059,12 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
   int rc;
   if (d.mix == CA_MIX_NONE) {
     a.voices_per_group = 1;
-    // Per-voice renders of up to 64 partials: the whole steady 16,384-sample chunks go to the tcgen05 kernel (operand tables
-    // of 128 KB per voice in device memory, at most 2 GB of them), everything else (attack, release, the tail, eased voices)
-    // to the kernel below, which skips what the other one renders.
-    const int64_t n_full = d.n_samples / kUChunk;
+    // Per-voice renders of up to 64 partials: the steady stretches go to the tcgen05 kernel in chunks of 16,384 samples (operand
+    // tables of 128 KB per voice in device memory, at most 2 GB of them), the 2048-sample chunks with an envelope transition
+    // (and eased voices) to the kernel below, which skips what the other one renders.
+    const int64_t n_full = (d.n_samples + kUChunk - 1) / kUChunk;
     const size_t table_bytes = static_cast<size_t>(d.n_voices) * kUTableBytes;
-    if (tensor && !(path && !strcmp(path, "mma")) && ppad <= 64 && n_full > 0 && eased != 2 && table_bytes <= (size_t{2} << 30)) {
+    if (tensor && !(path && !strcmp(path, "mma")) && ppad <= 64 && d.n_samples >= kUChunk / 2 && eased != 2 && table_bytes <= (size_t{2} << 30)) {
       if (ctx->osc_umma_bytes < table_bytes) {
         if (ctx->d_osc_umma) cudaFree(ctx->d_osc_umma);
         ctx->d_osc_umma = nullptr;
@@ -1004,14 +1081,15 @@ int oscbank_render(ca_ctx* ctx, const ca_oscbank_desc* desc, float* d_out, cudaS
       u.first_sample = d.first_sample;
       u.ppad = ppad;
       u.out = d_out;
+      u.ablate = getenv("CA_OSC_ABLATE") ? atoi(getenv("CA_OSC_ABLATE")) : 0;
       // one CTA per SM; enough CTAs per voice to fill the GPU twice when there are few voices
       const int64_t per_voice = std::min<int64_t>(n_full, std::max<int64_t>(1, (2 * ctx->sm_count + d.n_voices - 1) / d.n_voices));
       u.chunks_per_cta = static_cast<int32_t>((n_full + per_voice - 1) / per_voice);
       osc_umma_tables_kernel<<<static_cast<unsigned>(d.n_voices), 256, 0, stream>>>(u);
-      const size_t usmem = 6 * kUOperand + 128 * sizeof(float2) + 64;
+      const size_t usmem = 6 * kUOperand + 256 * sizeof(float2) + 64;
       CA_CUDA_OK(ctx, cudaFuncSetAttribute(osc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(usmem)));
       dim3 ugrid(static_cast<unsigned>((n_full + u.chunks_per_cta - 1) / u.chunks_per_cta), static_cast<unsigned>(d.n_voices));
-      osc_umma_kernel<<<ugrid, 256, usmem, stream>>>(u);
+      osc_umma_kernel<<<ugrid, kUWarps * 32, usmem, stream>>>(u);
       CA_CUDA_OK(ctx, cudaGetLastError());
       ctx->launches += 2;
       a.umma_skip = 1;
