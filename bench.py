@@ -419,46 +419,62 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sms = float(t.item())
         voice_samples = world * args.voices * ns / (sms * 1e-3)
-        # the same render with the sustain-regime product kept on the FP32 pipe (FFMA2) instead of the tensor cores
-        os.environ["CA_OSC_PATH"] = "fp32"
-        for _ in range(2):
-            synth_step()
-        sync_all()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(reps):
-            synth_step()
-        f1.record()
-        sync_all()
-        del os.environ["CA_OSC_PATH"]
-        fms = f0.elapsed_time(f1) / reps
-        if world > 1:
-            t = torch.tensor([fms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            fms = float(t.item())
+
+        def timed_variant(path):
+            """The same render with the sustain-regime product on another pipe (CA_OSC_PATH)."""
+            os.environ["CA_OSC_PATH"] = path
+            for _ in range(2):
+                synth_step()
+            sync_all()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                synth_step()
+            f1.record()
+            sync_all()
+            del os.environ["CA_OSC_PATH"]
+            ms = f0.elapsed_time(f1) / reps
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        mms, fms = timed_variant("mma"), timed_variant("fp32")
         fp32_peak = ctx.measure_fp32_peak()
+        peak_gbs_s, _ = measured_peaks()
         part = voice_samples * 64
-        fpart = world * args.voices * ns * 64 / (fms * 1e-3)
+        per_rank = args.voices * ns
         extra["synthesis"] = {
             "workload": f"C3: {args.voices} voices x 64 partials x {args.synth_seconds:g} s @48 kHz per GPU, per-voice float32 output",
-            "path": "sustain regime as a 32 x 64 x 128 matrix product per 2048-sample chunk on the tensor cores: mma.sync m16n8k16, "
-                    "FP16 operands split hi/lo (3 products, FP32-equivalent), FP32 accumulation",
+            "path": "sustain regime as a matrix product per chunk (samples x blocks x 2 partials), FP16 operands split hi/lo (3 products, "
+                    "FP32-equivalent), FP32 accumulation: tcgen05.mma with the accumulator in tensor memory for the steady 16,384-sample "
+                    "chunks, mma.sync m16n8k16 for the 2048-sample chunks with an envelope transition",
             "voice_samples_per_s": voice_samples, "partial_samples_per_s": part, "ms_per_render": sms,
-            "tensor_tflops_executed": part * 2 * 2 * 3 / world / 1e12,
+            "bound": "hbm (the output: 4 B per voice-sample)",
             "hbm_write_gbs": voice_samples * 4 / world / 1e9,
+            "hbm_frac": voice_samples * 4 / world / 1e9 / peak_gbs_s,
+            "tensor_tflops_executed": part * 2 * 2 * 3 / world / 1e12,
             "fp32_peak_tflops_measured": fp32_peak,
             "fp32_frac_official_8flop": part * 8 / world / 1e12 / fp32_peak,
             "note": "official count = 8 FLOP per partial-sample (rotate 6 + MAC 2, SURVEY §8d): the product form needs 2 FMA per "
-                    "partial-sample, and runs them on the tensor pipe, so this fraction of the FP32 peak can exceed 1",
-            # tensor-pipe / FP32-pipe utilisation as ncu counts it (committed captures; constants, not measured here)
-            "ncu": ncu_traffic("oscbank_kernel_counters"),
-            "fp32_pipe_variant": {
-                "path": "the same product on the FP32 pipe (CA_OSC_PATH=fp32): FFMA2, 2 FMA per partial-sample",
-                "voice_samples_per_s": fpart / 64, "ms_per_render": fms,
-                "fp32_frac_executed_4flop": fpart * 4 / world / 1e12 / fp32_peak,
-                "fp32_frac_official_8flop": fpart * 8 / world / 1e12 / fp32_peak,
-                "ncu": ncu_traffic("oscbank_fp32_kernel_counters"),
+                    "partial-sample and runs them on the tensor pipe, so this fraction of the FP32 peak exceeds 1; what bounds the render "
+                    "now is the 4 bytes written per voice-sample (hbm_frac)",
+            # pipe utilisation as ncu counts it (committed captures; constants, not measured here)
+            "ncu": ncu_traffic("oscbank_umma_counters"),
+            "mma_sync_variant": {
+                "path": "CA_OSC_PATH=mma: every chunk on mma.sync m16n8k16 (3 x FP16), no tcgen05 kernel",
+                "voice_samples_per_s": world * per_rank / (mms * 1e-3), "ms_per_render": mms,
+                "ncu": ncu_traffic("oscbank_mma_counters"),
             },
+            "fp32_pipe_variant": {
+                "path": "CA_OSC_PATH=fp32: the same product on the FP32 pipe (FFMA2, 2 FMA per partial-sample)",
+                "voice_samples_per_s": world * per_rank / (fms * 1e-3), "ms_per_render": fms,
+                "fp32_frac_executed_4flop": world * per_rank * 64 / (fms * 1e-3) * 4 / world / 1e12 / fp32_peak,
+                "fp32_frac_official_8flop": world * per_rank * 64 / (fms * 1e-3) * 8 / world / 1e12 / fp32_peak,
+                "ncu": ncu_traffic("oscbank_fp32_counters"),
+            },
+            "round1_kernel": ncu_traffic("oscbank_kernel_counters"),
         }
         del sout
 

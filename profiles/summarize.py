@@ -31,6 +31,16 @@ want = {
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
     "l1tex__throughput.avg.pct_of_peak_sustained_active": "l1tex_throughput_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_cycles_active_pct",
+    "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active": "tensor_pipe_inst_pct",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active": "tensor_hmma_cycles_active_pct",
+    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active": "uniform_pipe_pct",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier_per_issue",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio": "stall_lg_throttle_per_issue",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe_per_issue",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard_per_issue",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard_per_issue",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait_per_issue",
     "smsp__warp_issue_stalled_barrier_per_warp_active.pct": "stall_barrier_pct",
     "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct": "stall_short_scoreboard_pct",
     "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct": "stall_long_scoreboard_pct",
