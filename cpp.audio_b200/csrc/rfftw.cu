@@ -566,6 +566,329 @@ int launch_big2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cud
 
 
 // ---------------------------------------------------------------------------------------------------------------
+// N = 2^15 ... 2^17 in ONE pass through HBM, the frame held on chip across a thread-block cluster (CA_FFT_CLUSTER=0 restores the
+// CTA-per-frame / two-pass kernels above). M = N/2 = P x Q complex points, n = Q*r + c, k = kA + P*k2, with P = A*B rows and
+// Q = 32*R1 points per row chosen "square" so that both sides of HBM see long runs: a CTA of the C-CTA cluster reads a slab of P
+// rows x 16-32 columns (128-256-byte runs) and owns 2G = P/C rows of the transform (G adjacent rows and their G mirrors P - kA;
+// CTA 0 keeps row P/2 in the slot of row 0's mirror), so the untangled bins leave in runs of G >= 8 (64-128 bytes):
+//   columns  as big2_cols_kernel: A-point FFTs, exchange through the CTA's own shared memory, B-point FFTs, twiddle W_M^(c*kA);
+//            the 32 results per thread stay in registers across a cluster barrier (every CTA has started and is done with its
+//            exchange buffer, which is the row storage) and then go to the owners of their rows through distributed shared
+//            memory: st.shared::cluster + a second cluster barrier, or st.async counted on the owner's mbarrier (ASYNC),
+//   rows     one warp per 32/R1 rows (the warp-level transform of rfft_warp_kernel: R1 points per lane, 32-point columns),
+//   untangle X[k], X[M-k] from a row and its mirror, both local; consecutive threads take consecutive kA of the CTA's row set.
+// 16M bytes per frame instead of the 32M of the two-pass form; 35-40 KB of shared memory, 128 threads and 96 registers per CTA,
+// so five CTAs of different frames share an SM and one's loads overlap another's row transforms.
+// Measured and removed (profiles/fft_cluster_sweep_r02.txt): rows of 1024 points with P = 16/32/64-point columns in registers
+// (no column exchange, but G = 2-4: 16-32-byte output runs cost 2.6x the bytes on the L1->L2 path): 39-48 % of the HBM peak.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+// 8-byte store into a peer CTA's shared memory that also counts 8 bytes on the peer's mbarrier when it lands
+__device__ __forceinline__ void st_async_c2(uint32_t remote_addr, uint32_t remote_mbar, c2 v) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(v), "r"(remote_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+template <int A_, int B_, int R1_, int C_, bool ZT_ = true, bool ASYNC_ = false>
+struct Cluster2Cfg {
+  static constexpr bool ASYNC = ASYNC_;  // rows delivered by st.async counted on the owner's mbarrier, or by plain stores + a cluster barrier
+  static constexpr bool ZT = ZT_;  // transformed rows stored transposed (one more CTA barrier, no bank conflicts) or in place
+  static constexpr int A = A_, B = B_, R1 = R1_, C = C_;
+  static constexpr int P = A * B, Q = 32 * R1, M = P * Q;
+  static constexpr int G = P / (2 * C);        // adjacent rows per CTA (and as many mirrored ones)
+  static constexpr int FPW = 32 / R1;          // rows per warp
+  static constexpr int CWC = Q / C;            // columns per CTA (16 or 32: CWC*8-byte runs in HBM)
+  static constexpr int SUB = 32 / CWC;         // row groups per warp in the column phase
+  static constexpr int WARPS = 2 * G / FPW, T = 32 * WARPS, QT = WARPS * SUB;
+  // row stride while the rows are transformed (the warp's exchange layout fits in its rows); in-place form: G rows x 16/G
+  // consecutive k2 of the untangling loads cover the sixteen 8-byte banks once (the last row pass then stores with 2-4-way conflicts)
+  static constexpr int RS = ZT ? Q + 8 : Q + 16 + (G >= 16 ? 1 : 16 / G);
+  // the transformed rows are stored TRANSPOSED, Zt[k2][slot], KST apart: a half-warp's (R1 columns x 16/R1 rows) of the last
+  // row pass and the (G rows x 16/G values of k2) of the untangling loads both cover the sixteen 8-byte banks once
+  static constexpr int KST = 2 * G + 16 / R1;
+  static constexpr int kStore = (!ZT || RS * 2 * G > Q * KST) ? RS * 2 * G : Q * KST;
+  using W = WarpFftCfg<R1>;
+  static constexpr size_t smem = 16 + sizeof(float4) * W::kRows * 32 + sizeof(c2) * kStore;  // mbarrier, row tables, rows
+  static_assert(CWC == 32 || CWC == 16, "a CTA takes 16 or 32 columns");
+  static_assert(G == 32 || G == 16 || G == 8, "untangling lane maps");
+  static_assert(FPW * RS >= FPW * (R1 / 2) * kXStride && RS * 2 * G >= P * CWC, "exchange layouts fit in the row storage");
+  static_assert(A % QT == 0 && B % QT == 0 && (A / QT) * B == 32 && (FPW * RS) % 2 == 0, "32 points per thread");
+};
+
+template <typename Cf>
+__device__ __forceinline__ void cluster2_row_dest(int kA, uint32_t& rank, int& slot) {
+  constexpr int P = Cf::P, G = Cf::G;
+  if (kA < P / 2) {
+    rank = kA / G;
+    slot = kA % G;
+  } else if (kA == P / 2) {
+    rank = 0;
+    slot = G;
+  } else {
+    const int m = P - kA;
+    rank = m / G;
+    slot = G + m % G;
+  }
+}
+
+template <typename Cf, int I>
+__device__ __forceinline__ void cluster2_untangle(const c2* __restrict__ rows, float2* __restrict__ o, const TwP& wpb, int kA, int i, int k2_0) {
+  constexpr int P = Cf::P, Q = Cf::Q, M = Cf::M, G = Cf::G, KS = Cf::T / G;
+  constexpr int SK = Cf::ZT ? Cf::KST : 1, SR = Cf::ZT ? 1 : Cf::RS;  // strides of k2 and of the row slot
+  const int k2 = k2_0 + KS * I;
+  c2 zk, zm;
+  int64_t k;
+  if (kA == 0) {  // M - k = P*(Q - k2): the same row
+    if (k2 > Q / 2) return;
+    zk = rows[k2 * SK];
+    zm = rows[((Q - k2) & (Q - 1)) * SK];
+    k = static_cast<int64_t>(P) * k2;
+  } else {        // M - k = (P - kA) + P*(Q - 1 - k2)
+    zk = rows[k2 * SK + i * SR];
+    zm = rows[(Q - 1 - k2) * SK + (G + i) * SR];
+    k = kA + static_cast<int64_t>(P) * k2;
+  }
+  const c2 E = add2(zk, cconj(zm));
+  c2 D = csub(zk, cconj(zm));
+  if constexpr (I != 0) D = cmul_imm<Tw<2 * Q, KS * I>>(D);  // W_N^(P*KS*I) = W_2Q^(KS*I)
+  const c2 Tt = cmul_tw(D, wpb);
+  o[k] = upk(fma2(bc(0.5f), E, Tt));
+  o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
+}
+template <typename Cf, int... I>
+__device__ __forceinline__ void cluster2_untangle_all(const c2* rows, float2* o, const TwP& wpb, int kA, int i, int k2_0,
+                                                      std::integer_sequence<int, I...>) {
+  (cluster2_untangle<Cf, I>(rows, o, wpb, kA, i, k2_0), ...);
+}
+
+template <typename Cf>
+__global__ void __launch_bounds__(Cf::T, Cf::T == 128 ? 5 : (Cf::T == 256 ? 3 : 2)) rfft_cluster2_kernel(const float* __restrict__ in, float2* __restrict__ out) {
+  using W = typename Cf::W;
+  constexpr int A = Cf::A, B = Cf::B, R1 = Cf::R1, C = Cf::C, P = Cf::P, Q = Cf::Q, M = Cf::M, G = Cf::G, FPW = Cf::FPW, T = Cf::T,
+                QT = Cf::QT, RS = Cf::RS, NI1 = B / QT, NI2 = A / QT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* tab4 = reinterpret_cast<float4*>(smem_raw + 16);    // [W::kRows][32] row-transform twiddles
+  c2* rows = reinterpret_cast<c2*>(tab4 + W::kRows * 32);     // the column exchange u[A][B][32], then rows [2G][RS], then Zt[Q][KST]
+  constexpr int CWC = Cf::CWC;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int q = warp * Cf::SUB + lane / CWC, cl = lane % CWC;  // column phase: row group and column of the slab
+  const uint32_t rank = cluster_ctarank();
+  // the rows arrive from the whole cluster (this CTA included) as st.async stores that count their bytes on this mbarrier
+  const uint32_t mbar = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  if (Cf::ASYNC && t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(static_cast<uint32_t>(sizeof(c2) * 2 * G * Q)) : "memory");
+  }
+  const int64_t frame = blockIdx.x / C;
+  const int c = static_cast<int>(rank) * CWC + cl;  // this thread's column
+  const c2* src = reinterpret_cast<const c2*>(in) + frame * M + c;
+  // ---- columns, stage 1: r = B*r1 + r2; A-point FFT over r1 for r2 = q, q + QT, ...; twiddle W_P^(r2*k1) ----
+  c2 v[NI1][A];
+#pragma unroll
+  for (int it = 0; it < NI1; ++it)
+#pragma unroll
+    for (int r1 = 0; r1 < A; ++r1) v[it][bitrev(r1, ilog2(A))] = __ldg(src + (B * r1 + q + QT * it) * Q);
+  for (int i = t; i < (W::kRows - 1) * 32; i += T) {
+    const int r = i >> 5, l = i & 31;
+    const float2 w = r < W::B - 1 ? cis_neg_w(2.f * static_cast<float>(l * (r + 1)) / Q) : cis_neg_w(2.f * static_cast<float>(l * W::B * (r - (W::B - 2))) / Q);
+    tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
+  }
+  c2* u = rows;
+#pragma unroll
+  for (int it = 0; it < NI1; ++it) {
+    const int r2 = q + QT * it;
+    DitP<A, A, 0>::run(v[it]);
+    if (r2 != 0) {
+      c2 w[A];
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(r2) / P, &sn, &cs);
+      w[1] = pk(cs, -sn);
+      if constexpr (A > 2) cpow_all<A>(w, std::make_integer_sequence<int, A - 2>{});
+#pragma unroll
+      for (int k1 = 1; k1 < A; ++k1) {
+        const float2 a = upk(w[k1]);
+        v[it][k1] = cmul_tw(v[it][k1], TwP{a.x, pk(-a.y, a.y)});
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) u[(k1 * B + r2) * CWC + cl] = v[it][k1];
+  }
+  __syncthreads();
+  // ---- stage 2: B-point FFT over r2 for k1 = q, q + QT, ...: Y[k1 + A*k2], twiddle W_M^(c*(k1 + A*k2)); results stay in registers ----
+  c2 y[NI2][B];
+#pragma unroll
+  for (int it = 0; it < NI2; ++it)
+#pragma unroll
+    for (int r2 = 0; r2 < B; ++r2) y[it][bitrev(r2, ilog2(B))] = u[((q + QT * it) * B + r2) * CWC + cl];
+#pragma unroll
+  for (int it = 0; it < NI2; ++it) DitP<B, B, 0>::run(y[it]);  // (consumes the loads from u before the barrier is signalled)
+  cluster_arrive_relaxed();  // this CTA runs, its mbarrier is initialised (fence above) and it is done with its exchange buffer
+  {
+    c2 pw[B];  // pw[j] = W_M^(c*A*j)
+    {
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(c * A) / M, &sn, &cs);
+      pw[1] = pk(cs, -sn);
+    }
+    if constexpr (B > 2) cpow_all<B>(pw, std::make_integer_sequence<int, B - 2>{});
+#pragma unroll
+    for (int it = 0; it < NI2; ++it) {
+      float sn, cs;
+      sincospif(2.f * static_cast<float>(c * (q + QT * it)) / M, &sn, &cs);
+      const TwP base{cs, pk(sn, -sn)};
+#pragma unroll
+      for (int k2 = 0; k2 < B; ++k2) {
+        c2 val = cmul_tw(y[it][k2], base);
+        if (k2) {
+          const float2 a = upk(pw[k2]);
+          val = cmul_tw(val, TwP{a.x, pk(-a.y, a.y)});
+        }
+        y[it][k2] = val;
+      }
+    }
+  }
+  cluster_wait();
+  {
+    const uint32_t rows_addr = static_cast<uint32_t>(__cvta_generic_to_shared(rows));
+#pragma unroll
+    for (int it = 0; it < NI2; ++it)
+#pragma unroll
+      for (int k2 = 0; k2 < B; ++k2) {
+        uint32_t dr;
+        int slot;
+        cluster2_row_dest<Cf>(q + QT * it + A * k2, dr, slot);
+        const uint32_t rbase = mapa_u32(rows_addr, dr);  // the peer's window is a translation of this one: same offsets
+        if constexpr (Cf::ASYNC) st_async_c2(rbase + static_cast<uint32_t>(sizeof(c2)) * (slot * RS + c), rbase - (rows_addr - mbar), y[it][k2]);
+        else asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(rbase + static_cast<uint32_t>(sizeof(c2)) * (slot * RS + c)), "l"(y[it][k2]) : "memory");
+      }
+  }
+  if constexpr (Cf::ASYNC) {
+    mbar_wait_parity(mbar, 0);  // all 2G rows of this CTA have landed
+  } else {
+    cluster_arrive();  // the rows are complete once every CTA has stored its columns
+    cluster_wait();
+  }
+  // ---- rows: warp q transforms the FPW rows in slots [q*FPW, (q+1)*FPW) (Q = R1 x 32 points each), in place ----
+  {
+    c2* buf = rows + warp * FPW * RS;
+    c2 w1[FPW][R1];
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw)
+#pragma unroll
+      for (int n1 = 0; n1 < R1; ++n1) w1[fw][bitrev(n1, ilog2(R1))] = buf[fw * RS + 32 * n1 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int fw = 0; fw < FPW; ++fw) {
+      DitP<R1, R1, 0>::run(w1[fw]);
+      tww_chain<R1, 0>(w1[fw], tab4, lane, make_twp(tab4[lane]));
+      c2* xb = buf + fw * (R1 / 2) * kXStride;
+#pragma unroll
+      for (int m = 0; m < R1 / 2; ++m)
+        *reinterpret_cast<ulonglong2*>(xb + m * kXStride + 2 * lane) = make_ulonglong2(w1[fw][2 * m], w1[fw][2 * m + 1]);
+    }
+    __syncwarp();
+    c2 Acol[32];
+    const int col = lane & (R1 - 1), fr = lane / R1;
+    {
+      const c2* xb = buf + fr * (R1 / 2) * kXStride;
+#pragma unroll
+      for (int n2 = 0; n2 < 32; ++n2) Acol[bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
+    }
+    DitP<32, 32, 0>::run(Acol);
+    if constexpr (Cf::ZT) {
+      __syncthreads();  // every warp has read its exchange buffer: the storage is rewritten as Zt[k2][slot]
+      c2* Z = rows + warp * FPW + fr;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) Z[(col + R1 * k2) * Cf::KST] = Acol[k2];  // Z[kA + P*k2]
+    } else {
+      __syncwarp();
+      c2* Z = buf + fr * RS;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = Acol[k2];
+    }
+  }
+  __syncthreads();
+  // ---- untangle: consecutive threads take consecutive kA; k2 = k2_0 + (T/G)*I ----
+  float2* o = out + frame * (M + 1);
+  {
+    const int i = t & (G - 1);
+    int k2_0 = t / G;
+    if constexpr (G == 8 && Cf::ZT) {  // a half-warp takes k2 and k2 + R1/2 (banks 8 apart), see KST
+      const int j = (t >> 3) & 3, w = t >> 5;
+      k2_0 = (j & 1) * (R1 / 2) + (j >> 1) + (R1 == 8 ? 2 * (w & 1) + 8 * (w >> 1) : 4 * w);
+    }
+    const int kA = static_cast<int>(rank) * G + i;
+    float sn, cs;
+    sincospif(static_cast<float>(kA + P * k2_0) / M, &sn, &cs);  // W_N^(kA + P*k2_0) = (cs, -sn)
+    const TwP wpb{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};
+    cluster2_untangle_all<Cf>(rows, o, wpb, kA, i, k2_0, std::make_integer_sequence<int, Q * G / T>{});
+  }
+  if (rank == 0) {  // kA = P/2 (slot G): M - k = P/2 + P*(Q - 1 - k2)
+    constexpr int SK = Cf::ZT ? Cf::KST : 1, SR = Cf::ZT ? 1 : Cf::RS;
+    const c2* rs = rows + G * SR;
+    for (int k2 = t; k2 < Q / 2; k2 += T) {
+      float sn, cs;
+      sincospif(static_cast<float>(P / 2 + P * k2) / M, &sn, &cs);
+      const TwP wp{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};
+      const c2 zk = rs[k2 * SK], zm = rs[(Q - 1 - k2) * SK];
+      const c2 E = add2(zk, cconj(zm));
+      const c2 Tt = cmul_tw(csub(zk, cconj(zm)), wp);
+      const int64_t k = P / 2 + static_cast<int64_t>(P) * k2;
+      o[k] = upk(fma2(bc(0.5f), E, Tt));
+      o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
+    }
+  }
+}
+
+template <typename Cf>
+int launch_cluster2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
+  auto kern = rfft_cluster2_kernel<Cf>;
+  static int s_dev = -1;
+  if (s_dev != ctx->device) {
+    CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cf::smem)));
+    if (Cf::C > 8) CA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    s_dev = ctx->device;
+  }
+  const int64_t max_frames = (static_cast<int64_t>(1) << 31) / Cf::C - 1;
+  for (int64_t b0 = 0; b0 < batch; b0 += max_frames) {
+    const int64_t nb = std::min(max_frames, batch - b0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(nb * Cf::C));
+    cfg.blockDim = dim3(Cf::T);
+    cfg.dynamicSmemBytes = Cf::smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = Cf::C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CA_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, d_in + b0 * 2 * Cf::M, reinterpret_cast<float2*>(d_out) + b0 * (Cf::M + 1)));
+    ctx->launches += 1;
+  }
+  return CA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Fused analysis (window -> real FFT -> |X|^2 -> peaks) for the FFT lengths other than 4096: the transforms above with
 // the window applied on load and the untangling step producing |X|^2 (HBM row + a shared-memory copy) instead of complex
 // bins; the peak list is extracted from the shared-memory copy exactly as in stft.cu (strict local maxima above the
@@ -1230,6 +1553,9 @@ int big2_variant(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cu
 }  // namespace
 
 int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d_out, cudaStream_t stream) {
+  // A/B switch: CA_FFT_CLUSTER = 0 (CTA-per-frame / two-pass kernels) / 1 (cluster kernels, the measured default) / 2 (cluster
+  // kernels with the other delivery: st.async + mbarrier <-> plain stores + cluster barrier)
+  static const int cl = [] { const char* e = getenv("CA_FFT_CLUSTER"); return e ? atoi(e) : 1; }();
   switch (n_fft) {
     case 512: return launch_warp<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1024: return launch_warp<16, 8>(ctx, d_in, batch, d_out, stream);
@@ -1237,9 +1563,18 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 4096: return launch_warp<64, 12>(ctx, d_in, batch, d_out, stream);
     case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
-    case 32768: return launch_cta<16>(ctx, d_in, batch, d_out, stream);
-    case 1 << 16: return big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
-    case 1 << 17: return big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
+    case 32768:
+      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx, d_in, batch, d_out, stream);
+      return launch_cta<16>(ctx, d_in, batch, d_out, stream);
+    case 1 << 16:
+      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx, d_in, batch, d_out, stream);
+      return big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
+    case 1 << 17:
+      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx, d_in, batch, d_out, stream);
+      return big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1 << 18: return big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
     case 1 << 19: return big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
     case 1 << 20: return big2_variant<32, 16>(ctx, d_in, batch, d_out, stream);

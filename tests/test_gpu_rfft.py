@@ -116,3 +116,37 @@ def test_inverse_real_fft(pkg, ctx, p):
 def test_inverse_unsupported_length_fails_loudly(pkg, ctx):
     with pytest.raises(pkg.CaError):
         pkg.irfft_batched(ctx, torch.zeros((1, (1 << 16) // 2 + 1), dtype=torch.complex64, device="cuda"))
+
+
+@pytest.mark.parametrize("p,batch", [(15, 301), (16, 77), (17, 41)])
+def test_cluster_kernels_many_frames(pkg, ctx, p, batch):
+    """2^15 ... 2^17 run as one pass with the frame held across a thread-block cluster (rfft_cluster2_kernel): more frames than
+    clusters fit on the GPU at once, odd frame counts, every frame checked (torch.fft in double only as an independent anchor)."""
+    n = 1 << p
+    g = torch.Generator(device="cuda").manual_seed(9000 + p)
+    x = torch.empty((batch, n), device="cuda").uniform_(-1, 1, generator=g)
+    X = pkg.rfft_batched(ctx, x)
+    ref = torch.fft.rfft(x.double(), dim=1)
+    err = (X - ref).abs().max().item() / np.sqrt(n)
+    assert err < 1e-5, (p, err)
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_fft_ab_switch_paths(mode):
+    """CA_FFT_CLUSTER=0 (CTA-per-frame / two-pass kernels) and =2 (the other row delivery of the cluster kernels) stay correct:
+    the switch is read once per process, so each mode runs in its own interpreter."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import __graft_entry__ as g\n"
+        "pkg = g.load_package(); ctx = pkg.Context(0)\n"
+        "for p, b in ((15, 9), (16, 5), (17, 3)):\n"
+        "    x = torch.empty((b, 1 << p), device='cuda').uniform_(-1, 1)\n"
+        "    X = pkg.rfft_batched(ctx, x)\n"
+        "    err = (X - torch.fft.rfft(x.double(), dim=1)).abs().max().item() / np.sqrt(1 << p)\n"
+        "    assert err < 1e-5, (p, err)\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CA_FFT_CLUSTER=mode), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
