@@ -478,11 +478,13 @@ def run_ours(args):
         }
         del sout
 
-    # ---- BASELINE configs 1 and 5 (batched real FFT), three sizes of the sweep; the full sweep is profiles/sweep_rfft.py ----
+    # ---- BASELINE configs 1 and 5 (batched real FFT), points of the sweep (2^15 ... 2^17: the cluster kernels); the full sweep is
+    # profiles/sweep_rfft.py ----
     if not args.skip_rfft:
         peak_gbs, _ = measured_peaks()
         rf = {}
-        for n_fft, batch in ((1024, 4096), (1024, 262144), (4096, 65536), (16384, 16384), (1 << 18, 1024)):
+        for n_fft, batch in ((1024, 4096), (1024, 262144), (4096, 65536), (16384, 16384), (1 << 15, 8192), (1 << 16, 4096), (1 << 17, 2048),
+                             (1 << 18, 1024)):
             xr = torch.empty((batch, n_fft), dtype=torch.float32, device=dev).uniform_(-1, 1)
             yr = pkg.rfft_batched(ctx, xr)
             for _ in range(3):
