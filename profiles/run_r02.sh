@@ -25,6 +25,10 @@ cap oscbank_fp32 regex:oscbank_kernel 2 1 "CA_OSC_PATH=fp32" osc
 bash profiles/time_osc_paths.sh > gpurun_out/oscbank_paths_r02.txt 2>&1
 cap rfft1024 regex:rfft_warp 2 1 "" rfft 10
 cap big2 regex:big2_ 4 2 "" rfft 19
+# the single-pass cluster kernels (2^15: 4 CTAs per frame, 2^16: 8, 2^17: 16 with st.async delivery)
+cap rfft32768_cluster regex:rfft_cluster2 2 1 "" rfft 15
+cap rfft65536_cluster regex:rfft_cluster2 2 1 "" rfft 16
+cap rfft131072_cluster regex:rfft_cluster2 2 1 "" rfft 17
 cap roundtrip "regex:pitch_|stft64|tracks_kernel" 12 6 "" roundtrip_small
 CA_RT_TIMING=1 python profiles/time_roundtrip.py 32 60 > gpurun_out/roundtrip_time_r02.txt 2>&1
 python profiles/time_roundtrip.py 32 60 >> gpurun_out/roundtrip_time_r02.txt 2>&1

@@ -150,3 +150,43 @@ def test_fft_ab_switch_paths(mode):
         "print('ok')\n")
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CA_FFT_CLUSTER=mode), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("p", [15, 16, 17])
+def test_cluster_kernels_special_rows(pkg, ctx, p):
+    """Known answers that land on the rows the cluster kernels treat apart (row 0 and row P/2 pair with themselves; bins 0, N/4 and
+    N/2): a constant, the Nyquist alternation, an impulse (|X[k]| = 1 for every k, phase -2 pi k n0 / N) and tones in bins that
+    are multiples of the row count P, one off them, N/4 and N/2 - 1."""
+    n = 1 << p
+    t = np.arange(n)
+    n0 = 12345
+    frames = [np.ones(n), np.where(t % 2 == 0, 1.0, -1.0), (t == n0).astype(np.float64)]
+    tone_bins = [128, 129, 256, n // 4, n // 4 + 1, n // 2 - 1, 3 * (n // 8) + 5]
+    frames += [np.cos(2 * np.pi * k * t / n + 0.3) for k in tone_bins]
+    x = np.stack(frames).astype(np.float32)
+    X = gpu_rfft(pkg, ctx, x)
+    assert X.shape == (len(frames), n // 2 + 1)
+    # constant: X[0] = N, everything else 0
+    assert abs(X[0, 0] - n) / n < 1e-6 and np.abs(X[0, 1:]).max() / n < 1e-6
+    # alternation: X[N/2] = N
+    assert abs(X[1, n // 2] - n) / n < 1e-6 and np.abs(X[1, : n // 2]).max() / n < 1e-6
+    # impulse: unit magnitude in every bin, linear phase
+    k = np.arange(n // 2 + 1)
+    assert np.abs(X[2] - np.exp(-2j * np.pi * ((k * n0) % n) / n)).max() < 1e-5
+    # tones: N/2 * exp(i 0.3) in their bin, nothing elsewhere
+    for row, kb in zip(X[3:], tone_bins):
+        assert abs(row[kb] / (n / 2) - np.exp(0.3j)) < 1e-5, (p, kb)
+        rest = row.copy()
+        rest[kb] = 0
+        assert np.abs(rest).max() / (n / 2) < 1e-5, (p, kb)
+
+
+def test_cluster_kernel_single_frame_and_tail(pkg, ctx):
+    """One frame (one cluster) and a frame count that leaves the last wave of clusters partly empty."""
+    for p, batch in ((15, 1), (16, 1), (17, 1), (15, 149)):
+        n = 1 << p
+        rng = np.random.default_rng(4200 + p + batch)
+        x = rng.uniform(-1, 1, (batch, n)).astype(np.float32)
+        X = gpu_rfft(pkg, ctx, x)
+        ref = np.fft.rfft(x.astype(np.float64), axis=1)
+        assert np.abs(X - ref).max() / np.sqrt(n) < 1e-5, (p, batch)
