@@ -8,10 +8,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "cpp.audio_b200", "libcpp_audio_b200.so")
-want = sys.argv[1:] or ["stft4096p_kernel", "oscbank_kernel", "rfft_warp_kernel", "rfft_cta_kernel", "big2_", "stft_cta_kernel", "stft_warp_kernel",
+want = sys.argv[1:] or ["stft4096p_kernel", "osc_umma_kernel", "oscbank_kernel", "rfft_warp_kernel", "rfft_cta_kernel", "rfft_cluster2_kernel", "big2_",
+                        "stft_cta_kernel", "stft_warp_kernel",
                         "stft64_peaks_kernel", "pitch_track3_kernel", "pitch_prefix_kernel", "tracks_kernel", "sound_engine_kernel"]
 MNEMONICS = ["UTMALDG", "UBLKCP", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "DFMA", "DADD", "DMUL", "MUFU", "LDS", "STS", "LDG", "STG",
-             "SHFL", "BAR", "SYNCS", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "STL", "LDL"]
+             "SHFL", "BAR", "SYNCS", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "UTCBAR", "UCGABAR_ARV", "UCGABAR_WAIT", "ST", "STAS", "STL", "LDL"]
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 cur, counts, total = None, {}, {}
 for line in txt.splitlines():
@@ -28,8 +29,10 @@ for line in txt.splitlines():
         for k in MNEMONICS:
             if op == k or (k in ("LDS", "STS", "LDG", "STG", "SHFL", "BAR", "MUFU", "SYNCS") and op.startswith(k)):
                 counts[cur][k] += 1
-print(f"cuobjdump -sass {os.path.relpath(so, ROOT)} (sm_100a): static instruction counts per kernel; tensor-core mnemonics (UTC*MMA, HMMA, LDTM) are "
-      "expected to be absent: nothing on this path is a dense contraction")
+print(f"cuobjdump -sass {os.path.relpath(so, ROOT)} (sm_100a): static instruction counts per kernel. Tensor-core mnemonics are expected in the "
+      "oscillator bank only (UTCHMMA / LDTM / UTCBAR in osc_umma_kernel = tcgen05.mma / tcgen05.ld / tcgen05.commit, HMMA in oscbank_kernel = "
+      "mma.sync); UCGABAR_* / ST (generic store to a mapa address) / STAS (st.async) mark the cluster kernels' exchange through "
+      "distributed shared memory; UTMALDG / UBLKCP are TMA tensor and bulk copies")
 for name in sorted(counts):
     if not any(w in name for w in want):
         continue
