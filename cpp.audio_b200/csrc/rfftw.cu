@@ -858,6 +858,37 @@ __global__ void __launch_bounds__(Cf::T, Cf::T == 128 ? 5 : (Cf::T == 256 ? 3 : 
   }
 }
 
+// Can this device co-schedule one cluster of this shape (the 16-CTA clusters of 2^17 are a non-portable size)? Asked once per
+// instantiation and device; a "no" sends the length to the CTA-per-frame / two-pass kernels instead of failing the launch.
+template <typename Cf>
+bool cluster2_available(ca_ctx* ctx) {
+  static int s_dev = -1;
+  static bool s_ok = false;
+  if (s_dev != ctx->device) {
+    auto kern = rfft_cluster2_kernel<Cf>;
+    s_ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cf::smem)) == cudaSuccess;
+    if (s_ok && Cf::C > 8) s_ok = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (s_ok) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(Cf::C);
+      cfg.blockDim = dim3(Cf::T);
+      cfg.dynamicSmemBytes = Cf::smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = Cf::C;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      s_ok = cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1;
+    }
+    if (!s_ok) (void)cudaGetLastError();
+    s_dev = ctx->device;
+  }
+  return s_ok;
+}
+
 template <typename Cf>
 int launch_cluster2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out, cudaStream_t stream) {
   auto kern = rfft_cluster2_kernel<Cf>;
@@ -1568,16 +1599,16 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
     case 32768:
-      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx, d_in, batch, d_out, stream);
       return launch_cta<16>(ctx, d_in, batch, d_out, stream);
     case 1 << 16:
-      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx, d_in, batch, d_out, stream);
       return big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
     case 1 << 17:
-      if (cl == 1) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx, d_in, batch, d_out, stream);
       return big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1 << 18: return big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
     case 1 << 19: return big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
