@@ -21,6 +21,12 @@ struct StftPlan {
   double* d_window64 = nullptr;
   double2* d_tw64 = nullptr;
   int n64 = 0;
+  // internal (vocoder, FFT lengths >= 8192): per-frame band amplitudes sqrt(sum of |X|^2 over the bins [band_begin[b], band_begin[b+1])),
+  // summed from the kernel's shared-memory copy of the spectrum, so the |X|^2 rows need not go through HBM; set before each
+  // stft_analyze call (band_amps: [frames of the call][n_bands])
+  const int32_t* band_begin = nullptr;
+  int n_bands = 0;
+  float* band_amps = nullptr;
 };
 }  // namespace ca
 
@@ -85,6 +91,9 @@ struct StftArgs {
   float thr_below;  // largest float strictly below the sqmag threshold (-1 when there is no threshold)
   float bin_to_hz;
   int32_t freq_as_offset;  // internal: peak_freq receives the sub-bin offset p (round trip computes k+p in double)
+  const int32_t* band_begin;  // internal (vocoder): see StftPlan
+  int32_t n_bands;
+  float* band_amps;
   long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
 };
 

@@ -1259,6 +1259,17 @@ __global__ void __launch_bounds__(32 * M1, 16 / M1 > 4 ? 4 : 16 / M1) stft_cta_k
       if (rowo) rowo[M / 2] = s;
       sq[((M / 2) >> 5) * S::SB + ((M / 2) & 31)] = s;
     }
+    if (p.band_amps) {  // vocoder: amplitude of every band of this frame from the shared-memory copy of the spectrum
+      __syncthreads();
+      for (int b = warp; b < p.n_bands; b += M1) {
+        const int lo = p.band_begin[b], hi = p.band_begin[b + 1];
+        float acc = 0.f;
+        for (int i = lo + lane; i < hi; i += 32) acc += sq[(i >> 5) * S::SB + (i & 31)];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) p.band_amps[frame * p.n_bands + b] = sqrtf(acc);
+      }
+    }
     if (!p.peak_count) continue;
     __syncthreads();
     // ---- peaks: thread t owns bins [32t, 32t+32) ----

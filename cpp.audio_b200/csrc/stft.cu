@@ -562,6 +562,12 @@ int stft_analyze(ca_ctx* ctx, const StftPlan& plan, const float* d_x, int64_t n_
   a.max_peaks = plan.prm.max_peaks;
   a.thr_below = plan.thr_sq > 0.f ? nextafterf(plan.thr_sq, 0.f) : -1.f;
   a.bin_to_hz = static_cast<float>(static_cast<double>(plan.prm.sample_rate) / plan.n_fft);
+  if (plan.band_amps) {
+    if (plan.n_fft < 8192) return fail(ctx, CA_ERR_UNSUPPORTED, "stft_analyze: fused band amplitudes need an FFT length >= 8192");
+    a.band_begin = plan.band_begin;
+    a.n_bands = plan.n_bands;
+    a.band_amps = plan.band_amps;
+  }
   if (plan.n_fft != kN) {
     a.max_peaks = plan.prm.max_peaks;
     a.freq_as_offset = plan.freq_as_offset ? 1 : 0;

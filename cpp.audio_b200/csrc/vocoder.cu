@@ -145,9 +145,13 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
   const int64_t row_stride = (Nm / 2 + 1 + 3) & ~3ll;
   const size_t rows_m = static_cast<size_t>(frames_m) * n_streams, rows_c = static_cast<size_t>(frames_c) * n_streams;
   const size_t b_tab = sizeof(int32_t) * (nb + 1) + band_c.size();
+  // FFT lengths >= 8192 (the default window of 0.10 s is 4800 samples -> 8192 points): the band sums come out of the analysis kernel and
+  // the |X|^2 rows never reach HBM (CA_VOC_FUSED_BANDS=0: the two-kernel form, A/B)
+  static const bool fused_env = [] { const char* e = getenv("CA_VOC_FUSED_BANDS"); return !e || atoi(e) != 0; }();
+  const bool fused_bands = fused_env && Nm >= 8192;
   int rc = ensure_scratch(ctx, 0, sizeof(float) * total);
   if (!rc) rc = ensure_scratch(ctx, 1, sizeof(float) * total);
-  if (!rc) rc = ensure_scratch(ctx, 2, std::max<size_t>(16, sizeof(float) * rows_m * row_stride));
+  if (!rc) rc = ensure_scratch(ctx, 2, std::max<size_t>(16, fused_bands ? 16 : sizeof(float) * rows_m * row_stride));
   if (!rc) rc = ensure_scratch(ctx, 3, std::max<size_t>(16, sizeof(float) * rows_m * nb));
   if (!rc) rc = ensure_scratch(ctx, 4, std::max<size_t>(16, sizeof(float) * rows_c * Nc));
   if (!rc) rc = ensure_scratch(ctx, 5, std::max<size_t>(16, sizeof(float2) * rows_c * (Nc / 2 + 1)));
@@ -194,7 +198,14 @@ int vocoder_host(ca_ctx* ctx, const ca_vocoder_params* prm, const float* h_modul
     const size_t c0 = static_cast<size_t>(a0) * frames_c, nc = static_cast<size_t>(ns) * frames_c;
     cudaMemcpyAsync(d_xm + x0, h_modulator + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
     cudaMemcpyAsync(d_xc + x0, h_carrier + x0, sizeof(float) * nx, cudaMemcpyHostToDevice, sg);
-    if (nm) {  // modulator: |X|^2 of every frame, then the band amplitudes
+    if (nm && fused_bands) {  // modulator: the analysis kernel sums the bands of every frame from its shared-memory spectrum
+      ctx->plan_voc.band_begin = d_band_begin;
+      ctx->plan_voc.n_bands = nb;
+      ctx->plan_voc.band_amps = d_amps + m0 * nb;
+      rc = stft_analyze(ctx, ctx->plan_voc, d_xm + x0, n_samples, ns, n_samples, nullptr, 0, nullptr, nullptr, nullptr, nullptr, sg);
+      ctx->plan_voc.band_amps = nullptr;
+      if (rc) break;
+    } else if (nm) {  // modulator: |X|^2 of every frame, then the band amplitudes
       rc = stft_analyze(ctx, ctx->plan_voc, d_xm + x0, n_samples, ns, n_samples, d_sq + m0 * row_stride, row_stride, nullptr, nullptr, nullptr, nullptr, sg);
       if (rc) break;
       band_amps_kernel<<<static_cast<unsigned>((nm + 3) / 4), 128, 0, sg>>>(d_sq + m0 * row_stride, row_stride, static_cast<int64_t>(nm),

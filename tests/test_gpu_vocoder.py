@@ -58,3 +58,29 @@ def test_edge_cases(pkg, ctx):
         pkg.vocoder(ctx, mod, car, stride_seconds=0.001)      # carrier FFT below 512 points
     with pytest.raises(Exception):
         pkg.vocoder(ctx, mod, car, count_bands=51)
+
+
+def test_band_sums_inside_the_analysis_kernel_equal_the_two_kernel_form():
+    """CA_VOC_FUSED_BANDS=0 (|X|^2 rows through HBM + band_amps_kernel) and the default (band sums inside the analysis kernel at
+    modulator FFT lengths >= 8192) give the same audio; the switch is read once per process, so each form runs in its own interpreter."""
+    import os, subprocess, sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import __graft_entry__ as g\n"
+        "pkg = g.load_package(); ctx = pkg.Context(0)\n"
+        "import cpp_audio_b200.workloads as wl\n"
+        "mod = wl.tiled_streams(3, 2.0); car = np.random.default_rng(7).uniform(-0.5, 0.5, mod.shape).astype(np.float32)\n"
+        "out = pkg.vocoder(ctx, mod, car)\n"
+        "np.save(sys.argv[1], np.asarray(out))\n")
+    outs = []
+    for mode in ("1", "0"):
+        path = f"/tmp/voc_fused_{mode}_{os.getpid()}.npy"
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, CA_VOC_FUSED_BANDS=mode), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+        os.remove(path)
+    assert outs[0].shape == outs[1].shape and np.abs(outs[0]).max() > 1e-3
+    assert np.abs(outs[0] - outs[1]).max() < 1e-6
