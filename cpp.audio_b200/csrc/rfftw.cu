@@ -606,10 +606,9 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t mbar, uint32_t parity)
       "r"(parity)
       : "memory");
 }
-template <int A_, int B_, int R1_, int C_, bool ZT_ = true, bool ASYNC_ = false>
+template <int A_, int B_, int R1_, int C_, bool ASYNC_ = false>
 struct Cluster2Cfg {
   static constexpr bool ASYNC = ASYNC_;  // rows delivered by st.async counted on the owner's mbarrier, or by plain stores + a cluster barrier
-  static constexpr bool ZT = ZT_;  // transformed rows stored transposed (one more CTA barrier, no bank conflicts) or in place
   static constexpr int A = A_, B = B_, R1 = R1_, C = C_;
   static constexpr int P = A * B, Q = 32 * R1, M = P * Q;
   static constexpr int G = P / (2 * C);        // adjacent rows per CTA (and as many mirrored ones)
@@ -617,21 +616,26 @@ struct Cluster2Cfg {
   static constexpr int CWC = Q / C;            // columns per CTA (16 or 32: CWC*8-byte runs in HBM)
   static constexpr int SUB = 32 / CWC;         // row groups per warp in the column phase
   static constexpr int WARPS = 2 * G / FPW, T = 32 * WARPS, QT = WARPS * SUB;
-  // row stride while the rows are transformed (the warp's exchange layout fits in its rows); in-place form: G rows x 16/G
-  // consecutive k2 of the untangling loads cover the sixteen 8-byte banks once (the last row pass then stores with 2-4-way conflicts)
-  static constexpr int RS = ZT ? Q + 8 : Q + 16 + (G >= 16 ? 1 : 16 / G);
-  // the transformed rows are stored TRANSPOSED, Zt[k2][slot], KST apart: a half-warp's (R1 columns x 16/R1 rows) of the last
-  // row pass and the (G rows x 16/G values of k2) of the untangling loads both cover the sixteen 8-byte banks once
-  static constexpr int KST = 2 * G + 16 / R1;
-  static constexpr int kStore = (!ZT || RS * 2 * G > Q * KST) ? RS * 2 * G : Q * KST;
+  // Row storage [2G][RS], RS a multiple of 16 (the warp's exchange layout fits in its rows). The transformed rows stay in place with
+  // the 16-point groups of row slot s rotated by rho(s), so that the last row pass (16/R1 slots x R1 columns per half-warp) and the
+  // untangling loads (G slots x 16/G values of k2) both touch each of the sixteen 8-byte banks once: R1 = 8, G = 8:
+  // rho = 2*((s >> 1) + 4*(s & 1)); R1 = 4, G = 16: rho = 4*(s & 3) + ((s >> 2) & 3). Slots 0 and G (the self-paired rows of
+  // CTA 0) keep rho = 0. (Measured against it, profiles/fft_cluster_sweep_r02.txt: the rows stored transposed behind one more CTA
+  // barrier, and in place without the rotation, i.e. with 2-4-way conflicts on the last store: 1-3 % slower.)
+  static constexpr int RS = Q + 16;
+  static __device__ __forceinline__ int rho(int s) {
+    if constexpr (R1 == 8) return 2 * (((s & 7) >> 1) + 4 * (s & 1));
+    else return 4 * (s & 3) + ((s >> 2) & 3);
+  }
   using W = WarpFftCfg<R1>;
-  static constexpr size_t smem = 16 + sizeof(float4) * W::kRows * 32 + sizeof(c2) * kStore;  // mbarrier, row tables, rows
+  static constexpr size_t smem = 16 + sizeof(float4) * W::kRows * 32 + sizeof(c2) * RS * 2 * G;  // mbarrier, row tables, rows
   static_assert(CWC == 32 || CWC == 16, "a CTA takes 16 or 32 columns");
-  static_assert(G == 32 || G == 16 || G == 8, "untangling lane maps");
+  static_assert((G == 8 && R1 == 8) || (G == 16 && R1 == 4), "bank rotation of the row storage");
   static_assert(FPW * RS >= FPW * (R1 / 2) * kXStride && RS * 2 * G >= P * CWC, "exchange layouts fit in the row storage");
   static_assert(A % QT == 0 && B % QT == 0 && (A / QT) * B == 32 && (FPW * RS) % 2 == 0, "32 points per thread");
 };
 
+// row kA of the frame -> (CTA of the cluster, row slot)
 template <typename Cf>
 __device__ __forceinline__ void cluster2_row_dest(int kA, uint32_t& rank, int& slot) {
   constexpr int P = Cf::P, G = Cf::G;
@@ -649,20 +653,22 @@ __device__ __forceinline__ void cluster2_row_dest(int kA, uint32_t& rank, int& s
 }
 
 template <typename Cf, int I>
-__device__ __forceinline__ void cluster2_untangle(const c2* __restrict__ rows, float2* __restrict__ o, const TwP& wpb, int kA, int i, int k2_0) {
-  constexpr int P = Cf::P, Q = Cf::Q, M = Cf::M, G = Cf::G, KS = Cf::T / G;
-  constexpr int SK = Cf::ZT ? Cf::KST : 1, SR = Cf::ZT ? 1 : Cf::RS;  // strides of k2 and of the row slot
+__device__ __forceinline__ void cluster2_untangle(const c2* __restrict__ rows, float2* __restrict__ o, const TwP& wpb, int kA, int i, int k2_0,
+                                                  int zk_sw, int zm_sw) {
+  constexpr int P = Cf::P, Q = Cf::Q, M = Cf::M, G = Cf::G, RS = Cf::RS, KS = Cf::T / G;
+  static_assert(KS == 16 || KS == 8, "k2_0 + (KS*I & 15) stays inside a 16-point group");
   const int k2 = k2_0 + KS * I;
   c2 zk, zm;
   int64_t k;
-  if (kA == 0) {  // M - k = P*(Q - k2): the same row
+  if (kA == 0) {  // M - k = P*(Q - k2): the same row (slot 0, not rotated)
     if (k2 > Q / 2) return;
-    zk = rows[k2 * SK];
-    zm = rows[((Q - k2) & (Q - 1)) * SK];
+    zk = rows[k2];
+    zm = rows[(Q - k2) & (Q - 1)];
     k = static_cast<int64_t>(P) * k2;
-  } else {        // M - k = (P - kA) + P*(Q - 1 - k2)
-    zk = rows[k2 * SK + i * SR];
-    zm = rows[(Q - 1 - k2) * SK + (G + i) * SR];
+  } else {        // M - k = (P - kA) + P*(Q - 1 - k2); k2 and Q-1-k2 inside their rotated groups: zk_sw = k2_0 + rho, zm_sw = 15 - k2_0 + rho
+    constexpr int g0 = (KS * I) & ~15, w0 = (KS * I) & 15;
+    zk = rows[i * RS + g0 + ((zk_sw + w0) & 15)];
+    zm = rows[(G + i) * RS + Q - 16 - g0 + ((zm_sw - w0) & 15)];
     k = kA + static_cast<int64_t>(P) * k2;
   }
   const c2 E = add2(zk, cconj(zm));
@@ -673,9 +679,9 @@ __device__ __forceinline__ void cluster2_untangle(const c2* __restrict__ rows, f
   o[M - k] = upk(cconj(fma2(bc(0.5f), E, cneg(Tt))));
 }
 template <typename Cf, int... I>
-__device__ __forceinline__ void cluster2_untangle_all(const c2* rows, float2* o, const TwP& wpb, int kA, int i, int k2_0,
+__device__ __forceinline__ void cluster2_untangle_all(const c2* rows, float2* o, const TwP& wpb, int kA, int i, int k2_0, int zk_sw, int zm_sw,
                                                       std::integer_sequence<int, I...>) {
-  (cluster2_untangle<Cf, I>(rows, o, wpb, kA, i, k2_0), ...);
+  (cluster2_untangle<Cf, I>(rows, o, wpb, kA, i, k2_0, zk_sw, zm_sw), ...);
 }
 
 template <typename Cf>
@@ -685,7 +691,7 @@ __global__ void __launch_bounds__(Cf::T, Cf::T == 128 ? 5 : (Cf::T == 256 ? 3 : 
                 QT = Cf::QT, RS = Cf::RS, NI1 = B / QT, NI2 = A / QT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tab4 = reinterpret_cast<float4*>(smem_raw + 16);    // [W::kRows][32] row-transform twiddles
-  c2* rows = reinterpret_cast<c2*>(tab4 + W::kRows * 32);     // the column exchange u[A][B][32], then rows [2G][RS], then Zt[Q][KST]
+  c2* rows = reinterpret_cast<c2*>(tab4 + W::kRows * 32);     // the column exchange u[A][B][CWC], then the rows [2G][RS]
   constexpr int CWC = Cf::CWC;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int q = warp * Cf::SUB + lane / CWC, cl = lane % CWC;  // column phase: row group and column of the slab
@@ -813,42 +819,31 @@ __global__ void __launch_bounds__(Cf::T, Cf::T == 128 ? 5 : (Cf::T == 256 ? 3 : 
       for (int n2 = 0; n2 < 32; ++n2) Acol[bitrev(n2, 5)] = xb[(col >> 1) * kXStride + 2 * n2 + (col & 1)];
     }
     DitP<32, 32, 0>::run(Acol);
-    if constexpr (Cf::ZT) {
-      __syncthreads();  // every warp has read its exchange buffer: the storage is rewritten as Zt[k2][slot]
-      c2* Z = rows + warp * FPW + fr;
+    __syncwarp();
+    c2* Z = buf + fr * RS;
+    const int cr = col + Cf::rho(warp * FPW + fr);  // position col + R1*k2 inside its rotated 16-point group
 #pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) Z[(col + R1 * k2) * Cf::KST] = Acol[k2];  // Z[kA + P*k2]
-    } else {
-      __syncwarp();
-      c2* Z = buf + fr * RS;
-#pragma unroll
-      for (int k2 = 0; k2 < 32; ++k2) Z[col + R1 * k2] = Acol[k2];
-    }
+    for (int k2 = 0; k2 < 32; ++k2) Z[((R1 * k2) & ~15) + ((cr + ((R1 * k2) & 15)) & 15)] = Acol[k2];  // Z[kA + P*k2]
   }
   __syncthreads();
   // ---- untangle: consecutive threads take consecutive kA; k2 = k2_0 + (T/G)*I ----
   float2* o = out + frame * (M + 1);
   {
-    const int i = t & (G - 1);
-    int k2_0 = t / G;
-    if constexpr (G == 8 && Cf::ZT) {  // a half-warp takes k2 and k2 + R1/2 (banks 8 apart), see KST
-      const int j = (t >> 3) & 3, w = t >> 5;
-      k2_0 = (j & 1) * (R1 / 2) + (j >> 1) + (R1 == 8 ? 2 * (w & 1) + 8 * (w >> 1) : 4 * w);
-    }
+    const int i = t & (G - 1), k2_0 = t / G;
     const int kA = static_cast<int>(rank) * G + i;
     float sn, cs;
     sincospif(static_cast<float>(kA + P * k2_0) / M, &sn, &cs);  // W_N^(kA + P*k2_0) = (cs, -sn)
     const TwP wpb{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};
-    cluster2_untangle_all<Cf>(rows, o, wpb, kA, i, k2_0, std::make_integer_sequence<int, Q * G / T>{});
+    const int rho = Cf::rho(i);
+    cluster2_untangle_all<Cf>(rows, o, wpb, kA, i, k2_0, k2_0 + rho, 15 - k2_0 + rho, std::make_integer_sequence<int, Q * G / T>{});
   }
-  if (rank == 0) {  // kA = P/2 (slot G): M - k = P/2 + P*(Q - 1 - k2)
-    constexpr int SK = Cf::ZT ? Cf::KST : 1, SR = Cf::ZT ? 1 : Cf::RS;
-    const c2* rs = rows + G * SR;
+  if (rank == 0) {  // kA = P/2 (slot G, not rotated): M - k = P/2 + P*(Q - 1 - k2)
+    const c2* rs = rows + G * RS;
     for (int k2 = t; k2 < Q / 2; k2 += T) {
       float sn, cs;
       sincospif(static_cast<float>(P / 2 + P * k2) / M, &sn, &cs);
       const TwP wp{-0.5f * sn, pk(0.5f * cs, -0.5f * cs)};
-      const c2 zk = rs[k2 * SK], zm = rs[(Q - 1 - k2) * SK];
+      const c2 zk = rs[k2], zm = rs[Q - 1 - k2];
       const c2 E = add2(zk, cconj(zm));
       const c2 Tt = cmul_tw(csub(zk, cconj(zm)), wp);
       const int64_t k = P / 2 + static_cast<int64_t>(P) * k2;
@@ -1610,16 +1605,16 @@ int rfft_warp(ca_ctx* ctx, const float* d_in, int n_fft, int64_t batch, float* d
     case 8192: return launch_cta<4>(ctx, d_in, batch, d_out, stream);
     case 16384: return launch_cta<8>(ctx, d_in, batch, d_out, stream);
     case 32768:
-      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, false>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 4, 4, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 4, 4, true>>(ctx, d_in, batch, d_out, stream);
       return launch_cta<16>(ctx, d_in, batch, d_out, stream);
     case 1 << 16:
-      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, false>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 8, 8, 8, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 8, 8, 8, true>>(ctx, d_in, batch, d_out, stream);
       return big2_variant<4, 8>(ctx, d_in, batch, d_out, stream);
     case 1 << 17:
-      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, true>>(ctx, d_in, batch, d_out, stream);
-      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false, false>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 1 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, true>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, true>>(ctx, d_in, batch, d_out, stream);
+      if (cl == 2 && cluster2_available<Cluster2Cfg<16, 16, 8, 16, false>>(ctx)) return launch_cluster2<Cluster2Cfg<16, 16, 8, 16, false>>(ctx, d_in, batch, d_out, stream);
       return big2_variant<8, 8>(ctx, d_in, batch, d_out, stream);
     case 1 << 18: return big2_variant<8, 16>(ctx, d_in, batch, d_out, stream);
     case 1 << 19: return big2_variant<16, 16>(ctx, d_in, batch, d_out, stream);
