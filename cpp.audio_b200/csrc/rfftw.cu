@@ -629,6 +629,7 @@ struct Cluster2Cfg {
   }
   using W = WarpFftCfg<R1>;
   static constexpr size_t smem = 16 + sizeof(float4) * W::kRows * 32 + sizeof(c2) * RS * 2 * G;  // mbarrier, row tables, rows
+  static constexpr int kMinCtas = 5;  // 96 registers; six CTAs per SM (80 registers, 80-200 bytes of spills) measured 15 % slower
   static_assert(CWC == 32 || CWC == 16, "a CTA takes 16 or 32 columns");
   static_assert((G == 8 && R1 == 8) || (G == 16 && R1 == 4), "bank rotation of the row storage");
   static_assert(FPW * RS >= FPW * (R1 / 2) * kXStride && RS * 2 * G >= P * CWC, "exchange layouts fit in the row storage");
@@ -685,7 +686,7 @@ __device__ __forceinline__ void cluster2_untangle_all(const c2* rows, float2* o,
 }
 
 template <typename Cf>
-__global__ void __launch_bounds__(Cf::T, Cf::T == 128 ? 5 : (Cf::T == 256 ? 3 : 2)) rfft_cluster2_kernel(const float* __restrict__ in, float2* __restrict__ out) {
+__global__ void __launch_bounds__(Cf::T, Cf::kMinCtas) rfft_cluster2_kernel(const float* __restrict__ in, float2* __restrict__ out) {
   using W = typename Cf::W;
   constexpr int A = Cf::A, B = Cf::B, R1 = Cf::R1, C = Cf::C, P = Cf::P, Q = Cf::Q, M = Cf::M, G = Cf::G, FPW = Cf::FPW, T = Cf::T,
                 QT = Cf::QT, RS = Cf::RS, NI1 = B / QT, NI2 = A / QT;
