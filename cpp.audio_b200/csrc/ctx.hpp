@@ -94,6 +94,7 @@ struct StftArgs {
   const int32_t* band_begin;  // internal (vocoder): see StftPlan
   int32_t n_bands;
   float* band_amps;
+  int32_t step_streams, step_frames;  // stft4096p_kernel: its grid stride (frames) split as streams * frames_per_stream + frames
   long long* dbg;          // CA_STFT_TIMELINE builds: per-phase clock64 stamps of a few warps
 };
 

@@ -35,13 +35,23 @@ namespace {
 constexpr int kN = 4096;         // real FFT length
 constexpr int kM = 2048;         // complex FFT length
 constexpr int kBins = kM + 1;
-// transpose buffer of a warp: element (k1, n2) at (k1 >> 1)*kExchStride + 2*n2 + (k1 & 1), in complex units. A lane
-// stores two consecutive k1 with one 128-bit store; the readers (one column k1 per lane, consecutive columns in
-// consecutive lanes) are conflict-free because kExchStride = 2 (mod 16).
+// transpose buffer of a warp, 64 x 32 complex values in 32 * kExchStride slots.
+// Default: element (k1, n2) at (k1 >> 1)*kExchStride + 2*n2 + (k1 & 1); a lane stores two consecutive k1 with one 128-bit
+// store, the readers (one column k1 per lane, consecutive columns in consecutive lanes) are conflict-free because
+// kExchStride = 2 (mod 16). ptxas gathers each register quad of a 128-bit store with MOVs (about 100 per frame).
+// CA_STFT_EXCH64 (A/B): element (k1, n2) at k1*33 + n2 with 64-bit stores: no MOVs, 32 more store instructions per frame,
+// the same number of shared-memory wavefronts; measured 1 % slower (211.6 against 213.6 M frames/s): the load/store unit's
+// instruction queue weighs more than the ALU's.
 constexpr int kExchStride = 66;
 constexpr int kExchFloat2 = 32 * kExchStride;
 constexpr int kWinStride = 66;  // window table: 64 pairs per lane (+2 pad), the 32 even-n1 pairs first, then the odd ones
+#ifdef CA_STFT_EXCH64
+constexpr bool kExch128 = false;
+__device__ __forceinline__ int exch_idx(int k1, int n2) { return k1 * (kExchStride / 2) + n2; }
+#else
+constexpr bool kExch128 = true;
 __device__ __forceinline__ int exch_idx(int k1, int n2) { return (k1 >> 1) * kExchStride + 2 * n2 + (k1 & 1); }
+#endif
 
 #ifdef CA_STFT_TIMELINE
 #define CA_STAMP(i)                                                                                        \
@@ -156,10 +166,15 @@ __device__ __forceinline__ void tw_row_p(c2 (&v)[64], const TwP& w, std::integer
 }
 template <int A>
 __device__ __forceinline__ void tw_store8_p(const c2 (&v)[64], c2* exch, int lane) {
-  // 128-bit stores of (k1, k1+1) pairs (column 0 is stored but never read back)
+  // (column 0 is stored but never read back)
+  if constexpr (kExch128) {
 #pragma unroll
-  for (int b = 0; b < 8; b += 2)
-    *reinterpret_cast<ulonglong2*>(exch + ((8 * A + b) >> 1) * kExchStride + 2 * lane) = make_ulonglong2(v[8 * A + b], v[8 * A + b + 1]);
+    for (int b = 0; b < 8; b += 2)
+      *reinterpret_cast<ulonglong2*>(exch + ((8 * A + b) >> 1) * kExchStride + 2 * lane) = make_ulonglong2(v[8 * A + b], v[8 * A + b + 1]);
+  } else {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) exch[exch_idx(8 * A + b, lane)] = v[8 * A + b];
+  }
 }
 template <int R>
 __device__ __forceinline__ void tw_chain_p(c2 (&v)[64], const float4* __restrict__ tab4, c2* exch, int lane, const TwP& w) {
@@ -211,22 +226,41 @@ __device__ __forceinline__ void post_all_p(const c2 (&A)[32], const c2 (&B)[32],
 // No fence.proxy.async: the last generic-proxy accesses to the staging area are the transpose loads, which returned the
 // values of the stores before them, and every lane is past them (__syncwarp in the caller).
 __device__ __forceinline__ void frame_stage_even_p(c2* __restrict__ stage, const CUtensorMap* map, const StftArgs& p,
-                                                   const int64_t f, const int lane, uint64_t* bar) {
+                                                   const int stream, const int fr, const int lane, uint64_t* bar) {
   if (lane == 0) {
-    const int fps = static_cast<int>(p.frames_per_stream);
-    const int stream = static_cast<int>(f / fps);
-    const int fr = static_cast<int>(f - static_cast<int64_t>(stream) * fps);
     mbar_expect_tx(bar, 32 * 256);
     tma_load_3d(stage, map, 0, fr * (p.hop >> 7), stream, bar);
   }
 }
 
+// (stream, frame in stream) of a warp's current frame, advanced by the grid stride without a division per frame (the 64-bit
+// divide is a ~75-instruction subroutine, and it used to run twice per frame: once for the sample pointer, once for the copy)
+struct FramePos {
+  int stream, fr;  // position of the warp's frame
+  __device__ __forceinline__ FramePos(const int64_t f, const int fps) {
+    stream = static_cast<int>(f / fps);
+    fr = static_cast<int>(f - static_cast<int64_t>(stream) * fps);
+  }
+  // grid stride = p.step_streams streams + p.step_frames frames (split on the host)
+  __device__ __forceinline__ void advance(const StftArgs& p, const int fps) {
+    stream += p.step_streams;
+    fr += p.step_frames;
+    if (fr >= fps) {
+      fr -= fps;
+      ++stream;
+    }
+  }
+  __device__ __forceinline__ const float* samples(const StftArgs& p) const {
+    return p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
+  }
+};
+
 // windowed spectrum of the frame held (bit-reversed over n1, already windowed) in v[]: stage-1 FFT, transpose, stage-2
 // FFTs, untangling, |X|^2 to HBM and to the warp's shared buffer
 __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p, const float4* __restrict__ tab4,
                                                  const float2* __restrict__ tab2, c2* __restrict__ exch, const int lane,
-                                                 const int64_t f, const CUtensorMap* map, const int64_t f_next,
-                                                 uint64_t* bar, const int dbg_frame = 0) {
+                                                 const int64_t f, const CUtensorMap* map, const bool stage_next,
+                                                 const FramePos& next, uint64_t* bar, const int dbg_frame = 0) {
   float* sq = reinterpret_cast<float*>(exch);
   const int colA = lane ? lane : 32;
   const int colB = lane ? 64 - lane : 32;
@@ -247,7 +281,7 @@ __device__ __forceinline__ void frame_spectrum_p(c2 (&v)[64], const StftArgs& p,
   __syncwarp();  // exch is reused as the sqmag buffer below
   // the upper half of the buffer is dead from here to the next transpose: stage the even half of the warp's next frame
   // in it now, so that the copy has the rest of this frame (FFTs, untangling, peak extraction) to land
-  if (f_next >= 0) frame_stage_even_p(exch + kStageOff, map, p, f_next, lane, bar);
+  if (stage_next) frame_stage_even_p(exch + kStageOff, map, p, next.stream, next.fr, lane, bar);
   CA_STAMP(4);
   DitP<32, 32, 0>::run(A);
   DitP<32, 32, 0>::run(B);
@@ -362,19 +396,6 @@ __device__ __forceinline__ void frame_peaks_p(const StftArgs& p, float* __restri
 // PAR selects the half with n1 = PAR (mod 2), i.e. registers v[32*PAR .. 32*PAR+31]: the first five DIT stages stay inside
 // a half, so the even half can be prefetched early (64 registers) and the odd half fetched while the even half is transformed.
 // kFull: window == 4096 (no zero padding, no load predicates); kVec2: 8-byte aligned 64-bit loads are legal.
-__device__ __forceinline__ const float* frame_base_p(const StftArgs& p, const int64_t f) {
-  const int fps = static_cast<int>(p.frames_per_stream);
-  int stream, fr;
-  if (p.total_frames < (1ll << 31)) {
-    const unsigned uf = static_cast<unsigned>(f);
-    stream = static_cast<int>(uf / static_cast<unsigned>(fps));
-    fr = static_cast<int>(uf - static_cast<unsigned>(stream) * static_cast<unsigned>(fps));
-  } else {
-    stream = static_cast<int>(f / fps);
-    fr = static_cast<int>(f - static_cast<int64_t>(stream) * fps);
-  }
-  return p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
-}
 template <int PAR, bool kVec2, bool kFull>
 __device__ __forceinline__ void frame_load_p(c2 (&v)[64], const StftArgs& p, const float* __restrict__ xs, const int lane) {
 #pragma unroll
@@ -440,12 +461,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __gri
   if (f >= p.total_frames) return;
   c2* stage = exch + kStageOff;
   c2 v[64];
-  const float* xs = frame_base_p(p, f);
+  const int fps = static_cast<int>(p.frames_per_stream);
+  FramePos pos(f, fps);
   uint32_t parity = 0;
   int dbg_frame = 0;
-  if (kBulk) frame_stage_even_p(stage, &tmap, p, f, lane, bar);
+  if (kBulk) frame_stage_even_p(stage, &tmap, p, pos.stream, pos.fr, lane, bar);
   for (;;) {
     CA_STAMP(0);
+    const float* xs = pos.samples(p);
     frame_load_p<1, kVec2, kFull>(v, p, xs, lane);  // odd half: lands while the even half is transformed
     if (kBulk) {
       mbar_wait(bar, parity);
@@ -456,23 +479,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) stft4096p_kernel(const __gri
       frame_load_p<0, kVec2, kFull>(v, p, xs, lane);
       frame_window_p<0>(v, win_c, lane);
     }
-    DitP<64, 32, 0>::run(v);
-    frame_window_p<1>(v, win_c, lane);
+    DitP<64, 32, 0>::run(v);  // (ptxas contracts the window multiply into the first butterfly by itself: a hand-fused form
+    frame_window_p<1>(v, win_c, lane);  // compiles to the same instruction mix)
     DitP<64, 32, 32>::run(v);
     __syncwarp();  // every lane has taken its staged samples: the buffer may be overwritten by the transpose
     CA_STAMP(2);
-    const int64_t fn = f + fstep;
-    const bool more = fn < p.total_frames;
-    const float* xs_next = more ? frame_base_p(p, fn) : nullptr;
-    frame_spectrum_p(v, p, tab4, tab2, exch, lane, f, &tmap, (kBulk && more) ? fn : -1, bar, dbg_frame);
-    xs = xs_next;
+    const bool more = f + fstep < p.total_frames;
+    pos.advance(p, fps);  // from here on: the position of the warp's next frame
+    frame_spectrum_p(v, p, tab4, tab2, exch, lane, f, &tmap, kBulk && more, pos, bar, dbg_frame);
     CA_STAMP(7);
     CA_STAMP(8);
     if (p.peak_count) frame_peaks_p(p, reinterpret_cast<float*>(exch), lane, f);
     CA_STAMP(9);
     ++dbg_frame;
     if (!more) break;
-    f = fn;
+    f += fstep;
   }
 }
 
@@ -635,6 +656,8 @@ int stft_analyze(ca_ctx* ctx, const StftPlan& plan, const float* d_x, int64_t n_
   cudaMemset(d_dbg, 0, dbg_n * sizeof(long long));
   a.dbg = d_dbg;
 #endif
+  a.step_streams = static_cast<int32_t>((grid * PW) / frames);
+  a.step_frames = static_cast<int32_t>((grid * PW) % frames);
   kern<<<static_cast<unsigned>(grid), PW * 32, smem, stream>>>(a, tmap);
   CA_CUDA_OK(ctx, cudaGetLastError());
 #ifdef CA_STFT_TIMELINE
