@@ -927,6 +927,11 @@ int launch_cluster2(ca_ctx* ctx, const float* d_in, int64_t batch, float* d_out,
 // window_frames_kernel -> K1 -> sqmag_peaks_kernel.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ const float* frame_ptr(const StftArgs& p, int64_t f) {
+  if (p.total_frames < (1ll << 31)) {  // the usual case: a 32-bit divide (the 64-bit one is a ~75-instruction subroutine)
+    const unsigned uf = static_cast<unsigned>(f), fps = static_cast<unsigned>(p.frames_per_stream);
+    const unsigned stream = uf / fps, fr = uf - stream * fps;
+    return p.x + stream * p.stream_stride + static_cast<int64_t>(fr) * p.hop;
+  }
   const int64_t stream = f / p.frames_per_stream;
   const int64_t fr = f - stream * p.frames_per_stream;
   return p.x + stream * p.stream_stride + fr * p.hop;

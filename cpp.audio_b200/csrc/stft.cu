@@ -200,9 +200,20 @@ __device__ __forceinline__ void post_pair_p(const c2 (&A)[32], const c2 (&B)[32]
   c2 D = csub(zk, cconj(zm));        // Z[k] - conj(Z[M-k])
   if constexpr (K2 != 0) D = cmul_imm<Tw<64, K2>>(D);
   const c2 T = cmul_tw(D, wpb);
+#ifdef CA_STFT_SQ_SCALAR
   const float2 P = upk(add2(E, T)), Q = upk(csub(E, T));
   const float sk = fmaf(P.x, P.x, P.y * P.y);
   const float sm = fmaf(Q.x, Q.x, Q.y * Q.y);
+#else
+  // (P, Q) = E +- T formed component-wise, (P.x, Q.x) and (P.y, Q.y), so that |P|^2 and |Q|^2 come out of two packed
+  // instructions: four packed instructions per bin pair instead of two packed and four scalar ones
+  const float2 e = upk(E), t = upk(T);
+  const c2 pm = pk(1.f, -1.f);
+  const c2 X = fma2(bc(t.x), pm, bc(e.x));
+  const c2 Y = fma2(bc(t.y), pm, bc(e.y));
+  const float2 sq2 = upk(fma2(X, X, mul2(Y, Y)));
+  const float sk = sq2.x, sm = sq2.y;
+#endif
   if (rowA) {
     rowA[64 * K2] = sk;
     rowB[64 * (31 - K2)] = sm;
@@ -341,12 +352,39 @@ __device__ __forceinline__ void frame_peaks_p(const StftArgs& p, float* __restri
   }
   w[65] = sq[base + (lane == 31 ? 67 : 68)];  // first bin of the next block (bin 2048 sits in the very last pad)
   uint32_t mlo = 0, mhi = 0;
+#ifndef CA_STFT_PEAK_COMPARE
+  // the sign bit of max(l, r, thr) - c shifted into the mask: FMNMX3 + FADD + SHF per bin (FSETP + SEL + half a LOP3 for the
+  // compare-and-select form, CA_STFT_PEAK_COMPARE: 2 % slower); c == max gives +0, so the test stays strict. kChains independent
+  // shift chains per mask word keep the dependent SHFs apart.
+#ifndef CA_STFT_PEAK_CHAINS
+#define CA_STFT_PEAK_CHAINS 1
+#endif
+  constexpr int kChains = CA_STFT_PEAK_CHAINS, kLen = 32 / kChains;
+  uint32_t part[2][kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) part[0][c] = part[1][c] = 0;
+#pragma unroll
+  for (int j = kLen - 1; j >= 0; --j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < kChains; ++c) {
+        const int b = 32 * h + kLen * c + j;
+        part[h][c] = __funnelshift_l(__float_as_uint(fmaxf(fmaxf(w[b], w[b + 2]), p.thr_below) - w[b + 1]), part[h][c], 1);
+      }
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) {
+    mlo |= part[0][c] << (kLen * c);
+    mhi |= part[1][c] << (kLen * c);
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 64; ++j) {
     const bool is_peak = w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below);
     if (j < 32) mlo |= is_peak ? (1u << j) : 0u;
     else mhi |= is_peak ? (1u << (j - 32)) : 0u;
   }
+#endif
   uint64_t mask = (static_cast<uint64_t>(mhi) << 32) | mlo;
   const int cnt = __popcll(mask);
   int incl = cnt;
