@@ -961,16 +961,22 @@ __device__ __forceinline__ void peak_interp_store(const StftArgs& p, int64_t out
   p.peak_db[out_base + idx] = kDbPerLog2 * __log2f(sb) - 0.25f * (kDbPerLog2 * num) * pp;
 }
 
-// |X[k]|^2 and |X[M-k]|^2 from Z[k], Z[M-k]; wpb = 0.5 * (-i) * W_N^(k mod stride), imm = W_N^(stride * I)
+// |X[k]|^2 and |X[M-k]|^2 from Z[k], Z[M-k] of a frame whose window carries the 1/2 of the untangling (stft_plan);
+// wpb = (-i) * W_N^(k mod stride), imm = W_N^(stride * I)
 template <typename Imm, bool kHasImm>
 __device__ __forceinline__ void untangle_sq(c2 zk, c2 zm, const TwP& wpb, float& sk, float& sm) {
   const c2 E = add2(zk, cconj(zm));
   c2 D = csub(zk, cconj(zm));
   if constexpr (kHasImm) D = cmul_imm<Imm>(D);
   const c2 T = cmul_tw(D, wpb);
-  const float2 P = upk(fma2(bc(0.5f), E, T)), Q = upk(fma2(bc(0.5f), E, cneg(T)));
-  sk = fmaf(P.x, P.x, P.y * P.y);
-  sm = fmaf(Q.x, Q.x, Q.y * Q.y);
+  // (P, Q) = E +- T formed component-wise so that |P|^2 and |Q|^2 come out of two packed instructions (as post_pair_p in stft.cu)
+  const float2 e = upk(E), t = upk(T);
+  const c2 pm = pk(1.f, -1.f);
+  const c2 X = fma2(bc(t.x), pm, bc(e.x));
+  const c2 Y = fma2(bc(t.y), pm, bc(e.y));
+  const float2 sq2 = upk(fma2(X, X, mul2(Y, Y)));
+  sk = sq2.x;
+  sm = sq2.y;
 }
 
 // ---- one warp per frame: n_fft = 1024 (R1 = 16, two frames per warp), 2048 (R1 = 32) ----
@@ -1022,7 +1028,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft_warp_kernel(const __grid_c
     else {
       float s, c;
       sincospif(static_cast<float>(l) / M, &s, &c);
-      w = make_float2(-0.5f * s, -0.5f * c);  // 0.5 * (-i) * W_N^l
+      w = make_float2(-s, -c);  // (-i) * W_N^l (the window carries the 1/2)
     }
     tab4[i] = make_float4(w.x, w.y, -w.y, w.y);
   }
@@ -1095,7 +1101,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft_warp_kernel(const __grid_c
       warp_untangle_sq_all<R1>(Z, row, sq, wpb, lane, std::make_integer_sequence<int, M / 64>{});
       if (lane == 0) {  // X[M/2] = conj(Z[M/2])
         const float2 z = upk(Z[M / 2]);
-        const float s = fmaf(z.x, z.x, z.y * z.y);
+        const float s = 4.f * fmaf(z.x, z.x, z.y * z.y);  // X[M/2] = conj(Z[M/2]) of the unhalved frame (the window carries a 1/2)
         if (row) row[M / 2] = s;
         sq[((M / 2) / R1) * S::SB + ((M / 2) % R1)] = s;
       }
@@ -1116,8 +1122,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) stft_warp_kernel(const __grid_c
       w[R1 + 1] = sq[base + S::SB];  // first bin of the next block (bin M for the last lane)
       uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < R1; ++j)
-        if (w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below)) mask |= 1u << j;
+      for (int j = R1 - 1; j >= 0; --j)  // sign bit of max(l, r, thr) - c, shifted in (see frame_peaks_p in stft.cu)
+        mask = __funnelshift_l(__float_as_uint(fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below) - w[j + 1]), mask, 1);
       const int cnt = __popc(mask);
       int incl = cnt;
 #pragma unroll
@@ -1201,7 +1207,7 @@ __global__ void __launch_bounds__(32 * M1, 16 / M1 > 4 ? 4 : 16 / M1) stft_cta_k
   {
     float s, c;
     sincospif(static_cast<float>(t) / M, &s, &c);
-    wpb = TwP{-0.5f * s, pk(0.5f * c, -0.5f * c)};
+    wpb = TwP{-s, pk(c, -c)};  // (-i) * W_N^t (the window carries the 1/2)
   }
   for (int64_t frame = blockIdx.x; frame < p.total_frames; frame += gridDim.x) {
     const float* xs = frame_ptr(p, frame);
@@ -1256,7 +1262,7 @@ __global__ void __launch_bounds__(32 * M1, 16 / M1 > 4 ? 4 : 16 / M1) stft_cta_k
     cta_untangle_sq_all<M1>(Ys, rowo, sq, wpb, t, std::make_integer_sequence<int, M / (2 * T)>{});
     if (t == 0) {
       const float2 z = upk(Ys[((M / 2) % M1) * C::kRowC2 + (M / 2) / M1]);
-      const float s = fmaf(z.x, z.x, z.y * z.y);
+      const float s = 4.f * fmaf(z.x, z.x, z.y * z.y);  // X[M/2] = conj(Z[M/2]) of the unhalved frame (the window carries a 1/2)
       if (rowo) rowo[M / 2] = s;
       sq[((M / 2) >> 5) * S::SB + ((M / 2) & 31)] = s;
     }
@@ -1289,8 +1295,8 @@ __global__ void __launch_bounds__(32 * M1, 16 / M1 > 4 ? 4 : 16 / M1) stft_cta_k
       }
       w[33] = sq[base + S::SB];
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (w[j + 1] > fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below)) mask |= 1u << j;
+      for (int j = 31; j >= 0; --j)  // sign bit of max(l, r, thr) - c, shifted in (see frame_peaks_p in stft.cu)
+        mask = __funnelshift_l(__float_as_uint(fmaxf(fmaxf(w[j], w[j + 2]), p.thr_below) - w[j + 1]), mask, 1);
     }
     const int cnt = __popc(mask);
     int incl = cnt;

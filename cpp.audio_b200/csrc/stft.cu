@@ -559,7 +559,7 @@ int stft_plan(ca_ctx* ctx, StftPlan& plan, const ca_stft_params* p) {
     hw[j] = static_cast<double>(v);
     sum += v;
   }
-  const double norm = static_cast<double>(H / sum) * (n_fft == kN ? 0.5 : 1.0) / W;
+  const double norm = static_cast<double>(H / sum) * 0.5 / W;
   std::vector<float> full(n_fft, 0.f);
   for (int n = 0; n < W; ++n) full[n] = static_cast<float>((n < H ? hw[H - 1 - n] : hw[n - H]) * norm);
   plan.planned = false;
