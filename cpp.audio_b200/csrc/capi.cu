@@ -1,4 +1,5 @@
 // capi.cu — the extern "C" layer declared in include/cpp_audio_b200.h: context, argument checks, host-buffer wrappers.
+#include <stdlib.h>
 #include <math.h>
 
 #include <algorithm>
@@ -182,7 +183,13 @@ int ca_stft_analyze_host(ca_ctx* ctx, const float* h_x, int64_t n_samples, int64
   float* d_pd = any_peak ? static_cast<float*>(ctx->d_scratch[4]) : nullptr;
   int32_t* d_pc = any_peak ? static_cast<int32_t*>(ctx->d_scratch[5]) : nullptr;
   cudaStream_t lanes[2] = {ctx->own_stream, ctx->own_stream2};
-  const int64_t target_chunks = 8;
+  // 16 chunks: what the pipeline cannot overlap is the first chunk's copy up and the last chunk's kernel and copy down (with 8
+  // chunks 1.3 of the 7.4 ms of a 32-stream config-2 step; CA_E2E_CHUNKS overrides, A/B)
+  static const int64_t target_chunks = [] {
+    const char* e = getenv("CA_E2E_CHUNKS");
+    const int v = e ? atoi(e) : 16;
+    return static_cast<int64_t>(v > 0 ? v : 16);
+  }();
   int64_t streams_per_chunk = n_streams >= target_chunks ? (n_streams + target_chunks - 1) / target_chunks : 1;
   int64_t ranges_per_stream = n_streams >= target_chunks ? 1 : (target_chunks + n_streams - 1) / n_streams;
   if (ranges_per_stream > frames) ranges_per_stream = frames;
