@@ -530,6 +530,32 @@ def run_ours(args):
                       "are points of config 5 (1 GiB of input each)")
         extra["rfft"] = rf
 
+        # ---- the fused analysis at the reference's own default window: 0.1814 s / stride 0.09 s (source/rt.resynth.lib.cpp:945-946),
+        # at 48 kHz 8708 samples zero padded to 16384 points, hop 4320; same streams, device resident ----
+        dw_window, dw_hop = 8708, 4320
+        an_dw = pkg.SqMagAnalyzer(ctx, dw_window, dw_hop, sample_rate=SR, min_db=MIN_DB, max_peaks=MAX_PEAKS)
+        out_dw = an_dw.allocate(S, n_samples, dev)
+        for _ in range(3):
+            an_dw(x, out_dw)
+        sync_all()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(10):
+            an_dw(x, out_dw)
+        d1.record()
+        sync_all()
+        dms = d0.elapsed_time(d1) / 10
+        dw_frames = S * an_dw.num_frames(n_samples)
+        dw_bytes = dw_frames * (4 * dw_hop + 4 * (an_dw.n_fft // 2 + 1))
+        extra["stft_default_window"] = {
+            "workload": "reference defaults: window 8708 samples (0.1814 s), hop 4320 (0.09 s), 16384-point frames, Gaussian window, |X|^2 + peaks",
+            "kernel": "stft_cta_kernel<8> (one CTA per frame, csrc/rfftw.cu)", "ms": dms, "frames_per_s": dw_frames / (dms * 1e-3),
+            "algorithmic_gbs": dw_bytes / (dms * 1e-3) / 1e9, "frac_hbm": dw_bytes / (dms * 1e-3) / 1e9 / peak_gbs,
+            "note": "per rank; bound by the 16384-point transform (shared-memory wavefronts and latency, DESIGN.md K2 'other FFT lengths'), not by HBM",
+        }
+        del out_dw, an_dw
+        an._plan(an.window)  # the context holds one user plan: back to the headline analysis
+
     # ---- what the host can copy with all ranks at it: the ceiling of the host-buffer paths below ----
     ceiling = None
     if not args.skip_roundtrip:
