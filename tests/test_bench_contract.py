@@ -45,3 +45,18 @@ def test_reference_arm_other_ranks_exit_without_output():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_traffic_constants_follow_the_committed_ncu_summaries():
+    """profiles/traffic.json (the ncu constants bench.py quotes in roofline.traffic / roofline.ncu) is exactly what
+    profiles/make_traffic.py derives from the committed ncu summaries."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    before = open(path).read()
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "make_traffic.py")], capture_output=True, text=True, timeout=120, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        after = open(path).read()
+    finally:
+        with open(path, "w") as f:
+            f.write(before)
+    assert json.loads(after) == json.loads(before)
